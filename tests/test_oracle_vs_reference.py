@@ -1,0 +1,52 @@
+"""Build-container-only check: the oracle restatement reproduces the UNMODIFIED reference bit for
+bit (same torch build, same CPU).  Skipped wherever /root/reference is absent (e.g. the GPU box)."""
+import pytest
+import torch
+
+from ref_loader import cuda0_shim, load_reference, reference_available
+from oracle import p24_oracle as orc
+from p24 import synth
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+
+
+@pytest.mark.parametrize("kind,seed", [("smooth", 11), ("spiky", 12)])
+def test_loss_forward_bit_equal(kind, seed):
+    ref_models, _ = load_reference()
+    out = synth.make_head_outputs(2, 320, 80, seed=seed)
+    lab = synth.make_labels(2, [7, 3], 10, 320, 80, seed=seed, kind=kind)
+    xs, ys, ss = synth.make_grids(320)
+    ref, mine = ref_models.Loss_Function(80), orc.LossOracle(80)
+    for _ in range(2):
+        with cuda0_shim("cpu"):
+            r = ref.forward((xs, ys, ss, out.clone(), []), lab)
+        o = mine.forward((xs, ys, ss, out.clone(), []), lab)
+        for i in range(4):
+            assert torch.equal(r[i], o[i])
+        assert r[4] == o[4] and r[5] == o[5]
+        assert all(torch.equal(a, b) for a, b in zip(r[6], o[6]))
+
+
+def test_pairwise_and_matched_bit_equal():
+    ref_models, ref_utils = load_reference()
+    lab = synth.make_labels(1, 9, 10, 320, 80, seed=5, kind="spiky")[0, :9, 1:]
+    pred = synth.make_head_outputs(1, 320, 80, seed=5)[0, :700, :26]
+    assert torch.equal(ref_utils.bboxes_iou(lab, pred), orc.bboxes_iou(lab, pred))
+    a, _ = ref_models.IOUloss().forward(pred[:9], lab)
+    b, _ = orc.iou_loss_forward(pred[:9], lab)
+    assert torch.equal(a, b)
+    with pytest.raises(IndexError):
+        orc.iou_loss_forward(pred[:, :25], lab)
+    e, d = orc.iou_loss_forward(pred[:0], lab[:0])
+    er, dr = ref_models.IOUloss().forward(pred[:0], lab[:0])
+    assert torch.equal(e, er) and e.shape == (1, 24)
+
+
+def test_postprocess_bit_equal():
+    _, ref_utils = load_reference()
+    p = synth.make_postprocess_input(2, 320, 80, seed=9)
+    for c, n, ag in [(0.25, 0.45, False), (0.01, 0.3, True)]:
+        for i in range(2):
+            r = ref_utils.postprocess(p[i:i + 1].clone(), 80, c, n, ag)[0]
+            o = orc.postprocess(p[i:i + 1].clone(), 80, c, n, ag)[0]
+            assert (r is None) == (o is None) and (r is None or torch.equal(r, o))
