@@ -1,0 +1,133 @@
+// p24_common.cuh — workspace layout, GT record layout and block-level selection primitives shared
+// by the kernels of libp24_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+#include "../../include/p24.h"
+#include "p24_math.cuh"
+
+#define P24_THREADS 256
+#define P24_WARPS (P24_THREADS / 32)
+
+// ---- per-GT record (floats), built once per batch by k_gt_prep --------------------------------
+// [0] cx  [1] cy  [2] class (as float)  [3] rin2  [4] rout2  [5..7] pad
+// [8..31] vertex x  [32..55] vertex y  [56..79] ray length rg
+#define GT_CX 0
+#define GT_CY 1
+#define GT_CLS 2
+#define GT_RIN2 3
+#define GT_ROUT2 4
+#define GT_VX 8
+#define GT_VY 32
+#define GT_RG 56
+#define GT_REC 80
+
+static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct P24Workspace {
+    size_t gt_rec;      // [B, Lmax, GT_REC] float
+    size_t cand_flag;   // [B, A] uint8   candidate mask (fg_mask before matching, losses.py:546)
+    size_t cand_count;  // [B] int
+    size_t vcount;      // [B, Lmax] int  centre-window list length
+    size_t vlist;       // [B, Lmax, VCAP] int  anchor | in_box << 31
+    size_t vcost;       // [B, Lmax, VCAP] float  cost of valid pairs (+inf when not in_box)
+    size_t viou;        // [B, Lmax, VCAP] float  pair value of valid pairs
+    size_t sel_count;   // [B, Lmax] int          anchors actually selected by each GT (== dyn_k in contract)
+    size_t claim_cnt;   // [B, A] int             number of GTs that selected the anchor (bit 30: resolved)
+    size_t best_key;    // [B, A] u64             min over valid pairs of (cost bits << 32 | gt), losses.py:474
+    size_t err_flag;    // [1] int                sticky internal error bits (list overflow)
+    size_t sel_anchor;  // [B, Lmax, TOPK] int    anchors selected by each GT
+    size_t sel_cost;    // [B, Lmax, TOPK] float
+    size_t sel_iou;     // [B, Lmax, TOPK] float
+    size_t partials;    // [LOSS_BLOCKS, 28] double
+    size_t ticket;      // [1] unsigned (last-block-done counter)
+    size_t total;
+};
+
+#define P24_LOSS_BLOCKS 592  // 4 x 148 SMs
+
+static inline P24Workspace p24_layout(int B, int A, int Lmax) {
+    P24Workspace w;
+    size_t off = 0;
+    const size_t BL = (size_t)B * (size_t)Lmax;
+    w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
+    w.cand_flag = off;  off = p24_align(off + (size_t)B * A);
+    w.cand_count = off; off = p24_align(off + (size_t)B * sizeof(int));
+    w.vcount = off;     off = p24_align(off + BL * sizeof(int));
+    w.vlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));
+    w.vcost = off;      off = p24_align(off + BL * P24_VCAP * sizeof(float));
+    w.viou = off;       off = p24_align(off + BL * P24_VCAP * sizeof(float));
+    w.sel_count = off;  off = p24_align(off + BL * sizeof(int));
+    w.claim_cnt = off;  off = p24_align(off + (size_t)B * A * sizeof(int));
+    w.best_key = off;   off = p24_align(off + (size_t)B * A * sizeof(unsigned long long));
+    w.err_flag = off;   off = p24_align(off + sizeof(int));
+    w.sel_anchor = off; off = p24_align(off + BL * P24_TOPK * sizeof(int));
+    w.sel_cost = off;   off = p24_align(off + BL * P24_TOPK * sizeof(float));
+    w.sel_iou = off;    off = p24_align(off + BL * P24_TOPK * sizeof(float));
+    w.partials = off;   off = p24_align(off + (size_t)P24_LOSS_BLOCKS * 28 * sizeof(double));
+    w.ticket = off;     off = p24_align(off + sizeof(unsigned));
+    w.total = off;
+    return w;
+}
+
+#ifdef __CUDACC__
+// ---- (value, index) selection --------------------------------------------------------------
+struct KV {
+    float v;
+    int i;
+};
+
+// larger value wins; ties -> smaller index.  NaN never wins.
+__device__ __forceinline__ bool kv_gt(float v1, int i1, float v2, int i2) {
+    return (v1 > v2) || (v1 == v2 && i1 < i2);
+}
+// smaller value wins; ties -> smaller index.
+__device__ __forceinline__ bool kv_lt(float v1, int i1, float v2, int i2) {
+    return (v1 < v2) || (v1 == v2 && i1 < i2);
+}
+
+template <bool MAX>
+__device__ __forceinline__ KV warp_select(KV x) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, x.v, off);
+        const int i2 = __shfl_xor_sync(0xffffffffu, x.i, off);
+        const bool take = MAX ? kv_gt(v2, i2, x.v, x.i) : kv_lt(v2, i2, x.v, x.i);
+        if (take) {
+            x.v = v2;
+            x.i = i2;
+        }
+    }
+    return x;
+}
+
+// Block-wide arg-select over per-thread candidates; every thread gets the winner.
+// s_red: P24_WARPS entries of shared scratch.  Contains two __syncthreads().
+template <bool MAX>
+__device__ __forceinline__ KV block_select(KV x, KV* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x = warp_select<MAX>(x);
+    __syncthreads();  // protect s_red reuse from a previous call
+    if (lane == 0) s_red[warp] = x;
+    __syncthreads();
+    KV y = s_red[lane < P24_WARPS ? lane : 0];
+    y = warp_select<MAX>(y);
+    return y;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+#define P24_NEG_INF (-INFINITY)
+#define P24_POS_INF (INFINITY)
+#endif  // __CUDACC__

@@ -1,0 +1,148 @@
+// p24_math.cuh — scalar fp32 arithmetic of the YOLOX-24p loss / SimOTA path.
+//
+// Every expression here follows the operation order of SURVEY.md Appendix A, i.e. the order in
+// which the reference's eager PyTorch code rounds (one rounding per op, no FMA contraction).
+// The translation unit that includes this header for the device MUST be compiled with
+// `-fmad=false` (and the default -prec-div=true -prec-sqrt=true): discrete SimOTA decisions hang
+// on fp32 thresholds, so the association order is part of the contract.
+//
+// The functions are `__host__ __device__` so that a host-only build (tests/tools/hostmath.cpp,
+// test infrastructure) can check the formulas against the oracle on a CPU-only machine; the
+// product never calls the host versions.
+//
+// Reference lines (paths relative to /root/reference/yolox_24p):
+//   ray term            models/losses.py:36-72,118-151  ==  utils/boxes.py:127-157,201-235
+//   polygon angle sum   models/losses.py:566-588
+//   centre window       models/losses.py:523-542
+//   class cost          models/losses.py:399-416
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define P24_HD __host__ __device__ __forceinline__
+#else
+#define P24_HD inline
+#endif
+
+#define P24_RAYS 24
+
+// fp32 constants exactly as torch materialises them
+#define P24_PI 3.1415927410125732f        // torch.tensor(np.pi)
+#define P24_RAD2DEG 57.295780181884766f   // torch.rad2deg multiplier
+#define P24_PENALTY 100000.0f
+
+// ---------------------------------------------------------------------------------------------
+// One ray of the concentric-circle GIoU: returns loss24 = 1 - giou.  `inter_out` (optional)
+// receives the intersection area that IOUloss.circle_inter returns.
+// ---------------------------------------------------------------------------------------------
+P24_HD float p24_ray_loss(float rg, float rp, float d, float* inter_out = nullptr) {
+    const float rmin = fminf(rg, rp);
+    const float rmax = fmaxf(rg, rp);
+    const float rmin2 = rmin * rmin;
+    const float rmax2 = rmax * rmax;
+    const bool nested = fabsf(rg - rp) >= d;   // losses.py:60  (written first)
+    const bool apart = d >= rg + rp;           // losses.py:67  (written second: overrides)
+    float inter;
+    if (apart) {
+        inter = 0.0f;
+    } else if (nested) {
+        inter = P24_PI * rmin2;
+    } else {
+        const float d2 = d * d;
+        float ac_min = ((rmin2 + d2) - rmax2) / (((2.0f * rmin) * d) + 1e-8f);
+        float ac_max = ((rmax2 + d2) - rmin2) / (((2.0f * rmax) * d) + 1e-8f);
+        ac_min = fminf(fmaxf(ac_min, -0.99f), 0.99f);
+        ac_max = fminf(fmaxf(ac_max, -0.99f), 0.99f);
+        const float ang_min = acosf(ac_min);
+        const float ang_max = acosf(ac_max);
+        inter = ((ang_min * rmin2) + (ang_max * rmax2)) - ((rmin * d) * sinf(ang_min));
+    }
+    if (inter_out) *inter_out = inter;
+    const float ag = P24_PI * (rg * rg);
+    const float ap = P24_PI * (rp * rp);
+    const float uni = (ag + ap) - inter;
+    const float iou = inter / (uni + 1e-6f);
+    const float cl = nested ? rmax : (((rg + rp) + d) / 2.0f);
+    const float cs = P24_PI * (cl * cl);
+    const float giou = iou - ((cs - uni) / cs);
+    return 1.0f - giou;
+}
+
+// centre distance, losses.py:36 / boxes.py:127
+P24_HD float p24_centre_dist(float gcx, float gcy, float pcx, float pcy) {
+    const float dx = gcx - pcx;
+    const float dy = gcy - pcy;
+    return sqrtf((dx * dx) + (dy * dy));
+}
+
+// GT ray length: torch.norm over the 2-vector (losses.py:108, boxes.py:197).  ATen's CUDA norm
+// reduction accumulates `acc + x*x`, which nvcc contracts to an FMA; the same form is used here.
+P24_HD float p24_gt_radius(float vx, float vy) {
+    return sqrtf(fmaf(vy, vy, vx * vx));
+}
+
+// pairwise "iou" of SimOTA: mean ray loss / 2 (boxes.py:238-241).  rp points at 24 radii.
+P24_HD float p24_pair_value(const float* rg, const float* rp, float d) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < P24_RAYS; ++k) s = s + p24_ray_loss(rg[k], rp[k], d);
+    return (s / 24.0f) / 2.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// polygon "inside" test: total unsigned angular variation >= 350 degrees (losses.py:583-588)
+// vx, vy: 24 vertices.  Returns the angle sum in degrees.
+// ---------------------------------------------------------------------------------------------
+P24_HD float p24_angle_sum(const float* vx, const float* vy, float xc, float yc) {
+    float acc = 0.0f;
+    float sx = vx[0] - xc, sy = vy[0] - yc;
+    const float fx = sx, fy = sy;
+#pragma unroll
+    for (int k = 0; k < P24_RAYS; ++k) {
+        const float ex = (k == P24_RAYS - 1) ? fx : (vx[k + 1] - xc);
+        const float ey = (k == P24_RAYS - 1) ? fy : (vy[k + 1] - yc);
+        const float cross = (sx * ey) - (ex * sy);
+        const float dot = (sx * ex) + (sy * ey);
+        acc = acc + (atan2f(fabsf(cross), dot) * P24_RAD2DEG);
+        sx = ex;
+        sy = ey;
+    }
+    return acc;
+}
+
+// centre window, strict (losses.py:523-542)
+P24_HD bool p24_in_centre(float gcx, float gcy, float xc, float yc, float stride) {
+    const float r = 2.5f * stride;
+    const float cl = xc - (gcx - r);
+    const float cr = (gcx + r) - xc;
+    const float ct = yc - (gcy - r);
+    const float cb = (gcy + r) - yc;
+    return fminf(fminf(cl, ct), fminf(cr, cb)) > 0.0f;
+}
+
+// anchor centre (losses.py:506-516)
+P24_HD float p24_anchor_centre(float shift, float stride) {
+    return (shift * stride) + (0.5f * stride);
+}
+
+// ---------------------------------------------------------------------------------------------
+// class cost terms (losses.py:409-416): p = sqrt(sigmoid(cls) * sigmoid(obj)),
+// BCE(p, y) = -(y * max(log p, -100) + (1 - y) * max(log1p(-p), -100))
+// ---------------------------------------------------------------------------------------------
+P24_HD float p24_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+P24_HD float p24_joint_prob(float cls_logit, float obj_sig) { return sqrtf(p24_sigmoid(cls_logit) * obj_sig); }
+
+P24_HD float p24_bce_neg(float p) { return -fmaxf(log1pf(-p), -100.0f); }  // target 0
+P24_HD float p24_bce_pos(float p) { return -fmaxf(logf(p), -100.0f); }     // target 1
+
+// full SimOTA cost (losses.py:420-424)
+P24_HD float p24_cost(float cls_cost, float pair_value, bool valid) {
+    const float iou_cost = -logf(pair_value + 1e-8f);
+    return (cls_cost + (3.0f * iou_cost)) + (valid ? 0.0f : P24_PENALTY);
+}
+
+// BCEWithLogits (losses.py:294-302): max(x,0) - x*t + log1p(exp(-|x|))  (ATen's stable form)
+P24_HD float p24_bce_logits(float x, float t) {
+    return ((1.0f - t) * x) + (fmaxf(-x, 0.0f) + log1pf(expf(-fabsf(x))));
+}
