@@ -12,13 +12,15 @@
 #define P24_WARPS (P24_THREADS / 32)
 
 // ---- per-GT record (floats), built once per batch by k_gt_prep --------------------------------
-// [0] cx  [1] cy  [2] class (as float)  [3] rin2  [4] rout2  [5..7] pad
+// [0] cx  [1] cy  [2] class (as float)  [3] rin2  [4] rrej2  [5] rgmax  [6] rgmin  [7] pad
 // [8..31] vertex x  [32..55] vertex y  [56..79] ray length rg
 #define GT_CX 0
 #define GT_CY 1
 #define GT_CLS 2
-#define GT_RIN2 3
-#define GT_ROUT2 4
+#define GT_RIN2 3    // squared radius of a disc around (cx, cy) that lies inside the polygon (0: none)
+#define GT_RREJ2 4   // squared radius beyond which the angle sum is provably < 349 degrees
+#define GT_RGMAX 5
+#define GT_RGMIN 6
 #define GT_VX 8
 #define GT_VY 32
 #define GT_RG 56
@@ -28,46 +30,40 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct P24Workspace {
     size_t gt_rec;      // [B, Lmax, GT_REC] float
-    size_t cand_flag;   // [B, A] uint8   candidate mask (fg_mask before matching, losses.py:546)
-    size_t cand_count;  // [B] int
-    size_t vcount;      // [B, Lmax] int  centre-window list length
-    size_t vlist;       // [B, Lmax, VCAP] int  anchor | in_box << 31
-    size_t vcost;       // [B, Lmax, VCAP] float  cost of valid pairs (+inf when not in_box)
-    size_t viou;        // [B, Lmax, VCAP] float  pair value of valid pairs
-    size_t sel_count;   // [B, Lmax] int          anchors actually selected by each GT (== dyn_k in contract)
-    size_t claim_cnt;   // [B, A] int             number of GTs that selected the anchor (bit 30: resolved)
-    size_t best_key;    // [B, A] u64             min over valid pairs of (cost bits << 32 | gt), losses.py:474
-    size_t err_flag;    // [1] int                sticky internal error bits (list overflow)
-    size_t sel_anchor;  // [B, Lmax, TOPK] int    anchors selected by each GT
-    size_t sel_cost;    // [B, Lmax, TOPK] float
-    size_t sel_iou;     // [B, Lmax, TOPK] float
-    size_t partials;    // [LOSS_BLOCKS, 28] double
+    size_t anc4;        // [B, A] float4   (pred cx, pred cy, rpmax or -1 when not a candidate, rpmin)
+    size_t vcount;      // [B, Lmax] int   number of valid (in polygon AND in centre window) pairs of the GT
+    size_t vanchor;     // [B, Lmax, VCAP] int
+    size_t vcost;       // [B, Lmax, VCAP] float  SimOTA cost of the valid pair
+    size_t best_key;    // [B, A] u64      min over valid pairs of (ordered cost bits << 32 | gt), losses.py:474
+    size_t claim_cnt;   // [B, A] int      number of GTs that selected the anchor
+    size_t claim_gt;    // [B, A] int      the GT that selected the anchor (meaningful when claim_cnt == 1)
+    size_t obj_part;    // [B * tiles] double   per-block sums of BCEWithLogits(obj, 0)
+    size_t loss_part;   // [B * tiles, 28] double
     size_t ticket;      // [1] unsigned (last-block-done counter)
+    size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
     size_t total;
 };
 
-#define P24_LOSS_BLOCKS 592  // 4 x 148 SMs
+static inline int p24_tiles(int A) { return (A + P24_THREADS - 1) / P24_THREADS; }
 
 static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     P24Workspace w;
     size_t off = 0;
     const size_t BL = (size_t)B * (size_t)Lmax;
+    const size_t BA = (size_t)B * (size_t)A;
+    const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
-    w.cand_flag = off;  off = p24_align(off + (size_t)B * A);
-    w.cand_count = off; off = p24_align(off + (size_t)B * sizeof(int));
+    w.anc4 = off;       off = p24_align(off + BA * 4 * sizeof(float));
     w.vcount = off;     off = p24_align(off + BL * sizeof(int));
-    w.vlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));
+    w.vanchor = off;    off = p24_align(off + BL * P24_VCAP * sizeof(int));
     w.vcost = off;      off = p24_align(off + BL * P24_VCAP * sizeof(float));
-    w.viou = off;       off = p24_align(off + BL * P24_VCAP * sizeof(float));
-    w.sel_count = off;  off = p24_align(off + BL * sizeof(int));
-    w.claim_cnt = off;  off = p24_align(off + (size_t)B * A * sizeof(int));
-    w.best_key = off;   off = p24_align(off + (size_t)B * A * sizeof(unsigned long long));
-    w.err_flag = off;   off = p24_align(off + sizeof(int));
-    w.sel_anchor = off; off = p24_align(off + BL * P24_TOPK * sizeof(int));
-    w.sel_cost = off;   off = p24_align(off + BL * P24_TOPK * sizeof(float));
-    w.sel_iou = off;    off = p24_align(off + BL * P24_TOPK * sizeof(float));
-    w.partials = off;   off = p24_align(off + (size_t)P24_LOSS_BLOCKS * 28 * sizeof(double));
+    w.best_key = off;   off = p24_align(off + BA * sizeof(unsigned long long));
+    w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
+    w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));
+    w.obj_part = off;   off = p24_align(off + NB * sizeof(double));
+    w.loss_part = off;  off = p24_align(off + NB * 28 * sizeof(double));
     w.ticket = off;     off = p24_align(off + sizeof(unsigned));
+    w.err_flag = off;   off = p24_align(off + sizeof(int));
     w.total = off;
     return w;
 }
@@ -126,6 +122,12 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
+}
+
+// order-preserving map float -> uint32 (smaller float -> smaller key)
+__device__ __forceinline__ unsigned p24_ordered(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
 #define P24_NEG_INF (-INFINITY)

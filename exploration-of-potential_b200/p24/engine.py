@@ -1,0 +1,142 @@
+"""Host side of the fused SimOTA + loss-sum path: buffer management and the ctypes calls.
+
+PyTorch is used for device memory and streams only; all arithmetic runs in libp24_b200
+(``csrc/p24_simota.cu``).  Nothing here synchronises with the device.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Sequence, Tuple
+
+import torch
+
+from . import lib as _lib
+
+F_NO_PRUNE = 1   # evaluate every polygon angle sum exactly (self-check of the geometric pruning)
+F_NO_FILTER = 2  # evaluate every pair value exactly (self-check of the top-10 bound filter)
+F_ALL_ROWS = 4   # every label row is a GT (per-image API)
+
+
+@dataclass
+class Assignment:
+    """Device-resident result of one batch (no host sync has happened)."""
+    fg_mask: torch.Tensor      # [B, A] uint8
+    matched_gt: torch.Tensor   # [B, A] int32, -1 = background
+    pred_iou: torch.Tensor     # [B, A] fp32
+    num_fg: torch.Tensor       # [B] int32
+    num_gt: torch.Tensor       # [B] int32
+    dyn_k: torch.Tensor        # [B, Lmax] int32
+    sums28: torch.Tensor | None  # [28] fp32
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_cuda_f32(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.P24Error(f"{name} must be a CUDA tensor: the p24 path has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+
+
+class GridCache:
+    """Concatenated x_shifts / y_shifts / expanded_strides (losses.py:193-195), cached per 3-list."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, x_shifts, y_shifts, strides, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        if torch.is_tensor(x_shifts):
+            x_shifts, y_shifts, strides = [x_shifts], [y_shifts], [strides]
+        key = tuple((t.data_ptr(), tuple(t.shape), t._version) for t in list(x_shifts) + list(y_shifts) + list(strides))
+        if key != self._key:
+            cat = [torch.cat([t.reshape(1, -1) for t in lst], 1).reshape(-1).to(device=device, dtype=torch.float32)
+                   .contiguous() for lst in (x_shifts, y_shifts, strides)]
+            self._key, self._val = key, tuple(cat)
+        return self._val
+
+
+class SimOTAEngine:
+    """Owns the workspace and output buffers for one (B, A, Lmax) shape on one device."""
+
+    def __init__(self):
+        self._bufs: Dict[tuple, dict] = {}
+        self.grids = GridCache()
+
+    def _buffers(self, B, A, Lmax, device):
+        key = (B, A, Lmax, str(device))
+        buf = self._bufs.get(key)
+        if buf is None:
+            lib = _lib.load()
+            nbytes = lib.p24_workspace_bytes(B, A, Lmax)
+            buf = dict(
+                ws=torch.empty(nbytes + 256, dtype=torch.uint8, device=device),
+                nbytes=nbytes,
+            )
+            self._bufs[key] = buf
+        return buf
+
+    def run(self, outputs: torch.Tensor, labels: torch.Tensor, x_shifts, y_shifts, strides, num_classes: int,
+            flags: int = 0, want_sums: bool = True, out: Assignment | None = None) -> Assignment:
+        lib = _lib.load()
+        _check_cuda_f32(outputs, "outputs")
+        _check_cuda_f32(labels, "labels")
+        if outputs.dim() != 3 or outputs.shape[2] != 27 + num_classes:
+            raise IndexError("outputs must be [B, A, 27 + num_classes]")
+        if labels.dim() != 3 or labels.shape[2] != 51 or labels.shape[0] != outputs.shape[0]:
+            raise IndexError("labels must be [B, Lmax, 51]")
+        if outputs.stride(2) != 1:
+            outputs = outputs.contiguous()
+        if labels.stride(2) != 1:
+            labels = labels.contiguous()
+        B, A, _ = outputs.shape
+        Lmax = labels.shape[1]
+        dev = outputs.device
+        gx, gy, gs = self.grids.get(x_shifts, y_shifts, strides, dev)
+        if gx.numel() != A:
+            raise IndexError("grid length does not match the number of anchors")
+        if out is None:
+            out = Assignment(
+                fg_mask=torch.empty((B, A), dtype=torch.uint8, device=dev),
+                matched_gt=torch.empty((B, A), dtype=torch.int32, device=dev),
+                pred_iou=torch.empty((B, A), dtype=torch.float32, device=dev),
+                num_fg=torch.empty((B,), dtype=torch.int32, device=dev),
+                num_gt=torch.empty((B,), dtype=torch.int32, device=dev),
+                dyn_k=torch.empty((B, max(Lmax, 1)), dtype=torch.int32, device=dev),
+                sums28=torch.empty((28,), dtype=torch.float32, device=dev) if want_sums else None,
+            )
+        if Lmax == 0:  # no label rows at all: everything is background
+            out.fg_mask.zero_(); out.matched_gt.fill_(-1); out.pred_iou.zero_()
+            out.num_fg.zero_(); out.num_gt.zero_(); out.dyn_k.zero_()
+            labels = outputs.new_zeros((B, 1, 51))
+            Lmax = 1
+        buf = self._buffers(B, A, Lmax, dev)
+        ws = buf["ws"]
+        ws_ptr = (ws.data_ptr() + 255) & ~255
+        with torch.cuda.device(dev):
+            code = lib.p24_simota_loss_batch(
+                outputs.data_ptr(), outputs.stride(0), outputs.stride(1), B, A, num_classes,
+                labels.data_ptr(), labels.stride(0), labels.stride(1), Lmax,
+                gx.data_ptr(), gy.data_ptr(), gs.data_ptr(),
+                out.fg_mask.data_ptr(), out.matched_gt.data_ptr(), out.pred_iou.data_ptr(),
+                out.num_fg.data_ptr(), out.num_gt.data_ptr(), out.dyn_k.data_ptr(),
+                out.sums28.data_ptr() if out.sums28 is not None else None,
+                ws_ptr, buf["nbytes"], flags, _stream_ptr(dev))
+        _lib.check(code, "p24_simota_loss_batch")
+        return out
+
+    def finalize(self, sums28: torch.Tensor, state26: torch.Tensor, result54: torch.Tensor | None = None,
+                 weights27: torch.Tensor | None = None):
+        lib = _lib.load()
+        dev = sums28.device
+        if result54 is None:
+            result54 = torch.empty(54, dtype=torch.float32, device=dev)
+        if weights27 is None:
+            weights27 = torch.empty(27, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            code = lib.p24_loss_finalize(sums28.data_ptr(), state26.data_ptr(), result54.data_ptr(),
+                                         weights27.data_ptr(), _stream_ptr(dev))
+        _lib.check(code, "p24_loss_finalize")
+        return result54, weights27

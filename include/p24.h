@@ -39,6 +39,7 @@ extern "C" {
 /* p24_assign_batch flags */
 #define P24_F_NO_PRUNE 1u      /* evaluate every polygon angle sum exactly (self-check of the pruning) */
 #define P24_F_NO_FILTER 2u     /* evaluate every pair value exactly (self-check of the top-k filter) */
+#define P24_F_ALL_ROWS 4u      /* every label row is a GT (per-image API: the caller passes num_gt rows) */
 
 int p24_abi_version(void);
 const char* p24_error_string(int code);
@@ -47,28 +48,10 @@ const char* p24_error_string(int code);
  * label rows Lmax).  The caller allocates it once (device memory, 256-byte aligned). */
 size_t p24_workspace_bytes(int B, int A, int Lmax);
 
-/* IOUloss.circle_inter (models/losses.py:23-78), element-wise over n pairs.
- * gt_r / pd_r: [n, 24] with row strides; outputs res_inter, dist: dense [n, 24]. */
-int p24_circle_inter_fwd(const float* gt_cx, const float* gt_cy, const float* gt_r, int64_t gt_r_stride,
-                         const float* pd_cx, const float* pd_cy, const float* pd_r, int64_t pd_r_stride,
-                         int n, float* res_inter, float* dist, void* stream);
-
-/* IOUloss.forward (models/losses.py:80-157): pred [n,26], target [n,50] -> loss24 [n,24] dense. */
-int p24_iou_loss_fwd(const float* pred, int64_t pred_stride, const float* target, int64_t target_stride,
-                     int n, float* loss24, void* stream);
-
-/* Backward of IOUloss.forward w.r.t. pred (autograd of losses.py:80-157; clipped acos and branch
- * masks have zero gradient).  grad_loss24 dense [n,24]; grad_pred dense [n,26] (overwritten). */
-int p24_iou_loss_bwd(const float* pred, int64_t pred_stride, const float* target, int64_t target_stride,
-                     const float* grad_loss24, int n, float* grad_pred, void* stream);
-
-/* utils.boxes.bboxes_iou (utils/boxes.py:166-243): gt [G,50], pred [P,26] -> out dense [G,P]. */
-int p24_pair_iou(const float* gt50, int64_t gt_stride, int G, const float* pred26, int64_t pred_stride, int P,
-                 float* out, void* stream);
-
-/* Loss_Function.get_assignments + get_in_boxes_info + pts_in_poly + cost + dynamic_k_matching
- * (models/losses.py:359-592) for a whole batch in one call; the G x A cost matrix is never
- * written to memory.
+/* The fused training hot path: Loss_Function.get_assignments + get_in_boxes_info + pts_in_poly +
+ * cost + dynamic_k_matching (models/losses.py:359-592), utils.boxes.bboxes_iou (utils/boxes.py:166-243)
+ * and the loss sums of Loss_Function.forward (models/losses.py:246-302) for a whole batch in one call;
+ * the G x A cost matrix is never written to memory.
  *   outputs  [B, A, 27+nc] decoded head output (strides img_stride / row_stride, channel stride 1)
  *   labels   [B, Lmax, 51]  (cls, cx, cy, 24 x (x, y)); valid rows first, zero padded
  *   x_shifts, y_shifts, strides: [A] (the head's 3-lists concatenated, losses.py:193-195)
@@ -79,23 +62,19 @@ int p24_pair_iou(const float* gt50, int64_t gt_stride, int G, const float* pred2
  *   num_fg     [B]    int32   foreground anchors per image (losses.py:481)
  *   num_gt     [B]    int32   nlabel (losses.py:190)
  *   dyn_k      [B, Lmax] int32 dynamic k per GT, 0 beyond num_gt (losses.py:456)
+ *   sums28     [28] fp32 (may be NULL: assignment only):
+ *              sums[0..23] = sum_f loss24[f, k]            (IOUloss.forward on the matched pairs, losses.py:283)
+ *              sums[24]    = sum BCEWithLogits(obj, fg)     (losses.py:294)
+ *              sums[25]    = sum BCEWithLogits(cls[fg], onehot * pred_iou)   (losses.py:298)
+ *              sums[26]    = sum_b num_fg, sums[27] = sum_b num_gt
+ *              This 28-float vector is what is all-reduced across GPUs.
  */
-int p24_assign_batch(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A, int num_classes,
-                     const float* labels, int64_t lab_img_stride, int64_t lab_row_stride, int Lmax,
-                     const float* x_shifts, const float* y_shifts, const float* strides,
-                     uint8_t* fg_mask, int32_t* matched_gt, float* pred_iou,
-                     int32_t* num_fg, int32_t* num_gt, int32_t* dyn_k,
-                     void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
-
-/* Loss sums of Loss_Function.forward (models/losses.py:283-302) from the assignment:
- * sums[0..23] = sum_f loss24[f, k], sums[24] = sum BCEWithLogits(obj, fg), sums[25] = sum
- * BCEWithLogits(cls[fg], onehot * pred_iou), sums[26] = sum_b num_fg, sums[27] = sum_b num_gt.
- * This 28-float vector is what is all-reduced across GPUs. */
-int p24_loss_sums(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A, int num_classes,
-                  const float* labels, int64_t lab_img_stride, int64_t lab_row_stride, int Lmax,
-                  const uint8_t* fg_mask, const int32_t* matched_gt, const float* pred_iou,
-                  const int32_t* num_fg, const int32_t* num_gt,
-                  float* sums28, void* workspace, size_t workspace_bytes, void* stream);
+int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A, int num_classes,
+                          const float* labels, int64_t lab_img_stride, int64_t lab_row_stride, int Lmax,
+                          const float* x_shifts, const float* y_shifts, const float* strides,
+                          uint8_t* fg_mask, int32_t* matched_gt, float* pred_iou,
+                          int32_t* num_fg, int32_t* num_gt, int32_t* dyn_k, float* sums28,
+                          void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
 /* Normalisation and stateful re-weighting (models/losses.py:280-345).
  * state[26] = last_iou_loss[24], last_obj_loss, last_cls_loss (initially 1.0), updated in place.
@@ -103,36 +82,6 @@ int p24_loss_sums(const float* outputs, int64_t img_stride, int64_t row_stride, 
  *              reg_w[24], obj_w, cls_w;  weights_n[27] = reg_w[24], obj_w, cls_w, max(num_fg,1)
  *              (what the backward needs). */
 int p24_loss_finalize(const float* sums28, float* state26, float* result54, float* weights_n27, void* stream);
-
-/* Backward of the whole loss w.r.t. outputs (autograd of models/losses.py:283-341):
- * grad_outputs [B, A, 27+nc] dense, fully overwritten. grad_scale: device scalar (upstream grad). */
-int p24_loss_bwd(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A, int num_classes,
-                 const float* labels, int64_t lab_img_stride, int64_t lab_row_stride,
-                 const uint8_t* fg_mask, const int32_t* matched_gt, const float* pred_iou,
-                 const float* weights_n27, const float* grad_scale, float* grad_outputs, void* stream);
-
-/* Loss_Function.dynamic_k_matching (models/losses.py:444-494) on a materialised cost matrix.
- * cost, ious: dense [G, P];  fg_in [P] uint8, matched [P] int32 (-1 when not fg),
- * matched_iou [P] fp32, dyn_k [G] int32, num_fg [1] int32. */
-int p24_dynamic_k_matching(const float* cost, const float* ious, int G, int P,
-                           uint8_t* fg_in, int32_t* matched, float* matched_iou, int32_t* dyn_k, int32_t* num_fg,
-                           void* stream);
-
-/* utils.boxes.postprocess (utils/boxes.py:29-99; twin show_24p.py:212-264), per image.
- *   prediction [B, A, 27+nc] (obj / cls already sigmoid)
- *   coef_x, coef_y [24]: theta_k*cos(theta_k), theta_k*sin(theta_k) as the reference's own torch
- *     expression evaluates them (boxes.py:30-33), passed in so libm differences cannot enter
- *   class_agnostic != 0 -> nms, else batched_nms with the coordinate trick
- * writes, per image b (capacity `cap` rows each):
- *   det_count [B]        rows kept after NMS
- *   det_rows  [B, cap, 29]  cx, cy, r0..r23, obj, class_conf, class_pred in NMS (score) order
- *   cand_count [B]       rows that passed the score filter
- * debug outputs (may be NULL): rect [B, cap, 4] of the candidates in anchor order. */
-int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_stride, int B, int A, int num_classes,
-                    const float* coef_x, const float* coef_y, float conf_thre, float nms_thre, int class_agnostic,
-                    int cap, int32_t* cand_count, int32_t* det_count, float* det_rows, float* rect_debug,
-                    void* workspace, size_t workspace_bytes, void* stream);
-size_t p24_postprocess_workspace_bytes(int B, int A, int cap);
 
 #ifdef __cplusplus
 }
