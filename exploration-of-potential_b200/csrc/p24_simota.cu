@@ -793,6 +793,15 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
 
 size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float); }
 
+// optional per-stage timing (profiling aid for bench.py; process-global, not thread-safe)
+#define N_STAGES 4
+bool g_prof_on = false;
+cudaEvent_t g_prof_ev[N_STAGES + 1];
+bool g_prof_have = false;
+inline void prof_mark(int i, cudaStream_t st) {
+    if (g_prof_on) cudaEventRecord(g_prof_ev[i], st);
+}
+
 }  // namespace
 
 // -------------------------------------------------------------------------------------------
@@ -847,10 +856,15 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
         cudaFuncSetAttribute(k_anchor_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_done = true;
     }
+    prof_mark(0, st);
     k_gt_prep<<<B, 128, 0, st>>>(p);
+    prof_mark(1, st);
     k_anchor_pass<<<dim3(p.tiles, B), P24_THREADS, dyn, st>>>(p);
+    prof_mark(2, st);
     k_gt_match<<<dim3(Lmax, B), P24_THREADS, 0, st>>>(p);
+    prof_mark(3, st);
     k_resolve_loss<<<dim3(p.tiles, B), P24_THREADS, 0, st>>>(p);
+    prof_mark(4, st);
     return (int)cudaGetLastError();
 }
 
@@ -859,4 +873,27 @@ extern "C" int p24_loss_finalize(const float* sums28, float* state26, float* res
     if (!sums28 || !state26 || !result54 || !weights_n27) return P24_E_BADARG;
     k_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(sums28, state26, result54, weights_n27);
     return (int)cudaGetLastError();
+}
+
+extern "C" int p24_profile_enable(int on) {
+    if (on && !g_prof_have) {
+        for (int i = 0; i <= N_STAGES; ++i) {
+            const cudaError_t e = cudaEventCreate(&g_prof_ev[i]);
+            if (e != cudaSuccess) return (int)e;
+        }
+        g_prof_have = true;
+    }
+    g_prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int p24_profile_read(float* h_ms4) {
+    if (!g_prof_have || !h_ms4) return P24_E_BADARG;
+    cudaError_t e = cudaEventSynchronize(g_prof_ev[N_STAGES]);
+    if (e != cudaSuccess) return (int)e;
+    for (int i = 0; i < N_STAGES; ++i) {
+        e = cudaEventElapsedTime(&h_ms4[i], g_prof_ev[i], g_prof_ev[i + 1]);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
 }

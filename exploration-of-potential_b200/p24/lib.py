@@ -26,6 +26,8 @@ _PROTOS = {
                                         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr, C.c_size_t, C.c_uint32, c_ptr]),
     "p24_loss_finalize": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "p24_profile_enable": (C.c_int, [C.c_int]),
+    "p24_profile_read": (C.c_int, [C.POINTER(C.c_float)]),
 }
 
 

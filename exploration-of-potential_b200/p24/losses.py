@@ -34,6 +34,9 @@ class Loss_Function(nn.Module):
         self._state26 = None
         self._engine = SimOTAEngine()
         self.last_assignment: Assignment | None = None
+        # set to a torch.distributed group to shard the batch by image across GPUs: the only collective is the
+        # SUM all-reduce of the 28 loss sums
+        self.process_group = None
 
     # -- state ---------------------------------------------------------------------------------
     def _state(self, device):
@@ -57,6 +60,9 @@ class Loss_Function(nn.Module):
             raise NotImplementedError("use_l1 is never enabled by the 24p scripts (losses.py:163)")
         x_shifts, y_shifts, expanded_strides, outputs = outputs_train[:4]
         asg = self._engine.run(outputs, labels, x_shifts, y_shifts, expanded_strides, self.num_classes, flags=flags)
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(asg.sums28, op=dist.ReduceOp.SUM, group=self.process_group)
         state = self._state(outputs.device)
         result54, weights27 = self._engine.finalize(asg.sums28, state)
         self.last_assignment = asg

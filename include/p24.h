@@ -83,6 +83,12 @@ int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_
  *              (what the backward needs). */
 int p24_loss_finalize(const float* sums28, float* state26, float* result54, float* weights_n27, void* stream);
 
+/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its four
+ * kernels (gt_prep, anchor_pass, gt_match, resolve_loss) on the launching stream; p24_profile_read waits
+ * for the last call and returns the four durations in milliseconds into a HOST array.  Process-global. */
+int p24_profile_enable(int on);
+int p24_profile_read(float* h_ms4);
+
 #ifdef __cplusplus
 }
 #endif
