@@ -11,14 +11,15 @@
 #define P24_THREADS 256
 #define P24_WARPS (P24_THREADS / 32)
 
-// ---- per-GT record (floats), built once per batch by k_gt_prep --------------------------------
-// [0] cx  [1] cy  [2] class (as float)  [3] rin2  [4] rrej2  [5] rgmax  [6] rgmin  [7] pad
+// ---- per-GT record (floats), built once per image by the anchor pass ---------------------------
+// [0] cx  [1] cy  [2] rin2  [3] rrej2   (one 128-bit shared-memory load for the per-pair tests)
+// [4] class (as float)  [5] rgmax  [6] rgmin  [7] pad
 // [8..31] vertex x  [32..55] vertex y  [56..79] ray length rg
 #define GT_CX 0
 #define GT_CY 1
-#define GT_CLS 2
-#define GT_RIN2 3    // squared radius of a disc around (cx, cy) that lies inside the polygon (0: none)
-#define GT_RREJ2 4   // squared radius beyond which the angle sum is provably < 349 degrees
+#define GT_RIN2 2    // squared radius of a disc around (cx, cy) that lies inside the polygon (0: none)
+#define GT_RREJ2 3   // squared radius beyond which the angle sum is provably < 349 degrees
+#define GT_CLS 4
 #define GT_RGMAX 5
 #define GT_RGMIN 6
 #define GT_VX 8
@@ -30,16 +31,15 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct P24Workspace {
     size_t gt_rec;      // [B, Lmax, GT_REC] float
-    size_t anc4;        // [B, A] float4   (pred cx, pred cy, rpmax or -1 when not a candidate, rpmin)
-    size_t vcount;      // [B, Lmax] int   number of valid (in polygon AND in centre window) pairs of the GT
-    size_t vanchor;     // [B, Lmax, VCAP] int
-    size_t vcost;       // [B, Lmax, VCAP] float  SimOTA cost of the valid pair
-    size_t best_key;    // [B, A] u64      min over valid pairs of (ordered cost bits << 32 | gt), losses.py:474
+    size_t clist;       // [B, tiles, 256] float4  candidate anchors of a tile, compacted: (pred cx, pred cy, rpmax, anchor idx bits)
+    size_t ccount;      // [B, tiles] int          candidates per tile
+    size_t wcount;      // [B, Lmax] int           anchors inside the GT's centre window (zero between calls)
+    size_t wlist;       // [B, Lmax, VCAP] int
     size_t claim_cnt;   // [B, A] int      number of GTs that selected the anchor
     size_t claim_gt;    // [B, A] int      the GT that selected the anchor (meaningful when claim_cnt == 1)
     size_t obj_part;    // [B * tiles] double   per-block sums of BCEWithLogits(obj, 0)
     size_t loss_part;   // [B * tiles, 28] double
-    size_t ticket;      // [1] unsigned (last-block-done counter)
+    size_t ticket;      // [1] unsigned (last-block-done counter; zero between calls)
     size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
     size_t total;
 };
@@ -52,18 +52,18 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     const size_t BL = (size_t)B * (size_t)Lmax;
     const size_t BA = (size_t)B * (size_t)A;
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
+    // the counters that must be zero between calls come first (p24_workspace_init clears everything)
+    w.wcount = off;     off = p24_align(off + BL * sizeof(int));
+    w.ticket = off;     off = p24_align(off + sizeof(unsigned));
+    w.err_flag = off;   off = p24_align(off + sizeof(int));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
-    w.anc4 = off;       off = p24_align(off + BA * 4 * sizeof(float));
-    w.vcount = off;     off = p24_align(off + BL * sizeof(int));
-    w.vanchor = off;    off = p24_align(off + BL * P24_VCAP * sizeof(int));
-    w.vcost = off;      off = p24_align(off + BL * P24_VCAP * sizeof(float));
-    w.best_key = off;   off = p24_align(off + BA * sizeof(unsigned long long));
+    w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
+    w.ccount = off;     off = p24_align(off + NB * sizeof(int));
+    w.wlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));
     w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
     w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));
     w.obj_part = off;   off = p24_align(off + NB * sizeof(double));
     w.loss_part = off;  off = p24_align(off + NB * 28 * sizeof(double));
-    w.ticket = off;     off = p24_align(off + sizeof(unsigned));
-    w.err_flag = off;   off = p24_align(off + sizeof(int));
     w.total = off;
     return w;
 }
@@ -114,6 +114,21 @@ __device__ __forceinline__ KV block_select(KV x, KV* s_red) {
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ float warp_prod(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;

@@ -146,3 +146,73 @@ P24_HD float p24_cost(float cls_cost, float pair_value, bool valid) {
 P24_HD float p24_bce_logits(float x, float t) {
     return ((1.0f - t) * x) + (fmaxf(-x, 0.0f) + log1pf(expf(-fabsf(x))));
 }
+
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------
+// Fast polygon test (device only).  The reference thresholds the total UNSIGNED angle subtended by the
+// 24 edges at 350 degrees (losses.py:583-588).  Instead of 24 atan2 the unsigned angles are accumulated as
+// the argument of a complex product  prod_k (dot_k + i |cross_k|)  (each factor has argument in [0, pi]),
+// counting wraps across 2 pi.  Returns 1 (sum >= 350.05 deg), 0 (sum <= 349.95 deg) or 2 (within 0.05 deg of
+// the threshold, or degenerate): only then is the reference-order p24_angle_sum evaluated.  The
+// 0.05 degree band is > 50x the fp32 error of either evaluation (< 1e-3 degrees).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int p24_angle_test_fast(const float* __restrict__ vx, const float* __restrict__ vy, float xc,
+                                                   float yc) {
+    float re = 1.0f, im = 0.0f;
+    int wraps = 0;
+    float sx = vx[0] - xc, sy = vy[0] - yc;
+    const float fx = sx, fy = sy;
+#pragma unroll
+    for (int k = 0; k < P24_RAYS; ++k) {
+        const float ex = (k == P24_RAYS - 1) ? fx : (vx[k + 1] - xc);
+        const float ey = (k == P24_RAYS - 1) ? fy : (vy[k + 1] - yc);
+        const float cr = fabsf(fmaf(sx, ey, -(ex * sy)));
+        const float dt = fmaf(sx, ex, sy * ey);
+        const float nre = fmaf(re, dt, -(im * cr));
+        const float nim = fmaf(re, cr, im * dt);
+        wraps += (im < 0.0f && nim >= 0.0f) ? 1 : 0;
+        re = nre;
+        im = nim;
+        sx = ex;
+        sy = ey;
+        if ((k & 3) == 3) {  // renormalise by a power of two (exact) to stay inside the fp32 range
+            const float m = fmaxf(fabsf(re), fabsf(im));
+            const int e = (__float_as_int(m) >> 23) & 0xFF;
+            const float sc = __int_as_float((254 - e) << 23);
+            re *= sc;
+            im *= sc;
+        }
+    }
+    if (!(fabsf(re) + fabsf(im) > 0.0f) || !(re == re) || !(im == im) || isinf(re) || isinf(im)) return 2;
+    if (wraps > 0) return 1;
+    if (im < 0.0f && re > 0.0f) {
+        const float y = -im;
+        if (y < re * 0.17542f) return 1;   // tan(9.95 deg) = 0.175426
+        if (y > re * 0.17723f) return 0;   // tan(10.05 deg) = 0.177226
+        return 2;
+    }
+    return 0;
+}
+
+// exact decision, fast path first
+__device__ __forceinline__ bool p24_in_polygon(const float* __restrict__ vx, const float* __restrict__ vy, float xc,
+                                               float yc) {
+    const int r = p24_angle_test_fast(vx, vy, xc, yc);
+    if (r != 2) return r == 1;
+    return p24_angle_sum(vx, vy, xc, yc) >= 350.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Class cost in product form (device only).  sum_j -log1p(-p_j) = -log prod_j (1 - p_j) with
+// p_j = sqrt(sigmoid(cls_j) sigmoid(obj)) = rsqrt((1 + e^-cls_j)(1 + e^-obj)); one log per anchor instead of 80.
+// A lane accumulates the factors of its classes; saturated factors (p >= 1, the reference clamps the
+// term at 100) are counted separately.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void p24_neg_factor(float cls_logit, float eo1, float& prod, int& nsat) {
+    const float q = (1.0f + __expf(-cls_logit)) * eo1;
+    const float om = 1.0f - rsqrtf(q);
+    if (om > 0.0f) prod *= om;
+    else ++nsat;
+}
+#endif

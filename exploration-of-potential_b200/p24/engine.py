@@ -71,15 +71,19 @@ class SimOTAEngine:
         if buf is None:
             lib = _lib.load()
             nbytes = lib.p24_workspace_bytes(B, A, Lmax)
-            buf = dict(
-                ws=torch.empty(nbytes + 256, dtype=torch.uint8, device=device),
-                nbytes=nbytes,
-            )
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            ptr = (ws.data_ptr() + 255) & ~255
+            with torch.cuda.device(device):
+                _lib.check(lib.p24_workspace_init(ptr, nbytes, _stream_ptr(device)), "p24_workspace_init")
+            buf = dict(ws=ws, ptr=ptr, nbytes=nbytes)
             self._bufs[key] = buf
         return buf
 
     def run(self, outputs: torch.Tensor, labels: torch.Tensor, x_shifts, y_shifts, strides, num_classes: int,
-            flags: int = 0, want_sums: bool = True, out: Assignment | None = None) -> Assignment:
+            flags: int = 0, want_sums: bool = True, out: Assignment | None = None,
+            finalize: tuple | None = None) -> Assignment:
+        """Enqueue the kernel chain.  ``finalize=(state26, result54, weights27)`` fuses the normalisation and
+        re-weighting into the last kernel (single-GPU case)."""
         lib = _lib.load()
         _check_cuda_f32(outputs, "outputs")
         _check_cuda_f32(labels, "labels")
@@ -113,8 +117,8 @@ class SimOTAEngine:
             labels = outputs.new_zeros((B, 1, 51))
             Lmax = 1
         buf = self._buffers(B, A, Lmax, dev)
-        ws = buf["ws"]
-        ws_ptr = (ws.data_ptr() + 255) & ~255
+        ws_ptr = buf["ptr"]
+        fin = [t.data_ptr() for t in finalize] if finalize is not None else [None, None, None]
         with torch.cuda.device(dev):
             code = lib.p24_simota_loss_batch(
                 outputs.data_ptr(), outputs.stride(0), outputs.stride(1), B, A, num_classes,
@@ -123,6 +127,7 @@ class SimOTAEngine:
                 out.fg_mask.data_ptr(), out.matched_gt.data_ptr(), out.pred_iou.data_ptr(),
                 out.num_fg.data_ptr(), out.num_gt.data_ptr(), out.dyn_k.data_ptr(),
                 out.sums28.data_ptr() if out.sums28 is not None else None,
+                fin[0], fin[1], fin[2],
                 ws_ptr, buf["nbytes"], flags, _stream_ptr(dev))
         _lib.check(code, "p24_simota_loss_batch")
         return out

@@ -24,7 +24,9 @@ _PROTOS = {
                                         c_ptr, C.c_int64, C.c_int64, C.c_int,
                                         c_ptr, c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                        c_ptr, c_ptr, c_ptr,
                                         c_ptr, C.c_size_t, C.c_uint32, c_ptr]),
+    "p24_workspace_init": (C.c_int, [c_ptr, C.c_size_t, c_ptr]),
     "p24_loss_finalize": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "p24_profile_enable": (C.c_int, [C.c_int]),
     "p24_profile_read": (C.c_int, [C.POINTER(C.c_float)]),

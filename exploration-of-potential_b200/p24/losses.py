@@ -59,12 +59,18 @@ class Loss_Function(nn.Module):
         if self.use_l1:
             raise NotImplementedError("use_l1 is never enabled by the 24p scripts (losses.py:163)")
         x_shifts, y_shifts, expanded_strides, outputs = outputs_train[:4]
-        asg = self._engine.run(outputs, labels, x_shifts, y_shifts, expanded_strides, self.num_classes, flags=flags)
-        if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(asg.sums28, op=dist.ReduceOp.SUM, group=self.process_group)
         state = self._state(outputs.device)
-        result54, weights27 = self._engine.finalize(asg.sums28, state)
+        if self.process_group is None:
+            # single GPU: the last CTA of the chain applies the normalisation and re-weighting itself
+            result54 = torch.empty(54, dtype=torch.float32, device=outputs.device)
+            weights27 = torch.empty(27, dtype=torch.float32, device=outputs.device)
+            asg = self._engine.run(outputs, labels, x_shifts, y_shifts, expanded_strides, self.num_classes,
+                                   flags=flags, finalize=(state, result54, weights27))
+        else:
+            import torch.distributed as dist
+            asg = self._engine.run(outputs, labels, x_shifts, y_shifts, expanded_strides, self.num_classes, flags=flags)
+            dist.all_reduce(asg.sums28, op=dist.ReduceOp.SUM, group=self.process_group)
+            result54, weights27 = self._engine.finalize(asg.sums28, state)
         self.last_assignment = asg
         # expose the state like the reference does (views: no copy, no sync)
         self.last_iou_loss = state[:24]

@@ -47,6 +47,8 @@ const char* p24_error_string(int code);
 /* Bytes of scratch p24_assign_batch / p24_loss_sums need for a batch (B images, A anchors,
  * label rows Lmax).  The caller allocates it once (device memory, 256-byte aligned). */
 size_t p24_workspace_bytes(int B, int A, int Lmax);
+/* Clears a fresh workspace (cudaMemsetAsync on `stream`); needed once per allocation, or after a failed call. */
+int p24_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 
 /* The fused training hot path: Loss_Function.get_assignments + get_in_boxes_info + pts_in_poly +
  * cost + dynamic_k_matching (models/losses.py:359-592), utils.boxes.bboxes_iou (utils/boxes.py:166-243)
@@ -68,12 +70,18 @@ size_t p24_workspace_bytes(int B, int A, int Lmax);
  *              sums[25]    = sum BCEWithLogits(cls[fg], onehot * pred_iou)   (losses.py:298)
  *              sums[26]    = sum_b num_fg, sums[27] = sum_b num_gt
  *              This 28-float vector is what is all-reduced across GPUs.
+ *   state26 / result54 / weights_n27 (all three or none): when given, the last CTA also applies
+ *              p24_loss_finalize (single-GPU case: one launch less); with several GPUs pass NULL, all-reduce
+ *              sums28 and call p24_loss_finalize.
+ * The workspace (p24_workspace_bytes, 256-byte aligned) must have been cleared once with p24_workspace_init;
+ * a successful call leaves it ready for the next one.  One workspace serves one call at a time.
  */
 int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A, int num_classes,
                           const float* labels, int64_t lab_img_stride, int64_t lab_row_stride, int Lmax,
                           const float* x_shifts, const float* y_shifts, const float* strides,
                           uint8_t* fg_mask, int32_t* matched_gt, float* pred_iou,
                           int32_t* num_fg, int32_t* num_gt, int32_t* dyn_k, float* sums28,
+                          float* state26, float* result54, float* weights_n27,
                           void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
 /* Normalisation and stateful re-weighting (models/losses.py:280-345).
@@ -83,11 +91,11 @@ int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_
  *              (what the backward needs). */
 int p24_loss_finalize(const float* sums28, float* state26, float* result54, float* weights_n27, void* stream);
 
-/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its four
- * kernels (gt_prep, anchor_pass, gt_match, resolve_loss) on the launching stream; p24_profile_read waits
- * for the last call and returns the four durations in milliseconds into a HOST array.  Process-global. */
+/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its three
+ * kernels (anchor_pass, gt_match, resolve_loss) on the launching stream; p24_profile_read waits
+ * for the last call and returns the three durations in milliseconds into a HOST array.  Process-global. */
 int p24_profile_enable(int on);
-int p24_profile_read(float* h_ms4);
+int p24_profile_read(float* h_ms3);
 
 #ifdef __cplusplus
 }
