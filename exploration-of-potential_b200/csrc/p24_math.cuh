@@ -195,12 +195,43 @@ __device__ __forceinline__ int p24_angle_test_fast(const float* __restrict__ vx,
     return 0;
 }
 
+// reference-order evaluation, kept out of line (rare) so that it does not inflate the callers' registers
+__device__ __noinline__ bool p24_in_polygon_exact(const float* vx, const float* vy, float xc, float yc) {
+    float acc = 0.0f;
+    float sx = vx[0] - xc, sy = vy[0] - yc;
+#pragma unroll 1
+    for (int k = 0; k < P24_RAYS; ++k) {
+        const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
+        const float ex = vx[k2] - xc, ey = vy[k2] - yc;
+        const float cross = (sx * ey) - (ex * sy);
+        const float dot = (sx * ex) + (sy * ey);
+        acc = acc + (atan2f(fabsf(cross), dot) * P24_RAD2DEG);
+        sx = ex;
+        sy = ey;
+    }
+    return acc >= 350.0f;
+}
+
 // exact decision, fast path first
 __device__ __forceinline__ bool p24_in_polygon(const float* __restrict__ vx, const float* __restrict__ vy, float xc,
                                                float yc) {
     const int r = p24_angle_test_fast(vx, vy, xc, yc);
     if (r != 2) return r == 1;
-    return p24_angle_sum(vx, vy, xc, yc) >= 350.0f;
+    return p24_in_polygon_exact(vx, vy, xc, yc);
+}
+
+// one edge term of the reference's angle sum (losses.py:572-587), for lane-parallel evaluation
+__device__ __forceinline__ float p24_edge_angle(float sx, float sy, float ex, float ey) {
+    const float cross = (sx * ey) - (ex * sy);
+    const float dot = (sx * ex) + (sy * ey);
+    return atan2f(fabsf(cross), dot) * P24_RAD2DEG;
+}
+
+// upper bound of one ray's loss in fast arithmetic: exact (to ~1e-6) for apart rays, >= the loss of partial
+// rays (2 - uni/cs with the apart formula) and of nested rays (<= 1).  DESIGN.md "top-10 bracket".
+__device__ __forceinline__ float p24_ray_loss_ub(float rg, float rp, float d) {
+    const float q = (rg + rp) + d;
+    return fmaxf(1.0f, 2.0f - __fdividef(4.0f * fmaf(rg, rg, rp * rp), q * q));
 }
 
 // ---------------------------------------------------------------------------------------------

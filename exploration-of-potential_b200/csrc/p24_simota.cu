@@ -6,15 +6,18 @@
 //   Loss_Function.dynamic_k_matching                                 models/losses.py:444-494
 //   the loss sums and re-weighting of Loss_Function.forward          models/losses.py:246-345
 //
-// Kernel chain (all on the caller's stream, no host synchronisation):
-//   k_anchor_pass  one CTA per 256-anchor tile: the ONE pass over the head output (coalesced reads of the
-//                  27 geometry channels of every row).  Builds the image's GT records, the candidate mask
-//                  (polygon test OR centre window) with geometric pruning and an atan2-free angle test,
-//                  the per-GT centre-window lists, the compacted candidate list and sum BCEWithLogits(obj, 0)
-//   k_gt_match     one CTA per GT: dynamic k from the top-10-largest pair values over the candidates
-//                  (bracketed by exact seed values and a monotone upper bound; exact evaluation of the few
-//                  pairs the bound cannot exclude otherwise); exact cost of the GT's valid (in polygon AND in
-//                  window) pairs, the k smallest -> claims (spill into the penalised regime when too few)
+// Kernel chain (caller's stream, no host synchronisation, programmatic dependent launch between stages):
+//   k_gt_prep      one CTA per image: nlabel and the per-GT records (vertices, ray lengths, safe accept /
+//                  reject radii of the polygon test)
+//   k_anchor_pass  one CTA per 256-anchor tile: the ONE pass over the head output (cp.async reads of the
+//                  27 geometry channels of every row).  Candidate mask (polygon test OR centre window) with
+//                  geometric pruning and an atan2-free angle test, the per-GT centre-window lists, the
+//                  compacted candidate list and sum BCEWithLogits(obj, 0)
+//   k_gt_match     one CTA per GT, work split into 8-lane group tasks: dynamic k from the top-10-largest pair
+//                  values over the candidates (bracketed by exact seed values and a monotone upper bound;
+//                  bound-filtered exact evaluation otherwise); polygon test, exact pair value and cost of the
+//                  GT's centre-window anchors, the k smallest -> claims (spill into the penalised regime when
+//                  there are too few)
 //   k_resolve_loss one CTA per tile: conflict resolution (argmin over all GTs), fg_mask / matched_gt /
 //                  pred_iou, the 28 loss sums; the last CTA reduces them in a fixed order and, when asked,
 //                  applies the normalisation and the stateful re-weighting (losses.py:280-345)
@@ -61,79 +64,129 @@ struct Params {
     int tiles;
 };
 
-// -------------------------------------------------------------------------------------------
-// GT records of one image, built by every CTA of the anchor pass into shared memory
-// -------------------------------------------------------------------------------------------
-// nlabel = (labels.sum(2) > 0).sum(1)   losses.py:190 ; the first n rows are the GTs (losses.py:219-220)
-__device__ int count_labels(const Params& p, const float* lab, int* s_tmp) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (p.flags & P24_F_ALL_ROWS) return p.Lmax;
-    if (tid == 0) *s_tmp = 0;
-    __syncthreads();
-    int local = 0;
-    for (int r = warp; r < p.Lmax; r += P24_WARPS) {
-        const float* row = lab + (long long)r * p.lab_row_stride;
-        double s = (double)row[lane];
-        if (lane + 32 < 51) s += (double)row[lane + 32];
-        s = warp_sum_d(s);
-        if ((float)s > 0.0f) ++local;
-    }
-    if (lane == 0 && local) atomicAdd(s_tmp, local);
-    __syncthreads();
-    return *s_tmp;
+#define MATCH_THREADS 384
+#define MATCH_WARPS (MATCH_THREADS / 32)
+#define MATCH_GROUPS (MATCH_THREADS / 8)
+
+__device__ __forceinline__ void pdl_wait() {
+#if __CUDA_ARCH__ >= 900
+    cudaGridDependencySynchronize();
+#endif
 }
 
-__device__ void build_gt_record(const float* __restrict__ row, float* __restrict__ rec) {
-    const float cx = row[1], cy = row[2];
-    float rgmax = 0.0f, rgmin = INFINITY, perim = 0.0f, rin = INFINITY;
-    bool inside = false;
-    float x = row[3], y = row[4];
-    const float x0 = x, y0 = y;
-#pragma unroll 4
-    for (int k = 0; k < P24_RAYS; ++k) {
-        const float x2 = (k == P24_RAYS - 1) ? x0 : row[5 + 2 * k];
-        const float y2 = (k == P24_RAYS - 1) ? y0 : row[6 + 2 * k];
-        rec[GT_VX + k] = x;
-        rec[GT_VY + k] = y;
+// ---- 8-lane group reductions (the group's own mask: groups of a warp may diverge) -----------------------
+__device__ __forceinline__ unsigned group_mask() { return 0xFFu << (threadIdx.x & 24); }
+__device__ __forceinline__ float group_sum(float v, unsigned m) {
+    v += __shfl_xor_sync(m, v, 1);
+    v += __shfl_xor_sync(m, v, 2);
+    v += __shfl_xor_sync(m, v, 4);
+    return v;
+}
+__device__ __forceinline__ float group_prod(float v, unsigned m) {
+    v *= __shfl_xor_sync(m, v, 1);
+    v *= __shfl_xor_sync(m, v, 2);
+    v *= __shfl_xor_sync(m, v, 4);
+    return v;
+}
+__device__ __forceinline__ int group_sum_i(int v, unsigned m) {
+    v += __shfl_xor_sync(m, v, 1);
+    v += __shfl_xor_sync(m, v, 2);
+    v += __shfl_xor_sync(m, v, 4);
+    return v;
+}
+
+// -------------------------------------------------------------------------------------------
+// k_gt_prep: nlabel + GT records, one CTA per image, one warp per GT (lanes over the 24 vertices)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(P24_THREADS) k_gt_prep(Params p) {
+    pdl_wait();
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* lab = p.labels + (long long)b * p.lab_img_stride;
+    // nlabel = (labels.sum(2) > 0).sum(1)   losses.py:190 ; the first n rows are the GTs (losses.py:219-220)
+    int local = 0;
+    for (int r = tid; r < p.Lmax; r += P24_THREADS) {
+        const float* row = lab + (long long)r * p.lab_row_stride;
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 51; ++c) s += (double)row[c];
+        local += ((float)s > 0.0f) ? 1 : 0;
+    }
+    __shared__ int s_n;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    local = warp_sum_i(local);
+    if (lane == 0 && local) atomicAdd(&s_n, local);
+    __syncthreads();
+    const int n = (p.flags & P24_F_ALL_ROWS) ? p.Lmax : s_n;
+    if (tid == 0) {
+        p.num_gt[b] = n;
+        p.num_fg[b] = 0;
+    }
+    for (int g = warp; g < n; g += P24_WARPS) {
+        const float* row = lab + (long long)g * p.lab_row_stride;
+        float* rec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
+        const float cx = row[1], cy = row[2];
+        const int k = lane < P24_RAYS ? lane : 0;
+        const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
+        const float x = row[3 + 2 * k], y = row[4 + 2 * k];
+        const float x2 = row[3 + 2 * k2], y2 = row[4 + 2 * k2];
         const float rg = p24_gt_radius(x - cx, y - cy);
-        rec[GT_RG + k] = rg;
-        rgmax = fmaxf(rgmax, rg);
-        rgmin = fminf(rgmin, rg);
         const float ex = x2 - x, ey = y2 - y;
         const float len2 = fmaf(ex, ex, ey * ey);
-        perim += sqrtf(len2);
+        float len = sqrtf(len2);
         // distance from the centre to the edge segment
         const float wx = cx - x, wy = cy - y;
         float tt = len2 > 0.0f ? __fdividef(fmaf(wx, ex, wy * ey), len2) : 0.0f;
         tt = fminf(fmaxf(tt, 0.0f), 1.0f);
         const float qx = wx - tt * ex, qy = wy - tt * ey;
-        rin = fminf(rin, sqrtf(fmaf(qx, qx, qy * qy)));
+        float rin = sqrtf(fmaf(qx, qx, qy * qy));
         // crossing-number parity of the centre
+        bool cross = false;
         if ((y > cy) != (y2 > cy)) {
             const float xi = fmaf(ex, __fdividef(cy - y, ey), x);
-            if (cx < xi) inside = !inside;
+            cross = cx < xi;
         }
-        x = x2;
-        y = y2;
+        float rgmax = rg, rgmin = rg;
+        if (lane >= P24_RAYS) {
+            len = 0.0f;
+            rin = INFINITY;
+            cross = false;
+            rgmax = 0.0f;
+            rgmin = INFINITY;
+        }
+        const unsigned par = __ballot_sync(0xffffffffu, cross);
+        const bool nan_any = __any_sync(0xffffffffu, !(rin == rin) && lane < P24_RAYS);
+        const float perim = warp_sum(len);
+        rgmax = warp_max(rgmax);
+        rgmin = -warp_max(-rgmin);
+        rin = -warp_max(-rin);
+        if (lane < P24_RAYS) {
+            rec[GT_VX + lane] = x;
+            rec[GT_VY + lane] = y;
+            rec[GT_RG + lane] = rg;
+        }
+        if (lane == 0) {
+            const bool inside = (__popc(par) & 1) != 0;
+            // A point inside a closed polygon has |winding| >= 1, so its total unsigned angle is >= 360 degrees:
+            // a disc around an interior centre that stays clear of every edge passes the >= 350 test (2 % + 0.01 px
+            // of slack covers the fp32 evaluation of the distances above).
+            float ra = (inside && !nan_any) ? fmaf(0.98f, rin, -0.01f) : 0.0f;
+            ra = fmaxf(ra, 0.0f);
+            // Outside, the angle sum is <= perimeter / distance-to-polygon (radians): it is < 349 degrees beyond
+            // rgmax + perimeter * (180/pi) / 349 (1 % slack).
+            const float rr = fmaf(perim * 1.01f, 57.29578f / 349.0f, rgmax) * 1.001f + 1e-2f;
+            float rrej2 = rr * rr;
+            if (!(rrej2 == rrej2)) rrej2 = INFINITY;  // NaN labels: never reject
+            rec[GT_CX] = cx;
+            rec[GT_CY] = cy;
+            rec[GT_RIN2] = ra * ra;
+            rec[GT_RREJ2] = rrej2;
+            rec[GT_CLS] = row[0];
+            rec[GT_RGMAX] = rgmax;
+            rec[GT_RGMIN] = rgmin;
+            rec[7] = 0.0f;
+        }
     }
-    // A point inside a closed polygon has |winding| >= 1, so its total unsigned angle is >= 360 degrees: a disc
-    // around an interior centre that stays clear of every edge passes the >= 350 test (2 % + 0.01 px of slack
-    // covers the fp32 evaluation of the distances above).
-    float ra = (inside && rin == rin) ? fmaf(0.98f, rin, -0.01f) : 0.0f;
-    ra = fmaxf(ra, 0.0f);
-    // Outside, the angle sum is <= perimeter / distance-to-polygon (radians): it is < 349 degrees beyond
-    // rgmax + perimeter * (180/pi) / 349 (1 % slack).
-    const float rr = fmaf(perim * 1.01f, 57.29578f / 349.0f, rgmax) * 1.001f + 1e-2f;
-    float rrej2 = rr * rr;
-    if (!(rrej2 == rrej2)) rrej2 = INFINITY;  // NaN labels: never reject
-    rec[GT_CX] = cx;
-    rec[GT_CY] = cy;
-    rec[GT_RIN2] = ra * ra;
-    rec[GT_RREJ2] = rrej2;
-    rec[GT_CLS] = row[0];
-    rec[GT_RGMAX] = rgmax;
-    rec[GT_RGMIN] = rgmin;
-    rec[7] = 0.0f;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -143,8 +196,22 @@ __device__ void build_gt_record(const float* __restrict__ row, float* __restrict
 __device__ float pair_value_row(const float* __restrict__ rec, const float* __restrict__ row) {
     const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
     float s = 0.0f;
-#pragma unroll 4
+#pragma unroll 1
     for (int k = 0; k < P24_RAYS; ++k) s = s + p24_ray_loss(rec[GT_RG + k], row[2 + k], d);
+    return (s / 24.0f) / 2.0f;
+}
+
+// the same value by an 8-lane group (3 rays per lane, fixed reduction tree); every lane of the group returns it
+__device__ __forceinline__ float group_pair_value(const float* __restrict__ rec, const float* __restrict__ row, unsigned m) {
+    const int sub = threadIdx.x & 7;
+    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int k = sub * 3 + q;
+        s = s + p24_ray_loss(rec[GT_RG + k], row[2 + k], d);
+    }
+    s = group_sum(s, m);
     return (s / 24.0f) / 2.0f;
 }
 
@@ -153,7 +220,7 @@ __device__ __forceinline__ int gt_class(const float* rec, int nc) {
     return min(max(c, 0), nc - 1);
 }
 
-// Warp-cooperative sum over all classes of BCE(p_j, 0) (losses.py:406-416) in product form; every lane returns it.
+// Sum over all classes of BCE(p_j, 0) (losses.py:406-416) in product form, by the 32 lanes of a warp
 __device__ float warp_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1) {
     const int lane = threadIdx.x & 31;
     float prod = 1.0f;
@@ -170,7 +237,24 @@ __device__ float warp_cls_neg_sum(const float* __restrict__ cls, int nc, float e
     return -logf(prod) + 100.0f * (float)nsat;
 }
 
-// single-thread version of the same sum (rare slow paths)
+// ... by the 8 lanes of a group
+__device__ float group_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1, unsigned m) {
+    const int sub = threadIdx.x & 7;
+    float prod = 1.0f;
+    int nsat = 0;
+    for (int j = sub; j < nc; j += 8) p24_neg_factor(cls[j], eo1, prod, nsat);
+    prod = group_prod(prod, m);
+    nsat = group_sum_i(nsat, m);
+    if (!(prod > 1e-30f)) {
+        const float obj_sig = 1.0f / eo1;
+        float s = 0.0f;
+        for (int j = sub; j < nc; j += 8) s += p24_bce_neg(p24_joint_prob(cls[j], obj_sig));
+        return group_sum(s, m);
+    }
+    return -logf(prod) + 100.0f * (float)nsat;
+}
+
+// ... by a single thread (rare slow paths)
 __device__ float thread_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1) {
     const float obj_sig = 1.0f / eo1;
     float s = 0.0f;
@@ -188,10 +272,17 @@ __device__ __forceinline__ float cls_cost_from(float neg_sum, float cls_logit_c,
 // k_anchor_pass
 // -------------------------------------------------------------------------------------------
 #define ITEM_CAP 2048
-#define G_CHUNK 8
 #define ROW_CH 27  // channels 0..26 of a head row are read here: centre, 24 radii, objectness
 
-__global__ void __launch_bounds__(P24_THREADS) k_anchor_pass(Params p) {
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+__global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
     extern __shared__ float4 s_dyn4[];
     float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC]
     const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
@@ -202,37 +293,41 @@ __global__ void __launch_bounds__(P24_THREADS) k_anchor_pass(Params p) {
     __shared__ float s_row[P24_WARPS][ROW_CH][33];
     __shared__ unsigned s_items[ITEM_CAP];
     __shared__ int s_cand[P24_THREADS];
-    __shared__ int s_nitems, s_tmp;
+    __shared__ int s_nitems;
     __shared__ int s_wcnt[P24_WARPS];
     __shared__ double s_red[P24_WARPS];
 
-    // ---- GT records -----------------------------------------------------------------------------
-    const float* lab = p.labels + (long long)b * p.lab_img_stride;
-    const int n = count_labels(p, lab, &s_tmp);
-    for (int g = tid; g < n; g += P24_THREADS) build_gt_record(lab + (long long)g * p.lab_row_stride, s_gt + g * GT_REC);
-    s_cand[tid] = 0;
-
-    // ---- coalesced load of the tile's rows: each warp reads its 32 rows, 27 contiguous floats at a time --
+    // ---- the tile's rows: each warp reads its 32 rows, 27 contiguous floats per row (coalesced), straight into
+    // shared memory with cp.async; they do not depend on the previous kernel, so they are issued before the
+    // programmatic-dependency wait -----------------------------------------------------------------------------
     const float* img = p.outputs + (long long)b * p.img_stride;
     {
         const int a0 = tile * P24_THREADS + warp * 32;
         const int nrow = min(32, p.A - a0);
         if (lane < ROW_CH) {
-#pragma unroll 8
-            for (int r = 0; r < nrow; ++r) s_row[warp][lane][r] = img[(long long)(a0 + r) * p.row_stride + lane];
+            for (int r = 0; r < nrow; ++r) cp_async4(&s_row[warp][lane][r], img + (long long)(a0 + r) * p.row_stride + lane);
         }
     }
+    float st = 1.f, xs = 0.f, ys = 0.f;
+    if (active) {
+        st = p.strides[a];
+        xs = p.x_shifts[a];
+        ys = p.y_shifts[a];
+    }
+    if (tid == 0) s_nitems = 0;
+    s_cand[tid] = 0;
+    pdl_wait();
+    const int n = p.num_gt[b];
+    {
+        const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
+        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) s_dyn4[i] = gsrc[i];
+    }
+    cp_async_wait_all();
     __syncthreads();
-    if (tile == 0) {
-        float* gdst = p.gt_rec + (long long)b * p.Lmax * GT_REC;
-        for (int i = tid; i < n * GT_REC; i += P24_THREADS) gdst[i] = s_gt[i];
-        if (tid == 0) {
-            p.num_gt[b] = n;
-            p.num_fg[b] = 0;
-        }
-    }
+
     float pcx = 0.f, pcy = 0.f, rpmax = 0.f, rpmin = INFINITY, obj = 0.f;
-    float xc = 0.f, yc = 0.f, st = 1.f;
+    const float xc = p24_anchor_centre(xs, st);
+    const float yc = p24_anchor_centre(ys, st);
     if (active) {
         pcx = s_row[warp][0][lane];
         pcy = s_row[warp][1][lane];
@@ -243,9 +338,6 @@ __global__ void __launch_bounds__(P24_THREADS) k_anchor_pass(Params p) {
             rpmin = fminf(rpmin, v);
         }
         obj = s_row[warp][26][lane];
-        st = p.strides[a];
-        xc = p24_anchor_centre(p.x_shifts[a], st);
-        yc = p24_anchor_centre(p.y_shifts[a], st);
     }
     double objpart = active ? (double)p24_bce_logits(obj, 0.0f) : 0.0;
 
@@ -268,44 +360,51 @@ __global__ void __launch_bounds__(P24_THREADS) k_anchor_pass(Params p) {
     }
     const bool no_prune = (p.flags & P24_F_NO_PRUNE) != 0;
 
-    // ---- pass 2: anchors not yet accepted need a polygon test against every GT whose reject radius they
-    // are inside; the tests are compacted into a work list so that all threads stay busy -----------------
-    for (int g0 = 0; g0 < n; g0 += G_CHUNK) {
-        if (tid == 0) s_nitems = 0;
-        __syncthreads();
-        if (active && (!cheap || no_prune)) {
-            const int g1 = min(g0 + G_CHUNK, n);
-            for (int g = g0; g < g1; ++g) {
-                const float4 h = s_dyn4[g * (GT_REC / 4)];
-                const float dx = h.x - xc, dy = h.y - yc;
-                const float d2 = fmaf(dx, dx, dy * dy);
-                if (no_prune || (d2 <= h.w && !(d2 < h.z)))
-                    s_items[atomicAdd(&s_nitems, 1)] = (unsigned)tid | ((unsigned)g << 8);
+    // ---- pass 2: anchors not yet accepted need a polygon test against every GT whose reject radius they are
+    // inside; the tests go to a work list so that all threads stay busy (a full list is handled in place) --------
+    bool mine = false;
+    if (active && (!cheap || no_prune)) {
+        for (int g = 0; g < n; ++g) {
+            const float4 h = s_dyn4[g * (GT_REC / 4)];
+            const float dx = h.x - xc, dy = h.y - yc;
+            const float d2 = fmaf(dx, dx, dy * dy);
+            if (no_prune || d2 <= h.w) {
+                const int slot = atomicAdd(&s_nitems, 1);
+                if (slot < ITEM_CAP) {
+                    s_items[slot] = (unsigned)tid | ((unsigned)g << 8);
+                } else if (!mine) {
+                    const float* rec = s_gt + g * GT_REC;
+                    mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
+                                    : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
+                }
             }
         }
-        __syncthreads();
-        const int nitems = s_nitems;
-        for (int i = tid; i < nitems; i += P24_THREADS) {
-            const unsigned it = s_items[i];
-            const int al = it & 0xFF;
-            if (((volatile int*)s_cand)[al]) continue;  // already a candidate through another GT
-            const int g = it >> 8;
-            const float* rec = s_gt + g * GT_REC;
-            const int aa = tile * P24_THREADS + al;
-            const float st2 = p.strides[aa];
-            const float axc = p24_anchor_centre(p.x_shifts[aa], st2);
-            const float ayc = p24_anchor_centre(p.y_shifts[aa], st2);
-            const bool in = no_prune ? (p24_angle_sum(rec + GT_VX, rec + GT_VY, axc, ayc) >= 350.0f)
-                                     : p24_in_polygon(rec + GT_VX, rec + GT_VY, axc, ayc);
-            if (in) s_cand[al] = 1;
-        }
-        __syncthreads();
     }
+    if (mine) s_cand[tid] = 1;
+    __syncthreads();
+    const int nitems = min(s_nitems, ITEM_CAP);
+    for (int i = tid; i < nitems; i += P24_THREADS) {
+        const unsigned it = s_items[i];
+        const int al = it & 0xFF;
+        if (((volatile int*)s_cand)[al]) continue;  // already a candidate through another GT
+        const int g = it >> 8;
+        const float* rec = s_gt + g * GT_REC;
+        const int aa = tile * P24_THREADS + al;
+        const float st2 = p.strides[aa];
+        const float axc = p24_anchor_centre(p.x_shifts[aa], st2);
+        const float ayc = p24_anchor_centre(p.y_shifts[aa], st2);
+        const bool in = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, axc, ayc)
+                                 : p24_in_polygon(rec + GT_VX, rec + GT_VY, axc, ayc);
+        if (in) s_cand[al] = 1;
+    }
+    __syncthreads();
 
     // ---- compacted candidate list of the tile (deterministic order) + per-anchor scratch reset ----------
     const bool cand = active && (n > 0) && (cheap || s_cand[tid]);
     const unsigned bal = __ballot_sync(0xffffffffu, cand);
     if (lane == 0) s_wcnt[warp] = __popc(bal);
+    objpart = warp_sum_d(objpart);
+    if (lane == 0) s_red[warp] = objpart;
     __syncthreads();
     int base = 0, total = 0;
 #pragma unroll
@@ -320,13 +419,9 @@ __global__ void __launch_bounds__(P24_THREADS) k_anchor_pass(Params p) {
         // a prediction with a tiny radius disables the bound filter for its pairs: rpmax = +inf
         p.clist[blk * P24_THREADS + rank] = make_float4(pcx, pcy, rpmin < 0.25f ? INFINITY : rpmax, __int_as_float(a));
     }
-    if (tid == 0) p.ccount[blk] = total;
     if (active) p.claim_cnt[(long long)b * p.A + a] = 0;
-
-    objpart = warp_sum_d(objpart);
-    if (lane == 0) s_red[warp] = objpart;
-    __syncthreads();
     if (tid == 0) {
+        p.ccount[blk] = total;
         double t = 0.0;
         for (int w = 0; w < P24_WARPS; ++w) t += s_red[w];
         p.obj_part[blk] = t;
@@ -337,8 +432,8 @@ __global__ void __launch_bounds__(P24_THREADS) k_anchor_pass(Params p) {
 // k_gt_match
 // -------------------------------------------------------------------------------------------
 #define HIT_CAP 4096
-#define SURV_CAP (HIT_CAP + 1024)
-#define N_SEED 16
+#define EV_CAP 256
+#define N_SEED (2 * MATCH_WARPS)
 
 // Upper bound of the pair value as a function of t = rpmax + d: any ray has loss <= max(1, 2 - 4 rg^2 / (rg + rp + d)^2)
 // (nested rays: loss <= 1; partial and apart rays: loss <= 2 - uni/cs; DESIGN.md "top-10 bracket").
@@ -352,52 +447,84 @@ __device__ __forceinline__ float bound_H(float rg_lane, float t, int lane) {
     return warp_sum(term) * (1.0f / 48.0f);
 }
 
-// select the `want` largest of s_surv[0..n) into s_top (descending); block-wide, returns count
-__device__ int select_top(float* s_surv, int n, int want, float* s_top, KV* s_kv) {
+struct MatchShared {
+    float rec[GT_REC];
+    int hit[HIT_CAP];      // slow path: anchors that survive the bound filter
+    float hub[HIT_CAP];    // their upper bounds, later their exact values
+    float top[P24_TOPK];
+    int seed[N_SEED];
+    float seedv[N_SEED];
+    KV kv[MATCH_WARPS];
+    float wmax[MATCH_WARPS];
+    int red[MATCH_WARPS];
+    int cnt, nhit, k, slow, nvalid, nev;
+    float T, tau, thr;
+    float ev[EV_CAP + P24_TOPK];  // slow path: exact values found by the first refinement round
+    int wanchor[P24_VCAP];
+    float wcost[P24_VCAP];  // +inf: not valid
+};
+
+template <bool MAX>
+__device__ __forceinline__ KV match_block_select(KV x, KV* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x = warp_select<MAX>(x);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = x;
+    __syncthreads();
+    KV y = s_red[lane < MATCH_WARPS ? lane : 0];
+    y = warp_select<MAX>(y);
+    return y;
+}
+
+__device__ int match_block_count(bool pred, int* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = __popc(__ballot_sync(0xffffffffu, pred));
+    __syncthreads();
+    if (lane == 0) s_red[warp] = c;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < MATCH_WARPS; ++w) t += s_red[w];
+    return t;
+}
+
+// select the `want` largest of vals[0..n) into s_top (descending); block-wide, returns count.  Destroys vals.
+__device__ int select_top(float* vals, int n, int want, float* s_top, KV* s_kv) {
     const int m = min(want, n);
     for (int r = 0; r < m; ++r) {
         KV best = {P24_NEG_INF, 0x7fffffff};
-        for (int i = threadIdx.x; i < n; i += P24_THREADS) {
-            const float v = s_surv[i];
+        for (int i = threadIdx.x; i < n; i += MATCH_THREADS) {
+            const float v = vals[i];
             if (kv_gt(v, i, best.v, best.i)) {
                 best.v = v;
                 best.i = i;
             }
         }
-        best = block_select<true>(best, s_kv);
+        best = match_block_select<true>(best, s_kv);
         if (threadIdx.x == 0) {
             s_top[r] = best.v;
-            if (best.i < n) s_surv[best.i] = P24_NEG_INF;
+            if (best.i < n) vals[best.i] = P24_NEG_INF;
         }
         __syncthreads();
     }
     return m;
 }
 
-struct MatchShared {
-    float rec[GT_REC];
-    int hit[HIT_CAP];
-    float surv[SURV_CAP];
-    float top[P24_TOPK];
-    int seed[N_SEED];
-    float seedv[N_SEED];
-    KV kv[P24_WARPS];
-    float wmax[P24_WARPS];
-    int cnt, nhit, nsurv, k, slow;
-    float T, tau;
-    int wanchor[P24_VCAP];
-    float wcost[P24_VCAP];
-    float wval[P24_VCAP];
-};
-
-// Exact top-kc sum when the bracket is not conclusive: evaluate every pair the bound cannot exclude.
+// Exact top-kc sum when the bracket is not conclusive.
+//  1. candidates whose scalar bound H(t) cannot reach the seed threshold are dropped (one compare per pair);
+//  2. the rest get a per-ray upper bound ub (fast arithmetic, exact to ~1e-6 for far pairs); ub < T - eps drops more;
+//  3. the ~24 largest ub are evaluated exactly -> a tighter threshold T'; whatever still has ub >= T' - eps is
+//     evaluated exactly as well; the top-kc exact values are summed in descending order (torch.topk order).
+// Lists that overflow HIT_CAP are processed in chunks, carrying the best kc exact values forward.
 __device__ __noinline__ float exact_topk_sum(const Params& p, MatchShared& S, int b, int kc, float T_seed) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned gm = group_mask();
+    const int grp = tid >> 3, sub = tid & 7;
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     const float* img = p.outputs + (long long)b * p.img_stride;
+    const bool filter = !(p.flags & P24_F_NO_FILTER) && T_seed > P24_NEG_INF && S.rec[GT_RGMIN] >= 0.25f;
     if (warp == 0) {
         float tau = P24_NEG_INF;
-        const bool filter = !(p.flags & P24_F_NO_FILTER) && T_seed > P24_NEG_INF && S.rec[GT_RGMIN] >= 0.25f;
         if (filter) {
             const float target = T_seed - 2e-5f;
             const float rgl = lane < P24_RAYS ? S.rec[GT_RG + lane] : 0.0f;
@@ -414,42 +541,147 @@ __device__ __noinline__ float exact_topk_sum(const Params& p, MatchShared& S, in
         if (lane == 0) {
             S.T = filter ? T_seed : P24_NEG_INF;
             S.tau = tau;
-            S.nsurv = 0;
         }
     }
+    int ncarry = 0;  // exact values carried in S.top[0..ncarry)
     __syncthreads();
-    const float T = S.T, tau = S.tau;
-    for (int t0 = 0; t0 < p.tiles; t0 += HIT_CAP / P24_THREADS) {
-        if (tid == 0) S.nhit = 0;
+    const float tau = S.tau;
+    const int tiles_per_chunk = (HIT_CAP - P24_TOPK) / P24_THREADS;
+    for (int t0 = 0; t0 < p.tiles; t0 += tiles_per_chunk) {
+        const int t1 = min(t0 + tiles_per_chunk, p.tiles);
+        float T = S.T;
+        if (tid == 0) {
+            S.nhit = 0;
+            S.nev = 0;
+        }
         __syncthreads();
-        const int t1 = min(t0 + HIT_CAP / P24_THREADS, p.tiles);
-        for (int tl = t0 + warp; tl < t1; tl += P24_WARPS) {
+        // 1 + 2: bound filters
+        for (int tl = t0 + warp; tl < t1; tl += MATCH_WARPS) {
             const long long blk = (long long)b * p.tiles + tl;
             const int c = p.ccount[blk];
             for (int i = lane; i < c; i += 32) {
                 const float4 q = p.clist[blk * P24_THREADS + i];
                 const float dx = gcx - q.x, dy = gcy - q.y;
-                const float t = q.z + sqrtf(fmaf(dx, dx, dy * dy));
-                if (t >= tau || !(t == t)) S.hit[atomicAdd(&S.nhit, 1)] = __float_as_int(q.w);
+                const float d = sqrtf(fmaf(dx, dx, dy * dy));
+                const float t = q.z + d;
+                if (!(t >= tau || !(t == t))) continue;
+                const int a = __float_as_int(q.w);
+                float ub = P24_POS_INF;
+                if (filter && q.z < 60000.0f) {
+                    const float* row = img + (long long)a * p.row_stride;
+                    float s = 0.0f;
+#pragma unroll 4
+                    for (int k = 0; k < P24_RAYS; ++k) s += p24_ray_loss_ub(S.rec[GT_RG + k], row[2 + k], d);
+                    ub = s * (1.0f / 48.0f) + 2e-5f;
+                    if (ub < T) continue;
+                    if (!(ub == ub)) ub = P24_POS_INF;
+                }
+                const int slot = atomicAdd(&S.nhit, 1);
+                S.hit[slot] = a;
+                S.hub[slot] = ub;
             }
         }
         __syncthreads();
-        const int nhit = S.nhit;
-        for (int i = tid; i < nhit; i += P24_THREADS) {
-            const float v = pair_value_row(S.rec, img + (long long)S.hit[i] * p.row_stride);
-            if (v >= T || !(v == v)) S.surv[atomicAdd(&S.nsurv, 1)] = v;
+        int nhit = S.nhit;
+        // 3a: threshold thr such that about 24..64 entries have ub >= thr (bisection on the count)
+        float thr = P24_NEG_INF;
+        if (filter && nhit > 64) {
+            float lo = T, hi = 1.0f + 1e-3f;
+            for (int it = 0; it < 14; ++it) {
+                const float mid = 0.5f * (lo + hi);
+                int c = 0;
+                for (int i = tid; i < nhit; i += MATCH_THREADS) c += (S.hub[i] >= mid) ? 1 : 0;
+                // block sum of c
+                c = warp_sum_i(c);
+                __syncthreads();
+                if (lane == 0) S.red[warp] = c;
+                __syncthreads();
+                int tot = 0;
+#pragma unroll
+                for (int w = 0; w < MATCH_WARPS; ++w) tot += S.red[w];
+                if (tot >= 24) lo = mid;
+                else hi = mid;
+            }
+            thr = lo;
+        }
+        // 3b: exact values of the entries with ub >= thr (8-lane groups); others keep their bound, tagged negative
+        for (int i0 = 0; i0 < nhit; i0 += MATCH_GROUPS) {
+            const int i = i0 + grp;
+            if (i < nhit) {
+                const float ub = S.hub[i];
+                if (ub >= thr) {
+                    const float v = group_pair_value(S.rec, img + (long long)S.hit[i] * p.row_stride, gm);
+                    if (sub == 0) {
+                        const float vv = (v == v) ? v : P24_POS_INF;  // NaN pairs sort first, like torch.topk
+                        S.hub[i] = vv;
+                        S.hit[i] = -1;  // evaluated
+                        const int e = atomicAdd(&S.nev, 1);
+                        if (e < EV_CAP) S.ev[e] = vv;
+                    }
+                }
+            }
         }
         __syncthreads();
-        if (S.nsurv > 1024 && t1 < p.tiles) {
-            const int m = select_top(S.surv, S.nsurv, kc, S.top, S.kv);
-            if (tid < m) S.surv[tid] = S.top[tid];
-            if (tid == 0) S.nsurv = m;
+        // tighter threshold T' = kc-th largest exact value so far (carried + evaluated)
+        if (filter && nhit > 64) {
+            if (warp == 0) {
+                const int nev = min(S.nev, EV_CAP);
+                for (int i = lane; i < ncarry; i += 32) S.ev[nev + i] = S.top[i];
+                __syncwarp();
+                const int tot = nev + ncarry;
+                float kth = P24_NEG_INF;
+                int got = 0;
+                for (int r = 0; r < kc; ++r) {
+                    KV best = {P24_NEG_INF, 0x7fffffff};
+                    for (int i = lane; i < tot; i += 32) {
+                        const float v = S.ev[i];
+                        if (kv_gt(v, i, best.v, best.i)) {
+                            best.v = v;
+                            best.i = i;
+                        }
+                    }
+                    best = warp_select<true>(best);
+                    if (best.i == 0x7fffffff) break;
+                    if (lane == 0) S.ev[best.i] = P24_NEG_INF;
+                    __syncwarp();
+                    kth = best.v;
+                    ++got;
+                }
+                if (lane == 0) S.thr = (got >= kc) ? kth : P24_NEG_INF;
+            }
+            __syncthreads();
+            const float T2 = fmaxf(S.thr - 2e-5f, T);
+            // 3c: entries not yet evaluated whose bound still reaches T2
+            for (int i0 = 0; i0 < nhit; i0 += MATCH_GROUPS) {
+                const int i = i0 + grp;
+                if (i < nhit) {
+                    const int a = S.hit[i];
+                    if (a >= 0 && S.hub[i] >= T2) {
+                        const float v = group_pair_value(S.rec, img + (long long)a * p.row_stride, gm);
+                        if (sub == 0) {
+                            S.hub[i] = (v == v) ? v : P24_POS_INF;
+                            S.hit[i] = -1;
+                        }
+                    }
+                }
+            }
             __syncthreads();
         }
+        // keep exact values only, append the carried ones, select the best kc
+        for (int i = tid; i < nhit; i += MATCH_THREADS)
+            if (S.hit[i] >= 0) S.hub[i] = P24_NEG_INF;
+        if (tid < ncarry) S.hub[nhit + tid] = S.top[tid];
+        __syncthreads();
+        nhit += ncarry;
+        ncarry = select_top(S.hub, nhit, kc, S.top, S.kv);
+        if (ncarry == kc && filter && tid == 0) S.T = fmaxf(S.T, S.top[kc - 1] - 2e-5f);
+        __syncthreads();
     }
-    const int m = select_top(S.surv, S.nsurv, kc, S.top, S.kv);
     float ksum = 0.0f;
-    for (int i = 0; i < m; ++i) ksum = ksum + S.top[i];
+    for (int i = 0; i < ncarry; ++i) {
+        const float v = S.top[i];
+        ksum = ksum + (v == P24_POS_INF ? NAN : v);
+    }
     return ksum;
 }
 
@@ -469,10 +701,10 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
     for (int tl = 0; tl < p.tiles; ++tl) {
         const long long blk = (long long)b * p.tiles + tl;
         const int cc = p.ccount[blk];
-        for (int i = tid; i < cc; i += P24_THREADS) {
+        for (int i = tid; i < cc; i += MATCH_THREADS) {
             const int a = __float_as_int(p.clist[blk * P24_THREADS + i].w);
             bool isvalid = false;
-            for (int j = 0; j < nwin; ++j) isvalid |= (S.wanchor[j] == a && !(S.wval[j] < 0.0f));
+            for (int j = 0; j < nwin; ++j) isvalid |= (S.wanchor[j] == a && S.wcost[j] != P24_POS_INF);
             if (isvalid) continue;
             const float* row = img + (long long)a * p.row_stride;
             const float eo1 = 1.0f + expf(-row[26]);
@@ -498,7 +730,7 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
     }
     for (int r = 0; r < need; ++r) {
         const KV head = {lv[0], li[0]};
-        const KV win = block_select<false>(head, S.kv);
+        const KV win = match_block_select<false>(head, S.kv);
         if (win.i == 0x7fffffff) break;  // fewer candidates than needed
         if (li[0] == win.i && lv[0] == win.v) {
             const long long o = (long long)b * p.A + win.i;
@@ -515,7 +747,8 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
     }
 }
 
-__global__ void __launch_bounds__(P24_THREADS) k_gt_match(Params p) {
+__global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
+    pdl_wait();
     const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int n = p.num_gt[b];
@@ -524,17 +757,23 @@ __global__ void __launch_bounds__(P24_THREADS) k_gt_match(Params p) {
         return;
     }
     __shared__ MatchShared S;
-
-    if (tid < GT_REC) S.rec[tid] = p.gt_rec[((long long)b * p.Lmax + g) * GT_REC + tid];
+    const int wslot = b * p.Lmax + g;
+    if (tid < GT_REC) S.rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
+    const int nwin = min(p.wcount[wslot], P24_VCAP);
+    if (tid < P24_VCAP) {
+        S.wanchor[tid] = tid < nwin ? p.wlist[(long long)wslot * P24_VCAP + tid] : 0x7fffffff;
+        S.wcost[tid] = P24_POS_INF;
+    }
     if (tid == 0) S.cnt = 0;
     __syncthreads();
+    if (tid == 0) p.wcount[wslot] = 0;  // leave the list empty for the next call
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     const float* img = p.outputs + (long long)b * p.img_stride;
 
     // ---- scan the image's candidates: count, largest t, two seeds per warp -----------------------------
     float t1 = P24_NEG_INF, t2 = P24_NEG_INF;
     int a1 = 0x7fffffff, a2 = 0x7fffffff, cnt = 0;
-    for (int tl = warp; tl < p.tiles; tl += P24_WARPS) {
+    for (int tl = warp; tl < p.tiles; tl += MATCH_WARPS) {
         const long long blk = (long long)b * p.tiles + tl;
         const int c = p.ccount[blk];
         cnt += c;  // every lane of the warp holds the same running count
@@ -568,36 +807,71 @@ __global__ void __launch_bounds__(P24_THREADS) k_gt_match(Params p) {
     __syncthreads();
     const int ncand = S.cnt;
     const int kc = min(P24_TOPK, ncand);  // losses.py:452
-    if (tid < N_SEED) {
-        const int sa = S.seed[tid];
-        S.seedv[tid] = (sa >= 0) ? pair_value_row(S.rec, img + (long long)sa * p.row_stride) : P24_NEG_INF;
+
+    // ---- group tasks: [0, N_SEED) exact value of a seed; [N_SEED, N_SEED + nwin) a centre-window anchor:
+    // polygon test (reference-order edge terms, 3 per lane), exact pair value and cost when inside ----------
+    {
+        const unsigned gm = group_mask();
+        const int grp = tid >> 3, sub = tid & 7;
+        const int c = gt_class(S.rec, p.nc);
+        const int ntask = N_SEED + nwin;
+        for (int task = grp; task < ntask; task += MATCH_GROUPS) {
+            if (task < N_SEED) {
+                const int sa = S.seed[task];
+                float v = P24_NEG_INF;
+                if (sa >= 0) v = group_pair_value(S.rec, img + (long long)sa * p.row_stride, gm);
+                if (sub == 0) S.seedv[task] = v;
+                continue;
+            }
+            const int wi = task - N_SEED;
+            const int a = S.wanchor[wi];
+            const float st = p.strides[a];
+            const float xc = p24_anchor_centre(p.x_shifts[a], st);
+            const float yc = p24_anchor_centre(p.y_shifts[a], st);
+            float ang = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int k = sub * 3 + q;
+                const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
+                ang = ang + p24_edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
+                                           S.rec[GT_VY + k2] - yc);
+            }
+            ang = group_sum(ang, gm);
+            if (!(ang >= 350.0f)) continue;  // losses.py:588
+            const float* row = img + (long long)a * p.row_stride;
+            const float v = group_pair_value(S.rec, row, gm);
+            const float eo1 = 1.0f + expf(-row[26]);
+            const float neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+            if (sub == 0) {
+                float cost = p24_cost(cls_cost_from(neg, row[27 + c], 1.0f / eo1), v, true);
+                if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
+                S.wcost[wi] = cost;
+            }
+        }
     }
     __syncthreads();
     // ---- bracket the top-10 sum: L = sum of the 10 best seed values <= S <= 10 * H(t_max) = U ------------
     if (warp == 0) {
+        const float sv = lane < N_SEED ? S.seedv[lane] : P24_NEG_INF;
+        int rank = 0, ns = 0;
+#pragma unroll
+        for (int j = 0; j < N_SEED; ++j) {
+            const float o = __shfl_sync(0xffffffffu, sv, j);
+            rank += kv_gt(o, j, sv, lane) ? 1 : 0;
+            ns += (o > P24_NEG_INF) ? 1 : 0;
+        }
         float T = P24_NEG_INF, L = 0.0f;
-        if (lane == 0) {
-            float sv[N_SEED];
-            int ns = 0;
-            for (int i = 0; i < N_SEED; ++i) {
-                const float v = S.seedv[i];
-                if (v > P24_NEG_INF) {
-                    int j = ns++;
-                    while (j > 0 && sv[j - 1] < v) {
-                        sv[j] = sv[j - 1];
-                        --j;
-                    }
-                    sv[j] = v;
-                }
-            }
-            if (kc == P24_TOPK && ns >= P24_TOPK) {
-                T = sv[P24_TOPK - 1];
-                for (int i = 0; i < P24_TOPK; ++i) L = L + sv[i];
+        if (kc == P24_TOPK && ns >= P24_TOPK) {
+            // sum in descending order, like the reference sums torch.topk's output
+#pragma unroll
+            for (int r = 0; r < P24_TOPK; ++r) {
+                const unsigned who = __ballot_sync(0xffffffffu, rank == r && lane < N_SEED);
+                const float v = __shfl_sync(0xffffffffu, sv, __ffs(who) - 1);
+                L = L + v;
+                T = v;
             }
         }
-        T = __shfl_sync(0xffffffffu, T, 0);
-        L = __shfl_sync(0xffffffffu, L, 0);
-        float tmax = lane < P24_WARPS ? S.wmax[lane] : P24_NEG_INF;
+        float tmax = lane < MATCH_WARPS ? S.wmax[lane] : P24_NEG_INF;
         tmax = warp_max(tmax);
         int slow = 1, k = 0;
         if (T > P24_NEG_INF && !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && tmax < 60000.0f) {
@@ -625,76 +899,31 @@ __global__ void __launch_bounds__(P24_THREADS) k_gt_match(Params p) {
         k = S.k;
     }
     k = min(k, ncand);  // torch.topk would raise beyond the candidate count; clamp instead
-    if (tid == 0) p.dyn_k[b * p.Lmax + g] = k;
+    if (tid == 0) p.dyn_k[wslot] = k;
 
-    // ---- the GT's centre-window anchors: polygon test, exact pair value and cost of the valid ones --------
-    const int wslot = b * p.Lmax + g;
-    const int nwin = min(p.wcount[wslot], P24_VCAP);
-    __syncthreads();
-    if (tid == 0) p.wcount[wslot] = 0;  // leave the list empty for the next call
-    if (tid < P24_VCAP) {
-        int a = 0x7fffffff;
-        float v = -1.0f;  // -1: not valid
-        if (tid < nwin) {
-            a = p.wlist[(long long)wslot * P24_VCAP + tid];
-            const float st = p.strides[a];
-            const float xc = p24_anchor_centre(p.x_shifts[a], st);
-            const float yc = p24_anchor_centre(p.y_shifts[a], st);
-            const bool in = (p.flags & P24_F_NO_PRUNE) ? (p24_angle_sum(S.rec + GT_VX, S.rec + GT_VY, xc, yc) >= 350.0f)
-                                                       : p24_in_polygon(S.rec + GT_VX, S.rec + GT_VY, xc, yc);
-            if (in) v = pair_value_row(S.rec, img + (long long)a * p.row_stride);
-        }
-        S.wanchor[tid] = a;
-        S.wval[tid] = v;
-        S.wcost[tid] = P24_POS_INF;
-    }
-    __syncthreads();
-    {
-        const int c = gt_class(S.rec, p.nc);
-        for (int i = warp; i < nwin; i += P24_WARPS) {
-            const float v = S.wval[i];
-            if (v < 0.0f) continue;  // not in the polygon
-            const float* row = img + (long long)S.wanchor[i] * p.row_stride;
-            const float eo1 = 1.0f + expf(-row[26]);
-            const float neg = warp_cls_neg_sum(row + 27, p.nc, eo1);
-            if (lane == 0) {
-                float cost = p24_cost(cls_cost_from(neg, row[27 + c], 1.0f / eo1), v, true);
-                if (!(cost == cost)) cost = 3.0e38f;  // NaN inputs: keep the pair selectable, last
-                S.wcost[i] = cost;
-            }
-        }
-    }
-    __syncthreads();
-    int nvalid = 0;
+    // ---- the k smallest costs of the valid pairs -> claims ------------------------------------------------
     if (warp == 0) {
+        int nvalid = 0;
         for (int i = lane; i < nwin; i += 32) nvalid += (S.wcost[i] < P24_POS_INF) ? 1 : 0;
         nvalid = warp_sum_i(nvalid);
         const int take = min(k, nvalid);
-        for (int r = 0; r < take; ++r) {
-            KV best = {P24_POS_INF, 0x7fffffff};
-            int bslot = -1;
-            for (int i = lane; i < nwin; i += 32) {
-                if (kv_lt(S.wcost[i], S.wanchor[i], best.v, best.i)) {
-                    best.v = S.wcost[i];
-                    best.i = S.wanchor[i];
-                    bslot = i;
-                }
-            }
-            const KV win = warp_select<false>(best);
-            if (win.i == 0x7fffffff) break;
-            if (bslot >= 0 && best.i == win.i && best.v == win.v) {
-                const long long o = (long long)b * p.A + win.i;
+        // rank counting: entry i is selected iff fewer than `take` entries precede it in (cost, anchor) order
+        for (int i = lane; i < nwin; i += 32) {
+            const float ci = S.wcost[i];
+            if (!(ci < P24_POS_INF)) continue;
+            const int ai = S.wanchor[i];
+            int before = 0;
+            for (int j = 0; j < nwin; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
+            if (before < take) {
+                const long long o = (long long)b * p.A + ai;
                 atomicAdd(&p.claim_cnt[o], 1);
                 p.claim_gt[o] = g;
-                S.wcost[bslot] = P24_POS_INF;
             }
-            __syncwarp();
         }
-        if (lane == 0) S.cnt = nvalid;
+        if (lane == 0) S.nvalid = nvalid;
     }
     __syncthreads();
-    nvalid = S.cnt;
-    if (k > nvalid) spill_claims(p, S, b, g, nwin, k - nvalid);
+    if (k > S.nvalid) spill_claims(p, S, b, g, nwin, k - S.nvalid);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -747,9 +976,19 @@ __device__ void finalize_warp(const float* sums28, float* state26, float* result
     if (lane < 26) state26[lane] = loss;
 }
 
+// pair value by one warp (lanes over rays, fixed tree); every lane returns it, `l_out` is the lane's ray loss
+__device__ __forceinline__ float warp_pair_value(const float* __restrict__ rec, const float* __restrict__ row, float& l_out) {
+    const int lane = threadIdx.x & 31;
+    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
+    float l = 0.0f;
+    if (lane < P24_RAYS) l = p24_ray_loss(rec[GT_RG + lane], row[2 + lane], d);
+    l_out = l;
+    return (warp_sum(l) / 24.0f) / 2.0f;
+}
+
 // Anchor claimed by several GTs: argmin of the cost over ALL GTs (losses.py:471-476); first index on ties.
-// One warp per anchor, lanes over GTs (valid pairs always beat penalised ones).
-__device__ int resolve_conflict(const Params& p, const float* recs, int n, const float* row, int a) {
+// One warp per anchor: lanes over GTs for the window test, then the whole warp on each in-window GT.
+__device__ __noinline__ int resolve_conflict(const Params& p, const float* recs, int n, const float* row, int a) {
     const int lane = threadIdx.x & 31;
     const float st = p.strides[a];
     const float xc = p24_anchor_centre(p.x_shifts[a], st);
@@ -759,44 +998,48 @@ __device__ int resolve_conflict(const Params& p, const float* recs, int n, const
     const float obj_sig = 1.0f / eo1;
     KV best = {P24_POS_INF, 0x7fffffff};
     for (int g0 = 0; g0 < n; g0 += 32) {
-        const int g = g0 + lane;
-        if (g < n) {
+        const int gl = g0 + lane;
+        const bool inwin = gl < n && p24_in_centre(recs[gl * GT_REC + GT_CX], recs[gl * GT_REC + GT_CY], xc, yc, st);
+        unsigned m = __ballot_sync(0xffffffffu, inwin);
+        while (m) {
+            const int g = g0 + __ffs(m) - 1;
+            m &= m - 1;
             const float* rec = recs + g * GT_REC;
-            bool valid = p24_in_centre(rec[GT_CX], rec[GT_CY], xc, yc, st);
-            if (valid)
-                valid = (p.flags & P24_F_NO_PRUNE) ? (p24_angle_sum(rec + GT_VX, rec + GT_VY, xc, yc) >= 350.0f)
-                                                   : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
-            if (valid) {
-                const float v = pair_value_row(rec, row);
-                float c = p24_cost(cls_cost_from(neg, row[27 + gt_class(rec, p.nc)], obj_sig), v, true);
-                if (!(c == c)) c = 3.0e38f;
-                if (kv_lt(c, g, best.v, best.i)) {
-                    best.v = c;
-                    best.i = g;
-                }
+            float ang = 0.0f;
+            if (lane < P24_RAYS) {
+                const int k2 = (lane == P24_RAYS - 1) ? 0 : lane + 1;
+                ang = p24_edge_angle(rec[GT_VX + lane] - xc, rec[GT_VY + lane] - yc, rec[GT_VX + k2] - xc,
+                                     rec[GT_VY + k2] - yc);
             }
-        }
-    }
-    best = warp_select<false>(best);
-    if (best.i != 0x7fffffff) return best.i;
-    // no valid pair at all (every claim came from a spill): argmin over the penalised costs
-    for (int g0 = 0; g0 < n; g0 += 32) {
-        const int g = g0 + lane;
-        if (g < n) {
-            const float* rec = recs + g * GT_REC;
-            const float v = pair_value_row(rec, row);
-            const float c = p24_cost(cls_cost_from(neg, row[27 + gt_class(rec, p.nc)], obj_sig), v, false);
+            ang = warp_sum(ang);
+            if (!(ang >= 350.0f)) continue;
+            float l;
+            const float v = warp_pair_value(rec, row, l);
+            float c = p24_cost(cls_cost_from(neg, row[27 + gt_class(rec, p.nc)], obj_sig), v, true);
+            if (!(c < 3.0e38f)) c = 3.0e38f;
             if (kv_lt(c, g, best.v, best.i)) {
                 best.v = c;
                 best.i = g;
             }
         }
     }
-    best = warp_select<false>(best);
+    if (best.i != 0x7fffffff) return best.i;
+    // no valid pair at all (every claim came from a spill): argmin over the penalised costs
+    for (int g = 0; g < n; ++g) {
+        const float* rec = recs + g * GT_REC;
+        float l;
+        const float v = warp_pair_value(rec, row, l);
+        const float c = p24_cost(cls_cost_from(neg, row[27 + gt_class(rec, p.nc)], obj_sig), v, false);
+        if (kv_lt(c, g, best.v, best.i)) {
+            best.v = c;
+            best.i = g;
+        }
+    }
     return best.i != 0x7fffffff ? best.i : 0;
 }
 
-__global__ void __launch_bounds__(P24_THREADS) k_resolve_loss(Params p) {
+__global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
+    pdl_wait();
     const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int a = tile * P24_THREADS + tid;
@@ -857,14 +1100,9 @@ __global__ void __launch_bounds__(P24_THREADS) k_resolve_loss(Params p) {
         const int aa = tile * P24_THREADS + al;
         const float* rec = recs + g * GT_REC;
         const float* row = img + (long long)aa * p.row_stride;
-        const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
-        float l = 0.0f;
-        if (lane < P24_RAYS) l = p24_ray_loss(rec[GT_RG + lane], row[2 + lane], d);
+        float l;
+        const float v = warp_pair_value(rec, row, l);  // pair value == pred_ious_this_matching (losses.py:491)
         acc_ray += (double)l;
-        float s = 0.0f;
-#pragma unroll
-        for (int k = 0; k < P24_RAYS; ++k) s = s + __shfl_sync(0xffffffffu, l, k);
-        const float v = (s / 24.0f) / 2.0f;  // pair value == pred_ious_this_matching (losses.py:491)
         if (lane == 0) {
             p.pred_iou[(long long)b * p.A + aa] = v;
             acc_obj -= (double)row[26];
@@ -914,13 +1152,13 @@ __global__ void __launch_bounds__(P24_THREADS) k_resolve_loss(Params p) {
             const int col = warp * 4 + q;
             if (col < 26) {
                 double t = 0.0;
-                for (int i = lane; i < nblk; i += 32) t += ((volatile double*)p.loss_part)[(long long)i * 28 + col];
+                for (int i = lane; i < nblk; i += 32) t += __ldcg(p.loss_part + (long long)i * 28 + col);
                 t = warp_sum_d(t);
                 if (lane == 0) s_sums[col] = (float)t;
             } else {
                 int t = 0;
-                const volatile int32_t* src = (col == 26) ? p.num_fg : p.num_gt;
-                for (int i = lane; i < p.B; i += 32) t += src[i];
+                const int32_t* src = (col == 26) ? p.num_fg : p.num_gt;
+                for (int i = lane; i < p.B; i += 32) t += __ldcg(src + i);
                 t = warp_sum_i(t);
                 if (lane == 0) s_sums[col] = (float)t;
             }
@@ -940,12 +1178,27 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
 size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float); }
 
 // optional per-stage timing (profiling aid for bench.py; process-global, not thread-safe)
-#define N_STAGES 3
+#define N_STAGES 4
 bool g_prof_on = false;
 cudaEvent_t g_prof_ev[N_STAGES + 1];
 bool g_prof_have = false;
 inline void prof_mark(int i, cudaStream_t st) {
     if (g_prof_on) cudaEventRecord(g_prof_ev[i], st);
+}
+
+template <typename K>
+cudaError_t launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Params& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
 }  // namespace
@@ -1009,13 +1262,21 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
         cudaFuncSetAttribute(k_anchor_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_done = true;
     }
+    const bool pdl = !(flags & P24_F_NO_PDL) && !g_prof_on;
+    cudaError_t e;
     prof_mark(0, st);
-    k_anchor_pass<<<dim3(p.tiles, B), P24_THREADS, dyn, st>>>(p);
+    e = launch(k_gt_prep, dim3(B), dim3(P24_THREADS), 0, st, pdl, p);
+    if (e != cudaSuccess) return (int)e;
     prof_mark(1, st);
-    k_gt_match<<<dim3(Lmax, B), P24_THREADS, 0, st>>>(p);
+    e = launch(k_anchor_pass, dim3(p.tiles, B), dim3(P24_THREADS), dyn, st, pdl, p);
+    if (e != cudaSuccess) return (int)e;
     prof_mark(2, st);
-    k_resolve_loss<<<dim3(p.tiles, B), P24_THREADS, 0, st>>>(p);
+    e = launch(k_gt_match, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
+    if (e != cudaSuccess) return (int)e;
     prof_mark(3, st);
+    e = launch(k_resolve_loss, dim3(p.tiles, B), dim3(P24_THREADS), 0, st, pdl, p);
+    if (e != cudaSuccess) return (int)e;
+    prof_mark(4, st);
     return (int)cudaGetLastError();
 }
 
@@ -1038,12 +1299,12 @@ extern "C" int p24_profile_enable(int on) {
     return 0;
 }
 
-extern "C" int p24_profile_read(float* h_ms3) {
-    if (!g_prof_have || !h_ms3) return P24_E_BADARG;
+extern "C" int p24_profile_read(float* h_ms4) {
+    if (!g_prof_have || !h_ms4) return P24_E_BADARG;
     cudaError_t e = cudaEventSynchronize(g_prof_ev[N_STAGES]);
     if (e != cudaSuccess) return (int)e;
     for (int i = 0; i < N_STAGES; ++i) {
-        e = cudaEventElapsedTime(&h_ms3[i], g_prof_ev[i], g_prof_ev[i + 1]);
+        e = cudaEventElapsedTime(&h_ms4[i], g_prof_ev[i], g_prof_ev[i + 1]);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;

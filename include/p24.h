@@ -39,6 +39,7 @@ extern "C" {
 /* p24_assign_batch flags */
 #define P24_F_NO_PRUNE 1u      /* evaluate every polygon angle sum exactly (self-check of the pruning) */
 #define P24_F_NO_FILTER 2u     /* evaluate every pair value exactly (self-check of the top-k filter) */
+#define P24_F_NO_PDL 8u        /* plain stream-ordered launches instead of programmatic dependent launch */
 #define P24_F_ALL_ROWS 4u      /* every label row is a GT (per-image API: the caller passes num_gt rows) */
 
 int p24_abi_version(void);
@@ -91,11 +92,11 @@ int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_
  *              (what the backward needs). */
 int p24_loss_finalize(const float* sums28, float* state26, float* result54, float* weights_n27, void* stream);
 
-/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its three
- * kernels (anchor_pass, gt_match, resolve_loss) on the launching stream; p24_profile_read waits
- * for the last call and returns the three durations in milliseconds into a HOST array.  Process-global. */
+/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its four
+ * kernels (gt_prep, anchor_pass, gt_match, resolve_loss) on the launching stream; p24_profile_read waits
+ * for the last call and returns the four durations in milliseconds into a HOST array.  Process-global. */
 int p24_profile_enable(int on);
-int p24_profile_read(float* h_ms3);
+int p24_profile_read(float* h_ms4);
 
 #ifdef __cplusplus
 }
