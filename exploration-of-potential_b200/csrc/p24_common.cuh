@@ -14,7 +14,7 @@
 // ---- per-GT record (floats), built once per image by the anchor pass ---------------------------
 // [0] cx  [1] cy  [2] rin2  [3] rrej2   (one 128-bit shared-memory load for the per-pair tests)
 // [4] class (as float)  [5] rgmax  [6] rgmin  [7] pad
-// [8..31] vertex x  [32..55] vertex y  [56..79] ray length rg
+// [8..31] vertex x  [32..55] vertex y  [56..79] ray length rg  [80] mean rg^2  [81] mean rg  [82..83] pad
 #define GT_CX 0
 #define GT_CY 1
 #define GT_RIN2 2    // squared radius of a disc around (cx, cy) that lies inside the polygon (0: none)
@@ -25,13 +25,16 @@
 #define GT_VX 8
 #define GT_VY 32
 #define GT_RG 56
-#define GT_REC 80
+#define GT_RGMS 80    // mean of rg^2 (seed ranking)
+#define GT_RGMEAN 81  // mean of rg
+#define GT_REC 84
 
 static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct P24Workspace {
     size_t gt_rec;      // [B, Lmax, GT_REC] float
     size_t clist;       // [B, tiles, 256] float4  candidate anchors of a tile, compacted: (pred cx, pred cy, rpmax, anchor idx bits)
+    size_t clist2;      // [B, tiles, 256] float2  (mean rp^2, mean rp) of the same candidates (seed ranking)
     size_t ccount;      // [B, tiles] int          candidates per tile
     size_t wcount;      // [B, Lmax] int           anchors inside the GT's centre window (zero between calls)
     size_t wlist;       // [B, Lmax, VCAP] int
@@ -39,6 +42,8 @@ struct P24Workspace {
     size_t claim_gt;    // [B, A] int      the GT that selected the anchor (meaningful when claim_cnt == 1)
     size_t obj_part;    // [B * tiles] double   per-block sums of BCEWithLogits(obj, 0)
     size_t loss_part;   // [B * tiles, 28] double
+    size_t img_part;    // [B, 28] double       per-image sums (second reduction level)
+    size_t img_ticket;  // [B] unsigned         tiles of the image that have finished (zero between calls)
     size_t ticket;      // [1] unsigned (last-block-done counter; zero between calls)
     size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
     size_t total;
@@ -55,15 +60,18 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
     w.wcount = off;     off = p24_align(off + BL * sizeof(int));
     w.ticket = off;     off = p24_align(off + sizeof(unsigned));
+    w.img_ticket = off; off = p24_align(off + (size_t)B * sizeof(unsigned));
     w.err_flag = off;   off = p24_align(off + sizeof(int));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
     w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
     w.ccount = off;     off = p24_align(off + NB * sizeof(int));
+    w.clist2 = off;     off = p24_align(off + NB * P24_THREADS * 2 * sizeof(float));
     w.wlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));
     w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
     w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));
     w.obj_part = off;   off = p24_align(off + NB * sizeof(double));
     w.loss_part = off;  off = p24_align(off + NB * 28 * sizeof(double));
+    w.img_part = off;   off = p24_align(off + (size_t)B * 28 * sizeof(double));
     w.total = off;
     return w;
 }

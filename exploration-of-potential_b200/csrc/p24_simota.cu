@@ -51,6 +51,7 @@ struct Params {
     // workspace
     float* gt_rec;
     float4* clist;
+    float2* clist2;
     int* ccount;
     int* wcount;
     int* wlist;
@@ -58,11 +59,28 @@ struct Params {
     int* claim_gt;
     double* obj_part;
     double* loss_part;
+    double* img_part;
+    unsigned* img_ticket;
     unsigned* ticket;
     int* err_flag;
     unsigned flags;
     int tiles;
 };
+
+// Debug-only phase timers (-DP24_TIMING): thread 0 of every CTA stores %globaltimer at phase boundaries.
+#ifdef P24_TIMING
+__device__ unsigned long long g_tstamp[3][4096][12];
+__device__ __forceinline__ void tmark(int kern, int cta, int slot) {
+    if (threadIdx.x == 0 && cta < 4096) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_tstamp[kern][cta][slot] = t;
+    }
+}
+#define TMARK(kern, cta, slot) tmark(kern, cta, slot)
+#else
+#define TMARK(kern, cta, slot)
+#endif
 
 #define MATCH_THREADS 384
 #define MATCH_WARPS (MATCH_THREADS / 32)
@@ -98,13 +116,14 @@ __device__ __forceinline__ int group_sum_i(int v, unsigned m) {
 // -------------------------------------------------------------------------------------------
 // k_gt_prep: nlabel + GT records, one CTA per image, one warp per GT (lanes over the 24 vertices)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(P24_THREADS) k_gt_prep(Params p) {
+#define PREP_THREADS 1024
+__global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(Params p) {
     pdl_wait();
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* lab = p.labels + (long long)b * p.lab_img_stride;
     // nlabel = (labels.sum(2) > 0).sum(1)   losses.py:190 ; the first n rows are the GTs (losses.py:219-220)
     int local = 0;
-    for (int r = tid; r < p.Lmax; r += P24_THREADS) {
+    for (int r = tid; r < p.Lmax; r += PREP_THREADS) {
         const float* row = lab + (long long)r * p.lab_row_stride;
         double s = 0.0;
 #pragma unroll
@@ -122,7 +141,7 @@ __global__ void __launch_bounds__(P24_THREADS) k_gt_prep(Params p) {
         p.num_gt[b] = n;
         p.num_fg[b] = 0;
     }
-    for (int g = warp; g < n; g += P24_WARPS) {
+    for (int g = warp; g < n; g += PREP_THREADS / 32) {
         const float* row = lab + (long long)g * p.lab_row_stride;
         float* rec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
         const float cx = row[1], cy = row[2];
@@ -157,6 +176,8 @@ __global__ void __launch_bounds__(P24_THREADS) k_gt_prep(Params p) {
         const unsigned par = __ballot_sync(0xffffffffu, cross);
         const bool nan_any = __any_sync(0xffffffffu, !(rin == rin) && lane < P24_RAYS);
         const float perim = warp_sum(len);
+        const float rgsum = warp_sum(lane < P24_RAYS ? rg : 0.0f);
+        const float rg2sum = warp_sum(lane < P24_RAYS ? rg * rg : 0.0f);
         rgmax = warp_max(rgmax);
         rgmin = -warp_max(-rgmin);
         rin = -warp_max(-rin);
@@ -185,6 +206,10 @@ __global__ void __launch_bounds__(P24_THREADS) k_gt_prep(Params p) {
             rec[GT_RGMAX] = rgmax;
             rec[GT_RGMIN] = rgmin;
             rec[7] = 0.0f;
+            rec[GT_RGMS] = rg2sum * (1.0f / 24.0f);
+            rec[GT_RGMEAN] = rgsum * (1.0f / 24.0f);
+            rec[82] = 0.0f;
+            rec[83] = 0.0f;
         }
     }
 }
@@ -272,6 +297,7 @@ __device__ __forceinline__ float cls_cost_from(float neg_sum, float cls_logit_c,
 // k_anchor_pass
 // -------------------------------------------------------------------------------------------
 #define ITEM_CAP 2048
+#define WIN_CAP 1024
 #define ROW_CH 27  // channels 0..26 of a head row are read here: centre, 24 radii, objectness
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -292,8 +318,9 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
 
     __shared__ float s_row[P24_WARPS][ROW_CH][33];
     __shared__ unsigned s_items[ITEM_CAP];
+    __shared__ unsigned s_win[WIN_CAP];
     __shared__ int s_cand[P24_THREADS];
-    __shared__ int s_nitems;
+    __shared__ int s_nitems, s_nwin;
     __shared__ int s_wcnt[P24_WARPS];
     __shared__ double s_red[P24_WARPS];
 
@@ -314,9 +341,14 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
         xs = p.x_shifts[a];
         ys = p.y_shifts[a];
     }
-    if (tid == 0) s_nitems = 0;
+    if (tid == 0) {
+        s_nitems = 0;
+        s_nwin = 0;
+    }
     s_cand[tid] = 0;
+    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 0);
     pdl_wait();
+    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 1);
     const int n = p.num_gt[b];
     {
         const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
@@ -324,8 +356,9 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
     }
     cp_async_wait_all();
     __syncthreads();
+    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 2);
 
-    float pcx = 0.f, pcy = 0.f, rpmax = 0.f, rpmin = INFINITY, obj = 0.f;
+    float pcx = 0.f, pcy = 0.f, rpmax = 0.f, rpmin = INFINITY, rpsum = 0.f, rp2sum = 0.f, obj = 0.f;
     const float xc = p24_anchor_centre(xs, st);
     const float yc = p24_anchor_centre(ys, st);
     if (active) {
@@ -336,6 +369,8 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
             const float v = s_row[warp][c][lane];
             rpmax = fmaxf(rpmax, v);
             rpmin = fminf(rpmin, v);
+            rpsum += v;
+            rp2sum = fmaf(v, v, rp2sum);
         }
         obj = s_row[warp][26][lane];
     }
@@ -352,9 +387,16 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
             cheap |= d2 < h.z;
             if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) {
                 cheap = true;
-                const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
-                if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
-                else atomicOr(p.err_flag, 1);
+                // (anchor, GT) goes to the GT's centre-window list; staged in shared memory so that the global
+                // atomics of a tile are issued together instead of one round trip at a time
+                const int ws = atomicAdd(&s_nwin, 1);
+                if (ws < WIN_CAP) {
+                    s_win[ws] = (unsigned)tid | ((unsigned)g << 8);
+                } else {
+                    const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
+                    if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
+                    else atomicOr(p.err_flag, 1);
+                }
             }
         }
     }
@@ -382,6 +424,17 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
     }
     if (mine) s_cand[tid] = 1;
     __syncthreads();
+    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 3);
+    {
+        const int nw = min(s_nwin, WIN_CAP);
+        for (int i = tid; i < nw; i += P24_THREADS) {
+            const unsigned it = s_win[i];
+            const int g = it >> 8;
+            const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
+            if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = tile * P24_THREADS + (int)(it & 0xFF);
+            else atomicOr(p.err_flag, 1);
+        }
+    }
     const int nitems = min(s_nitems, ITEM_CAP);
     for (int i = tid; i < nitems; i += P24_THREADS) {
         const unsigned it = s_items[i];
@@ -399,6 +452,7 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
     }
     __syncthreads();
 
+    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 4);
     // ---- compacted candidate list of the tile (deterministic order) + per-anchor scratch reset ----------
     const bool cand = active && (n > 0) && (cheap || s_cand[tid]);
     const unsigned bal = __ballot_sync(0xffffffffu, cand);
@@ -418,6 +472,7 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
         const int rank = base + __popc(bal & ((1u << lane) - 1u));
         // a prediction with a tiny radius disables the bound filter for its pairs: rpmax = +inf
         p.clist[blk * P24_THREADS + rank] = make_float4(pcx, pcy, rpmin < 0.25f ? INFINITY : rpmax, __int_as_float(a));
+        p.clist2[blk * P24_THREADS + rank] = make_float2(rp2sum * (1.0f / 24.0f), rpsum * (1.0f / 24.0f));
     }
     if (active) p.claim_cnt[(long long)b * p.A + a] = 0;
     if (tid == 0) {
@@ -426,40 +481,43 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
         for (int w = 0; w < P24_WARPS; ++w) t += s_red[w];
         p.obj_part[blk] = t;
     }
+    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 5);
 }
 
 // -------------------------------------------------------------------------------------------
 // k_gt_match
 // -------------------------------------------------------------------------------------------
-#define HIT_CAP 4096
+#define HIT_CAP 3072
 #define EV_CAP 256
 #define N_SEED (2 * MATCH_WARPS)
+#define MAX_TILES 1024  // candidate counts of an image kept in shared memory (A <= 262144)
 
 // Upper bound of the pair value as a function of t = rpmax + d: any ray has loss <= max(1, 2 - 4 rg^2 / (rg + rp + d)^2)
 // (nested rays: loss <= 1; partial and apart rays: loss <= 2 - uni/cs; DESIGN.md "top-10 bracket").
-// Evaluated by lanes 0..23 of one warp.
-__device__ __forceinline__ float bound_H(float rg_lane, float t, int lane) {
-    float term = 0.0f;
-    if (lane < P24_RAYS) {
-        const float q = rg_lane + t;
-        term = fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg_lane * rg_lane, q * q));
+// One thread evaluates it from the GT record in shared memory.
+__device__ __forceinline__ float bound_H_thread(const float* __restrict__ rec, float t) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < P24_RAYS; ++k) {
+        const float rg = rec[GT_RG + k];
+        const float q = rg + t;
+        s += fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, q * q));
     }
-    return warp_sum(term) * (1.0f / 48.0f);
+    return s * (1.0f / 48.0f);
 }
 
 struct MatchShared {
     float rec[GT_REC];
-    int hit[HIT_CAP];      // slow path: anchors that survive the bound filter
-    float hub[HIT_CAP];    // their upper bounds, later their exact values
+    int ccount[MAX_TILES];
+    int hit[HIT_CAP];       // slow path: anchors the scalar bound cannot exclude
+    float ev[EV_CAP];       // slow path: exact values that reach the seed threshold
     float top[P24_TOPK];
     int seed[N_SEED];
     float seedv[N_SEED];
     KV kv[MATCH_WARPS];
     float wmax[MATCH_WARPS];
-    int red[MATCH_WARPS];
-    int cnt, nhit, k, slow, nvalid, nev;
-    float T, tau, thr;
-    float ev[EV_CAP + P24_TOPK];  // slow path: exact values found by the first refinement round
+    int cnt, nhit, nev, k, slow, nvalid, overflow;
+    float T, L, tau, tmax;
     int wanchor[P24_VCAP];
     float wcost[P24_VCAP];  // +inf: not valid
 };
@@ -476,212 +534,151 @@ __device__ __forceinline__ KV match_block_select(KV x, KV* s_red) {
     return y;
 }
 
-__device__ int match_block_count(bool pred, int* s_red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = __popc(__ballot_sync(0xffffffffu, pred));
-    __syncthreads();
-    if (lane == 0) s_red[warp] = c;
-    __syncthreads();
-    int t = 0;
-#pragma unroll
-    for (int w = 0; w < MATCH_WARPS; ++w) t += s_red[w];
-    return t;
-}
-
-// select the `want` largest of vals[0..n) into s_top (descending); block-wide, returns count.  Destroys vals.
-__device__ int select_top(float* vals, int n, int want, float* s_top, KV* s_kv) {
-    const int m = min(want, n);
-    for (int r = 0; r < m; ++r) {
+// the `want` largest of vals[0..n) into S.top (descending) by one warp; destroys vals; returns the count
+__device__ int warp_select_top(float* vals, int n, int want, float* top) {
+    const int lane = threadIdx.x & 31;
+    int got = 0;
+    for (int r = 0; r < want; ++r) {
         KV best = {P24_NEG_INF, 0x7fffffff};
-        for (int i = threadIdx.x; i < n; i += MATCH_THREADS) {
+        for (int i = lane; i < n; i += 32) {
             const float v = vals[i];
             if (kv_gt(v, i, best.v, best.i)) {
                 best.v = v;
                 best.i = i;
             }
         }
-        best = match_block_select<true>(best, s_kv);
-        if (threadIdx.x == 0) {
-            s_top[r] = best.v;
-            if (best.i < n) vals[best.i] = P24_NEG_INF;
+        best = warp_select<true>(best);
+        if (best.i == 0x7fffffff) break;
+        if (lane == 0) {
+            top[r] = best.v;
+            vals[best.i] = P24_NEG_INF;
         }
-        __syncthreads();
+        __syncwarp();
+        ++got;
     }
-    return m;
+    return got;
 }
 
-// Exact top-kc sum when the bracket is not conclusive.
-//  1. candidates whose scalar bound H(t) cannot reach the seed threshold are dropped (one compare per pair);
-//  2. the rest get a per-ray upper bound ub (fast arithmetic, exact to ~1e-6 for far pairs); ub < T - eps drops more;
-//  3. the ~24 largest ub are evaluated exactly -> a tighter threshold T'; whatever still has ub >= T' - eps is
-//     evaluated exactly as well; the top-kc exact values are summed in descending order (torch.topk order).
-// Lists that overflow HIT_CAP are processed in chunks, carrying the best kc exact values forward.
-__device__ __noinline__ float exact_topk_sum(const Params& p, MatchShared& S, int b, int kc, float T_seed) {
+// Brute force (no usable threshold, P24_F_NO_FILTER, or list overflow): exact value of EVERY candidate, in chunks,
+// carrying the best kc forward.
+__device__ __noinline__ float topk_sum_bruteforce(const Params& p, MatchShared& S, int b, int kc) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const unsigned gm = group_mask();
+    const int grp = tid >> 3, sub = tid & 7;
+    const float* img = p.outputs + (long long)b * p.img_stride;
+    float* vals = reinterpret_cast<float*>(S.hit);  // HIT_CAP floats
+    int ncarry = 0;
+    const int tiles_per_chunk = (HIT_CAP - P24_TOPK) / P24_THREADS;
+    for (int t0 = 0; t0 < p.tiles; t0 += tiles_per_chunk) {
+        const int t1 = min(t0 + tiles_per_chunk, p.tiles);
+        __syncthreads();
+        if (tid < ncarry) vals[tid] = S.top[tid];
+        if (tid == 0) S.nhit = ncarry;
+        __syncthreads();
+        for (int tl = t0; tl < t1; ++tl) {
+            const long long blk = (long long)b * p.tiles + tl;
+            const int c = S.ccount[tl];
+            for (int i = grp; i < c; i += MATCH_GROUPS) {
+                const int a = __float_as_int(p.clist[blk * P24_THREADS + i].w);
+                const float v = group_pair_value(S.rec, img + (long long)a * p.row_stride, gm);
+                if (sub == 0) vals[atomicAdd(&S.nhit, 1)] = (v == v) ? v : P24_POS_INF;  // NaN sorts first (torch.topk)
+            }
+        }
+        __syncthreads();
+        if (warp == 0) warp_select_top(vals, S.nhit, kc, S.top);
+        __syncthreads();
+        ncarry = min(kc, S.nhit);
+    }
+    float ksum = 0.0f;
+    for (int i = 0; i < ncarry; ++i) ksum = ksum + (S.top[i] == P24_POS_INF ? NAN : S.top[i]);
+    return ksum;
+}
+
+// Exact top-10 sum when the bracket is not conclusive (about 1 GT in 200):
+//  1. tau: the largest t with H(t) <= T - eps (T = 10th best seed value), two rounds of 32-way search by one warp;
+//     candidates with t = rpmax + d < tau cannot reach T (one compare per candidate);
+//  2. the others get the per-ray bound ub (8-lane groups, 3 rays per lane); those with ub >= T are evaluated exactly
+//     on the spot and kept when they reach T;
+//  3. the 10 largest kept values (the best seeds are among them) are summed in descending order (torch.topk order).
+__device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S, int b) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned gm = group_mask();
     const int grp = tid >> 3, sub = tid & 7;
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     const float* img = p.outputs + (long long)b * p.img_stride;
-    const bool filter = !(p.flags & P24_F_NO_FILTER) && T_seed > P24_NEG_INF && S.rec[GT_RGMIN] >= 0.25f;
+    const float T = S.T;
     if (warp == 0) {
+        const float target = T - 2e-5f;
+        float lo = 0.0f, hi = S.tmax * 1.001f + 1.0f;
         float tau = P24_NEG_INF;
-        if (filter) {
-            const float target = T_seed - 2e-5f;
-            const float rgl = lane < P24_RAYS ? S.rec[GT_RG + lane] : 0.0f;
-            float lo = 0.0f, hi = 65536.0f;
-            if (bound_H(rgl, lo, lane) <= target) {
-                for (int it = 0; it < 26; ++it) {
-                    const float mid = 0.5f * (lo + hi);
-                    if (bound_H(rgl, mid, lane) <= target) lo = mid;
-                    else hi = mid;
-                }
-                tau = lo - 0.01f - 1e-4f * lo;
+        if (bound_H_thread(S.rec, lo) <= target) {
+#pragma unroll 1
+            for (int round = 0; round < 2; ++round) {
+                const float step = (hi - lo) * (1.0f / 32.0f);
+                const float tj = lo + step * (float)(lane + 1);
+                const bool ok = bound_H_thread(S.rec, tj) <= target;     // monotone in t: a prefix of lanes
+                const int nok = __popc(__ballot_sync(0xffffffffu, ok));
+                const float nlo = lo + step * (float)nok;
+                hi = (nok == 32) ? hi : (nlo + step);
+                lo = nlo;
             }
+            tau = lo - 0.01f - 1e-4f * lo;
         }
         if (lane == 0) {
-            S.T = filter ? T_seed : P24_NEG_INF;
             S.tau = tau;
-        }
-    }
-    int ncarry = 0;  // exact values carried in S.top[0..ncarry)
-    __syncthreads();
-    const float tau = S.tau;
-    const int tiles_per_chunk = (HIT_CAP - P24_TOPK) / P24_THREADS;
-    for (int t0 = 0; t0 < p.tiles; t0 += tiles_per_chunk) {
-        const int t1 = min(t0 + tiles_per_chunk, p.tiles);
-        float T = S.T;
-        if (tid == 0) {
             S.nhit = 0;
             S.nev = 0;
+            S.overflow = 0;
         }
-        __syncthreads();
-        // 1 + 2: bound filters
-        for (int tl = t0 + warp; tl < t1; tl += MATCH_WARPS) {
-            const long long blk = (long long)b * p.tiles + tl;
-            const int c = p.ccount[blk];
-            for (int i = lane; i < c; i += 32) {
-                const float4 q = p.clist[blk * P24_THREADS + i];
-                const float dx = gcx - q.x, dy = gcy - q.y;
-                const float d = sqrtf(fmaf(dx, dx, dy * dy));
-                const float t = q.z + d;
-                if (!(t >= tau || !(t == t))) continue;
-                const int a = __float_as_int(q.w);
-                float ub = P24_POS_INF;
-                if (filter && q.z < 60000.0f) {
-                    const float* row = img + (long long)a * p.row_stride;
-                    float s = 0.0f;
-#pragma unroll 4
-                    for (int k = 0; k < P24_RAYS; ++k) s += p24_ray_loss_ub(S.rec[GT_RG + k], row[2 + k], d);
-                    ub = s * (1.0f / 48.0f) + 2e-5f;
-                    if (ub < T) continue;
-                    if (!(ub == ub)) ub = P24_POS_INF;
-                }
-                const int slot = atomicAdd(&S.nhit, 1);
-                S.hit[slot] = a;
-                S.hub[slot] = ub;
-            }
+    }
+    __syncthreads();
+    const float tau = S.tau;
+    const int nslot = p.tiles * P24_THREADS;
+    for (int i0 = tid; i0 < nslot; i0 += MATCH_THREADS) {
+        const int tl = i0 >> 8, rk = i0 & 255;
+        if (rk >= S.ccount[tl]) continue;
+        const float4 q = p.clist[((long long)b * p.tiles + tl) * P24_THREADS + rk];
+        const float dx = gcx - q.x, dy = gcy - q.y;
+        const float t = q.z + sqrtf(fmaf(dx, dx, dy * dy));
+        if (t >= tau || !(t == t)) {
+            const int slot = atomicAdd(&S.nhit, 1);
+            if (slot < HIT_CAP) S.hit[slot] = __float_as_int(q.w);
+            else S.overflow = 1;
         }
-        __syncthreads();
-        int nhit = S.nhit;
-        // 3a: threshold thr such that about 24..64 entries have ub >= thr (bisection on the count)
-        float thr = P24_NEG_INF;
-        if (filter && nhit > 64) {
-            float lo = T, hi = 1.0f + 1e-3f;
-            for (int it = 0; it < 14; ++it) {
-                const float mid = 0.5f * (lo + hi);
-                int c = 0;
-                for (int i = tid; i < nhit; i += MATCH_THREADS) c += (S.hub[i] >= mid) ? 1 : 0;
-                // block sum of c
-                c = warp_sum_i(c);
-                __syncthreads();
-                if (lane == 0) S.red[warp] = c;
-                __syncthreads();
-                int tot = 0;
+    }
+    __syncthreads();
+    if (S.overflow) return NAN;  // caller falls back to brute force
+    const int nhit = S.nhit;
+    for (int i = grp; i < nhit; i += MATCH_GROUPS) {
+        const float* row = img + (long long)S.hit[i] * p.row_stride;
+        const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
+        float rp[3], ub = 0.0f;
 #pragma unroll
-                for (int w = 0; w < MATCH_WARPS; ++w) tot += S.red[w];
-                if (tot >= 24) lo = mid;
-                else hi = mid;
-            }
-            thr = lo;
+        for (int q = 0; q < 3; ++q) {
+            rp[q] = row[2 + sub * 3 + q];
+            ub += p24_ray_loss_ub(S.rec[GT_RG + sub * 3 + q], rp[q], d);
         }
-        // 3b: exact values of the entries with ub >= thr (8-lane groups); others keep their bound, tagged negative
-        for (int i0 = 0; i0 < nhit; i0 += MATCH_GROUPS) {
-            const int i = i0 + grp;
-            if (i < nhit) {
-                const float ub = S.hub[i];
-                if (ub >= thr) {
-                    const float v = group_pair_value(S.rec, img + (long long)S.hit[i] * p.row_stride, gm);
-                    if (sub == 0) {
-                        const float vv = (v == v) ? v : P24_POS_INF;  // NaN pairs sort first, like torch.topk
-                        S.hub[i] = vv;
-                        S.hit[i] = -1;  // evaluated
-                        const int e = atomicAdd(&S.nev, 1);
-                        if (e < EV_CAP) S.ev[e] = vv;
-                    }
-                }
-            }
+        ub = group_sum(ub, gm) * (1.0f / 48.0f) + 2e-5f;
+        if (ub < T) continue;
+        float s = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) s = s + p24_ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
+        s = group_sum(s, gm);
+        const float v = (s / 24.0f) / 2.0f;
+        if (sub == 0 && (v >= T || !(v == v))) {
+            const int e = atomicAdd(&S.nev, 1);
+            if (e < EV_CAP) S.ev[e] = (v == v) ? v : P24_POS_INF;
+            else S.overflow = 1;
         }
-        __syncthreads();
-        // tighter threshold T' = kc-th largest exact value so far (carried + evaluated)
-        if (filter && nhit > 64) {
-            if (warp == 0) {
-                const int nev = min(S.nev, EV_CAP);
-                for (int i = lane; i < ncarry; i += 32) S.ev[nev + i] = S.top[i];
-                __syncwarp();
-                const int tot = nev + ncarry;
-                float kth = P24_NEG_INF;
-                int got = 0;
-                for (int r = 0; r < kc; ++r) {
-                    KV best = {P24_NEG_INF, 0x7fffffff};
-                    for (int i = lane; i < tot; i += 32) {
-                        const float v = S.ev[i];
-                        if (kv_gt(v, i, best.v, best.i)) {
-                            best.v = v;
-                            best.i = i;
-                        }
-                    }
-                    best = warp_select<true>(best);
-                    if (best.i == 0x7fffffff) break;
-                    if (lane == 0) S.ev[best.i] = P24_NEG_INF;
-                    __syncwarp();
-                    kth = best.v;
-                    ++got;
-                }
-                if (lane == 0) S.thr = (got >= kc) ? kth : P24_NEG_INF;
-            }
-            __syncthreads();
-            const float T2 = fmaxf(S.thr - 2e-5f, T);
-            // 3c: entries not yet evaluated whose bound still reaches T2
-            for (int i0 = 0; i0 < nhit; i0 += MATCH_GROUPS) {
-                const int i = i0 + grp;
-                if (i < nhit) {
-                    const int a = S.hit[i];
-                    if (a >= 0 && S.hub[i] >= T2) {
-                        const float v = group_pair_value(S.rec, img + (long long)a * p.row_stride, gm);
-                        if (sub == 0) {
-                            S.hub[i] = (v == v) ? v : P24_POS_INF;
-                            S.hit[i] = -1;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        // keep exact values only, append the carried ones, select the best kc
-        for (int i = tid; i < nhit; i += MATCH_THREADS)
-            if (S.hit[i] >= 0) S.hub[i] = P24_NEG_INF;
-        if (tid < ncarry) S.hub[nhit + tid] = S.top[tid];
-        __syncthreads();
-        nhit += ncarry;
-        ncarry = select_top(S.hub, nhit, kc, S.top, S.kv);
-        if (ncarry == kc && filter && tid == 0) S.T = fmaxf(S.T, S.top[kc - 1] - 2e-5f);
-        __syncthreads();
     }
+    __syncthreads();
+    if (S.overflow || S.nev < P24_TOPK) return NAN;
+    int got = 0;
+    if (warp == 0) got = warp_select_top(S.ev, S.nev, P24_TOPK, S.top);
+    __syncthreads();
+    (void)got;
     float ksum = 0.0f;
-    for (int i = 0; i < ncarry; ++i) {
-        const float v = S.top[i];
-        ksum = ksum + (v == P24_POS_INF ? NAN : v);
-    }
+    for (int i = 0; i < P24_TOPK; ++i) ksum = ksum + (S.top[i] == P24_POS_INF ? NAN : S.top[i]);
     return ksum;
 }
 
@@ -700,7 +697,7 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
     const int c = gt_class(S.rec, p.nc);
     for (int tl = 0; tl < p.tiles; ++tl) {
         const long long blk = (long long)b * p.tiles + tl;
-        const int cc = p.ccount[blk];
+        const int cc = S.ccount[tl];
         for (int i = tid; i < cc; i += MATCH_THREADS) {
             const int a = __float_as_int(p.clist[blk * P24_THREADS + i].w);
             bool isvalid = false;
@@ -748,14 +745,17 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
 }
 
 __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
-    pdl_wait();
     const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+#define MCTA (b * 20 + g)
+    if (g < 20) TMARK(1, MCTA, 0);
+    pdl_wait();
     const int n = p.num_gt[b];
     if (g >= n) {
         if (tid == 0) p.dyn_k[b * p.Lmax + g] = 0;
         return;
     }
+    TMARK(1, MCTA, 1);
     __shared__ MatchShared S;
     const int wslot = b * p.Lmax + g;
     if (tid < GT_REC) S.rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
@@ -764,52 +764,70 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
         S.wanchor[tid] = tid < nwin ? p.wlist[(long long)wslot * P24_VCAP + tid] : 0x7fffffff;
         S.wcost[tid] = P24_POS_INF;
     }
+    int cnt = 0;
+    for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) {
+        const int c = p.ccount[(long long)b * p.tiles + tl];
+        S.ccount[tl] = c;
+        cnt += c;
+    }
     if (tid == 0) S.cnt = 0;
     __syncthreads();
+    cnt = warp_sum_i(cnt);
+    if (lane == 0 && cnt) atomicAdd(&S.cnt, cnt);
     if (tid == 0) p.wcount[wslot] = 0;  // leave the list empty for the next call
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     const float* img = p.outputs + (long long)b * p.img_stride;
 
-    // ---- scan the image's candidates: count, largest t, two seeds per warp -----------------------------
-    float t1 = P24_NEG_INF, t2 = P24_NEG_INF;
-    int a1 = 0x7fffffff, a2 = 0x7fffffff, cnt = 0;
-    for (int tl = warp; tl < p.tiles; tl += MATCH_WARPS) {
-        const long long blk = (long long)b * p.tiles + tl;
-        const int c = p.ccount[blk];
-        cnt += c;  // every lane of the warp holds the same running count
-        for (int i = lane; i < c; i += 32) {
-            const float4 q = p.clist[blk * P24_THREADS + i];
-            const float dx = gcx - q.x, dy = gcy - q.y;
-            const float t = q.z + sqrtf(fmaf(dx, dx, dy * dy));
-            const int a = __float_as_int(q.w);
-            if (kv_gt(t, a, t1, a1)) {
-                t2 = t1;
+    // ---- scan the image's candidates (padded [tile][256] layout, independent loads): largest t, and two seeds per
+    // warp ranked by a first-order proxy of the pair value, q = (mean rg^2 + mean rp^2) / (mean rg + mean rp + d)^2
+    // (value ~ 1 - q / 3 for far pairs): the smallest q are almost always the true top-10 ---------------------------
+    float q1 = P24_POS_INF, q2 = P24_POS_INF, tmax = P24_NEG_INF;
+    int a1 = 0x7fffffff, a2 = 0x7fffffff;
+    {
+        const float rgms = S.rec[GT_RGMS], rgmean = S.rec[GT_RGMEAN];
+        const int nslot = p.tiles * P24_THREADS;
+        const float4* cl = p.clist + (long long)b * p.tiles * P24_THREADS;
+        const float2* cl2 = p.clist2 + (long long)b * p.tiles * P24_THREADS;
+#pragma unroll 4
+        for (int i0 = tid; i0 < nslot; i0 += MATCH_THREADS) {
+            if ((i0 & 255) >= S.ccount[i0 >> 8]) continue;
+            const float4 c4 = cl[i0];
+            const float2 c2 = cl2[i0];
+            const float dx = gcx - c4.x, dy = gcy - c4.y;
+            const float d2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-12f);
+            const float d = d2 * rsqrtf(d2);
+            tmax = fmaxf(tmax, c4.z + d);
+            const float den = (rgmean + c2.y) + d;
+            const float q = __fdividef(rgms + c2.x, den * den);
+            const int a = __float_as_int(c4.w);
+            if (kv_lt(q, a, q1, a1)) {
+                q2 = q1;
                 a2 = a1;
-                t1 = t;
+                q1 = q;
                 a1 = a;
-            } else if (kv_gt(t, a, t2, a2)) {
-                t2 = t;
+            } else if (kv_lt(q, a, q2, a2)) {
+                q2 = q;
                 a2 = a;
             }
         }
-    }
-    {
-        if (lane == 0 && cnt) atomicAdd(&S.cnt, cnt);
-        const KV w1 = warp_select<true>(KV{t1, a1});
+        const KV w1 = warp_select<false>(KV{q1, a1});
         const bool owner = (a1 == w1.i) && (a1 != 0x7fffffff);
-        const KV w2 = warp_select<true>(owner ? KV{t2, a2} : KV{t1, a1});
+        const KV w2 = warp_select<false>(owner ? KV{q2, a2} : KV{q1, a1});
+        tmax = warp_max(tmax);
         if (lane == 0) {
             S.seed[2 * warp] = (w1.i != 0x7fffffff) ? w1.i : -1;
             S.seed[2 * warp + 1] = (w2.i != 0x7fffffff) ? w2.i : -1;
-            S.wmax[warp] = w1.v;
+            S.wmax[warp] = tmax;
         }
     }
     __syncthreads();
+    TMARK(1, MCTA, 2);
     const int ncand = S.cnt;
     const int kc = min(P24_TOPK, ncand);  // losses.py:452
 
     // ---- group tasks: [0, N_SEED) exact value of a seed; [N_SEED, N_SEED + nwin) a centre-window anchor:
-    // polygon test (reference-order edge terms, 3 per lane), exact pair value and cost when inside ----------
+    // polygon test (reference-order edge terms, 3 per lane), exact pair value and cost when inside.  Every load
+    // of a task is issued before its arithmetic (one memory round trip per task) ------------------------------
     {
         const unsigned gm = group_mask();
         const int grp = tid >> 3, sub = tid & 7;
@@ -825,9 +843,17 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
             }
             const int wi = task - N_SEED;
             const int a = S.wanchor[wi];
+            const float* row = img + (long long)a * p.row_stride;
             const float st = p.strides[a];
-            const float xc = p24_anchor_centre(p.x_shifts[a], st);
-            const float yc = p24_anchor_centre(p.y_shifts[a], st);
+            const float xs = p.x_shifts[a], ys = p.y_shifts[a];
+            const float pcx = row[0], pcy = row[1], obj = row[26], clsc = row[27 + c];
+            float rp[3], cl[10];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) rp[q] = row[2 + sub * 3 + q];
+#pragma unroll
+            for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
+            const float xc = p24_anchor_centre(xs, st);
+            const float yc = p24_anchor_centre(ys, st);
             float ang = 0.0f;
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
@@ -838,18 +864,35 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
             }
             ang = group_sum(ang, gm);
             if (!(ang >= 350.0f)) continue;  // losses.py:588
-            const float* row = img + (long long)a * p.row_stride;
-            const float v = group_pair_value(S.rec, row, gm);
-            const float eo1 = 1.0f + expf(-row[26]);
-            const float neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+            const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
+            float s = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) s = s + p24_ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
+            s = group_sum(s, gm);
+            const float v = (s / 24.0f) / 2.0f;
+            const float eo1 = 1.0f + expf(-obj);
+            float neg;
+            if (p.nc <= 80) {
+                float prod = 1.0f;
+                int nsat = 0;
+#pragma unroll
+                for (int q = 0; q < 10; ++q)
+                    if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
+                prod = group_prod(prod, gm);
+                nsat = group_sum_i(nsat, gm);
+                neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+            } else {
+                neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+            }
             if (sub == 0) {
-                float cost = p24_cost(cls_cost_from(neg, row[27 + c], 1.0f / eo1), v, true);
+                float cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
                 if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
                 S.wcost[wi] = cost;
             }
         }
     }
     __syncthreads();
+    TMARK(1, MCTA, 3);
     // ---- bracket the top-10 sum: L = sum of the 10 best seed values <= S <= 10 * H(t_max) = U ------------
     if (warp == 0) {
         const float sv = lane < N_SEED ? S.seedv[lane] : P24_NEG_INF;
@@ -871,12 +914,14 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
                 T = v;
             }
         }
-        float tmax = lane < MATCH_WARPS ? S.wmax[lane] : P24_NEG_INF;
-        tmax = warp_max(tmax);
+        float tm = lane < MATCH_WARPS ? S.wmax[lane] : P24_NEG_INF;
+        tm = warp_max(tm);
         int slow = 1, k = 0;
-        if (T > P24_NEG_INF && !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && tmax < 60000.0f) {
-            const float rgl = lane < P24_RAYS ? S.rec[GT_RG + lane] : 0.0f;
-            const float U = 10.0f * (bound_H(rgl, tmax * 1.0001f + 0.01f, lane) + 2e-5f);
+        const bool usable = T > P24_NEG_INF && !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && tm < 60000.0f;
+        if (usable) {
+            float U = 0.0f;
+            if (lane == 0) U = 10.0f * (bound_H_thread(S.rec, tm * 1.0001f + 0.01f) + 2e-5f);
+            U = __shfl_sync(0xffffffffu, U, 0);
             const float fl = floorf(L - 1e-4f), fu = floorf(U + 1e-4f);
             if (fl == fu && fl >= 1.0f) {
                 slow = 0;
@@ -884,15 +929,19 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
             }
         }
         if (lane == 0) {
-            S.slow = slow;
+            S.slow = slow ? (usable ? 1 : 2) : 0;  // 1: filtered exact path, 2: brute force
             S.k = k;
             S.T = T;
+            S.tmax = tm;
         }
     }
     __syncthreads();
+    TMARK(1, MCTA, 4);
     int k;
     if (S.slow) {
-        const float ksum = exact_topk_sum(p, S, b, kc, S.T);
+        float ksum = NAN;
+        if (S.slow == 1) ksum = topk_sum_filtered(p, S, b);
+        if (!(ksum == ksum)) ksum = topk_sum_bruteforce(p, S, b, kc);
         k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
         if (k < 1) k = 1;
     } else {
@@ -900,18 +949,16 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
     }
     k = min(k, ncand);  // torch.topk would raise beyond the candidate count; clamp instead
     if (tid == 0) p.dyn_k[wslot] = k;
+    TMARK(1, MCTA, 5);
 
-    // ---- the k smallest costs of the valid pairs -> claims ------------------------------------------------
-    if (warp == 0) {
-        int nvalid = 0;
-        for (int i = lane; i < nwin; i += 32) nvalid += (S.wcost[i] < P24_POS_INF) ? 1 : 0;
-        nvalid = warp_sum_i(nvalid);
-        const int take = min(k, nvalid);
-        // rank counting: entry i is selected iff fewer than `take` entries precede it in (cost, anchor) order
-        for (int i = lane; i < nwin; i += 32) {
-            const float ci = S.wcost[i];
-            if (!(ci < P24_POS_INF)) continue;
-            const int ai = S.wanchor[i];
+    // ---- the k smallest costs of the valid pairs -> claims (rank counting, one thread per window anchor) ------
+    {
+        const bool mine = tid < nwin && S.wcost[tid] < P24_POS_INF;
+        const int nv = __syncthreads_count(mine);
+        const int take = min(k, nv);
+        if (mine) {
+            const float ci = S.wcost[tid];
+            const int ai = S.wanchor[tid];
             int before = 0;
             for (int j = 0; j < nwin; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
             if (before < take) {
@@ -920,10 +967,16 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
                 p.claim_gt[o] = g;
             }
         }
-        if (lane == 0) S.nvalid = nvalid;
+        TMARK(1, MCTA, 6);
+        if (k > nv) {
+            __syncthreads();
+            spill_claims(p, S, b, g, nwin, k - nv);
+        }
     }
-    __syncthreads();
-    if (k > S.nvalid) spill_claims(p, S, b, g, nwin, k - S.nvalid);
+    TMARK(1, MCTA, 7);
+#ifdef P24_TIMING
+    if (tid == 0) g_tstamp[1][MCTA][8] = S.slow;
+#endif
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1039,7 +1092,9 @@ __device__ __noinline__ int resolve_conflict(const Params& p, const float* recs,
 }
 
 __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
+    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 0);
     pdl_wait();
+    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 1);
     const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int a = tile * P24_THREADS + tid;
@@ -1075,6 +1130,7 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
         }
     }
     __syncthreads();
+    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 2);
     const int nconf = s_nconf;
     for (int i = warp; i < nconf; i += P24_WARPS) {
         const int al = s_conf[i];
@@ -1088,6 +1144,7 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
         }
     }
     __syncthreads();
+    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 3);
     const int nfg = s_nfg;
     if (tid == 0 && nfg) atomicAdd(&p.num_fg[b], nfg);
 
@@ -1123,12 +1180,15 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
         }
     }
     if (!p.sums28) return;
+    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 4);
     if (lane < P24_RAYS) s_acc[warp][lane] = acc_ray;
     if (lane == 0) {
         s_acc[warp][24] = acc_obj;
         s_acc[warp][25] = acc_cls;
     }
     __syncthreads();
+    // ---- two-level, fixed-order reduction: tile partials -> image sums (last tile of the image) -> batch sums
+    // (last image) -> optional finalize.  Deterministic: every sum is formed in the same order on every run. -------
     const int blk = b * p.tiles + tile;
     if (tid < 26) {
         double t = 0.0;
@@ -1139,35 +1199,53 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned done = atomicAdd(p.ticket, 1u);
-        s_last = (done == (unsigned)(gridDim.x * gridDim.y) - 1u);
+        const unsigned done = atomicAdd(&p.img_ticket[b], 1u);
+        s_last = (done == (unsigned)gridDim.x - 1u);
     }
     __syncthreads();
+    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 5);
     if (!s_last) return;
     __threadfence();
-    // last block: fixed-order reduction of the partials -> deterministic sums
-    const int nblk = gridDim.x * gridDim.y;
     if (warp < 7) {
         for (int q = 0; q < 4; ++q) {
             const int col = warp * 4 + q;
             if (col < 26) {
                 double t = 0.0;
-                for (int i = lane; i < nblk; i += 32) t += __ldcg(p.loss_part + (long long)i * 28 + col);
+                for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(p.loss_part + ((long long)b * p.tiles + i) * 28 + col);
                 t = warp_sum_d(t);
-                if (lane == 0) s_sums[col] = (float)t;
-            } else {
-                int t = 0;
-                const int32_t* src = (col == 26) ? p.num_fg : p.num_gt;
-                for (int i = lane; i < p.B; i += 32) t += __ldcg(src + i);
-                t = warp_sum_i(t);
-                if (lane == 0) s_sums[col] = (float)t;
+                if (lane == 0) p.img_part[b * 28 + col] = t;
             }
         }
     }
+    __threadfence();
     __syncthreads();
-    if (tid < 28) p.sums28[tid] = s_sums[tid];
+    if (tid == 0) {
+        p.img_ticket[b] = 0u;  // ready for the next call
+        const unsigned done = atomicAdd(p.ticket, 1u);
+        s_last = (done == (unsigned)gridDim.y - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < 28) {
+        float r;
+        if (tid < 26) {
+            double t = 0.0;
+            for (int i = 0; i < p.B; ++i) t += __ldcg(p.img_part + i * 28 + tid);
+            r = (float)t;
+        } else {
+            int t = 0;
+            const int32_t* src = (tid == 26) ? p.num_fg : p.num_gt;
+            for (int i = 0; i < p.B; ++i) t += __ldcg(src + i);
+            r = (float)t;
+        }
+        s_sums[tid] = r;
+        p.sums28[tid] = r;
+    }
     if (tid == 0) *p.ticket = 0u;  // ready for the next call
+    __syncthreads();
     if (p.state26 && warp == 0) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
+    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 6);
 }
 
 __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__ state26, float* __restrict__ result54,
@@ -1232,7 +1310,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     if (workspace_bytes < L.total) return P24_E_WORKSPACE;
     if (((uintptr_t)workspace & 255) != 0) return P24_E_BADARG;
     const size_t dyn = anchor_pass_smem(Lmax);
-    if (dyn > 160 * 1024) return P24_E_UNSUPPORTED;
+    if (dyn > 160 * 1024 || p24_tiles(A) > MAX_TILES) return P24_E_UNSUPPORTED;
     char* ws = (char*)workspace;
     Params p;
     p.outputs = outputs; p.img_stride = img_stride; p.row_stride = row_stride;
@@ -1244,6 +1322,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.state26 = state26; p.result54 = result54; p.weights27 = weights_n27;
     p.gt_rec = (float*)(ws + L.gt_rec);
     p.clist = (float4*)(ws + L.clist);
+    p.clist2 = (float2*)(ws + L.clist2);
     p.ccount = (int*)(ws + L.ccount);
     p.wcount = (int*)(ws + L.wcount);
     p.wlist = (int*)(ws + L.wlist);
@@ -1251,6 +1330,8 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.claim_gt = (int*)(ws + L.claim_gt);
     p.obj_part = (double*)(ws + L.obj_part);
     p.loss_part = (double*)(ws + L.loss_part);
+    p.img_part = (double*)(ws + L.img_part);
+    p.img_ticket = (unsigned*)(ws + L.img_ticket);
     p.ticket = (unsigned*)(ws + L.ticket);
     p.err_flag = (int*)(ws + L.err_flag);
     p.flags = flags;
@@ -1265,7 +1346,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     const bool pdl = !(flags & P24_F_NO_PDL) && !g_prof_on;
     cudaError_t e;
     prof_mark(0, st);
-    e = launch(k_gt_prep, dim3(B), dim3(P24_THREADS), 0, st, pdl, p);
+    e = launch(k_gt_prep, dim3(B), dim3(PREP_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     prof_mark(1, st);
     e = launch(k_anchor_pass, dim3(p.tiles, B), dim3(P24_THREADS), dyn, st, pdl, p);
@@ -1309,3 +1390,9 @@ extern "C" int p24_profile_read(float* h_ms4) {
     }
     return 0;
 }
+
+#ifdef P24_TIMING
+extern "C" int p24_debug_read_timers(unsigned long long* h_out) {
+    return (int)cudaMemcpyFromSymbol(h_out, g_tstamp, sizeof(unsigned long long) * 3 * 4096 * 12);
+}
+#endif

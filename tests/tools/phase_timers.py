@@ -1,0 +1,49 @@
+"""Debug tool (GPU box): per-CTA phase timestamps of the SimOTA chain from the -DP24_TIMING build.
+Build first: nvcc ... -DP24_TIMING -o p24/_lib/libp24_timing.so (see tests/tools/README in DESIGN.md)."""
+import ctypes
+import os
+import sys
+import numpy as np
+ROOT = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+sys.path.insert(0, os.path.join(ROOT, "exploration-of-potential_b200"))
+sys.path.insert(0, ROOT)
+import torch
+from p24 import lib as p24_lib
+from p24 import synth
+lib = p24_lib.load(os.path.join(ROOT, "exploration-of-potential_b200", "p24", "_lib", "libp24_timing.so"))
+p24_lib._LIB = lib
+from p24.losses import Loss_Function
+
+B, size, G, Lmax = 20, 640, 20, 50
+dev = "cuda:0"
+sets = [(synth.make_head_outputs(B, size, 80, seed=1 + 100 * i).to(dev),
+         synth.make_labels(B, G, Lmax, size, 80, seed=1 + 100 * i, kind="smooth").to(dev)) for i in range(3)]
+xs, ys, ss = synth.make_grids(size)
+g = [[t.to(dev) for t in l] for l in (xs, ys, ss)]
+lf = Loss_Function(80)
+for i in range(6):
+    o, l = sets[i % 3]
+    lf.forward_async((g[0], g[1], g[2], o, []), l)
+torch.cuda.synchronize()
+buf = np.zeros((3, 4096, 12), dtype=np.uint64)
+lib.p24_debug_read_timers.argtypes = [ctypes.c_void_p]
+assert lib.p24_debug_read_timers(buf.ctypes.data) == 0
+t = buf.astype(np.int64)
+names = {0: ("k_anchor_pass", 660, ["start", "pdl", "rows+recs", "pass1/2 gen", "items", "end"]),
+         1: ("k_gt_match", 400, ["start", "pdl", "scan", "tasks", "bracket", "dyn_k", "select", "spill/end"]),
+         2: ("k_resolve_loss", 660, ["start", "pdl", "classify", "conflicts", "fg loss", "partials", "last"])}
+base = t[0, :660, 0].min()
+for k, (nm, ncta, ph) in names.items():
+    tt = t[k, :ncta, :len(ph)]
+    ok = tt[:, len(ph) - 2] > 0
+    print(f"== {nm}: first start {(tt[ok, 0].min() - base) / 1e3:.1f} us, last end {(tt[ok].max() - base) / 1e3:.1f} us after chain start")
+    for i in range(1, len(ph)):
+        valid = ok & (tt[:, i] > 0)
+        d = (tt[valid, i] - tt[valid, i - 1]) / 1e3
+        if d.size:
+            print(f"   {ph[i]:14s} mean {d.mean():7.2f} us  p50 {np.median(d):7.2f}  max {d.max():7.2f}  (n={d.size})")
+    if k == 1:
+        slow = t[1, :ncta, 8]
+        print("   slow-path CTAs:", int((slow != 0).sum()), "of", ncta)
+        tot = (tt[ok, 7] - tt[ok, 1]) / 1e3
+        print(f"   CTA total mean {tot.mean():.2f} us max {tot.max():.2f} us; slow ones: {np.round(tot[slow[ok] != 0], 1).tolist()[:20]}")
