@@ -41,9 +41,9 @@ struct P24Workspace {
     size_t claim_cnt;   // [B, A] int      number of GTs that selected the anchor
     size_t claim_gt;    // [B, A] int      the GT that selected the anchor (meaningful when claim_cnt == 1)
     size_t obj_part;    // [B * tiles] double   per-block sums of BCEWithLogits(obj, 0)
-    size_t loss_part;   // [B * tiles, 28] double
-    size_t img_part;    // [B, 28] double       per-image sums (second reduction level)
-    size_t img_ticket;  // [B] unsigned         tiles of the image that have finished (zero between calls)
+    size_t claimed;     // [B, 10 * Lmax] int   anchors claimed by at least one GT (arrival order)
+    size_t nclaimed;    // [B] int
+    size_t acc_fix;     // [B, 28] int64        fixed-point loss sums of the image (zero between calls)
     size_t ticket;      // [1] unsigned (last-block-done counter; zero between calls)
     size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
     size_t total;
@@ -60,7 +60,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
     w.wcount = off;     off = p24_align(off + BL * sizeof(int));
     w.ticket = off;     off = p24_align(off + sizeof(unsigned));
-    w.img_ticket = off; off = p24_align(off + (size_t)B * sizeof(unsigned));
+    w.acc_fix = off;    off = p24_align(off + (size_t)B * 28 * sizeof(long long));
     w.err_flag = off;   off = p24_align(off + sizeof(int));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
     w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
@@ -70,8 +70,8 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
     w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));
     w.obj_part = off;   off = p24_align(off + NB * sizeof(double));
-    w.loss_part = off;  off = p24_align(off + NB * 28 * sizeof(double));
-    w.img_part = off;   off = p24_align(off + (size_t)B * 28 * sizeof(double));
+    w.claimed = off;    off = p24_align(off + BL * P24_TOPK * sizeof(int));
+    w.nclaimed = off;   off = p24_align(off + (size_t)B * sizeof(int));
     w.total = off;
     return w;
 }

@@ -58,9 +58,9 @@ struct Params {
     int* claim_cnt;
     int* claim_gt;
     double* obj_part;
-    double* loss_part;
-    double* img_part;
-    unsigned* img_ticket;
+    int* claimed;
+    int* nclaimed;
+    long long* acc_fix;
     unsigned* ticket;
     int* err_flag;
     unsigned flags;
@@ -376,26 +376,35 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
     }
     double objpart = active ? (double)p24_bce_logits(obj, 0.0f) : 0.0;
 
-    // ---- pass 1 over the GTs: centre windows (-> per-GT lists) and the inscribed-disc accept ------------
+    // ---- pass 1 over the GTs: centre windows (-> per-GT lists) and the inscribed-disc accept.  The loops are
+    // warp-uniform so that list slots are allocated with one shared-memory atomic per warp (ballot + prefix) ----
     bool cheap = false;
-    if (active) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    {
         const float r25 = 2.5f * st + 1e-3f * st;  // conservative pre-filter radius of the window test
         for (int g = 0; g < n; ++g) {
             const float4 h = s_dyn4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             const float d2 = fmaf(dx, dx, dy * dy);
-            cheap |= d2 < h.z;
-            if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) {
-                cheap = true;
+            cheap |= active && d2 < h.z;
+            const bool inwin = active && fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st);
+            const unsigned bal = __ballot_sync(0xffffffffu, inwin);
+            if (bal) {
                 // (anchor, GT) goes to the GT's centre-window list; staged in shared memory so that the global
                 // atomics of a tile are issued together instead of one round trip at a time
-                const int ws = atomicAdd(&s_nwin, 1);
-                if (ws < WIN_CAP) {
-                    s_win[ws] = (unsigned)tid | ((unsigned)g << 8);
-                } else {
-                    const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
-                    if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
-                    else atomicOr(p.err_flag, 1);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nwin, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (inwin) {
+                    cheap = true;
+                    const int ws = base + __popc(bal & lt_mask);
+                    if (ws < WIN_CAP) {
+                        s_win[ws] = (unsigned)tid | ((unsigned)g << 8);
+                    } else {
+                        const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
+                        if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
+                        else atomicOr(p.err_flag, 1);
+                    }
                 }
             }
         }
@@ -405,19 +414,28 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
     // ---- pass 2: anchors not yet accepted need a polygon test against every GT whose reject radius they are
     // inside; the tests go to a work list so that all threads stay busy (a full list is handled in place) --------
     bool mine = false;
-    if (active && (!cheap || no_prune)) {
-        for (int g = 0; g < n; ++g) {
-            const float4 h = s_dyn4[g * (GT_REC / 4)];
-            const float dx = h.x - xc, dy = h.y - yc;
-            const float d2 = fmaf(dx, dx, dy * dy);
-            if (no_prune || d2 <= h.w) {
-                const int slot = atomicAdd(&s_nitems, 1);
-                if (slot < ITEM_CAP) {
-                    s_items[slot] = (unsigned)tid | ((unsigned)g << 8);
-                } else if (!mine) {
-                    const float* rec = s_gt + g * GT_REC;
-                    mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
-                                    : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
+    {
+        const bool todo = active && (!cheap || no_prune);
+        if (__any_sync(0xffffffffu, todo)) {
+            for (int g = 0; g < n; ++g) {
+                const float4 h = s_dyn4[g * (GT_REC / 4)];
+                const float dx = h.x - xc, dy = h.y - yc;
+                const float d2 = fmaf(dx, dx, dy * dy);
+                const bool need = todo && (no_prune || d2 <= h.w);
+                const unsigned bal = __ballot_sync(0xffffffffu, need);
+                if (!bal) continue;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nitems, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (need) {
+                    const int slot = base + __popc(bal & lt_mask);
+                    if (slot < ITEM_CAP) {
+                        s_items[slot] = (unsigned)tid | ((unsigned)g << 8);
+                    } else if (!mine) {
+                        const float* rec = s_gt + g * GT_REC;
+                        mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
+                                        : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
+                    }
                 }
             }
         }
@@ -474,8 +492,16 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
         p.clist[blk * P24_THREADS + rank] = make_float4(pcx, pcy, rpmin < 0.25f ? INFINITY : rpmax, __int_as_float(a));
         p.clist2[blk * P24_THREADS + rank] = make_float2(rp2sum * (1.0f / 24.0f), rpsum * (1.0f / 24.0f));
     }
-    if (active) p.claim_cnt[(long long)b * p.A + a] = 0;
+    if (active) {
+        // every anchor starts as background; k_resolve_loss overwrites the claimed ones
+        const long long o = (long long)b * p.A + a;
+        p.claim_cnt[o] = 0;
+        p.fg_mask[o] = 0;
+        p.matched_gt[o] = -1;
+        p.pred_iou[o] = 0.0f;
+    }
     if (tid == 0) {
+        if (tile == 0) p.nclaimed[b] = 0;
         p.ccount[blk] = total;
         double t = 0.0;
         for (int w = 0; w < P24_WARPS; ++w) t += s_red[w];
@@ -487,6 +513,18 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
 // -------------------------------------------------------------------------------------------
 // k_gt_match
 // -------------------------------------------------------------------------------------------
+// GT g selects anchor a: count the claim; the first claimant also puts the anchor on the image's claimed list
+__device__ __forceinline__ void claim_anchor(const Params& p, int b, int a, int g) {
+    const long long o = (long long)b * p.A + a;
+    const int old = atomicAdd(&p.claim_cnt[o], 1);
+    p.claim_gt[o] = g;
+    if (old == 0) {
+        const int slot = atomicAdd(&p.nclaimed[b], 1);
+        if (slot < P24_TOPK * p.Lmax) p.claimed[(long long)b * P24_TOPK * p.Lmax + slot] = a;
+        else atomicOr(p.err_flag, 2);
+    }
+}
+
 #define HIT_CAP 3072
 #define EV_CAP 256
 #define N_SEED (2 * MATCH_WARPS)
@@ -730,9 +768,7 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
         const KV win = match_block_select<false>(head, S.kv);
         if (win.i == 0x7fffffff) break;  // fewer candidates than needed
         if (li[0] == win.i && lv[0] == win.v) {
-            const long long o = (long long)b * p.A + win.i;
-            atomicAdd(&p.claim_cnt[o], 1);
-            p.claim_gt[o] = g;
+            claim_anchor(p, b, win.i, g);
 #pragma unroll
             for (int q = 0; q < P24_TOPK - 1; ++q) {
                 lv[q] = lv[q + 1];
@@ -788,26 +824,38 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
         const int nslot = p.tiles * P24_THREADS;
         const float4* cl = p.clist + (long long)b * p.tiles * P24_THREADS;
         const float2* cl2 = p.clist2 + (long long)b * p.tiles * P24_THREADS;
-#pragma unroll 4
-        for (int i0 = tid; i0 < nslot; i0 += MATCH_THREADS) {
-            if ((i0 & 255) >= S.ccount[i0 >> 8]) continue;
-            const float4 c4 = cl[i0];
-            const float2 c2 = cl2[i0];
-            const float dx = gcx - c4.x, dy = gcy - c4.y;
-            const float d2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-12f);
-            const float d = d2 * rsqrtf(d2);
-            tmax = fmaxf(tmax, c4.z + d);
-            const float den = (rgmean + c2.y) + d;
-            const float q = __fdividef(rgms + c2.x, den * den);
-            const int a = __float_as_int(c4.w);
-            if (kv_lt(q, a, q1, a1)) {
-                q2 = q1;
-                a2 = a1;
-                q1 = q;
-                a1 = a;
-            } else if (kv_lt(q, a, q2, a2)) {
-                q2 = q;
-                a2 = a;
+        for (int base = tid; base < nslot; base += 4 * MATCH_THREADS) {
+            float4 c4[4];
+            float2 c2[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // all loads of the batch are in flight before the first use
+                const int i0 = base + u * MATCH_THREADS;
+                ok[u] = i0 < nslot && (i0 & 255) < S.ccount[i0 >> 8];
+                if (ok[u]) {
+                    c4[u] = cl[i0];
+                    c2[u] = cl2[i0];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u]) continue;
+                const float dx = gcx - c4[u].x, dy = gcy - c4[u].y;
+                const float d2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-12f);
+                const float d = d2 * rsqrtf(d2);
+                tmax = fmaxf(tmax, c4[u].z + d);
+                const float den = (rgmean + c2[u].y) + d;
+                const float q = __fdividef(rgms + c2[u].x, den * den);
+                const int a = __float_as_int(c4[u].w);
+                if (kv_lt(q, a, q1, a1)) {
+                    q2 = q1;
+                    a2 = a1;
+                    q1 = q;
+                    a1 = a;
+                } else if (kv_lt(q, a, q2, a2)) {
+                    q2 = q;
+                    a2 = a;
+                }
             }
         }
         const KV w1 = warp_select<false>(KV{q1, a1});
@@ -854,16 +902,22 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
             for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
             const float xc = p24_anchor_centre(xs, st);
             const float yc = p24_anchor_centre(ys, st);
-            float ang = 0.0f;
+            {
+                // inside the inscribed disc the angle sum is >= 360 (see k_gt_prep): no edge terms needed
+                const float ddx = gcx - xc, ddy = gcy - yc;
+                if (!(fmaf(ddx, ddx, ddy * ddy) < S.rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
+                    float ang = 0.0f;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int k = sub * 3 + q;
-                const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
-                ang = ang + p24_edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
-                                           S.rec[GT_VY + k2] - yc);
+                    for (int q = 0; q < 3; ++q) {
+                        const int k = sub * 3 + q;
+                        const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
+                        ang = ang + p24_edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
+                                                   S.rec[GT_VY + k2] - yc);
+                    }
+                    ang = group_sum(ang, gm);
+                    if (!(ang >= 350.0f)) continue;  // losses.py:588
+                }
             }
-            ang = group_sum(ang, gm);
-            if (!(ang >= 350.0f)) continue;  // losses.py:588
             const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
             float s = 0.0f;
 #pragma unroll
@@ -919,9 +973,13 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
         int slow = 1, k = 0;
         const bool usable = T > P24_NEG_INF && !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && tm < 60000.0f;
         if (usable) {
-            float U = 0.0f;
-            if (lane == 0) U = 10.0f * (bound_H_thread(S.rec, tm * 1.0001f + 0.01f) + 2e-5f);
-            U = __shfl_sync(0xffffffffu, U, 0);
+            float term = 0.0f;
+            if (lane < P24_RAYS) {
+                const float rg = S.rec[GT_RG + lane];
+                const float q = rg + (tm * 1.0001f + 0.01f);
+                term = fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, q * q));
+            }
+            const float U = 10.0f * (warp_sum(term) * (1.0f / 48.0f) + 2e-5f);
             const float fl = floorf(L - 1e-4f), fu = floorf(U + 1e-4f);
             if (fl == fu && fl >= 1.0f) {
                 slow = 0;
@@ -961,11 +1019,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
             const int ai = S.wanchor[tid];
             int before = 0;
             for (int j = 0; j < nwin; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
-            if (before < take) {
-                const long long o = (long long)b * p.A + ai;
-                atomicAdd(&p.claim_cnt[o], 1);
-                p.claim_gt[o] = g;
-            }
+            if (before < take) claim_anchor(p, b, ai, g);
         }
         TMARK(1, MCTA, 6);
         if (k > nv) {
@@ -1091,79 +1145,46 @@ __device__ __noinline__ int resolve_conflict(const Params& p, const float* recs,
     return best.i != 0x7fffffff ? best.i : 0;
 }
 
+#define FIX_SCALE 68719476736.0  // 2^36: fixed-point unit of the loss accumulators (order-independent sums)
+#define RESOLVE_GRID_X 32
+
+__device__ __forceinline__ long long to_fix(double x) { return __double2ll_rn(x * FIX_SCALE); }
+
 __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 0);
     pdl_wait();
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 1);
-    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int a = tile * P24_THREADS + tid;
     const int n = p.num_gt[b];
-    __shared__ int s_fg[P24_THREADS];    // a_local | g << 8
-    __shared__ int s_conf[P24_THREADS];  // a_local of anchors claimed by several GTs
-    __shared__ int s_nfg, s_nconf;
-    __shared__ double s_acc[P24_WARPS][28];
+    __shared__ long long s_acc[P24_WARPS][26];
     __shared__ float s_sums[28];
     __shared__ bool s_last;
-    if (tid == 0) {
-        s_nfg = 0;
-        s_nconf = 0;
-    }
-    __syncthreads();
 
     const float* img = p.outputs + (long long)b * p.img_stride;
     const float* recs = p.gt_rec + (long long)b * p.Lmax * GT_REC;
-    if (a < p.A) {
-        const long long o = (long long)b * p.A + a;
-        const int cnt = n > 0 ? p.claim_cnt[o] : 0;
-        if (cnt == 1) {
-            const int g = p.claim_gt[o];
-            p.fg_mask[o] = 1;
-            p.matched_gt[o] = g;
-            s_fg[atomicAdd(&s_nfg, 1)] = tid | (g << 8);
-        } else if (cnt > 1) {
-            s_conf[atomicAdd(&s_nconf, 1)] = tid;
-        } else {
-            p.fg_mask[o] = 0;
-            p.matched_gt[o] = -1;
-            p.pred_iou[o] = 0.0f;
-        }
-    }
-    __syncthreads();
-    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 2);
-    const int nconf = s_nconf;
-    for (int i = warp; i < nconf; i += P24_WARPS) {
-        const int al = s_conf[i];
-        const int aa = tile * P24_THREADS + al;
-        const int g = resolve_conflict(p, recs, n, img + (long long)aa * p.row_stride, aa);
-        if (lane == 0) {
-            const long long o = (long long)b * p.A + aa;
-            p.fg_mask[o] = 1;
-            p.matched_gt[o] = g;
-            s_fg[atomicAdd(&s_nfg, 1)] = al | (g << 8);
-        }
-    }
-    __syncthreads();
-    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 3);
-    const int nfg = s_nfg;
-    if (tid == 0 && nfg) atomicAdd(&p.num_fg[b], nfg);
+    const int nclaim = min(p.nclaimed[b], P24_TOPK * p.Lmax);
+    if (blockIdx.x == 0 && tid == 0) p.num_fg[b] = nclaim;  // every claimed anchor ends up foreground (losses.py:479)
 
-    // ---- loss terms of the foreground anchors: one warp per anchor, lanes over rays / classes --------
-    double acc_ray = 0.0;  // lane k < 24: sum of loss24[:, k]
-    double acc_obj = 0.0;  // lane 0: -sum of obj logits at fg
-    double acc_cls = 0.0;  // lane 0: cls BCE
-    for (int i = warp; i < nfg; i += P24_WARPS) {
-        const int al = s_fg[i] & 0xFF, g = s_fg[i] >> 8;
-        const int aa = tile * P24_THREADS + al;
-        const float* rec = recs + g * GT_REC;
+    // ---- one warp per claimed anchor: conflict resolution, outputs, loss terms (lanes over rays / classes).
+    // Contributions are accumulated as 2^-36 fixed-point integers: the sums do not depend on the list order. ------
+    long long acc = 0;  // lane k < 24: sum of loss24[:, k]; lane 24: -sum of obj logits at fg; lane 25: cls BCE
+    for (int e = blockIdx.x * P24_WARPS + warp; e < nclaim; e += gridDim.x * P24_WARPS) {
+        const int aa = p.claimed[(long long)b * P24_TOPK * p.Lmax + e];
+        const long long o = (long long)b * p.A + aa;
         const float* row = img + (long long)aa * p.row_stride;
+        const int cnt = p.claim_cnt[o];
+        int g = p.claim_gt[o];
+        if (cnt > 1) g = resolve_conflict(p, recs, n, row, aa);
+        const float* rec = recs + g * GT_REC;
         float l;
         const float v = warp_pair_value(rec, row, l);  // pair value == pred_ious_this_matching (losses.py:491)
-        acc_ray += (double)l;
         if (lane == 0) {
-            p.pred_iou[(long long)b * p.A + aa] = v;
-            acc_obj -= (double)row[26];
+            p.fg_mask[o] = 1;
+            p.matched_gt[o] = g;
+            p.pred_iou[o] = v;
         }
+        double contrib = (double)l;
         if (p.sums28) {
             // sum_j BCEWithLogits(x_j, t_j), t = v at the GT class and 0 elsewhere (losses.py:246-248, 298-302):
             // sum_j softplus(x_j) - x_c * v, the softplus sum in product form (one log per anchor)
@@ -1176,74 +1197,57 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
             }
             prod = warp_prod(prod);
             big = warp_sum(big);
-            if (lane == 0) acc_cls += ((double)logf(prod) + (double)big) - (double)row[27 + c] * (double)v;
+            if (lane == 24) contrib = -(double)row[26];
+            if (lane == 25) contrib = ((double)logf(prod) + (double)big) - (double)row[27 + c] * (double)v;
         }
+        if (lane < 26) acc += to_fix(contrib);
     }
     if (!p.sums28) return;
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 4);
-    if (lane < P24_RAYS) s_acc[warp][lane] = acc_ray;
-    if (lane == 0) {
-        s_acc[warp][24] = acc_obj;
-        s_acc[warp][25] = acc_cls;
-    }
+    if (lane < 26) s_acc[warp][lane] = acc;
     __syncthreads();
-    // ---- two-level, fixed-order reduction: tile partials -> image sums (last tile of the image) -> batch sums
-    // (last image) -> optional finalize.  Deterministic: every sum is formed in the same order on every run. -------
-    const int blk = b * p.tiles + tile;
     if (tid < 26) {
-        double t = 0.0;
+        long long t = 0;
+#pragma unroll
         for (int w = 0; w < P24_WARPS; ++w) t += s_acc[w][tid];
-        if (tid == 24) t += p.obj_part[blk];
-        p.loss_part[(long long)blk * 28 + tid] = t;
+        if (t != 0) atomicAdd((unsigned long long*)&p.acc_fix[b * 28 + tid], (unsigned long long)t);
     }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned done = atomicAdd(&p.img_ticket[b], 1u);
-        s_last = (done == (unsigned)gridDim.x - 1u);
+        const unsigned done = atomicAdd(p.ticket, 1u);
+        s_last = (done == (unsigned)(gridDim.x * gridDim.y) - 1u);
     }
     __syncthreads();
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 5);
     if (!s_last) return;
     __threadfence();
-    if (warp < 7) {
-        for (int q = 0; q < 4; ++q) {
-            const int col = warp * 4 + q;
-            if (col < 26) {
-                double t = 0.0;
-                for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(p.loss_part + ((long long)b * p.tiles + i) * 28 + col);
-                t = warp_sum_d(t);
-                if (lane == 0) p.img_part[b * 28 + col] = t;
-            }
+    // ---- last CTA: batch sums (integer adds over the images: exact), the all-anchor objectness term in a fixed
+    // order, then the optional finalize ------------------------------------------------------------------------------
+    if (tid < 26) {
+        long long t = 0;
+        for (int i = 0; i < p.B; ++i) {
+            t += __ldcg(&p.acc_fix[i * 28 + tid]);
+            p.acc_fix[i * 28 + tid] = 0;  // ready for the next call
         }
+        s_sums[tid] = (float)((double)t / FIX_SCALE);
+    } else if (tid == 26 || tid == 27) {
+        int t = 0;
+        const int32_t* src = (tid == 26) ? p.nclaimed : p.num_gt;
+        for (int i = 0; i < p.B; ++i) t += min(__ldcg(src + i), tid == 26 ? P24_TOPK * p.Lmax : 0x7fffffff);
+        s_sums[tid] = (float)t;
     }
-    __threadfence();
+    double objsum = 0.0;
+    if (warp == 1) {
+        const int nblk = p.B * p.tiles;
+        for (int i = lane; i < nblk; i += 32) objsum += __ldcg(p.obj_part + i);
+        objsum = warp_sum_d(objsum);
+    }
     __syncthreads();
-    if (tid == 0) {
-        p.img_ticket[b] = 0u;  // ready for the next call
-        const unsigned done = atomicAdd(p.ticket, 1u);
-        s_last = (done == (unsigned)gridDim.y - 1u);
-    }
+    if (tid == 32) s_sums[24] = (float)((double)s_sums[24] + objsum);
     __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (tid < 28) {
-        float r;
-        if (tid < 26) {
-            double t = 0.0;
-            for (int i = 0; i < p.B; ++i) t += __ldcg(p.img_part + i * 28 + tid);
-            r = (float)t;
-        } else {
-            int t = 0;
-            const int32_t* src = (tid == 26) ? p.num_fg : p.num_gt;
-            for (int i = 0; i < p.B; ++i) t += __ldcg(src + i);
-            r = (float)t;
-        }
-        s_sums[tid] = r;
-        p.sums28[tid] = r;
-    }
+    if (tid < 28) p.sums28[tid] = s_sums[tid];
     if (tid == 0) *p.ticket = 0u;  // ready for the next call
-    __syncthreads();
     if (p.state26 && warp == 0) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 6);
 }
@@ -1329,9 +1333,9 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.claim_cnt = (int*)(ws + L.claim_cnt);
     p.claim_gt = (int*)(ws + L.claim_gt);
     p.obj_part = (double*)(ws + L.obj_part);
-    p.loss_part = (double*)(ws + L.loss_part);
-    p.img_part = (double*)(ws + L.img_part);
-    p.img_ticket = (unsigned*)(ws + L.img_ticket);
+    p.claimed = (int*)(ws + L.claimed);
+    p.nclaimed = (int*)(ws + L.nclaimed);
+    p.acc_fix = (long long*)(ws + L.acc_fix);
     p.ticket = (unsigned*)(ws + L.ticket);
     p.err_flag = (int*)(ws + L.err_flag);
     p.flags = flags;
@@ -1355,7 +1359,10 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     e = launch(k_gt_match, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     prof_mark(3, st);
-    e = launch(k_resolve_loss, dim3(p.tiles, B), dim3(P24_THREADS), 0, st, pdl, p);
+    {
+        const int gx = (P24_TOPK * Lmax + P24_WARPS - 1) / P24_WARPS;
+        e = launch(k_resolve_loss, dim3(gx < RESOLVE_GRID_X ? gx : RESOLVE_GRID_X, B), dim3(P24_THREADS), 0, st, pdl, p);
+    }
     if (e != cudaSuccess) return (int)e;
     prof_mark(4, st);
     return (int)cudaGetLastError();

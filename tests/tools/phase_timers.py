@@ -31,15 +31,20 @@ assert lib.p24_debug_read_timers(buf.ctypes.data) == 0
 t = buf.astype(np.int64)
 names = {0: ("k_anchor_pass", 660, ["start", "pdl", "rows+recs", "pass1/2 gen", "items", "end"]),
          1: ("k_gt_match", 400, ["start", "pdl", "scan", "tasks", "bracket", "dyn_k", "select", "spill/end"]),
-         2: ("k_resolve_loss", 660, ["start", "pdl", "classify", "conflicts", "fg loss", "partials", "last"])}
+         2: ("k_resolve_loss", 640, ["start", "pdl", "-", "-", "entries", "partials", "last"])}
 base = t[0, :660, 0].min()
 for k, (nm, ncta, ph) in names.items():
     tt = t[k, :ncta, :len(ph)]
     ok = tt[:, len(ph) - 2] > 0
     print(f"== {nm}: first start {(tt[ok, 0].min() - base) / 1e3:.1f} us, last end {(tt[ok].max() - base) / 1e3:.1f} us after chain start")
     for i in range(1, len(ph)):
-        valid = ok & (tt[:, i] > 0)
-        d = (tt[valid, i] - tt[valid, i - 1]) / 1e3
+        if ph[i] == "-":
+            continue
+        j = i - 1
+        while ph[j] == "-":
+            j -= 1
+        valid = ok & (tt[:, i] > 0) & (tt[:, j] > 0)
+        d = (tt[valid, i] - tt[valid, j]) / 1e3
         if d.size:
             print(f"   {ph[i]:14s} mean {d.mean():7.2f} us  p50 {np.median(d):7.2f}  max {d.max():7.2f}  (n={d.size})")
     if k == 1:
