@@ -34,7 +34,9 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 struct P24Workspace {
     size_t gt_rec;      // [B, Lmax, GT_REC] float
     size_t clist;       // [B, tiles, 256] float4  candidate anchors of a tile, compacted: (pred cx, pred cy, rpmax, anchor idx bits)
-    size_t clist2;      // [B, tiles, 256] float2  (mean rp^2, mean rp) of the same candidates (seed ranking)
+    size_t wseed;       // [B, Lmax, tiles * 8] float4  per (GT, warp of the anchor pass): the two candidates with the smallest
+                        //                              seed proxy (q1, anchor1, q2, anchor2)
+    size_t wtmax;       // [B, Lmax, tiles * 8] float   largest t = rpmax + d of the warp's candidates
     size_t ccount;      // [B, tiles] int          candidates per tile
     size_t wcount;      // [B, Lmax] int           anchors inside the GT's centre window (zero between calls)
     size_t wlist;       // [B, Lmax, VCAP] int
@@ -65,7 +67,8 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
     w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
     w.ccount = off;     off = p24_align(off + NB * sizeof(int));
-    w.clist2 = off;     off = p24_align(off + NB * P24_THREADS * 2 * sizeof(float));
+    w.wseed = off;      off = p24_align(off + BL * (size_t)p24_tiles(A) * P24_WARPS * 4 * sizeof(float));
+    w.wtmax = off;      off = p24_align(off + BL * (size_t)p24_tiles(A) * P24_WARPS * sizeof(float));
     w.wlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));
     w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
     w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));

@@ -51,7 +51,8 @@ struct Params {
     // workspace
     float* gt_rec;
     float4* clist;
-    float2* clist2;
+    float4* wseed;
+    float* wtmax;
     int* ccount;
     int* wcount;
     int* wlist;
@@ -217,12 +218,17 @@ __global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(Params p) {
 // -------------------------------------------------------------------------------------------
 // shared device helpers
 // -------------------------------------------------------------------------------------------
+// Out-of-line copies of the two heavy scalar routines: the kernels call them from many places, and inlining every
+// call made k_gt_match 17k instructions long (instruction-cache bound).
+__device__ __noinline__ float ray_loss(float rg, float rp, float d) { return p24_ray_loss(rg, rp, d); }
+__device__ __noinline__ float edge_angle(float sx, float sy, float ex, float ey) { return p24_edge_angle(sx, sy, ex, ey); }
+
 // exact pair value of (GT record, prediction row in global memory): utils/boxes.py:166-243, one thread
-__device__ float pair_value_row(const float* __restrict__ rec, const float* __restrict__ row) {
+__device__ __noinline__ float pair_value_row(const float* __restrict__ rec, const float* __restrict__ row) {
     const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
     float s = 0.0f;
 #pragma unroll 1
-    for (int k = 0; k < P24_RAYS; ++k) s = s + p24_ray_loss(rec[GT_RG + k], row[2 + k], d);
+    for (int k = 0; k < P24_RAYS; ++k) s = s + ray_loss(rec[GT_RG + k], row[2 + k], d);
     return (s / 24.0f) / 2.0f;
 }
 
@@ -231,10 +237,10 @@ __device__ __forceinline__ float group_pair_value(const float* __restrict__ rec,
     const int sub = threadIdx.x & 7;
     const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
     float s = 0.0f;
-#pragma unroll
+#pragma unroll 1
     for (int q = 0; q < 3; ++q) {
         const int k = sub * 3 + q;
-        s = s + p24_ray_loss(rec[GT_RG + k], row[2 + k], d);
+        s = s + ray_loss(rec[GT_RG + k], row[2 + k], d);
     }
     s = group_sum(s, m);
     return (s / 24.0f) / 2.0f;
@@ -246,7 +252,7 @@ __device__ __forceinline__ int gt_class(const float* rec, int nc) {
 }
 
 // Sum over all classes of BCE(p_j, 0) (losses.py:406-416) in product form, by the 32 lanes of a warp
-__device__ float warp_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1) {
+__device__ __noinline__ float warp_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1) {
     const int lane = threadIdx.x & 31;
     float prod = 1.0f;
     int nsat = 0;
@@ -263,7 +269,7 @@ __device__ float warp_cls_neg_sum(const float* __restrict__ cls, int nc, float e
 }
 
 // ... by the 8 lanes of a group
-__device__ float group_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1, unsigned m) {
+__device__ __noinline__ float group_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1, unsigned m) {
     const int sub = threadIdx.x & 7;
     float prod = 1.0f;
     int nsat = 0;
@@ -280,7 +286,7 @@ __device__ float group_cls_neg_sum(const float* __restrict__ cls, int nc, float 
 }
 
 // ... by a single thread (rare slow paths)
-__device__ float thread_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1) {
+__device__ __noinline__ float thread_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1) {
     const float obj_sig = 1.0f / eo1;
     float s = 0.0f;
     for (int j = 0; j < nc; ++j) s += p24_bce_neg(p24_joint_prob(cls[j], obj_sig));
@@ -308,7 +314,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-__global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
+__global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
     extern __shared__ float4 s_dyn4[];
     float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC]
     const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
@@ -376,67 +382,63 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
     }
     double objpart = active ? (double)p24_bce_logits(obj, 0.0f) : 0.0;
 
-    // ---- pass 1 over the GTs: centre windows (-> per-GT lists) and the inscribed-disc accept.  The loops are
-    // warp-uniform so that list slots are allocated with one shared-memory atomic per warp (ballot + prefix) ----
+    // ---- one pass over the GTs: centre windows (-> per-GT lists), the inscribed-disc accept, and a bit mask of the
+    // GTs whose reject radius the anchor is inside (the only ones that may need a polygon test) ------------------
     bool cheap = false;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const bool no_prune = (p.flags & P24_F_NO_PRUNE) != 0;
+    unsigned near[4] = {0u, 0u, 0u, 0u};  // GTs 0..127; beyond that every GT counts as near (see below)
     {
         const float r25 = 2.5f * st + 1e-3f * st;  // conservative pre-filter radius of the window test
         for (int g = 0; g < n; ++g) {
             const float4 h = s_dyn4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             const float d2 = fmaf(dx, dx, dy * dy);
-            cheap |= active && d2 < h.z;
-            const bool inwin = active && fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st);
-            const unsigned bal = __ballot_sync(0xffffffffu, inwin);
-            if (bal) {
+            cheap |= d2 < h.z;
+            if (g < 128 && (d2 <= h.w || no_prune)) near[g >> 5] |= 1u << (g & 31);
+            if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && active && p24_in_centre(h.x, h.y, xc, yc, st)) {
+                cheap = true;
                 // (anchor, GT) goes to the GT's centre-window list; staged in shared memory so that the global
                 // atomics of a tile are issued together instead of one round trip at a time
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_nwin, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (inwin) {
-                    cheap = true;
-                    const int ws = base + __popc(bal & lt_mask);
-                    if (ws < WIN_CAP) {
-                        s_win[ws] = (unsigned)tid | ((unsigned)g << 8);
-                    } else {
-                        const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
-                        if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
-                        else atomicOr(p.err_flag, 1);
-                    }
+                const int ws = atomicAdd(&s_nwin, 1);
+                if (ws < WIN_CAP) {
+                    s_win[ws] = (unsigned)tid | ((unsigned)g << 8);
+                } else {
+                    const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
+                    if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
+                    else atomicOr(p.err_flag, 1);
                 }
             }
         }
     }
-    const bool no_prune = (p.flags & P24_F_NO_PRUNE) != 0;
+    cheap = cheap && active;
 
-    // ---- pass 2: anchors not yet accepted need a polygon test against every GT whose reject radius they are
-    // inside; the tests go to a work list so that all threads stay busy (a full list is handled in place) --------
+    // ---- anchors not yet accepted need a polygon test against every near GT; the tests go to a work list so that
+    // all threads stay busy (a full list is handled in place) ---------------------------------------------------
     bool mine = false;
-    {
-        const bool todo = active && (!cheap || no_prune);
-        if (__any_sync(0xffffffffu, todo)) {
-            for (int g = 0; g < n; ++g) {
-                const float4 h = s_dyn4[g * (GT_REC / 4)];
-                const float dx = h.x - xc, dy = h.y - yc;
-                const float d2 = fmaf(dx, dx, dy * dy);
-                const bool need = todo && (no_prune || d2 <= h.w);
-                const unsigned bal = __ballot_sync(0xffffffffu, need);
-                if (!bal) continue;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_nitems, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (need) {
-                    const int slot = base + __popc(bal & lt_mask);
-                    if (slot < ITEM_CAP) {
-                        s_items[slot] = (unsigned)tid | ((unsigned)g << 8);
-                    } else if (!mine) {
-                        const float* rec = s_gt + g * GT_REC;
-                        mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
-                                        : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
-                    }
+    if (active && (!cheap || no_prune)) {
+        for (int w = 0; w < 4; ++w) {
+            unsigned m = near[w];
+            while (m) {
+                const int g = w * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const int slot = atomicAdd(&s_nitems, 1);
+                if (slot < ITEM_CAP) {
+                    s_items[slot] = (unsigned)tid | ((unsigned)g << 8);
+                } else if (!mine) {
+                    const float* rec = s_gt + g * GT_REC;
+                    mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
+                                    : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
                 }
+            }
+        }
+        for (int g = 128; g < n && !mine; ++g) {  // more than 128 GTs: test the rest in place
+            const float4 h = s_dyn4[g * (GT_REC / 4)];
+            const float dx = h.x - xc, dy = h.y - yc;
+            if (no_prune || fmaf(dx, dx, dy * dy) <= h.w) {
+                const float* rec = s_gt + g * GT_REC;
+                mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
+                                : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
             }
         }
     }
@@ -473,6 +475,50 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
     TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 4);
     // ---- compacted candidate list of the tile (deterministic order) + per-anchor scratch reset ----------
     const bool cand = active && (n > 0) && (cheap || s_cand[tid]);
+    // ---- seeds of the top-10 search: lane g of every warp ranks the warp's candidates for GT g by the first-order
+    // proxy q = (mean rg^2 + mean rp^2) / (mean rg + mean rp + d)^2 of the pair value (value ~ 1 - q / 3 for far
+    // pairs; the smallest q are almost always the true top-10) and records the largest t = rpmax + d -----------
+    s_row[warp][2][lane] = rp2sum * (1.0f / 24.0f);
+    s_row[warp][3][lane] = rpsum * (1.0f / 24.0f);
+    s_row[warp][4][lane] = cand ? (rpmin < 0.25f ? INFINITY : rpmax) : -1.0f;
+    __syncthreads();
+    {
+        // warp w looks at anchors i = 8 j + ((w - j) & 7), j = 0..31, of the tile: neighbouring anchors (which have
+        // nearly equal proxies) land in different warps, so the per-warp best two keep the whole top of the tile
+        const int nw = p.tiles * P24_WARPS;
+        for (int g = lane; g < n; g += 32) {
+            const float* rec = s_gt + g * GT_REC;
+            const float gcx = rec[GT_CX], gcy = rec[GT_CY], rgms = rec[GT_RGMS], rgmean = rec[GT_RGMEAN];
+            float q1 = P24_POS_INF, q2 = P24_POS_INF, tmax = P24_NEG_INF;
+            int a1 = 0x7fffffff, a2 = 0x7fffffff;
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                const int i = 8 * j + ((warp - j) & 7);
+                const int wj = i >> 5, lj = i & 31;
+                const float rz = s_row[wj][4][lj];
+                if (rz < 0.0f) continue;  // not a candidate
+                const float dx = gcx - s_row[wj][0][lj], dy = gcy - s_row[wj][1][lj];
+                const float d2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-12f);
+                const float d = d2 * rsqrtf(d2);
+                tmax = fmaxf(tmax, rz + d);
+                const float den = (rgmean + s_row[wj][3][lj]) + d;
+                const float q = __fdividef(rgms + s_row[wj][2][lj], den * den);
+                const int aj = tile * P24_THREADS + i;
+                if (q < q1) {
+                    q2 = q1;
+                    a2 = a1;
+                    q1 = q;
+                    a1 = aj;
+                } else if (q < q2) {
+                    q2 = q;
+                    a2 = aj;
+                }
+            }
+            const long long o = ((long long)b * p.Lmax + g) * nw + tile * P24_WARPS + warp;
+            p.wseed[o] = make_float4(q1, __int_as_float(a1), q2, __int_as_float(a2));
+            p.wtmax[o] = tmax;
+        }
+    }
     const unsigned bal = __ballot_sync(0xffffffffu, cand);
     if (lane == 0) s_wcnt[warp] = __popc(bal);
     objpart = warp_sum_d(objpart);
@@ -490,7 +536,6 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_anchor_pass(Params p) {
         const int rank = base + __popc(bal & ((1u << lane) - 1u));
         // a prediction with a tiny radius disables the bound filter for its pairs: rpmax = +inf
         p.clist[blk * P24_THREADS + rank] = make_float4(pcx, pcy, rpmin < 0.25f ? INFINITY : rpmax, __int_as_float(a));
-        p.clist2[blk * P24_THREADS + rank] = make_float2(rp2sum * (1.0f / 24.0f), rpsum * (1.0f / 24.0f));
     }
     if (active) {
         // every anchor starts as background; k_resolve_loss overwrites the claimed ones
@@ -526,7 +571,6 @@ __device__ __forceinline__ void claim_anchor(const Params& p, int b, int a, int 
 }
 
 #define HIT_CAP 3072
-#define EV_CAP 256
 #define N_SEED (2 * MATCH_WARPS)
 #define MAX_TILES 1024  // candidate counts of an image kept in shared memory (A <= 262144)
 
@@ -548,7 +592,7 @@ struct MatchShared {
     float rec[GT_REC];
     int ccount[MAX_TILES];
     int hit[HIT_CAP];       // slow path: anchors the scalar bound cannot exclude
-    float ev[EV_CAP];       // slow path: exact values that reach the seed threshold
+    float ev[HIT_CAP];      // slow path: exact values that reach the seed threshold
     float top[P24_TOPK];
     int seed[N_SEED];
     float seedv[N_SEED];
@@ -700,21 +744,17 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
         if (ub < T) continue;
         float s = 0.0f;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) s = s + p24_ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
+        for (int q = 0; q < 3; ++q) s = s + ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
         s = group_sum(s, gm);
         const float v = (s / 24.0f) / 2.0f;
         if (sub == 0 && (v >= T || !(v == v))) {
-            const int e = atomicAdd(&S.nev, 1);
-            if (e < EV_CAP) S.ev[e] = (v == v) ? v : P24_POS_INF;
-            else S.overflow = 1;
+            S.ev[atomicAdd(&S.nev, 1)] = (v == v) ? v : P24_POS_INF;  // nev <= nhit <= HIT_CAP
         }
     }
     __syncthreads();
-    if (S.overflow || S.nev < P24_TOPK) return NAN;
-    int got = 0;
-    if (warp == 0) got = warp_select_top(S.ev, S.nev, P24_TOPK, S.top);
+    if (S.nev < P24_TOPK) return NAN;
+    if (warp == 0) warp_select_top(S.ev, S.nev, P24_TOPK, S.top);
     __syncthreads();
-    (void)got;
     float ksum = 0.0f;
     for (int i = 0; i < P24_TOPK; ++i) ksum = ksum + (S.top[i] == P24_POS_INF ? NAN : S.top[i]);
     return ksum;
@@ -814,39 +854,23 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     const float* img = p.outputs + (long long)b * p.img_stride;
 
-    // ---- scan the image's candidates (padded [tile][256] layout, independent loads): largest t, and two seeds per
-    // warp ranked by a first-order proxy of the pair value, q = (mean rg^2 + mean rp^2) / (mean rg + mean rp + d)^2
-    // (value ~ 1 - q / 3 for far pairs): the smallest q are almost always the true top-10 ---------------------------
+    // ---- seeds: the anchor pass left, per warp of 32 anchors, the two candidates with the smallest proxy for this
+    // GT and the largest t; take the best two of every slice of them (24 seeds) and the overall largest t ------------
     float q1 = P24_POS_INF, q2 = P24_POS_INF, tmax = P24_NEG_INF;
     int a1 = 0x7fffffff, a2 = 0x7fffffff;
     {
-        const float rgms = S.rec[GT_RGMS], rgmean = S.rec[GT_RGMEAN];
-        const int nslot = p.tiles * P24_THREADS;
-        const float4* cl = p.clist + (long long)b * p.tiles * P24_THREADS;
-        const float2* cl2 = p.clist2 + (long long)b * p.tiles * P24_THREADS;
-        for (int base = tid; base < nslot; base += 4 * MATCH_THREADS) {
-            float4 c4[4];
-            float2 c2[4];
-            bool ok[4];
+        const int nw = p.tiles * P24_WARPS;
+        const float4* ws4 = p.wseed + (long long)wslot * nw;
+        const float* wt = p.wtmax + (long long)wslot * nw;
+        // entry e (one warp of the anchor pass) goes to warp e % 12: the 8 warps of a tile, which share the best
+        // region of the image, are spread over 8 different warps here
+        for (int i = warp + MATCH_WARPS * lane; i < nw; i += MATCH_WARPS * 32) {
+            const float4 e = ws4[i];
+            tmax = fmaxf(tmax, wt[i]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {  // all loads of the batch are in flight before the first use
-                const int i0 = base + u * MATCH_THREADS;
-                ok[u] = i0 < nslot && (i0 & 255) < S.ccount[i0 >> 8];
-                if (ok[u]) {
-                    c4[u] = cl[i0];
-                    c2[u] = cl2[i0];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (!ok[u]) continue;
-                const float dx = gcx - c4[u].x, dy = gcy - c4[u].y;
-                const float d2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-12f);
-                const float d = d2 * rsqrtf(d2);
-                tmax = fmaxf(tmax, c4[u].z + d);
-                const float den = (rgmean + c2[u].y) + d;
-                const float q = __fdividef(rgms + c2[u].x, den * den);
-                const int a = __float_as_int(c4[u].w);
+            for (int u = 0; u < 2; ++u) {
+                const float q = u ? e.z : e.x;
+                const int a = __float_as_int(u ? e.w : e.y);
                 if (kv_lt(q, a, q1, a1)) {
                     q2 = q1;
                     a2 = a1;
@@ -911,8 +935,8 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
                     for (int q = 0; q < 3; ++q) {
                         const int k = sub * 3 + q;
                         const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
-                        ang = ang + p24_edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
-                                                   S.rec[GT_VY + k2] - yc);
+                        ang = ang + edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
+                                               S.rec[GT_VY + k2] - yc);
                     }
                     ang = group_sum(ang, gm);
                     if (!(ang >= 350.0f)) continue;  // losses.py:588
@@ -921,7 +945,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
             const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
             float s = 0.0f;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) s = s + p24_ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
+            for (int q = 0; q < 3; ++q) s = s + ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
             s = group_sum(s, gm);
             const float v = (s / 24.0f) / 2.0f;
             const float eo1 = 1.0f + expf(-obj);
@@ -1029,7 +1053,12 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
     }
     TMARK(1, MCTA, 7);
 #ifdef P24_TIMING
-    if (tid == 0) g_tstamp[1][MCTA][8] = S.slow;
+    if (tid == 0) {
+        g_tstamp[1][MCTA][8] = S.slow;
+        g_tstamp[1][MCTA][9] = S.nhit;
+        g_tstamp[1][MCTA][10] = S.nev;
+        g_tstamp[1][MCTA][11] = S.overflow;
+    }
 #endif
 }
 
@@ -1088,7 +1117,7 @@ __device__ __forceinline__ float warp_pair_value(const float* __restrict__ rec, 
     const int lane = threadIdx.x & 31;
     const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
     float l = 0.0f;
-    if (lane < P24_RAYS) l = p24_ray_loss(rec[GT_RG + lane], row[2 + lane], d);
+    if (lane < P24_RAYS) l = ray_loss(rec[GT_RG + lane], row[2 + lane], d);
     l_out = l;
     return (warp_sum(l) / 24.0f) / 2.0f;
 }
@@ -1115,8 +1144,7 @@ __device__ __noinline__ int resolve_conflict(const Params& p, const float* recs,
             float ang = 0.0f;
             if (lane < P24_RAYS) {
                 const int k2 = (lane == P24_RAYS - 1) ? 0 : lane + 1;
-                ang = p24_edge_angle(rec[GT_VX + lane] - xc, rec[GT_VY + lane] - yc, rec[GT_VX + k2] - xc,
-                                     rec[GT_VY + k2] - yc);
+                ang = edge_angle(rec[GT_VX + lane] - xc, rec[GT_VY + lane] - yc, rec[GT_VX + k2] - xc, rec[GT_VY + k2] - yc);
             }
             ang = warp_sum(ang);
             if (!(ang >= 350.0f)) continue;
@@ -1326,7 +1354,8 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.state26 = state26; p.result54 = result54; p.weights27 = weights_n27;
     p.gt_rec = (float*)(ws + L.gt_rec);
     p.clist = (float4*)(ws + L.clist);
-    p.clist2 = (float2*)(ws + L.clist2);
+    p.wseed = (float4*)(ws + L.wseed);
+    p.wtmax = (float*)(ws + L.wtmax);
     p.ccount = (int*)(ws + L.ccount);
     p.wcount = (int*)(ws + L.wcount);
     p.wlist = (int*)(ws + L.wlist);

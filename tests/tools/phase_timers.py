@@ -21,8 +21,11 @@ sets = [(synth.make_head_outputs(B, size, 80, seed=1 + 100 * i).to(dev),
 xs, ys, ss = synth.make_grids(size)
 g = [[t.to(dev) for t in l] for l in (xs, ys, ss)]
 lf = Loss_Function(80)
-for i in range(6):
-    o, l = sets[i % 3]
+sets += [(synth.make_head_outputs(B, size, 80, seed=1 + 100 * i).to(dev),
+          synth.make_labels(B, G, Lmax, size, 80, seed=1 + 100 * i, kind="smooth").to(dev)) for i in range(3, 5)]
+only = int(sys.argv[1]) if len(sys.argv) > 1 else None
+for i in range(10):
+    o, l = sets[(i % 5) if only is None else only]
     lf.forward_async((g[0], g[1], g[2], o, []), l)
 torch.cuda.synchronize()
 buf = np.zeros((3, 4096, 12), dtype=np.uint64)
@@ -49,6 +52,8 @@ for k, (nm, ncta, ph) in names.items():
             print(f"   {ph[i]:14s} mean {d.mean():7.2f} us  p50 {np.median(d):7.2f}  max {d.max():7.2f}  (n={d.size})")
     if k == 1:
         slow = t[1, :ncta, 8]
-        print("   slow-path CTAs:", int((slow != 0).sum()), "of", ncta)
+        print("   slow-path CTAs:", int((slow != 0).sum()), "of", ncta, "kinds", slow[slow != 0].tolist(),
+              "nhit", t[1, :ncta, 9][slow != 0].tolist(), "nev", t[1, :ncta, 10][slow != 0].tolist(),
+              "overflow", t[1, :ncta, 11][slow != 0].tolist())
         tot = (tt[ok, 7] - tt[ok, 1]) / 1e3
         print(f"   CTA total mean {tot.mean():.2f} us max {tot.max():.2f} us; slow ones: {np.round(tot[slow[ok] != 0], 1).tolist()[:20]}")
