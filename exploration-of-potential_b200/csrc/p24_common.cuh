@@ -36,7 +36,8 @@ struct P24Workspace {
     size_t clist;       // [B, tiles, 256] float4  candidate anchors of a tile, compacted: (pred cx, pred cy, rpmax, anchor idx bits)
     size_t wseed;       // [B, Lmax, tiles * 8] float4  per (GT, warp of the anchor pass): the two candidates with the smallest
                         //                              seed proxy (q1, anchor1, q2, anchor2)
-    size_t wtmax;       // [B, Lmax, tiles * 8] float   largest t = rpmax + d of the warp's candidates
+    size_t wbox;        // [B, tiles * 8, 8] float      per warp of the anchor pass: bounding box of its candidates' predicted
+                        //                              centres (xmin, xmax, ymin, ymax), largest rpmax, pad
     size_t ccount;      // [B, tiles] int          candidates per tile
     size_t wcount;      // [B, Lmax] int           anchors inside the GT's centre window (zero between calls)
     size_t wlist;       // [B, Lmax, VCAP] int
@@ -68,7 +69,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
     w.ccount = off;     off = p24_align(off + NB * sizeof(int));
     w.wseed = off;      off = p24_align(off + BL * (size_t)p24_tiles(A) * P24_WARPS * 4 * sizeof(float));
-    w.wtmax = off;      off = p24_align(off + BL * (size_t)p24_tiles(A) * P24_WARPS * sizeof(float));
+    w.wbox = off;       off = p24_align(off + NB * P24_WARPS * 8 * sizeof(float));
     w.wlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));
     w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
     w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));

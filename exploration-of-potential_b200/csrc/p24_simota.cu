@@ -52,7 +52,7 @@ struct Params {
     float* gt_rec;
     float4* clist;
     float4* wseed;
-    float* wtmax;
+    float* wbox;
     int* ccount;
     int* wcount;
     int* wlist;
@@ -483,16 +483,30 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
     s_row[warp][4][lane] = cand ? (rpmin < 0.25f ? INFINITY : rpmax) : -1.0f;
     __syncthreads();
     {
-        // warp w looks at anchors i = 8 j + ((w - j) & 7), j = 0..31, of the tile: neighbouring anchors (which have
-        // nearly equal proxies) land in different warps, so the per-warp best two keep the whole top of the tile
+        // bounding box of the warp's candidates (GT independent): k_gt_match bounds t = rpmax + d with it
+        {
+            const float rz = cand ? (rpmin < 0.25f ? INFINITY : rpmax) : P24_NEG_INF;
+            const float bx0 = -warp_max(cand ? -pcx : P24_NEG_INF), bx1 = warp_max(cand ? pcx : P24_NEG_INF);
+            const float by0 = -warp_max(cand ? -pcy : P24_NEG_INF), by1 = warp_max(cand ? pcy : P24_NEG_INF);
+            const float rzm = warp_max(rz);
+            if (lane == 0) {
+                float4* dst = reinterpret_cast<float4*>(p.wbox + (((long long)b * p.tiles + tile) * P24_WARPS + warp) * 8);
+                dst[0] = make_float4(bx0, bx1, by0, by1);
+                dst[1] = make_float4(rzm, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        // warp w ranks a quarter of the tile's anchors, i = 8 j + ((w - j) & 7) for every 4th j: neighbouring anchors
+        // (nearly equal proxies) land in different warps, and a quarter sample is enough for seeds (any candidate
+        // is a valid seed; better ones only make the bracket tighter)
         const int nw = p.tiles * P24_WARPS;
         for (int g = lane; g < n; g += 32) {
             const float* rec = s_gt + g * GT_REC;
             const float gcx = rec[GT_CX], gcy = rec[GT_CY], rgms = rec[GT_RGMS], rgmean = rec[GT_RGMEAN];
-            float q1 = P24_POS_INF, q2 = P24_POS_INF, tmax = P24_NEG_INF;
+            float q1 = P24_POS_INF, q2 = P24_POS_INF;
             int a1 = 0x7fffffff, a2 = 0x7fffffff;
-#pragma unroll 4
-            for (int j = 0; j < 32; ++j) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int j = 4 * jj + (warp & 3);
                 const int i = 8 * j + ((warp - j) & 7);
                 const int wj = i >> 5, lj = i & 31;
                 const float rz = s_row[wj][4][lj];
@@ -500,7 +514,6 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
                 const float dx = gcx - s_row[wj][0][lj], dy = gcy - s_row[wj][1][lj];
                 const float d2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-12f);
                 const float d = d2 * rsqrtf(d2);
-                tmax = fmaxf(tmax, rz + d);
                 const float den = (rgmean + s_row[wj][3][lj]) + d;
                 const float q = __fdividef(rgms + s_row[wj][2][lj], den * den);
                 const int aj = tile * P24_THREADS + i;
@@ -516,7 +529,6 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
             }
             const long long o = ((long long)b * p.Lmax + g) * nw + tile * P24_WARPS + warp;
             p.wseed[o] = make_float4(q1, __int_as_float(a1), q2, __int_as_float(a2));
-            p.wtmax[o] = tmax;
         }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, cand);
@@ -861,12 +873,21 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
     {
         const int nw = p.tiles * P24_WARPS;
         const float4* ws4 = p.wseed + (long long)wslot * nw;
-        const float* wt = p.wtmax + (long long)wslot * nw;
+        const float4* wb = reinterpret_cast<const float4*>(p.wbox + (long long)b * nw * 8);
         // entry e (one warp of the anchor pass) goes to warp e % 12: the 8 warps of a tile, which share the best
         // region of the image, are spread over 8 different warps here
         for (int i = warp + MATCH_WARPS * lane; i < nw; i += MATCH_WARPS * 32) {
             const float4 e = ws4[i];
-            tmax = fmaxf(tmax, wt[i]);
+            {
+                // t = rpmax + d <= largest rpmax of the warp + distance to the farthest corner of its box
+                const float4 bx = wb[2 * i];
+                const float rzm = wb[2 * i + 1].x;
+                if (rzm > P24_NEG_INF) {
+                    const float fx = fmaxf(fabsf(gcx - bx.x), fabsf(gcx - bx.y));
+                    const float fy = fmaxf(fabsf(gcy - bx.z), fabsf(gcy - bx.w));
+                    tmax = fmaxf(tmax, rzm + sqrtf(fmaf(fx, fx, fy * fy)) * 1.00001f);
+                }
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const float q = u ? e.z : e.x;
@@ -1355,7 +1376,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.gt_rec = (float*)(ws + L.gt_rec);
     p.clist = (float4*)(ws + L.clist);
     p.wseed = (float4*)(ws + L.wseed);
-    p.wtmax = (float*)(ws + L.wtmax);
+    p.wbox = (float*)(ws + L.wbox);
     p.ccount = (int*)(ws + L.ccount);
     p.wcount = (int*)(ws + L.wcount);
     p.wlist = (int*)(ws + L.wlist);
