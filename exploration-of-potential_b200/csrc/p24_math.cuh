@@ -196,7 +196,7 @@ __device__ __forceinline__ int p24_angle_test_fast(const float* __restrict__ vx,
 }
 
 // reference-order evaluation, kept out of line (rare) so that it does not inflate the callers' registers
-__device__ __noinline__ bool p24_in_polygon_exact(const float* vx, const float* vy, float xc, float yc) {
+static __device__ __noinline__ bool p24_in_polygon_exact(const float* vx, const float* vy, float xc, float yc) {
     float acc = 0.0f;
     float sx = vx[0] - xc, sy = vy[0] - yc;
 #pragma unroll 1

@@ -1,0 +1,444 @@
+// p24_post.cu — inference postprocess of YOLOX-24p for sm_100a.
+//
+// Replaces utils.boxes.postprocess (utils/boxes.py:29-99; twin show_24p.py:212-264), image by image (the reference's
+// batched call raises for B >= 2, boxes.py:64-65; the contract is "the per-image result for each i"):
+//   class_conf, class_pred = max over the class scores (first maximum on ties)       boxes.py:51
+//   keep anchors with obj * class_conf >= conf_thre                                  boxes.py:55
+//   rectangle of the 24 decoded points r_k * (theta_k cos theta_k, theta_k sin theta_k) + centre   boxes.py:67-76
+//   torchvision nms / batched_nms (coordinate trick) on the rectangles, scores obj * class_conf    boxes.py:78-90
+//   rows [cx, cy, r0..r23, obj, class_conf, class_pred] of the kept anchors in NMS (score) order   boxes.py:92
+//
+// Kernels:
+//   k_post_filter  one CTA per 256-anchor tile.  The ONE pass over the prediction: each warp stages its 32 rows
+//                  (32 x (27+nc) contiguous floats) in shared memory with a single TMA bulk copy (cp.async.bulk +
+//                  mbarrier) when the layout allows it, then every lane reduces its own row (class max / argmax,
+//                  score, rectangle) and the tile's candidates are compacted in anchor order.  HBM bound.
+//   k_post_nms     one CTA per image: stable descending sort of the candidates by score (bitonic sort of 64-bit
+//                  (score, position) keys in shared memory), greedy NMS in chunks of 64 sorted boxes, output rows.
+//
+// torchvision is third-party arithmetic that the reference does not vendor.  The IoU test repeats
+// torchvision's expression  inter / (area_a + area_b - inter) > thr  in fp32 without FMA contraction (this file is
+// compiled with -fmad=false), the sort is stable, and batched NMS adds  class * (max_coordinate + 1)  to the boxes in
+// fp32 exactly like _batched_nms_coordinate_trick.
+#include "p24_common.cuh"
+
+namespace {
+
+#define POST_THREADS 256
+#define POST_WARPS 8
+#define NMS_THREADS 1024
+#define SORT_SMEM_MAX 16384  // candidates of one image sorted in shared memory (128 KB of keys)
+
+struct PostParams {
+    const float* pred;
+    long long img_stride, row_stride;
+    int B, A, nc, C;
+    float coef_x[P24_RAYS], coef_y[P24_RAYS];
+    float conf_thre, nms_thre;
+    int class_agnostic;
+    int32_t* cand_count;
+    int32_t* det_count;
+    float* det_rows;
+    int32_t* keep_idx;
+    float* rect_debug;
+    // workspace
+    int* tcount;     // [B, tiles]
+    float* c_score;  // [B, tiles*256]
+    float* c_conf;   // [B, tiles*256]
+    int* c_anchor;   // [B, tiles*256]
+    int* c_cls;      // [B, tiles*256]
+    float4* c_rect;  // [B, tiles*256]
+    float4* s_rect;  // [B, A]   sorted (and class-shifted) rectangles
+    unsigned long long* g_keys;  // [B, npad]  global sort scratch (only when an image has > SORT_SMEM_MAX candidates)
+    int tiles;
+    int npad_global;
+};
+
+struct PostWorkspace {
+    size_t tcount, c_score, c_conf, c_anchor, c_cls, c_rect, s_rect, g_keys, total;
+};
+
+inline int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+inline PostWorkspace post_layout(int B, int A) {
+    PostWorkspace w;
+    size_t off = 0;
+    const size_t tiles = (size_t)p24_tiles(A);
+    const size_t slots = (size_t)B * tiles * POST_THREADS;
+    w.tcount = off;   off = p24_align(off + (size_t)B * tiles * sizeof(int));
+    w.c_score = off;  off = p24_align(off + slots * sizeof(float));
+    w.c_conf = off;   off = p24_align(off + slots * sizeof(float));
+    w.c_anchor = off; off = p24_align(off + slots * sizeof(int));
+    w.c_cls = off;    off = p24_align(off + slots * sizeof(int));
+    w.c_rect = off;   off = p24_align(off + slots * sizeof(float4));
+    w.s_rect = off;   off = p24_align(off + (size_t)B * A * sizeof(float4));
+    w.g_keys = off;   off = p24_align(off + (A > SORT_SMEM_MAX ? (size_t)B * next_pow2(A) * sizeof(unsigned long long) : 0));
+    w.total = off;
+    return w;
+}
+
+// ---- mbarrier / TMA bulk copy (1D) ----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+// -------------------------------------------------------------------------------------------
+// k_post_filter
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(POST_THREADS) k_post_filter(PostParams p) {
+    extern __shared__ __align__(128) float s_rows[];  // [8 warps][32 rows * C]
+    __shared__ __align__(8) unsigned long long s_bar[POST_WARPS];
+    __shared__ int s_wcnt[POST_WARPS];
+    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int a0 = tile * POST_THREADS + warp * 32;
+    const int nrow = max(0, min(32, p.A - a0));
+    const int a = a0 + lane;
+    const bool active = lane < nrow;
+    float* my = s_rows + (size_t)warp * 32 * p.C;
+    const float* src = p.pred + (long long)b * p.img_stride + (long long)a0 * p.row_stride;
+
+    // rows of a warp are one contiguous block when row_stride == C; TMA bulk copy needs 16-byte alignment / size
+    const unsigned bytes = (unsigned)(nrow * p.C * sizeof(float));
+    const bool bulk = nrow > 0 && p.row_stride == p.C && ((uintptr_t)src & 15) == 0 && (bytes & 15) == 0;
+    if (bulk) {
+        if (lane == 0) {
+            mbar_init(&s_bar[warp], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect_tx(&s_bar[warp], bytes);
+            bulk_g2s(my, src, bytes, &s_bar[warp]);
+        }
+        mbar_wait(&s_bar[warp], 0);
+    } else {
+        for (int r = 0; r < nrow; ++r)
+            for (int c = lane; c < p.C; c += 32) my[r * p.C + c] = src[(long long)r * p.row_stride + c];
+        __syncwarp();
+    }
+
+    // ---- every lane reduces its own row (stride C = 27 + nc floats: odd for nc = 80 -> conflict free) ----------
+    bool cand = false;
+    float score = 0.f, conf = 0.f;
+    int cls = 0;
+    float4 rect = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        const float* row = my + lane * p.C;
+        conf = row[27];
+        for (int j = 1; j < p.nc; ++j) {  // torch.max: first maximum on ties
+            const float v = row[27 + j];
+            if (v > conf || (v != v && conf == conf)) {
+                conf = v;
+                cls = j;
+            }
+        }
+        score = row[26] * conf;          // boxes.py:55, 78
+        cand = score >= p.conf_thre;
+        if (cand) {
+            const float cx = row[0], cy = row[1];
+            float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < P24_RAYS; ++k) {
+                const float r = row[2 + k];
+                const float px = (r * p.coef_x[k]) + cx;  // boxes.py:67-68 (sic: theta * cos theta)
+                const float py = (r * p.coef_y[k]) + cy;
+                x0 = fminf(x0, px);
+                x1 = fmaxf(x1, px);
+                y0 = fminf(y0, py);
+                y1 = fmaxf(y1, py);
+            }
+            rect = make_float4(x0, y0, x1, y1);
+        }
+    }
+    // ---- ordered compaction of the tile's candidates -----------------------------------------------------------
+    const unsigned bal = __ballot_sync(0xffffffffu, cand);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < POST_WARPS; ++w) {
+        const int c = s_wcnt[w];
+        base += (w < warp) ? c : 0;
+        total += c;
+    }
+    const long long blk = (long long)b * p.tiles + tile;
+    if (cand) {
+        const long long o = blk * POST_THREADS + base + __popc(bal & ((1u << lane) - 1u));
+        p.c_score[o] = score;
+        p.c_conf[o] = conf;
+        p.c_anchor[o] = a;
+        p.c_cls[o] = cls;
+        p.c_rect[o] = rect;
+    }
+    if (tid == 0) p.tcount[blk] = total;
+}
+
+// -------------------------------------------------------------------------------------------
+// k_post_nms
+// -------------------------------------------------------------------------------------------
+// torchvision's devIoU > threshold (boxes without +1, fp32)
+__device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float thr) {
+    const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+    const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    const float w = fmaxf(right - left, 0.0f), h = fmaxf(bottom - top, 0.0f);
+    const float inter = w * h;
+    const float sa = (a.z - a.x) * (a.w - a.y);
+    const float sb = (b.z - b.x) * (b.w - b.y);
+    return (inter / ((sa + sb) - inter)) > thr;
+}
+
+// in-place ascending bitonic sort of npad (power of two) 64-bit keys by the whole CTA
+__device__ void bitonic_sort(unsigned long long* keys, int npad) {
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = keys[i], y = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        keys[i] = y;
+                        keys[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];  // [npad] when the image fits, else unused
+    __shared__ int s_prefix[1025];                               // candidates before tile t (tiles <= 1024)
+    __shared__ unsigned long long s_mask[64];
+    __shared__ float4 s_kept[64];
+    __shared__ int s_nkept, s_ndet;
+    __shared__ float s_red[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- number of candidates, prefix of the tile counts ----------------------------------------------------------
+    if (tid == 0) {
+        int acc = 0;
+        for (int t = 0; t < p.tiles; ++t) {
+            s_prefix[t] = acc;
+            acc += p.tcount[(long long)b * p.tiles + t];
+        }
+        s_prefix[p.tiles] = acc;
+        s_ndet = 0;
+    }
+    __syncthreads();
+    const int n = s_prefix[p.tiles];
+    if (tid == 0) p.cand_count[b] = n;
+    if (n == 0) {
+        if (tid == 0) p.det_count[b] = 0;
+        return;
+    }
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    const bool in_smem = npad <= SORT_SMEM_MAX;
+    unsigned long long* keys = in_smem ? s_keys : (p.g_keys + (long long)b * p.npad_global);
+
+    // ---- keys: (descending score, ascending candidate position) -> one ascending 64-bit key; max of the coordinates
+    float cmax = -INFINITY;
+    const long long slot0 = (long long)b * p.tiles * POST_THREADS;
+    for (int t = warp; t < p.tiles; t += NMS_THREADS / 32) {
+        const int c = s_prefix[t + 1] - s_prefix[t];
+        for (int i = lane; i < c; i += 32) {
+            const long long o = slot0 + (long long)t * POST_THREADS + i;
+            const unsigned pos = (unsigned)(s_prefix[t] + i);
+            keys[pos] = ((unsigned long long)(~p24_ordered(p.c_score[o])) << 32) | pos;
+            const float4 r = p.c_rect[o];
+            cmax = fmaxf(cmax, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
+            if (p.rect_debug) reinterpret_cast<float4*>(p.rect_debug)[(long long)b * p.A + pos] = r;
+        }
+    }
+    for (int i = n + tid; i < npad; i += NMS_THREADS) keys[i] = ~0ull;
+    cmax = warp_max(cmax);
+    if (lane == 0) s_red[warp] = cmax;
+    __syncthreads();
+    cmax = s_red[0];
+    for (int w = 1; w < NMS_THREADS / 32; ++w) cmax = fmaxf(cmax, s_red[w]);
+    bitonic_sort(keys, npad);
+
+    // ---- sorted rectangles (+ class offset for batched NMS: boxes + idxs * (max_coordinate + 1)) --------------------
+    float4* srect = p.s_rect + (long long)b * p.A;
+    const float step = cmax + 1.0f;
+    for (int i = tid; i < n; i += NMS_THREADS) {
+        const unsigned pos = (unsigned)(keys[i] & 0xFFFFFFFFull);
+        // position -> (tile, rank): binary search in the prefix
+        int lo = 0, hi = p.tiles;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_prefix[mid] <= (int)pos) lo = mid;
+            else hi = mid;
+        }
+        const long long o = slot0 + (long long)lo * POST_THREADS + ((int)pos - s_prefix[lo]);
+        float4 r = p.c_rect[o];
+        if (!p.class_agnostic) {
+            const float off = (float)p.c_cls[o] * step;
+            r.x = r.x + off;
+            r.y = r.y + off;
+            r.z = r.z + off;
+            r.w = r.w + off;
+        }
+        srect[i] = r;
+        keys[i] = (keys[i] & 0xFFFFFFFF00000000ull) | (unsigned long long)(unsigned)(o - slot0);  // now: slot of the candidate
+    }
+    __syncthreads();
+
+    // ---- greedy NMS over the sorted boxes in chunks of 64; suppression flags live in the low bit 31 of the key ------
+    // (bit 31 of the slot field is free: slots < 2^31)
+    for (int c0 = 0; c0 < n; c0 += 64) {
+        const int cn = min(64, n - c0);
+        if (tid < 64) s_mask[tid] = 0ull;
+        __syncthreads();
+        // 64 x 64 pairwise tests of the chunk (j > i)
+        for (int q = tid; q < cn * cn; q += NMS_THREADS) {
+            const int i = q / cn, j = q - i * cn;
+            if (j > i && iou_over(srect[c0 + i], srect[c0 + j], p.nms_thre)) atomicOr(&s_mask[i], 1ull << j);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long removed = 0ull;
+            int nk = 0;
+            for (int i = 0; i < cn; ++i) {
+                const bool dead = ((keys[c0 + i] >> 31) & 1ull) || ((removed >> i) & 1ull);
+                if (dead) {
+                    keys[c0 + i] |= (1ull << 31);
+                } else {
+                    removed |= s_mask[i];
+                    s_kept[nk++] = srect[c0 + i];
+                }
+            }
+            s_nkept = nk;
+        }
+        __syncthreads();
+        const int nk = s_nkept;
+        for (int j = c0 + cn + tid; j < n; j += NMS_THREADS) {
+            if ((keys[j] >> 31) & 1ull) continue;
+            const float4 bj = srect[j];
+            bool dead = false;
+            for (int i = 0; i < nk && !dead; ++i) dead = iou_over(s_kept[i], bj, p.nms_thre);
+            if (dead) keys[j] |= (1ull << 31);
+        }
+        __syncthreads();
+    }
+
+    // ---- output rows of the survivors in sorted order ------------------------------------------------------------
+    // ordered compaction over i = 0..n-1
+    __shared__ int s_base;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += NMS_THREADS) {
+        const int i = i0 + tid;
+        const bool keep = i < n && !((keys[i] >> 31) & 1ull);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_red[warp] = __int_as_float(__popc(bal));
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += __float_as_int(s_red[w]);
+        int tot = 0;
+        for (int w = 0; w < NMS_THREADS / 32; ++w) tot += __float_as_int(s_red[w]);
+        if (keep) {
+            const int k = before + __popc(bal & ((1u << lane) - 1u));
+            const long long o = slot0 + (long long)(keys[i] & 0x7FFFFFFFull);
+            const int a = p.c_anchor[o];
+            const float* row = p.pred + (long long)b * p.img_stride + (long long)a * p.row_stride;
+            float* dst = p.det_rows + ((long long)b * p.A + k) * 29;
+            for (int c = 0; c < 27; ++c) dst[c] = row[c];
+            dst[27] = p.c_conf[o];
+            dst[28] = (float)p.c_cls[o];
+            p.keep_idx[(long long)b * p.A + k] = a;
+        }
+        __syncthreads();
+        if (tid == 0) s_base += tot;
+        __syncthreads();
+    }
+    if (tid == 0) p.det_count[b] = s_base;
+}
+
+}  // namespace
+
+extern "C" size_t p24_postprocess_workspace_bytes(int B, int A) {
+    if (B <= 0 || A <= 0) return 0;
+    return post_layout(B, A).total;
+}
+
+extern "C" int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_stride, int B, int A,
+                               int num_classes, const float* h_coef_x, const float* h_coef_y, float conf_thre,
+                               float nms_thre, int class_agnostic, int32_t* cand_count, int32_t* det_count,
+                               float* det_rows, int32_t* keep_idx, float* rect_debug, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!prediction || !h_coef_x || !h_coef_y || !cand_count || !det_count || !det_rows || !keep_idx || !workspace)
+        return P24_E_BADARG;
+    if (B <= 0 || A <= 0 || num_classes <= 0) return P24_E_BADARG;
+    if (((uintptr_t)workspace & 255) != 0) return P24_E_BADARG;
+    const PostWorkspace L = post_layout(B, A);
+    if (workspace_bytes < L.total) return P24_E_WORKSPACE;
+    const int tiles = p24_tiles(A);
+    if (tiles > 1024) return P24_E_UNSUPPORTED;
+    const int C = 27 + num_classes;
+    const size_t smem_filter = (size_t)POST_WARPS * 32 * C * sizeof(float);
+    if (smem_filter > 200 * 1024) return P24_E_UNSUPPORTED;
+    char* ws = (char*)workspace;
+    PostParams p;
+    p.pred = prediction; p.img_stride = img_stride; p.row_stride = row_stride;
+    p.B = B; p.A = A; p.nc = num_classes; p.C = C;
+    for (int k = 0; k < P24_RAYS; ++k) {
+        p.coef_x[k] = h_coef_x[k];
+        p.coef_y[k] = h_coef_y[k];
+    }
+    p.conf_thre = conf_thre; p.nms_thre = nms_thre; p.class_agnostic = class_agnostic;
+    p.cand_count = cand_count; p.det_count = det_count; p.det_rows = det_rows; p.keep_idx = keep_idx;
+    p.rect_debug = rect_debug;
+    p.tcount = (int*)(ws + L.tcount);
+    p.c_score = (float*)(ws + L.c_score);
+    p.c_conf = (float*)(ws + L.c_conf);
+    p.c_anchor = (int*)(ws + L.c_anchor);
+    p.c_cls = (int*)(ws + L.c_cls);
+    p.c_rect = (float4*)(ws + L.c_rect);
+    p.s_rect = (float4*)(ws + L.s_rect);
+    p.g_keys = (unsigned long long*)(ws + L.g_keys);
+    p.tiles = tiles;
+    p.npad_global = next_pow2(A);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int npad_max = next_pow2(A);
+    const size_t smem_nms = (size_t)(npad_max <= SORT_SMEM_MAX ? npad_max : 0) * sizeof(unsigned long long);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_post_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_post_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_MAX * 8);
+        attr_done = true;
+    }
+    k_post_filter<<<dim3(tiles, B), POST_THREADS, smem_filter, st>>>(p);
+    k_post_nms<<<B, NMS_THREADS, smem_nms, st>>>(p);
+    return (int)cudaGetLastError();
+}

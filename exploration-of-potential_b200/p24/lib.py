@@ -28,6 +28,20 @@ _PROTOS = {
                                         c_ptr, C.c_size_t, C.c_uint32, c_ptr]),
     "p24_workspace_init": (C.c_int, [c_ptr, C.c_size_t, c_ptr]),
     "p24_loss_finalize": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "p24_circle_inter_fwd": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int,
+                                       c_ptr, c_ptr, c_ptr]),
+    "p24_iou_loss_fwd": (C.c_int, [c_ptr, C.c_int64, c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr]),
+    "p24_iou_loss_bwd": (C.c_int, [c_ptr, C.c_int64, c_ptr, C.c_int64, c_ptr, C.c_int, c_ptr, c_ptr]),
+    "p24_pair_iou": (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr]),
+    "p24_loss_bwd": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                               c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "p24_dynamic_k_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "p24_dynamic_k_matching": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                         c_ptr, C.c_size_t, c_ptr]),
+    "p24_postprocess_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "p24_postprocess": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int,
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "p24_profile_enable": (C.c_int, [C.c_int]),
     "p24_profile_read": (C.c_int, [C.POINTER(C.c_float)]),
 }

@@ -18,7 +18,108 @@ import torch
 import torch.nn as nn
 
 from . import lib as _lib
-from .engine import Assignment, SimOTAEngine, F_ALL_ROWS
+from .engine import Assignment, SimOTAEngine, F_ALL_ROWS, _check_cuda_f32, _stream_ptr
+
+
+def _rows(t: torch.Tensor, width: int, name: str) -> torch.Tensor:
+    t = t.reshape(-1, width)
+    _check_cuda_f32(t, name)
+    return t if t.stride(1) == 1 else t.contiguous()
+
+
+class _IouLossFn(torch.autograd.Function):
+    """loss24 = IOUloss.forward(pred, target)[0] with the hand-written backward (p24_iou_loss_bwd)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        lib = _lib.load()
+        p, t = _rows(pred.detach(), 26, "pred"), _rows(target.detach().float(), 50, "target")
+        n = p.shape[0]
+        out = torch.empty((n, 24), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            _lib.check(lib.p24_iou_loss_fwd(p.data_ptr(), p.stride(0), t.data_ptr(), t.stride(0), n, out.data_ptr(),
+                                            _stream_ptr(p.device)), "p24_iou_loss_fwd")
+        ctx.save_for_backward(p, t)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad24):
+        lib = _lib.load()
+        p, t = ctx.saved_tensors
+        n = p.shape[0]
+        g = grad24.contiguous().float()
+        gp = torch.empty((n, 26), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            _lib.check(lib.p24_iou_loss_bwd(p.data_ptr(), p.stride(0), t.data_ptr(), t.stride(0), g.data_ptr(), n,
+                                            gp.data_ptr(), _stream_ptr(p.device)), "p24_iou_loss_bwd")
+        return gp, None
+
+
+class IOUloss(nn.Module):
+    """24-ray concentric-circle GIoU loss (reference ``models/losses.py:14-157``)."""
+
+    def __init__(self, reduction="none"):
+        super().__init__()
+        self.reduction = reduction
+
+    def circle_inter(self, c_gtx, c_gty, gt_r, c_pdx, c_pdy, pd_r):
+        """Element-wise over N pairs -> (res_inter [N, 24], dist [N, 24])   (losses.py:23-78)."""
+        lib = _lib.load()
+        n = gt_r.shape[0]
+        res = torch.zeros_like(gt_r, dtype=torch.float32)
+        if n == 0 or pd_r.shape[0] == 0:  # losses.py:40-42
+            dist = torch.sqrt((c_gtx - c_pdx) ** 2 + (c_gty - c_pdy) ** 2).unsqueeze(1).repeat(1, 24)
+            return res, dist
+        gr, pr = _rows(gt_r.float(), 24, "gt_r"), _rows(pd_r.float(), 24, "pd_r")
+        gx, gy = c_gtx.float().contiguous(), c_gty.float().contiguous()
+        px, py = c_pdx.float().contiguous(), c_pdy.float().contiguous()
+        dist = torch.empty((n, 24), dtype=torch.float32, device=gr.device)
+        with torch.cuda.device(gr.device):
+            _lib.check(lib.p24_circle_inter_fwd(gx.data_ptr(), gy.data_ptr(), gr.data_ptr(), gr.stride(0), px.data_ptr(),
+                                                py.data_ptr(), pr.data_ptr(), pr.stride(0), n, res.data_ptr(),
+                                                dist.data_ptr(), _stream_ptr(gr.device)), "p24_circle_inter_fwd")
+        return res, dist
+
+    def forward(self, pred, target):
+        """pred [N, 26], target [N, 50] -> (loss24 [N, 24] un-reduced 1 - giou per ray, [pd_cx, pd_cy, pd_r])."""
+        if pred.shape[1] != 26 or target.shape[1] != 50:
+            raise IndexError
+        pred = pred.view(-1, 26)
+        target = target.view(-1, 50)
+        pcx, pcy, pr = pred[:, 0].to(torch.float), pred[:, 1].to(torch.float), pred[:, 2:]
+        if pred.shape[0] == 0 or target.shape[0] == 0:  # losses.py:111-115
+            return pred.new_zeros(1, 24), [pcx.new_zeros(1, 24), pcy.new_zeros(1, 24), pr.new_zeros(1, 24)]
+        return _IouLossFn.apply(pred, target), [pcx, pcy, pr]
+
+
+class _LossFn(torch.autograd.Function):
+    """result54 = the whole fused loss forward; backward = p24_loss_bwd scaled by d(loss)."""
+
+    @staticmethod
+    def forward(ctx, outputs, labels, owner, x_shifts, y_shifts, strides):
+        result54, weights27, asg = owner.forward_async((x_shifts, y_shifts, strides, outputs.detach(), []), labels)
+        ctx.owner_nc = owner.num_classes
+        ctx.asg = asg
+        ctx.save_for_backward(outputs.detach(), labels, weights27)
+        return result54
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        outputs, labels, w27 = ctx.saved_tensors
+        asg = ctx.asg
+        if outputs.stride(2) != 1:
+            outputs = outputs.contiguous()
+        lab = labels if labels.stride(2) == 1 else labels.contiguous()
+        B, A, C = outputs.shape
+        gout = torch.empty((B, A, C), dtype=torch.float32, device=outputs.device)
+        scale = g[0:1].contiguous().float()  # only d/d(loss) is propagated (the training script backpropagates the loss)
+        with torch.cuda.device(outputs.device):
+            _lib.check(lib.p24_loss_bwd(outputs.data_ptr(), outputs.stride(0), outputs.stride(1), B, A, ctx.owner_nc,
+                                        lab.data_ptr(), lab.stride(0), lab.stride(1), asg.fg_mask.data_ptr(),
+                                        asg.matched_gt.data_ptr(), asg.pred_iou.data_ptr(), w27.data_ptr(),
+                                        scale.data_ptr(), gout.data_ptr(), _stream_ptr(outputs.device)), "p24_loss_bwd")
+        return gout, None, None, None, None, None
 
 
 class Loss_Function(nn.Module):
@@ -26,6 +127,8 @@ class Loss_Function(nn.Module):
         super().__init__()
         self.num_classes = num_classes
         self.use_l1 = False  # never enabled by the 24p scripts (losses.py:163); the L1 branch is not provided
+        self.iou_loss = IOUloss(reduction="none")
+        self.bcewithlog_loss = nn.BCEWithLogitsLoss(reduction="none")
         # stateful re-weighting memory (losses.py:170-172); kept as Python/torch state on the object and,
         # like the reference, not checkpointed
         self.last_iou_loss = 1.0
@@ -80,8 +183,11 @@ class Loss_Function(nn.Module):
 
     def forward(self, outputs_train, labels):
         outputs = outputs_train[3]
-        result54, weights27, asg = self.forward_async(outputs_train, labels)
-        r = result54
+        if torch.is_grad_enabled() and outputs.requires_grad:
+            r = _LossFn.apply(outputs, labels, self, outputs_train[0], outputs_train[1], outputs_train[2])
+            asg = self.last_assignment
+        else:
+            r, _, asg = self.forward_async(outputs_train, labels)
         fg = asg.fg_mask.view(-1).bool()
         rows = outputs.reshape(-1, outputs.shape[-1])[fg]
         if rows.shape[0] == 0:  # losses.py:111-115
@@ -89,7 +195,7 @@ class Loss_Function(nn.Module):
         else:
             draw = [rows[:, 0], rows[:, 1], rows[:, 2:26]]
         draw += [r[28:52], r[52], r[53]]
-        ratio = float(r[27])  # one D2H read per step (the reference returns a Python float here)
+        ratio = float(r[27].detach())  # one D2H read per step (the reference returns a Python float here)
         return (r[0], r[1:25], r[25], r[26], 0.0, ratio, draw)
 
     # -- per-image API (losses.py:359-442) -----------------------------------------------------------
@@ -119,3 +225,32 @@ class Loss_Function(nn.Module):
         num_fg = int(asg.num_fg[0])
         self.last_assignment = asg
         return gt_classes[matched], fg_mask, ious, matched, num_fg
+
+    # -- losses.py:444-494 on materialised matrices ------------------------------------------------------
+    @torch.no_grad()
+    def dynamic_k_matching(self, cost, pair_wise_ious, gt_classes, num_gt, fg_mask):
+        """Same contract as the reference: returns (num_fg, gt_matched_classes, pred_ious_this_matching,
+        matched_gt_inds) and updates ``fg_mask`` in place (``fg_mask[fg_mask.clone()] = fg_mask_inboxes``)."""
+        lib = _lib.load()
+        cost = cost.float().contiguous()
+        ious = pair_wise_ious.float().contiguous()
+        _check_cuda_f32(cost, "cost")
+        G, P = cost.shape
+        dev = cost.device
+        fg_in = torch.empty(P, dtype=torch.uint8, device=dev)
+        matched = torch.empty(P, dtype=torch.int32, device=dev)
+        miou = torch.empty(P, dtype=torch.float32, device=dev)
+        dyn_k = torch.empty(G, dtype=torch.int32, device=dev)
+        nfg = torch.empty(1, dtype=torch.int32, device=dev)
+        nbytes = lib.p24_dynamic_k_workspace_bytes(G, P)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.p24_dynamic_k_matching(cost.data_ptr(), ious.data_ptr(), G, P, fg_in.data_ptr(),
+                                                  matched.data_ptr(), miou.data_ptr(), dyn_k.data_ptr(), nfg.data_ptr(),
+                                                  (ws.data_ptr() + 255) & ~255, nbytes, _stream_ptr(dev)),
+                       "p24_dynamic_k_matching")
+        inb = fg_in.bool()
+        fg_mask[fg_mask.clone()] = inb
+        idx = matched[inb].long()
+        self.last_dynamic_ks = dyn_k
+        return int(nfg), gt_classes[idx], miou[inb], idx

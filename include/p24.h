@@ -92,6 +92,59 @@ int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_
  *              (what the backward needs). */
 int p24_loss_finalize(const float* sums28, float* state26, float* result54, float* weights_n27, void* stream);
 
+/* IOUloss.circle_inter (models/losses.py:23-78), element-wise over n pairs.
+ * gt_r / pd_r: [n, 24] with row strides; outputs res_inter, dist: dense [n, 24]. */
+int p24_circle_inter_fwd(const float* gt_cx, const float* gt_cy, const float* gt_r, int64_t gt_r_stride,
+                         const float* pd_cx, const float* pd_cy, const float* pd_r, int64_t pd_r_stride,
+                         int n, float* res_inter, float* dist, void* stream);
+
+/* IOUloss.forward (models/losses.py:80-157): pred [n,26], target [n,50] -> loss24 [n,24] dense. */
+int p24_iou_loss_fwd(const float* pred, int64_t pred_stride, const float* target, int64_t target_stride,
+                     int n, float* loss24, void* stream);
+
+/* Backward of IOUloss.forward w.r.t. pred (autograd of losses.py:80-157; clipped acos and branch
+ * masks have zero gradient).  grad_loss24 dense [n,24]; grad_pred dense [n,26] (overwritten). */
+int p24_iou_loss_bwd(const float* pred, int64_t pred_stride, const float* target, int64_t target_stride,
+                     const float* grad_loss24, int n, float* grad_pred, void* stream);
+
+/* utils.boxes.bboxes_iou (utils/boxes.py:166-243): gt [G,50], pred [P,26] -> out dense [G,P]
+ * (the mean ray LOSS / 2 that SimOTA consumes as an "iou", SURVEY.md note 3). */
+int p24_pair_iou(const float* gt50, int64_t gt_stride, int G, const float* pred26, int64_t pred_stride, int P,
+                 float* out, void* stream);
+
+/* Backward of the whole loss w.r.t. outputs (autograd of models/losses.py:283-341; the weights are constants,
+ * losses.py:312-314): grad_outputs [B, A, 27+nc] dense, fully overwritten.  weights_n27 from p24_loss_finalize /
+ * p24_simota_loss_batch; grad_scale: device scalar (upstream gradient of the loss) or NULL for 1. */
+int p24_loss_bwd(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A, int num_classes,
+                 const float* labels, int64_t lab_img_stride, int64_t lab_row_stride,
+                 const uint8_t* fg_mask, const int32_t* matched_gt, const float* pred_iou,
+                 const float* weights_n27, const float* grad_scale, float* grad_outputs, void* stream);
+
+/* Loss_Function.dynamic_k_matching (models/losses.py:444-494) on a materialised cost matrix.
+ * cost, ious: dense [G, P];  fg_in [P] uint8, matched [P] int32 (-1 when not fg), matched_iou [P] fp32,
+ * dyn_k [G] int32, num_fg [1] int32.  torch.topk leaves tie order unspecified; ties go to the lower index here. */
+size_t p24_dynamic_k_workspace_bytes(int G, int P);
+int p24_dynamic_k_matching(const float* cost, const float* ious, int G, int P,
+                           uint8_t* fg_in, int32_t* matched, float* matched_iou, int32_t* dyn_k, int32_t* num_fg,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* utils.boxes.postprocess (utils/boxes.py:29-99; twin show_24p.py:212-264), per image.
+ *   prediction [B, A, 27+nc] (obj / cls already sigmoid)
+ *   h_coef_x, h_coef_y [24] HOST arrays: theta_k*cos(theta_k), theta_k*sin(theta_k) as the reference's own torch
+ *     expression evaluates them (boxes.py:30-33), passed in so libm differences cannot enter
+ *   class_agnostic != 0 -> torchvision nms, else batched_nms with the coordinate trick
+ * writes, per image b (capacity A rows each):
+ *   cand_count [B]          rows that passed the score filter
+ *   det_count  [B]          rows kept after NMS
+ *   det_rows   [B, A, 29]   cx, cy, r0..r23, obj, class_conf, class_pred in NMS (score) order
+ *   keep_idx   [B, A]       anchor index of every kept row, same order
+ *   rect_debug [B, A, 4]    (may be NULL) rectangles of the candidates in anchor order */
+size_t p24_postprocess_workspace_bytes(int B, int A);
+int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_stride, int B, int A, int num_classes,
+                    const float* h_coef_x, const float* h_coef_y, float conf_thre, float nms_thre, int class_agnostic,
+                    int32_t* cand_count, int32_t* det_count, float* det_rows, int32_t* keep_idx, float* rect_debug,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its four
  * kernels (gt_prep, anchor_pass, gt_match, resolve_loss) on the launching stream; p24_profile_read waits
  * for the last call and returns the four durations in milliseconds into a HOST array.  Process-global. */
