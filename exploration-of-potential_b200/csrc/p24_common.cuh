@@ -34,10 +34,10 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 struct P24Workspace {
     size_t gt_rec;      // [B, Lmax, GT_REC] float
     size_t clist;       // [B, tiles, 256] float4  candidate anchors of a tile, compacted: (pred cx, pred cy, rpmax, anchor idx bits)
-    size_t wseed;       // [B, Lmax, tiles * 8] float4  per (GT, warp of the anchor pass): the two candidates with the smallest
-                        //                              seed proxy (q1, anchor1, q2, anchor2)
-    size_t wbox;        // [B, tiles * 8, 8] float      per warp of the anchor pass: bounding box of its candidates' predicted
-                        //                              centres (xmin, xmax, ymin, ymax), largest rpmax, pad
+    size_t sseed;       // [B, Lmax, 2 * tiles] int     per (GT, tile): the two candidates with the smallest seed proxy (-1: none)
+    size_t sval;        // [B, Lmax, 2 * tiles] float   their exact pair values (k_pair_eval)
+    size_t wcostv;      // [B, Lmax, VCAP] float        SimOTA cost of the GT's centre-window anchors (+inf: not in the polygon)
+    size_t tbox;        // [B, tiles, 8] float          bounding box of a tile's candidate centres (xmin, xmax, ymin, ymax), max rpmax
     size_t ccount;      // [B, tiles] int          candidates per tile
     size_t wcount;      // [B, Lmax] int           anchors inside the GT's centre window (zero between calls)
     size_t wlist;       // [B, Lmax, VCAP] int
@@ -47,7 +47,7 @@ struct P24Workspace {
     size_t claimed;     // [B, 10 * Lmax] int   anchors claimed by at least one GT (arrival order)
     size_t nclaimed;    // [B] int
     size_t acc_fix;     // [B, 28] int64        fixed-point loss sums of the image (zero between calls)
-    size_t ticket;      // [1] unsigned (last-block-done counter; zero between calls)
+    size_t ticket;      // [1 + B] unsigned: batch counter, then one counter per image (zero between calls)
     size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
     size_t total;
 };
@@ -62,14 +62,16 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
     w.wcount = off;     off = p24_align(off + BL * sizeof(int));
-    w.ticket = off;     off = p24_align(off + sizeof(unsigned));
+    w.ticket = off;     off = p24_align(off + (size_t)(1 + B) * sizeof(unsigned));
     w.acc_fix = off;    off = p24_align(off + (size_t)B * 28 * sizeof(long long));
     w.err_flag = off;   off = p24_align(off + sizeof(int));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
     w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
     w.ccount = off;     off = p24_align(off + NB * sizeof(int));
-    w.wseed = off;      off = p24_align(off + BL * (size_t)p24_tiles(A) * P24_WARPS * 4 * sizeof(float));
-    w.wbox = off;       off = p24_align(off + NB * P24_WARPS * 8 * sizeof(float));
+    w.sseed = off;      off = p24_align(off + BL * 2 * (size_t)p24_tiles(A) * sizeof(int));
+    w.sval = off;       off = p24_align(off + BL * 2 * (size_t)p24_tiles(A) * sizeof(float));
+    w.wcostv = off;     off = p24_align(off + BL * P24_VCAP * sizeof(float));
+    w.tbox = off;       off = p24_align(off + NB * 8 * sizeof(float));
     w.wlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));
     w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
     w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));

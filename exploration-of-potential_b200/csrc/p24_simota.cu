@@ -51,8 +51,10 @@ struct Params {
     // workspace
     float* gt_rec;
     float4* clist;
-    float4* wseed;
-    float* wbox;
+    int* sseed;
+    float* sval;
+    float* wcostv;
+    float* tbox;
     int* ccount;
     int* wcount;
     int* wlist;
@@ -83,7 +85,7 @@ __device__ __forceinline__ void tmark(int kern, int cta, int slot) {
 #define TMARK(kern, cta, slot)
 #endif
 
-#define MATCH_THREADS 384
+#define MATCH_THREADS 256
 #define MATCH_WARPS (MATCH_THREADS / 32)
 #define MATCH_GROUPS (MATCH_THREADS / 8)
 
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
     s_row[warp][3][lane] = rpsum * (1.0f / 24.0f);
     s_row[warp][4][lane] = cand ? (rpmin < 0.25f ? INFINITY : rpmax) : -1.0f;
     __syncthreads();
+    __shared__ float s_box[P24_WARPS][5];
     {
         // bounding box of the warp's candidates (GT independent): k_gt_match bounds t = rpmax + d with it
         {
@@ -490,20 +493,22 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
             const float by0 = -warp_max(cand ? -pcy : P24_NEG_INF), by1 = warp_max(cand ? pcy : P24_NEG_INF);
             const float rzm = warp_max(rz);
             if (lane == 0) {
-                float4* dst = reinterpret_cast<float4*>(p.wbox + (((long long)b * p.tiles + tile) * P24_WARPS + warp) * 8);
-                dst[0] = make_float4(bx0, bx1, by0, by1);
-                dst[1] = make_float4(rzm, 0.0f, 0.0f, 0.0f);
+                s_box[warp][0] = bx0;
+                s_box[warp][1] = bx1;
+                s_box[warp][2] = by0;
+                s_box[warp][3] = by1;
+                s_box[warp][4] = rzm;
             }
         }
         // warp w ranks a quarter of the tile's anchors, i = 8 j + ((w - j) & 7) for every 4th j: neighbouring anchors
         // (nearly equal proxies) land in different warps, and a quarter sample is enough for seeds (any candidate
-        // is a valid seed; better ones only make the bracket tighter)
-        const int nw = p.tiles * P24_WARPS;
+        // is a valid seed; better ones only make the bracket tighter).  Per-warp results go to the free rows of s_row.
+        float* wres = &s_row[warp][5][0];  // [n][4]: q1, a1, q2, a2   (22 * 33 = 726 floats: n <= 181)
         for (int g = lane; g < n; g += 32) {
             const float* rec = s_gt + g * GT_REC;
             const float gcx = rec[GT_CX], gcy = rec[GT_CY], rgms = rec[GT_RGMS], rgmean = rec[GT_RGMEAN];
             float q1 = P24_POS_INF, q2 = P24_POS_INF;
-            int a1 = 0x7fffffff, a2 = 0x7fffffff;
+            int a1 = -1, a2 = -1;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 const int j = 4 * jj + (warp & 3);
@@ -527,8 +532,12 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
                     a2 = aj;
                 }
             }
-            const long long o = ((long long)b * p.Lmax + g) * nw + tile * P24_WARPS + warp;
-            p.wseed[o] = make_float4(q1, __int_as_float(a1), q2, __int_as_float(a2));
+            if (g < 181) {
+                wres[g * 4 + 0] = q1;
+                wres[g * 4 + 1] = __int_as_float(a1);
+                wres[g * 4 + 2] = q2;
+                wres[g * 4 + 3] = __int_as_float(a2);
+            }
         }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, cand);
@@ -544,6 +553,47 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
         total += c;
     }
     const long long blk = (long long)b * p.tiles + tile;
+    // the tile's two best seeds per GT (merge of the 8 warps) and the tile's candidate box
+    for (int g = tid; g < n; g += P24_THREADS) {
+        float q1 = P24_POS_INF, q2 = P24_POS_INF;
+        int a1 = -1, a2 = -1;
+        if (g < 181) {
+#pragma unroll
+            for (int w = 0; w < P24_WARPS; ++w) {
+                const float* e = &s_row[w][5][0] + g * 4;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float q = e[2 * u];
+                    const int aq = __float_as_int(e[2 * u + 1]);
+                    if (q < q1) {
+                        q2 = q1;
+                        a2 = a1;
+                        q1 = q;
+                        a1 = aq;
+                    } else if (q < q2) {
+                        q2 = q;
+                        a2 = aq;
+                    }
+                }
+            }
+        }
+        const long long o = ((long long)b * p.Lmax + g) * 2 * p.tiles + 2 * tile;
+        p.sseed[o] = a1;
+        p.sseed[o + 1] = a2;
+    }
+    if (tid == 32) {
+        float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY, rzm = -INFINITY;
+        for (int w = 0; w < P24_WARPS; ++w) {
+            bx0 = fminf(bx0, s_box[w][0]);
+            bx1 = fmaxf(bx1, s_box[w][1]);
+            by0 = fminf(by0, s_box[w][2]);
+            by1 = fmaxf(by1, s_box[w][3]);
+            rzm = fmaxf(rzm, s_box[w][4]);
+        }
+        float4* dst = reinterpret_cast<float4*>(p.tbox + blk * 8);
+        dst[0] = make_float4(bx0, bx1, by0, by1);
+        dst[1] = make_float4(rzm, 0.0f, 0.0f, 0.0f);
+    }
     if (cand) {
         const int rank = base + __popc(bal & ((1u << lane) - 1u));
         // a prediction with a tiny radius disables the bound filter for its pairs: rpmax = +inf
@@ -583,7 +633,6 @@ __device__ __forceinline__ void claim_anchor(const Params& p, int b, int a, int 
 }
 
 #define HIT_CAP 3072
-#define N_SEED (2 * MATCH_WARPS)
 #define MAX_TILES 1024  // candidate counts of an image kept in shared memory (A <= 262144)
 
 // Upper bound of the pair value as a function of t = rpmax + d: any ray has loss <= max(1, 2 - 4 rg^2 / (rg + rp + d)^2)
@@ -606,8 +655,6 @@ struct MatchShared {
     int hit[HIT_CAP];       // slow path: anchors the scalar bound cannot exclude
     float ev[HIT_CAP];      // slow path: exact values that reach the seed threshold
     float top[P24_TOPK];
-    int seed[N_SEED];
-    float seedv[N_SEED];
     KV kv[MATCH_WARPS];
     float wmax[MATCH_WARPS];
     int cnt, nhit, nev, k, slow, nvalid, overflow;
@@ -727,41 +774,75 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
     }
     __syncthreads();
     const float tau = S.tau;
-    const int nslot = p.tiles * P24_THREADS;
-    for (int i0 = tid; i0 < nslot; i0 += MATCH_THREADS) {
-        const int tl = i0 >> 8, rk = i0 & 255;
-        if (rk >= S.ccount[tl]) continue;
-        const float4 q = p.clist[((long long)b * p.tiles + tl) * P24_THREADS + rk];
-        const float dx = gcx - q.x, dy = gcy - q.y;
-        const float t = q.z + sqrtf(fmaf(dx, dx, dy * dy));
-        if (t >= tau || !(t == t)) {
-            const int slot = atomicAdd(&S.nhit, 1);
-            if (slot < HIT_CAP) S.hit[slot] = __float_as_int(q.w);
-            else S.overflow = 1;
+    // 1. scalar filter: a tile whose box bound t_tile is below tau holds no survivor at all; the candidates of the
+    // other tiles are tested with independent loads (flat index over the passing tiles)
+    int* plist = reinterpret_cast<int*>(S.ev);  // passing tiles (S.ev is not in use yet; tiles <= MAX_TILES <= HIT_CAP)
+    if (tid == 0) S.k = 0;  // number of passing tiles (S.k is rewritten by the caller afterwards)
+    __syncthreads();
+    {
+        const float4* tb = reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
+        for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) {
+            if (S.ccount[tl] == 0) continue;
+            const float4 bx = tb[2 * tl];
+            const float rzm = tb[2 * tl + 1].x;
+            const float fx = fmaxf(fabsf(gcx - bx.x), fabsf(gcx - bx.y));
+            const float fy = fmaxf(fabsf(gcy - bx.z), fabsf(gcy - bx.w));
+            const float ttile = rzm + sqrtf(fmaf(fx, fx, fy * fy)) * 1.00001f;
+            if (!(ttile < tau)) plist[atomicAdd(&S.k, 1)] = tl;  // (NaN / inf boxes pass)
+        }
+    }
+    __syncthreads();
+    {
+        const int npass = S.k;
+        const int nslot = npass * P24_THREADS;
+        for (int base = tid; base < nslot; base += 4 * MATCH_THREADS) {
+            float4 q[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i0 = base + u * MATCH_THREADS;
+                ok[u] = false;
+                if (i0 < nslot) {
+                    const int tl = plist[i0 >> 8], rk = i0 & 255;
+                    ok[u] = rk < S.ccount[tl];
+                    if (ok[u]) q[u] = p.clist[((long long)b * p.tiles + tl) * P24_THREADS + rk];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u]) continue;
+                const float dx = gcx - q[u].x, dy = gcy - q[u].y;
+                const float t = q[u].z + sqrtf(fmaf(dx, dx, dy * dy));
+                if (t >= tau || !(t == t)) {
+                    const int slot = atomicAdd(&S.nhit, 1);
+                    if (slot < HIT_CAP) S.hit[slot] = __float_as_int(q[u].w);
+                    else S.overflow = 1;
+                }
+            }
         }
     }
     __syncthreads();
     if (S.overflow) return NAN;  // caller falls back to brute force
     const int nhit = S.nhit;
-    for (int i = grp; i < nhit; i += MATCH_GROUPS) {
+    // 2. per-ray bound, one thread per survivor (24 independent loads in flight); the anchor is tagged when the
+    // bound excludes it
+    for (int i = tid; i < nhit; i += MATCH_THREADS) {
         const float* row = img + (long long)S.hit[i] * p.row_stride;
         const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
-        float rp[3], ub = 0.0f;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            rp[q] = row[2 + sub * 3 + q];
-            ub += p24_ray_loss_ub(S.rec[GT_RG + sub * 3 + q], rp[q], d);
-        }
-        ub = group_sum(ub, gm) * (1.0f / 48.0f) + 2e-5f;
-        if (ub < T) continue;
-        float s = 0.0f;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) s = s + ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
-        s = group_sum(s, gm);
-        const float v = (s / 24.0f) / 2.0f;
-        if (sub == 0 && (v >= T || !(v == v))) {
-            S.ev[atomicAdd(&S.nev, 1)] = (v == v) ? v : P24_POS_INF;  // nev <= nhit <= HIT_CAP
-        }
+        float ub = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < P24_RAYS; ++k) ub += p24_ray_loss_ub(S.rec[GT_RG + k], row[2 + k], d);
+        ub = ub * (1.0f / 48.0f) + 2e-5f;
+        if (ub < T) S.hit[i] = -1;
+    }
+    __syncthreads();
+    // 3. exact value of what is left (8-lane groups); values that reach T are kept
+    for (int i0 = 0; i0 < nhit; i0 += MATCH_GROUPS) {
+        const int i = i0 + grp;
+        const int a = i < nhit ? S.hit[i] : -1;
+        if (a < 0) continue;
+        const float v = group_pair_value(S.rec, img + (long long)a * p.row_stride, gm);
+        if (sub == 0 && (v >= T || !(v == v))) S.ev[atomicAdd(&S.nev, 1)] = (v == v) ? v : P24_POS_INF;  // nev <= nhit
     }
     __syncthreads();
     if (S.nev < P24_TOPK) return NAN;
@@ -832,7 +913,105 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
     }
 }
 
-__global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
+// -------------------------------------------------------------------------------------------
+// k_pair_eval: every exact (GT, anchor) evaluation of the batch as independent 8-lane group tasks
+//   tasks [0, 2 * tiles) of a GT: exact pair value of a seed;
+//   tasks [2 * tiles, 2 * tiles + nwin): a centre-window anchor: polygon test (inscribed-disc accept, else the
+//   reference-order edge terms, 3 per lane), exact pair value and SimOTA cost when inside.
+// Every load of a task is issued before its arithmetic (one memory round trip per task); no barriers.
+// -------------------------------------------------------------------------------------------
+#define EVAL_SPLIT 4
+
+__global__ void __launch_bounds__(P24_THREADS, 4) k_pair_eval(Params p) {
+    const int g = blockIdx.x / EVAL_SPLIT, part = blockIdx.x % EVAL_SPLIT, b = blockIdx.y, tid = threadIdx.x;
+    pdl_wait();
+    const int n = p.num_gt[b];
+    if (g >= n) return;
+    __shared__ float s_rec[GT_REC];
+    const int wslot = b * p.Lmax + g;
+    if (tid < GT_REC) s_rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
+    const int nwin = min(p.wcount[wslot], P24_VCAP);
+    __syncthreads();
+    const float gcx = s_rec[GT_CX], gcy = s_rec[GT_CY];
+    const float* img = p.outputs + (long long)b * p.img_stride;
+    const unsigned gm = group_mask();
+    const int grp = tid >> 3, sub = tid & 7;
+    const int c = gt_class(s_rec, p.nc);
+    const int nseed = 2 * p.tiles;
+    const int ntask = nseed + nwin;
+    for (int task = part * (P24_THREADS / 8) + grp; task < ntask; task += EVAL_SPLIT * (P24_THREADS / 8)) {
+        if (task < nseed) {
+            const long long o = (long long)wslot * nseed + task;
+            const int sa = p.sseed[o];
+            float v = P24_NEG_INF;
+            if (sa >= 0) v = group_pair_value(s_rec, img + (long long)sa * p.row_stride, gm);
+            if (sub == 0) p.sval[o] = v;
+            continue;
+        }
+        const int wi = task - nseed;
+        const int a = p.wlist[(long long)wslot * P24_VCAP + wi];
+        const float* row = img + (long long)a * p.row_stride;
+        const float st = p.strides[a];
+        const float xs = p.x_shifts[a], ys = p.y_shifts[a];
+        const float pcx = row[0], pcy = row[1], obj = row[26], clsc = row[27 + c];
+        float rp[3], cl[10];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) rp[q] = row[2 + sub * 3 + q];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
+        const float xc = p24_anchor_centre(xs, st);
+        const float yc = p24_anchor_centre(ys, st);
+        float cost = P24_POS_INF;
+        bool inside = true;
+        {
+            // inside the inscribed disc the angle sum is >= 360 (see k_gt_prep): no edge terms needed
+            const float ddx = gcx - xc, ddy = gcy - yc;
+            if (!(fmaf(ddx, ddx, ddy * ddy) < s_rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
+                float ang = 0.0f;
+#pragma unroll 1
+                for (int q = 0; q < 3; ++q) {
+                    const int k = sub * 3 + q;
+                    const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
+                    ang = ang + edge_angle(s_rec[GT_VX + k] - xc, s_rec[GT_VY + k] - yc, s_rec[GT_VX + k2] - xc,
+                                           s_rec[GT_VY + k2] - yc);
+                }
+                ang = group_sum(ang, gm);
+                inside = ang >= 350.0f;  // losses.py:588
+            }
+        }
+        if (inside) {
+            const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
+            float s = 0.0f;
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) s = s + ray_loss(s_rec[GT_RG + sub * 3 + q], rp[q], d);
+            s = group_sum(s, gm);
+            const float v = (s / 24.0f) / 2.0f;
+            const float eo1 = 1.0f + expf(-obj);
+            float neg;
+            if (p.nc <= 80) {
+                float prod = 1.0f;
+                int nsat = 0;
+#pragma unroll
+                for (int q = 0; q < 10; ++q)
+                    if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
+                prod = group_prod(prod, gm);
+                nsat = group_sum_i(nsat, gm);
+                neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+            } else {
+                neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+            }
+            cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
+            if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
+        }
+        if (sub == 0) p.wcostv[(long long)wslot * P24_VCAP + wi] = cost;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// k_gt_match: per GT, from the exact values of k_pair_eval: dynamic k (top-10 bracket, exact paths when it is not
+// conclusive) and the k smallest costs -> claims
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MATCH_THREADS) k_gt_match(Params p) {
     const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 #define MCTA (b * 20 + g)
@@ -850,7 +1029,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
     const int nwin = min(p.wcount[wslot], P24_VCAP);
     if (tid < P24_VCAP) {
         S.wanchor[tid] = tid < nwin ? p.wlist[(long long)wslot * P24_VCAP + tid] : 0x7fffffff;
-        S.wcost[tid] = P24_POS_INF;
+        S.wcost[tid] = tid < nwin ? p.wcostv[(long long)wslot * P24_VCAP + tid] : P24_POS_INF;
     }
     int cnt = 0;
     for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) {
@@ -864,157 +1043,55 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_gt_match(Params p) {
     if (lane == 0 && cnt) atomicAdd(&S.cnt, cnt);
     if (tid == 0) p.wcount[wslot] = 0;  // leave the list empty for the next call
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
-    const float* img = p.outputs + (long long)b * p.img_stride;
-
-    // ---- seeds: the anchor pass left, per warp of 32 anchors, the two candidates with the smallest proxy for this
-    // GT and the largest t; take the best two of every slice of them (24 seeds) and the overall largest t ------------
-    float q1 = P24_POS_INF, q2 = P24_POS_INF, tmax = P24_NEG_INF;
-    int a1 = 0x7fffffff, a2 = 0x7fffffff;
-    {
-        const int nw = p.tiles * P24_WARPS;
-        const float4* ws4 = p.wseed + (long long)wslot * nw;
-        const float4* wb = reinterpret_cast<const float4*>(p.wbox + (long long)b * nw * 8);
-        // entry e (one warp of the anchor pass) goes to warp e % 12: the 8 warps of a tile, which share the best
-        // region of the image, are spread over 8 different warps here
-        for (int i = warp + MATCH_WARPS * lane; i < nw; i += MATCH_WARPS * 32) {
-            const float4 e = ws4[i];
-            {
-                // t = rpmax + d <= largest rpmax of the warp + distance to the farthest corner of its box
-                const float4 bx = wb[2 * i];
-                const float rzm = wb[2 * i + 1].x;
-                if (rzm > P24_NEG_INF) {
-                    const float fx = fmaxf(fabsf(gcx - bx.x), fabsf(gcx - bx.y));
-                    const float fy = fmaxf(fabsf(gcy - bx.z), fabsf(gcy - bx.w));
-                    tmax = fmaxf(tmax, rzm + sqrtf(fmaf(fx, fx, fy * fy)) * 1.00001f);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const float q = u ? e.z : e.x;
-                const int a = __float_as_int(u ? e.w : e.y);
-                if (kv_lt(q, a, q1, a1)) {
-                    q2 = q1;
-                    a2 = a1;
-                    q1 = q;
-                    a1 = a;
-                } else if (kv_lt(q, a, q2, a2)) {
-                    q2 = q;
-                    a2 = a;
-                }
-            }
-        }
-        const KV w1 = warp_select<false>(KV{q1, a1});
-        const bool owner = (a1 == w1.i) && (a1 != 0x7fffffff);
-        const KV w2 = warp_select<false>(owner ? KV{q2, a2} : KV{q1, a1});
-        tmax = warp_max(tmax);
-        if (lane == 0) {
-            S.seed[2 * warp] = (w1.i != 0x7fffffff) ? w1.i : -1;
-            S.seed[2 * warp + 1] = (w2.i != 0x7fffffff) ? w2.i : -1;
-            S.wmax[warp] = tmax;
-        }
-    }
     __syncthreads();
     TMARK(1, MCTA, 2);
     const int ncand = S.cnt;
     const int kc = min(P24_TOPK, ncand);  // losses.py:452
 
-    // ---- group tasks: [0, N_SEED) exact value of a seed; [N_SEED, N_SEED + nwin) a centre-window anchor:
-    // polygon test (reference-order edge terms, 3 per lane), exact pair value and cost when inside.  Every load
-    // of a task is issued before its arithmetic (one memory round trip per task) ------------------------------
-    {
-        const unsigned gm = group_mask();
-        const int grp = tid >> 3, sub = tid & 7;
-        const int c = gt_class(S.rec, p.nc);
-        const int ntask = N_SEED + nwin;
-        for (int task = grp; task < ntask; task += MATCH_GROUPS) {
-            if (task < N_SEED) {
-                const int sa = S.seed[task];
-                float v = P24_NEG_INF;
-                if (sa >= 0) v = group_pair_value(S.rec, img + (long long)sa * p.row_stride, gm);
-                if (sub == 0) S.seedv[task] = v;
-                continue;
-            }
-            const int wi = task - N_SEED;
-            const int a = S.wanchor[wi];
-            const float* row = img + (long long)a * p.row_stride;
-            const float st = p.strides[a];
-            const float xs = p.x_shifts[a], ys = p.y_shifts[a];
-            const float pcx = row[0], pcy = row[1], obj = row[26], clsc = row[27 + c];
-            float rp[3], cl[10];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) rp[q] = row[2 + sub * 3 + q];
-#pragma unroll
-            for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
-            const float xc = p24_anchor_centre(xs, st);
-            const float yc = p24_anchor_centre(ys, st);
-            {
-                // inside the inscribed disc the angle sum is >= 360 (see k_gt_prep): no edge terms needed
-                const float ddx = gcx - xc, ddy = gcy - yc;
-                if (!(fmaf(ddx, ddx, ddy * ddy) < S.rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
-                    float ang = 0.0f;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const int k = sub * 3 + q;
-                        const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
-                        ang = ang + edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
-                                               S.rec[GT_VY + k2] - yc);
-                    }
-                    ang = group_sum(ang, gm);
-                    if (!(ang >= 350.0f)) continue;  // losses.py:588
-                }
-            }
-            const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
-            float s = 0.0f;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) s = s + ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
-            s = group_sum(s, gm);
-            const float v = (s / 24.0f) / 2.0f;
-            const float eo1 = 1.0f + expf(-obj);
-            float neg;
-            if (p.nc <= 80) {
-                float prod = 1.0f;
-                int nsat = 0;
-#pragma unroll
-                for (int q = 0; q < 10; ++q)
-                    if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
-                prod = group_prod(prod, gm);
-                nsat = group_sum_i(nsat, gm);
-                neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(row + 27, p.nc, eo1, gm);
-            } else {
-                neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
-            }
-            if (sub == 0) {
-                float cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
-                if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
-                S.wcost[wi] = cost;
-            }
-        }
-    }
-    __syncthreads();
-    TMARK(1, MCTA, 3);
-    // ---- bracket the top-10 sum: L = sum of the 10 best seed values <= S <= 10 * H(t_max) = U ------------
+    // ---- bracket the top-10 sum: L = sum of the 10 best seed values <= S <= 10 * H(t_max) = U (warp 0) ------------
     if (warp == 0) {
-        const float sv = lane < N_SEED ? S.seedv[lane] : P24_NEG_INF;
-        int rank = 0, ns = 0;
-#pragma unroll
-        for (int j = 0; j < N_SEED; ++j) {
-            const float o = __shfl_sync(0xffffffffu, sv, j);
-            rank += kv_gt(o, j, sv, lane) ? 1 : 0;
-            ns += (o > P24_NEG_INF) ? 1 : 0;
-        }
-        float T = P24_NEG_INF, L = 0.0f;
-        if (kc == P24_TOPK && ns >= P24_TOPK) {
-            // sum in descending order, like the reference sums torch.topk's output
-#pragma unroll
-            for (int r = 0; r < P24_TOPK; ++r) {
-                const unsigned who = __ballot_sync(0xffffffffu, rank == r && lane < N_SEED);
-                const float v = __shfl_sync(0xffffffffu, sv, __ffs(who) - 1);
-                L = L + v;
-                T = v;
+        // largest t = rpmax + d over the candidates, bounded per tile by its box
+        float tm = P24_NEG_INF;
+        const float4* tb = reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
+        for (int i = lane; i < p.tiles; i += 32) {
+            const float4 bx = tb[2 * i];
+            const float rzm = tb[2 * i + 1].x;
+            if (rzm > P24_NEG_INF) {
+                const float fx = fmaxf(fabsf(gcx - bx.x), fabsf(gcx - bx.y));
+                const float fy = fmaxf(fabsf(gcy - bx.z), fabsf(gcy - bx.w));
+                tm = fmaxf(tm, rzm + sqrtf(fmaf(fx, fx, fy * fy)) * 1.00001f);
             }
         }
-        float tm = lane < MATCH_WARPS ? S.wmax[lane] : P24_NEG_INF;
         tm = warp_max(tm);
+        // the 10 largest seed values, summed in descending order (like the reference sums torch.topk's output)
+        const int nseed = 2 * p.tiles;
+        const float* sv = p.sval + (long long)wslot * nseed;
+        float v0 = P24_NEG_INF, v1 = P24_NEG_INF, v2 = P24_NEG_INF, v3 = P24_NEG_INF;  // up to 128 seeds: 4 per lane
+        if (lane < nseed) v0 = sv[lane];
+        if (lane + 32 < nseed) v1 = sv[lane + 32];
+        if (lane + 64 < nseed) v2 = sv[lane + 64];
+        if (lane + 96 < nseed) v3 = sv[lane + 96];
+        for (int i = lane + 128; i < nseed; i += 32) v3 = fmaxf(v3, sv[i]);  // more than 128 seeds: keep the best of the rest
+        float T = P24_NEG_INF, L = 0.0f;
+        int got = 0;
+        if (kc == P24_TOPK) {
+#pragma unroll 1
+            for (int r = 0; r < P24_TOPK; ++r) {
+                const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+                const KV best = warp_select<true>(KV{m, lane});
+                if (!(best.v > P24_NEG_INF)) break;
+                if (lane == best.i) {  // remove one copy of the winner
+                    if (v0 == m) v0 = P24_NEG_INF;
+                    else if (v1 == m) v1 = P24_NEG_INF;
+                    else if (v2 == m) v2 = P24_NEG_INF;
+                    else v3 = P24_NEG_INF;
+                }
+                L = L + best.v;
+                T = best.v;
+                ++got;
+            }
+            if (got < P24_TOPK) T = P24_NEG_INF;
+        }
         int slow = 1, k = 0;
         const bool usable = T > P24_NEG_INF && !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && tm < 60000.0f;
         if (usable) {
@@ -1195,7 +1272,7 @@ __device__ __noinline__ int resolve_conflict(const Params& p, const float* recs,
 }
 
 #define FIX_SCALE 68719476736.0  // 2^36: fixed-point unit of the loss accumulators (order-independent sums)
-#define RESOLVE_GRID_X 32
+#define RESOLVE_GRID_X 16
 
 __device__ __forceinline__ long long to_fix(double x) { return __double2ll_rn(x * FIX_SCALE); }
 
@@ -1264,8 +1341,16 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned done = atomicAdd(p.ticket, 1u);
-        s_last = (done == (unsigned)(gridDim.x * gridDim.y) - 1u);
+        // two-level completion count (image, then batch): few atomics per address
+        bool last = false;
+        const unsigned done = atomicAdd(&p.ticket[1 + b], 1u);
+        if (done == (unsigned)gridDim.x - 1u) {
+            p.ticket[1 + b] = 0u;  // ready for the next call
+            __threadfence();
+            const unsigned done2 = atomicAdd(&p.ticket[0], 1u);
+            last = (done2 == (unsigned)gridDim.y - 1u);
+        }
+        s_last = last;
     }
     __syncthreads();
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 5);
@@ -1309,7 +1394,7 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
 size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float); }
 
 // optional per-stage timing (profiling aid for bench.py; process-global, not thread-safe)
-#define N_STAGES 4
+#define N_STAGES 5
 bool g_prof_on = false;
 cudaEvent_t g_prof_ev[N_STAGES + 1];
 bool g_prof_have = false;
@@ -1375,8 +1460,10 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.state26 = state26; p.result54 = result54; p.weights27 = weights_n27;
     p.gt_rec = (float*)(ws + L.gt_rec);
     p.clist = (float4*)(ws + L.clist);
-    p.wseed = (float4*)(ws + L.wseed);
-    p.wbox = (float*)(ws + L.wbox);
+    p.sseed = (int*)(ws + L.sseed);
+    p.sval = (float*)(ws + L.sval);
+    p.wcostv = (float*)(ws + L.wcostv);
+    p.tbox = (float*)(ws + L.tbox);
     p.ccount = (int*)(ws + L.ccount);
     p.wcount = (int*)(ws + L.wcount);
     p.wlist = (int*)(ws + L.wlist);
@@ -1406,15 +1493,18 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     e = launch(k_anchor_pass, dim3(p.tiles, B), dim3(P24_THREADS), dyn, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     prof_mark(2, st);
-    e = launch(k_gt_match, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
+    e = launch(k_pair_eval, dim3(Lmax * EVAL_SPLIT, B), dim3(P24_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     prof_mark(3, st);
+    e = launch(k_gt_match, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
+    if (e != cudaSuccess) return (int)e;
+    prof_mark(4, st);
     {
         const int gx = (P24_TOPK * Lmax + P24_WARPS - 1) / P24_WARPS;
         e = launch(k_resolve_loss, dim3(gx < RESOLVE_GRID_X ? gx : RESOLVE_GRID_X, B), dim3(P24_THREADS), 0, st, pdl, p);
     }
     if (e != cudaSuccess) return (int)e;
-    prof_mark(4, st);
+    prof_mark(5, st);
     return (int)cudaGetLastError();
 }
 
@@ -1437,12 +1527,12 @@ extern "C" int p24_profile_enable(int on) {
     return 0;
 }
 
-extern "C" int p24_profile_read(float* h_ms4) {
-    if (!g_prof_have || !h_ms4) return P24_E_BADARG;
+extern "C" int p24_profile_read(float* h_ms5) {
+    if (!g_prof_have || !h_ms5) return P24_E_BADARG;
     cudaError_t e = cudaEventSynchronize(g_prof_ev[N_STAGES]);
     if (e != cudaSuccess) return (int)e;
     for (int i = 0; i < N_STAGES; ++i) {
-        e = cudaEventElapsedTime(&h_ms4[i], g_prof_ev[i], g_prof_ev[i + 1]);
+        e = cudaEventElapsedTime(&h_ms5[i], g_prof_ev[i], g_prof_ev[i + 1]);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;

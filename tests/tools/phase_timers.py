@@ -33,8 +33,8 @@ lib.p24_debug_read_timers.argtypes = [ctypes.c_void_p]
 assert lib.p24_debug_read_timers(buf.ctypes.data) == 0
 t = buf.astype(np.int64)
 names = {0: ("k_anchor_pass", 660, ["start", "pdl", "rows+recs", "pass1/2 gen", "items", "end"]),
-         1: ("k_gt_match", 400, ["start", "pdl", "scan", "tasks", "bracket", "dyn_k", "select", "spill/end"]),
-         2: ("k_resolve_loss", 640, ["start", "pdl", "-", "-", "entries", "partials", "last"])}
+         1: ("k_gt_match", 400, ["start", "pdl", "load", "-", "bracket", "dyn_k", "select", "spill/end"]),
+         2: ("k_resolve_loss", 320, ["start", "pdl", "-", "-", "entries", "partials", "last"])}
 base = t[0, :660, 0].min()
 for k, (nm, ncta, ph) in names.items():
     tt = t[k, :ncta, :len(ph)]
