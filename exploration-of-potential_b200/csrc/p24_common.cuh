@@ -41,6 +41,7 @@ struct P24Workspace {
     size_t ccount;      // [B, tiles] int          candidates per tile
     size_t wcount;      // [B, Lmax] int           anchors inside the GT's centre window (zero between calls)
     size_t wlist;       // [B, Lmax, VCAP] int
+    size_t best_key;    // [B, A] u64      min over the anchor's valid pairs of (ordered cost bits << 32 | gt)  (losses.py:474)
     size_t claim_cnt;   // [B, A] int      number of GTs that selected the anchor
     size_t claim_gt;    // [B, A] int      the GT that selected the anchor (meaningful when claim_cnt == 1)
     size_t obj_part;    // [B * tiles] double   per-block sums of BCEWithLogits(obj, 0)
@@ -73,6 +74,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     w.wcostv = off;     off = p24_align(off + BL * P24_VCAP * sizeof(float));
     w.tbox = off;       off = p24_align(off + NB * 8 * sizeof(float));
     w.wlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));
+    w.best_key = off;   off = p24_align(off + BA * sizeof(unsigned long long));
     w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
     w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));
     w.obj_part = off;   off = p24_align(off + NB * sizeof(double));

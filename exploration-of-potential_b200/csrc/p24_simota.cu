@@ -58,6 +58,7 @@ struct Params {
     int* ccount;
     int* wcount;
     int* wlist;
+    unsigned long long* best_key;
     int* claim_cnt;
     int* claim_gt;
     double* obj_part;
@@ -72,9 +73,9 @@ struct Params {
 
 // Debug-only phase timers (-DP24_TIMING): thread 0 of every CTA stores %globaltimer at phase boundaries.
 #ifdef P24_TIMING
-__device__ unsigned long long g_tstamp[3][4096][12];
+__device__ unsigned long long g_tstamp[3][4096][20];
 __device__ __forceinline__ void tmark(int kern, int cta, int slot) {
-    if (threadIdx.x == 0 && cta < 4096) {
+    if (threadIdx.x == 0 && cta >= 0 && cta < 4096) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_tstamp[kern][cta][slot] = t;
@@ -603,6 +604,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
         // every anchor starts as background; k_resolve_loss overwrites the claimed ones
         const long long o = (long long)b * p.A + a;
         p.claim_cnt[o] = 0;
+        p.best_key[o] = 0xFFFFFFFFFFFFFFFFull;
         p.fg_mask[o] = 0;
         p.matched_gt[o] = -1;
         p.pred_iou[o] = 0.0f;
@@ -773,6 +775,7 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
         }
     }
     __syncthreads();
+    TMARK(1, b * 20 + (int)blockIdx.x, 12);
     const float tau = S.tau;
     // 1. scalar filter: a tile whose box bound t_tile is below tau holds no survivor at all; the candidates of the
     // other tiles are tested with independent loads (flat index over the passing tiles)
@@ -822,6 +825,7 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
         }
     }
     __syncthreads();
+    TMARK(1, b * 20 + (int)blockIdx.x, 13);
     if (S.overflow) return NAN;  // caller falls back to brute force
     const int nhit = S.nhit;
     // 2. per-ray bound, one thread per survivor (24 independent loads in flight); the anchor is tagged when the
@@ -836,6 +840,7 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
         if (ub < T) S.hit[i] = -1;
     }
     __syncthreads();
+    TMARK(1, b * 20 + (int)blockIdx.x, 14);
     // 3. exact value of what is left (8-lane groups); values that reach T are kept
     for (int i0 = 0; i0 < nhit; i0 += MATCH_GROUPS) {
         const int i = i0 + grp;
@@ -845,6 +850,7 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
         if (sub == 0 && (v >= T || !(v == v))) S.ev[atomicAdd(&S.nev, 1)] = (v == v) ? v : P24_POS_INF;  // nev <= nhit
     }
     __syncthreads();
+    TMARK(1, b * 20 + (int)blockIdx.x, 15);
     if (S.nev < P24_TOPK) return NAN;
     if (warp == 0) warp_select_top(S.ev, S.nev, P24_TOPK, S.top);
     __syncthreads();
@@ -1002,6 +1008,9 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pair_eval(Params p) {
             }
             cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
             if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
+            // per-anchor argmin over its valid pairs (first GT index on ties): what conflict resolution needs
+            if (sub == 0)
+                atomicMin(&p.best_key[(long long)b * p.A + a], ((unsigned long long)p24_ordered(cost) << 32) | (unsigned)g);
         }
         if (sub == 0) p.wcostv[(long long)wslot * P24_VCAP + wi] = cost;
     }
@@ -1220,44 +1229,13 @@ __device__ __forceinline__ float warp_pair_value(const float* __restrict__ rec, 
     return (warp_sum(l) / 24.0f) / 2.0f;
 }
 
-// Anchor claimed by several GTs: argmin of the cost over ALL GTs (losses.py:471-476); first index on ties.
-// One warp per anchor: lanes over GTs for the window test, then the whole warp on each in-window GT.
+// Anchor claimed by several GTs none of which is valid for it (every claim came from a spill): argmin of the
+// PENALISED cost over all GTs (losses.py:471-476), first index on ties.  One warp, rare.
 __device__ __noinline__ int resolve_conflict(const Params& p, const float* recs, int n, const float* row, int a) {
-    const int lane = threadIdx.x & 31;
-    const float st = p.strides[a];
-    const float xc = p24_anchor_centre(p.x_shifts[a], st);
-    const float yc = p24_anchor_centre(p.y_shifts[a], st);
     const float eo1 = 1.0f + expf(-row[26]);
     const float neg = warp_cls_neg_sum(row + 27, p.nc, eo1);
     const float obj_sig = 1.0f / eo1;
     KV best = {P24_POS_INF, 0x7fffffff};
-    for (int g0 = 0; g0 < n; g0 += 32) {
-        const int gl = g0 + lane;
-        const bool inwin = gl < n && p24_in_centre(recs[gl * GT_REC + GT_CX], recs[gl * GT_REC + GT_CY], xc, yc, st);
-        unsigned m = __ballot_sync(0xffffffffu, inwin);
-        while (m) {
-            const int g = g0 + __ffs(m) - 1;
-            m &= m - 1;
-            const float* rec = recs + g * GT_REC;
-            float ang = 0.0f;
-            if (lane < P24_RAYS) {
-                const int k2 = (lane == P24_RAYS - 1) ? 0 : lane + 1;
-                ang = edge_angle(rec[GT_VX + lane] - xc, rec[GT_VY + lane] - yc, rec[GT_VX + k2] - xc, rec[GT_VY + k2] - yc);
-            }
-            ang = warp_sum(ang);
-            if (!(ang >= 350.0f)) continue;
-            float l;
-            const float v = warp_pair_value(rec, row, l);
-            float c = p24_cost(cls_cost_from(neg, row[27 + gt_class(rec, p.nc)], obj_sig), v, true);
-            if (!(c < 3.0e38f)) c = 3.0e38f;
-            if (kv_lt(c, g, best.v, best.i)) {
-                best.v = c;
-                best.i = g;
-            }
-        }
-    }
-    if (best.i != 0x7fffffff) return best.i;
-    // no valid pair at all (every claim came from a spill): argmin over the penalised costs
     for (int g = 0; g < n; ++g) {
         const float* rec = recs + g * GT_REC;
         float l;
@@ -1268,6 +1246,7 @@ __device__ __noinline__ int resolve_conflict(const Params& p, const float* recs,
             best.i = g;
         }
     }
+    (void)a;
     return best.i != 0x7fffffff ? best.i : 0;
 }
 
@@ -1301,7 +1280,13 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
         const float* row = img + (long long)aa * p.row_stride;
         const int cnt = p.claim_cnt[o];
         int g = p.claim_gt[o];
-        if (cnt > 1) g = resolve_conflict(p, recs, n, row, aa);
+        if (cnt > 1) {
+            // claimed by several GTs: argmin of the cost over ALL GTs (losses.py:471-476).  Valid pairs always beat
+            // penalised ones and their argmin was recorded by k_pair_eval; without any valid pair (every claim came
+            // from a spill) the penalised costs are evaluated here
+            const unsigned long long key = p.best_key[o];
+            g = (key != 0xFFFFFFFFFFFFFFFFull) ? (int)(key & 0xFFFFFFFFu) : resolve_conflict(p, recs, n, row, aa);
+        }
         const float* rec = recs + g * GT_REC;
         float l;
         const float v = warp_pair_value(rec, row, l);  // pair value == pred_ious_this_matching (losses.py:491)
@@ -1467,6 +1452,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.ccount = (int*)(ws + L.ccount);
     p.wcount = (int*)(ws + L.wcount);
     p.wlist = (int*)(ws + L.wlist);
+    p.best_key = (unsigned long long*)(ws + L.best_key);
     p.claim_cnt = (int*)(ws + L.claim_cnt);
     p.claim_gt = (int*)(ws + L.claim_gt);
     p.obj_part = (double*)(ws + L.obj_part);
@@ -1540,6 +1526,6 @@ extern "C" int p24_profile_read(float* h_ms5) {
 
 #ifdef P24_TIMING
 extern "C" int p24_debug_read_timers(unsigned long long* h_out) {
-    return (int)cudaMemcpyFromSymbol(h_out, g_tstamp, sizeof(unsigned long long) * 3 * 4096 * 12);
+    return (int)cudaMemcpyFromSymbol(h_out, g_tstamp, sizeof(unsigned long long) * 3 * 4096 * 20);
 }
 #endif

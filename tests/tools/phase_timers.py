@@ -28,7 +28,7 @@ for i in range(10):
     o, l = sets[(i % 5) if only is None else only]
     lf.forward_async((g[0], g[1], g[2], o, []), l)
 torch.cuda.synchronize()
-buf = np.zeros((3, 4096, 12), dtype=np.uint64)
+buf = np.zeros((3, 4096, 20), dtype=np.uint64)
 lib.p24_debug_read_timers.argtypes = [ctypes.c_void_p]
 assert lib.p24_debug_read_timers(buf.ctypes.data) == 0
 t = buf.astype(np.int64)
@@ -55,5 +55,10 @@ for k, (nm, ncta, ph) in names.items():
         print("   slow-path CTAs:", int((slow != 0).sum()), "of", ncta, "kinds", slow[slow != 0].tolist(),
               "nhit", t[1, :ncta, 9][slow != 0].tolist(), "nev", t[1, :ncta, 10][slow != 0].tolist(),
               "overflow", t[1, :ncta, 11][slow != 0].tolist())
+        full = t[1, :ncta]
+        for ci in np.nonzero(slow != 0)[0][:6]:
+            r = full[ci]
+            print("      slow CTA", int(ci), "dyn_k phases us: tau", (r[12] - r[4]) / 1e3, "scan", (r[13] - r[12]) / 1e3,
+                  "ub", (r[14] - r[13]) / 1e3, "exact", (r[15] - r[14]) / 1e3, "select", (r[5] - r[15]) / 1e3)
         tot = (tt[ok, 7] - tt[ok, 1]) / 1e3
         print(f"   CTA total mean {tot.mean():.2f} us max {tot.max():.2f} us; slow ones: {np.round(tot[slow[ok] != 0], 1).tolist()[:20]}")
