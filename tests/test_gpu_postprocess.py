@@ -88,3 +88,35 @@ def test_strided_view_without_bulk_copy_path():
     b = p24_boxes.postprocess(wide[:, :, :107], 80, 0.25, 0.45)
     for x, y in zip(a, b):
         assert (x is None) == (y is None) and (x is None or torch.equal(x, y))
+
+
+def test_config4_full_batch64_properties():
+    """BASELINE.json configs[3] at full size (B=64): per-image independence, score ordering, and the NMS invariant
+    (no kept rectangle overlaps an earlier kept one of its class above the threshold)."""
+    p = synth.make_postprocess_input(64, 640, 80, seed=3).to(DEV)
+    conf, nms = 0.25, 0.45
+    cand, cnt, rows, keep, rects = p24_boxes.postprocess_raw(p, 80, conf, nms, False, want_rects=True)
+    single = p24_boxes.postprocess_raw(p[17:18], 80, conf, nms, False)
+    n17 = int(cnt[17])
+    assert n17 == int(single[1][0]) and torch.equal(rows[17, :n17], single[2][0, :n17])
+    cx, cy = p24_boxes.spiral_coefficients()
+    cx, cy = cx.to(DEV), cy.to(DEV)
+    for b in (0, 31, 63):
+        n = int(cnt[b])
+        r = rows[b, :n]
+        score = r[:, 26] * r[:, 27]
+        assert (score >= conf).all() and (score[:-1] >= score[1:]).all()
+        assert torch.equal(r[:, :27], p[b, keep[b, :n].long(), :27])
+        px = r[:, 2:26] * cx + r[:, 0:1]
+        py = r[:, 2:26] * cy + r[:, 1:2]
+        box = torch.stack([px.min(1).values, py.min(1).values, px.max(1).values, py.max(1).values], 1).double()
+        area = (box[:, 2] - box[:, 0]) * (box[:, 3] - box[:, 1])
+        lt = torch.max(box[:, None, :2], box[None, :, :2])
+        rb = torch.min(box[:, None, 2:], box[None, :, 2:])
+        wh = (rb - lt).clamp(min=0)
+        inter = wh[..., 0] * wh[..., 1]
+        iou = inter / (area[:, None] + area[None, :] - inter)
+        same = r[:, 28][:, None] == r[:, 28][None, :]
+        iou = torch.where(same, iou, torch.zeros_like(iou))
+        iou.fill_diagonal_(0)
+        assert float(iou.max()) <= nms + 1e-5

@@ -181,3 +181,37 @@ def test_full_size_batch20_properties():
         _, _, s = Loss_Function(80).forward_async((gx, gy, gs, out[b:b + 1], []), lab[b:b + 1])
         assert torch.equal(s.fg_mask[0], a.fg_mask[b]) and torch.equal(s.matched_gt[0], a.matched_gt[b])
         assert torch.equal(s.pred_iou[0], a.pred_iou[b]) and torch.equal(s.dyn_k[0], a.dyn_k[b])
+
+
+def test_config5_highres_1280_vs_oracle_on_gpu():
+    """BASELINE.json configs[4] shape (1280x1280, 33600 anchors, 20 GT/img) at a reduced batch."""
+    out = synth.make_head_outputs(2, 1280, 80, seed=4)
+    lab = synth.make_labels(2, 20, 50, 1280, 80, seed=4, kind="smooth")
+    _run_both(out, lab, 1280, steps=1)
+
+
+def test_crowded_full_batch_properties():
+    """BASELINE.json configs[2] at full size (B=20, 100 GT/img): per-image independence and count consistency."""
+    out = synth.make_head_outputs(20, 640, 80, seed=2).to(DEV)
+    lab = synth.make_labels(20, 100, 100, 640, 80, seed=2, kind="smooth").to(DEV)
+    gx, gy, gs = _grids(640)
+    res, _, a = Loss_Function(80).forward_async((gx, gy, gs, out, []), lab)
+    assert int(a.sums28[26]) == int(a.num_fg.sum()) == int(a.fg_mask.sum()) and int(a.sums28[27]) == 2000
+    assert ((a.matched_gt >= 0) == a.fg_mask.bool()).all() and int(a.matched_gt.max()) < 100
+    assert (a.dyn_k >= 1).all() and (a.dyn_k <= 10).all()
+    # every GT keeps at most dyn_k anchors after conflict resolution
+    for b in (0, 13):
+        counts = torch.bincount(a.matched_gt[b][a.fg_mask[b].bool()].long(), minlength=100)
+        assert (counts <= a.dyn_k[b].long()).all()
+        _, _, s = Loss_Function(80).forward_async((gx, gy, gs, out[b:b + 1], []), lab[b:b + 1])
+        assert torch.equal(s.fg_mask[0], a.fg_mask[b]) and torch.equal(s.matched_gt[0], a.matched_gt[b])
+        assert torch.equal(s.dyn_k[0], a.dyn_k[b])
+    assert torch.isfinite(res).all()
+
+
+def test_mixed_label_kinds_many_seeds_vs_oracle_on_gpu():
+    """Several seeds / label kinds / GT counts at 640x640 against the oracle on the same GPU (decisions bit-exact)."""
+    for seed, kind, n in [(51, "smooth", 7), (52, "spiky", 13), (53, "smooth", 33), (54, "spiky", 2)]:
+        out = synth.make_head_outputs(2, 640, 80, seed=seed)
+        lab = synth.make_labels(2, [n, max(n // 2, 1)], 50, 640, 80, seed=seed, kind=kind)
+        _run_both(out, lab, 640, steps=1)
