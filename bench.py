@@ -245,18 +245,18 @@ def main():
     # launching stream) -> roofline of the dominant kernel ------------------------------------------------------
     import ctypes
     lib.p24_profile_enable(1)
-    acc = [0.0] * 5
-    buf = (ctypes.c_float * 5)()
+    acc = [0.0] * 6
+    buf = (ctypes.c_float * 6)()
     for i in range(args.steps):
         step(i)
         p24_lib.check(lib.p24_profile_read(buf), "p24_profile_read")
-        for k in range(5):
+        for k in range(6):
             acc[k] += buf[k]
     lib.p24_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
     kern_ms = [a / args.steps for a in acc]
-    names = ["k_gt_prep", "k_anchor_pass", "k_pair_eval", "k_gt_match", "k_resolve_loss"]
-    top = max(range(5), key=lambda k: kern_ms[k])
+    names = ["k_gt_prep", "k_anchor_pass", "k_dyn_k", "k_window_eval", "k_select", "k_resolve_loss"]
+    top = max(range(6), key=lambda k: kern_ms[k])
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes_per_image(A, 107, Lmax) * B
     achieved = alg / (kern_ms[top] * 1e-3) / 1e9
@@ -312,7 +312,7 @@ def main():
         cpu_baseline = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
-        launches_per_step = 5 if world == 1 else 6  # gt_prep, anchor_pass, pair_eval, gt_match, resolve_loss (+ finalize after the all-reduce)
+        launches_per_step = 6 if world == 1 else 7  # gt_prep, anchor_pass, dyn_k, window_eval, select, resolve_loss (+ finalize after the all-reduce)
         print(json.dumps({"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,

@@ -14,7 +14,7 @@
 // ---- per-GT record (floats), built once per image by the anchor pass ---------------------------
 // [0] cx  [1] cy  [2] rin2  [3] rrej2   (one 128-bit shared-memory load for the per-pair tests)
 // [4] class (as float)  [5] rgmax  [6] rgmin  [7] pad
-// [8..31] vertex x  [32..55] vertex y  [56..79] ray length rg  [80] mean rg^2  [81] mean rg  [82..83] pad
+// [8..31] vertex x  [32..55] vertex y  [56] mean rg^2  [57] mean rg  [58..59] pad  [60..83] ray length rg
 #define GT_CX 0
 #define GT_CY 1
 #define GT_RIN2 2    // squared radius of a disc around (cx, cy) that lies inside the polygon (0: none)
@@ -24,9 +24,10 @@
 #define GT_RGMIN 6
 #define GT_VX 8
 #define GT_VY 32
-#define GT_RG 56
-#define GT_RGMS 80    // mean of rg^2 (seed ranking)
-#define GT_RGMEAN 81  // mean of rg
+#define GT_RGMS 56    // mean of rg^2 (seed ranking)
+#define GT_RGMEAN 57  // mean of rg
+#define GT_RG 60      // ray lengths come last: the anchor pass keeps only the first GT_REC_HEAD floats in shared memory
+#define GT_REC_HEAD 60
 #define GT_REC 84
 
 static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -48,7 +49,8 @@ struct P24Workspace {
     size_t claimed;     // [B, 10 * Lmax] int   anchors claimed by at least one GT (arrival order)
     size_t nclaimed;    // [B] int
     size_t acc_fix;     // [B, 28] int64        fixed-point loss sums of the image (zero between calls)
-    size_t ticket;      // [1 + B] unsigned: batch counter, then one counter per image (zero between calls)
+    size_t ticket;      // [2 + B] unsigned: batch counter, work-queue head of k_window_eval, one counter per image
+                        //                   (zero between calls)
     size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
     size_t total;
 };
@@ -63,7 +65,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
     w.wcount = off;     off = p24_align(off + BL * sizeof(int));
-    w.ticket = off;     off = p24_align(off + (size_t)(1 + B) * sizeof(unsigned));
+    w.ticket = off;     off = p24_align(off + (size_t)(2 + B) * sizeof(unsigned));
     w.acc_fix = off;    off = p24_align(off + (size_t)B * 28 * sizeof(long long));
     w.err_flag = off;   off = p24_align(off + sizeof(int));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));

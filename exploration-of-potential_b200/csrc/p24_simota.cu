@@ -73,7 +73,7 @@ struct Params {
 
 // Debug-only phase timers (-DP24_TIMING): thread 0 of every CTA stores %globaltimer at phase boundaries.
 #ifdef P24_TIMING
-__device__ unsigned long long g_tstamp[3][4096][20];
+__device__ unsigned long long g_tstamp[6][4096][20];
 __device__ __forceinline__ void tmark(int kern, int cta, int slot) {
     if (threadIdx.x == 0 && cta >= 0 && cta < 4096) {
         unsigned long long t;
@@ -93,6 +93,13 @@ __device__ __forceinline__ void tmark(int kern, int cta, int slot) {
 __device__ __forceinline__ void pdl_wait() {
 #if __CUDA_ARCH__ >= 900
     cudaGridDependencySynchronize();
+#endif
+}
+// lets the next kernel of the stream start launching now (it must not read this kernel's outputs before its own
+// pdl_wait)
+__device__ __forceinline__ void pdl_trigger() {
+#if __CUDA_ARCH__ >= 900
+    cudaTriggerProgrammaticLaunchCompletion();
 #endif
 }
 
@@ -122,7 +129,9 @@ __device__ __forceinline__ int group_sum_i(int v, unsigned m) {
 // -------------------------------------------------------------------------------------------
 #define PREP_THREADS 1024
 __global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(Params p) {
+    TMARK(3, blockIdx.x, 0);
     pdl_wait();
+    TMARK(3, blockIdx.x, 1);
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* lab = p.labels + (long long)b * p.lab_img_stride;
     // nlabel = (labels.sum(2) > 0).sum(1)   losses.py:190 ; the first n rows are the GTs (losses.py:219-220)
@@ -212,10 +221,11 @@ __global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(Params p) {
             rec[7] = 0.0f;
             rec[GT_RGMS] = rg2sum * (1.0f / 24.0f);
             rec[GT_RGMEAN] = rgsum * (1.0f / 24.0f);
-            rec[82] = 0.0f;
-            rec[83] = 0.0f;
+            rec[58] = 0.0f;
+            rec[59] = 0.0f;
         }
     }
+    TMARK(3, blockIdx.x, 2);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -305,8 +315,8 @@ __device__ __forceinline__ float cls_cost_from(float neg_sum, float cls_logit_c,
 // -------------------------------------------------------------------------------------------
 // k_anchor_pass
 // -------------------------------------------------------------------------------------------
-#define ITEM_CAP 2048
-#define WIN_CAP 1024
+#define ITEM_CAP 704
+#define WIN_CAP 704
 #define ROW_CH 27  // channels 0..26 of a head row are read here: centre, 24 radii, objectness
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -317,17 +327,18 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-__global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
+__global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
     extern __shared__ float4 s_dyn4[];
-    float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC]
+    float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC_HEAD]: everything but the ray lengths
     const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int a = tile * P24_THREADS + tid;
     const bool active = a < p.A;
 
     __shared__ float s_row[P24_WARPS][ROW_CH][33];
-    __shared__ unsigned s_items[ITEM_CAP];
-    __shared__ unsigned s_win[WIN_CAP];
+    // the work lists live in rows 5.. of s_row (free between the row reduction and the seed search)
+    unsigned* s_items = reinterpret_cast<unsigned*>(&s_row[0][5][0]);  // 726 floats per warp region; ITEM_CAP <= 726
+    unsigned* s_win = reinterpret_cast<unsigned*>(&s_row[1][5][0]);    // WIN_CAP <= 726
     __shared__ int s_cand[P24_THREADS];
     __shared__ int s_nitems, s_nwin;
     __shared__ int s_wcnt[P24_WARPS];
@@ -361,7 +372,10 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
     const int n = p.num_gt[b];
     {
         const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
-        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) s_dyn4[i] = gsrc[i];
+        for (int i = tid; i < n * (GT_REC_HEAD / 4); i += P24_THREADS) {
+            const int g = i / (GT_REC_HEAD / 4), q = i - g * (GT_REC_HEAD / 4);
+            s_dyn4[i] = gsrc[g * (GT_REC / 4) + q];
+        }
     }
     cp_async_wait_all();
     __syncthreads();
@@ -384,6 +398,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
         obj = s_row[warp][26][lane];
     }
     double objpart = active ? (double)p24_bce_logits(obj, 0.0f) : 0.0;
+    __syncthreads();  // the radii rows of s_row are recycled as work lists from here on
 
     // ---- one pass over the GTs: centre windows (-> per-GT lists), the inscribed-disc accept, and a bit mask of the
     // GTs whose reject radius the anchor is inside (the only ones that may need a polygon test) ------------------
@@ -394,7 +409,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
     {
         const float r25 = 2.5f * st + 1e-3f * st;  // conservative pre-filter radius of the window test
         for (int g = 0; g < n; ++g) {
-            const float4 h = s_dyn4[g * (GT_REC / 4)];
+            const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             const float d2 = fmaf(dx, dx, dy * dy);
             cheap |= d2 < h.z;
@@ -429,17 +444,17 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
                 if (slot < ITEM_CAP) {
                     s_items[slot] = (unsigned)tid | ((unsigned)g << 8);
                 } else if (!mine) {
-                    const float* rec = s_gt + g * GT_REC;
+                    const float* rec = s_gt + g * GT_REC_HEAD;
                     mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
                                     : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
                 }
             }
         }
         for (int g = 128; g < n && !mine; ++g) {  // more than 128 GTs: test the rest in place
-            const float4 h = s_dyn4[g * (GT_REC / 4)];
+            const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             if (no_prune || fmaf(dx, dx, dy * dy) <= h.w) {
-                const float* rec = s_gt + g * GT_REC;
+                const float* rec = s_gt + g * GT_REC_HEAD;
                 mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
                                 : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
             }
@@ -464,7 +479,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
         const int al = it & 0xFF;
         if (((volatile int*)s_cand)[al]) continue;  // already a candidate through another GT
         const int g = it >> 8;
-        const float* rec = s_gt + g * GT_REC;
+        const float* rec = s_gt + g * GT_REC_HEAD;
         const int aa = tile * P24_THREADS + al;
         const float st2 = p.strides[aa];
         const float axc = p24_anchor_centre(p.x_shifts[aa], st2);
@@ -506,7 +521,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
         // is a valid seed; better ones only make the bracket tighter).  Per-warp results go to the free rows of s_row.
         float* wres = &s_row[warp][5][0];  // [n][4]: q1, a1, q2, a2   (22 * 33 = 726 floats: n <= 181)
         for (int g = lane; g < n; g += 32) {
-            const float* rec = s_gt + g * GT_REC;
+            const float* rec = s_gt + g * GT_REC_HEAD;
             const float gcx = rec[GT_CX], gcy = rec[GT_CY], rgms = rec[GT_RGMS], rgmean = rec[GT_RGMEAN];
             float q1 = P24_POS_INF, q2 = P24_POS_INF;
             int a1 = -1, a2 = -1;
@@ -554,33 +569,52 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_anchor_pass(Params p) {
         total += c;
     }
     const long long blk = (long long)b * p.tiles + tile;
-    // the tile's two best seeds per GT (merge of the 8 warps) and the tile's candidate box
-    for (int g = tid; g < n; g += P24_THREADS) {
-        float q1 = P24_POS_INF, q2 = P24_POS_INF;
-        int a1 = -1, a2 = -1;
-        if (g < 181) {
+    // the tile's two best seeds per GT (merge of the 8 warps), evaluated exactly right away (8-lane groups): what
+    // k_dyn_k brackets the top-10 sum with.  128 GTs at a time.
+    __shared__ int s_seedA[2 * 128];
+    for (int g0 = 0; g0 < n; g0 += 128) {
+        const int gn = min(128, n - g0);
+        if (tid < gn) {
+            const int g = g0 + tid;
+            float q1 = P24_POS_INF, q2 = P24_POS_INF;
+            int a1 = -1, a2 = -1;
+            if (g < 181) {
 #pragma unroll
-            for (int w = 0; w < P24_WARPS; ++w) {
-                const float* e = &s_row[w][5][0] + g * 4;
+                for (int w = 0; w < P24_WARPS; ++w) {
+                    const float* e = &s_row[w][5][0] + g * 4;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const float q = e[2 * u];
-                    const int aq = __float_as_int(e[2 * u + 1]);
-                    if (q < q1) {
-                        q2 = q1;
-                        a2 = a1;
-                        q1 = q;
-                        a1 = aq;
-                    } else if (q < q2) {
-                        q2 = q;
-                        a2 = aq;
+                    for (int u = 0; u < 2; ++u) {
+                        const float q = e[2 * u];
+                        const int aq = __float_as_int(e[2 * u + 1]);
+                        if (q < q1) {
+                            q2 = q1;
+                            a2 = a1;
+                            q1 = q;
+                            a1 = aq;
+                        } else if (q < q2) {
+                            q2 = q;
+                            a2 = aq;
+                        }
                     }
                 }
             }
+            s_seedA[2 * tid] = a1;
+            s_seedA[2 * tid + 1] = a2;
         }
-        const long long o = ((long long)b * p.Lmax + g) * 2 * p.tiles + 2 * tile;
-        p.sseed[o] = a1;
-        p.sseed[o + 1] = a2;
+        __syncthreads();
+        {
+            const unsigned gm = group_mask();
+            const int grp = tid >> 3, sub = tid & 7;
+            for (int t = grp; t < 2 * gn; t += P24_THREADS / 8) {
+                const int sa = s_seedA[t];
+                const int g = g0 + (t >> 1);
+                float v = P24_NEG_INF;
+                if (sa >= 0)
+                    v = group_pair_value(p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC, img + (long long)sa * p.row_stride, gm);
+                if (sub == 0) p.sval[((long long)b * p.Lmax + g) * 2 * p.tiles + 2 * tile + (t & 1)] = v;
+            }
+        }
+        __syncthreads();
     }
     if (tid == 32) {
         float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY, rzm = -INFINITY;
@@ -920,126 +954,130 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
 }
 
 // -------------------------------------------------------------------------------------------
-// k_pair_eval: every exact (GT, anchor) evaluation of the batch as independent 8-lane group tasks
-//   tasks [0, 2 * tiles) of a GT: exact pair value of a seed;
-//   tasks [2 * tiles, 2 * tiles + nwin): a centre-window anchor: polygon test (inscribed-disc accept, else the
-//   reference-order edge terms, 3 per lane), exact pair value and SimOTA cost when inside.
-// Every load of a task is issued before its arithmetic (one memory round trip per task); no barriers.
+// k_window_eval: every (GT, centre-window anchor) pair of the batch as an independent 8-lane group task:
+// polygon test (inscribed-disc accept, else the reference-order edge terms, 3 per lane), exact pair value and
+// SimOTA cost when inside, per-anchor argmin key.  Every load of a task is issued before its arithmetic.
+// Persistent grid (one wave).  It needs nothing from k_dyn_k, which precedes it in the stream: it starts while
+// k_dyn_k's slow CTAs are still running and only waits for them at its very end, so that the kernels after it
+// are ordered after both.
 // -------------------------------------------------------------------------------------------
 #define EVAL_SPLIT 4
 
-__global__ void __launch_bounds__(P24_THREADS, 4) k_pair_eval(Params p) {
-    const int g = blockIdx.x / EVAL_SPLIT, part = blockIdx.x % EVAL_SPLIT, b = blockIdx.y, tid = threadIdx.x;
-    pdl_wait();
-    const int n = p.num_gt[b];
-    if (g >= n) return;
+__global__ void __launch_bounds__(P24_THREADS, 4) k_window_eval(Params p) {
+    const int tid = threadIdx.x;
+    TMARK(4, blockIdx.x, 0);
     __shared__ float s_rec[GT_REC];
-    const int wslot = b * p.Lmax + g;
-    if (tid < GT_REC) s_rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
-    const int nwin = min(p.wcount[wslot], P24_VCAP);
-    __syncthreads();
-    const float gcx = s_rec[GT_CX], gcy = s_rec[GT_CY];
-    const float* img = p.outputs + (long long)b * p.img_stride;
     const unsigned gm = group_mask();
     const int grp = tid >> 3, sub = tid & 7;
-    const int c = gt_class(s_rec, p.nc);
-    const int nseed = 2 * p.tiles;
-    const int ntask = nseed + nwin;
-    for (int task = part * (P24_THREADS / 8) + grp; task < ntask; task += EVAL_SPLIT * (P24_THREADS / 8)) {
-        if (task < nseed) {
-            const long long o = (long long)wslot * nseed + task;
-            const int sa = p.sseed[o];
-            float v = P24_NEG_INF;
-            if (sa >= 0) v = group_pair_value(s_rec, img + (long long)sa * p.row_stride, gm);
-            if (sub == 0) p.sval[o] = v;
-            continue;
-        }
-        const int wi = task - nseed;
-        const int a = p.wlist[(long long)wslot * P24_VCAP + wi];
-        const float* row = img + (long long)a * p.row_stride;
-        const float st = p.strides[a];
-        const float xs = p.x_shifts[a], ys = p.y_shifts[a];
-        const float pcx = row[0], pcy = row[1], obj = row[26], clsc = row[27 + c];
-        float rp[3], cl[10];
+    const int nitem = p.B * p.Lmax * EVAL_SPLIT;
+    __shared__ int s_item;
+    for (;;) {
+        // dynamic work queue: (GT, part) items are very uneven (rows beyond num_gt are empty)
+        __syncthreads();
+        if (tid == 0) s_item = (int)atomicAdd(&p.ticket[1], 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= nitem) break;
+        const int part = item % EVAL_SPLIT;
+        const int wslot = item / EVAL_SPLIT;  // b * Lmax + g
+        const int b = wslot / p.Lmax, g = wslot - b * p.Lmax;
+        if (g >= p.num_gt[b]) continue;
+        const int nwin = min(p.wcount[wslot], P24_VCAP);
+        if (part * (P24_THREADS / 8) >= nwin) continue;
+        __syncthreads();
+        if (tid < GT_REC) s_rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
+        __syncthreads();
+        const float gcx = s_rec[GT_CX], gcy = s_rec[GT_CY];
+        const float* img = p.outputs + (long long)b * p.img_stride;
+        const int c = gt_class(s_rec, p.nc);
+        for (int wi = part * (P24_THREADS / 8) + grp; wi < nwin; wi += EVAL_SPLIT * (P24_THREADS / 8)) {
+            const int a = p.wlist[(long long)wslot * P24_VCAP + wi];
+            const float* row = img + (long long)a * p.row_stride;
+            const float st = p.strides[a];
+            const float xs = p.x_shifts[a], ys = p.y_shifts[a];
+            const float pcx = row[0], pcy = row[1], obj = row[26], clsc = row[27 + c];
+            float rp[3], cl[10];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) rp[q] = row[2 + sub * 3 + q];
+            for (int q = 0; q < 3; ++q) rp[q] = row[2 + sub * 3 + q];
 #pragma unroll
-        for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
-        const float xc = p24_anchor_centre(xs, st);
-        const float yc = p24_anchor_centre(ys, st);
-        float cost = P24_POS_INF;
-        bool inside = true;
-        {
-            // inside the inscribed disc the angle sum is >= 360 (see k_gt_prep): no edge terms needed
-            const float ddx = gcx - xc, ddy = gcy - yc;
-            if (!(fmaf(ddx, ddx, ddy * ddy) < s_rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
-                float ang = 0.0f;
+            for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
+            const float xc = p24_anchor_centre(xs, st);
+            const float yc = p24_anchor_centre(ys, st);
+            float cost = P24_POS_INF;
+            bool inside = true;
+            {
+                // inside the inscribed disc the angle sum is >= 360 (see k_gt_prep): no edge terms needed
+                const float ddx = gcx - xc, ddy = gcy - yc;
+                if (!(fmaf(ddx, ddx, ddy * ddy) < s_rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
+                    float ang = 0.0f;
 #pragma unroll 1
-                for (int q = 0; q < 3; ++q) {
-                    const int k = sub * 3 + q;
-                    const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
-                    ang = ang + edge_angle(s_rec[GT_VX + k] - xc, s_rec[GT_VY + k] - yc, s_rec[GT_VX + k2] - xc,
-                                           s_rec[GT_VY + k2] - yc);
+                    for (int q = 0; q < 3; ++q) {
+                        const int k = sub * 3 + q;
+                        const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
+                        ang = ang + edge_angle(s_rec[GT_VX + k] - xc, s_rec[GT_VY + k] - yc, s_rec[GT_VX + k2] - xc,
+                                               s_rec[GT_VY + k2] - yc);
+                    }
+                    ang = group_sum(ang, gm);
+                    inside = ang >= 350.0f;  // losses.py:588
                 }
-                ang = group_sum(ang, gm);
-                inside = ang >= 350.0f;  // losses.py:588
             }
-        }
-        if (inside) {
-            const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
-            float s = 0.0f;
+            if (inside) {
+                const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
+                float s = 0.0f;
 #pragma unroll 1
-            for (int q = 0; q < 3; ++q) s = s + ray_loss(s_rec[GT_RG + sub * 3 + q], rp[q], d);
-            s = group_sum(s, gm);
-            const float v = (s / 24.0f) / 2.0f;
-            const float eo1 = 1.0f + expf(-obj);
-            float neg;
-            if (p.nc <= 80) {
-                float prod = 1.0f;
-                int nsat = 0;
+                for (int q = 0; q < 3; ++q) s = s + ray_loss(s_rec[GT_RG + sub * 3 + q], rp[q], d);
+                s = group_sum(s, gm);
+                const float v = (s / 24.0f) / 2.0f;
+                const float eo1 = 1.0f + expf(-obj);
+                float neg;
+                if (p.nc <= 80) {
+                    float prod = 1.0f;
+                    int nsat = 0;
 #pragma unroll
-                for (int q = 0; q < 10; ++q)
-                    if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
-                prod = group_prod(prod, gm);
-                nsat = group_sum_i(nsat, gm);
-                neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(row + 27, p.nc, eo1, gm);
-            } else {
-                neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+                    for (int q = 0; q < 10; ++q)
+                        if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
+                    prod = group_prod(prod, gm);
+                    nsat = group_sum_i(nsat, gm);
+                    neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+                } else {
+                    neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+                }
+                cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
+                if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
+                // per-anchor argmin over its valid pairs (first GT index on ties): what conflict resolution needs
+                if (sub == 0)
+                    atomicMin(&p.best_key[(long long)b * p.A + a], ((unsigned long long)p24_ordered(cost) << 32) | (unsigned)g);
             }
-            cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
-            if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
-            // per-anchor argmin over its valid pairs (first GT index on ties): what conflict resolution needs
-            if (sub == 0)
-                atomicMin(&p.best_key[(long long)b * p.A + a], ((unsigned long long)p24_ordered(cost) << 32) | (unsigned)g);
+            if (sub == 0) p.wcostv[(long long)wslot * P24_VCAP + wi] = cost;
         }
-        if (sub == 0) p.wcostv[(long long)wslot * P24_VCAP + wi] = cost;
     }
+    TMARK(4, blockIdx.x, 1);
+    pdl_wait();  // late: k_dyn_k (the previous kernel) must be complete before k_select starts
+    TMARK(4, blockIdx.x, 2);
 }
 
 // -------------------------------------------------------------------------------------------
-// k_gt_match: per GT, from the exact values of k_pair_eval: dynamic k (top-10 bracket, exact paths when it is not
-// conclusive) and the k smallest costs -> claims
+// k_dyn_k: per GT, dynamic k = clamp(int(sum of the 10 largest pair values over the candidates), 1) from the exact seed
+// values of the anchor pass (top-10 bracket; exact filtered / brute-force paths when it is not conclusive)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MATCH_THREADS) k_gt_match(Params p) {
+__global__ void __launch_bounds__(MATCH_THREADS) k_dyn_k(Params p) {
     const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 #define MCTA (b * 20 + g)
     if (g < 20) TMARK(1, MCTA, 0);
-    pdl_wait();
+    // num_gt was written by k_gt_prep, which completed before k_anchor_pass let this kernel launch: rows beyond it
+    // leave at once (their dyn_k slot is not read by anyone before the next call rewrites it)
     const int n = p.num_gt[b];
     if (g >= n) {
         if (tid == 0) p.dyn_k[b * p.Lmax + g] = 0;
         return;
     }
+    pdl_wait();
+    pdl_trigger();  // k_window_eval does not depend on this kernel
     TMARK(1, MCTA, 1);
     __shared__ MatchShared S;
     const int wslot = b * p.Lmax + g;
     if (tid < GT_REC) S.rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
-    const int nwin = min(p.wcount[wslot], P24_VCAP);
-    if (tid < P24_VCAP) {
-        S.wanchor[tid] = tid < nwin ? p.wlist[(long long)wslot * P24_VCAP + tid] : 0x7fffffff;
-        S.wcost[tid] = tid < nwin ? p.wcostv[(long long)wslot * P24_VCAP + tid] : P24_POS_INF;
-    }
     int cnt = 0;
     for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) {
         const int c = p.ccount[(long long)b * p.tiles + tl];
@@ -1050,7 +1088,6 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_gt_match(Params p) {
     __syncthreads();
     cnt = warp_sum_i(cnt);
     if (lane == 0 && cnt) atomicAdd(&S.cnt, cnt);
-    if (tid == 0) p.wcount[wslot] = 0;  // leave the list empty for the next call
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     __syncthreads();
     TMARK(1, MCTA, 2);
@@ -1139,26 +1176,6 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_gt_match(Params p) {
     k = min(k, ncand);  // torch.topk would raise beyond the candidate count; clamp instead
     if (tid == 0) p.dyn_k[wslot] = k;
     TMARK(1, MCTA, 5);
-
-    // ---- the k smallest costs of the valid pairs -> claims (rank counting, one thread per window anchor) ------
-    {
-        const bool mine = tid < nwin && S.wcost[tid] < P24_POS_INF;
-        const int nv = __syncthreads_count(mine);
-        const int take = min(k, nv);
-        if (mine) {
-            const float ci = S.wcost[tid];
-            const int ai = S.wanchor[tid];
-            int before = 0;
-            for (int j = 0; j < nwin; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
-            if (before < take) claim_anchor(p, b, ai, g);
-        }
-        TMARK(1, MCTA, 6);
-        if (k > nv) {
-            __syncthreads();
-            spill_claims(p, S, b, g, nwin, k - nv);
-        }
-    }
-    TMARK(1, MCTA, 7);
 #ifdef P24_TIMING
     if (tid == 0) {
         g_tstamp[1][MCTA][8] = S.slow;
@@ -1167,6 +1184,46 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_gt_match(Params p) {
         g_tstamp[1][MCTA][11] = S.overflow;
     }
 #endif
+}
+
+// -------------------------------------------------------------------------------------------
+// k_select: per GT, the dyn_k smallest costs of its valid pairs -> claims (rank counting, one thread per window
+// anchor); spill into the penalised regime when the GT has fewer valid anchors than dyn_k
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MATCH_THREADS) k_select(Params p) {
+    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (g < 20) TMARK(5, b * 20 + g, 0);
+    const int n = p.num_gt[b];
+    if (g >= n) return;
+    pdl_wait();
+    TMARK(5, b * 20 + g, 1);
+    __shared__ MatchShared S;
+    const int wslot = b * p.Lmax + g;
+    const int nwin = min(p.wcount[wslot], P24_VCAP);
+    const int k = p.dyn_k[wslot];
+    if (tid < P24_VCAP) {
+        S.wanchor[tid] = tid < nwin ? p.wlist[(long long)wslot * P24_VCAP + tid] : 0x7fffffff;
+        S.wcost[tid] = tid < nwin ? p.wcostv[(long long)wslot * P24_VCAP + tid] : P24_POS_INF;
+    }
+    __syncthreads();
+    if (tid == 0) p.wcount[wslot] = 0;  // leave the list empty for the next call
+    const bool mine = tid < nwin && S.wcost[tid] < P24_POS_INF;
+    const int nv = __syncthreads_count(mine);
+    const int take = min(k, nv);
+    if (mine) {
+        const float ci = S.wcost[tid];
+        const int ai = S.wanchor[tid];
+        int before = 0;
+        for (int j = 0; j < nwin; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
+        if (before < take) claim_anchor(p, b, ai, g);
+    }
+    if (k > nv) {
+        if (tid < GT_REC) S.rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
+        for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) S.ccount[tl] = p.ccount[(long long)b * p.tiles + tl];
+        __syncthreads();
+        spill_claims(p, S, b, g, nwin, k - nv);
+    }
+    TMARK(5, b * 20 + g, 2);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1328,9 +1385,9 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     if (tid == 0) {
         // two-level completion count (image, then batch): few atomics per address
         bool last = false;
-        const unsigned done = atomicAdd(&p.ticket[1 + b], 1u);
+        const unsigned done = atomicAdd(&p.ticket[2 + b], 1u);
         if (done == (unsigned)gridDim.x - 1u) {
-            p.ticket[1 + b] = 0u;  // ready for the next call
+            p.ticket[2 + b] = 0u;  // ready for the next call
             __threadfence();
             const unsigned done2 = atomicAdd(&p.ticket[0], 1u);
             last = (done2 == (unsigned)gridDim.y - 1u);
@@ -1366,7 +1423,10 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     if (tid == 32) s_sums[24] = (float)((double)s_sums[24] + objsum);
     __syncthreads();
     if (tid < 28) p.sums28[tid] = s_sums[tid];
-    if (tid == 0) *p.ticket = 0u;  // ready for the next call
+    if (tid == 0) {
+        p.ticket[0] = 0u;  // ready for the next call
+        p.ticket[1] = 0u;
+    }
     if (p.state26 && warp == 0) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 6);
 }
@@ -1376,10 +1436,10 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
     finalize_warp(sums28, state26, result54, weights_n27);
 }
 
-size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float); }
+size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC_HEAD * sizeof(float); }
 
 // optional per-stage timing (profiling aid for bench.py; process-global, not thread-safe)
-#define N_STAGES 5
+#define N_STAGES 6
 bool g_prof_on = false;
 cudaEvent_t g_prof_ev[N_STAGES + 1];
 bool g_prof_have = false;
@@ -1479,18 +1539,32 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     e = launch(k_anchor_pass, dim3(p.tiles, B), dim3(P24_THREADS), dyn, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     prof_mark(2, st);
-    e = launch(k_pair_eval, dim3(Lmax * EVAL_SPLIT, B), dim3(P24_THREADS), 0, st, pdl, p);
+    e = launch(k_dyn_k, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     prof_mark(3, st);
-    e = launch(k_gt_match, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
-    if (e != cudaSuccess) return (int)e;
+    {
+        static int n_sm = 0;
+        if (!n_sm) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            if (n_sm <= 0) n_sm = 148;
+        }
+        const int items = B * Lmax * EVAL_SPLIT;
+        const int gx = items < 4 * n_sm ? items : 4 * n_sm;  // persistent: one wave (4 CTAs of 256 threads per SM)
+        e = launch(k_window_eval, dim3(gx), dim3(P24_THREADS), 0, st, pdl, p);
+        if (e != cudaSuccess) return (int)e;
+    }
     prof_mark(4, st);
+    e = launch(k_select, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
+    if (e != cudaSuccess) return (int)e;
+    prof_mark(5, st);
     {
         const int gx = (P24_TOPK * Lmax + P24_WARPS - 1) / P24_WARPS;
         e = launch(k_resolve_loss, dim3(gx < RESOLVE_GRID_X ? gx : RESOLVE_GRID_X, B), dim3(P24_THREADS), 0, st, pdl, p);
     }
     if (e != cudaSuccess) return (int)e;
-    prof_mark(5, st);
+    prof_mark(6, st);
     return (int)cudaGetLastError();
 }
 
@@ -1513,12 +1587,12 @@ extern "C" int p24_profile_enable(int on) {
     return 0;
 }
 
-extern "C" int p24_profile_read(float* h_ms5) {
-    if (!g_prof_have || !h_ms5) return P24_E_BADARG;
+extern "C" int p24_profile_read(float* h_ms6) {
+    if (!g_prof_have || !h_ms6) return P24_E_BADARG;
     cudaError_t e = cudaEventSynchronize(g_prof_ev[N_STAGES]);
     if (e != cudaSuccess) return (int)e;
     for (int i = 0; i < N_STAGES; ++i) {
-        e = cudaEventElapsedTime(&h_ms5[i], g_prof_ev[i], g_prof_ev[i + 1]);
+        e = cudaEventElapsedTime(&h_ms6[i], g_prof_ev[i], g_prof_ev[i + 1]);
         if (e != cudaSuccess) return (int)e;
     }
     return 0;
@@ -1526,6 +1600,6 @@ extern "C" int p24_profile_read(float* h_ms5) {
 
 #ifdef P24_TIMING
 extern "C" int p24_debug_read_timers(unsigned long long* h_out) {
-    return (int)cudaMemcpyFromSymbol(h_out, g_tstamp, sizeof(unsigned long long) * 3 * 4096 * 20);
+    return (int)cudaMemcpyFromSymbol(h_out, g_tstamp, sizeof(unsigned long long) * 6 * 4096 * 20);
 }
 #endif

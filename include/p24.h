@@ -145,11 +145,11 @@ int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_str
                     int32_t* cand_count, int32_t* det_count, float* det_rows, int32_t* keep_idx, float* rect_debug,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its five
- * kernels (gt_prep, anchor_pass, pair_eval, gt_match, resolve_loss) on the launching stream; p24_profile_read waits
- * for the last call and returns the five durations in milliseconds into a HOST array.  Process-global. */
+/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its six
+ * kernels (gt_prep, anchor_pass, dyn_k, window_eval, select, resolve_loss) on the launching stream; p24_profile_read waits
+ * for the last call and returns the six durations in milliseconds into a HOST array.  Process-global. */
 int p24_profile_enable(int on);
-int p24_profile_read(float* h_ms5);
+int p24_profile_read(float* h_ms6);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ lib.p24_debug_read_timers.argtypes = [ctypes.c_void_p]
 assert lib.p24_debug_read_timers(buf.ctypes.data) == 0
 t = buf.astype(np.int64)
 names = {0: ("k_anchor_pass", 660, ["start", "pdl", "rows+recs", "pass1/2 gen", "items", "end"]),
-         1: ("k_gt_match", 400, ["start", "pdl", "load", "-", "bracket", "dyn_k", "select", "spill/end"]),
+         1: ("k_dyn_k", 400, ["start", "pdl", "load", "-", "bracket", "dyn_k"]),
          2: ("k_resolve_loss", 320, ["start", "pdl", "-", "-", "entries", "partials", "last"])}
 base = t[0, :660, 0].min()
 for k, (nm, ncta, ph) in names.items():
@@ -59,6 +59,7 @@ for k, (nm, ncta, ph) in names.items():
         for ci in np.nonzero(slow != 0)[0][:6]:
             r = full[ci]
             print("      slow CTA", int(ci), "dyn_k phases us: tau", (r[12] - r[4]) / 1e3, "scan", (r[13] - r[12]) / 1e3,
-                  "ub", (r[14] - r[13]) / 1e3, "exact", (r[15] - r[14]) / 1e3, "select", (r[5] - r[15]) / 1e3)
-        tot = (tt[ok, 7] - tt[ok, 1]) / 1e3
+                  "ub", (r[14] - r[13]) / 1e3, "exact", (r[15] - r[14]) / 1e3, "select", (r[5] - r[15]) / 1e3,
+                  "| ends at", (r[5] - base) / 1e3)
+        tot = (tt[ok, 5] - tt[ok, 1]) / 1e3
         print(f"   CTA total mean {tot.mean():.2f} us max {tot.max():.2f} us; slow ones: {np.round(tot[slow[ok] != 0], 1).tolist()[:20]}")
