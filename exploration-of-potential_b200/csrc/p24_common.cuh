@@ -9,6 +9,7 @@
 #include "p24_math.cuh"
 
 #define P24_THREADS 256
+#define P24_SEEDS 2  // seeds per (GT, tile)
 #define P24_WARPS (P24_THREADS / 32)
 
 // ---- per-GT record (floats), built once per image by the anchor pass ---------------------------
@@ -35,8 +36,8 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 struct P24Workspace {
     size_t gt_rec;      // [B, Lmax, GT_REC] float
     size_t clist;       // [B, tiles, 256] float4  candidate anchors of a tile, compacted: (pred cx, pred cy, rpmax, anchor idx bits)
-    size_t sseed;       // [B, Lmax, 2 * tiles] int     per (GT, tile): the two candidates with the smallest seed proxy (-1: none)
-    size_t sval;        // [B, Lmax, 2 * tiles] float   their exact pair values (k_pair_eval)
+    size_t sval;        // [B, Lmax, P24_SEEDS * tiles] float   exact pair values of the tile's best candidates by the seed proxy
+                        //                                       (-inf: none), written by the anchor pass
     size_t wcostv;      // [B, Lmax, VCAP] float        SimOTA cost of the GT's centre-window anchors (+inf: not in the polygon)
     size_t tbox;        // [B, tiles, 8] float          bounding box of a tile's candidate centres (xmin, xmax, ymin, ymax), max rpmax
     size_t ccount;      // [B, tiles] int          candidates per tile
@@ -71,8 +72,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
     w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
     w.ccount = off;     off = p24_align(off + NB * sizeof(int));
-    w.sseed = off;      off = p24_align(off + BL * 2 * (size_t)p24_tiles(A) * sizeof(int));
-    w.sval = off;       off = p24_align(off + BL * 2 * (size_t)p24_tiles(A) * sizeof(float));
+    w.sval = off;       off = p24_align(off + BL * P24_SEEDS * (size_t)p24_tiles(A) * sizeof(float));
     w.wcostv = off;     off = p24_align(off + BL * P24_VCAP * sizeof(float));
     w.tbox = off;       off = p24_align(off + NB * 8 * sizeof(float));
     w.wlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));

@@ -51,7 +51,6 @@ struct Params {
     // workspace
     float* gt_rec;
     float4* clist;
-    int* sseed;
     float* sval;
     float* wcostv;
     float* tbox;
@@ -259,6 +258,39 @@ __device__ __forceinline__ float group_pair_value(const float* __restrict__ rec,
     return (s / 24.0f) / 2.0f;
 }
 
+// A certified LOWER bound of the pair value by an 8-lane group, for seeds: when every ray is in the "apart" branch
+// (d >= rg + rp, the same fp32 comparison as the reference) the value has the closed form
+// (1/48) sum_k (2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2), evaluated here in fast arithmetic; it differs from the
+// reference-order fp32 value by < 3e-6, so value - 1e-5 is a valid lower bound.  Other pairs are evaluated exactly.
+__device__ __forceinline__ float group_pair_value_lb(const float* __restrict__ rec, const float* __restrict__ row, unsigned m) {
+    const int sub = threadIdx.x & 7;
+    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
+    float rg[3], rp[3];
+    bool apart = true;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        rg[q] = rec[GT_RG + sub * 3 + q];
+        rp[q] = row[2 + sub * 3 + q];
+        apart = apart && (d >= rg[q] + rp[q]);
+    }
+    const unsigned all = __ballot_sync(m, apart);
+    if ((all & m) == m) {
+        float s = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float t = (rg[q] + rp[q]) + d;
+            s += 2.0f - __fdividef(4.0f * fmaf(rg[q], rg[q], rp[q] * rp[q]), t * t);
+        }
+        s = group_sum(s, m);
+        return s * (1.0f / 48.0f) - 1e-5f;
+    }
+    float s = 0.0f;
+#pragma unroll 1
+    for (int q = 0; q < 3; ++q) s = s + ray_loss(rg[q], rp[q], d);
+    s = group_sum(s, m);
+    return (s / 24.0f) / 2.0f;
+}
+
 __device__ __forceinline__ int gt_class(const float* rec, int nc) {
     const int c = (int)rec[GT_CLS];
     return min(max(c, 0), nc - 1);
@@ -405,27 +437,45 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
     bool cheap = false;
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool no_prune = (p.flags & P24_F_NO_PRUNE) != 0;
-    unsigned near[4] = {0u, 0u, 0u, 0u};  // GTs 0..127; beyond that every GT counts as near (see below)
+    unsigned near[4] = {0u, 0u, 0u, 0u};  // GTs 0..127; beyond that every GT is tested in place (see below)
     {
         const float r25 = 2.5f * st + 1e-3f * st;  // conservative pre-filter radius of the window test
-        for (int g = 0; g < n; ++g) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            unsigned m = 0u;
+            const int ge = min(32, n - w * 32);
+            for (int j = 0; j < ge; ++j) {
+                const int g = w * 32 + j;
+                const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
+                const float dx = h.x - xc, dy = h.y - yc;
+                const float d2 = fmaf(dx, dx, dy * dy);
+                cheap |= d2 < h.z;
+                m |= (d2 <= h.w ? 1u : 0u) << j;
+                if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && active && p24_in_centre(h.x, h.y, xc, yc, st)) {
+                    cheap = true;
+                    // (anchor, GT) goes to the GT's centre-window list; staged in shared memory so that the global
+                    // atomics of a tile are issued together instead of one round trip at a time
+                    const int ws = atomicAdd(&s_nwin, 1);
+                    if (ws < WIN_CAP) {
+                        s_win[ws] = (unsigned)tid | ((unsigned)g << 8);
+                    } else {
+                        const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
+                        if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
+                        else atomicOr(p.err_flag, 1);
+                    }
+                }
+            }
+            near[w] = no_prune ? (ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u)) : m;
+        }
+        for (int g = 128; g < n; ++g) {  // more than 128 GTs: windows and discs of the rest
             const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
-            const float d2 = fmaf(dx, dx, dy * dy);
-            cheap |= d2 < h.z;
-            if (g < 128 && (d2 <= h.w || no_prune)) near[g >> 5] |= 1u << (g & 31);
+            cheap |= fmaf(dx, dx, dy * dy) < h.z;
             if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && active && p24_in_centre(h.x, h.y, xc, yc, st)) {
                 cheap = true;
-                // (anchor, GT) goes to the GT's centre-window list; staged in shared memory so that the global
-                // atomics of a tile are issued together instead of one round trip at a time
-                const int ws = atomicAdd(&s_nwin, 1);
-                if (ws < WIN_CAP) {
-                    s_win[ws] = (unsigned)tid | ((unsigned)g << 8);
-                } else {
-                    const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
-                    if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
-                    else atomicOr(p.err_flag, 1);
-                }
+                const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
+                if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
+                else atomicOr(p.err_flag, 1);
             }
         }
     }
@@ -571,47 +621,55 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
     const long long blk = (long long)b * p.tiles + tile;
     // the tile's two best seeds per GT (merge of the 8 warps), evaluated exactly right away (8-lane groups): what
     // k_dyn_k brackets the top-10 sum with.  128 GTs at a time.
-    __shared__ int s_seedA[2 * 128];
+    __shared__ int s_seedA[P24_SEEDS * 128];
     for (int g0 = 0; g0 < n; g0 += 128) {
         const int gn = min(128, n - g0);
         if (tid < gn) {
             const int g = g0 + tid;
-            float q1 = P24_POS_INF, q2 = P24_POS_INF;
-            int a1 = -1, a2 = -1;
+            float qb[P24_SEEDS];
+            int ab[P24_SEEDS];
+#pragma unroll
+            for (int u = 0; u < P24_SEEDS; ++u) {
+                qb[u] = P24_POS_INF;
+                ab[u] = -1;
+            }
             if (g < 181) {
 #pragma unroll
                 for (int w = 0; w < P24_WARPS; ++w) {
                     const float* e = &s_row[w][5][0] + g * 4;
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        const float q = e[2 * u];
-                        const int aq = __float_as_int(e[2 * u + 1]);
-                        if (q < q1) {
-                            q2 = q1;
-                            a2 = a1;
-                            q1 = q;
-                            a1 = aq;
-                        } else if (q < q2) {
-                            q2 = q;
-                            a2 = aq;
+                        float q = e[2 * u];
+                        int aq = __float_as_int(e[2 * u + 1]);
+#pragma unroll
+                        for (int r = 0; r < P24_SEEDS; ++r) {  // sorted insert
+                            if (q < qb[r]) {
+                                const float tq = qb[r];
+                                const int ta = ab[r];
+                                qb[r] = q;
+                                ab[r] = aq;
+                                q = tq;
+                                aq = ta;
+                            }
                         }
                     }
                 }
             }
-            s_seedA[2 * tid] = a1;
-            s_seedA[2 * tid + 1] = a2;
+#pragma unroll
+            for (int u = 0; u < P24_SEEDS; ++u) s_seedA[P24_SEEDS * tid + u] = ab[u];
         }
         __syncthreads();
         {
             const unsigned gm = group_mask();
             const int grp = tid >> 3, sub = tid & 7;
-            for (int t = grp; t < 2 * gn; t += P24_THREADS / 8) {
+            for (int t = grp; t < P24_SEEDS * gn; t += P24_THREADS / 8) {
                 const int sa = s_seedA[t];
-                const int g = g0 + (t >> 1);
+                const int g = g0 + t / P24_SEEDS;
                 float v = P24_NEG_INF;
                 if (sa >= 0)
-                    v = group_pair_value(p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC, img + (long long)sa * p.row_stride, gm);
-                if (sub == 0) p.sval[((long long)b * p.Lmax + g) * 2 * p.tiles + 2 * tile + (t & 1)] = v;
+                    v = group_pair_value_lb(p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC, img + (long long)sa * p.row_stride, gm);
+                if (sub == 0)
+                    p.sval[((long long)b * p.Lmax + g) * P24_SEEDS * p.tiles + P24_SEEDS * tile + (t % P24_SEEDS)] = v;
             }
         }
         __syncthreads();
@@ -832,11 +890,11 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
     {
         const int npass = S.k;
         const int nslot = npass * P24_THREADS;
-        for (int base = tid; base < nslot; base += 4 * MATCH_THREADS) {
-            float4 q[4];
-            bool ok[4];
+        for (int base = tid; base < nslot; base += 8 * MATCH_THREADS) {
+            float4 q[8];
+            bool ok[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int i0 = base + u * MATCH_THREADS;
                 ok[u] = false;
                 if (i0 < nslot) {
@@ -846,7 +904,7 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 if (!ok[u]) continue;
                 const float dx = gcx - q[u].x, dy = gcy - q[u].y;
                 const float t = q[u].z + sqrtf(fmaf(dx, dx, dy * dy));
@@ -886,7 +944,16 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
     __syncthreads();
     TMARK(1, b * 20 + (int)blockIdx.x, 15);
     if (S.nev < P24_TOPK) return NAN;
-    if (warp == 0) warp_select_top(S.ev, S.nev, P24_TOPK, S.top);
+    {
+        // rank counting, one thread per kept value: the 10 largest land in S.top in descending order
+        const int nev = S.nev;
+        for (int i = tid; i < nev; i += MATCH_THREADS) {
+            const float vi = S.ev[i];
+            int rank = 0;
+            for (int j = 0; j < nev; ++j) rank += kv_gt(S.ev[j], j, vi, i) ? 1 : 0;
+            if (rank < P24_TOPK) S.top[rank] = vi;
+        }
+    }
     __syncthreads();
     float ksum = 0.0f;
     for (int i = 0; i < P24_TOPK; ++i) ksum = ksum + (S.top[i] == P24_POS_INF ? NAN : S.top[i]);
@@ -1110,14 +1177,16 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_dyn_k(Params p) {
         }
         tm = warp_max(tm);
         // the 10 largest seed values, summed in descending order (like the reference sums torch.topk's output)
-        const int nseed = 2 * p.tiles;
+        const int nseed = P24_SEEDS * p.tiles;
         const float* sv = p.sval + (long long)wslot * nseed;
-        float v0 = P24_NEG_INF, v1 = P24_NEG_INF, v2 = P24_NEG_INF, v3 = P24_NEG_INF;  // up to 128 seeds: 4 per lane
-        if (lane < nseed) v0 = sv[lane];
-        if (lane + 32 < nseed) v1 = sv[lane + 32];
-        if (lane + 64 < nseed) v2 = sv[lane + 64];
-        if (lane + 96 < nseed) v3 = sv[lane + 96];
-        for (int i = lane + 128; i < nseed; i += 32) v3 = fmaxf(v3, sv[i]);  // more than 128 seeds: keep the best of the rest
+        float v0 = P24_NEG_INF, v1 = P24_NEG_INF, v2 = P24_NEG_INF, v3 = P24_NEG_INF;  // the lane's 4 best seeds
+        for (int i = lane; i < nseed; i += 32) {
+            float v = sv[i];
+            if (v > v0) { const float t0 = v0; v0 = v; v = t0; }
+            if (v > v1) { const float t1 = v1; v1 = v; v = t1; }
+            if (v > v2) { const float t2 = v2; v2 = v; v = t2; }
+            if (v > v3) v3 = v;
+        }
         float T = P24_NEG_INF, L = 0.0f;
         int got = 0;
         if (kc == P24_TOPK) {
@@ -1505,7 +1574,6 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.state26 = state26; p.result54 = result54; p.weights27 = weights_n27;
     p.gt_rec = (float*)(ws + L.gt_rec);
     p.clist = (float4*)(ws + L.clist);
-    p.sseed = (int*)(ws + L.sseed);
     p.sval = (float*)(ws + L.sval);
     p.wcostv = (float*)(ws + L.wcostv);
     p.tbox = (float*)(ws + L.tbox);

@@ -28,15 +28,18 @@ for i in range(10):
     o, l = sets[(i % 5) if only is None else only]
     lf.forward_async((g[0], g[1], g[2], o, []), l)
 torch.cuda.synchronize()
-buf = np.zeros((3, 4096, 20), dtype=np.uint64)
+buf = np.zeros((6, 4096, 20), dtype=np.uint64)
 lib.p24_debug_read_timers.argtypes = [ctypes.c_void_p]
 assert lib.p24_debug_read_timers(buf.ctypes.data) == 0
 t = buf.astype(np.int64)
 names = {0: ("k_anchor_pass", 660, ["start", "pdl", "rows+recs", "pass1/2 gen", "items", "end"]),
+         3: ("-", 0, []), 4: ("-", 0, []), 5: ("-", 0, []),
          1: ("k_dyn_k", 400, ["start", "pdl", "load", "-", "bracket", "dyn_k"]),
          2: ("k_resolve_loss", 320, ["start", "pdl", "-", "-", "entries", "partials", "last"])}
 base = t[0, :660, 0].min()
 for k, (nm, ncta, ph) in names.items():
+    if not ncta:
+        continue
     tt = t[k, :ncta, :len(ph)]
     ok = tt[:, len(ph) - 2] > 0
     print(f"== {nm}: first start {(tt[ok, 0].min() - base) / 1e3:.1f} us, last end {(tt[ok].max() - base) / 1e3:.1f} us after chain start")
