@@ -10,6 +10,7 @@
 
 #define P24_THREADS 256
 #define P24_SEEDS 2  // seeds per (GT, tile)
+#define P24_MAX_SPLIT 4  // batch slices processed as concurrent kernel chains
 #define P24_WARPS (P24_THREADS / 32)
 
 // ---- per-GT record (floats), built once per image by the anchor pass ---------------------------
@@ -50,8 +51,8 @@ struct P24Workspace {
     size_t claimed;     // [B, 10 * Lmax] int   anchors claimed by at least one GT (arrival order)
     size_t nclaimed;    // [B] int
     size_t acc_fix;     // [B, 28] int64        fixed-point loss sums of the image (zero between calls)
-    size_t ticket;      // [2 + B] unsigned: batch counter, work-queue head of k_window_eval, one counter per image
-                        //                   (zero between calls)
+    size_t ticket;      // [1 + P24_MAX_SPLIT + B] unsigned: batch counter, work-queue heads of k_window_eval (one per batch
+                        //                   slice), one counter per image (zero between calls)
     size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
     size_t total;
 };
@@ -66,7 +67,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
     w.wcount = off;     off = p24_align(off + BL * sizeof(int));
-    w.ticket = off;     off = p24_align(off + (size_t)(2 + B) * sizeof(unsigned));
+    w.ticket = off;     off = p24_align(off + (size_t)(1 + P24_MAX_SPLIT + B) * sizeof(unsigned));
     w.acc_fix = off;    off = p24_align(off + (size_t)B * 28 * sizeof(long long));
     w.err_flag = off;   off = p24_align(off + sizeof(int));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));

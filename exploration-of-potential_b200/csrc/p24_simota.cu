@@ -68,6 +68,7 @@ struct Params {
     int* err_flag;
     unsigned flags;
     int tiles;
+    int b0, nb, slice;  // this launch covers images [b0, b0 + nb) (batch slice `slice`)
 };
 
 // Debug-only phase timers (-DP24_TIMING): thread 0 of every CTA stores %globaltimer at phase boundaries.
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(Params p) {
     TMARK(3, blockIdx.x, 0);
     pdl_wait();
     TMARK(3, blockIdx.x, 1);
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = p.b0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* lab = p.labels + (long long)b * p.lab_img_stride;
     // nlabel = (labels.sum(2) > 0).sum(1)   losses.py:190 ; the first n rows are the GTs (losses.py:219-220)
     int local = 0;
@@ -362,7 +363,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
     extern __shared__ float4 s_dyn4[];
     float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC_HEAD]: everything but the ray lengths
-    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int b = p.b0 + blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int a = tile * P24_THREADS + tid;
     const bool active = a < p.A;
@@ -1036,17 +1037,17 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_window_eval(Params p) {
     __shared__ float s_rec[GT_REC];
     const unsigned gm = group_mask();
     const int grp = tid >> 3, sub = tid & 7;
-    const int nitem = p.B * p.Lmax * EVAL_SPLIT;
+    const int nitem = p.nb * p.Lmax * EVAL_SPLIT;
     __shared__ int s_item;
     for (;;) {
         // dynamic work queue: (GT, part) items are very uneven (rows beyond num_gt are empty)
         __syncthreads();
-        if (tid == 0) s_item = (int)atomicAdd(&p.ticket[1], 1u);
+        if (tid == 0) s_item = (int)atomicAdd(&p.ticket[1 + p.slice], 1u);
         __syncthreads();
         const int item = s_item;
         if (item >= nitem) break;
         const int part = item % EVAL_SPLIT;
-        const int wslot = item / EVAL_SPLIT;  // b * Lmax + g
+        const int wslot = p.b0 * p.Lmax + item / EVAL_SPLIT;  // b * Lmax + g
         const int b = wslot / p.Lmax, g = wslot - b * p.Lmax;
         if (g >= p.num_gt[b]) continue;
         const int nwin = min(p.wcount[wslot], P24_VCAP);
@@ -1128,7 +1129,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_window_eval(Params p) {
 // values of the anchor pass (top-10 bracket; exact filtered / brute-force paths when it is not conclusive)
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MATCH_THREADS) k_dyn_k(Params p) {
-    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int g = blockIdx.x, b = p.b0 + blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 #define MCTA (b * 20 + g)
     if (g < 20) TMARK(1, MCTA, 0);
@@ -1260,7 +1261,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_dyn_k(Params p) {
 // anchor); spill into the penalised regime when the GT has fewer valid anchors than dyn_k
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MATCH_THREADS) k_select(Params p) {
-    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int g = blockIdx.x, b = p.b0 + blockIdx.y, tid = threadIdx.x;
     if (g < 20) TMARK(5, b * 20 + g, 0);
     const int n = p.num_gt[b];
     if (g >= n) return;
@@ -1385,7 +1386,7 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 0);
     pdl_wait();
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 1);
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const int b = p.b0 + blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int n = p.num_gt[b];
     __shared__ long long s_acc[P24_WARPS][26];
@@ -1454,12 +1455,12 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     if (tid == 0) {
         // two-level completion count (image, then batch): few atomics per address
         bool last = false;
-        const unsigned done = atomicAdd(&p.ticket[2 + b], 1u);
+        const unsigned done = atomicAdd(&p.ticket[1 + P24_MAX_SPLIT + b], 1u);
         if (done == (unsigned)gridDim.x - 1u) {
-            p.ticket[2 + b] = 0u;  // ready for the next call
+            p.ticket[1 + P24_MAX_SPLIT + b] = 0u;  // ready for the next call
             __threadfence();
             const unsigned done2 = atomicAdd(&p.ticket[0], 1u);
-            last = (done2 == (unsigned)gridDim.y - 1u);
+            last = (done2 == (unsigned)p.B - 1u);
         }
         s_last = last;
     }
@@ -1494,7 +1495,7 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     if (tid < 28) p.sums28[tid] = s_sums[tid];
     if (tid == 0) {
         p.ticket[0] = 0u;  // ready for the next call
-        p.ticket[1] = 0u;
+        for (int q = 0; q < P24_MAX_SPLIT; ++q) p.ticket[1 + q] = 0u;
     }
     if (p.state26 && warp == 0) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 6);
@@ -1599,40 +1600,79 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
         attr_done = true;
     }
     const bool pdl = !(flags & P24_F_NO_PDL) && !g_prof_on;
-    cudaError_t e;
-    prof_mark(0, st);
-    e = launch(k_gt_prep, dim3(B), dim3(PREP_THREADS), 0, st, pdl, p);
-    if (e != cudaSuccess) return (int)e;
-    prof_mark(1, st);
-    e = launch(k_anchor_pass, dim3(p.tiles, B), dim3(P24_THREADS), dyn, st, pdl, p);
-    if (e != cudaSuccess) return (int)e;
-    prof_mark(2, st);
-    e = launch(k_dyn_k, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
-    if (e != cudaSuccess) return (int)e;
-    prof_mark(3, st);
-    {
-        static int n_sm = 0;
-        if (!n_sm) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            if (n_sm <= 0) n_sm = 148;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    // The batch is cut into slices whose kernel chains run concurrently (the caller's stream + internal streams, forked and
+    // joined with events): the latency-bound stages of one slice overlap the throughput-bound stages of another.  The
+    // last CTA of the last slice to finish reduces the whole batch.
+    // Measured on B200 at B = 20: the slices advance in lockstep, so nothing complementary overlaps and the extra launches
+    // only cost host time: off by default, opt-in with P24_F_SPLIT.
+    int nsplit = (flags & P24_F_SPLIT) && !g_prof_on ? (B >= 16 ? 4 : (B >= 4 ? 2 : 1)) : 1;
+    if (nsplit > P24_MAX_SPLIT) nsplit = P24_MAX_SPLIT;
+    static cudaStream_t xs[P24_MAX_SPLIT] = {nullptr, nullptr, nullptr, nullptr};
+    static cudaEvent_t ev_fork = nullptr, ev_join[P24_MAX_SPLIT] = {nullptr, nullptr, nullptr, nullptr};
+    if (nsplit > 1 && !ev_fork) {
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+        for (int q = 1; q < P24_MAX_SPLIT; ++q) {
+            cudaStreamCreateWithFlags(&xs[q], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming);
         }
-        const int items = B * Lmax * EVAL_SPLIT;
-        const int gx = items < 4 * n_sm ? items : 4 * n_sm;  // persistent: one wave (4 CTAs of 256 threads per SM)
-        e = launch(k_window_eval, dim3(gx), dim3(P24_THREADS), 0, st, pdl, p);
+    }
+    cudaError_t e = cudaSuccess;
+    if (nsplit > 1) {
+        e = cudaEventRecord(ev_fork, st);
         if (e != cudaSuccess) return (int)e;
     }
-    prof_mark(4, st);
-    e = launch(k_select, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
-    if (e != cudaSuccess) return (int)e;
-    prof_mark(5, st);
-    {
-        const int gx = (P24_TOPK * Lmax + P24_WARPS - 1) / P24_WARPS;
-        e = launch(k_resolve_loss, dim3(gx < RESOLVE_GRID_X ? gx : RESOLVE_GRID_X, B), dim3(P24_THREADS), 0, st, pdl, p);
+    for (int q = 0; q < nsplit; ++q) {
+        cudaStream_t sq = q == 0 ? st : xs[q];
+        if (q > 0) {
+            e = cudaStreamWaitEvent(sq, ev_fork, 0);
+            if (e != cudaSuccess) return (int)e;
+        }
+        p.slice = q;
+        p.b0 = (int)((long long)B * q / nsplit);
+        p.nb = (int)((long long)B * (q + 1) / nsplit) - p.b0;
+        if (p.nb <= 0) continue;
+        prof_mark(0, sq);
+        e = launch(k_gt_prep, dim3(p.nb), dim3(PREP_THREADS), 0, sq, pdl, p);
+        if (e != cudaSuccess) return (int)e;
+        prof_mark(1, sq);
+        e = launch(k_anchor_pass, dim3(p.tiles, p.nb), dim3(P24_THREADS), dyn, sq, pdl, p);
+        if (e != cudaSuccess) return (int)e;
+        prof_mark(2, sq);
+        e = launch(k_dyn_k, dim3(Lmax, p.nb), dim3(MATCH_THREADS), 0, sq, pdl, p);
+        if (e != cudaSuccess) return (int)e;
+        prof_mark(3, sq);
+        {
+            const int items = p.nb * Lmax * EVAL_SPLIT;
+            const int cap = (4 * n_sm + nsplit - 1) / nsplit;  // persistent: the slices together fill one wave
+            e = launch(k_window_eval, dim3(items < cap ? items : cap), dim3(P24_THREADS), 0, sq, pdl, p);
+            if (e != cudaSuccess) return (int)e;
+        }
+        prof_mark(4, sq);
+        e = launch(k_select, dim3(Lmax, p.nb), dim3(MATCH_THREADS), 0, sq, pdl, p);
+        if (e != cudaSuccess) return (int)e;
+        prof_mark(5, sq);
+        {
+            const int gx = (P24_TOPK * Lmax + P24_WARPS - 1) / P24_WARPS;
+            e = launch(k_resolve_loss, dim3(gx < RESOLVE_GRID_X ? gx : RESOLVE_GRID_X, p.nb), dim3(P24_THREADS), 0, sq, pdl, p);
+            if (e != cudaSuccess) return (int)e;
+        }
+        prof_mark(6, sq);
+        if (q > 0) {
+            e = cudaEventRecord(ev_join[q], sq);
+            if (e != cudaSuccess) return (int)e;
+        }
     }
-    if (e != cudaSuccess) return (int)e;
-    prof_mark(6, st);
+    for (int q = 1; q < nsplit; ++q) {
+        e = cudaStreamWaitEvent(st, ev_join[q], 0);
+        if (e != cudaSuccess) return (int)e;
+    }
     return (int)cudaGetLastError();
 }
 

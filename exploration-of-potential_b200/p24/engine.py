@@ -15,6 +15,8 @@ from . import lib as _lib
 F_NO_PRUNE = 1   # evaluate every polygon angle sum exactly (self-check of the geometric pruning)
 F_NO_FILTER = 2  # evaluate every pair value exactly (self-check of the top-10 bound filter)
 F_ALL_ROWS = 4   # every label row is a GT (per-image API)
+F_NO_PDL = 8     # plain stream-ordered launches
+F_SPLIT = 16     # concurrent batch slices on internal streams (opt-in)
 
 
 @dataclass

@@ -39,6 +39,7 @@ extern "C" {
 /* p24_assign_batch flags */
 #define P24_F_NO_PRUNE 1u      /* evaluate every polygon angle sum exactly (self-check of the pruning) */
 #define P24_F_NO_FILTER 2u     /* evaluate every pair value exactly (self-check of the top-k filter) */
+#define P24_F_SPLIT 16u        /* cut the batch into slices whose kernel chains run concurrently on internal streams */
 #define P24_F_NO_PDL 8u        /* plain stream-ordered launches instead of programmatic dependent launch */
 #define P24_F_ALL_ROWS 4u      /* every label row is a GT (per-image API: the caller passes num_gt rows) */
 
