@@ -10,7 +10,11 @@
 
 #define P24_THREADS 256
 #define P24_SEEDS 2  // seeds per (GT, tile)
-#define P24_MAX_SPLIT 4  // batch slices processed as concurrent kernel chains
+#define P24_MAX_LEVELS 4   // feature levels of the anchor grid
+#define P24_WSIDE 7        // a GT's centre window lies inside a 7 x 7 block of grid cells per level (5 x 5 pass the test)
+#define P24_WSLOTS (P24_WSIDE * P24_WSIDE)
+#define P24_WT_HDR (P24_WSLOTS * P24_MAX_LEVELS)   // wtab row: [slot costs | ix0, iy0 per level (int bits)]
+#define P24_WT_STRIDE (P24_WT_HDR + 2 * P24_MAX_LEVELS + 4)   // 208 floats
 #define P24_WARPS (P24_THREADS / 32)
 
 // ---- per-GT record (floats), built once per image by the anchor pass ---------------------------
@@ -37,22 +41,19 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 struct P24Workspace {
     size_t gt_rec;      // [B, Lmax, GT_REC] float
     size_t clist;       // [B, tiles, 256] float4  candidate anchors of a tile, compacted: (pred cx, pred cy, rpmax, anchor idx bits)
-    size_t sval;        // [B, Lmax, P24_SEEDS * tiles] float   exact pair values of the tile's best candidates by the seed proxy
-                        //                                       (-inf: none), written by the anchor pass
-    size_t wcostv;      // [B, Lmax, VCAP] float        SimOTA cost of the GT's centre-window anchors (+inf: not in the polygon)
+    size_t sval;        // [B, Lmax, P24_SEEDS * tiles] float   certified lower bounds of the pair values of the tile's best
+                        //                                       candidates by the seed proxy (-inf: none), written by the anchor pass
+    size_t wtab;        // [B, Lmax, P24_WT_STRIDE] float  SimOTA cost of the GT's centre-window anchors by window slot
+                        //                                  (+inf: not in the window / not in the polygon) + the window origins
     size_t tbox;        // [B, tiles, 8] float          bounding box of a tile's candidate centres (xmin, xmax, ymin, ymax), max rpmax
     size_t ccount;      // [B, tiles] int          candidates per tile
-    size_t wcount;      // [B, Lmax] int           anchors inside the GT's centre window (zero between calls)
-    size_t wlist;       // [B, Lmax, VCAP] int
-    size_t best_key;    // [B, A] u64      min over the anchor's valid pairs of (ordered cost bits << 32 | gt)  (losses.py:474)
     size_t claim_cnt;   // [B, A] int      number of GTs that selected the anchor
     size_t claim_gt;    // [B, A] int      the GT that selected the anchor (meaningful when claim_cnt == 1)
     size_t obj_part;    // [B * tiles] double   per-block sums of BCEWithLogits(obj, 0)
     size_t claimed;     // [B, 10 * Lmax] int   anchors claimed by at least one GT (arrival order)
     size_t nclaimed;    // [B] int
     size_t acc_fix;     // [B, 28] int64        fixed-point loss sums of the image (zero between calls)
-    size_t ticket;      // [1 + P24_MAX_SPLIT + B] unsigned: batch counter, work-queue heads of k_window_eval (one per batch
-                        //                   slice), one counter per image (zero between calls)
+    size_t ticket;      // [1 + B] unsigned: batch counter, one counter per image (zero between calls)
     size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
     size_t total;
 };
@@ -66,18 +67,15 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     const size_t BA = (size_t)B * (size_t)A;
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
-    w.wcount = off;     off = p24_align(off + BL * sizeof(int));
-    w.ticket = off;     off = p24_align(off + (size_t)(1 + P24_MAX_SPLIT + B) * sizeof(unsigned));
+    w.ticket = off;     off = p24_align(off + (size_t)(1 + B) * sizeof(unsigned));
     w.acc_fix = off;    off = p24_align(off + (size_t)B * 28 * sizeof(long long));
     w.err_flag = off;   off = p24_align(off + sizeof(int));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
     w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
     w.ccount = off;     off = p24_align(off + NB * sizeof(int));
     w.sval = off;       off = p24_align(off + BL * P24_SEEDS * (size_t)p24_tiles(A) * sizeof(float));
-    w.wcostv = off;     off = p24_align(off + BL * P24_VCAP * sizeof(float));
+    w.wtab = off;       off = p24_align(off + BL * P24_WT_STRIDE * sizeof(float));
     w.tbox = off;       off = p24_align(off + NB * 8 * sizeof(float));
-    w.wlist = off;      off = p24_align(off + BL * P24_VCAP * sizeof(int));
-    w.best_key = off;   off = p24_align(off + BA * sizeof(unsigned long long));
     w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
     w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));
     w.obj_part = off;   off = p24_align(off + NB * sizeof(double));

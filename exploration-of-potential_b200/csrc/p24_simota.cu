@@ -7,18 +7,19 @@
 //   the loss sums and re-weighting of Loss_Function.forward          models/losses.py:246-345
 //
 // Kernel chain (caller's stream, no host synchronisation, programmatic dependent launch between stages):
-//   k_gt_prep      one CTA per image: nlabel and the per-GT records (vertices, ray lengths, safe accept /
-//                  reject radii of the polygon test)
-//   k_anchor_pass  one CTA per 256-anchor tile: the ONE pass over the head output (cp.async reads of the
-//                  27 geometry channels of every row).  Candidate mask (polygon test OR centre window) with
-//                  geometric pruning and an atan2-free angle test, the per-GT centre-window lists, the
-//                  compacted candidate list and sum BCEWithLogits(obj, 0)
-//   k_gt_match     one CTA per GT, work split into 8-lane group tasks: dynamic k from the top-10-largest pair
-//                  values over the candidates (bracketed by exact seed values and a monotone upper bound;
-//                  bound-filtered exact evaluation otherwise); polygon test, exact pair value and cost of the
-//                  GT's centre-window anchors, the k smallest -> claims (spill into the penalised regime when
-//                  there are too few)
-//   k_resolve_loss one CTA per tile: conflict resolution (argmin over all GTs), fg_mask / matched_gt /
+//   k_pass         two kinds of CTA side by side, both self-sufficient (each computes nlabel and the per-GT records
+//                  of its image from the label rows):
+//                  - anchor CTAs, one per 256-anchor tile: the ONE pass over the head output (cp.async reads of the
+//                    27 geometry channels of every row).  Candidate mask (polygon test OR centre window) with
+//                    geometric pruning and an atan2-free angle test, the compacted candidate list, per-tile seed
+//                    values for the top-10 bracket, sum BCEWithLogits(obj, 0), outputs initialised to background;
+//                  - centre-window CTAs: the (GT, centre-window anchor) pairs enumerated from the level grids:
+//                    polygon test, exact pair value and SimOTA cost -> the GT's window cost table
+//   k_match        one CTA per GT: dynamic k from the top-10-largest pair values over the candidates (bracketed by
+//                  seed values and a monotone upper bound; bound-filtered exact evaluation otherwise), then the k
+//                  smallest costs of the window table -> claims (spill into the penalised regime when there are
+//                  too few valid anchors)
+//   k_resolve_loss one warp per claimed anchor: conflict resolution (argmin over all GTs), fg_mask / matched_gt /
 //                  pred_iou, the 28 loss sums; the last CTA reduces them in a fixed order and, when asked,
 //                  applies the normalisation and the stateful re-weighting (losses.py:280-345)
 //
@@ -27,6 +28,10 @@
 #include "p24_common.cuh"
 
 namespace {
+
+struct Level {
+    int off, W, H, pad;  // anchors [off, off + W * H) form a W x H grid, row-major (yolo_head_24p.py:222-230)
+};
 
 struct Params {
     const float* outputs;
@@ -52,12 +57,9 @@ struct Params {
     float* gt_rec;
     float4* clist;
     float* sval;
-    float* wcostv;
+    float* wtab;
     float* tbox;
     int* ccount;
-    int* wcount;
-    int* wlist;
-    unsigned long long* best_key;
     int* claim_cnt;
     int* claim_gt;
     double* obj_part;
@@ -68,7 +70,9 @@ struct Params {
     int* err_flag;
     unsigned flags;
     int tiles;
-    int b0, nb, slice;  // this launch covers images [b0, b0 + nb) (batch slice `slice`)
+    int wctas;  // centre-window CTAs per image in k_pass
+    int nlev;
+    Level lev[P24_MAX_LEVELS];
 };
 
 // Debug-only phase timers (-DP24_TIMING): thread 0 of every CTA stores %globaltimer at phase boundaries.
@@ -125,107 +129,107 @@ __device__ __forceinline__ int group_sum_i(int v, unsigned m) {
 }
 
 // -------------------------------------------------------------------------------------------
-// k_gt_prep: nlabel + GT records, one CTA per image, one warp per GT (lanes over the 24 vertices)
+// GT preparation, executed inside every CTA of k_pass for its own image (no separate kernel: the records are a few
+// hundred instructions per GT and the label rows stay in L2)
 // -------------------------------------------------------------------------------------------
-#define PREP_THREADS 1024
-__global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(Params p) {
-    TMARK(3, blockIdx.x, 0);
-    pdl_wait();
-    TMARK(3, blockIdx.x, 1);
-    const int b = p.b0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* lab = p.labels + (long long)b * p.lab_img_stride;
-    // nlabel = (labels.sum(2) > 0).sum(1)   losses.py:190 ; the first n rows are the GTs (losses.py:219-220)
-    int local = 0;
-    for (int r = tid; r < p.Lmax; r += PREP_THREADS) {
-        const float* row = lab + (long long)r * p.lab_row_stride;
-        double s = 0.0;
-#pragma unroll
-        for (int c = 0; c < 51; ++c) s += (double)row[c];
-        local += ((float)s > 0.0f) ? 1 : 0;
-    }
-    __shared__ int s_n;
-    if (tid == 0) s_n = 0;
+// nlabel = (labels.sum(2) > 0).sum(1)   losses.py:190 ; the first n rows are the GTs (losses.py:219-220).
+// Four threads per label row (double partial sums); every thread returns the count.  Contains __syncthreads().
+__device__ __forceinline__ int block_count_labels(const Params& p, const float* __restrict__ lab, int* s_n) {
+    const int tid = threadIdx.x;
+    if (tid == 0) *s_n = 0;
     __syncthreads();
-    local = warp_sum_i(local);
-    if (lane == 0 && local) atomicAdd(&s_n, local);
+    if (!(p.flags & P24_F_ALL_ROWS)) {
+        const int part = tid & 3;
+        int local = 0;
+        for (int r0 = 0; r0 < p.Lmax; r0 += P24_THREADS / 4) {
+            const int r = r0 + (tid >> 2);
+            double s = 0.0;
+            if (r < p.Lmax) {
+                const float* row = lab + (long long)r * p.lab_row_stride;
+                const int c0 = part * 13, c1 = min(51, c0 + 13);
+                for (int c = c0; c < c1; ++c) s += (double)row[c];
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            local += (part == 0 && r < p.Lmax && (float)s > 0.0f) ? 1 : 0;
+        }
+        local = warp_sum_i(local);
+        if ((tid & 31) == 0 && local) atomicAdd(s_n, local);
+    }
     __syncthreads();
-    const int n = (p.flags & P24_F_ALL_ROWS) ? p.Lmax : s_n;
-    if (tid == 0) {
-        p.num_gt[b] = n;
-        p.num_fg[b] = 0;
+    return (p.flags & P24_F_ALL_ROWS) ? p.Lmax : *s_n;
+}
+
+// the record of one GT (p24_common.cuh) from its label row, by one warp (lanes over the 24 vertices)
+__device__ __forceinline__ void warp_gt_record(const float* __restrict__ row, float* __restrict__ rec) {
+    const int lane = threadIdx.x & 31;
+    const float cx = row[1], cy = row[2];
+    const int k = lane < P24_RAYS ? lane : 0;
+    const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
+    const float x = row[3 + 2 * k], y = row[4 + 2 * k];
+    const float x2 = row[3 + 2 * k2], y2 = row[4 + 2 * k2];
+    const float rg = p24_gt_radius(x - cx, y - cy);
+    const float ex = x2 - x, ey = y2 - y;
+    const float len2 = fmaf(ex, ex, ey * ey);
+    float len = sqrtf(len2);
+    // distance from the centre to the edge segment
+    const float wx = cx - x, wy = cy - y;
+    float tt = len2 > 0.0f ? __fdividef(fmaf(wx, ex, wy * ey), len2) : 0.0f;
+    tt = fminf(fmaxf(tt, 0.0f), 1.0f);
+    const float qx = wx - tt * ex, qy = wy - tt * ey;
+    float rin = sqrtf(fmaf(qx, qx, qy * qy));
+    // crossing-number parity of the centre
+    bool cross = false;
+    if ((y > cy) != (y2 > cy)) {
+        const float xi = fmaf(ex, __fdividef(cy - y, ey), x);
+        cross = cx < xi;
     }
-    for (int g = warp; g < n; g += PREP_THREADS / 32) {
-        const float* row = lab + (long long)g * p.lab_row_stride;
-        float* rec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
-        const float cx = row[1], cy = row[2];
-        const int k = lane < P24_RAYS ? lane : 0;
-        const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
-        const float x = row[3 + 2 * k], y = row[4 + 2 * k];
-        const float x2 = row[3 + 2 * k2], y2 = row[4 + 2 * k2];
-        const float rg = p24_gt_radius(x - cx, y - cy);
-        const float ex = x2 - x, ey = y2 - y;
-        const float len2 = fmaf(ex, ex, ey * ey);
-        float len = sqrtf(len2);
-        // distance from the centre to the edge segment
-        const float wx = cx - x, wy = cy - y;
-        float tt = len2 > 0.0f ? __fdividef(fmaf(wx, ex, wy * ey), len2) : 0.0f;
-        tt = fminf(fmaxf(tt, 0.0f), 1.0f);
-        const float qx = wx - tt * ex, qy = wy - tt * ey;
-        float rin = sqrtf(fmaf(qx, qx, qy * qy));
-        // crossing-number parity of the centre
-        bool cross = false;
-        if ((y > cy) != (y2 > cy)) {
-            const float xi = fmaf(ex, __fdividef(cy - y, ey), x);
-            cross = cx < xi;
-        }
-        float rgmax = rg, rgmin = rg;
-        if (lane >= P24_RAYS) {
-            len = 0.0f;
-            rin = INFINITY;
-            cross = false;
-            rgmax = 0.0f;
-            rgmin = INFINITY;
-        }
-        const unsigned par = __ballot_sync(0xffffffffu, cross);
-        const bool nan_any = __any_sync(0xffffffffu, !(rin == rin) && lane < P24_RAYS);
-        const float perim = warp_sum(len);
-        const float rgsum = warp_sum(lane < P24_RAYS ? rg : 0.0f);
-        const float rg2sum = warp_sum(lane < P24_RAYS ? rg * rg : 0.0f);
-        rgmax = warp_max(rgmax);
-        rgmin = -warp_max(-rgmin);
-        rin = -warp_max(-rin);
-        if (lane < P24_RAYS) {
-            rec[GT_VX + lane] = x;
-            rec[GT_VY + lane] = y;
-            rec[GT_RG + lane] = rg;
-        }
-        if (lane == 0) {
-            const bool inside = (__popc(par) & 1) != 0;
-            // A point inside a closed polygon has |winding| >= 1, so its total unsigned angle is >= 360 degrees:
-            // a disc around an interior centre that stays clear of every edge passes the >= 350 test (2 % + 0.01 px
-            // of slack covers the fp32 evaluation of the distances above).
-            float ra = (inside && !nan_any) ? fmaf(0.98f, rin, -0.01f) : 0.0f;
-            ra = fmaxf(ra, 0.0f);
-            // Outside, the angle sum is <= perimeter / distance-to-polygon (radians): it is < 349 degrees beyond
-            // rgmax + perimeter * (180/pi) / 349 (1 % slack).
-            const float rr = fmaf(perim * 1.01f, 57.29578f / 349.0f, rgmax) * 1.001f + 1e-2f;
-            float rrej2 = rr * rr;
-            if (!(rrej2 == rrej2)) rrej2 = INFINITY;  // NaN labels: never reject
-            rec[GT_CX] = cx;
-            rec[GT_CY] = cy;
-            rec[GT_RIN2] = ra * ra;
-            rec[GT_RREJ2] = rrej2;
-            rec[GT_CLS] = row[0];
-            rec[GT_RGMAX] = rgmax;
-            rec[GT_RGMIN] = rgmin;
-            rec[7] = 0.0f;
-            rec[GT_RGMS] = rg2sum * (1.0f / 24.0f);
-            rec[GT_RGMEAN] = rgsum * (1.0f / 24.0f);
-            rec[58] = 0.0f;
-            rec[59] = 0.0f;
-        }
+    float rgmax = rg, rgmin = rg;
+    if (lane >= P24_RAYS) {
+        len = 0.0f;
+        rin = INFINITY;
+        cross = false;
+        rgmax = 0.0f;
+        rgmin = INFINITY;
     }
-    TMARK(3, blockIdx.x, 2);
+    const unsigned par = __ballot_sync(0xffffffffu, cross);
+    const bool nan_any = __any_sync(0xffffffffu, !(rin == rin) && lane < P24_RAYS);
+    const float perim = warp_sum(len);
+    const float rgsum = warp_sum(lane < P24_RAYS ? rg : 0.0f);
+    const float rg2sum = warp_sum(lane < P24_RAYS ? rg * rg : 0.0f);
+    rgmax = warp_max(rgmax);
+    rgmin = -warp_max(-rgmin);
+    rin = -warp_max(-rin);
+    if (lane < P24_RAYS) {
+        rec[GT_VX + lane] = x;
+        rec[GT_VY + lane] = y;
+        rec[GT_RG + lane] = rg;
+    }
+    if (lane == 0) {
+        const bool inside = (__popc(par) & 1) != 0;
+        // A point inside a closed polygon has |winding| >= 1, so its total unsigned angle is >= 360 degrees:
+        // a disc around an interior centre that stays clear of every edge passes the >= 350 test (2 % + 0.01 px
+        // of slack covers the fp32 evaluation of the distances above).
+        float ra = (inside && !nan_any) ? fmaf(0.98f, rin, -0.01f) : 0.0f;
+        ra = fmaxf(ra, 0.0f);
+        // Outside, the angle sum is <= perimeter / distance-to-polygon (radians): it is < 349 degrees beyond
+        // rgmax + perimeter * (180/pi) / 349 (1 % slack).
+        const float rr = fmaf(perim * 1.01f, 57.29578f / 349.0f, rgmax) * 1.001f + 1e-2f;
+        float rrej2 = rr * rr;
+        if (!(rrej2 == rrej2)) rrej2 = INFINITY;  // NaN labels: never reject
+        rec[GT_CX] = cx;
+        rec[GT_CY] = cy;
+        rec[GT_RIN2] = ra * ra;
+        rec[GT_RREJ2] = rrej2;
+        rec[GT_CLS] = row[0];
+        rec[GT_RGMAX] = rgmax;
+        rec[GT_RGMIN] = rgmin;
+        rec[7] = 0.0f;
+        rec[GT_RGMS] = rg2sum * (1.0f / 24.0f);
+        rec[GT_RGMEAN] = rgsum * (1.0f / 24.0f);
+        rec[58] = 0.0f;
+        rec[59] = 0.0f;
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -346,10 +350,9 @@ __device__ __forceinline__ float cls_cost_from(float neg_sum, float cls_logit_c,
 }
 
 // -------------------------------------------------------------------------------------------
-// k_anchor_pass
+// k_pass, anchor CTAs: one CTA per 256-anchor tile
 // -------------------------------------------------------------------------------------------
 #define ITEM_CAP 704
-#define WIN_CAP 704
 #define ROW_CH 27  // channels 0..26 of a head row are read here: centre, 24 radii, objectness
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -360,32 +363,33 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-__global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
-    extern __shared__ float4 s_dyn4[];
-    float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC_HEAD]: everything but the ray lengths
-    const int b = p.b0 + blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+struct AnchorShared {
+    float row[P24_WARPS][ROW_CH][33];
+    int cand[P24_THREADS];
+    int seedA[P24_SEEDS * 128];
+    double red[P24_WARPS];
+    float box[P24_WARPS][5];
+    int wcnt[P24_WARPS];
+    int nitems, n;
+};
+
+__device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, AnchorShared& S) {
+    float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC]
+    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int a = tile * P24_THREADS + tid;
     const bool active = a < p.A;
-
-    __shared__ float s_row[P24_WARPS][ROW_CH][33];
-    // the work lists live in rows 5.. of s_row (free between the row reduction and the seed search)
-    unsigned* s_items = reinterpret_cast<unsigned*>(&s_row[0][5][0]);  // 726 floats per warp region; ITEM_CAP <= 726
-    unsigned* s_win = reinterpret_cast<unsigned*>(&s_row[1][5][0]);    // WIN_CAP <= 726
-    __shared__ int s_cand[P24_THREADS];
-    __shared__ int s_nitems, s_nwin;
-    __shared__ int s_wcnt[P24_WARPS];
-    __shared__ double s_red[P24_WARPS];
+    // the work list lives in rows 5.. of S.row (free between the row reduction and the seed search)
+    unsigned* s_items = reinterpret_cast<unsigned*>(&S.row[0][5][0]);  // 726 floats per warp region; ITEM_CAP <= 726
 
     // ---- the tile's rows: each warp reads its 32 rows, 27 contiguous floats per row (coalesced), straight into
-    // shared memory with cp.async; they do not depend on the previous kernel, so they are issued before the
-    // programmatic-dependency wait -----------------------------------------------------------------------------
+    // shared memory with cp.async; the GT records are computed while they are in flight -------------------------
     const float* img = p.outputs + (long long)b * p.img_stride;
     {
         const int a0 = tile * P24_THREADS + warp * 32;
         const int nrow = min(32, p.A - a0);
         if (lane < ROW_CH) {
-            for (int r = 0; r < nrow; ++r) cp_async4(&s_row[warp][lane][r], img + (long long)(a0 + r) * p.row_stride + lane);
+            for (int r = 0; r < nrow; ++r) cp_async4(&S.row[warp][lane][r], img + (long long)(a0 + r) * p.row_stride + lane);
         }
     }
     float st = 1.f, xs = 0.f, ys = 0.f;
@@ -394,49 +398,49 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
         xs = p.x_shifts[a];
         ys = p.y_shifts[a];
     }
-    if (tid == 0) {
-        s_nitems = 0;
-        s_nwin = 0;
-    }
-    s_cand[tid] = 0;
+    if (tid == 0) S.nitems = 0;
+    S.cand[tid] = 0;
     TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 0);
-    pdl_wait();
+    const float* lab = p.labels + (long long)b * p.lab_img_stride;
+    const int n = block_count_labels(p, lab, &S.n);
+    for (int g = warp; g < n; g += P24_WARPS) warp_gt_record(lab + (long long)g * p.lab_row_stride, s_gt + g * GT_REC);
     TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 1);
-    const int n = p.num_gt[b];
-    {
-        const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
-        for (int i = tid; i < n * (GT_REC_HEAD / 4); i += P24_THREADS) {
-            const int g = i / (GT_REC_HEAD / 4), q = i - g * (GT_REC_HEAD / 4);
-            s_dyn4[i] = gsrc[g * (GT_REC / 4) + q];
-        }
-    }
     cp_async_wait_all();
     __syncthreads();
+    if (tile == 0) {
+        // the image's records for the kernels that follow
+        float4* gdst = reinterpret_cast<float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
+        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) gdst[i] = s_dyn4[i];
+        if (tid == 0) {
+            p.num_gt[b] = n;
+            p.num_fg[b] = 0;
+            p.nclaimed[b] = 0;
+        }
+    }
     TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 2);
 
     float pcx = 0.f, pcy = 0.f, rpmax = 0.f, rpmin = INFINITY, rpsum = 0.f, rp2sum = 0.f, obj = 0.f;
     const float xc = p24_anchor_centre(xs, st);
     const float yc = p24_anchor_centre(ys, st);
     if (active) {
-        pcx = s_row[warp][0][lane];
-        pcy = s_row[warp][1][lane];
+        pcx = S.row[warp][0][lane];
+        pcy = S.row[warp][1][lane];
 #pragma unroll
         for (int c = 2; c < 26; ++c) {
-            const float v = s_row[warp][c][lane];
+            const float v = S.row[warp][c][lane];
             rpmax = fmaxf(rpmax, v);
             rpmin = fminf(rpmin, v);
             rpsum += v;
             rp2sum = fmaf(v, v, rp2sum);
         }
-        obj = s_row[warp][26][lane];
+        obj = S.row[warp][26][lane];
     }
     double objpart = active ? (double)p24_bce_logits(obj, 0.0f) : 0.0;
-    __syncthreads();  // the radii rows of s_row are recycled as work lists from here on
+    __syncthreads();  // the radii rows of S.row are recycled as the work list from here on
 
-    // ---- one pass over the GTs: centre windows (-> per-GT lists), the inscribed-disc accept, and a bit mask of the
-    // GTs whose reject radius the anchor is inside (the only ones that may need a polygon test) ------------------
+    // ---- one pass over the GTs: centre windows, the inscribed-disc accept, and a bit mask of the GTs whose reject
+    // radius the anchor is inside (the only ones that may need a polygon test) ------------------------------------
     bool cheap = false;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const bool no_prune = (p.flags & P24_F_NO_PRUNE) != 0;
     unsigned near[4] = {0u, 0u, 0u, 0u};  // GTs 0..127; beyond that every GT is tested in place (see below)
     {
@@ -447,37 +451,20 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
             const int ge = min(32, n - w * 32);
             for (int j = 0; j < ge; ++j) {
                 const int g = w * 32 + j;
-                const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
+                const float4 h = s_dyn4[g * (GT_REC / 4)];
                 const float dx = h.x - xc, dy = h.y - yc;
                 const float d2 = fmaf(dx, dx, dy * dy);
                 cheap |= d2 < h.z;
                 m |= (d2 <= h.w ? 1u : 0u) << j;
-                if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && active && p24_in_centre(h.x, h.y, xc, yc, st)) {
-                    cheap = true;
-                    // (anchor, GT) goes to the GT's centre-window list; staged in shared memory so that the global
-                    // atomics of a tile are issued together instead of one round trip at a time
-                    const int ws = atomicAdd(&s_nwin, 1);
-                    if (ws < WIN_CAP) {
-                        s_win[ws] = (unsigned)tid | ((unsigned)g << 8);
-                    } else {
-                        const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
-                        if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
-                        else atomicOr(p.err_flag, 1);
-                    }
-                }
+                if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
             }
             near[w] = no_prune ? (ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u)) : m;
         }
         for (int g = 128; g < n; ++g) {  // more than 128 GTs: windows and discs of the rest
-            const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
+            const float4 h = s_dyn4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             cheap |= fmaf(dx, dx, dy * dy) < h.z;
-            if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && active && p24_in_centre(h.x, h.y, xc, yc, st)) {
-                cheap = true;
-                const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
-                if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = a;
-                else atomicOr(p.err_flag, 1);
-            }
+            if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
         }
     }
     cheap = cheap && active;
@@ -491,88 +478,77 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
             while (m) {
                 const int g = w * 32 + __ffs(m) - 1;
                 m &= m - 1;
-                const int slot = atomicAdd(&s_nitems, 1);
+                const int slot = atomicAdd(&S.nitems, 1);
                 if (slot < ITEM_CAP) {
                     s_items[slot] = (unsigned)tid | ((unsigned)g << 8);
                 } else if (!mine) {
-                    const float* rec = s_gt + g * GT_REC_HEAD;
+                    const float* rec = s_gt + g * GT_REC;
                     mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
                                     : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
                 }
             }
         }
         for (int g = 128; g < n && !mine; ++g) {  // more than 128 GTs: test the rest in place
-            const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
+            const float4 h = s_dyn4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             if (no_prune || fmaf(dx, dx, dy * dy) <= h.w) {
-                const float* rec = s_gt + g * GT_REC_HEAD;
+                const float* rec = s_gt + g * GT_REC;
                 mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
                                 : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
             }
         }
     }
-    if (mine) s_cand[tid] = 1;
+    if (mine) S.cand[tid] = 1;
     __syncthreads();
     TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 3);
-    {
-        const int nw = min(s_nwin, WIN_CAP);
-        for (int i = tid; i < nw; i += P24_THREADS) {
-            const unsigned it = s_win[i];
-            const int g = it >> 8;
-            const int slot = atomicAdd(&p.wcount[b * p.Lmax + g], 1);
-            if (slot < P24_VCAP) p.wlist[((long long)b * p.Lmax + g) * P24_VCAP + slot] = tile * P24_THREADS + (int)(it & 0xFF);
-            else atomicOr(p.err_flag, 1);
-        }
-    }
-    const int nitems = min(s_nitems, ITEM_CAP);
+    const int nitems = min(S.nitems, ITEM_CAP);
     for (int i = tid; i < nitems; i += P24_THREADS) {
         const unsigned it = s_items[i];
         const int al = it & 0xFF;
-        if (((volatile int*)s_cand)[al]) continue;  // already a candidate through another GT
+        if (((volatile int*)S.cand)[al]) continue;  // already a candidate through another GT
         const int g = it >> 8;
-        const float* rec = s_gt + g * GT_REC_HEAD;
+        const float* rec = s_gt + g * GT_REC;
         const int aa = tile * P24_THREADS + al;
         const float st2 = p.strides[aa];
         const float axc = p24_anchor_centre(p.x_shifts[aa], st2);
         const float ayc = p24_anchor_centre(p.y_shifts[aa], st2);
         const bool in = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, axc, ayc)
                                  : p24_in_polygon(rec + GT_VX, rec + GT_VY, axc, ayc);
-        if (in) s_cand[al] = 1;
+        if (in) S.cand[al] = 1;
     }
     __syncthreads();
 
     TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 4);
     // ---- compacted candidate list of the tile (deterministic order) + per-anchor scratch reset ----------
-    const bool cand = active && (n > 0) && (cheap || s_cand[tid]);
+    const bool cand = active && (n > 0) && (cheap || S.cand[tid]);
     // ---- seeds of the top-10 search: lane g of every warp ranks the warp's candidates for GT g by the first-order
     // proxy q = (mean rg^2 + mean rp^2) / (mean rg + mean rp + d)^2 of the pair value (value ~ 1 - q / 3 for far
     // pairs; the smallest q are almost always the true top-10) and records the largest t = rpmax + d -----------
-    s_row[warp][2][lane] = rp2sum * (1.0f / 24.0f);
-    s_row[warp][3][lane] = rpsum * (1.0f / 24.0f);
-    s_row[warp][4][lane] = cand ? (rpmin < 0.25f ? INFINITY : rpmax) : -1.0f;
+    S.row[warp][2][lane] = rp2sum * (1.0f / 24.0f);
+    S.row[warp][3][lane] = rpsum * (1.0f / 24.0f);
+    S.row[warp][4][lane] = cand ? (rpmin < 0.25f ? INFINITY : rpmax) : -1.0f;
     __syncthreads();
-    __shared__ float s_box[P24_WARPS][5];
     {
-        // bounding box of the warp's candidates (GT independent): k_gt_match bounds t = rpmax + d with it
+        // bounding box of the warp's candidates (GT independent): k_match bounds t = rpmax + d with it
         {
             const float rz = cand ? (rpmin < 0.25f ? INFINITY : rpmax) : P24_NEG_INF;
             const float bx0 = -warp_max(cand ? -pcx : P24_NEG_INF), bx1 = warp_max(cand ? pcx : P24_NEG_INF);
             const float by0 = -warp_max(cand ? -pcy : P24_NEG_INF), by1 = warp_max(cand ? pcy : P24_NEG_INF);
             const float rzm = warp_max(rz);
             if (lane == 0) {
-                s_box[warp][0] = bx0;
-                s_box[warp][1] = bx1;
-                s_box[warp][2] = by0;
-                s_box[warp][3] = by1;
-                s_box[warp][4] = rzm;
+                S.box[warp][0] = bx0;
+                S.box[warp][1] = bx1;
+                S.box[warp][2] = by0;
+                S.box[warp][3] = by1;
+                S.box[warp][4] = rzm;
             }
         }
         // warp w ranks a quarter of the tile's anchors, i = 8 j + ((w - j) & 7) for every 4th j: neighbouring anchors
         // (nearly equal proxies) land in different warps, and a quarter sample is enough for seeds (any candidate
-        // is a valid seed; better ones only make the bracket tighter).  Per-warp results go to the free rows of s_row.
-        float* wres = &s_row[warp][5][0];  // [n][4]: q1, a1, q2, a2   (22 * 33 = 726 floats: n <= 181)
+        // is a valid seed; better ones only make the bracket tighter).  Per-warp results go to the free rows of S.row.
+        float* wres = &S.row[warp][5][0];  // [n][4]: q1, a1, q2, a2   (22 * 33 = 726 floats: n <= 181)
         for (int g = lane; g < n; g += 32) {
-            const float* rec = s_gt + g * GT_REC_HEAD;
+            const float* rec = s_gt + g * GT_REC;
             const float gcx = rec[GT_CX], gcy = rec[GT_CY], rgms = rec[GT_RGMS], rgmean = rec[GT_RGMEAN];
             float q1 = P24_POS_INF, q2 = P24_POS_INF;
             int a1 = -1, a2 = -1;
@@ -581,13 +557,13 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
                 const int j = 4 * jj + (warp & 3);
                 const int i = 8 * j + ((warp - j) & 7);
                 const int wj = i >> 5, lj = i & 31;
-                const float rz = s_row[wj][4][lj];
+                const float rz = S.row[wj][4][lj];
                 if (rz < 0.0f) continue;  // not a candidate
-                const float dx = gcx - s_row[wj][0][lj], dy = gcy - s_row[wj][1][lj];
+                const float dx = gcx - S.row[wj][0][lj], dy = gcy - S.row[wj][1][lj];
                 const float d2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-12f);
                 const float d = d2 * rsqrtf(d2);
-                const float den = (rgmean + s_row[wj][3][lj]) + d;
-                const float q = __fdividef(rgms + s_row[wj][2][lj], den * den);
+                const float den = (rgmean + S.row[wj][3][lj]) + d;
+                const float q = __fdividef(rgms + S.row[wj][2][lj], den * den);
                 const int aj = tile * P24_THREADS + i;
                 if (q < q1) {
                     q2 = q1;
@@ -608,21 +584,20 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
         }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, cand);
-    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    if (lane == 0) S.wcnt[warp] = __popc(bal);
     objpart = warp_sum_d(objpart);
-    if (lane == 0) s_red[warp] = objpart;
+    if (lane == 0) S.red[warp] = objpart;
     __syncthreads();
     int base = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < P24_WARPS; ++w) {
-        const int c = s_wcnt[w];
+        const int c = S.wcnt[w];
         base += (w < warp) ? c : 0;
         total += c;
     }
     const long long blk = (long long)b * p.tiles + tile;
-    // the tile's two best seeds per GT (merge of the 8 warps), evaluated exactly right away (8-lane groups): what
-    // k_dyn_k brackets the top-10 sum with.  128 GTs at a time.
-    __shared__ int s_seedA[P24_SEEDS * 128];
+    // the tile's two best seeds per GT (merge of the 8 warps), evaluated right away (8-lane groups): what
+    // k_match brackets the top-10 sum with.  128 GTs at a time.
     for (int g0 = 0; g0 < n; g0 += 128) {
         const int gn = min(128, n - g0);
         if (tid < gn) {
@@ -637,7 +612,7 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
             if (g < 181) {
 #pragma unroll
                 for (int w = 0; w < P24_WARPS; ++w) {
-                    const float* e = &s_row[w][5][0] + g * 4;
+                    const float* e = &S.row[w][5][0] + g * 4;
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         float q = e[2 * u];
@@ -657,18 +632,17 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < P24_SEEDS; ++u) s_seedA[P24_SEEDS * tid + u] = ab[u];
+            for (int u = 0; u < P24_SEEDS; ++u) S.seedA[P24_SEEDS * tid + u] = ab[u];
         }
         __syncthreads();
         {
             const unsigned gm = group_mask();
             const int grp = tid >> 3, sub = tid & 7;
             for (int t = grp; t < P24_SEEDS * gn; t += P24_THREADS / 8) {
-                const int sa = s_seedA[t];
+                const int sa = S.seedA[t];
                 const int g = g0 + t / P24_SEEDS;
                 float v = P24_NEG_INF;
-                if (sa >= 0)
-                    v = group_pair_value_lb(p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC, img + (long long)sa * p.row_stride, gm);
+                if (sa >= 0) v = group_pair_value_lb(s_gt + g * GT_REC, img + (long long)sa * p.row_stride, gm);
                 if (sub == 0)
                     p.sval[((long long)b * p.Lmax + g) * P24_SEEDS * p.tiles + P24_SEEDS * tile + (t % P24_SEEDS)] = v;
             }
@@ -678,11 +652,11 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
     if (tid == 32) {
         float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY, rzm = -INFINITY;
         for (int w = 0; w < P24_WARPS; ++w) {
-            bx0 = fminf(bx0, s_box[w][0]);
-            bx1 = fmaxf(bx1, s_box[w][1]);
-            by0 = fminf(by0, s_box[w][2]);
-            by1 = fmaxf(by1, s_box[w][3]);
-            rzm = fmaxf(rzm, s_box[w][4]);
+            bx0 = fminf(bx0, S.box[w][0]);
+            bx1 = fmaxf(bx1, S.box[w][1]);
+            by0 = fminf(by0, S.box[w][2]);
+            by1 = fmaxf(by1, S.box[w][3]);
+            rzm = fmaxf(rzm, S.box[w][4]);
         }
         float4* dst = reinterpret_cast<float4*>(p.tbox + blk * 8);
         dst[0] = make_float4(bx0, bx1, by0, by1);
@@ -697,16 +671,14 @@ __global__ void __launch_bounds__(P24_THREADS, 5) k_anchor_pass(Params p) {
         // every anchor starts as background; k_resolve_loss overwrites the claimed ones
         const long long o = (long long)b * p.A + a;
         p.claim_cnt[o] = 0;
-        p.best_key[o] = 0xFFFFFFFFFFFFFFFFull;
         p.fg_mask[o] = 0;
         p.matched_gt[o] = -1;
         p.pred_iou[o] = 0.0f;
     }
     if (tid == 0) {
-        if (tile == 0) p.nclaimed[b] = 0;
         p.ccount[blk] = total;
         double t = 0.0;
-        for (int w = 0; w < P24_WARPS; ++w) t += s_red[w];
+        for (int w = 0; w < P24_WARPS; ++w) t += S.red[w];
         p.obj_part[blk] = t;
     }
     TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 5);
@@ -728,6 +700,7 @@ __device__ __forceinline__ void claim_anchor(const Params& p, int b, int a, int 
 }
 
 #define HIT_CAP 3072
+#define MATCH_WCAP (25 * P24_MAX_LEVELS)  // at most 5 x 5 cells per level pass the window test
 #define MAX_TILES 1024  // candidate counts of an image kept in shared memory (A <= 262144)
 
 // Upper bound of the pair value as a function of t = rpmax + d: any ray has loss <= max(1, 2 - 4 rg^2 / (rg + rp + d)^2)
@@ -754,8 +727,8 @@ struct MatchShared {
     float wmax[MATCH_WARPS];
     int cnt, nhit, nev, k, slow, nvalid, overflow;
     float T, L, tau, tmax;
-    int wanchor[P24_VCAP];
-    float wcost[P24_VCAP];  // +inf: not valid
+    int wanchor[MATCH_WCAP];   // the GT's valid (in window, in polygon) anchors and their costs
+    float wcost[MATCH_WCAP];
 };
 
 template <bool MAX>
@@ -1022,44 +995,73 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
 }
 
 // -------------------------------------------------------------------------------------------
-// k_window_eval: every (GT, centre-window anchor) pair of the batch as an independent 8-lane group task:
+// k_pass, centre-window CTAs: every (GT, centre-window anchor) pair as an independent 8-lane group task:
 // polygon test (inscribed-disc accept, else the reference-order edge terms, 3 per lane), exact pair value and
-// SimOTA cost when inside, per-anchor argmin key.  Every load of a task is issued before its arithmetic.
-// Persistent grid (one wave).  It needs nothing from k_dyn_k, which precedes it in the stream: it starts while
-// k_dyn_k's slow CTAs are still running and only waits for them at its very end, so that the kernels after it
-// are ordered after both.
+// SimOTA cost when inside.  The window of a GT is enumerated straight from the level grids (a 7 x 7 block of cells
+// per level around the centre holds every anchor that can pass the strict test of losses.py:523-542, which is then
+// applied in the reference's own arithmetic), so this part needs nothing from the anchor CTAs and runs beside them.
+// Costs land in the GT's window table by slot (level, row, column); the anchor of a slot and the slot of an anchor
+// are both computable, which is what k_match (selection) and k_resolve_loss (conflict argmin) rely on.
 // -------------------------------------------------------------------------------------------
-#define EVAL_SPLIT 4
+struct WindowShared {
+    float rec[GT_REC];
+    int list[P24_WT_HDR];  // slots that pass the centre-window test
+    int org[2 * P24_MAX_LEVELS];
+    int npair, n;
+};
 
-__global__ void __launch_bounds__(P24_THREADS, 4) k_window_eval(Params p) {
-    const int tid = threadIdx.x;
-    TMARK(4, blockIdx.x, 0);
-    __shared__ float s_rec[GT_REC];
+// first cell of the 7-wide block that contains every cell centre within 2.5 strides of c (one cell of slack per side)
+__device__ __forceinline__ int window_origin(float c, float st) {
+    float v = floorf(c / st) - 3.0f;
+    v = fminf(fmaxf(v, -1.0e6f), 1.0e6f);  // NaN -> -1e6: an empty window
+    return (int)v;
+}
+
+__device__ __forceinline__ void window_part(const Params& p, WindowShared& S) {
+    const int b = blockIdx.y, w = blockIdx.x - p.tiles, tid = threadIdx.x;
+    TMARK(4, blockIdx.y * p.wctas + w, 0);
+    const float* lab = p.labels + (long long)b * p.lab_img_stride;
+    const int n = block_count_labels(p, lab, &S.n);
     const unsigned gm = group_mask();
     const int grp = tid >> 3, sub = tid & 7;
-    const int nitem = p.nb * p.Lmax * EVAL_SPLIT;
-    __shared__ int s_item;
-    for (;;) {
-        // dynamic work queue: (GT, part) items are very uneven (rows beyond num_gt are empty)
+    const float* img = p.outputs + (long long)b * p.img_stride;
+    const int nslot = P24_WSLOTS * p.nlev;
+    for (int g = w; g < n; g += p.wctas) {
         __syncthreads();
-        if (tid == 0) s_item = (int)atomicAdd(&p.ticket[1 + p.slice], 1u);
+        if (tid < 32) warp_gt_record(lab + (long long)g * p.lab_row_stride, S.rec);
+        if (tid == 32) S.npair = 0;
         __syncthreads();
-        const int item = s_item;
-        if (item >= nitem) break;
-        const int part = item % EVAL_SPLIT;
-        const int wslot = p.b0 * p.Lmax + item / EVAL_SPLIT;  // b * Lmax + g
-        const int b = wslot / p.Lmax, g = wslot - b * p.Lmax;
-        if (g >= p.num_gt[b]) continue;
-        const int nwin = min(p.wcount[wslot], P24_VCAP);
-        if (part * (P24_THREADS / 8) >= nwin) continue;
+        const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
+        float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
+        if (tid < 2 * p.nlev) {
+            const float st = p.strides[p.lev[tid >> 1].off];
+            const int o = window_origin((tid & 1) ? gcy : gcx, st);
+            S.org[tid] = o;
+            tab[P24_WT_HDR + tid] = __int_as_float(o);
+        }
         __syncthreads();
-        if (tid < GT_REC) s_rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
+        for (int t = tid; t < nslot; t += P24_THREADS) {
+            const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
+            const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+            const int ix = S.org[2 * l] + sx, iy = S.org[2 * l + 1] + sy;
+            const Level lv = p.lev[l];
+            bool in = false;
+            if (ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
+                const int a = lv.off + iy * lv.W + ix;
+                const float st = p.strides[a];
+                in = p24_in_centre(gcx, gcy, p24_anchor_centre(p.x_shifts[a], st), p24_anchor_centre(p.y_shifts[a], st), st);
+            }
+            tab[t] = P24_POS_INF;
+            if (in) S.list[atomicAdd(&S.npair, 1)] = t;
+        }
         __syncthreads();
-        const float gcx = s_rec[GT_CX], gcy = s_rec[GT_CY];
-        const float* img = p.outputs + (long long)b * p.img_stride;
-        const int c = gt_class(s_rec, p.nc);
-        for (int wi = part * (P24_THREADS / 8) + grp; wi < nwin; wi += EVAL_SPLIT * (P24_THREADS / 8)) {
-            const int a = p.wlist[(long long)wslot * P24_VCAP + wi];
+        const int npair = S.npair;
+        const int c = gt_class(S.rec, p.nc);
+        for (int wi = grp; wi < npair; wi += P24_THREADS / 8) {
+            const int t = S.list[wi];
+            const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
+            const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+            const int a = p.lev[l].off + (S.org[2 * l + 1] + sy) * p.lev[l].W + (S.org[2 * l] + sx);
             const float* row = img + (long long)a * p.row_stride;
             const float st = p.strides[a];
             const float xs = p.x_shifts[a], ys = p.y_shifts[a];
@@ -1071,19 +1073,18 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_window_eval(Params p) {
             for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
             const float xc = p24_anchor_centre(xs, st);
             const float yc = p24_anchor_centre(ys, st);
-            float cost = P24_POS_INF;
             bool inside = true;
             {
-                // inside the inscribed disc the angle sum is >= 360 (see k_gt_prep): no edge terms needed
+                // inside the inscribed disc the angle sum is >= 360 (see warp_gt_record): no edge terms needed
                 const float ddx = gcx - xc, ddy = gcy - yc;
-                if (!(fmaf(ddx, ddx, ddy * ddy) < s_rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
+                if (!(fmaf(ddx, ddx, ddy * ddy) < S.rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
                     float ang = 0.0f;
 #pragma unroll 1
                     for (int q = 0; q < 3; ++q) {
                         const int k = sub * 3 + q;
                         const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
-                        ang = ang + edge_angle(s_rec[GT_VX + k] - xc, s_rec[GT_VY + k] - yc, s_rec[GT_VX + k2] - xc,
-                                               s_rec[GT_VY + k2] - yc);
+                        ang = ang + edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
+                                               S.rec[GT_VY + k2] - yc);
                     }
                     ang = group_sum(ang, gm);
                     inside = ang >= 350.0f;  // losses.py:588
@@ -1093,7 +1094,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_window_eval(Params p) {
                 const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
                 float s = 0.0f;
 #pragma unroll 1
-                for (int q = 0; q < 3; ++q) s = s + ray_loss(s_rec[GT_RG + sub * 3 + q], rp[q], d);
+                for (int q = 0; q < 3; ++q) s = s + ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
                 s = group_sum(s, gm);
                 const float v = (s / 24.0f) / 2.0f;
                 const float eo1 = 1.0f + expf(-obj);
@@ -1110,38 +1111,46 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_window_eval(Params p) {
                 } else {
                     neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
                 }
-                cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
+                float cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
                 if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
-                // per-anchor argmin over its valid pairs (first GT index on ties): what conflict resolution needs
-                if (sub == 0)
-                    atomicMin(&p.best_key[(long long)b * p.A + a], ((unsigned long long)p24_ordered(cost) << 32) | (unsigned)g);
+                if (sub == 0) tab[t] = cost;
             }
-            if (sub == 0) p.wcostv[(long long)wslot * P24_VCAP + wi] = cost;
         }
     }
-    TMARK(4, blockIdx.x, 1);
-    pdl_wait();  // late: k_dyn_k (the previous kernel) must be complete before k_select starts
-    TMARK(4, blockIdx.x, 2);
+    TMARK(4, blockIdx.y * p.wctas + w, 1);
+}
+
+// k_pass: blockIdx.x < tiles: anchor tiles; the rest: centre-window CTAs of the same image (blockIdx.y)
+__global__ void __launch_bounds__(P24_THREADS, 4) k_pass(Params p) {
+    extern __shared__ float4 s_dyn4[];
+    pdl_trigger();  // k_match may become resident (it waits for this grid's completion before it reads anything)
+    if ((int)blockIdx.x < p.tiles) {
+        __shared__ AnchorShared SA;
+        anchor_part(p, s_dyn4, SA);
+    } else {
+        __shared__ WindowShared SW;
+        window_part(p, SW);
+    }
 }
 
 // -------------------------------------------------------------------------------------------
-// k_dyn_k: per GT, dynamic k = clamp(int(sum of the 10 largest pair values over the candidates), 1) from the exact seed
-// values of the anchor pass (top-10 bracket; exact filtered / brute-force paths when it is not conclusive)
+// k_match: per GT, dynamic k = clamp(int(sum of the 10 largest pair values over the candidates), 1) from the seed
+// values of the anchor pass (top-10 bracket; exact filtered / brute-force paths when it is not conclusive), then
+// the k smallest costs of its valid pairs -> claims (rank counting; spill into the penalised regime when the GT
+// has fewer valid anchors than k)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MATCH_THREADS) k_dyn_k(Params p) {
-    const int g = blockIdx.x, b = p.b0 + blockIdx.y, tid = threadIdx.x;
+__global__ void __launch_bounds__(MATCH_THREADS) k_match(Params p) {
+    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 #define MCTA (b * 20 + g)
     if (g < 20) TMARK(1, MCTA, 0);
-    // num_gt was written by k_gt_prep, which completed before k_anchor_pass let this kernel launch: rows beyond it
-    // leave at once (their dyn_k slot is not read by anyone before the next call rewrites it)
+    pdl_trigger();  // k_resolve_loss may become resident
+    pdl_wait();
     const int n = p.num_gt[b];
     if (g >= n) {
         if (tid == 0) p.dyn_k[b * p.Lmax + g] = 0;
         return;
     }
-    pdl_wait();
-    pdl_trigger();  // k_window_eval does not depend on this kernel
     TMARK(1, MCTA, 1);
     __shared__ MatchShared S;
     const int wslot = b * p.Lmax + g;
@@ -1254,46 +1263,41 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_dyn_k(Params p) {
         g_tstamp[1][MCTA][11] = S.overflow;
     }
 #endif
-}
-
-// -------------------------------------------------------------------------------------------
-// k_select: per GT, the dyn_k smallest costs of its valid pairs -> claims (rank counting, one thread per window
-// anchor); spill into the penalised regime when the GT has fewer valid anchors than dyn_k
-// -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MATCH_THREADS) k_select(Params p) {
-    const int g = blockIdx.x, b = p.b0 + blockIdx.y, tid = threadIdx.x;
-    if (g < 20) TMARK(5, b * 20 + g, 0);
-    const int n = p.num_gt[b];
-    if (g >= n) return;
-    pdl_wait();
-    TMARK(5, b * 20 + g, 1);
-    __shared__ MatchShared S;
-    const int wslot = b * p.Lmax + g;
-    const int nwin = min(p.wcount[wslot], P24_VCAP);
-    const int k = p.dyn_k[wslot];
-    if (tid < P24_VCAP) {
-        S.wanchor[tid] = tid < nwin ? p.wlist[(long long)wslot * P24_VCAP + tid] : 0x7fffffff;
-        S.wcost[tid] = tid < nwin ? p.wcostv[(long long)wslot * P24_VCAP + tid] : P24_POS_INF;
+    // ---- selection: the k smallest costs among the GT's valid pairs (losses.py:460-464), ties -> lower anchor index
+    __syncthreads();
+    if (tid == 0) S.nvalid = 0;
+    __syncthreads();
+    {
+        const float* tab = p.wtab + (long long)wslot * P24_WT_STRIDE;
+        const int nslot = P24_WSLOTS * p.nlev;
+        for (int t = tid; t < nslot; t += MATCH_THREADS) {
+            const float c = tab[t];
+            if (c < P24_POS_INF) {
+                const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
+                const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+                const int ix = __float_as_int(tab[P24_WT_HDR + 2 * l]) + sx, iy = __float_as_int(tab[P24_WT_HDR + 2 * l + 1]) + sy;
+                const int slot = atomicAdd(&S.nvalid, 1);
+                if (slot < MATCH_WCAP) {
+                    S.wanchor[slot] = p.lev[l].off + iy * p.lev[l].W + ix;
+                    S.wcost[slot] = c;
+                } else {
+                    atomicOr(p.err_flag, 1);
+                }
+            }
+        }
     }
     __syncthreads();
-    if (tid == 0) p.wcount[wslot] = 0;  // leave the list empty for the next call
-    const bool mine = tid < nwin && S.wcost[tid] < P24_POS_INF;
-    const int nv = __syncthreads_count(mine);
+    const int nv = min(S.nvalid, MATCH_WCAP);
     const int take = min(k, nv);
-    if (mine) {
+    if (tid < nv) {
         const float ci = S.wcost[tid];
         const int ai = S.wanchor[tid];
         int before = 0;
-        for (int j = 0; j < nwin; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
+        for (int j = 0; j < nv; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
         if (before < take) claim_anchor(p, b, ai, g);
     }
-    if (k > nv) {
-        if (tid < GT_REC) S.rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
-        for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) S.ccount[tl] = p.ccount[(long long)b * p.tiles + tl];
-        __syncthreads();
-        spill_claims(p, S, b, g, nwin, k - nv);
-    }
-    TMARK(5, b * 20 + g, 2);
+    if (k > nv) spill_claims(p, S, b, g, nv, k - nv);
+    TMARK(1, MCTA, 6);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1377,6 +1381,32 @@ __device__ __noinline__ int resolve_conflict(const Params& p, const float* recs,
     return best.i != 0x7fffffff ? best.i : 0;
 }
 
+// Anchor claimed by several GTs: the GT with the smallest cost among those the anchor is valid for (in window and in
+// polygon), first index on ties; -1 when there is none.  One warp, lanes over the GTs: the anchor's slot in a GT's
+// window table follows from its grid cell and the table's origins.
+__device__ __forceinline__ int valid_argmin(const Params& p, int b, int n, int a) {
+    const int lane = threadIdx.x & 31;
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < P24_MAX_LEVELS; ++q) l += (q < p.nlev && a >= p.lev[q].off) ? 1 : 0;
+    const int r = a - p.lev[l].off;
+    const int iy = r / p.lev[l].W, ix = r - iy * p.lev[l].W;
+    KV best = {P24_POS_INF, 0x7fffffff};
+    for (int g = lane; g < n; g += 32) {
+        const float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
+        const int sx = ix - __float_as_int(tab[P24_WT_HDR + 2 * l]), sy = iy - __float_as_int(tab[P24_WT_HDR + 2 * l + 1]);
+        if (sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE) {
+            const float c = tab[l * P24_WSLOTS + sy * P24_WSIDE + sx];
+            if (c < P24_POS_INF && kv_lt(c, g, best.v, best.i)) {
+                best.v = c;
+                best.i = g;
+            }
+        }
+    }
+    best = warp_select<false>(best);
+    return best.i != 0x7fffffff ? best.i : -1;
+}
+
 #define FIX_SCALE 68719476736.0  // 2^36: fixed-point unit of the loss accumulators (order-independent sums)
 #define RESOLVE_GRID_X 16
 
@@ -1386,7 +1416,7 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 0);
     pdl_wait();
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 1);
-    const int b = p.b0 + blockIdx.y, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int n = p.num_gt[b];
     __shared__ long long s_acc[P24_WARPS][26];
@@ -1409,10 +1439,10 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
         int g = p.claim_gt[o];
         if (cnt > 1) {
             // claimed by several GTs: argmin of the cost over ALL GTs (losses.py:471-476).  Valid pairs always beat
-            // penalised ones and their argmin was recorded by k_pair_eval; without any valid pair (every claim came
+            // penalised ones and their costs are in the GTs' window tables; without any valid pair (every claim came
             // from a spill) the penalised costs are evaluated here
-            const unsigned long long key = p.best_key[o];
-            g = (key != 0xFFFFFFFFFFFFFFFFull) ? (int)(key & 0xFFFFFFFFu) : resolve_conflict(p, recs, n, row, aa);
+            const int gv = valid_argmin(p, b, n, aa);
+            g = gv >= 0 ? gv : resolve_conflict(p, recs, n, row, aa);
         }
         const float* rec = recs + g * GT_REC;
         float l;
@@ -1455,9 +1485,9 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     if (tid == 0) {
         // two-level completion count (image, then batch): few atomics per address
         bool last = false;
-        const unsigned done = atomicAdd(&p.ticket[1 + P24_MAX_SPLIT + b], 1u);
+        const unsigned done = atomicAdd(&p.ticket[1 + b], 1u);
         if (done == (unsigned)gridDim.x - 1u) {
-            p.ticket[1 + P24_MAX_SPLIT + b] = 0u;  // ready for the next call
+            p.ticket[1 + b] = 0u;  // ready for the next call
             __threadfence();
             const unsigned done2 = atomicAdd(&p.ticket[0], 1u);
             last = (done2 == (unsigned)p.B - 1u);
@@ -1495,7 +1525,6 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     if (tid < 28) p.sums28[tid] = s_sums[tid];
     if (tid == 0) {
         p.ticket[0] = 0u;  // ready for the next call
-        for (int q = 0; q < P24_MAX_SPLIT; ++q) p.ticket[1 + q] = 0u;
     }
     if (p.state26 && warp == 0) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 6);
@@ -1506,10 +1535,10 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
     finalize_warp(sums28, state26, result54, weights_n27);
 }
 
-size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC_HEAD * sizeof(float); }
+size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float); }
 
 // optional per-stage timing (profiling aid for bench.py; process-global, not thread-safe)
-#define N_STAGES 6
+#define N_STAGES 3
 bool g_prof_on = false;
 cudaEvent_t g_prof_ev[N_STAGES + 1];
 bool g_prof_have = false;
@@ -1550,15 +1579,18 @@ extern "C" int p24_workspace_init(void* workspace, size_t workspace_bytes, void*
 extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A,
                                      int num_classes, const float* labels, int64_t lab_img_stride,
                                      int64_t lab_row_stride, int Lmax, const float* x_shifts, const float* y_shifts,
-                                     const float* strides, uint8_t* fg_mask, int32_t* matched_gt, float* pred_iou,
-                                     int32_t* num_fg, int32_t* num_gt, int32_t* dyn_k, float* sums28, float* state26,
-                                     float* result54, float* weights_n27, void* workspace, size_t workspace_bytes,
-                                     uint32_t flags, void* stream) {
+                                     const float* strides, const int32_t* h_levels, int n_levels, uint8_t* fg_mask,
+                                     int32_t* matched_gt, float* pred_iou, int32_t* num_fg, int32_t* num_gt,
+                                     int32_t* dyn_k, float* sums28, float* state26, float* result54,
+                                     float* weights_n27, void* workspace, size_t workspace_bytes, uint32_t flags,
+                                     void* stream) {
     if (!outputs || !labels || !x_shifts || !y_shifts || !strides || !fg_mask || !matched_gt || !pred_iou || !num_fg ||
-        !num_gt || !dyn_k || !workspace)
+        !num_gt || !dyn_k || !workspace || !h_levels)
         return P24_E_BADARG;
     if (B <= 0 || A <= 0 || Lmax <= 0 || num_classes <= 0 || Lmax > 65535 || B > 65535) return P24_E_BADARG;
     if (state26 && (!sums28 || !result54 || !weights_n27)) return P24_E_BADARG;
+    if (n_levels <= 0) return P24_E_BADARG;
+    if (n_levels > P24_MAX_LEVELS) return P24_E_UNSUPPORTED;
     const P24Workspace L = p24_layout(B, A, Lmax);
     if (workspace_bytes < L.total) return P24_E_WORKSPACE;
     if (((uintptr_t)workspace & 255) != 0) return P24_E_BADARG;
@@ -1576,12 +1608,9 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.gt_rec = (float*)(ws + L.gt_rec);
     p.clist = (float4*)(ws + L.clist);
     p.sval = (float*)(ws + L.sval);
-    p.wcostv = (float*)(ws + L.wcostv);
+    p.wtab = (float*)(ws + L.wtab);
     p.tbox = (float*)(ws + L.tbox);
     p.ccount = (int*)(ws + L.ccount);
-    p.wcount = (int*)(ws + L.wcount);
-    p.wlist = (int*)(ws + L.wlist);
-    p.best_key = (unsigned long long*)(ws + L.best_key);
     p.claim_cnt = (int*)(ws + L.claim_cnt);
     p.claim_gt = (int*)(ws + L.claim_gt);
     p.obj_part = (double*)(ws + L.obj_part);
@@ -1592,87 +1621,45 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.err_flag = (int*)(ws + L.err_flag);
     p.flags = flags;
     p.tiles = p24_tiles(A);
+    p.wctas = Lmax < 32 ? Lmax : 32;
+    p.nlev = n_levels;
+    {
+        // the levels must tile [0, A) in order: anchors [off, off + W * H) of level l form a W x H grid
+        long long next = 0;
+        for (int l = 0; l < P24_MAX_LEVELS; ++l) {
+            p.lev[l].off = 0; p.lev[l].W = 1; p.lev[l].H = 0; p.lev[l].pad = 0;
+            if (l < n_levels) {
+                const int32_t* d = h_levels + 4 * l;
+                if (d[0] != next || d[1] <= 0 || d[2] <= 0) return P24_E_BADARG;
+                p.lev[l].off = d[0]; p.lev[l].W = d[1]; p.lev[l].H = d[2];
+                next += (long long)d[1] * d[2];
+            }
+        }
+        if (next != A) return P24_E_BADARG;
+    }
     cudaStream_t st = (cudaStream_t)stream;
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_anchor_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_done = true;
     }
     const bool pdl = !(flags & P24_F_NO_PDL) && !g_prof_on;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
-    // The batch is cut into slices whose kernel chains run concurrently (the caller's stream + internal streams, forked and
-    // joined with events): the latency-bound stages of one slice overlap the throughput-bound stages of another.  The
-    // last CTA of the last slice to finish reduces the whole batch.
-    // Measured on B200 at B = 20: the slices advance in lockstep, so nothing complementary overlaps and the extra launches
-    // only cost host time: off by default, opt-in with P24_F_SPLIT.
-    int nsplit = (flags & P24_F_SPLIT) && !g_prof_on ? (B >= 16 ? 4 : (B >= 4 ? 2 : 1)) : 1;
-    if (nsplit > P24_MAX_SPLIT) nsplit = P24_MAX_SPLIT;
-    static cudaStream_t xs[P24_MAX_SPLIT] = {nullptr, nullptr, nullptr, nullptr};
-    static cudaEvent_t ev_fork = nullptr, ev_join[P24_MAX_SPLIT] = {nullptr, nullptr, nullptr, nullptr};
-    if (nsplit > 1 && !ev_fork) {
-        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-        for (int q = 1; q < P24_MAX_SPLIT; ++q) {
-            cudaStreamCreateWithFlags(&xs[q], cudaStreamNonBlocking);
-            cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming);
-        }
-    }
     cudaError_t e = cudaSuccess;
-    if (nsplit > 1) {
-        e = cudaEventRecord(ev_fork, st);
+    prof_mark(0, st);
+    // k_pass never waits for its predecessor in the stream, so it is launched in plain stream order
+    e = launch(k_pass, dim3(p.tiles + p.wctas, B), dim3(P24_THREADS), dyn, st, false, p);
+    if (e != cudaSuccess) return (int)e;
+    prof_mark(1, st);
+    e = launch(k_match, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
+    if (e != cudaSuccess) return (int)e;
+    prof_mark(2, st);
+    {
+        const int gx = (P24_TOPK * Lmax + P24_WARPS - 1) / P24_WARPS;
+        e = launch(k_resolve_loss, dim3(gx < RESOLVE_GRID_X ? gx : RESOLVE_GRID_X, B), dim3(P24_THREADS), 0, st, pdl, p);
         if (e != cudaSuccess) return (int)e;
     }
-    for (int q = 0; q < nsplit; ++q) {
-        cudaStream_t sq = q == 0 ? st : xs[q];
-        if (q > 0) {
-            e = cudaStreamWaitEvent(sq, ev_fork, 0);
-            if (e != cudaSuccess) return (int)e;
-        }
-        p.slice = q;
-        p.b0 = (int)((long long)B * q / nsplit);
-        p.nb = (int)((long long)B * (q + 1) / nsplit) - p.b0;
-        if (p.nb <= 0) continue;
-        prof_mark(0, sq);
-        e = launch(k_gt_prep, dim3(p.nb), dim3(PREP_THREADS), 0, sq, pdl, p);
-        if (e != cudaSuccess) return (int)e;
-        prof_mark(1, sq);
-        e = launch(k_anchor_pass, dim3(p.tiles, p.nb), dim3(P24_THREADS), dyn, sq, pdl, p);
-        if (e != cudaSuccess) return (int)e;
-        prof_mark(2, sq);
-        e = launch(k_dyn_k, dim3(Lmax, p.nb), dim3(MATCH_THREADS), 0, sq, pdl, p);
-        if (e != cudaSuccess) return (int)e;
-        prof_mark(3, sq);
-        {
-            const int items = p.nb * Lmax * EVAL_SPLIT;
-            const int cap = (4 * n_sm + nsplit - 1) / nsplit;  // persistent: the slices together fill one wave
-            e = launch(k_window_eval, dim3(items < cap ? items : cap), dim3(P24_THREADS), 0, sq, pdl, p);
-            if (e != cudaSuccess) return (int)e;
-        }
-        prof_mark(4, sq);
-        e = launch(k_select, dim3(Lmax, p.nb), dim3(MATCH_THREADS), 0, sq, pdl, p);
-        if (e != cudaSuccess) return (int)e;
-        prof_mark(5, sq);
-        {
-            const int gx = (P24_TOPK * Lmax + P24_WARPS - 1) / P24_WARPS;
-            e = launch(k_resolve_loss, dim3(gx < RESOLVE_GRID_X ? gx : RESOLVE_GRID_X, p.nb), dim3(P24_THREADS), 0, sq, pdl, p);
-            if (e != cudaSuccess) return (int)e;
-        }
-        prof_mark(6, sq);
-        if (q > 0) {
-            e = cudaEventRecord(ev_join[q], sq);
-            if (e != cudaSuccess) return (int)e;
-        }
-    }
-    for (int q = 1; q < nsplit; ++q) {
-        e = cudaStreamWaitEvent(st, ev_join[q], 0);
-        if (e != cudaSuccess) return (int)e;
-    }
+    prof_mark(3, st);
     return (int)cudaGetLastError();
 }
 
@@ -1697,6 +1684,7 @@ extern "C" int p24_profile_enable(int on) {
 
 extern "C" int p24_profile_read(float* h_ms6) {
     if (!g_prof_have || !h_ms6) return P24_E_BADARG;
+    for (int i = 0; i < 6; ++i) h_ms6[i] = 0.0f;
     cudaError_t e = cudaEventSynchronize(g_prof_ev[N_STAGES]);
     if (e != cudaSuccess) return (int)e;
     for (int i = 0; i < N_STAGES; ++i) {

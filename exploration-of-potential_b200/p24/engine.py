@@ -8,6 +8,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, Sequence, Tuple
 
+import ctypes as C
+
 import torch
 
 from . import lib as _lib
@@ -16,7 +18,6 @@ F_NO_PRUNE = 1   # evaluate every polygon angle sum exactly (self-check of the g
 F_NO_FILTER = 2  # evaluate every pair value exactly (self-check of the top-10 bound filter)
 F_ALL_ROWS = 4   # every label row is a GT (per-image API)
 F_NO_PDL = 8     # plain stream-ordered launches
-F_SPLIT = 16     # concurrent batch slices on internal streams (opt-in)
 
 
 @dataclass
@@ -43,20 +44,47 @@ def _check_cuda_f32(t: torch.Tensor, name: str):
 
 
 class GridCache:
-    """Concatenated x_shifts / y_shifts / expanded_strides (losses.py:193-195), cached per 3-list."""
+    """Concatenated x_shifts / y_shifts / expanded_strides (losses.py:193-195) and the level structure of the grid
+    (anchor offset, width, height per level), cached per 3-list.  Building an entry reads the grids back once
+    (one host sync per new grid, none afterwards)."""
 
     def __init__(self):
         self._key = None
         self._val = None
 
-    def get(self, x_shifts, y_shifts, strides, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    @staticmethod
+    def _levels(gx: torch.Tensor, gy: torch.Tensor, gs: torch.Tensor):
+        """Level table of a grid laid out as the head builds it (yolo_head_24p.py:222-230): a new level starts
+        wherever the stride value changes; inside a level the anchors are the cells of a W x H grid, row-major."""
+        x, y, st = gx.cpu(), gy.cpu(), gs.cpu()
+        A = x.numel()
+        cuts = [0] + (torch.nonzero(st[1:] != st[:-1]).flatten() + 1).tolist() + [A]
+        levels = []
+        for off, end in zip(cuts[:-1], cuts[1:]):
+            n = end - off
+            W = int(x[off:end].max().item()) + 1
+            H = int(y[off:end].max().item()) + 1
+            idx = torch.arange(n)
+            ok = (W * H == n and torch.equal(x[off:end], (idx % W).to(x.dtype))
+                  and torch.equal(y[off:end], (idx // W).to(y.dtype)))
+            if not ok:
+                raise _lib.P24Error("x_shifts / y_shifts / expanded_strides do not form per-level row-major grids "
+                                    "(yolo_head_24p.py:222-230): unsupported anchor layout")
+            levels.append((off, W, H, 0))
+        if len(levels) > 4:
+            raise _lib.P24Error(f"{len(levels)} feature levels: at most 4 are supported")
+        arr = (C.c_int32 * (4 * len(levels)))(*[v for lv in levels for v in lv])
+        return arr, len(levels)
+
+    def get(self, x_shifts, y_shifts, strides, device):
         if torch.is_tensor(x_shifts):
             x_shifts, y_shifts, strides = [x_shifts], [y_shifts], [strides]
         key = tuple((t.data_ptr(), tuple(t.shape), t._version) for t in list(x_shifts) + list(y_shifts) + list(strides))
         if key != self._key:
             cat = [torch.cat([t.reshape(1, -1) for t in lst], 1).reshape(-1).to(device=device, dtype=torch.float32)
                    .contiguous() for lst in (x_shifts, y_shifts, strides)]
-            self._key, self._val = key, tuple(cat)
+            lv, nlev = self._levels(*cat)
+            self._key, self._val = key, (cat[0], cat[1], cat[2], lv, nlev)
         return self._val
 
 
@@ -100,7 +128,7 @@ class SimOTAEngine:
         B, A, _ = outputs.shape
         Lmax = labels.shape[1]
         dev = outputs.device
-        gx, gy, gs = self.grids.get(x_shifts, y_shifts, strides, dev)
+        gx, gy, gs, lv, nlev = self.grids.get(x_shifts, y_shifts, strides, dev)
         if gx.numel() != A:
             raise IndexError("grid length does not match the number of anchors")
         if out is None:
@@ -125,7 +153,7 @@ class SimOTAEngine:
             code = lib.p24_simota_loss_batch(
                 outputs.data_ptr(), outputs.stride(0), outputs.stride(1), B, A, num_classes,
                 labels.data_ptr(), labels.stride(0), labels.stride(1), Lmax,
-                gx.data_ptr(), gy.data_ptr(), gs.data_ptr(),
+                gx.data_ptr(), gy.data_ptr(), gs.data_ptr(), lv, nlev,
                 out.fg_mask.data_ptr(), out.matched_gt.data_ptr(), out.pred_iou.data_ptr(),
                 out.num_fg.data_ptr(), out.num_gt.data_ptr(), out.dyn_k.data_ptr(),
                 out.sums28.data_ptr() if out.sums28 is not None else None,

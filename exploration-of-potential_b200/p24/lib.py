@@ -12,6 +12,7 @@ import os
 from . import build as _build
 
 _LIB = None
+ABI_VERSION = 2
 
 c_f32p = C.c_void_p  # device pointers travel as integers
 c_ptr = C.c_void_p
@@ -23,6 +24,7 @@ _PROTOS = {
     "p24_simota_loss_batch": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                         c_ptr, C.c_int64, C.c_int64, C.c_int,
                                         c_ptr, c_ptr, c_ptr,
+                                        C.POINTER(C.c_int32), C.c_int,
                                         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr,
                                         c_ptr, C.c_size_t, C.c_uint32, c_ptr]),
@@ -72,7 +74,7 @@ def load(path: str | None = None):
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.p24_abi_version() != 1:
+    if lib.p24_abi_version() != ABI_VERSION:
         raise P24Error("libp24_b200 ABI version mismatch")
     _LIB = lib
     return lib

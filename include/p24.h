@@ -27,10 +27,9 @@
 extern "C" {
 #endif
 
-#define P24_ABI_VERSION 1
+#define P24_ABI_VERSION 2
 #define P24_RAYS 24
 #define P24_TOPK 10        /* n_candidate_k cap, losses.py:452 */
-#define P24_VCAP 80        /* capacity of a GT's centre-window list (<= 75 by construction) */
 
 #define P24_E_BADARG (-1)
 #define P24_E_WORKSPACE (-2)
@@ -39,7 +38,6 @@ extern "C" {
 /* p24_assign_batch flags */
 #define P24_F_NO_PRUNE 1u      /* evaluate every polygon angle sum exactly (self-check of the pruning) */
 #define P24_F_NO_FILTER 2u     /* evaluate every pair value exactly (self-check of the top-k filter) */
-#define P24_F_SPLIT 16u        /* cut the batch into slices whose kernel chains run concurrently on internal streams */
 #define P24_F_NO_PDL 8u        /* plain stream-ordered launches instead of programmatic dependent launch */
 #define P24_F_ALL_ROWS 4u      /* every label row is a GT (per-image API: the caller passes num_gt rows) */
 
@@ -59,6 +57,10 @@ int p24_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
  *   outputs  [B, A, 27+nc] decoded head output (strides img_stride / row_stride, channel stride 1)
  *   labels   [B, Lmax, 51]  (cls, cx, cy, 24 x (x, y)); valid rows first, zero padded
  *   x_shifts, y_shifts, strides: [A] (the head's 3-lists concatenated, losses.py:193-195)
+ *   h_levels [n_levels][4] HOST int32 (anchor offset, grid width, grid height, 0): the level structure of the grid as
+ *            the head builds it (yolo_head_24p.py:222-230): anchors [offset, offset + W*H) of a level are its W x H cells,
+ *            row-major, x_shifts = column, y_shifts = row, one stride value.  The levels must tile [0, A) in order
+ *            (n_levels <= 4).  The centre-window anchors of a GT are enumerated from it instead of being searched.
  * writes
  *   fg_mask    [B, A] uint8   final foreground mask (losses.py:486)
  *   matched_gt [B, A] int32   GT row matched to the anchor, -1 for background (losses.py:488)
@@ -81,6 +83,7 @@ int p24_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A, int num_classes,
                           const float* labels, int64_t lab_img_stride, int64_t lab_row_stride, int Lmax,
                           const float* x_shifts, const float* y_shifts, const float* strides,
+                          const int32_t* h_levels, int n_levels,
                           uint8_t* fg_mask, int32_t* matched_gt, float* pred_iou,
                           int32_t* num_fg, int32_t* num_gt, int32_t* dyn_k, float* sums28,
                           float* state26, float* result54, float* weights_n27,
@@ -146,9 +149,10 @@ int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_str
                     int32_t* cand_count, int32_t* det_count, float* det_rows, int32_t* keep_idx, float* rect_debug,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its six
- * kernels (gt_prep, anchor_pass, dyn_k, window_eval, select, resolve_loss) on the launching stream; p24_profile_read waits
- * for the last call and returns the six durations in milliseconds into a HOST array.  Process-global. */
+/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its three
+ * kernels (k_pass, k_match, k_resolve_loss) on the launching stream and launches them in plain stream order;
+ * p24_profile_read waits for the last call and returns the durations in milliseconds into h_ms6[0..2]
+ * (h_ms6[3..5] = 0) of a HOST array.  Process-global. */
 int p24_profile_enable(int on);
 int p24_profile_read(float* h_ms6);
 
