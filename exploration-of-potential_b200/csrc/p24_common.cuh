@@ -53,8 +53,12 @@ struct P24Workspace {
     size_t claimed;     // [B, 10 * Lmax] int   anchors claimed by at least one GT (arrival order)
     size_t nclaimed;    // [B] int
     size_t acc_fix;     // [B, 28] int64        fixed-point loss sums of the image (zero between calls)
-    size_t ticket;      // [1 + B] unsigned: batch counter, one counter per image (zero between calls)
+    size_t ticket;      // [2 + B] unsigned: batch counter, one counter per image, work-queue head of k_pass (zero between calls)
     size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
+    size_t slow_n;      // [1] int     GTs published for the cooperative exact top-10 path (zero between calls)
+    size_t slow_ctl;    // [B, Lmax, 4] int   ready, next chunk, chunks done, kept values (zero between calls)
+    size_t slow_desc;   // [B, Lmax, 8] float image, GT, candidate count, T, tau
+    size_t slow_ev;     // [B, Lmax, 512] float  kept exact values
     size_t total;
 };
 
@@ -67,9 +71,13 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     const size_t BA = (size_t)B * (size_t)A;
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
-    w.ticket = off;     off = p24_align(off + (size_t)(1 + B) * sizeof(unsigned));
+    w.ticket = off;     off = p24_align(off + (size_t)(2 + B) * sizeof(unsigned));
     w.acc_fix = off;    off = p24_align(off + (size_t)B * 28 * sizeof(long long));
     w.err_flag = off;   off = p24_align(off + sizeof(int));
+    w.slow_n = off;     off = p24_align(off + sizeof(int));
+    w.slow_ctl = off;   off = p24_align(off + BL * 4 * sizeof(int));
+    w.slow_desc = off;  off = p24_align(off + BL * 8 * sizeof(float));
+    w.slow_ev = off;    off = p24_align(off + BL * 512 * sizeof(float));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
     w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
     w.ccount = off;     off = p24_align(off + NB * sizeof(int));

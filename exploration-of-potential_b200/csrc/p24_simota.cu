@@ -59,6 +59,10 @@ struct Params {
     float* sval;
     float* wtab;
     float* tbox;
+    int* slow_n;      // published GTs of the exact top-10 path
+    int* slow_ctl;    // [B * Lmax][4]: ready, next chunk, chunks done, kept values
+    float* slow_desc; // [B * Lmax][8]: image, GT, candidate count, T, tau
+    float* slow_ev;   // [B * Lmax][SLOW_EV_CAP]
     int* ccount;
     int* claim_cnt;
     int* claim_gt;
@@ -70,7 +74,6 @@ struct Params {
     int* err_flag;
     unsigned flags;
     int tiles;
-    int wctas;  // centre-window CTAs per image in k_pass
     int nlev;
     Level lev[P24_MAX_LEVELS];
 };
@@ -232,6 +235,26 @@ __device__ __forceinline__ void warp_gt_record(const float* __restrict__ row, fl
     }
 }
 
+// k_gt_prep: one CTA per image.  It lets k_pass launch at once (programmatic dependent launch): k_pass's CTAs stage
+// their first rows while this kernel runs and wait for it only before they read the records.
+#define PREP_THREADS 256
+__global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(Params p) {
+    pdl_trigger();
+    TMARK(3, blockIdx.x, 0);
+    __shared__ int s_n;
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+    const float* lab = p.labels + (long long)b * p.lab_img_stride;
+    const int n = block_count_labels(p, lab, &s_n);
+    if (tid == 0) {
+        p.num_gt[b] = n;
+        p.num_fg[b] = 0;
+        p.nclaimed[b] = 0;
+    }
+    for (int g = warp; g < n; g += PREP_THREADS / 32)
+        warp_gt_record(lab + (long long)g * p.lab_row_stride, p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC);
+    TMARK(3, blockIdx.x, 1);
+}
+
 // -------------------------------------------------------------------------------------------
 // shared device helpers
 // -------------------------------------------------------------------------------------------
@@ -373,9 +396,9 @@ struct AnchorShared {
     int nitems, n;
 };
 
-__device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, AnchorShared& S) {
+__device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, AnchorShared& S, int b, int tile, bool first) {
     float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC]
-    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int a = tile * P24_THREADS + tid;
     const bool active = a < p.A;
@@ -400,24 +423,17 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
     }
     if (tid == 0) S.nitems = 0;
     S.cand[tid] = 0;
-    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 0);
-    const float* lab = p.labels + (long long)b * p.lab_img_stride;
-    const int n = block_count_labels(p, lab, &S.n);
-    for (int g = warp; g < n; g += P24_WARPS) warp_gt_record(lab + (long long)g * p.lab_row_stride, s_gt + g * GT_REC);
-    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 1);
+    TMARK(0, b * p.tiles + tile, 0);
+    if (first) pdl_wait();  // the records come from k_gt_prep
+    TMARK(0, b * p.tiles + tile, 1);
+    const int n = p.num_gt[b];
+    {
+        const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
+        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) s_dyn4[i] = gsrc[i];
+    }
     cp_async_wait_all();
     __syncthreads();
-    if (tile == 0) {
-        // the image's records for the kernels that follow
-        float4* gdst = reinterpret_cast<float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
-        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) gdst[i] = s_dyn4[i];
-        if (tid == 0) {
-            p.num_gt[b] = n;
-            p.num_fg[b] = 0;
-            p.nclaimed[b] = 0;
-        }
-    }
-    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 2);
+    TMARK(0, b * p.tiles + tile, 2);
 
     float pcx = 0.f, pcy = 0.f, rpmax = 0.f, rpmin = INFINITY, rpsum = 0.f, rp2sum = 0.f, obj = 0.f;
     const float xc = p24_anchor_centre(xs, st);
@@ -500,7 +516,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
     }
     if (mine) S.cand[tid] = 1;
     __syncthreads();
-    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 3);
+    TMARK(0, b * p.tiles + tile, 3);
     const int nitems = min(S.nitems, ITEM_CAP);
     for (int i = tid; i < nitems; i += P24_THREADS) {
         const unsigned it = s_items[i];
@@ -518,7 +534,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
     }
     __syncthreads();
 
-    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 4);
+    TMARK(0, b * p.tiles + tile, 4);
     // ---- compacted candidate list of the tile (deterministic order) + per-anchor scratch reset ----------
     const bool cand = active && (n > 0) && (cheap || S.cand[tid]);
     // ---- seeds of the top-10 search: lane g of every warp ranks the warp's candidates for GT g by the first-order
@@ -681,7 +697,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
         for (int w = 0; w < P24_WARPS; ++w) t += S.red[w];
         p.obj_part[blk] = t;
     }
-    TMARK(0, blockIdx.y * gridDim.x + blockIdx.x, 5);
+    TMARK(0, b * p.tiles + tile, 5);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -700,6 +716,7 @@ __device__ __forceinline__ void claim_anchor(const Params& p, int b, int a, int 
 }
 
 #define HIT_CAP 3072
+#define SLOW_EV_CAP 512  // kept values per published GT (overflow -> brute force)
 #define MATCH_WCAP (25 * P24_MAX_LEVELS)  // at most 5 x 5 cells per level pass the window test
 #define MAX_TILES 1024  // candidate counts of an image kept in shared memory (A <= 262144)
 
@@ -803,99 +820,84 @@ __device__ __noinline__ float topk_sum_bruteforce(const Params& p, MatchShared& 
     return ksum;
 }
 
-// Exact top-10 sum when the bracket is not conclusive (about 1 GT in 200):
+// Exact top-10 sum when the bracket is not conclusive (about 1 GT in 100), as cooperative work of the whole grid:
 //  1. tau: the largest t with H(t) <= T - eps (T = 10th best seed value), two rounds of 32-way search by one warp;
-//     candidates with t = rpmax + d < tau cannot reach T (one compare per candidate);
-//  2. the others get the per-ray bound ub (8-lane groups, 3 rays per lane); those with ub >= T are evaluated exactly
-//     on the spot and kept when they reach T;
-//  3. the 10 largest kept values (the best seeds are among them) are summed in descending order (torch.topk order).
-__device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S, int b) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+//     candidates with t = rpmax + d < tau cannot reach T (one compare per candidate)               [the GT's own CTA]
+//  2. per chunk of tiles: the survivors of the scalar filter get the per-ray bound ub (one thread each); those with
+//     ub >= T are evaluated exactly (8-lane groups) and kept in the GT's global list when they reach T  [any CTA]
+//  3. the 10 largest kept values (the best seeds are among them) are summed in descending order (torch.topk
+//     order), then the GT's selection runs                                            [the CTA that ends the last chunk]
+// The GT's CTA publishes a descriptor; every CTA of k_match that has finished its own GT takes chunks from the
+// published GTs (and so does the publisher): nobody ever waits for anybody.
+__device__ __forceinline__ float warp_tau(const float* rec, float T, float tmax) {
+    const int lane = threadIdx.x & 31;
+    const float target = T - 2e-5f;
+    float lo = 0.0f, hi = tmax * 1.001f + 1.0f;
+    float tau = P24_NEG_INF;
+    if (bound_H_thread(rec, lo) <= target) {
+#pragma unroll 1
+        for (int round = 0; round < 2; ++round) {
+            const float step = (hi - lo) * (1.0f / 32.0f);
+            const float tj = lo + step * (float)(lane + 1);
+            const bool ok = bound_H_thread(rec, tj) <= target;     // monotone in t: a prefix of lanes
+            const int nok = __popc(__ballot_sync(0xffffffffu, ok));
+            const float nlo = lo + step * (float)nok;
+            hi = (nok == 32) ? hi : (nlo + step);
+            lo = nlo;
+        }
+        tau = lo - 0.01f - 1e-4f * lo;
+    }
+    return tau;
+}
+
+// tiles per chunk: at most 12 (12 * 256 candidates fit the hit list), about 16 chunks per GT
+__device__ __forceinline__ int slow_tiles_per_chunk(int tiles) { return min(12, (tiles + 15) / 16); }
+
+// S.rec / S.ccount <- GT g of image b.  Contains __syncthreads().
+__device__ __forceinline__ void load_gt_context(const Params& p, MatchShared& S, int b, int g) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    if (tid < GT_REC) S.rec[tid] = p.gt_rec[((long long)b * p.Lmax + g) * GT_REC + tid];
+    for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) S.ccount[tl] = p.ccount[(long long)b * p.tiles + tl];
+    __syncthreads();
+}
+
+// step 2 for chunk c of the published GT `slot` (its context is in S); returns true in the CTA that completes the GT's
+// last chunk
+__device__ __noinline__ bool slow_chunk(const Params& p, MatchShared& S, int slot, int c, int b, float T, float tau) {
+    const int tid = threadIdx.x;
     const unsigned gm = group_mask();
     const int grp = tid >> 3, sub = tid & 7;
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     const float* img = p.outputs + (long long)b * p.img_stride;
-    const float T = S.T;
-    if (warp == 0) {
-        const float target = T - 2e-5f;
-        float lo = 0.0f, hi = S.tmax * 1.001f + 1.0f;
-        float tau = P24_NEG_INF;
-        if (bound_H_thread(S.rec, lo) <= target) {
-#pragma unroll 1
-            for (int round = 0; round < 2; ++round) {
-                const float step = (hi - lo) * (1.0f / 32.0f);
-                const float tj = lo + step * (float)(lane + 1);
-                const bool ok = bound_H_thread(S.rec, tj) <= target;     // monotone in t: a prefix of lanes
-                const int nok = __popc(__ballot_sync(0xffffffffu, ok));
-                const float nlo = lo + step * (float)nok;
-                hi = (nok == 32) ? hi : (nlo + step);
-                lo = nlo;
-            }
-            tau = lo - 0.01f - 1e-4f * lo;
-        }
-        if (lane == 0) {
-            S.tau = tau;
-            S.nhit = 0;
-            S.nev = 0;
-            S.overflow = 0;
-        }
-    }
+    const int tpc = slow_tiles_per_chunk(p.tiles);
+    const int t0 = c * tpc, t1 = min(p.tiles, t0 + tpc);
     __syncthreads();
-    TMARK(1, b * 20 + (int)blockIdx.x, 12);
-    const float tau = S.tau;
-    // 1. scalar filter: a tile whose box bound t_tile is below tau holds no survivor at all; the candidates of the
-    // other tiles are tested with independent loads (flat index over the passing tiles)
-    int* plist = reinterpret_cast<int*>(S.ev);  // passing tiles (S.ev is not in use yet; tiles <= MAX_TILES <= HIT_CAP)
-    if (tid == 0) S.k = 0;  // number of passing tiles (S.k is rewritten by the caller afterwards)
+    if (tid == 0) S.nhit = 0;
     __syncthreads();
     {
         const float4* tb = reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
-        for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) {
-            if (S.ccount[tl] == 0) continue;
+        for (int tl = t0; tl < t1; ++tl) {
+            const int cc = S.ccount[tl];
+            if (cc == 0) continue;
             const float4 bx = tb[2 * tl];
             const float rzm = tb[2 * tl + 1].x;
             const float fx = fmaxf(fabsf(gcx - bx.x), fabsf(gcx - bx.y));
             const float fy = fmaxf(fabsf(gcy - bx.z), fabsf(gcy - bx.w));
             const float ttile = rzm + sqrtf(fmaf(fx, fx, fy * fy)) * 1.00001f;
-            if (!(ttile < tau)) plist[atomicAdd(&S.k, 1)] = tl;  // (NaN / inf boxes pass)
-        }
-    }
-    __syncthreads();
-    {
-        const int npass = S.k;
-        const int nslot = npass * P24_THREADS;
-        for (int base = tid; base < nslot; base += 8 * MATCH_THREADS) {
-            float4 q[8];
-            bool ok[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i0 = base + u * MATCH_THREADS;
-                ok[u] = false;
-                if (i0 < nslot) {
-                    const int tl = plist[i0 >> 8], rk = i0 & 255;
-                    ok[u] = rk < S.ccount[tl];
-                    if (ok[u]) q[u] = p.clist[((long long)b * p.tiles + tl) * P24_THREADS + rk];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (!ok[u]) continue;
-                const float dx = gcx - q[u].x, dy = gcy - q[u].y;
-                const float t = q[u].z + sqrtf(fmaf(dx, dx, dy * dy));
-                if (t >= tau || !(t == t)) {
-                    const int slot = atomicAdd(&S.nhit, 1);
-                    if (slot < HIT_CAP) S.hit[slot] = __float_as_int(q[u].w);
-                    else S.overflow = 1;
-                }
+            if (ttile < tau) continue;  // no survivor in this tile (NaN / inf boxes pass)
+            if (tid < cc) {
+                const float4 q = p.clist[((long long)b * p.tiles + tl) * P24_THREADS + tid];
+                const float dx = gcx - q.x, dy = gcy - q.y;
+                const float t = q.z + sqrtf(fmaf(dx, dx, dy * dy));
+                if (t >= tau || !(t == t)) S.hit[atomicAdd(&S.nhit, 1)] = __float_as_int(q.w);  // <= 12 * 256 < HIT_CAP
             }
         }
     }
     __syncthreads();
-    TMARK(1, b * 20 + (int)blockIdx.x, 13);
-    if (S.overflow) return NAN;  // caller falls back to brute force
     const int nhit = S.nhit;
-    // 2. per-ray bound, one thread per survivor (24 independent loads in flight); the anchor is tagged when the
-    // bound excludes it
+    // per-ray bound, one thread per survivor (24 independent loads in flight); the anchor is tagged when the bound
+    // excludes it
     for (int i = tid; i < nhit; i += MATCH_THREADS) {
         const float* row = img + (long long)S.hit[i] * p.row_stride;
         const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
@@ -906,27 +908,47 @@ __device__ __noinline__ float topk_sum_filtered(const Params& p, MatchShared& S,
         if (ub < T) S.hit[i] = -1;
     }
     __syncthreads();
-    TMARK(1, b * 20 + (int)blockIdx.x, 14);
-    // 3. exact value of what is left (8-lane groups); values that reach T are kept
+    // exact value of what is left (8-lane groups); values that reach T go to the GT's list
+    float* ev = p.slow_ev + (long long)slot * SLOW_EV_CAP;
+    int* ctl = p.slow_ctl + 4 * slot;  // ready, next, done, nev
     for (int i0 = 0; i0 < nhit; i0 += MATCH_GROUPS) {
         const int i = i0 + grp;
         const int a = i < nhit ? S.hit[i] : -1;
         if (a < 0) continue;
         const float v = group_pair_value(S.rec, img + (long long)a * p.row_stride, gm);
-        if (sub == 0 && (v >= T || !(v == v))) S.ev[atomicAdd(&S.nev, 1)] = (v == v) ? v : P24_POS_INF;  // nev <= nhit
+        if (sub == 0 && (v >= T || !(v == v))) {
+            const int at = atomicAdd(&ctl[3], 1);
+            if (at < SLOW_EV_CAP) ev[at] = (v == v) ? v : P24_POS_INF;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int nchunk = (p.tiles + tpc - 1) / tpc;
+        S.overflow = (atomicAdd(&ctl[2], 1) == nchunk - 1) ? 1 : 0;
     }
     __syncthreads();
-    TMARK(1, b * 20 + (int)blockIdx.x, 15);
-    if (S.nev < P24_TOPK) return NAN;
-    {
-        // rank counting, one thread per kept value: the 10 largest land in S.top in descending order
-        const int nev = S.nev;
-        for (int i = tid; i < nev; i += MATCH_THREADS) {
-            const float vi = S.ev[i];
-            int rank = 0;
-            for (int j = 0; j < nev; ++j) rank += kv_gt(S.ev[j], j, vi, i) ? 1 : 0;
-            if (rank < P24_TOPK) S.top[rank] = vi;
-        }
+    return S.overflow != 0;
+}
+
+// step 3: the sum of the 10 largest kept values, or NaN when the list cannot be used (overflow, fewer than 10 values):
+// the caller falls back to brute force
+__device__ __noinline__ float slow_topk_sum(const Params& p, MatchShared& S, int slot) {
+    const int tid = threadIdx.x;
+    __threadfence();
+    const int nev = __ldcg(p.slow_ctl + 4 * slot + 3);
+    if (nev > SLOW_EV_CAP || nev < P24_TOPK) return NAN;
+    const float* ev = p.slow_ev + (long long)slot * SLOW_EV_CAP;
+    __syncthreads();
+    for (int i = tid; i < nev; i += MATCH_THREADS) S.ev[i] = __ldcg(ev + i);
+    __syncthreads();
+    // rank counting, one thread per kept value: the 10 largest land in S.top in descending order (ties in the value
+    // do not change the sum)
+    for (int i = tid; i < nev; i += MATCH_THREADS) {
+        const float vi = S.ev[i];
+        int rank = 0;
+        for (int j = 0; j < nev; ++j) rank += kv_gt(S.ev[j], j, vi, i) ? 1 : 0;
+        if (rank < P24_TOPK) S.top[rank] = vi;
     }
     __syncthreads();
     float ksum = 0.0f;
@@ -1005,9 +1027,9 @@ __device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b
 // -------------------------------------------------------------------------------------------
 struct WindowShared {
     float rec[GT_REC];
-    int list[P24_WT_HDR];  // slots that pass the centre-window test
-    int org[2 * P24_MAX_LEVELS];
-    int npair, n;
+    int list[P24_WSLOTS];  // slots of the level that pass the centre-window test
+    int org[2];
+    int npair;
 };
 
 // first cell of the 7-wide block that contains every cell centre within 2.5 strides of c (one cell of slack per side)
@@ -1017,120 +1039,181 @@ __device__ __forceinline__ int window_origin(float c, float st) {
     return (int)v;
 }
 
-__device__ __forceinline__ void window_part(const Params& p, WindowShared& S) {
-    const int b = blockIdx.y, w = blockIdx.x - p.tiles, tid = threadIdx.x;
-    TMARK(4, blockIdx.y * p.wctas + w, 0);
-    const float* lab = p.labels + (long long)b * p.lab_img_stride;
-    const int n = block_count_labels(p, lab, &S.n);
+// one work item: the window of GT g of image b on level l
+__device__ __forceinline__ void window_part(const Params& p, WindowShared& S, int b, int g, int l) {
+    const int tid = threadIdx.x;
     const unsigned gm = group_mask();
     const int grp = tid >> 3, sub = tid & 7;
     const float* img = p.outputs + (long long)b * p.img_stride;
-    const int nslot = P24_WSLOTS * p.nlev;
-    for (int g = w; g < n; g += p.wctas) {
-        __syncthreads();
-        if (tid < 32) warp_gt_record(lab + (long long)g * p.lab_row_stride, S.rec);
-        if (tid == 32) S.npair = 0;
-        __syncthreads();
-        const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
-        float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
-        if (tid < 2 * p.nlev) {
-            const float st = p.strides[p.lev[tid >> 1].off];
-            const int o = window_origin((tid & 1) ? gcy : gcx, st);
-            S.org[tid] = o;
-            tab[P24_WT_HDR + tid] = __int_as_float(o);
-        }
-        __syncthreads();
-        for (int t = tid; t < nslot; t += P24_THREADS) {
-            const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
-            const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
-            const int ix = S.org[2 * l] + sx, iy = S.org[2 * l + 1] + sy;
-            const Level lv = p.lev[l];
-            bool in = false;
-            if (ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
-                const int a = lv.off + iy * lv.W + ix;
-                const float st = p.strides[a];
-                in = p24_in_centre(gcx, gcy, p24_anchor_centre(p.x_shifts[a], st), p24_anchor_centre(p.y_shifts[a], st), st);
-            }
-            tab[t] = P24_POS_INF;
-            if (in) S.list[atomicAdd(&S.npair, 1)] = t;
-        }
-        __syncthreads();
-        const int npair = S.npair;
-        const int c = gt_class(S.rec, p.nc);
-        for (int wi = grp; wi < npair; wi += P24_THREADS / 8) {
-            const int t = S.list[wi];
-            const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
-            const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
-            const int a = p.lev[l].off + (S.org[2 * l + 1] + sy) * p.lev[l].W + (S.org[2 * l] + sx);
-            const float* row = img + (long long)a * p.row_stride;
+    const Level lv = p.lev[l];
+    if (tid < GT_REC) S.rec[tid] = p.gt_rec[((long long)b * p.Lmax + g) * GT_REC + tid];
+    if (tid == GT_REC) S.npair = 0;
+    __syncthreads();
+    const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
+    float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
+    const float lst = p.strides[lv.off];
+    const int ox = window_origin(gcx, lst), oy = window_origin(gcy, lst);
+    if (tid < 2) tab[P24_WT_HDR + 2 * l + tid] = __int_as_float(tid ? oy : ox);
+    if (tid < P24_WSLOTS) {
+        const int sy = tid / P24_WSIDE, sx = tid - sy * P24_WSIDE;
+        const int ix = ox + sx, iy = oy + sy;
+        bool in = false;
+        if (ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
+            const int a = lv.off + iy * lv.W + ix;
             const float st = p.strides[a];
-            const float xs = p.x_shifts[a], ys = p.y_shifts[a];
-            const float pcx = row[0], pcy = row[1], obj = row[26], clsc = row[27 + c];
-            float rp[3], cl[10];
+            in = p24_in_centre(gcx, gcy, p24_anchor_centre(p.x_shifts[a], st), p24_anchor_centre(p.y_shifts[a], st), st);
+        }
+        tab[l * P24_WSLOTS + tid] = P24_POS_INF;
+        if (in) S.list[atomicAdd(&S.npair, 1)] = tid;
+    }
+    __syncthreads();
+    const int npair = S.npair;
+    const int c = gt_class(S.rec, p.nc);
+    for (int wi = grp; wi < npair; wi += P24_THREADS / 8) {
+        const int t = S.list[wi];
+        const int sy = t / P24_WSIDE, sx = t - sy * P24_WSIDE;
+        const int a = lv.off + (oy + sy) * lv.W + (ox + sx);
+        const float* row = img + (long long)a * p.row_stride;
+        const float st = p.strides[a];
+        const float xs = p.x_shifts[a], ys = p.y_shifts[a];
+        const float pcx = row[0], pcy = row[1], obj = row[26], clsc = row[27 + c];
+        float rp[3], cl[10];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) rp[q] = row[2 + sub * 3 + q];
+        for (int q = 0; q < 3; ++q) rp[q] = row[2 + sub * 3 + q];
 #pragma unroll
-            for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
-            const float xc = p24_anchor_centre(xs, st);
-            const float yc = p24_anchor_centre(ys, st);
-            bool inside = true;
-            {
-                // inside the inscribed disc the angle sum is >= 360 (see warp_gt_record): no edge terms needed
-                const float ddx = gcx - xc, ddy = gcy - yc;
-                if (!(fmaf(ddx, ddx, ddy * ddy) < S.rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
-                    float ang = 0.0f;
+        for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
+        const float xc = p24_anchor_centre(xs, st);
+        const float yc = p24_anchor_centre(ys, st);
+        bool inside = true;
+        {
+            // inside the inscribed disc the angle sum is >= 360 (see warp_gt_record): no edge terms needed
+            const float ddx = gcx - xc, ddy = gcy - yc;
+            if (!(fmaf(ddx, ddx, ddy * ddy) < S.rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
+                float ang = 0.0f;
 #pragma unroll 1
-                    for (int q = 0; q < 3; ++q) {
-                        const int k = sub * 3 + q;
-                        const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
-                        ang = ang + edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
-                                               S.rec[GT_VY + k2] - yc);
-                    }
-                    ang = group_sum(ang, gm);
-                    inside = ang >= 350.0f;  // losses.py:588
+                for (int q = 0; q < 3; ++q) {
+                    const int k = sub * 3 + q;
+                    const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
+                    ang = ang + edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
+                                           S.rec[GT_VY + k2] - yc);
                 }
+                ang = group_sum(ang, gm);
+                inside = ang >= 350.0f;  // losses.py:588
             }
-            if (inside) {
-                const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
-                float s = 0.0f;
+        }
+        if (inside) {
+            const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
+            float sm = 0.0f;
 #pragma unroll 1
-                for (int q = 0; q < 3; ++q) s = s + ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
-                s = group_sum(s, gm);
-                const float v = (s / 24.0f) / 2.0f;
-                const float eo1 = 1.0f + expf(-obj);
-                float neg;
-                if (p.nc <= 80) {
-                    float prod = 1.0f;
-                    int nsat = 0;
+            for (int q = 0; q < 3; ++q) sm = sm + ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
+            sm = group_sum(sm, gm);
+            const float v = (sm / 24.0f) / 2.0f;
+            const float eo1 = 1.0f + expf(-obj);
+            float neg;
+            if (p.nc <= 80) {
+                float prod = 1.0f;
+                int nsat = 0;
 #pragma unroll
-                    for (int q = 0; q < 10; ++q)
-                        if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
-                    prod = group_prod(prod, gm);
-                    nsat = group_sum_i(nsat, gm);
-                    neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(row + 27, p.nc, eo1, gm);
-                } else {
-                    neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
-                }
-                float cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
-                if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
-                if (sub == 0) tab[t] = cost;
+                for (int q = 0; q < 10; ++q)
+                    if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
+                prod = group_prod(prod, gm);
+                nsat = group_sum_i(nsat, gm);
+                neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+            } else {
+                neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
             }
+            float cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
+            if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
+            if (sub == 0) tab[l * P24_WSLOTS + t] = cost;
         }
     }
-    TMARK(4, blockIdx.y * p.wctas + w, 1);
 }
 
-// k_pass: blockIdx.x < tiles: anchor tiles; the rest: centre-window CTAs of the same image (blockIdx.y)
+// k_pass: persistent CTAs (one wave) drawing work items from a ticket counter: first the anchor tiles (the long items),
+// then the (GT, level) centre-window items.  Launched as a programmatic dependent of k_gt_prep: the first item's rows
+// are in flight before the CTA waits for the records.
+union PassShared {
+    AnchorShared a;
+    WindowShared w;
+};
+
 __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(Params p) {
     extern __shared__ float4 s_dyn4[];
-    pdl_trigger();  // k_match may become resident (it waits for this grid's completion before it reads anything)
-    if ((int)blockIdx.x < p.tiles) {
-        __shared__ AnchorShared SA;
-        anchor_part(p, s_dyn4, SA);
-    } else {
-        __shared__ WindowShared SW;
-        window_part(p, SW);
+    __shared__ PassShared S;
+    __shared__ int s_item;
+    const int n_anchor = p.B * p.tiles;
+    const int n_item = n_anchor + p.B * p.Lmax * p.nlev;
+    bool first = true;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(&p.ticket[1 + p.B], 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_item) break;
+        if (item < n_anchor) {
+            // image-major order keeps an image's tiles (and its records) together in time
+            anchor_part(p, s_dyn4, S.a, item / p.tiles, item % p.tiles, first);
+            first = false;
+        } else {
+            if (first) {
+                pdl_wait();
+                first = false;
+            }
+            const int wi = item - n_anchor;
+            const int l = wi % p.nlev, bg = wi / p.nlev;
+            const int b = bg / p.Lmax, g = bg - b * p.Lmax;
+            if (g < p.num_gt[b]) {
+                TMARK(4, wi, 0);
+                window_part(p, S.w, b, g, l);
+                TMARK(4, wi, 1);
+            }
+        }
     }
+    pdl_trigger();
+}
+
+// dynamic k is known: record it and select the k smallest costs among the GT's valid pairs (losses.py:460-464), ties ->
+// lower anchor index; spill into the penalised regime when there are fewer valid pairs than k.  The GT's context is in S.
+__device__ __noinline__ void finish_gt(const Params& p, MatchShared& S, int b, int g, int k) {
+    const int tid = threadIdx.x;
+    const int wslot = b * p.Lmax + g;
+    __syncthreads();
+    if (tid == 0) {
+        p.dyn_k[wslot] = k;
+        S.nvalid = 0;
+    }
+    __syncthreads();
+    {
+        const float* tab = p.wtab + (long long)wslot * P24_WT_STRIDE;
+        const int nslot = P24_WSLOTS * p.nlev;
+        for (int t = tid; t < nslot; t += MATCH_THREADS) {
+            const float c = tab[t];
+            if (c < P24_POS_INF) {
+                const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
+                const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+                const int ix = __float_as_int(tab[P24_WT_HDR + 2 * l]) + sx, iy = __float_as_int(tab[P24_WT_HDR + 2 * l + 1]) + sy;
+                const int slot = atomicAdd(&S.nvalid, 1);
+                if (slot < MATCH_WCAP) {
+                    S.wanchor[slot] = p.lev[l].off + iy * p.lev[l].W + ix;
+                    S.wcost[slot] = c;
+                } else {
+                    atomicOr(p.err_flag, 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int nv = min(S.nvalid, MATCH_WCAP);
+    const int take = min(k, nv);
+    if (tid < nv) {
+        const float ci = S.wcost[tid];
+        const int ai = S.wanchor[tid];
+        int before = 0;
+        for (int j = 0; j < nv; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
+        if (before < take) claim_anchor(p, b, ai, g);
+    }
+    if (k > nv) spill_claims(p, S, b, g, nv, k - nv);
+    __syncthreads();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1139,7 +1222,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(Params p) {
 // the k smallest costs of its valid pairs -> claims (rank counting; spill into the penalised regime when the GT
 // has fewer valid anchors than k)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MATCH_THREADS) k_match(Params p) {
+__global__ void __launch_bounds__(MATCH_THREADS, 4) k_match(Params p) {
     const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 #define MCTA (b * 20 + g)
@@ -1242,61 +1325,92 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(Params p) {
     }
     __syncthreads();
     TMARK(1, MCTA, 4);
-    int k;
-    if (S.slow) {
-        float ksum = NAN;
-        if (S.slow == 1) ksum = topk_sum_filtered(p, S, b);
-        if (!(ksum == ksum)) ksum = topk_sum_bruteforce(p, S, b, kc);
-        k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
-        if (k < 1) k = 1;
-    } else {
-        k = S.k;
-    }
-    k = min(k, ncand);  // torch.topk would raise beyond the candidate count; clamp instead
-    if (tid == 0) p.dyn_k[wslot] = k;
-    TMARK(1, MCTA, 5);
 #ifdef P24_TIMING
     if (tid == 0) {
         g_tstamp[1][MCTA][8] = S.slow;
-        g_tstamp[1][MCTA][9] = S.nhit;
-        g_tstamp[1][MCTA][10] = S.nev;
-        g_tstamp[1][MCTA][11] = S.overflow;
+        g_tstamp[1][MCTA][9] = 0;
     }
 #endif
-    // ---- selection: the k smallest costs among the GT's valid pairs (losses.py:460-464), ties -> lower anchor index
-    __syncthreads();
-    if (tid == 0) S.nvalid = 0;
-    __syncthreads();
-    {
-        const float* tab = p.wtab + (long long)wslot * P24_WT_STRIDE;
-        const int nslot = P24_WSLOTS * p.nlev;
-        for (int t = tid; t < nslot; t += MATCH_THREADS) {
-            const float c = tab[t];
-            if (c < P24_POS_INF) {
-                const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
-                const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
-                const int ix = __float_as_int(tab[P24_WT_HDR + 2 * l]) + sx, iy = __float_as_int(tab[P24_WT_HDR + 2 * l + 1]) + sy;
-                const int slot = atomicAdd(&S.nvalid, 1);
-                if (slot < MATCH_WCAP) {
-                    S.wanchor[slot] = p.lev[l].off + iy * p.lev[l].W + ix;
-                    S.wcost[slot] = c;
-                } else {
-                    atomicOr(p.err_flag, 1);
-                }
+    if (S.slow == 1) {
+        // publish the GT: whoever is free takes its chunks
+        if (warp == 0) {
+            const float tau = warp_tau(S.rec, S.T, S.tmax);
+            if (lane == 0) {
+                const int slot = atomicAdd(p.slow_n, 1);
+                float* d = p.slow_desc + 8 * slot;
+                d[0] = __int_as_float(b);
+                d[1] = __int_as_float(g);
+                d[2] = __int_as_float(ncand);
+                d[3] = S.T;
+                d[4] = tau;
+                __threadfence();
+                atomicExch(p.slow_ctl + 4 * slot, 1);
             }
         }
+    } else {
+        int k;
+        if (S.slow) {
+            const float ksum = topk_sum_bruteforce(p, S, b, kc);
+            k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
+            if (k < 1) k = 1;
+        } else {
+            k = S.k;
+        }
+        finish_gt(p, S, b, g, min(k, ncand));  // torch.topk would raise beyond the candidate count; clamp instead
     }
-    __syncthreads();
-    const int nv = min(S.nvalid, MATCH_WCAP);
-    const int take = min(k, nv);
-    if (tid < nv) {
-        const float ci = S.wcost[tid];
-        const int ai = S.wanchor[tid];
-        int before = 0;
-        for (int j = 0; j < nv; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
-        if (before < take) claim_anchor(p, b, ai, g);
+    TMARK(1, MCTA, 5);
+    // ---- help with the published GTs until no chunk is left ----------------------------------------------------------
+    int cur_b = b, cur_g = g;  // the context in S.rec / S.ccount
+    int cursor = 0;
+    const int nchunk = (p.tiles + slow_tiles_per_chunk(p.tiles) - 1) / slow_tiles_per_chunk(p.tiles);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            int found = -1, chunk = 0;
+            const int ns = *(volatile int*)p.slow_n;
+            for (int sidx = cursor; sidx < ns; ++sidx) {
+                volatile int* ctl = p.slow_ctl + 4 * sidx;
+                if (!ctl[0]) continue;  // not published yet: its own CTA will work on it
+                if (ctl[1] >= nchunk) {
+                    if (sidx == cursor) ++cursor;
+                    continue;
+                }
+                const int c = atomicAdd(p.slow_ctl + 4 * sidx + 1, 1);
+                if (c < nchunk) {
+                    found = sidx;
+                    chunk = c;
+                    break;
+                }
+            }
+            S.nvalid = found;
+            S.k = chunk;
+            S.cnt = cursor;
+        }
+        __syncthreads();
+        const int slot = S.nvalid, chunk = S.k;
+        cursor = S.cnt;
+        if (slot < 0) break;
+#ifdef P24_TIMING
+        if (tid == 0) g_tstamp[1][MCTA][9] += 1;
+#endif
+        __threadfence();
+        const float* d = p.slow_desc + 8 * slot;
+        const int sb = __float_as_int(__ldcg(d + 0)), sg = __float_as_int(__ldcg(d + 1));
+        const int sncand = __float_as_int(__ldcg(d + 2));
+        const float sT = __ldcg(d + 3), stau = __ldcg(d + 4);
+        if (sb != cur_b || sg != cur_g) {
+            load_gt_context(p, S, sb, sg);
+            cur_b = sb;
+            cur_g = sg;
+        }
+        if (slow_chunk(p, S, slot, chunk, sb, sT, stau)) {
+            float ksum = slow_topk_sum(p, S, slot);
+            if (!(ksum == ksum)) ksum = topk_sum_bruteforce(p, S, sb, min(P24_TOPK, sncand));
+            int k = (int)ksum;
+            if (k < 1) k = 1;
+            finish_gt(p, S, sb, sg, min(k, sncand));
+        }
     }
-    if (k > nv) spill_claims(p, S, b, g, nv, k - nv);
     TMARK(1, MCTA, 6);
 }
 
@@ -1525,6 +1639,10 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     if (tid < 28) p.sums28[tid] = s_sums[tid];
     if (tid == 0) {
         p.ticket[0] = 0u;  // ready for the next call
+        p.ticket[1 + p.B] = 0u;
+        const int ns = *p.slow_n;
+        for (int i = 0; i < 4 * ns; ++i) p.slow_ctl[i] = 0;
+        *p.slow_n = 0;
     }
     if (p.state26 && warp == 0) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 6);
@@ -1610,6 +1728,10 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.sval = (float*)(ws + L.sval);
     p.wtab = (float*)(ws + L.wtab);
     p.tbox = (float*)(ws + L.tbox);
+    p.slow_n = (int*)(ws + L.slow_n);
+    p.slow_ctl = (int*)(ws + L.slow_ctl);
+    p.slow_desc = (float*)(ws + L.slow_desc);
+    p.slow_ev = (float*)(ws + L.slow_ev);
     p.ccount = (int*)(ws + L.ccount);
     p.claim_cnt = (int*)(ws + L.claim_cnt);
     p.claim_gt = (int*)(ws + L.claim_gt);
@@ -1621,7 +1743,6 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.err_flag = (int*)(ws + L.err_flag);
     p.flags = flags;
     p.tiles = p24_tiles(A);
-    p.wctas = Lmax < 32 ? Lmax : 32;
     p.nlev = n_levels;
     {
         // the levels must tile [0, A) in order: anchors [off, off + W * H) of level l form a W x H grid
@@ -1646,10 +1767,23 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     }
     const bool pdl = !(flags & P24_F_NO_PDL) && !g_prof_on;
     cudaError_t e = cudaSuccess;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
     prof_mark(0, st);
-    // k_pass never waits for its predecessor in the stream, so it is launched in plain stream order
-    e = launch(k_pass, dim3(p.tiles + p.wctas, B), dim3(P24_THREADS), dyn, st, false, p);
+    // k_gt_prep never waits for its predecessor in the stream, so it is launched in plain stream order
+    e = launch(k_gt_prep, dim3(B), dim3(PREP_THREADS), 0, st, false, p);
     if (e != cudaSuccess) return (int)e;
+    {
+        const long long items = (long long)B * p.tiles + (long long)B * Lmax * n_levels;
+        const long long cap = 4LL * n_sm;  // one wave of persistent CTAs
+        e = launch(k_pass, dim3((unsigned)(items < cap ? items : cap)), dim3(P24_THREADS), dyn, st, pdl, p);
+        if (e != cudaSuccess) return (int)e;
+    }
     prof_mark(1, st);
     e = launch(k_match, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;

@@ -1,4 +1,5 @@
-"""Debug tool (GPU box): per-kernel [first CTA start, last CTA end] of one step from the -DP24_TIMING build."""
+"""Debug tool (GPU box): per-kernel CTA start / end distribution of one step from the -DP24_TIMING build
+(nvcc ... -DP24_TIMING -o p24/_lib/libp24_timing.so).  Usage: timeline.py [flags] [B size G Lmax]"""
 import ctypes, os, sys
 import numpy as np
 ROOT = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
@@ -10,13 +11,15 @@ lib = p24_lib.load(os.path.join(ROOT, "exploration-of-potential_b200", "p24", "_
 p24_lib._LIB = lib
 from p24.losses import Loss_Function
 B, size, G, Lmax = 20, 640, 20, 50
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+if len(sys.argv) > 5:
+    B, size, G, Lmax = [int(x) for x in sys.argv[2:6]]
 dev = "cuda:0"
 sets = [(synth.make_head_outputs(B, size, 80, seed=1 + 100 * i).to(dev),
          synth.make_labels(B, G, Lmax, size, 80, seed=1 + 100 * i, kind="smooth").to(dev)) for i in range(5)]
 xs, ys, ss = synth.make_grids(size)
 g = [[t.to(dev) for t in l] for l in (xs, ys, ss)]
 lf = Loss_Function(80)
-flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 for i in range(10):
     lf.forward_async((g[0], g[1], g[2], sets[i % 5][0], []), sets[i % 5][1], flags=flags)
 torch.cuda.synchronize()
@@ -24,16 +27,42 @@ buf = np.zeros((6, 4096, 20), dtype=np.uint64)
 lib.p24_debug_read_timers.argtypes = [ctypes.c_void_p]
 assert lib.p24_debug_read_timers(buf.ctypes.data) == 0
 t = buf.astype(np.int64)
-order = [(3, "k_gt_prep", 2), (0, "k_anchor_pass", 5), (1, "k_dyn_k", 5), (4, "k_window_eval", 2), (5, "k_select", 2), (2, "k_resolve_loss", 5)]
+# (timer bank, name, slots in order)
+order = [(3, "k_gt_prep", ["start", "end"]),
+         (0, "k_pass/anchor", ["start", "wait", "recs+rows", "gt loop", "items", "end"]),
+         (4, "k_pass/window", ["start", "end"]),
+         (1, "k_match", ["start", "wait", "load", None, "bracket", "own GT", "helping"]),
+         (2, "k_resolve_loss", ["start", "wait", None, None, "entries", "partials"])]
 base = None
-for k, nm, last in order:
+pct = lambda x: "min %7.1f p10 %7.1f p50 %7.1f p90 %7.1f max %7.1f" % tuple(np.percentile(x, [0, 10, 50, 90, 100]))
+for k, nm, slots in order:
     tt = t[k]
+    last = max(i for i, s in enumerate(slots) if s)
     ok = (tt[:, 0] > 0) & (tt[:, last] > 0)
     if not ok.any():
         print(nm, "no data"); continue
-    st, en = tt[ok, 0].min(), tt[ok][:, 1:last + 1].max()
     if base is None:
-        base = st
-    work = tt[ok, last] - tt[ok, 1]
-    print(f"{nm:16s} first start {(st - base) / 1e3:7.1f}  after-wait start {(tt[ok, 1].min() - base) / 1e3:7.1f}  last end {(en - base) / 1e3:7.1f}"
-          f"   CTAs {int(ok.sum()):5d}  per-CTA work mean {work.mean() / 1e3:6.2f} max {work.max() / 1e3:6.2f} us")
+        base = tt[ok, 0].min()
+    print(f"== {nm}: {int(ok.sum())} CTAs")
+    print(f"   start  {pct((tt[ok, 0] - base) / 1e3)}")
+    print(f"   end    {pct((tt[ok, last] - base) / 1e3)}")
+    prev = 0
+    for i in range(1, last + 1):
+        if not slots[i]:
+            continue
+        v = ok & (tt[:, i] > 0) & (tt[:, prev] > 0)
+        d = (tt[v, i] - tt[v, prev]) / 1e3
+        if d.size:
+            print(f"   {slots[i]:10s} mean {d.mean():7.2f}  {pct(d)}")
+        prev = i
+    if k == 1:
+        slow = tt[:, 8]
+        sl = ok & (slow != 0)
+        print("   slow-path CTAs:", int(sl.sum()), "kinds", slow[sl].tolist())
+        nch = tt[ok, 9]
+        print("   chunks taken per CTA: total", int(nch.sum()), "CTAs with any", int((nch > 0).sum()), "max", int(nch.max()))
+        hp = (tt[ok, 6] - tt[ok, 5]) / 1e3
+        for c in range(0, int(nch.max()) + 1):
+            m = nch == c
+            if m.any():
+                print(f"      {c} chunks: {int(m.sum())} CTAs, helping phase mean {hp[m].mean():.2f} max {hp[m].max():.2f} us")
