@@ -738,7 +738,8 @@ struct MatchShared {
     float rec[GT_REC];
     int ccount[MAX_TILES];
     int hit[HIT_CAP];       // slow path: anchors the scalar bound cannot exclude
-    float ev[HIT_CAP];      // slow path: exact values that reach the seed threshold
+    float ev[HIT_CAP];      // slow path: upper bounds of the chunk's survivors / kept exact values
+    float lb[1024];         // slow path: certified lower bounds of the chunk's survivors
     float top[P24_TOPK];
     KV kv[MATCH_WARPS];
     float wmax[MATCH_WARPS];
@@ -850,8 +851,9 @@ __device__ __forceinline__ float warp_tau(const float* rec, float T, float tmax)
     return tau;
 }
 
-// tiles per chunk: at most 12 (12 * 256 candidates fit the hit list), about 16 chunks per GT
-__device__ __forceinline__ int slow_tiles_per_chunk(int tiles) { return min(12, (tiles + 15) / 16); }
+// tiles per chunk: one while the image has at most 64 tiles (the far tiles hold most survivors: fine chunks keep the
+// items even), never more than 12 (12 * 256 candidates fit the hit list)
+__device__ __forceinline__ int slow_tiles_per_chunk(int tiles) { return min(12, (tiles + 63) / 64); }
 
 // S.rec / S.ccount <- GT g of image b.  Contains __syncthreads().
 __device__ __forceinline__ void load_gt_context(const Params& p, MatchShared& S, int b, int g) {
@@ -897,15 +899,40 @@ __device__ __noinline__ bool slow_chunk(const Params& p, MatchShared& S, int slo
     __syncthreads();
     const int nhit = S.nhit;
     // per-ray bound, one thread per survivor (24 independent loads in flight); the anchor is tagged when the bound
-    // excludes it
+    // excludes it.  For a pair whose rays are all apart (the reference's own fp32 comparison) the bound is the value
+    // itself to within 3e-6, so ub - 1e-5 is a certified lower bound: the chunk's 10th largest lower bound replaces T
+    // (any candidate below it has 10 better ones in this chunk alone), which leaves a handful of exact evaluations.
     for (int i = tid; i < nhit; i += MATCH_THREADS) {
         const float* row = img + (long long)S.hit[i] * p.row_stride;
         const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
         float ub = 0.0f;
+        bool apart = true;
 #pragma unroll 8
-        for (int k = 0; k < P24_RAYS; ++k) ub += p24_ray_loss_ub(S.rec[GT_RG + k], row[2 + k], d);
+        for (int k = 0; k < P24_RAYS; ++k) {
+            const float rg = S.rec[GT_RG + k], rp = row[2 + k];
+            ub += p24_ray_loss_ub(rg, rp, d);
+            apart = apart && (d >= rg + rp);
+        }
         ub = ub * (1.0f / 48.0f) + 2e-5f;
+        S.ev[i] = ub;
+        if (i < 1024) S.lb[i] = (apart && ub == ub) ? ub - 3e-5f : P24_NEG_INF;
         if (ub < T) S.hit[i] = -1;
+    }
+    __syncthreads();
+    if (nhit > P24_TOPK && nhit <= 1024) {
+        if (tid == 0) S.tau = T;
+        __syncthreads();
+        for (int i = tid; i < nhit; i += MATCH_THREADS) {
+            const float li = S.lb[i];
+            if (!(li > T)) continue;
+            int rank = 0;
+            for (int j = 0; j < nhit; ++j) rank += kv_gt(S.lb[j], j, li, i) ? 1 : 0;
+            if (rank == P24_TOPK - 1) S.tau = li;  // exactly one thread: ranks are distinct
+        }
+        __syncthreads();
+        const float tl = S.tau;
+        for (int i = tid; i < nhit; i += MATCH_THREADS)
+            if (S.ev[i] < tl) S.hit[i] = -1;
     }
     __syncthreads();
     // exact value of what is left (8-lane groups); values that reach T go to the GT's list
@@ -1187,11 +1214,12 @@ __device__ __noinline__ void finish_gt(const Params& p, MatchShared& S, int b, i
         const float* tab = p.wtab + (long long)wslot * P24_WT_STRIDE;
         const int nslot = P24_WSLOTS * p.nlev;
         for (int t = tid; t < nslot; t += MATCH_THREADS) {
+            const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
             const float c = tab[t];
+            const float ox = tab[P24_WT_HDR + 2 * l], oy = tab[P24_WT_HDR + 2 * l + 1];  // issued with the cost: one round trip
             if (c < P24_POS_INF) {
-                const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
                 const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
-                const int ix = __float_as_int(tab[P24_WT_HDR + 2 * l]) + sx, iy = __float_as_int(tab[P24_WT_HDR + 2 * l + 1]) + sy;
+                const int ix = __float_as_int(ox) + sx, iy = __float_as_int(oy) + sy;
                 const int slot = atomicAdd(&S.nvalid, 1);
                 if (slot < MATCH_WCAP) {
                     S.wanchor[slot] = p.lev[l].off + iy * p.lev[l].W + ix;
@@ -1222,8 +1250,10 @@ __device__ __noinline__ void finish_gt(const Params& p, MatchShared& S, int b, i
 // the k smallest costs of its valid pairs -> claims (rank counting; spill into the penalised regime when the GT
 // has fewer valid anchors than k)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MATCH_THREADS, 4) k_match(Params p) {
-    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+__global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(Params p) {
+    // images vary fastest over the grid: the low GT rows (the real ones: valid rows come first) are dispatched before
+    // the rows beyond num_gt, which leave at once
+    const int g = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 #define MCTA (b * 20 + g)
     if (g < 20) TMARK(1, MCTA, 0);
@@ -1244,6 +1274,16 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) k_match(Params p) {
         S.ccount[tl] = c;
         cnt += c;
     }
+    // everything the bracket reads, staged by all threads in one round trip (S.hit / S.ev are free until a slow path)
+    float4* s_tb = reinterpret_cast<float4*>(S.hit);   // [2 * tiles] float4   (tiles <= 384 here, else read in place)
+    float* s_sv = S.ev;                                // [P24_SEEDS * tiles]
+    const bool staged = p.tiles <= 384;
+    if (staged) {
+        const float4* tbg = reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
+        for (int i = tid; i < 2 * p.tiles; i += MATCH_THREADS) s_tb[i] = tbg[i];
+        const float* svg = p.sval + (long long)wslot * (P24_SEEDS * p.tiles);
+        for (int i = tid; i < P24_SEEDS * p.tiles; i += MATCH_THREADS) s_sv[i] = svg[i];
+    }
     if (tid == 0) S.cnt = 0;
     __syncthreads();
     cnt = warp_sum_i(cnt);
@@ -1258,7 +1298,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) k_match(Params p) {
     if (warp == 0) {
         // largest t = rpmax + d over the candidates, bounded per tile by its box
         float tm = P24_NEG_INF;
-        const float4* tb = reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
+        const float4* tb = staged ? s_tb : reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
         for (int i = lane; i < p.tiles; i += 32) {
             const float4 bx = tb[2 * i];
             const float rzm = tb[2 * i + 1].x;
@@ -1271,7 +1311,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) k_match(Params p) {
         tm = warp_max(tm);
         // the 10 largest seed values, summed in descending order (like the reference sums torch.topk's output)
         const int nseed = P24_SEEDS * p.tiles;
-        const float* sv = p.sval + (long long)wslot * nseed;
+        const float* sv = staged ? s_sv : p.sval + (long long)wslot * nseed;
         float v0 = P24_NEG_INF, v1 = P24_NEG_INF, v2 = P24_NEG_INF, v3 = P24_NEG_INF;  // the lane's 4 best seeds
         for (int i = lane; i < nseed; i += 32) {
             float v = sv[i];
@@ -1365,26 +1405,38 @@ __global__ void __launch_bounds__(MATCH_THREADS, 4) k_match(Params p) {
     const int nchunk = (p.tiles + slow_tiles_per_chunk(p.tiles) - 1) / slow_tiles_per_chunk(p.tiles);
     for (;;) {
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
+            // lanes look at 32 published GTs at a time (one 16-byte load each); the first one with a chunk left is tried
             int found = -1, chunk = 0;
-            const int ns = *(volatile int*)p.slow_n;
-            for (int sidx = cursor; sidx < ns; ++sidx) {
-                volatile int* ctl = p.slow_ctl + 4 * sidx;
-                if (!ctl[0]) continue;  // not published yet: its own CTA will work on it
-                if (ctl[1] >= nchunk) {
-                    if (sidx == cursor) ++cursor;
-                    continue;
-                }
-                const int c = atomicAdd(p.slow_ctl + 4 * sidx + 1, 1);
-                if (c < nchunk) {
-                    found = sidx;
-                    chunk = c;
-                    break;
+            const int ns = *(volatile int*)p.slow_n;  // 0 almost always: one load and out
+            const int cur0 = cursor;
+            for (int base = cur0; base < ns && found < 0; base += 32) {
+                const int sidx = base + lane;
+                int4 c4 = make_int4(0, 0, 0, 0);
+                if (sidx < ns) c4 = __ldcg(reinterpret_cast<const int4*>(p.slow_ctl) + sidx);
+                const bool spent = sidx < ns && c4.x != 0 && c4.y >= nchunk;
+                const bool avail = sidx < ns && c4.x != 0 && c4.y < nchunk;
+                // the cursor moves over the leading run of spent GTs
+                const unsigned sp = __ballot_sync(0xffffffffu, spent);
+                if (base == cur0) cursor = cur0 + (sp == 0xffffffffu ? 32 : __ffs(~sp) - 1);
+                unsigned av = __ballot_sync(0xffffffffu, avail);
+                while (av && found < 0) {
+                    const int l = __ffs(av) - 1;
+                    av &= av - 1;
+                    int c = 0;
+                    if (lane == 0) c = atomicAdd(p.slow_ctl + 4 * (base + l) + 1, 1);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c < nchunk) {
+                        found = base + l;
+                        chunk = c;
+                    }
                 }
             }
-            S.nvalid = found;
-            S.k = chunk;
-            S.cnt = cursor;
+            if (lane == 0) {
+                S.nvalid = found;
+                S.k = chunk;
+                S.cnt = cursor;
+            }
         }
         __syncthreads();
         const int slot = S.nvalid, chunk = S.k;
@@ -1785,7 +1837,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
         if (e != cudaSuccess) return (int)e;
     }
     prof_mark(1, st);
-    e = launch(k_match, dim3(Lmax, B), dim3(MATCH_THREADS), 0, st, pdl, p);
+    e = launch(k_match, dim3(B, Lmax), dim3(MATCH_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     prof_mark(2, st);
     {
