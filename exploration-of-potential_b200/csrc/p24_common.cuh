@@ -46,6 +46,7 @@ struct P24Workspace {
     size_t wtab;        // [B, Lmax, P24_WT_STRIDE] float  SimOTA cost of the GT's centre-window anchors by window slot
                         //                                  (+inf: not in the window / not in the polygon) + the window origins
     size_t tbox;        // [B, tiles, 8] float          bounding box of a tile's candidate centres (xmin, xmax, ymin, ymax), max rpmax
+    size_t seg;         // [B, tiles, 8, 8] float       the same per warp segment of a tile's list + count and first rank
     size_t ccount;      // [B, tiles] int          candidates per tile
     size_t claim_cnt;   // [B, A] int      number of GTs that selected the anchor
     size_t claim_gt;    // [B, A] int      the GT that selected the anchor (meaningful when claim_cnt == 1)
@@ -53,12 +54,8 @@ struct P24Workspace {
     size_t claimed;     // [B, 10 * Lmax] int   anchors claimed by at least one GT (arrival order)
     size_t nclaimed;    // [B] int
     size_t acc_fix;     // [B, 28] int64        fixed-point loss sums of the image (zero between calls)
-    size_t ticket;      // [2 + B] unsigned: batch counter, one counter per image, work-queue head of k_pass (zero between calls)
+    size_t ticket;      // [3 + B] unsigned: batch counter, one counter per image, work-queue head of k_pass, largest num_gt (zero between calls)
     size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
-    size_t slow_n;      // [1] int     GTs published for the cooperative exact top-10 path (zero between calls)
-    size_t slow_ctl;    // [B, Lmax, 4] int   ready, next chunk, chunks done, kept values (zero between calls)
-    size_t slow_desc;   // [B, Lmax, 8] float image, GT, candidate count, T, tau
-    size_t slow_ev;     // [B, Lmax, 512] float  kept exact values
     size_t total;
 };
 
@@ -71,19 +68,16 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     const size_t BA = (size_t)B * (size_t)A;
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
-    w.ticket = off;     off = p24_align(off + (size_t)(2 + B) * sizeof(unsigned));
+    w.ticket = off;     off = p24_align(off + (size_t)(3 + B) * sizeof(unsigned));
     w.acc_fix = off;    off = p24_align(off + (size_t)B * 28 * sizeof(long long));
     w.err_flag = off;   off = p24_align(off + sizeof(int));
-    w.slow_n = off;     off = p24_align(off + sizeof(int));
-    w.slow_ctl = off;   off = p24_align(off + BL * 4 * sizeof(int));
-    w.slow_desc = off;  off = p24_align(off + BL * 8 * sizeof(float));
-    w.slow_ev = off;    off = p24_align(off + BL * 512 * sizeof(float));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
     w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
     w.ccount = off;     off = p24_align(off + NB * sizeof(int));
     w.sval = off;       off = p24_align(off + BL * P24_SEEDS * (size_t)p24_tiles(A) * sizeof(float));
     w.wtab = off;       off = p24_align(off + BL * P24_WT_STRIDE * sizeof(float));
     w.tbox = off;       off = p24_align(off + NB * 8 * sizeof(float));
+    w.seg = off;        off = p24_align(off + NB * P24_WARPS * 8 * sizeof(float));
     w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
     w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));
     w.obj_part = off;   off = p24_align(off + NB * sizeof(double));

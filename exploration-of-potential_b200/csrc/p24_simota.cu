@@ -59,10 +59,7 @@ struct Params {
     float* sval;
     float* wtab;
     float* tbox;
-    int* slow_n;      // published GTs of the exact top-10 path
-    int* slow_ctl;    // [B * Lmax][4]: ready, next chunk, chunks done, kept values
-    float* slow_desc; // [B * Lmax][8]: image, GT, candidate count, T, tau
-    float* slow_ev;   // [B * Lmax][SLOW_EV_CAP]
+    float* seg;       // [B, tiles, 8 warps, 8]: per-warp boxes / counts of the candidate lists
     int* ccount;
     int* claim_cnt;
     int* claim_gt;
@@ -249,6 +246,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(Params p) {
         p.num_gt[b] = n;
         p.num_fg[b] = 0;
         p.nclaimed[b] = 0;
+        atomicMax(&p.ticket[2 + p.B], (unsigned)n);  // the batch's largest num_gt: k_pass lays its window items out for it
     }
     for (int g = warp; g < n; g += PREP_THREADS / 32)
         warp_gt_record(lab + (long long)g * p.lab_row_stride, p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC);
@@ -678,6 +676,12 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
         dst[0] = make_float4(bx0, bx1, by0, by1);
         dst[1] = make_float4(rzm, 0.0f, 0.0f, 0.0f);
     }
+    if (lane == 0) {
+        // the warp's segment of the candidate list: box of its candidates' predicted centres, largest rpmax, extent
+        float4* dst = reinterpret_cast<float4*>(p.seg + (blk * P24_WARPS + warp) * 8);
+        dst[0] = make_float4(S.box[warp][0], S.box[warp][1], S.box[warp][2], S.box[warp][3]);
+        dst[1] = make_float4(S.box[warp][4], __int_as_float(S.wcnt[warp]), __int_as_float(base), __uint_as_float(bal));
+    }
     if (cand) {
         const int rank = base + __popc(bal & ((1u << lane) - 1u));
         // a prediction with a tiny radius disables the bound filter for its pairs: rpmax = +inf
@@ -716,7 +720,6 @@ __device__ __forceinline__ void claim_anchor(const Params& p, int b, int a, int 
 }
 
 #define HIT_CAP 3072
-#define SLOW_EV_CAP 512  // kept values per published GT (overflow -> brute force)
 #define MATCH_WCAP (25 * P24_MAX_LEVELS)  // at most 5 x 5 cells per level pass the window test
 #define MAX_TILES 1024  // candidate counts of an image kept in shared memory (A <= 262144)
 
@@ -734,17 +737,21 @@ __device__ __forceinline__ float bound_H_thread(const float* __restrict__ rec, f
     return s * (1.0f / 48.0f);
 }
 
+#define EXACT_CAP 2048  // candidates the exact path can hold bounds for (more -> brute force)
 struct MatchShared {
     float rec[GT_REC];
     int ccount[MAX_TILES];
-    int hit[HIT_CAP];       // slow path: anchors the scalar bound cannot exclude
-    float ev[HIT_CAP];      // slow path: upper bounds of the chunk's survivors / kept exact values
-    float lb[1024];         // slow path: certified lower bounds of the chunk's survivors
+    int hit[HIT_CAP];       // brute force: exact values; bracket: staged tile boxes; exact path: anchors
+    float ev[1024];         // bracket: staged seed values; exact path: exact values of the survivors
+    float ub[EXACT_CAP];    // exact path: per-candidate bounds
+    float lb[EXACT_CAP];
+    int qseg[1024];         // exact path: survivors of the refined threshold
+    int hist[32];
     float top[P24_TOPK];
     KV kv[MATCH_WARPS];
     float wmax[MATCH_WARPS];
     int cnt, nhit, nev, k, slow, nvalid, overflow;
-    float T, L, tau, tmax;
+    float T, L, tau, tmax, dmax;
     int wanchor[MATCH_WCAP];   // the GT's valid (in window, in polygon) anchors and their costs
     float wcost[MATCH_WCAP];
 };
@@ -821,160 +828,166 @@ __device__ __noinline__ float topk_sum_bruteforce(const Params& p, MatchShared& 
     return ksum;
 }
 
-// Exact top-10 sum when the bracket is not conclusive (about 1 GT in 100), as cooperative work of the whole grid:
-//  1. tau: the largest t with H(t) <= T - eps (T = 10th best seed value), two rounds of 32-way search by one warp;
-//     candidates with t = rpmax + d < tau cannot reach T (one compare per candidate)               [the GT's own CTA]
-//  2. per chunk of tiles: the survivors of the scalar filter get the per-ray bound ub (one thread each); those with
-//     ub >= T are evaluated exactly (8-lane groups) and kept in the GT's global list when they reach T  [any CTA]
-//  3. the 10 largest kept values (the best seeds are among them) are summed in descending order (torch.topk
-//     order), then the GT's selection runs                                            [the CTA that ends the last chunk]
-// The GT's CTA publishes a descriptor; every CTA of k_match that has finished its own GT takes chunks from the
-// published GTs (and so does the publisher): nobody ever waits for anybody.
-__device__ __forceinline__ float warp_tau(const float* rec, float T, float tmax) {
-    const int lane = threadIdx.x & 31;
-    const float target = T - 2e-5f;
-    float lo = 0.0f, hi = tmax * 1.001f + 1.0f;
-    float tau = P24_NEG_INF;
-    if (bound_H_thread(rec, lo) <= target) {
-#pragma unroll 1
-        for (int round = 0; round < 2; ++round) {
-            const float step = (hi - lo) * (1.0f / 32.0f);
-            const float tj = lo + step * (float)(lane + 1);
-            const bool ok = bound_H_thread(rec, tj) <= target;     // monotone in t: a prefix of lanes
-            const int nok = __popc(__ballot_sync(0xffffffffu, ok));
-            const float nlo = lo + step * (float)nok;
-            hi = (nok == 32) ? hi : (nlo + step);
-            lo = nlo;
-        }
-        tau = lo - 0.01f - 1e-4f * lo;
+// Upper bound of the pair value as a function of the centre distance d alone.  For an apart ray the loss is
+// 2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2 (and that expression bounds partial rays too, see bound_H_thread); over all
+// rp > 0 the fraction is smallest at rp* = rg^2 / (rg + d), where it equals rg^2 / ((rg + d)^2 + rg^2).  So every
+// ray has loss <= max(1, 2 - 4 rg^2 / ((rg + d)^2 + rg^2)) whatever the prediction: monotone in d, and tight for large
+// GTs, where bound_H_thread (which pays for the largest predicted radius of a whole tile) is loose.
+__device__ __forceinline__ float bound_Hstar_thread(const float* __restrict__ rec, float d) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < P24_RAYS; ++k) {
+        const float rg = rec[GT_RG + k];
+        const float q = rg + d;
+        s += fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, fmaf(q, q, rg * rg)));
     }
-    return tau;
+    return s * (1.0f / 48.0f);
 }
 
-// tiles per chunk: one while the image has at most 64 tiles (the far tiles hold most survivors: fine chunks keep the
-// items even), never more than 12 (12 * 256 candidates fit the hit list)
-__device__ __forceinline__ int slow_tiles_per_chunk(int tiles) { return min(12, (tiles + 63) / 64); }
-
-// S.rec / S.ccount <- GT g of image b.  Contains __syncthreads().
-__device__ __forceinline__ void load_gt_context(const Params& p, MatchShared& S, int b, int g) {
-    const int tid = threadIdx.x;
-    __syncthreads();
-    if (tid < GT_REC) S.rec[tid] = p.gt_rec[((long long)b * p.Lmax + g) * GT_REC + tid];
-    for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) S.ccount[tl] = p.ccount[(long long)b * p.tiles + tl];
-    __syncthreads();
-}
-
-// step 2 for chunk c of the published GT `slot` (its context is in S); returns true in the CTA that completes the GT's
-// last chunk
-__device__ __noinline__ bool slow_chunk(const Params& p, MatchShared& S, int slot, int c, int b, float T, float tau) {
-    const int tid = threadIdx.x;
+// Exact top-10 sum when the bracket is not conclusive (about 1 GT in 100; the large ones, whose values sit near 0.9
+// and whose sums sit near 9), in one pass over what can matter:
+//  1. every warp segment of the candidate lists (32 anchors: a short run of one grid row) whose value bound
+//     min(H(t), H*(d)) over its box reaches T (the 10th best seed value, a certified lower bound of the 10th largest
+//     value) is kept: the far corners of the image as seen from the GT;
+//  2. their candidates get per-candidate bounds (one thread each: ub = the apart formula, which bounds every ray;
+//     for a pair whose rays are all apart -- the reference's own fp32 comparison -- the value is ub to within 3e-6,
+//     so ub - 5e-5 is a certified lower bound);
+//  3. the 10th largest lower bound (two rounds of a 32-bin histogram) replaces T;
+//  4. the candidates whose ub still reaches it (a handful) are evaluated exactly (8-lane groups);
+//  5. the 10 largest exact values are summed in descending order (torch.topk order).
+// Returns NaN when the lists do not fit (the caller falls back to brute force).
+__device__ __noinline__ float topk_sum_exact(const Params& p, MatchShared& S, int b) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned gm = group_mask();
     const int grp = tid >> 3, sub = tid & 7;
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     const float* img = p.outputs + (long long)b * p.img_stride;
-    const int tpc = slow_tiles_per_chunk(p.tiles);
-    const int t0 = c * tpc, t1 = min(p.tiles, t0 + tpc);
-    __syncthreads();
-    if (tid == 0) S.nhit = 0;
+    const float T0 = S.T;
+    if (tid == 0) {
+        S.nhit = 0;  // qualifying segments
+        S.cnt = 0;   // their candidates
+        S.nev = 0;
+        S.overflow = 0;
+    }
     __syncthreads();
     {
-        const float4* tb = reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
-        for (int tl = t0; tl < t1; ++tl) {
-            const int cc = S.ccount[tl];
-            if (cc == 0) continue;
-            const float4 bx = tb[2 * tl];
-            const float rzm = tb[2 * tl + 1].x;
+        const float4* sg = reinterpret_cast<const float4*>(p.seg + (long long)b * p.tiles * P24_WARPS * 8);
+        const int nseg = p.tiles * P24_WARPS;
+        for (int si = tid; si < nseg; si += MATCH_THREADS) {
+            const float4 bx = sg[2 * si];
+            const float4 r1 = sg[2 * si + 1];
+            const int cnt = __float_as_int(r1.y);
+            if (cnt <= 0) continue;
             const float fx = fmaxf(fabsf(gcx - bx.x), fabsf(gcx - bx.y));
             const float fy = fmaxf(fabsf(gcy - bx.z), fabsf(gcy - bx.w));
-            const float ttile = rzm + sqrtf(fmaf(fx, fx, fy * fy)) * 1.00001f;
-            if (ttile < tau) continue;  // no survivor in this tile (NaN / inf boxes pass)
-            if (tid < cc) {
-                const float4 q = p.clist[((long long)b * p.tiles + tl) * P24_THREADS + tid];
-                const float dx = gcx - q.x, dy = gcy - q.y;
-                const float t = q.z + sqrtf(fmaf(dx, dx, dy * dy));
-                if (t >= tau || !(t == t)) S.hit[atomicAdd(&S.nhit, 1)] = __float_as_int(q.w);  // <= 12 * 256 < HIT_CAP
+            const float dm = sqrtf(fmaf(fx, fx, fy * fy)) * 1.0001f + 0.01f;
+            const float u = fminf(bound_H_thread(S.rec, r1.x + dm), bound_Hstar_thread(S.rec, dm)) + 2e-5f;
+            if (u < T0 && r1.x < 60000.0f) continue;  // (NaN bounds and tiny predicted radii stay in)
+            const int pos = atomicAdd(&S.cnt, cnt);
+            const int q = atomicAdd(&S.nhit, 1);
+            if (pos + cnt <= EXACT_CAP && q < 512) {
+                S.qseg[2 * q] = si | (pos << 16);  // si < 8192, pos < 2048
+                S.qseg[2 * q + 1] = __float_as_int(r1.w);  // which of the segment's 32 anchors are candidates
+            } else {
+                S.overflow = 1;
             }
         }
     }
     __syncthreads();
-    const int nhit = S.nhit;
-    // per-ray bound, one thread per survivor (24 independent loads in flight); the anchor is tagged when the bound
-    // excludes it.  For a pair whose rays are all apart (the reference's own fp32 comparison) the bound is the value
-    // itself to within 3e-6, so ub - 1e-5 is a certified lower bound: the chunk's 10th largest lower bound replaces T
-    // (any candidate below it has 10 better ones in this chunk alone), which leaves a handful of exact evaluations.
-    for (int i = tid; i < nhit; i += MATCH_THREADS) {
-        const float* row = img + (long long)S.hit[i] * p.row_stride;
-        const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
-        float ub = 0.0f;
-        bool apart = true;
-#pragma unroll 8
-        for (int k = 0; k < P24_RAYS; ++k) {
-            const float rg = S.rec[GT_RG + k], rp = row[2 + k];
-            ub += p24_ray_loss_ub(rg, rp, d);
-            apart = apart && (d >= rg + rp);
-        }
-        ub = ub * (1.0f / 48.0f) + 2e-5f;
-        S.ev[i] = ub;
-        if (i < 1024) S.lb[i] = (apart && ub == ub) ? ub - 3e-5f : P24_NEG_INF;
-        if (ub < T) S.hit[i] = -1;
-    }
-    __syncthreads();
-    if (nhit > P24_TOPK && nhit <= 1024) {
-        if (tid == 0) S.tau = T;
-        __syncthreads();
-        for (int i = tid; i < nhit; i += MATCH_THREADS) {
-            const float li = S.lb[i];
-            if (!(li > T)) continue;
-            int rank = 0;
-            for (int j = 0; j < nhit; ++j) rank += kv_gt(S.lb[j], j, li, i) ? 1 : 0;
-            if (rank == P24_TOPK - 1) S.tau = li;  // exactly one thread: ranks are distinct
-        }
-        __syncthreads();
-        const float tl = S.tau;
-        for (int i = tid; i < nhit; i += MATCH_THREADS)
-            if (S.ev[i] < tl) S.hit[i] = -1;
-    }
-    __syncthreads();
-    // exact value of what is left (8-lane groups); values that reach T go to the GT's list
-    float* ev = p.slow_ev + (long long)slot * SLOW_EV_CAP;
-    int* ctl = p.slow_ctl + 4 * slot;  // ready, next, done, nev
-    for (int i0 = 0; i0 < nhit; i0 += MATCH_GROUPS) {
-        const int i = i0 + grp;
-        const int a = i < nhit ? S.hit[i] : -1;
-        if (a < 0) continue;
-        const float v = group_pair_value(S.rec, img + (long long)a * p.row_stride, gm);
-        if (sub == 0 && (v >= T || !(v == v))) {
-            const int at = atomicAdd(&ctl[3], 1);
-            if (at < SLOW_EV_CAP) ev[at] = (v == v) ? v : P24_POS_INF;
-        }
-    }
-    __threadfence();
-    __syncthreads();
+#ifdef P24_TIMING
     if (tid == 0) {
-        const int nchunk = (p.tiles + tpc - 1) / tpc;
-        S.overflow = (atomicAdd(&ctl[2], 1) == nchunk - 1) ? 1 : 0;
+        g_tstamp[1][b * 20 + (int)blockIdx.y][9] = S.nhit;
+        g_tstamp[1][b * 20 + (int)blockIdx.y][10] = S.cnt;
+        g_tstamp[1][b * 20 + (int)blockIdx.y][11] = S.overflow;
+    }
+    TMARK(1, b * 20 + (int)blockIdx.y, 16);
+#endif
+    if (S.overflow) return NAN;
+    const int n1 = S.cnt;
+    // the anchors of the kept segments (a segment is 32 consecutive anchors; its candidates are the set bits)
+    for (int q = warp; q < S.nhit; q += MATCH_WARPS) {
+        const int si = S.qseg[2 * q] & 0xFFFF, pos = S.qseg[2 * q] >> 16;
+        const unsigned m = (unsigned)S.qseg[2 * q + 1];
+        if ((m >> lane) & 1u) S.hit[pos + __popc(m & ((1u << lane) - 1u))] = si * 32 + lane;
     }
     __syncthreads();
-    return S.overflow != 0;
-}
-
-// step 3: the sum of the 10 largest kept values, or NaN when the list cannot be used (overflow, fewer than 10 values):
-// the caller falls back to brute force
-__device__ __noinline__ float slow_topk_sum(const Params& p, MatchShared& S, int slot) {
-    const int tid = threadIdx.x;
-    __threadfence();
-    const int nev = __ldcg(p.slow_ctl + 4 * slot + 3);
-    if (nev > SLOW_EV_CAP || nev < P24_TOPK) return NAN;
-    const float* ev = p.slow_ev + (long long)slot * SLOW_EV_CAP;
+    // per-candidate bounds, one candidate per thread and pass: all loads of a pass are independent
+    for (int i = tid; i < n1; i += MATCH_THREADS) {
+        const int a = S.hit[i];
+        const float* row = img + (long long)a * p.row_stride;
+        float rpv[P24_RAYS];
+#pragma unroll
+        for (int k = 0; k < P24_RAYS; ++k) rpv[k] = row[2 + k];  // one round trip for the whole row
+        const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
+        float u = 0.0f, rpmin = INFINITY;
+        bool apart = true;
+#pragma unroll
+        for (int k = 0; k < P24_RAYS; ++k) {
+            const float rg = S.rec[GT_RG + k], rp = rpv[k];
+            u += p24_ray_loss_ub(rg, rp, d);
+            apart = apart && (d >= rg + rp);
+            rpmin = fminf(rpmin, rp);
+        }
+        u = u * (1.0f / 48.0f) + 2e-5f;
+        const bool trust = rpmin >= 0.25f && u == u;  // tiny predicted radii / NaN: evaluated exactly, no bounds
+        S.ub[i] = trust ? u : P24_POS_INF;
+        S.lb[i] = (trust && apart) ? u - 5e-5f : P24_NEG_INF;
+    }
     __syncthreads();
-    for (int i = tid; i < nev; i += MATCH_THREADS) S.ev[i] = __ldcg(ev + i);
+    TMARK(1, b * 20 + (int)blockIdx.y, 17);
+    // the 10th largest lower bound to within (1 - T0) / 1024: two rounds of a 32-bin histogram, starting from [T0, 1]
+    float lo = T0, width = fmaxf(1.0f - T0, 1e-6f);
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        if (tid < 32) S.hist[tid] = 0;
+        __syncthreads();
+        const float scale = 32.0f / width;
+        for (int i = tid; i < n1; i += MATCH_THREADS) {
+            const float l = S.lb[i];
+            if (l >= lo) atomicAdd(&S.hist[min((int)((l - lo) * scale), 31)], 1);
+        }
+        __syncthreads();
+        // the highest bin whose count, together with the bins above it, reaches 10
+        int above = 0, bin = -1;
+        for (int j = 31; j >= 0; --j) {
+            above += S.hist[j];
+            if (above >= P24_TOPK) {
+                bin = j;
+                break;
+            }
+        }
+        __syncthreads();
+        if (bin < 0) break;  // fewer than 10 lower bounds reach lo: lo stays (it is certified by the seeds or the last round)
+        lo = lo + (float)bin * (width * (1.0f / 32.0f));
+        width = width * (1.0f / 32.0f);
+    }
+    const float tcur = fmaxf(T0, lo - 1e-6f);
+    for (int i = tid; i < n1; i += MATCH_THREADS)
+        if (!(S.ub[i] < tcur)) {
+            const int at = atomicAdd(&S.nev, 1);
+            if (at < 1024) S.qseg[at] = S.hit[i];  // (the segment list is no longer needed)
+            else S.overflow = 1;
+        }
     __syncthreads();
-    // rank counting, one thread per kept value: the 10 largest land in S.top in descending order (ties in the value
-    // do not change the sum)
-    for (int i = tid; i < nev; i += MATCH_THREADS) {
+    TMARK(1, b * 20 + (int)blockIdx.y, 18);
+#ifdef P24_TIMING
+    if (tid == 0) g_tstamp[1][b * 20 + (int)blockIdx.y][7] = S.nev;
+#endif
+    if (S.overflow) return NAN;
+    const int nsurv = S.nev;
+    for (int i0 = 0; i0 < nsurv; i0 += MATCH_GROUPS) {
+        const int i = i0 + grp;
+        if (i >= nsurv) continue;
+        const float v = group_pair_value(S.rec, img + (long long)S.qseg[i] * p.row_stride, gm);
+        if (sub == 0) S.ev[i] = (v == v) ? v : P24_POS_INF;  // NaN sorts first (torch.topk)
+    }
+    __syncthreads();
+    TMARK(1, b * 20 + (int)blockIdx.y, 19);
+    if (nsurv < P24_TOPK) return NAN;
+    for (int i = tid; i < nsurv; i += MATCH_THREADS) {
         const float vi = S.ev[i];
         int rank = 0;
-        for (int j = 0; j < nev; ++j) rank += kv_gt(S.ev[j], j, vi, i) ? 1 : 0;
+        for (int j = 0; j < nsurv; ++j) rank += kv_gt(S.ev[j], j, vi, i) ? 1 : 0;
         if (rank < P24_TOPK) S.top[rank] = vi;
     }
     __syncthreads();
@@ -1169,14 +1182,13 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(Params p) {
     __shared__ PassShared S;
     __shared__ int s_item;
     const int n_anchor = p.B * p.tiles;
-    const int n_item = n_anchor + p.B * p.Lmax * p.nlev;
     bool first = true;
+    int leff = 0;  // the batch's largest num_gt (known once k_gt_prep is complete)
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = (int)atomicAdd(&p.ticket[1 + p.B], 1u);
         __syncthreads();
         const int item = s_item;
-        if (item >= n_item) break;
         if (item < n_anchor) {
             // image-major order keeps an image's tiles (and its records) together in time
             anchor_part(p, s_dyn4, S.a, item / p.tiles, item % p.tiles, first);
@@ -1186,9 +1198,11 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(Params p) {
                 pdl_wait();
                 first = false;
             }
+            if (leff == 0) leff = (int)__ldcg(&p.ticket[2 + p.B]);
             const int wi = item - n_anchor;
+            if (wi >= p.B * leff * p.nlev) break;
             const int l = wi % p.nlev, bg = wi / p.nlev;
-            const int b = bg / p.Lmax, g = bg - b * p.Lmax;
+            const int b = bg / leff, g = bg - b * leff;
             if (g < p.num_gt[b]) {
                 TMARK(4, wi, 0);
                 window_part(p, S.w, b, g, l);
@@ -1297,7 +1311,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(Params p) {
     // ---- bracket the top-10 sum: L = sum of the 10 best seed values <= S <= 10 * H(t_max) = U (warp 0) ------------
     if (warp == 0) {
         // largest t = rpmax + d over the candidates, bounded per tile by its box
-        float tm = P24_NEG_INF;
+        float tm = P24_NEG_INF, dm = P24_NEG_INF;  // ... and the largest centre distance d
         const float4* tb = staged ? s_tb : reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
         for (int i = lane; i < p.tiles; i += 32) {
             const float4 bx = tb[2 * i];
@@ -1305,10 +1319,13 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(Params p) {
             if (rzm > P24_NEG_INF) {
                 const float fx = fmaxf(fabsf(gcx - bx.x), fabsf(gcx - bx.y));
                 const float fy = fmaxf(fabsf(gcy - bx.z), fabsf(gcy - bx.w));
-                tm = fmaxf(tm, rzm + sqrtf(fmaf(fx, fx, fy * fy)) * 1.00001f);
+                const float dd = sqrtf(fmaf(fx, fx, fy * fy)) * 1.00001f;
+                tm = fmaxf(tm, rzm + dd);
+                dm = fmaxf(dm, dd);
             }
         }
         tm = warp_max(tm);
+        dm = warp_max(dm);
         // the 10 largest seed values, summed in descending order (like the reference sums torch.topk's output)
         const int nseed = P24_SEEDS * p.tiles;
         const float* sv = staged ? s_sv : p.sval + (long long)wslot * nseed;
@@ -1343,14 +1360,25 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(Params p) {
         int slow = 1, k = 0;
         const bool usable = T > P24_NEG_INF && !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && tm < 60000.0f;
         if (usable) {
-            float term = 0.0f;
+            // two monotone bounds of any candidate's value: H(t_max) (bound_H_thread) and H*(d_max) (bound_Hstar_thread)
+            float term = 0.0f, term2 = 0.0f;
             if (lane < P24_RAYS) {
                 const float rg = S.rec[GT_RG + lane];
                 const float q = rg + (tm * 1.0001f + 0.01f);
                 term = fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, q * q));
+                const float q2 = rg + (dm * 1.0001f + 0.01f);
+                term2 = fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, fmaf(q2, q2, rg * rg)));
             }
-            const float U = 10.0f * (warp_sum(term) * (1.0f / 48.0f) + 2e-5f);
+            const float U = 10.0f * (fminf(warp_sum(term), warp_sum(term2)) * (1.0f / 48.0f) + 2e-5f);
             const float fl = floorf(L - 1e-4f), fu = floorf(U + 1e-4f);
+#ifdef P24_TIMING
+            if (lane == 0) {
+                g_tstamp[1][MCTA][12] = __float_as_uint(L);
+                g_tstamp[1][MCTA][13] = __float_as_uint(U);
+                g_tstamp[1][MCTA][14] = __float_as_uint(tm);
+                g_tstamp[1][MCTA][15] = __float_as_uint(S.rec[GT_RGMAX]);
+            }
+#endif
             if (fl == fu && fl >= 1.0f) {
                 slow = 0;
                 k = (int)fl;
@@ -1371,98 +1399,18 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(Params p) {
         g_tstamp[1][MCTA][9] = 0;
     }
 #endif
-    if (S.slow == 1) {
-        // publish the GT: whoever is free takes its chunks
-        if (warp == 0) {
-            const float tau = warp_tau(S.rec, S.T, S.tmax);
-            if (lane == 0) {
-                const int slot = atomicAdd(p.slow_n, 1);
-                float* d = p.slow_desc + 8 * slot;
-                d[0] = __int_as_float(b);
-                d[1] = __int_as_float(g);
-                d[2] = __int_as_float(ncand);
-                d[3] = S.T;
-                d[4] = tau;
-                __threadfence();
-                atomicExch(p.slow_ctl + 4 * slot, 1);
-            }
-        }
+    int k;
+    if (S.slow) {
+        float ksum = NAN;
+        if (S.slow == 1) ksum = topk_sum_exact(p, S, b);
+        if (!(ksum == ksum)) ksum = topk_sum_bruteforce(p, S, b, kc);
+        k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
+        if (k < 1) k = 1;
     } else {
-        int k;
-        if (S.slow) {
-            const float ksum = topk_sum_bruteforce(p, S, b, kc);
-            k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
-            if (k < 1) k = 1;
-        } else {
-            k = S.k;
-        }
-        finish_gt(p, S, b, g, min(k, ncand));  // torch.topk would raise beyond the candidate count; clamp instead
+        k = S.k;
     }
     TMARK(1, MCTA, 5);
-    // ---- help with the published GTs until no chunk is left ----------------------------------------------------------
-    int cur_b = b, cur_g = g;  // the context in S.rec / S.ccount
-    int cursor = 0;
-    const int nchunk = (p.tiles + slow_tiles_per_chunk(p.tiles) - 1) / slow_tiles_per_chunk(p.tiles);
-    for (;;) {
-        __syncthreads();
-        if (warp == 0) {
-            // lanes look at 32 published GTs at a time (one 16-byte load each); the first one with a chunk left is tried
-            int found = -1, chunk = 0;
-            const int ns = *(volatile int*)p.slow_n;  // 0 almost always: one load and out
-            const int cur0 = cursor;
-            for (int base = cur0; base < ns && found < 0; base += 32) {
-                const int sidx = base + lane;
-                int4 c4 = make_int4(0, 0, 0, 0);
-                if (sidx < ns) c4 = __ldcg(reinterpret_cast<const int4*>(p.slow_ctl) + sidx);
-                const bool spent = sidx < ns && c4.x != 0 && c4.y >= nchunk;
-                const bool avail = sidx < ns && c4.x != 0 && c4.y < nchunk;
-                // the cursor moves over the leading run of spent GTs
-                const unsigned sp = __ballot_sync(0xffffffffu, spent);
-                if (base == cur0) cursor = cur0 + (sp == 0xffffffffu ? 32 : __ffs(~sp) - 1);
-                unsigned av = __ballot_sync(0xffffffffu, avail);
-                while (av && found < 0) {
-                    const int l = __ffs(av) - 1;
-                    av &= av - 1;
-                    int c = 0;
-                    if (lane == 0) c = atomicAdd(p.slow_ctl + 4 * (base + l) + 1, 1);
-                    c = __shfl_sync(0xffffffffu, c, 0);
-                    if (c < nchunk) {
-                        found = base + l;
-                        chunk = c;
-                    }
-                }
-            }
-            if (lane == 0) {
-                S.nvalid = found;
-                S.k = chunk;
-                S.cnt = cursor;
-            }
-        }
-        __syncthreads();
-        const int slot = S.nvalid, chunk = S.k;
-        cursor = S.cnt;
-        if (slot < 0) break;
-#ifdef P24_TIMING
-        if (tid == 0) g_tstamp[1][MCTA][9] += 1;
-#endif
-        __threadfence();
-        const float* d = p.slow_desc + 8 * slot;
-        const int sb = __float_as_int(__ldcg(d + 0)), sg = __float_as_int(__ldcg(d + 1));
-        const int sncand = __float_as_int(__ldcg(d + 2));
-        const float sT = __ldcg(d + 3), stau = __ldcg(d + 4);
-        if (sb != cur_b || sg != cur_g) {
-            load_gt_context(p, S, sb, sg);
-            cur_b = sb;
-            cur_g = sg;
-        }
-        if (slow_chunk(p, S, slot, chunk, sb, sT, stau)) {
-            float ksum = slow_topk_sum(p, S, slot);
-            if (!(ksum == ksum)) ksum = topk_sum_bruteforce(p, S, sb, min(P24_TOPK, sncand));
-            int k = (int)ksum;
-            if (k < 1) k = 1;
-            finish_gt(p, S, sb, sg, min(k, sncand));
-        }
-    }
+    finish_gt(p, S, b, g, min(k, ncand));  // torch.topk would raise beyond the candidate count; clamp instead
     TMARK(1, MCTA, 6);
 }
 
@@ -1692,9 +1640,7 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     if (tid == 0) {
         p.ticket[0] = 0u;  // ready for the next call
         p.ticket[1 + p.B] = 0u;
-        const int ns = *p.slow_n;
-        for (int i = 0; i < 4 * ns; ++i) p.slow_ctl[i] = 0;
-        *p.slow_n = 0;
+        p.ticket[2 + p.B] = 0u;
     }
     if (p.state26 && warp == 0) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 6);
@@ -1780,10 +1726,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.sval = (float*)(ws + L.sval);
     p.wtab = (float*)(ws + L.wtab);
     p.tbox = (float*)(ws + L.tbox);
-    p.slow_n = (int*)(ws + L.slow_n);
-    p.slow_ctl = (int*)(ws + L.slow_ctl);
-    p.slow_desc = (float*)(ws + L.slow_desc);
-    p.slow_ev = (float*)(ws + L.slow_ev);
+    p.seg = (float*)(ws + L.seg);
     p.ccount = (int*)(ws + L.ccount);
     p.claim_cnt = (int*)(ws + L.claim_cnt);
     p.claim_gt = (int*)(ws + L.claim_gt);

@@ -31,7 +31,7 @@ t = buf.astype(np.int64)
 order = [(3, "k_gt_prep", ["start", "end"]),
          (0, "k_pass/anchor", ["start", "wait", "recs+rows", "gt loop", "items", "end"]),
          (4, "k_pass/window", ["start", "end"]),
-         (1, "k_match", ["start", "wait", "load", None, "bracket", "own GT", "helping"]),
+         (1, "k_match", ["start", "wait", "load", None, "bracket", "dyn_k", "select"]),
          (2, "k_resolve_loss", ["start", "wait", None, None, "entries", "partials"])]
 base = None
 pct = lambda x: "min %7.1f p10 %7.1f p50 %7.1f p90 %7.1f max %7.1f" % tuple(np.percentile(x, [0, 10, 50, 90, 100]))
@@ -59,10 +59,12 @@ for k, nm, slots in order:
         slow = tt[:, 8]
         sl = ok & (slow != 0)
         print("   slow-path CTAs:", int(sl.sum()), "kinds", slow[sl].tolist())
-        nch = tt[ok, 9]
-        print("   chunks taken per CTA: total", int(nch.sum()), "CTAs with any", int((nch > 0).sum()), "max", int(nch.max()))
-        hp = (tt[ok, 6] - tt[ok, 5]) / 1e3
-        for c in range(0, int(nch.max()) + 1):
-            m = nch == c
-            if m.any():
-                print(f"      {c} chunks: {int(m.sum())} CTAs, helping phase mean {hp[m].mean():.2f} max {hp[m].max():.2f} us")
+        f32 = lambda x: np.array(x, dtype=np.uint64).astype(np.uint32).view(np.float32)
+        for ci in np.nonzero(sl)[0]:
+            print("      slow GT", int(ci), "L", f32(t[1, ci, 12]), "U", f32(t[1, ci, 13]), "tmax", f32(t[1, ci, 14]), "rgmax", f32(t[1, ci, 15]))
+        for ci in np.nonzero(sl)[0]:
+            r = t[1, ci]
+            print(f"      slow GT {int(ci)}: segments {r[9]} candidates {r[10]} overflow {r[11]} survivors {r[7]} | seg scan {(r[16]-r[4])/1e3:.1f} bounds {(r[17]-r[16])/1e3:.1f} "
+                  f"threshold {(r[18]-r[17])/1e3:.1f} exact {(r[19]-r[18])/1e3:.1f} rest {(r[5]-r[19])/1e3:.1f} us")
+        wid = f32(t[1][ok][:, 13]) - f32(t[1][ok][:, 12])
+        print("   bracket width U-L quantiles (10/50/90/99 %):", np.percentile(wid, [10, 50, 90, 99]))
