@@ -28,6 +28,7 @@ namespace {
 #define POST_WARPS 8
 #define NMS_THREADS 1024
 #define SORT_SMEM_MAX 16384  // candidates of one image sorted in shared memory (128 KB of keys)
+#define NCELL_MAX 2048
 
 struct PostParams {
     const float* pred;
@@ -50,12 +51,15 @@ struct PostParams {
     float4* c_rect;  // [B, tiles*256]
     float4* s_rect;  // [B, A]   sorted (and class-shifted) rectangles
     unsigned long long* g_keys;  // [B, npad]  global sort scratch (only when an image has > SORT_SMEM_MAX candidates)
+    int* s_order;    // [B, A]   sorted boxes grouped by x cell
+    int* s_cell;     // [B, A]   x cell of every sorted box
+    float4* c_srect; // [B, A]   the sorted rectangles again, in cell order (coalesced reads of a cell)
     int tiles;
     int npad_global;
 };
 
 struct PostWorkspace {
-    size_t tcount, c_score, c_conf, c_anchor, c_cls, c_rect, s_rect, g_keys, total;
+    size_t tcount, c_score, c_conf, c_anchor, c_cls, c_rect, s_rect, g_keys, s_order, s_cell, c_srect, total;
 };
 
 inline int next_pow2(int x) {
@@ -77,6 +81,9 @@ inline PostWorkspace post_layout(int B, int A) {
     w.c_rect = off;   off = p24_align(off + slots * sizeof(float4));
     w.s_rect = off;   off = p24_align(off + (size_t)B * A * sizeof(float4));
     w.g_keys = off;   off = p24_align(off + (A > SORT_SMEM_MAX ? (size_t)B * next_pow2(A) * sizeof(unsigned long long) : 0));
+    w.s_order = off;  off = p24_align(off + (size_t)B * A * sizeof(int));
+    w.s_cell = off;   off = p24_align(off + (size_t)B * A * sizeof(int));
+    w.c_srect = off;  off = p24_align(off + (size_t)B * A * sizeof(float4));
     w.total = off;
     return w;
 }
@@ -314,43 +321,205 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     }
     __syncthreads();
 
-    // ---- greedy NMS over the sorted boxes in chunks of 64; suppression flags live in the low bit 31 of the key ------
-    // (bit 31 of the slot field is free: slots < 2^31)
-    for (int c0 = 0; c0 < n; c0 += 64) {
-        const int cn = min(64, n - c0);
-        if (tid < 64) s_mask[tid] = 0ull;
-        __syncthreads();
-        // 64 x 64 pairwise tests of the chunk (j > i)
-        for (int q = tid; q < cn * cn; q += NMS_THREADS) {
-            const int i = q / cn, j = q - i * cn;
-            if (j > i && iou_over(srect[c0 + i], srect[c0 + j], p.nms_thre)) atomicOr(&s_mask[i], 1ull << j);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned long long removed = 0ull;
-            int nk = 0;
-            for (int i = 0; i < cn; ++i) {
-                const bool dead = ((keys[c0 + i] >> 31) & 1ull) || ((removed >> i) & 1ull);
-                if (dead) {
-                    keys[c0 + i] |= (1ull << 31);
-                } else {
-                    removed |= s_mask[i];
-                    s_kept[nk++] = srect[c0 + i];
-                }
-            }
-            s_nkept = nk;
-        }
-        __syncthreads();
-        const int nk = s_nkept;
-        for (int j = c0 + cn + tid; j < n; j += NMS_THREADS) {
-            if ((keys[j] >> 31) & 1ull) continue;
-            const float4 bj = srect[j];
-            bool dead = false;
-            for (int i = 0; i < nk && !dead; ++i) dead = iou_over(s_kept[i], bj, p.nms_thre);
-            if (dead) keys[j] |= (1ull << 31);
-        }
-        __syncthreads();
+    // ---- greedy NMS over the sorted boxes.  Bit 31 of a key: suppressed; bit 30: kept (slots < 2^30).
+    // Two exact evaluations of the same recursion "a box is kept iff no kept box before it overlaps it":
+    //  (I) boxes are binned by x0 into cells at least as wide as the widest box, so that overlapping boxes sit in the
+    //      same or in adjacent cells (with the class offsets of batched NMS the cells separate the classes); then
+    //      every undecided box looks at the earlier boxes of its three cells: overlapped by a kept one -> suppressed;
+    //      every earlier overlapping box suppressed -> kept; else it waits for the next sweep.  The sweeps reach the
+    //      fixed point of the recursion in as many rounds as the longest chain of overlaps.
+    //  (C) when the boxes do not spread over many cells (class-agnostic NMS): chunks of the next 64 boxes that are
+    //      still alive: 64 x 64 tests, a serial pass over the chunk, then the kept ones sweep the boxes after it.
+    __shared__ int s_cellstart[NCELL_MAX + 2];
+    __shared__ int s_cellfill[NCELL_MAX + 1];
+    __shared__ float s_redf[3][32];
+    __shared__ int s_flag, s_cn, s_last;
+    __shared__ int s_idx[64];
+    float xlo = INFINITY, xhi = -INFINITY, wmx = 0.0f;
+    bool finite = true;
+    for (int i = tid; i < n; i += NMS_THREADS) {
+        const float4 r = srect[i];
+        xlo = fminf(xlo, r.x);
+        xhi = fmaxf(xhi, r.x);
+        wmx = fmaxf(wmx, r.z - r.x);
+        finite = finite && (fabsf(r.x) < 1e30f) && (fabsf(r.z) < 1e30f);  // false for NaN / inf
     }
+    xlo = -warp_max(-xlo);
+    xhi = warp_max(xhi);
+    wmx = warp_max(wmx);
+    if (lane == 0) {
+        s_redf[0][warp] = xlo;
+        s_redf[1][warp] = xhi;
+        s_redf[2][warp] = wmx;
+    }
+    const int allfinite = __syncthreads_and(finite ? 1 : 0);
+    xlo = s_redf[0][0];
+    xhi = s_redf[1][0];
+    wmx = s_redf[2][0];
+    for (int w = 1; w < NMS_THREADS / 32; ++w) {
+        xlo = fminf(xlo, s_redf[0][w]);
+        xhi = fmaxf(xhi, s_redf[1][w]);
+        wmx = fmaxf(wmx, s_redf[2][w]);
+    }
+    int ncell = 1;
+    float cellw = 1.0f;
+    if (allfinite && wmx >= 0.0f) {
+        const float span = xhi - xlo;
+        cellw = fmaxf(fmaxf(wmx, span * (1.0f / (float)NCELL_MAX)) * 1.0001f, 1e-6f);
+        ncell = min(NCELL_MAX, (int)(span / cellw) + 1);
+    }
+    if (ncell >= 16 && p.nms_thre >= 0.0f) {
+        // ---- (I) ----
+        int* order = p.s_order + (long long)b * p.A;
+        int* cellof = p.s_cell + (long long)b * p.A;
+        for (int c = tid; c <= ncell; c += NMS_THREADS) {
+            s_cellstart[c] = 0;
+            s_cellfill[c] = 0;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const int c = min(ncell - 1, max(0, (int)((srect[i].x - xlo) / cellw)));
+            cellof[i] = c;
+            atomicAdd(&s_cellstart[c + 1], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {  // inclusive scan of the counts -> start of every cell
+            int carry = 0;
+            for (int c0 = 0; c0 <= ncell; c0 += 32) {
+                const int c = c0 + lane;
+                int v = c <= ncell ? s_cellstart[c] : 0;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, v, off);
+                    if (lane >= off) v += t;
+                }
+                if (c <= ncell) s_cellstart[c] = v + carry;
+                carry += __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+        float4* crect = p.c_srect + (long long)b * p.A;
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const int c = cellof[i];
+            const int e = s_cellstart[c] + atomicAdd(&s_cellfill[c], 1);
+            order[e] = i;
+            crect[e] = srect[i];
+        }
+        __syncthreads();
+        // Warp w owns the cells c with c % 32 == w (adjacent cells belong to different warps) and walks through ITS boxes
+        // in sorted order, one box at a time, the lanes over the earlier boxes of the box's three cells.  An earlier
+        // overlapping box of another warp that is not decided yet is waited for: every wait points to a smaller
+        // sorted index and every warp advances in sorted order, so the smallest undecided box can always be decided.
+        for (int base = 0; base < n; base += 32) {
+            const int im = base + lane;
+            const bool mine = im < n && (cellof[im] & 31) == warp;
+            unsigned todo = __ballot_sync(0xffffffffu, mine);
+            while (todo) {
+                const int i = base + __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float4 bi = srect[i];
+                const int ci = cellof[i];
+                const int e0 = s_cellstart[max(ci - 1, 0)], e1 = s_cellstart[min(ci + 2, ncell)];
+                bool dead = false;
+                // the entries of the three cells are contiguous in cell order: coalesced loads, the next 32 entries
+                // are requested before the current ones are tested
+                int jn = (e0 + lane < e1) ? order[e0 + lane] : 0x7fffffff;
+                float4 rn = (e0 + lane < e1) ? crect[e0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int eb = e0; eb < e1 && !dead; eb += 32) {
+                    const int j = jn;
+                    const float4 bj = rn;
+                    const int en = eb + 32 + lane;
+                    jn = (en < e1) ? order[en] : 0x7fffffff;
+                    if (en < e1) rn = crect[en];
+                    bool hit = false;
+                    {
+                        if (j < i) {
+                            const bool disjoint = bj.x >= bi.z || bi.x >= bj.z || bj.y >= bi.w || bi.y >= bj.w;  // IoU = 0
+                            if (!disjoint && iou_over(bj, bi, p.nms_thre)) {
+                                unsigned st;
+                                do {
+                                    st = (unsigned)(((volatile unsigned long long*)keys)[j] >> 30) & 3u;
+                                } while (st == 0u);
+                                hit = (st & 1u) != 0u;  // overlapped by a kept box
+                            }
+                        }
+                    }
+                    dead = __any_sync(0xffffffffu, hit);
+                }
+                if (lane == 0) {
+                    atomicOr(&keys[i], dead ? (1ull << 31) : (1ull << 30));
+                    __threadfence_block();
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---- (C) ----
+        int cursor = 0;
+        while (cursor < n) {
+            // the next (up to) 64 boxes that are still alive, in order
+            if (tid == 0) {
+                s_cn = 0;
+                s_last = n;
+            }
+            __syncthreads();
+            for (int w0 = cursor; w0 < n; w0 += NMS_THREADS) {
+                const int i = w0 + tid;
+                const bool alive = i < n && !((keys[i] >> 31) & 1ull);
+                const unsigned bal = __ballot_sync(0xffffffffu, alive);
+                if (lane == 0) s_red[warp] = __int_as_float(__popc(bal));
+                __syncthreads();
+                int before = s_cn;
+                for (int w = 0; w < warp; ++w) before += __float_as_int(s_red[w]);
+                int tot = 0;
+                for (int w = 0; w < NMS_THREADS / 32; ++w) tot += __float_as_int(s_red[w]);
+                if (alive) {
+                    const int k = before + __popc(bal & ((1u << lane) - 1u));
+                    if (k < 64) s_idx[k] = i;
+                    if (k == 63) s_last = i + 1;
+                }
+                __syncthreads();
+                if (tid == 0) s_cn = min(64, s_cn + tot);
+                __syncthreads();
+                if (s_cn >= 64) break;
+            }
+            const int cn = s_cn;
+            const int cend = s_last;  // everything before cend is decided after this round
+            if (cn == 0) break;
+            if (tid < 64) s_mask[tid] = 0ull;
+            __syncthreads();
+            for (int q = tid; q < cn * cn; q += NMS_THREADS) {
+                const int i = q / cn, j = q - i * cn;
+                if (j > i && iou_over(srect[s_idx[i]], srect[s_idx[j]], p.nms_thre)) atomicOr(&s_mask[i], 1ull << j);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long removed = 0ull;
+                int nk = 0;
+                for (int i = 0; i < cn; ++i) {
+                    if ((removed >> i) & 1ull) {
+                        keys[s_idx[i]] |= (1ull << 31);
+                    } else {
+                        removed |= s_mask[i];
+                        s_kept[nk++] = srect[s_idx[i]];
+                    }
+                }
+                s_nkept = nk;
+            }
+            __syncthreads();
+            const int nk = s_nkept;
+            for (int j = cend + tid; j < n; j += NMS_THREADS) {
+                if ((keys[j] >> 31) & 1ull) continue;
+                const float4 bj = srect[j];
+                bool dead = false;
+                for (int i = 0; i < nk && !dead; ++i) dead = iou_over(s_kept[i], bj, p.nms_thre);
+                if (dead) keys[j] |= (1ull << 31);
+            }
+            __syncthreads();
+            cursor = cend;
+        }
+    }
+    __syncthreads();
 
     // ---- output rows of the survivors in sorted order ------------------------------------------------------------
     // ordered compaction over i = 0..n-1
@@ -369,7 +538,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
         for (int w = 0; w < NMS_THREADS / 32; ++w) tot += __float_as_int(s_red[w]);
         if (keep) {
             const int k = before + __popc(bal & ((1u << lane) - 1u));
-            const long long o = slot0 + (long long)(keys[i] & 0x7FFFFFFFull);
+            const long long o = slot0 + (long long)(keys[i] & 0x3FFFFFFFull);
             const int a = p.c_anchor[o];
             const float* row = p.pred + (long long)b * p.img_stride + (long long)a * p.row_stride;
             float* dst = p.det_rows + ((long long)b * p.A + k) * 29;
@@ -427,6 +596,9 @@ extern "C" int p24_postprocess(const float* prediction, int64_t img_stride, int6
     p.c_rect = (float4*)(ws + L.c_rect);
     p.s_rect = (float4*)(ws + L.s_rect);
     p.g_keys = (unsigned long long*)(ws + L.g_keys);
+    p.s_order = (int*)(ws + L.s_order);
+    p.s_cell = (int*)(ws + L.s_cell);
+    p.c_srect = (float4*)(ws + L.c_srect);
     p.tiles = tiles;
     p.npad_global = next_pow2(A);
     cudaStream_t st = (cudaStream_t)stream;

@@ -395,7 +395,7 @@ struct AnchorShared {
 };
 
 __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, AnchorShared& S, int b, int tile, bool first) {
-    float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC]
+    float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC_HEAD]: everything but the ray lengths
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int a = tile * P24_THREADS + tid;
@@ -427,7 +427,10 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
     const int n = p.num_gt[b];
     {
         const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
-        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) s_dyn4[i] = gsrc[i];
+        for (int i = tid; i < n * (GT_REC_HEAD / 4); i += P24_THREADS) {
+            const int g = i / (GT_REC_HEAD / 4), q = i - g * (GT_REC_HEAD / 4);
+            s_dyn4[i] = gsrc[g * (GT_REC / 4) + q];
+        }
     }
     cp_async_wait_all();
     __syncthreads();
@@ -465,7 +468,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
             const int ge = min(32, n - w * 32);
             for (int j = 0; j < ge; ++j) {
                 const int g = w * 32 + j;
-                const float4 h = s_dyn4[g * (GT_REC / 4)];
+                const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
                 const float dx = h.x - xc, dy = h.y - yc;
                 const float d2 = fmaf(dx, dx, dy * dy);
                 cheap |= d2 < h.z;
@@ -475,7 +478,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
             near[w] = no_prune ? (ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u)) : m;
         }
         for (int g = 128; g < n; ++g) {  // more than 128 GTs: windows and discs of the rest
-            const float4 h = s_dyn4[g * (GT_REC / 4)];
+            const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             cheap |= fmaf(dx, dx, dy * dy) < h.z;
             if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
@@ -496,17 +499,17 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
                 if (slot < ITEM_CAP) {
                     s_items[slot] = (unsigned)tid | ((unsigned)g << 8);
                 } else if (!mine) {
-                    const float* rec = s_gt + g * GT_REC;
+                    const float* rec = s_gt + g * GT_REC_HEAD;
                     mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
                                     : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
                 }
             }
         }
         for (int g = 128; g < n && !mine; ++g) {  // more than 128 GTs: test the rest in place
-            const float4 h = s_dyn4[g * (GT_REC / 4)];
+            const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             if (no_prune || fmaf(dx, dx, dy * dy) <= h.w) {
-                const float* rec = s_gt + g * GT_REC;
+                const float* rec = s_gt + g * GT_REC_HEAD;
                 mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
                                 : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
             }
@@ -521,7 +524,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
         const int al = it & 0xFF;
         if (((volatile int*)S.cand)[al]) continue;  // already a candidate through another GT
         const int g = it >> 8;
-        const float* rec = s_gt + g * GT_REC;
+        const float* rec = s_gt + g * GT_REC_HEAD;
         const int aa = tile * P24_THREADS + al;
         const float st2 = p.strides[aa];
         const float axc = p24_anchor_centre(p.x_shifts[aa], st2);
@@ -562,7 +565,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
         // is a valid seed; better ones only make the bracket tighter).  Per-warp results go to the free rows of S.row.
         float* wres = &S.row[warp][5][0];  // [n][4]: q1, a1, q2, a2   (22 * 33 = 726 floats: n <= 181)
         for (int g = lane; g < n; g += 32) {
-            const float* rec = s_gt + g * GT_REC;
+            const float* rec = s_gt + g * GT_REC_HEAD;
             const float gcx = rec[GT_CX], gcy = rec[GT_CY], rgms = rec[GT_RGMS], rgmean = rec[GT_RGMEAN];
             float q1 = P24_POS_INF, q2 = P24_POS_INF;
             int a1 = -1, a2 = -1;
@@ -656,7 +659,8 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
                 const int sa = S.seedA[t];
                 const int g = g0 + t / P24_SEEDS;
                 float v = P24_NEG_INF;
-                if (sa >= 0) v = group_pair_value_lb(s_gt + g * GT_REC, img + (long long)sa * p.row_stride, gm);
+                if (sa >= 0)
+                    v = group_pair_value_lb(p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC, img + (long long)sa * p.row_stride, gm);
                 if (sub == 0)
                     p.sval[((long long)b * p.Lmax + g) * P24_SEEDS * p.tiles + P24_SEEDS * tile + (t % P24_SEEDS)] = v;
             }
@@ -1522,7 +1526,7 @@ __device__ __forceinline__ int valid_argmin(const Params& p, int b, int n, int a
 }
 
 #define FIX_SCALE 68719476736.0  // 2^36: fixed-point unit of the loss accumulators (order-independent sums)
-#define RESOLVE_GRID_X 16
+#define RESOLVE_GRID_X 32
 
 __device__ __forceinline__ long long to_fix(double x) { return __double2ll_rn(x * FIX_SCALE); }
 
@@ -1651,7 +1655,7 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
     finalize_warp(sums28, state26, result54, weights_n27);
 }
 
-size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float); }
+size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC_HEAD * sizeof(float); }
 
 // optional per-stage timing (profiling aid for bench.py; process-global, not thread-safe)
 #define N_STAGES 3
@@ -1775,7 +1779,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     if (e != cudaSuccess) return (int)e;
     {
         const long long items = (long long)B * p.tiles + (long long)B * Lmax * n_levels;
-        const long long cap = 4LL * n_sm;  // one wave of persistent CTAs
+        const long long cap = 4LL * n_sm;  // one wave of persistent CTAs (5 per SM at 48 registers measured slower)
         e = launch(k_pass, dim3((unsigned)(items < cap ? items : cap)), dim3(P24_THREADS), dyn, st, pdl, p);
         if (e != cudaSuccess) return (int)e;
     }

@@ -20,12 +20,18 @@ from .engine import _check_cuda_f32, _stream_ptr
 _WS = {}
 
 
+_COEF = None
+
+
 def spiral_coefficients():
     """theta_k * cos(theta_k), theta_k * sin(theta_k) exactly as the reference evaluates them (boxes.py:30-33):
-    fp32 torch ops on the host (sic: not cos / sin)."""
-    theta = torch.tensor(15 * np.pi / 180)
-    th = torch.arange(24) * theta
-    return (th * torch.cos(th)).contiguous(), (th * torch.sin(th)).contiguous()
+    fp32 torch ops on the host (sic: not cos / sin).  Evaluated once."""
+    global _COEF
+    if _COEF is None:
+        theta = torch.tensor(15 * np.pi / 180)
+        th = torch.arange(24) * theta
+        _COEF = ((th * torch.cos(th)).contiguous(), (th * torch.sin(th)).contiguous())
+    return _COEF
 
 
 def _workspace(key, nbytes, device):
