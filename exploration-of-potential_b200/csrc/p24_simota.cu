@@ -26,6 +26,7 @@
 // Compile with -fmad=false: the discrete decisions hang on fp32 thresholds evaluated in the
 // reference's operation order; bounds and fast paths use explicit fmaf.
 #include "p24_common.cuh"
+#include <string.h>
 
 namespace {
 
@@ -70,6 +71,9 @@ struct Params {
     unsigned* ticket;
     int* err_flag;
     unsigned flags;
+    float* mbox[P24_MAX_RANKS];  // peer mailboxes of the fused all-reduce (nranks > 1)
+    int rank, nranks;
+    unsigned epoch;
     int tiles;
     int nlev;
     Level lev[P24_MAX_LEVELS];
@@ -1525,6 +1529,7 @@ __device__ __forceinline__ int valid_argmin(const Params& p, int b, int n, int a
     return best.i != 0x7fffffff ? best.i : -1;
 }
 
+#define MBOX_SLOT 64  // floats per (epoch half, rank) slot of a mailbox: 28 sums, flag at [32]
 #define FIX_SCALE 68719476736.0  // 2^36: fixed-point unit of the loss accumulators (order-independent sums)
 #define RESOLVE_GRID_X 32
 
@@ -1640,6 +1645,39 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
     __syncthreads();
     if (tid == 32) s_sums[24] = (float)((double)s_sums[24] + objsum);
     __syncthreads();
+    if (p.nranks > 1) {
+        // ---- all-reduce of the 28 sums over peer memory: my sums into everybody's mailbox, a flag behind them, then the
+        // contributions of all ranks from my own mailbox, added in rank order (the same bits on every rank).  Two
+        // mailbox halves alternate with the epoch: a rank cannot run two epochs ahead of a peer, so a half is never
+        // overwritten before everybody has read it.
+        const unsigned ep = p.epoch;
+        const int half = (int)(ep & 1u) * P24_MAX_RANKS;
+        for (int q = warp; q < p.nranks; q += P24_WARPS)
+            if (lane < 28) p.mbox[q][(half + p.rank) * MBOX_SLOT + lane] = s_sums[lane];
+        __threadfence_system();
+        __syncthreads();
+        if (tid < p.nranks) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned*>(p.mbox[tid] + (half + p.rank) * MBOX_SLOT + 32) = ep;
+            volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.mbox[p.rank] + (half + tid) * MBOX_SLOT + 32);
+            const long long t0 = clock64();
+            while (*f != ep) {
+                if (clock64() - t0 > 400000000LL) {  // ~0.2 s: a peer is gone; do not hang the GPU
+                    atomicOr(p.err_flag, 4);
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (tid < 28) {
+            float t = 0.0f;
+            for (int r = 0; r < p.nranks; ++r)
+                t += *reinterpret_cast<volatile float*>(p.mbox[p.rank] + (half + r) * MBOX_SLOT + tid);
+            s_sums[tid] = t;
+        }
+        __syncthreads();
+    }
     if (tid < 28) p.sums28[tid] = s_sums[tid];
     if (tid == 0) {
         p.ticket[0] = 0u;  // ready for the next call
@@ -1703,7 +1741,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
                                      int32_t* matched_gt, float* pred_iou, int32_t* num_fg, int32_t* num_gt,
                                      int32_t* dyn_k, float* sums28, float* state26, float* result54,
                                      float* weights_n27, void* workspace, size_t workspace_bytes, uint32_t flags,
-                                     void* stream) {
+                                     void* const* h_mailboxes, int rank, int nranks, uint32_t epoch, void* stream) {
     if (!outputs || !labels || !x_shifts || !y_shifts || !strides || !fg_mask || !matched_gt || !pred_iou || !num_fg ||
         !num_gt || !dyn_k || !workspace || !h_levels)
         return P24_E_BADARG;
@@ -1741,6 +1779,16 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.ticket = (unsigned*)(ws + L.ticket);
     p.err_flag = (int*)(ws + L.err_flag);
     p.flags = flags;
+    p.rank = 0; p.nranks = 1; p.epoch = 0;
+    for (int r = 0; r < P24_MAX_RANKS; ++r) p.mbox[r] = nullptr;
+    if (h_mailboxes && nranks > 1) {
+        if (nranks > P24_MAX_RANKS || rank < 0 || rank >= nranks || !sums28) return P24_E_BADARG;
+        for (int r = 0; r < nranks; ++r) {
+            if (!h_mailboxes[r]) return P24_E_BADARG;
+            p.mbox[r] = (float*)h_mailboxes[r];
+        }
+        p.rank = rank; p.nranks = nranks; p.epoch = epoch;
+    }
     p.tiles = p24_tiles(A);
     p.nlev = n_levels;
     {
@@ -1795,6 +1843,34 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     prof_mark(3, st);
     return (int)cudaGetLastError();
 }
+
+extern "C" size_t p24_comm_mailbox_bytes(void) { return (size_t)2 * P24_MAX_RANKS * MBOX_SLOT * sizeof(float); }
+
+extern "C" int p24_comm_alloc(void** d_mailbox) {
+    if (!d_mailbox) return P24_E_BADARG;
+    cudaError_t e = cudaMalloc(d_mailbox, p24_comm_mailbox_bytes());
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(*d_mailbox, 0, p24_comm_mailbox_bytes());
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaDeviceSynchronize();
+}
+
+extern "C" int p24_comm_free(void* d_mailbox) { return (int)cudaFree(d_mailbox); }
+
+extern "C" int p24_comm_export(void* d_mailbox, void* h_handle64) {
+    if (!d_mailbox || !h_handle64) return P24_E_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    return (int)cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(h_handle64), d_mailbox);
+}
+
+extern "C" int p24_comm_import(const void* h_handle64, void** d_peer_mailbox) {
+    if (!h_handle64 || !d_peer_mailbox) return P24_E_BADARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle64, sizeof(h));
+    return (int)cudaIpcOpenMemHandle(d_peer_mailbox, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+extern "C" int p24_comm_close(void* d_peer_mailbox) { return (int)cudaIpcCloseMemHandle(d_peer_mailbox); }
 
 extern "C" int p24_loss_finalize(const float* sums28, float* state26, float* result54, float* weights_n27,
                                  void* stream) {

@@ -1,7 +1,15 @@
 """Multi-GPU sharding of the loss path: the batch shards by image across the GPUs of one box, one
 process per GPU; the only collective is the SUM all-reduce of the 28 loss sums (24 per-ray IoU sums, obj BCE, cls BCE,
-num_fg, num_gt), enqueued on the compute stream between the sums kernel and the finalize kernel.  Assignments are
-strictly per image, so no other data crosses GPUs; the postprocess needs no collective at all.
+num_fg, num_gt).  Assignments are strictly per image, so no other data crosses GPUs; the postprocess needs no collective
+at all.
+
+Two ways to do the all-reduce:
+  * ``PeerComm`` (default on GPUs of one box): every rank owns a small mailbox in device memory that its peers map
+    through CUDA IPC; the last CTA of the kernel chain stores its sums into every peer's mailbox over NVLink / NVSwitch,
+    waits for the peers' flags and adds the contributions in rank order, then applies the normalisation itself: the
+    compute step and its collective are one kernel (no NCCL launch, no separate finalize kernel).
+  * NCCL ``all_reduce`` of the 28-float vector on the compute stream followed by ``p24_loss_finalize`` (fallback when
+    the mailboxes cannot be mapped; gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -34,10 +42,72 @@ def allreduce_sums(sums28: torch.Tensor, group=None) -> torch.Tensor:
     return sums28
 
 
-def attach(loss_function, group=None):
-    """Make ``Loss_Function.forward`` shard-aware: sums are all-reduced over ``group`` (default WORLD) before the
-    normalisation, so every rank computes the same loss / weights / state."""
+class PeerComm:
+    """Mailboxes of the fused all-reduce (``include/p24.h``: p24_comm_*), one per rank, mapped into this process."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+        from . import lib as _lib
+        lib = _lib.load()
+        self._lib = lib
+        self.rank = dist.get_rank(group)
+        self.nranks = dist.get_world_size(group)
+        if self.nranks > 16:
+            raise RuntimeError("PeerComm serves at most 16 ranks (one box)")
+        own = C.c_void_p()
+        _lib.check(lib.p24_comm_alloc(C.byref(own)), "p24_comm_alloc")
+        self._own = own
+        handle = C.create_string_buffer(64)
+        _lib.check(lib.p24_comm_export(own, handle), "p24_comm_export")
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self._peers = []
+        ptrs = (C.c_void_p * self.nranks)()
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs[r] = own.value
+            else:
+                peer = C.c_void_p()
+                _lib.check(lib.p24_comm_import(C.create_string_buffer(h, 64), C.byref(peer)), "p24_comm_import")
+                self._peers.append(peer)
+                ptrs[r] = peer.value
+        self.pointers = ptrs
+        self._epoch = 0
+        dist.barrier(group=group)  # every mailbox is mapped everywhere before the first kernel writes to it
+
+    def close(self):
+        """Unmap the peers' mailboxes and free the own one (call on every rank, after the last step has completed)."""
+        if self._own is None:
+            return
+        torch.cuda.synchronize()
+        for peer in self._peers:
+            self._lib.p24_comm_close(peer)
+        self._peers = []
+        self._lib.p24_comm_free(self._own)
+        self._own = None
+
+    def next_epoch(self) -> int:
+        self._epoch = (self._epoch + 1) & 0xFFFFFFFF or 1
+        return self._epoch
+
+
+def attach(loss_function, group=None, peer: bool = True):
+    """Make ``Loss_Function.forward`` shard-aware: the 28 sums are all-reduced over ``group`` (default WORLD) before the
+    normalisation, so every rank computes the same loss / weights / state.  ``peer=True`` uses the fused peer-memory
+    all-reduce when the ranks' mailboxes can be mapped (GPUs of one box) and says so on stderr when it cannot."""
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("torch.distributed is not initialised")
     loss_function.process_group = group if group is not None else dist.group.WORLD
+    loss_function.peer_comm = None
+    if peer and torch.cuda.is_available() and dist.get_backend(group) == "nccl":
+        ok = torch.ones(1, device="cuda")
+        comm = None
+        try:
+            comm = PeerComm(group)
+        except Exception as exc:  # IPC not permitted / no peer access: every rank must take the same path
+            import sys
+            print(f"p24.dist: peer-memory all-reduce unavailable ({exc}); using NCCL", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        loss_function.peer_comm = comm if float(ok) > 0 else None
     return loss_function

@@ -79,7 +79,7 @@ class GridCache:
     def get(self, x_shifts, y_shifts, strides, device):
         if torch.is_tensor(x_shifts):
             x_shifts, y_shifts, strides = [x_shifts], [y_shifts], [strides]
-        key = tuple((t.data_ptr(), tuple(t.shape), t._version) for t in list(x_shifts) + list(y_shifts) + list(strides))
+        key = tuple([(t.data_ptr(), t.numel(), t._version) for lst in (x_shifts, y_shifts, strides) for t in lst])
         if key != self._key:
             cat = [torch.cat([t.reshape(1, -1) for t in lst], 1).reshape(-1).to(device=device, dtype=torch.float32)
                    .contiguous() for lst in (x_shifts, y_shifts, strides)]
@@ -94,6 +94,10 @@ class SimOTAEngine:
     def __init__(self):
         self._bufs: Dict[tuple, dict] = {}
         self.grids = GridCache()
+        # reuse_buffers: the Assignment of a shape is allocated once and overwritten by every call (less host work per
+        # step; the caller must be done with one step's results before it enqueues the next)
+        self.reuse_buffers = False
+        self._out_cache: Dict[tuple, Assignment] = {}
 
     def _buffers(self, B, A, Lmax, device):
         key = (B, A, Lmax, str(device))
@@ -111,9 +115,10 @@ class SimOTAEngine:
 
     def run(self, outputs: torch.Tensor, labels: torch.Tensor, x_shifts, y_shifts, strides, num_classes: int,
             flags: int = 0, want_sums: bool = True, out: Assignment | None = None,
-            finalize: tuple | None = None) -> Assignment:
+            finalize: tuple | None = None, comm=None) -> Assignment:
         """Enqueue the kernel chain.  ``finalize=(state26, result54, weights27)`` fuses the normalisation and
-        re-weighting into the last kernel (single-GPU case)."""
+        re-weighting into the last kernel.  ``comm`` (``p24.dist.PeerComm``): the 28 sums are all-reduced over peer
+        memory inside the last kernel first (one process per GPU, images sharded by rank)."""
         lib = _lib.load()
         _check_cuda_f32(outputs, "outputs")
         _check_cuda_f32(labels, "labels")
@@ -131,6 +136,8 @@ class SimOTAEngine:
         gx, gy, gs, lv, nlev = self.grids.get(x_shifts, y_shifts, strides, dev)
         if gx.numel() != A:
             raise IndexError("grid length does not match the number of anchors")
+        if out is None and self.reuse_buffers:
+            out = self._out_cache.get((B, A, Lmax, want_sums, dev))
         if out is None:
             out = Assignment(
                 fg_mask=torch.empty((B, A), dtype=torch.uint8, device=dev),
@@ -141,6 +148,8 @@ class SimOTAEngine:
                 dyn_k=torch.empty((B, max(Lmax, 1)), dtype=torch.int32, device=dev),
                 sums28=torch.empty((28,), dtype=torch.float32, device=dev) if want_sums else None,
             )
+        if self.reuse_buffers:
+            self._out_cache[(B, A, Lmax, want_sums, dev)] = out
         if Lmax == 0:  # no label rows at all: everything is background
             out.fg_mask.zero_(); out.matched_gt.fill_(-1); out.pred_iou.zero_()
             out.num_fg.zero_(); out.num_gt.zero_(); out.dyn_k.zero_()
@@ -149,16 +158,22 @@ class SimOTAEngine:
         buf = self._buffers(B, A, Lmax, dev)
         ws_ptr = buf["ptr"]
         fin = [t.data_ptr() for t in finalize] if finalize is not None else [None, None, None]
-        with torch.cuda.device(dev):
-            code = lib.p24_simota_loss_batch(
-                outputs.data_ptr(), outputs.stride(0), outputs.stride(1), B, A, num_classes,
+        args = (outputs.data_ptr(), outputs.stride(0), outputs.stride(1), B, A, num_classes,
                 labels.data_ptr(), labels.stride(0), labels.stride(1), Lmax,
                 gx.data_ptr(), gy.data_ptr(), gs.data_ptr(), lv, nlev,
                 out.fg_mask.data_ptr(), out.matched_gt.data_ptr(), out.pred_iou.data_ptr(),
                 out.num_fg.data_ptr(), out.num_gt.data_ptr(), out.dyn_k.data_ptr(),
                 out.sums28.data_ptr() if out.sums28 is not None else None,
                 fin[0], fin[1], fin[2],
-                ws_ptr, buf["nbytes"], flags, _stream_ptr(dev))
+                ws_ptr, buf["nbytes"], flags,
+                comm.pointers if comm is not None else None, comm.rank if comm is not None else 0,
+                comm.nranks if comm is not None else 1, comm.next_epoch() if comm is not None else 0,
+                _stream_ptr(dev))
+        if torch.cuda.current_device() == dev.index:
+            code = lib.p24_simota_loss_batch(*args)
+        else:  # the launches go to the tensors' device
+            with torch.cuda.device(dev):
+                code = lib.p24_simota_loss_batch(*args)
         _lib.check(code, "p24_simota_loss_batch")
         return out
 

@@ -12,7 +12,7 @@ import os
 from . import build as _build
 
 _LIB = None
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_f32p = C.c_void_p  # device pointers travel as integers
 c_ptr = C.c_void_p
@@ -27,7 +27,14 @@ _PROTOS = {
                                         C.POINTER(C.c_int32), C.c_int,
                                         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr,
-                                        c_ptr, C.c_size_t, C.c_uint32, c_ptr]),
+                                        c_ptr, C.c_size_t, C.c_uint32,
+                                        C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint32, c_ptr]),
+    "p24_comm_mailbox_bytes": (C.c_size_t, []),
+    "p24_comm_alloc": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "p24_comm_free": (C.c_int, [c_ptr]),
+    "p24_comm_export": (C.c_int, [c_ptr, C.c_char_p]),
+    "p24_comm_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "p24_comm_close": (C.c_int, [c_ptr]),
     "p24_workspace_init": (C.c_int, [c_ptr, C.c_size_t, c_ptr]),
     "p24_loss_finalize": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "p24_circle_inter_fwd": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int,

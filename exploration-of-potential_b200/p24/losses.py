@@ -140,6 +140,19 @@ class Loss_Function(nn.Module):
         # set to a torch.distributed group to shard the batch by image across GPUs: the only collective is the
         # SUM all-reduce of the 28 loss sums
         self.process_group = None
+        # reuse_buffers = True: result / assignment tensors are allocated once per shape and overwritten by the next
+        # forward (less host work per step); the default hands out fresh tensors like the reference does
+        self.reuse_buffers = False
+        self._res_cache = {}
+
+    def _result_buffers(self, device):
+        if self.reuse_buffers:
+            buf = self._res_cache.get(device)
+            if buf is None:
+                buf = (torch.empty(54, dtype=torch.float32, device=device), torch.empty(27, dtype=torch.float32, device=device))
+                self._res_cache[device] = buf
+            return buf
+        return (torch.empty(54, dtype=torch.float32, device=device), torch.empty(27, dtype=torch.float32, device=device))
 
     # -- state ---------------------------------------------------------------------------------
     def _state(self, device):
@@ -163,12 +176,17 @@ class Loss_Function(nn.Module):
             raise NotImplementedError("use_l1 is never enabled by the 24p scripts (losses.py:163)")
         x_shifts, y_shifts, expanded_strides, outputs = outputs_train[:4]
         state = self._state(outputs.device)
+        self._engine.reuse_buffers = self.reuse_buffers
         if self.process_group is None:
             # single GPU: the last CTA of the chain applies the normalisation and re-weighting itself
-            result54 = torch.empty(54, dtype=torch.float32, device=outputs.device)
-            weights27 = torch.empty(27, dtype=torch.float32, device=outputs.device)
+            result54, weights27 = self._result_buffers(outputs.device)
             asg = self._engine.run(outputs, labels, x_shifts, y_shifts, expanded_strides, self.num_classes,
                                    flags=flags, finalize=(state, result54, weights27))
+        elif getattr(self, "peer_comm", None) is not None:
+            # several GPUs of one box: the last CTA all-reduces the 28 sums over peer memory, then finalizes
+            result54, weights27 = self._result_buffers(outputs.device)
+            asg = self._engine.run(outputs, labels, x_shifts, y_shifts, expanded_strides, self.num_classes,
+                                   flags=flags, finalize=(state, result54, weights27), comm=self.peer_comm)
         else:
             import torch.distributed as dist
             asg = self._engine.run(outputs, labels, x_shifts, y_shifts, expanded_strides, self.num_classes, flags=flags)

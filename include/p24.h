@@ -27,13 +27,15 @@
 extern "C" {
 #endif
 
-#define P24_ABI_VERSION 2
+#define P24_ABI_VERSION 3
 #define P24_RAYS 24
 #define P24_TOPK 10        /* n_candidate_k cap, losses.py:452 */
 
 #define P24_E_BADARG (-1)
 #define P24_E_WORKSPACE (-2)
 #define P24_E_UNSUPPORTED (-3)
+
+#define P24_MAX_RANKS 16    /* GPUs of one box that can share the fused all-reduce */
 
 /* p24_assign_batch flags */
 #define P24_F_NO_PRUNE 1u      /* evaluate every polygon angle sum exactly (self-check of the pruning) */
@@ -87,7 +89,26 @@ int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_
                           uint8_t* fg_mask, int32_t* matched_gt, float* pred_iou,
                           int32_t* num_fg, int32_t* num_gt, int32_t* dyn_k, float* sums28,
                           float* state26, float* result54, float* weights_n27,
-                          void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+                          void* workspace, size_t workspace_bytes, uint32_t flags,
+                          void* const* h_mailboxes, int rank, int nranks, uint32_t epoch, void* stream);
+
+/* Fused all-reduce of the 28 loss sums over NVLink / NVSwitch peer memory (the one collective of the path).
+ * Every rank (one process per GPU) owns a small mailbox allocated with p24_comm_alloc and maps its peers' mailboxes
+ * through CUDA IPC (p24_comm_export on the owner, p24_comm_import on the peers).  p24_simota_loss_batch then takes
+ *   h_mailboxes  HOST array of nranks device pointers, entry r = the mailbox of rank r as mapped in this process
+ *   rank, nranks this process's rank and the number of ranks (<= P24_MAX_RANKS); nranks <= 1 or h_mailboxes == NULL:
+ *                no exchange
+ *   epoch        call counter, the same on every rank, starting at 1 and incremented by the caller for every call
+ * and the last CTA of the chain stores its 28 sums into every peer's mailbox (P2P stores + a flag), waits for the
+ * flags of all peers in its own mailbox, adds the contributions in rank order (bit-identical on all ranks) and goes on
+ * to the normalisation / re-weighting: no NCCL launch, no separate finalize kernel.  sums28 then holds the global sums.
+ * All ranks must make the same sequence of calls. */
+size_t p24_comm_mailbox_bytes(void);
+int p24_comm_alloc(void** d_mailbox);
+int p24_comm_free(void* d_mailbox);
+int p24_comm_export(void* d_mailbox, void* h_handle64);
+int p24_comm_import(const void* h_handle64, void** d_peer_mailbox);
+int p24_comm_close(void* d_peer_mailbox);
 
 /* Normalisation and stateful re-weighting (models/losses.py:280-345).
  * state[26] = last_iou_loss[24], last_obj_loss, last_cls_loss (initially 1.0), updated in place.

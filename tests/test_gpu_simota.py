@@ -228,3 +228,17 @@ def test_mixed_label_kinds_many_seeds_vs_oracle_on_gpu():
         out = synth.make_head_outputs(2, 640, 80, seed=seed)
         lab = synth.make_labels(2, [n, max(n // 2, 1)], 50, 640, 80, seed=seed, kind=kind)
         _run_both(out, lab, 640, steps=1)
+
+
+def test_two_gpu_fused_allreduce_matches_full_batch():
+    """Images sharded over 2 GPUs, the 28 sums all-reduced inside the last kernel over peer memory (and, for comparison,
+    with NCCL): same loss as the whole batch on one GPU, bit-identical on both ranks.  Needs 2 GPUs."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(root, "tests", "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
