@@ -40,7 +40,7 @@ def _fingerprint() -> str:
             [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())  # names, not absolute paths: the tree moves (GPU box snapshot)
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -59,19 +59,31 @@ def is_fresh() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile when the sources changed.  Safe when several processes (one per GPU) call it at once: an exclusive
+    file lock serialises them, the library is written under a temporary name and renamed into place."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
     if not force and is_fresh():
         return lib_path()
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC] + (["-Xptxas", "-v"] if verbose else []) + \
-          sources() + ["-o", lib_path()]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libp24_b200.so")
-    if verbose:
-        print(res.stdout + res.stderr)
-    with open(os.path.join(LIBDIR, "build.stamp"), "w") as fh:
-        fh.write(_fingerprint())
+    with open(os.path.join(LIBDIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():  # another process built it while this one waited
+                return lib_path()
+            tmp = lib_path() + f".tmp{os.getpid()}"
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC] + (["-Xptxas", "-v"] if verbose else []) + \
+                  sources() + ["-o", tmp]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("nvcc failed building libp24_b200.so")
+            if verbose:
+                print(res.stdout + res.stderr)
+            os.replace(tmp, lib_path())
+            with open(os.path.join(LIBDIR, "build.stamp"), "w") as fh:
+                fh.write(_fingerprint())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return lib_path()
 
 
