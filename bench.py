@@ -197,14 +197,17 @@ def main():
 
     img_bytes = A * 107 * 4
     n_sets = max(2, -(-int(2.2 * L2_BYTES) // (B * img_bytes)))  # rotate over > 2x L2 of distinct inputs
-    sets, (xs, ys, ss) = make_inputs(args.workload, rank, n_sets, dev)
+    # (P24_SEED_RANK: debug aid, the inputs another rank would get)
+    sets, (xs, ys, ss) = make_inputs(args.workload, int(os.environ.get("P24_SEED_RANK", rank)), n_sets, dev)
     dsets = [(o.to(dev), l.to(dev)) for o, l in sets]
     gx, gy, gs = [t.to(dev) for t in xs], [t.to(dev) for t in ys], [t.to(dev) for t in ss]
     config["l2"] = f"inputs rotate over {n_sets} distinct batches ({n_sets * B * img_bytes / 2**20:.0f} MiB > 126 MiB L2)"
     from p24 import dist as p24_dist
     lf = Loss_Function(80)
-    lf.reuse_buffers = True  # result tensors allocated once and overwritten per step (public option: less host work)
-    if world > 1:
+    lf.reuse_buffers = not os.environ.get("P24_NO_REUSE")  # result tensors allocated once and overwritten per step (public option: less host work)
+    if world > 1 and os.environ.get("P24_DEBUG_NO_EXCHANGE"):
+        config["sharding"] = "DEBUG: ranks run independently (no all-reduce)"
+    elif world > 1:
         p24_dist.attach(lf, peer=(args.allreduce == "peer"))
         fused = lf.peer_comm is not None
         config["sharding"] = (f"images sharded over {world} GPU(s); 28-float all-reduce per step: " +
@@ -220,7 +223,7 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("P24_NO_CLOCK_SAMPLER"):
         sampler.start()
     t_load = time.perf_counter()
     for i in range(args.warmup):
@@ -240,11 +243,19 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host = time.perf_counter()
     for i in range(args.steps):
         res = step(i)
+    t_host = (time.perf_counter() - t_host) / args.steps * 1e3  # host time to enqueue one step on this rank
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    host_ms = [t_host]
+    if world > 1:
+        th = torch.tensor([t_host], device=dev)
+        tg = [torch.zeros_like(th) for _ in range(world)]
+        dist.all_gather(tg, th)
+        host_ms = [float(x) for x in tg]
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -266,6 +277,12 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     names = ["k_pass", "k_match", "k_resolve_loss"]
     kern_ms = [a / args.steps for a in acc[:len(names)]]
+    rank_kernel_ms = None
+    if world > 1:
+        tk = torch.tensor(kern_ms + [ms_total / args.steps], device=dev)
+        tg = [torch.zeros_like(tk) for _ in range(world)]
+        dist.all_gather(tg, tk)
+        rank_kernel_ms = [[round(float(v), 4) for v in t] for t in tg]  # per rank: k_pass, k_match, k_resolve_loss, step
     top = max(range(len(names)), key=lambda k: kern_ms[k])
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes_per_image(A, 107, Lmax) * B
@@ -323,12 +340,14 @@ def main():
 
     if rank == 0:
         # k_gt_prep, k_pass, k_match, k_resolve_loss (+ k_finalize after an NCCL all-reduce)
-        launches_per_step = 4 if (world == 1 or lf.peer_comm is not None) else 5
+        launches_per_step = 4 if (world == 1 or getattr(lf, "peer_comm", None) is not None or lf.process_group is None) else 5
         print(json.dumps({"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                           "roofline": roofline, "cpu_baseline": cpu_baseline,
+                          "host_enqueue_ms_per_step": [round(x, 4) for x in host_ms],
+                          "per_rank_kernel_and_step_ms": rank_kernel_ms,
                           "loss_check": float(res[0][0])}))
     if world > 1:
         barrier()

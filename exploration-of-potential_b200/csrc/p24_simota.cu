@@ -239,7 +239,7 @@ __device__ __forceinline__ void warp_gt_record(const float* __restrict__ row, fl
 // k_gt_prep: one CTA per image.  It lets k_pass launch at once (programmatic dependent launch): k_pass's CTAs stage
 // their first rows while this kernel runs and wait for it only before they read the records.
 #define PREP_THREADS 256
-__global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(Params p) {
+__global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(const __grid_constant__ Params p) {
     pdl_trigger();
     TMARK(3, blockIdx.x, 0);
     __shared__ int s_n;
@@ -727,7 +727,7 @@ __device__ __forceinline__ void claim_anchor(const Params& p, int b, int a, int 
     }
 }
 
-#define HIT_CAP 3072
+#define HIT_CAP 2112
 #define MATCH_WCAP (25 * P24_MAX_LEVELS)  // at most 5 x 5 cells per level pass the window test
 #define MAX_TILES 1024  // candidate counts of an image kept in shared memory (A <= 262144)
 
@@ -745,7 +745,8 @@ __device__ __forceinline__ float bound_H_thread(const float* __restrict__ rec, f
     return s * (1.0f / 48.0f);
 }
 
-#define EXACT_CAP 2048  // candidates the exact path can hold bounds for (more -> brute force)
+#define EXACT_CAP 2048   // candidates the exact path holds bounds for at a time
+#define EXACT_QCAP 512   // warp segments the exact path can keep (more -> brute force)
 struct MatchShared {
     float rec[GT_REC];
     int ccount[MAX_TILES];
@@ -753,7 +754,10 @@ struct MatchShared {
     float ev[1024];         // bracket: staged seed values; exact path: exact values of the survivors
     float ub[EXACT_CAP];    // exact path: per-candidate bounds
     float lb[EXACT_CAP];
-    int qseg[1024];         // exact path: survivors of the refined threshold
+    int qseg[2 * EXACT_QCAP];  // exact path: kept segments (index, candidate ballot); later the survivors of the threshold
+    float qsu[EXACT_QCAP];     // their value bounds, counts, positions in decreasing order of the bound
+    int qcnt[EXACT_QCAP];
+    int qorder[EXACT_QCAP];
     int hist[32];
     float top[P24_TOPK];
     KV kv[MATCH_WARPS];
@@ -891,14 +895,68 @@ __device__ __noinline__ float topk_sum_exact(const Params& p, MatchShared& S, in
             const float dm = sqrtf(fmaf(fx, fx, fy * fy)) * 1.0001f + 0.01f;
             const float u = fminf(bound_H_thread(S.rec, r1.x + dm), bound_Hstar_thread(S.rec, dm)) + 2e-5f;
             if (u < T0 && r1.x < 60000.0f) continue;  // (NaN bounds and tiny predicted radii stay in)
-            const int pos = atomicAdd(&S.cnt, cnt);
             const int q = atomicAdd(&S.nhit, 1);
-            if (pos + cnt <= EXACT_CAP && q < 512) {
-                S.qseg[2 * q] = si | (pos << 16);  // si < 8192, pos < 2048
+            const int pos = atomicAdd(&S.cnt, cnt);
+            if (q < EXACT_QCAP) {
+                S.qseg[2 * q] = si;
                 S.qseg[2 * q + 1] = __float_as_int(r1.w);  // which of the segment's 32 anchors are candidates
+                S.qsu[q] = (u == u && r1.x < 60000.0f) ? u : P24_POS_INF;
+                S.qcnt[q] = cnt;
+                S.qorder[q] = pos;  // the segment's first slot when everything fits (the usual case)
             } else {
                 S.overflow = 1;
             }
+        }
+    }
+    __syncthreads();
+    if (S.overflow) return NAN;
+    const int nq = S.nhit;
+    const bool all_fit = S.cnt <= EXACT_CAP;
+    __syncthreads();
+    if (all_fit) {
+        for (int q = tid; q < nq; q += MATCH_THREADS) {
+            S.qcnt[q] = S.qorder[q];
+            S.qorder[q] = q;
+        }
+        if (tid == 0) {
+            S.k = nq;
+            S.L = P24_NEG_INF;
+        }
+    }
+    // otherwise: the kept segments in decreasing order of their bound; the first ones that fit EXACT_CAP candidates are
+    // examined, and the best bound among the others (S.L) must end up below the refined threshold
+    for (int q = tid; q < nq && !all_fit; q += MATCH_THREADS) {
+        const float uq = S.qsu[q];
+        int rank = 0;
+        for (int j = 0; j < nq; ++j) rank += kv_gt(S.qsu[j], j, uq, q) ? 1 : 0;
+        S.qorder[rank] = q;
+    }
+    __syncthreads();
+    if (warp == 0 && !all_fit) {
+        int run = 0, ncut = nq;  // candidates so far; number of examined segments
+        for (int r0 = 0; r0 < nq && ncut == nq; r0 += 32) {
+            const int r = r0 + lane;
+            const int q = r < nq ? S.qorder[r] : 0;
+            const int c = r < nq ? S.qcnt[q] : 0;
+            int inc = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += t;
+            }
+            const bool fits = r < nq && run + inc <= EXACT_CAP;
+            if (fits) S.qcnt[q] = run + inc - c;  // from here on: the segment's first slot
+            const unsigned fm = __ballot_sync(0xffffffffu, fits);
+            const unsigned vm = __ballot_sync(0xffffffffu, r < nq);
+            const int nfit = __popc(fm);  // fits is a prefix of the valid lanes (counts are positive)
+            if (fm != vm) ncut = r0 + nfit;
+            const int last = __shfl_sync(0xffffffffu, inc, nfit > 0 ? nfit - 1 : 0);
+            if (nfit > 0) run += last;
+        }
+        if (lane == 0) {
+            S.k = ncut;
+            S.cnt = run;
+            S.L = ncut < nq ? S.qsu[S.qorder[ncut]] : P24_NEG_INF;
         }
     }
     __syncthreads();
@@ -906,15 +964,16 @@ __device__ __noinline__ float topk_sum_exact(const Params& p, MatchShared& S, in
     if (tid == 0) {
         g_tstamp[1][b * 20 + (int)blockIdx.y][9] = S.nhit;
         g_tstamp[1][b * 20 + (int)blockIdx.y][10] = S.cnt;
-        g_tstamp[1][b * 20 + (int)blockIdx.y][11] = S.overflow;
+        g_tstamp[1][b * 20 + (int)blockIdx.y][11] = S.k;
     }
     TMARK(1, b * 20 + (int)blockIdx.y, 16);
 #endif
-    if (S.overflow) return NAN;
-    const int n1 = S.cnt;
-    // the anchors of the kept segments (a segment is 32 consecutive anchors; its candidates are the set bits)
-    for (int q = warp; q < S.nhit; q += MATCH_WARPS) {
-        const int si = S.qseg[2 * q] & 0xFFFF, pos = S.qseg[2 * q] >> 16;
+    const int n1 = S.cnt, ncut = S.k;
+    const float su_rest = S.L;
+    // the anchors of the examined segments (a segment is 32 consecutive anchors; its candidates are the set bits)
+    for (int r = warp; r < ncut; r += MATCH_WARPS) {
+        const int q = S.qorder[r];
+        const int si = S.qseg[2 * q], pos = S.qcnt[q];
         const unsigned m = (unsigned)S.qseg[2 * q + 1];
         if ((m >> lane) & 1u) S.hit[pos + __popc(m & ((1u << lane) - 1u))] = si * 32 + lane;
     }
@@ -970,6 +1029,7 @@ __device__ __noinline__ float topk_sum_exact(const Params& p, MatchShared& S, in
         width = width * (1.0f / 32.0f);
     }
     const float tcur = fmaxf(T0, lo - 1e-6f);
+    if (!(su_rest < tcur)) return NAN;  // a segment that was not examined could still hold a top-10 value (rare)
     for (int i = tid; i < n1; i += MATCH_THREADS)
         if (!(S.ub[i] < tcur)) {
             const int at = atomicAdd(&S.nev, 1);
@@ -1185,7 +1245,7 @@ union PassShared {
     WindowShared w;
 };
 
-__global__ void __launch_bounds__(P24_THREADS, 4) k_pass(Params p) {
+__global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__ Params p) {
     extern __shared__ float4 s_dyn4[];
     __shared__ PassShared S;
     __shared__ int s_item;
@@ -1272,7 +1332,7 @@ __device__ __noinline__ void finish_gt(const Params& p, MatchShared& S, int b, i
 // the k smallest costs of its valid pairs -> claims (rank counting; spill into the penalised regime when the GT
 // has fewer valid anchors than k)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(Params p) {
+__global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(const __grid_constant__ Params p) {
     // images vary fastest over the grid: the low GT rows (the real ones: valid rows come first) are dispatched before
     // the rows beyond num_gt, which leave at once
     const int g = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
@@ -1297,9 +1357,9 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(Params p) {
         cnt += c;
     }
     // everything the bracket reads, staged by all threads in one round trip (S.hit / S.ev are free until a slow path)
-    float4* s_tb = reinterpret_cast<float4*>(S.hit);   // [2 * tiles] float4   (tiles <= 384 here, else read in place)
+    float4* s_tb = reinterpret_cast<float4*>(S.hit);   // [2 * tiles] float4   (tiles <= 256 here, else read in place)
     float* s_sv = S.ev;                                // [P24_SEEDS * tiles]
-    const bool staged = p.tiles <= 384;
+    const bool staged = p.tiles <= 256;
     if (staged) {
         const float4* tbg = reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
         for (int i = tid; i < 2 * p.tiles; i += MATCH_THREADS) s_tb[i] = tbg[i];
@@ -1535,7 +1595,7 @@ __device__ __forceinline__ int valid_argmin(const Params& p, int b, int n, int a
 
 __device__ __forceinline__ long long to_fix(double x) { return __double2ll_rn(x * FIX_SCALE); }
 
-__global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(Params p) {
+__global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(const __grid_constant__ Params p) {
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 0);
     pdl_wait();
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 1);

@@ -15,8 +15,9 @@ flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 if len(sys.argv) > 5:
     B, size, G, Lmax = [int(x) for x in sys.argv[2:6]]
 dev = "cuda:0"
-sets = [(synth.make_head_outputs(B, size, 80, seed=1 + 100 * i).to(dev),
-         synth.make_labels(B, G, Lmax, size, 80, seed=1 + 100 * i, kind="smooth").to(dev)) for i in range(5)]
+SEED0 = int(os.environ.get("P24_SEED0", "1"))  # bench.py rank r uses 1 + 1000 r
+sets = [(synth.make_head_outputs(B, size, 80, seed=SEED0 + 100 * i).to(dev),
+         synth.make_labels(B, G, Lmax, size, 80, seed=SEED0 + 100 * i, kind="smooth").to(dev)) for i in range(5)]
 xs, ys, ss = synth.make_grids(size)
 g = [[t.to(dev) for t in l] for l in (xs, ys, ss)]
 lf = Loss_Function(80)
@@ -64,7 +65,7 @@ for k, nm, slots in order:
             print("      slow GT", int(ci), "L", f32(t[1, ci, 12]), "U", f32(t[1, ci, 13]), "tmax", f32(t[1, ci, 14]), "rgmax", f32(t[1, ci, 15]))
         for ci in np.nonzero(sl)[0]:
             r = t[1, ci]
-            print(f"      slow GT {int(ci)}: segments {r[9]} candidates {r[10]} overflow {r[11]} survivors {r[7]} | seg scan {(r[16]-r[4])/1e3:.1f} bounds {(r[17]-r[16])/1e3:.1f} "
+            print(f"      slow GT {int(ci)}: segments {r[9]} candidates {r[10]} examined segments {r[11]} survivors {r[7]} | seg scan {(r[16]-r[4])/1e3:.1f} bounds {(r[17]-r[16])/1e3:.1f} "
                   f"threshold {(r[18]-r[17])/1e3:.1f} exact {(r[19]-r[18])/1e3:.1f} rest {(r[5]-r[19])/1e3:.1f} us")
         wid = f32(t[1][ok][:, 13]) - f32(t[1][ok][:, 12])
         print("   bracket width U-L quantiles (10/50/90/99 %):", np.percentile(wid, [10, 50, 90, 99]))
