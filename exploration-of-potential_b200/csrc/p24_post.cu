@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     __shared__ int s_prefix[1025];                               // candidates before tile t (tiles <= 1024)
     __shared__ unsigned long long s_mask[64];
     __shared__ float4 s_kept[64];
-    __shared__ int s_nkept, s_ndet;
+    __shared__ int s_nkept;
     __shared__ float s_red[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -259,7 +259,6 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
             acc += p.tcount[(long long)b * p.tiles + t];
         }
         s_prefix[p.tiles] = acc;
-        s_ndet = 0;
     }
     __syncthreads();
     const int n = s_prefix[p.tiles];
@@ -333,7 +332,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     __shared__ int s_cellstart[NCELL_MAX + 2];
     __shared__ int s_cellfill[NCELL_MAX + 1];
     __shared__ float s_redf[3][32];
-    __shared__ int s_flag, s_cn, s_last;
+    __shared__ int s_cn, s_last;
     __shared__ int s_idx[64];
     float xlo = INFINITY, xhi = -INFINITY, wmx = 0.0f;
     bool finite = true;
