@@ -766,6 +766,7 @@ struct MatchShared {
     float T, L, tau, tmax, dmax;
     int wanchor[MATCH_WCAP];   // the GT's valid (in window, in polygon) anchors and their costs
     float wcost[MATCH_WCAP];
+    int wrank[MATCH_WCAP];     // how many valid pairs cost less
 };
 
 template <bool MAX>
@@ -1281,49 +1282,17 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
     pdl_trigger();
 }
 
-// dynamic k is known: record it and select the k smallest costs among the GT's valid pairs (losses.py:460-464), ties ->
-// lower anchor index; spill into the penalised regime when there are fewer valid pairs than k.  The GT's context is in S.
-__device__ __noinline__ void finish_gt(const Params& p, MatchShared& S, int b, int g, int k) {
+// dynamic k is known: record it and claim the k smallest costs among the GT's valid pairs (losses.py:460-464; the valid
+// pairs and their ranks -- ties -> lower anchor index -- were prepared while the bracket was being evaluated); spill into
+// the penalised regime when there are fewer valid pairs than k.
+__device__ __forceinline__ void claim_selected(const Params& p, MatchShared& S, int b, int g, int k) {
     const int tid = threadIdx.x;
-    const int wslot = b * p.Lmax + g;
     __syncthreads();
-    if (tid == 0) {
-        p.dyn_k[wslot] = k;
-        S.nvalid = 0;
-    }
-    __syncthreads();
-    {
-        const float* tab = p.wtab + (long long)wslot * P24_WT_STRIDE;
-        const int nslot = P24_WSLOTS * p.nlev;
-        for (int t = tid; t < nslot; t += MATCH_THREADS) {
-            const int l = t / P24_WSLOTS, r = t - l * P24_WSLOTS;
-            const float c = tab[t];
-            const float ox = tab[P24_WT_HDR + 2 * l], oy = tab[P24_WT_HDR + 2 * l + 1];  // issued with the cost: one round trip
-            if (c < P24_POS_INF) {
-                const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
-                const int ix = __float_as_int(ox) + sx, iy = __float_as_int(oy) + sy;
-                const int slot = atomicAdd(&S.nvalid, 1);
-                if (slot < MATCH_WCAP) {
-                    S.wanchor[slot] = p.lev[l].off + iy * p.lev[l].W + ix;
-                    S.wcost[slot] = c;
-                } else {
-                    atomicOr(p.err_flag, 1);
-                }
-            }
-        }
-    }
-    __syncthreads();
+    if (tid == 0) p.dyn_k[b * p.Lmax + g] = k;
     const int nv = min(S.nvalid, MATCH_WCAP);
     const int take = min(k, nv);
-    if (tid < nv) {
-        const float ci = S.wcost[tid];
-        const int ai = S.wanchor[tid];
-        int before = 0;
-        for (int j = 0; j < nv; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
-        if (before < take) claim_anchor(p, b, ai, g);
-    }
+    if (tid < nv && S.wrank[tid] < take) claim_anchor(p, b, S.wanchor[tid], g);
     if (k > nv) spill_claims(p, S, b, g, nv, k - nv);
-    __syncthreads();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1366,10 +1335,36 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(const __grid_constan
         const float* svg = p.sval + (long long)wslot * (P24_SEEDS * p.tiles);
         for (int i = tid; i < P24_SEEDS * p.tiles; i += MATCH_THREADS) s_sv[i] = svg[i];
     }
-    if (tid == 0) S.cnt = 0;
+    // the GT's window table (costs of its valid pairs), requested in the same round trip: the selection is prepared by
+    // warps 1..7 while warp 0 evaluates the bracket
+    const float* tab = p.wtab + (long long)wslot * P24_WT_STRIDE;
+    const int nslot = P24_WSLOTS * p.nlev;  // <= 196 < MATCH_THREADS
+    float wc = P24_POS_INF, wox = 0.0f, woy = 0.0f;
+    if (tid < nslot) {
+        const int l = tid / P24_WSLOTS;
+        wc = tab[tid];
+        wox = tab[P24_WT_HDR + 2 * l];
+        woy = tab[P24_WT_HDR + 2 * l + 1];
+    }
+    if (tid == 0) {
+        S.cnt = 0;
+        S.nvalid = 0;
+    }
     __syncthreads();
     cnt = warp_sum_i(cnt);
     if (lane == 0 && cnt) atomicAdd(&S.cnt, cnt);
+    if (wc < P24_POS_INF) {
+        const int l = tid / P24_WSLOTS, r = tid - l * P24_WSLOTS;
+        const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+        const int ix = __float_as_int(wox) + sx, iy = __float_as_int(woy) + sy;
+        const int slot = atomicAdd(&S.nvalid, 1);
+        if (slot < MATCH_WCAP) {
+            S.wanchor[slot] = p.lev[l].off + iy * p.lev[l].W + ix;
+            S.wcost[slot] = wc;
+        } else {
+            atomicOr(p.err_flag, 1);
+        }
+    }
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     __syncthreads();
     TMARK(1, MCTA, 2);
@@ -1458,6 +1453,16 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(const __grid_constan
             S.T = T;
             S.tmax = tm;
         }
+    } else {
+        // ---- meanwhile: rank of every valid pair by (cost, anchor) -----------------------------------------------------
+        const int nv = min(S.nvalid, MATCH_WCAP);
+        for (int e = tid - 32; e < nv; e += MATCH_THREADS - 32) {
+            const float ci = S.wcost[e];
+            const int ai = S.wanchor[e];
+            int before = 0;
+            for (int j = 0; j < nv; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
+            S.wrank[e] = before;
+        }
     }
     __syncthreads();
     TMARK(1, MCTA, 4);
@@ -1478,7 +1483,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(const __grid_constan
         k = S.k;
     }
     TMARK(1, MCTA, 5);
-    finish_gt(p, S, b, g, min(k, ncand));  // torch.topk would raise beyond the candidate count; clamp instead
+    claim_selected(p, S, b, g, min(k, ncand));  // torch.topk would raise beyond the candidate count; clamp instead
     TMARK(1, MCTA, 6);
 }
 
