@@ -240,6 +240,10 @@ __device__ __forceinline__ void warp_gt_record(const float* __restrict__ row, fl
 // their first rows while this kernel runs and wait for it only before they read the records.
 #define PREP_THREADS 256
 __global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(const __grid_constant__ Params p) {
+    // launched as a programmatic dependent of whatever precedes it in the stream (in back-to-back steps: the previous
+    // step's k_resolve_loss, which triggers at once): resident early, it starts the moment that work is complete.  It
+    // must not let k_pass go before that: k_pass draws tickets that the previous step's last CTA resets.
+    pdl_wait();
     pdl_trigger();
     TMARK(3, blockIdx.x, 0);
     __shared__ int s_n;
@@ -1602,6 +1606,7 @@ __device__ __forceinline__ long long to_fix(double x) { return __double2ll_rn(x 
 
 __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(const __grid_constant__ Params p) {
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 0);
+    pdl_trigger();  // the next step's k_gt_prep may become resident (it waits for this grid's completion)
     pdl_wait();
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 1);
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -1887,8 +1892,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
         if (n_sm <= 0) n_sm = 148;
     }
     prof_mark(0, st);
-    // k_gt_prep never waits for its predecessor in the stream, so it is launched in plain stream order
-    e = launch(k_gt_prep, dim3(B), dim3(PREP_THREADS), 0, st, false, p);
+    e = launch(k_gt_prep, dim3(B), dim3(PREP_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     {
         const long long items = (long long)B * p.tiles + (long long)B * Lmax * n_levels;
