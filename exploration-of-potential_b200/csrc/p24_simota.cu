@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(const __grid_constant_
 // shared device helpers
 // -------------------------------------------------------------------------------------------
 // Out-of-line copies of the two heavy scalar routines: the kernels call them from many places, and inlining every
-// call made k_gt_match 17k instructions long (instruction-cache bound).
+// call made the per-GT kernel 17k instructions long (instruction-cache bound).
 __device__ __noinline__ float ray_loss(float rg, float rp, float d) { return p24_ray_loss(rg, rp, d); }
 __device__ __noinline__ float edge_angle(float sx, float sy, float ex, float ey) { return p24_edge_angle(sx, sy, ex, ey); }
 
@@ -717,7 +717,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
 }
 
 // -------------------------------------------------------------------------------------------
-// k_gt_match
+// per-GT helpers of k_match
 // -------------------------------------------------------------------------------------------
 // GT g selects anchor a: count the claim; the first claimant also puts the anchor on the image's claimed list
 __device__ __forceinline__ void claim_anchor(const Params& p, int b, int a, int g) {
