@@ -21,6 +21,7 @@
 // compiled with -fmad=false), the sort is stable, and batched NMS adds  class * (max_coordinate + 1)  to the boxes in
 // fp32 exactly like _batched_nms_coordinate_trick.
 #include "p24_common.cuh"
+#include "p24_host.h"
 
 namespace {
 
@@ -603,13 +604,14 @@ extern "C" int p24_postprocess(const float* prediction, int64_t img_stride, int6
     cudaStream_t st = (cudaStream_t)stream;
     const int npad_max = next_pow2(A);
     const size_t smem_nms = (size_t)(npad_max <= SORT_SMEM_MAX ? npad_max : 0) * sizeof(unsigned long long);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (p24::dev_once(1u << 8)) {  // per device: a process may drive several GPUs
         cudaFuncSetAttribute(k_post_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_post_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_MAX * 8);
-        attr_done = true;
     }
+    p24::prof_mark(4, st);
     k_post_filter<<<dim3(tiles, B), POST_THREADS, smem_filter, st>>>(p);
+    p24::prof_mark(5, st);
     k_post_nms<<<B, NMS_THREADS, smem_nms, st>>>(p);
+    p24::prof_mark(6, st);
     return (int)cudaGetLastError();
 }

@@ -26,6 +26,7 @@
 // Compile with -fmad=false: the discrete decisions hang on fp32 thresholds evaluated in the
 // reference's operation order; bounds and fast paths use explicit fmaf.
 #include "p24_common.cuh"
+#include "p24_host.h"
 #include <string.h>
 
 namespace {
@@ -1663,11 +1664,10 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(const __grid_co
         }
         if (lane < 26) acc += to_fix(contrib);
     }
-    if (!p.sums28) return;
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 4);
     if (lane < 26) s_acc[warp][lane] = acc;
     __syncthreads();
-    if (tid < 26) {
+    if (tid < 26 && p.sums28) {
         long long t = 0;
 #pragma unroll
         for (int w = 0; w < P24_WARPS; ++w) t += s_acc[w][tid];
@@ -1691,6 +1691,14 @@ __global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(const __grid_co
     TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 5);
     if (!s_last) return;
     __threadfence();
+    if (!p.sums28) {  // assignment only (get_assignments): nothing to reduce, but the tickets must be reset
+        if (tid == 0) {
+            p.ticket[0] = 0u;
+            p.ticket[1 + p.B] = 0u;
+            p.ticket[2 + p.B] = 0u;
+        }
+        return;
+    }
     // ---- last CTA: batch sums (integer adds over the images: exact), the all-anchor objectness term in a fixed
     // order, then the optional finalize ------------------------------------------------------------------------------
     if (tid < 26) {
@@ -1765,14 +1773,8 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
 
 size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC_HEAD * sizeof(float); }
 
-// optional per-stage timing (profiling aid for bench.py; process-global, not thread-safe)
-#define N_STAGES 3
-bool g_prof_on = false;
-cudaEvent_t g_prof_ev[N_STAGES + 1];
-bool g_prof_have = false;
-inline void prof_mark(int i, cudaStream_t st) {
-    if (g_prof_on) cudaEventRecord(g_prof_ev[i], st);
-}
+inline void prof_mark(int i, cudaStream_t st) { p24::prof_mark(i, st); }
+#define g_prof_on (p24::prof_on())
 
 template <typename K>
 cudaError_t launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Params& p) {
@@ -1877,20 +1879,10 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     }
     cudaStream_t st = (cudaStream_t)stream;
 
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_done = true;
-    }
+    if (p24::dev_once(1u << 0)) cudaFuncSetAttribute(k_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     const bool pdl = !(flags & P24_F_NO_PDL) && !g_prof_on;
     cudaError_t e = cudaSuccess;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
+    const int n_sm = p24::dev_info().n_sm;
     prof_mark(0, st);
     e = launch(k_gt_prep, dim3(B), dim3(PREP_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
@@ -1946,30 +1938,6 @@ extern "C" int p24_loss_finalize(const float* sums28, float* state26, float* res
     if (!sums28 || !state26 || !result54 || !weights_n27) return P24_E_BADARG;
     k_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(sums28, state26, result54, weights_n27);
     return (int)cudaGetLastError();
-}
-
-extern "C" int p24_profile_enable(int on) {
-    if (on && !g_prof_have) {
-        for (int i = 0; i <= N_STAGES; ++i) {
-            const cudaError_t e = cudaEventCreate(&g_prof_ev[i]);
-            if (e != cudaSuccess) return (int)e;
-        }
-        g_prof_have = true;
-    }
-    g_prof_on = on != 0;
-    return 0;
-}
-
-extern "C" int p24_profile_read(float* h_ms6) {
-    if (!g_prof_have || !h_ms6) return P24_E_BADARG;
-    for (int i = 0; i < 6; ++i) h_ms6[i] = 0.0f;
-    cudaError_t e = cudaEventSynchronize(g_prof_ev[N_STAGES]);
-    if (e != cudaSuccess) return (int)e;
-    for (int i = 0; i < N_STAGES; ++i) {
-        e = cudaEventElapsedTime(&h_ms6[i], g_prof_ev[i], g_prof_ev[i + 1]);
-        if (e != cudaSuccess) return (int)e;
-    }
-    return 0;
 }
 
 #ifdef P24_TIMING

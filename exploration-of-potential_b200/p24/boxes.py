@@ -20,18 +20,19 @@ from .engine import _check_cuda_f32, _stream_ptr
 _WS = {}
 
 
-_COEF = None
+_COEF = {}
 
 
-def spiral_coefficients():
-    """theta_k * cos(theta_k), theta_k * sin(theta_k) exactly as the reference evaluates them (boxes.py:30-33):
-    fp32 torch ops on the host (sic: not cos / sin).  Evaluated once."""
-    global _COEF
-    if _COEF is None:
-        theta = torch.tensor(15 * np.pi / 180)
-        th = torch.arange(24) * theta
-        _COEF = ((th * torch.cos(th)).contiguous(), (th * torch.sin(th)).contiguous())
-    return _COEF
+def spiral_coefficients(device="cpu"):
+    """theta_k * cos(theta_k), theta_k * sin(theta_k) exactly as the reference evaluates them (boxes.py:30-33): fp32
+    torch ops ON THE DEVICE OF THE PREDICTION (sic: not cos / sin).  Evaluated once per device and kept on the host
+    (the C ABI takes them as host constants); a CUDA device costs one read-back the first time."""
+    key = str(torch.device(device))
+    if key not in _COEF:
+        theta = torch.tensor(15 * np.pi / 180, device=device)
+        th = torch.arange(24, device=device) * theta
+        _COEF[key] = ((th * torch.cos(th)).cpu().contiguous(), (th * torch.sin(th)).cpu().contiguous())
+    return _COEF[key]
 
 
 def _workspace(key, nbytes, device):
@@ -42,9 +43,11 @@ def _workspace(key, nbytes, device):
     return buf, (buf.data_ptr() + 255) & ~255
 
 
-def postprocess_raw(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, class_agnostic=False, want_rects=False):
+def postprocess_raw(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, class_agnostic=False, want_rects=False,
+                    coef=None):
     """Device-resident result of the whole batch: (cand_count[B], det_count[B], det_rows[B, A, 29], keep_idx[B, A],
-    rects[B, A, 4] | None).  No host synchronisation."""
+    rects[B, A, 4] | None).  No host synchronisation.  ``coef``: (coef_x[24], coef_y[24]) host fp32 tensors overriding the
+    coefficients evaluated on the prediction's device (tests against CPU-made fixtures pass the CPU ones)."""
     lib = _lib.load()
     _check_cuda_f32(prediction, "prediction")
     if prediction.dim() != 3 or prediction.shape[2] != 27 + num_classes:
@@ -60,7 +63,7 @@ def postprocess_raw(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, class
     rects = torch.empty((B, A, 4), dtype=torch.float32, device=dev) if want_rects else None
     nbytes = lib.p24_postprocess_workspace_bytes(B, A)
     _, ws_ptr = _workspace(("post", B, A, str(dev)), nbytes, dev)
-    cx, cy = spiral_coefficients()
+    cx, cy = spiral_coefficients(dev) if coef is None else coef
     cxp = cx.numpy().ctypes.data_as(C.POINTER(C.c_float))
     cyp = cy.numpy().ctypes.data_as(C.POINTER(C.c_float))
     # the reference compares fp32 tensors with Python floats: the scalars are rounded to fp32 (boxes.py:55)

@@ -199,6 +199,22 @@ class Loss_Function(nn.Module):
         self.last_cls_loss = state[25]
         return result54, weights27, asg
 
+    # -- bookkeeping of the asynchronous path ---------------------------------------------------------------
+    def wait_results(self):
+        """Order everything ``forward_async`` has enqueued before later work of the current stream."""
+        return None
+
+    def check_errors(self):
+        """Raise ``P24Error`` when a kernel reported an internal error (list overflow, peer time-out).  One host
+        read of a 4-byte flag: ``forward`` calls it with its own result read, ``forward_async`` does not."""
+        return None
+
+    def exchange_wait_us(self):
+        return [0.0]
+
+    def path_stats(self):
+        return None
+
     def forward(self, outputs_train, labels):
         outputs = outputs_train[3]
         if torch.is_grad_enabled() and outputs.requires_grad:

@@ -47,20 +47,25 @@ def num_anchors(img_size: int = 640, strides: Sequence[int] = STRIDES) -> int:
 def make_head_outputs(batch: int, img_size: int = 640, num_classes: int = 80, seed: int = 0,
                       device="cpu", strides: Sequence[int] = STRIDES, prior_logit: float = -4.6,
                       raw_std: float = 0.5) -> torch.Tensor:
-    """Random-init-like decoded head output ``[B, A, 27 + nc]`` (training layout, logits)."""
-    g = torch.Generator().manual_seed(seed)
+    """Random-init-like decoded head output ``[B, A, 27 + nc]`` (training layout, logits).
+
+    ``device="cpu"`` (default) draws from a CPU generator: the same tensors on every host.  With a CUDA device the
+    values are drawn and decoded there (large batches: bench.py configs[4]); same distributions, different numbers."""
+    dev = torch.device(device)
+    gen_dev = dev if dev.type == "cuda" else torch.device("cpu")
+    g = torch.Generator(device=gen_dev).manual_seed(seed)
     A = num_anchors(img_size, strides)
     C = 27 + num_classes
-    raw = torch.randn(batch, A, C, generator=g) * raw_std
-    raw[:, :, 26:] += prior_logit
+    out = torch.randn(batch, A, C, generator=g, device=gen_dev) * raw_std
+    out[:, :, 26:] += prior_logit
     xs, ys, ss = make_grids(img_size, strides)
-    gx = torch.cat(xs, 1)[0]
-    gy = torch.cat(ys, 1)[0]
-    st = torch.cat(ss, 1)[0]
-    out = raw.clone()
-    out[:, :, 0] = (raw[:, :, 0] + gx) * st
-    out[:, :, 1] = (raw[:, :, 1] + gy) * st
-    out[:, :, 2:26] = torch.exp(raw[:, :, 2:26]) * st[None, :, None]
+    gx = torch.cat(xs, 1)[0].to(gen_dev)
+    gy = torch.cat(ys, 1)[0].to(gen_dev)
+    st = torch.cat(ss, 1)[0].to(gen_dev)
+    raw01 = out[:, :, 0:2].clone()
+    out[:, :, 0] = (raw01[:, :, 0] + gx) * st
+    out[:, :, 1] = (raw01[:, :, 1] + gy) * st
+    out[:, :, 2:26] = torch.exp(out[:, :, 2:26]) * st[None, :, None]
     return out.to(device)
 
 
