@@ -9,53 +9,56 @@
 #include "p24_math.cuh"
 
 #define P24_THREADS 256
-#define P24_SEEDS 2  // seeds per (GT, tile); 1 and 4 measured: no gain (k_pass -1.3 / +2 us, k_match +3.5 / 0 us)
 #define P24_MAX_LEVELS 4   // feature levels of the anchor grid
 #define P24_WSIDE 7        // a GT's centre window lies inside a 7 x 7 block of grid cells per level (5 x 5 pass the test)
 #define P24_WSLOTS (P24_WSIDE * P24_WSIDE)
 #define P24_WT_HDR (P24_WSLOTS * P24_MAX_LEVELS)   // wtab row: [slot costs | ix0, iy0 per level (int bits)]
 #define P24_WT_STRIDE (P24_WT_HDR + 2 * P24_MAX_LEVELS + 4)   // 208 floats
 #define P24_WARPS (P24_THREADS / 32)
+#define P24_LISTCAP 2048   // pair values a GT's top-10 list can hold (more -> brute-force path of k_tail)
 
-// ---- per-GT record (floats), built once per image by the anchor pass ---------------------------
+// ---- per-GT record (floats): k_prep writes it, the seed items of k_pass add [4] and [58] ----------------------
 // [0] cx  [1] cy  [2] rin2  [3] rrej2   (one 128-bit shared-memory load for the per-pair tests)
-// [4] class (as float)  [5] rgmax  [6] rgmin  [7] pad
-// [8..31] vertex x  [32..55] vertex y  [56] mean rg^2  [57] mean rg  [58..59] pad  [60..83] ray length rg
+// [4] far2  [5] class (as float)  [6] rgmax  [7] rgmin
+// [8..31] vertex x  [32..55] vertex y  [56] mean rg^2  [57] mean rg  [58] T  [59] pad  [60..83] ray length rg
 #define GT_CX 0
 #define GT_CY 1
 #define GT_RIN2 2    // squared radius of a disc around (cx, cy) that lies inside the polygon (0: none)
 #define GT_RREJ2 3   // squared radius beyond which the angle sum is provably < 349 degrees
-#define GT_CLS 4
-#define GT_RGMAX 5
-#define GT_RGMIN 6
+#define GT_FAR2 4    // squared centre distance below which no prediction's pair value can reach T (0: none)
+#define GT_CLS 5
+#define GT_RGMAX 6
+#define GT_RGMIN 7
 #define GT_VX 8
 #define GT_VY 32
-#define GT_RGMS 56    // mean of rg^2 (seed ranking)
+#define GT_RGMS 56    // mean of rg^2
 #define GT_RGMEAN 57  // mean of rg
-#define GT_RG 60      // ray lengths come last: the anchor pass keeps only the first GT_REC_HEAD floats in shared memory
-#define GT_REC_HEAD 60
+#define GT_T 58       // certified lower bound of the GT's 10th largest pair value over the candidates (-inf: none)
+#define GT_RG 60
 #define GT_REC 84
 
 static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// status words (workspace): sticky error bits + path statistics, read back by p24_read_status
+#define ST_ERR 0        // P24_ERR_* bits
+#define ST_BRUTE 1      // GTs whose dynamic k took the brute-force path (cumulative)
+#define ST_SPILL 2      // GTs that spilled into the penalised regime (cumulative)
+#define ST_LISTMAX 3    // longest top-10 list seen
+#define ST_WAITCYC 4    // clock cycles the last fused all-reduce waited for its peers
+#define ST_WORDS 8
+
 struct P24Workspace {
+    size_t ticket;      // [4] unsigned: work-queue head of k_pass, largest num_gt, completion count of k_tail, seed-queue head
+    size_t acc_fix;     // [28] int64   fixed-point loss sums of the batch (zero between calls)
+    size_t status;      // [ST_WORDS] int
+    size_t seed_done;   // [B] int      seed items of the image that are complete (zero between calls)
+    size_t ncand;       // [B] int      candidate anchors of the image (zero between calls)
+    size_t lcount;      // [B, Lmax] int   entries in the GT's top-10 list (zero between calls)
     size_t gt_rec;      // [B, Lmax, GT_REC] float
-    size_t clist;       // [B, tiles, 256] float4  candidate anchors of a tile, compacted: (pred cx, pred cy, rpmax, anchor idx bits)
-    size_t sval;        // [B, Lmax, P24_SEEDS * tiles] float   certified lower bounds of the pair values of the tile's best
-                        //                                       candidates by the seed proxy (-inf: none), written by the anchor pass
     size_t wtab;        // [B, Lmax, P24_WT_STRIDE] float  SimOTA cost of the GT's centre-window anchors by window slot
                         //                                  (+inf: not in the window / not in the polygon) + the window origins
-    size_t tbox;        // [B, tiles, 8] float          bounding box of a tile's candidate centres (xmin, xmax, ymin, ymax), max rpmax
-    size_t seg;         // [B, tiles, 8, 8] float       the same per warp segment of a tile's list + count and first rank
-    size_t ccount;      // [B, tiles] int          candidates per tile
-    size_t claim_cnt;   // [B, A] int      number of GTs that selected the anchor
-    size_t claim_gt;    // [B, A] int      the GT that selected the anchor (meaningful when claim_cnt == 1)
-    size_t obj_part;    // [B * tiles] double   per-block sums of BCEWithLogits(obj, 0)
-    size_t claimed;     // [B, 10 * Lmax] int   anchors claimed by at least one GT (arrival order)
-    size_t nclaimed;    // [B] int
-    size_t acc_fix;     // [B, 28] int64        fixed-point loss sums of the image (zero between calls)
-    size_t ticket;      // [3 + B] unsigned: batch counter, one counter per image, work-queue head of k_pass, largest num_gt (zero between calls)
-    size_t err_flag;    // [1] int     sticky internal error bits (list overflow)
+    size_t list;        // [B, Lmax, P24_LISTCAP] float    pair values >= T of the GT's far candidates (arrival order)
+    size_t cbits;       // [B, tiles * 8] unsigned         candidate bitmap (bit l of word w: anchor 32 w + l)
     size_t total;
 };
 
@@ -65,24 +68,18 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     P24Workspace w;
     size_t off = 0;
     const size_t BL = (size_t)B * (size_t)Lmax;
-    const size_t BA = (size_t)B * (size_t)A;
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
-    w.ticket = off;     off = p24_align(off + (size_t)(3 + B) * sizeof(unsigned));
-    w.acc_fix = off;    off = p24_align(off + (size_t)B * 28 * sizeof(long long));
-    w.err_flag = off;   off = p24_align(off + sizeof(int));
+    w.ticket = off;     off = p24_align(off + 4 * sizeof(unsigned));
+    w.acc_fix = off;    off = p24_align(off + 28 * sizeof(long long));
+    w.status = off;     off = p24_align(off + ST_WORDS * sizeof(int));
+    w.seed_done = off;  off = p24_align(off + (size_t)B * sizeof(int));
+    w.ncand = off;      off = p24_align(off + (size_t)B * sizeof(int));
+    w.lcount = off;     off = p24_align(off + BL * sizeof(int));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
-    w.clist = off;      off = p24_align(off + NB * P24_THREADS * 4 * sizeof(float));
-    w.ccount = off;     off = p24_align(off + NB * sizeof(int));
-    w.sval = off;       off = p24_align(off + BL * P24_SEEDS * (size_t)p24_tiles(A) * sizeof(float));
     w.wtab = off;       off = p24_align(off + BL * P24_WT_STRIDE * sizeof(float));
-    w.tbox = off;       off = p24_align(off + NB * 8 * sizeof(float));
-    w.seg = off;        off = p24_align(off + NB * P24_WARPS * 8 * sizeof(float));
-    w.claim_cnt = off;  off = p24_align(off + BA * sizeof(int));
-    w.claim_gt = off;   off = p24_align(off + BA * sizeof(int));
-    w.obj_part = off;   off = p24_align(off + NB * sizeof(double));
-    w.claimed = off;    off = p24_align(off + BL * P24_TOPK * sizeof(int));
-    w.nclaimed = off;   off = p24_align(off + (size_t)B * sizeof(int));
+    w.list = off;       off = p24_align(off + BL * P24_LISTCAP * sizeof(float));
+    w.cbits = off;      off = p24_align(off + NB * P24_WARPS * sizeof(unsigned));
     w.total = off;
     return w;
 }

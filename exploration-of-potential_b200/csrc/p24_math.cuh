@@ -61,7 +61,8 @@ P24_HD float p24_ray_loss(float rg, float rp, float d, float* inter_out = nullpt
     const float ag = P24_PI * (rg * rg);
     const float ap = P24_PI * (rp * rp);
     const float uni = (ag + ap) - inter;
-    const float iou = inter / (uni + 1e-6f);
+    // (apart: inter is +0 and uni + 1e-6 is positive or NaN, which reaches giou through uni anyway)
+    const float iou = apart ? 0.0f : inter / (uni + 1e-6f);
     const float cl = nested ? rmax : (((rg + rp) + d) / 2.0f);
     const float cs = P24_PI * (cl * cl);
     const float giou = iou - ((cs - uni) / cs);

@@ -6,22 +6,26 @@
 //   Loss_Function.dynamic_k_matching                                 models/losses.py:444-494
 //   the loss sums and re-weighting of Loss_Function.forward          models/losses.py:246-345
 //
-// Kernel chain (caller's stream, no host synchronisation, programmatic dependent launch between stages):
-//   k_pass         two kinds of CTA side by side, both self-sufficient (each computes nlabel and the per-GT records
-//                  of its image from the label rows):
-//                  - anchor CTAs, one per 256-anchor tile: the ONE pass over the head output (cp.async reads of the
-//                    27 geometry channels of every row).  Candidate mask (polygon test OR centre window) with
-//                    geometric pruning and an atan2-free angle test, the compacted candidate list, per-tile seed
-//                    values for the top-10 bracket, sum BCEWithLogits(obj, 0), outputs initialised to background;
-//                  - centre-window CTAs: the (GT, centre-window anchor) pairs enumerated from the level grids:
-//                    polygon test, exact pair value and SimOTA cost -> the GT's window cost table
-//   k_match        one CTA per GT: dynamic k from the top-10-largest pair values over the candidates (bracketed by
-//                  seed values and a monotone upper bound; bound-filtered exact evaluation otherwise), then the k
-//                  smallest costs of the window table -> claims (spill into the penalised regime when there are
-//                  too few valid anchors)
-//   k_resolve_loss one warp per claimed anchor: conflict resolution (argmin over all GTs), fg_mask / matched_gt /
-//                  pred_iou, the 28 loss sums; the last CTA reduces them in a fixed order and, when asked,
-//                  applies the normalisation and the stateful re-weighting (losses.py:280-345)
+// Kernel chain (caller's stream, no host synchronisation, programmatic dependent launch between the stages):
+//   k_prep   one CTA per image: nlabel (losses.py:190) and the per-GT records (ray lengths, inscribed / reject radii)
+//   k_pass   persistent CTAs drawing work items from ticket counters:
+//            - seed items, one per GT: a handful of anchors that are certainly candidates (centre windows, inscribed
+//              discs and polygon tips of the farthest other GTs) are evaluated; the 10th best value T is a certified
+//              lower bound of the GT's 10th largest pair value, and far2 the squared centre distance below which no
+//              prediction whatsoever can reach T (the bound H* depends on the GT and the distance only);
+//            - anchor tiles (256 anchors): THE pass over the head output (cp.async reads of the 27 geometry channels
+//              of every row).  Candidate mask (polygon test OR centre window) with geometric pruning and an atan2-free
+//              angle test; for the few (GT, candidate) pairs beyond far2 the exact pair value, appended to the GT's
+//              top-10 list when it reaches T; sum BCEWithLogits(obj, 0); outputs initialised to background;
+//            - centre-window items, one per (GT, level): polygon test, exact pair value and SimOTA cost of the <= 25
+//              anchors that can pass the centre-window test -> the GT's window cost table
+//   k_tail   one CTA per image: dynamic k = clamp(int(sum of the 10 largest list values), 1) per GT (exact: the list
+//            holds every candidate value >= T), the k smallest costs of the window table -> claims in shared memory,
+//            conflict resolution (argmin over all GTs), fg_mask / matched_gt / pred_iou, the loss terms of the
+//            foreground anchors; the last CTA reduces the batch sums and applies the normalisation and the stateful
+//            re-weighting (losses.py:280-345), or hands the sums to the fused peer all-reduce (k_fin)
+//   k_fin    (several GPUs) one warp: waits for the peers' sums in the mailbox, adds them in rank order, finalizes.
+//            It overlaps the next step's k_prep / k_pass, which do not depend on the global sums.
 //
 // Compile with -fmad=false: the discrete decisions hang on fp32 thresholds evaluated in the
 // reference's operation order; bounds and fast paths use explicit fmaf.
@@ -56,21 +60,16 @@ struct Params {
     float* result54;
     float* weights27;
     // workspace
-    float* gt_rec;
-    float4* clist;
-    float* sval;
-    float* wtab;
-    float* tbox;
-    float* seg;       // [B, tiles, 8 warps, 8]: per-warp boxes / counts of the candidate lists
-    int* ccount;
-    int* claim_cnt;
-    int* claim_gt;
-    double* obj_part;
-    int* claimed;
-    int* nclaimed;
-    long long* acc_fix;
     unsigned* ticket;
-    int* err_flag;
+    long long* acc_fix;
+    int* status;
+    int* seed_done;
+    int* ncand;
+    int* lcount;
+    float* gt_rec;
+    float* wtab;
+    float* list;
+    unsigned* cbits;
     unsigned flags;
     float* mbox[P24_MAX_RANKS];  // peer mailboxes of the fused all-reduce (nranks > 1)
     int rank, nranks;
@@ -80,24 +79,10 @@ struct Params {
     Level lev[P24_MAX_LEVELS];
 };
 
-// Debug-only phase timers (-DP24_TIMING): thread 0 of every CTA stores %globaltimer at phase boundaries.
-#ifdef P24_TIMING
-__device__ unsigned long long g_tstamp[6][4096][20];
-__device__ __forceinline__ void tmark(int kern, int cta, int slot) {
-    if (threadIdx.x == 0 && cta >= 0 && cta < 4096) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_tstamp[kern][cta][slot] = t;
-    }
-}
-#define TMARK(kern, cta, slot) tmark(kern, cta, slot)
-#else
-#define TMARK(kern, cta, slot)
-#endif
-
-#define MATCH_THREADS 256
-#define MATCH_WARPS (MATCH_THREADS / 32)
-#define MATCH_GROUPS (MATCH_THREADS / 8)
+#define TK_ITEM 0   // ticket words
+#define TK_LEFF 1
+#define TK_TAIL 2
+#define TK_SEED 3
 
 __device__ __forceinline__ void pdl_wait() {
 #if __CUDA_ARCH__ >= 900
@@ -110,6 +95,12 @@ __device__ __forceinline__ void pdl_trigger() {
 #if __CUDA_ARCH__ >= 900
     cudaTriggerProgrammaticLaunchCompletion();
 #endif
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // ---- 8-lane group reductions (the group's own mask: groups of a warp may diverge) -----------------------
@@ -134,8 +125,7 @@ __device__ __forceinline__ int group_sum_i(int v, unsigned m) {
 }
 
 // -------------------------------------------------------------------------------------------
-// GT preparation, executed inside every CTA of k_pass for its own image (no separate kernel: the records are a few
-// hundred instructions per GT and the label rows stay in L2)
+// k_prep: nlabel and the per-GT records
 // -------------------------------------------------------------------------------------------
 // nlabel = (labels.sum(2) > 0).sum(1)   losses.py:190 ; the first n rows are the GTs (losses.py:219-220).
 // Four threads per label row (double partial sums); every thread returns the count.  Contains __syncthreads().
@@ -226,47 +216,39 @@ __device__ __forceinline__ void warp_gt_record(const float* __restrict__ row, fl
         rec[GT_CY] = cy;
         rec[GT_RIN2] = ra * ra;
         rec[GT_RREJ2] = rrej2;
+        rec[GT_FAR2] = 0.0f;   // set by the GT's seed item
         rec[GT_CLS] = row[0];
         rec[GT_RGMAX] = rgmax;
         rec[GT_RGMIN] = rgmin;
-        rec[7] = 0.0f;
         rec[GT_RGMS] = rg2sum * (1.0f / 24.0f);
         rec[GT_RGMEAN] = rgsum * (1.0f / 24.0f);
-        rec[58] = 0.0f;
+        rec[GT_T] = P24_NEG_INF;
         rec[59] = 0.0f;
     }
 }
 
-// k_gt_prep: one CTA per image.  It lets k_pass launch at once (programmatic dependent launch): k_pass's CTAs stage
-// their first rows while this kernel runs and wait for it only before they read the records.
 #define PREP_THREADS 256
-__global__ void __launch_bounds__(PREP_THREADS) k_gt_prep(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ Params p) {
     // launched as a programmatic dependent of whatever precedes it in the stream (in back-to-back steps: the previous
-    // step's k_resolve_loss, which triggers at once): resident early, it starts the moment that work is complete.  It
-    // must not let k_pass go before that: k_pass draws tickets that the previous step's last CTA resets.
+    // step's k_tail, which triggers at once): resident early, it starts the moment that work is complete
     pdl_wait();
     pdl_trigger();
-    TMARK(3, blockIdx.x, 0);
     __shared__ int s_n;
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
     const float* lab = p.labels + (long long)b * p.lab_img_stride;
     const int n = block_count_labels(p, lab, &s_n);
     if (tid == 0) {
         p.num_gt[b] = n;
-        p.num_fg[b] = 0;
-        p.nclaimed[b] = 0;
-        atomicMax(&p.ticket[2 + p.B], (unsigned)n);  // the batch's largest num_gt: k_pass lays its window items out for it
+        atomicMax(&p.ticket[TK_LEFF], (unsigned)n);  // the batch's largest num_gt: k_pass lays its items out for it
     }
     for (int g = warp; g < n; g += PREP_THREADS / 32)
         warp_gt_record(lab + (long long)g * p.lab_row_stride, p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC);
-    TMARK(3, blockIdx.x, 1);
 }
 
 // -------------------------------------------------------------------------------------------
 // shared device helpers
 // -------------------------------------------------------------------------------------------
-// Out-of-line copies of the two heavy scalar routines: the kernels call them from many places, and inlining every
-// call made the per-GT kernel 17k instructions long (instruction-cache bound).
+// Out-of-line copies of the two heavy scalar routines: the kernels call them from many places
 __device__ __noinline__ float ray_loss(float rg, float rp, float d) { return p24_ray_loss(rg, rp, d); }
 __device__ __noinline__ float edge_angle(float sx, float sy, float ex, float ey) { return p24_edge_angle(sx, sy, ex, ey); }
 
@@ -279,53 +261,6 @@ __device__ __noinline__ float pair_value_row(const float* __restrict__ rec, cons
     return (s / 24.0f) / 2.0f;
 }
 
-// the same value by an 8-lane group (3 rays per lane, fixed reduction tree); every lane of the group returns it
-__device__ __forceinline__ float group_pair_value(const float* __restrict__ rec, const float* __restrict__ row, unsigned m) {
-    const int sub = threadIdx.x & 7;
-    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
-    float s = 0.0f;
-#pragma unroll 1
-    for (int q = 0; q < 3; ++q) {
-        const int k = sub * 3 + q;
-        s = s + ray_loss(rec[GT_RG + k], row[2 + k], d);
-    }
-    s = group_sum(s, m);
-    return (s / 24.0f) / 2.0f;
-}
-
-// A certified LOWER bound of the pair value by an 8-lane group, for seeds: when every ray is in the "apart" branch
-// (d >= rg + rp, the same fp32 comparison as the reference) the value has the closed form
-// (1/48) sum_k (2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2), evaluated here in fast arithmetic; it differs from the
-// reference-order fp32 value by < 3e-6, so value - 1e-5 is a valid lower bound.  Other pairs are evaluated exactly.
-__device__ __forceinline__ float group_pair_value_lb(const float* __restrict__ rec, const float* __restrict__ row, unsigned m) {
-    const int sub = threadIdx.x & 7;
-    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
-    float rg[3], rp[3];
-    bool apart = true;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        rg[q] = rec[GT_RG + sub * 3 + q];
-        rp[q] = row[2 + sub * 3 + q];
-        apart = apart && (d >= rg[q] + rp[q]);
-    }
-    const unsigned all = __ballot_sync(m, apart);
-    if ((all & m) == m) {
-        float s = 0.0f;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const float t = (rg[q] + rp[q]) + d;
-            s += 2.0f - __fdividef(4.0f * fmaf(rg[q], rg[q], rp[q] * rp[q]), t * t);
-        }
-        s = group_sum(s, m);
-        return s * (1.0f / 48.0f) - 1e-5f;
-    }
-    float s = 0.0f;
-#pragma unroll 1
-    for (int q = 0; q < 3; ++q) s = s + ray_loss(rg[q], rp[q], d);
-    s = group_sum(s, m);
-    return (s / 24.0f) / 2.0f;
-}
-
 __device__ __forceinline__ int gt_class(const float* rec, int nc) {
     const int c = (int)rec[GT_CLS];
     return min(max(c, 0), nc - 1);
@@ -334,35 +269,19 @@ __device__ __forceinline__ int gt_class(const float* rec, int nc) {
 // Sum over all classes of BCE(p_j, 0) (losses.py:406-416) in product form, by the 32 lanes of a warp
 __device__ __noinline__ float warp_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1) {
     const int lane = threadIdx.x & 31;
-    float prod = 1.0f;
-    int nsat = 0;
-    for (int j = lane; j < nc; j += 32) p24_neg_factor(cls[j], eo1, prod, nsat);
-    prod = warp_prod(prod);
-    nsat = warp_sum_i(nsat);
-    if (!(prod > 1e-30f)) {  // pathological logits: fall back to the term-by-term sum
-        const float obj_sig = 1.0f / eo1;
-        float s = 0.0f;
-        for (int j = lane; j < nc; j += 32) s += p24_bce_neg(p24_joint_prob(cls[j], obj_sig));
-        return warp_sum(s);
-    }
-    return -logf(prod) + 100.0f * (float)nsat;
+    const float obj_sig = 1.0f / eo1;
+    float s = 0.0f;
+    for (int j = lane; j < nc; j += 32) s += p24_bce_neg(p24_joint_prob(cls[j], obj_sig));
+    return warp_sum(s);
 }
 
-// ... by the 8 lanes of a group
+// ... by the 8 lanes of a group, term by term (fallback of the product form)
 __device__ __noinline__ float group_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1, unsigned m) {
     const int sub = threadIdx.x & 7;
-    float prod = 1.0f;
-    int nsat = 0;
-    for (int j = sub; j < nc; j += 8) p24_neg_factor(cls[j], eo1, prod, nsat);
-    prod = group_prod(prod, m);
-    nsat = group_sum_i(nsat, m);
-    if (!(prod > 1e-30f)) {
-        const float obj_sig = 1.0f / eo1;
-        float s = 0.0f;
-        for (int j = sub; j < nc; j += 8) s += p24_bce_neg(p24_joint_prob(cls[j], obj_sig));
-        return group_sum(s, m);
-    }
-    return -logf(prod) + 100.0f * (float)nsat;
+    const float obj_sig = 1.0f / eo1;
+    float s = 0.0f;
+    for (int j = sub; j < nc; j += 8) s += p24_bce_neg(p24_joint_prob(cls[j], obj_sig));
+    return group_sum(s, m);
 }
 
 // ... by a single thread (rare slow paths)
@@ -380,10 +299,248 @@ __device__ __forceinline__ float cls_cost_from(float neg_sum, float cls_logit_c,
 }
 
 // -------------------------------------------------------------------------------------------
-// k_pass, anchor CTAs: one CTA per 256-anchor tile
+// Upper bound of the pair value as a function of the centre distance d alone.  Any ray has
+// loss <= max(1, 2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2) (nested rays: loss <= 1; partial and apart rays:
+// loss <= 2 - uni/cs with the apart formula; tests/test_bounds_cpu.py).  Over all rp > 0 the fraction is smallest at
+// rp* = rg^2 / (rg + d), where it equals rg^2 / ((rg + d)^2 + rg^2).  So every ray has
+// loss <= max(1, 2 - 4 rg^2 / ((rg + d)^2 + rg^2)) whatever the prediction: monotone in d.
+// One warp, lanes over the rays; every lane returns the bound H*(d) of the pair value.
 // -------------------------------------------------------------------------------------------
-#define ITEM_CAP 704
+__device__ __forceinline__ float warp_bound_Hstar(float rg_lane, float d) {
+    const int lane = threadIdx.x & 31;
+    float t = 0.0f;
+    if (lane < P24_RAYS) {
+        const float q = rg_lane + d;
+        t = fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg_lane * rg_lane, fmaf(q, q, rg_lane * rg_lane)));
+    }
+    return warp_sum(t) * (1.0f / 48.0f);
+}
+
+// -------------------------------------------------------------------------------------------
+// k_pass, seed items.  Dynamic k needs the 10 LARGEST pair values of a GT over the image's candidate anchors
+// (losses.py:452-456); the pair value grows with the centre distance, so they belong to candidates far away from the
+// GT.  A seed item evaluates a handful of anchors that are certainly candidates and far away: the centre-window and
+// inscribed-disc anchors of the SEED_FAR farthest GTs of the image on the side that looks away from this GT, and the
+// anchors just inside their polygon tips on that side (verified with the polygon test).  T = the 10th best seed value
+// is a certified lower bound of the 10th largest pair value, and far2 = the squared centre distance below which
+// H*(d) < T: the anchor tiles evaluate only the (GT, candidate) pairs beyond it.
+// -------------------------------------------------------------------------------------------
+#define SEED_FAR 3
+#define SEED_VERT 6
+#define SEED_PTS (3 + SEED_VERT)
+#define SEED_MAX (SEED_FAR * P24_MAX_LEVELS * SEED_PTS)   // 108 <= P24_THREADS
+
+struct SeedShared {
+    float rec[GT_REC];
+    int far[SEED_FAR];
+    int vsel[SEED_FAR][SEED_VERT];
+    float val[SEED_MAX];
+    int anc[SEED_MAX];
+    int nfar, nseed;
+    float T;
+};
+
+__device__ __forceinline__ int cell_index(float q, float st) {
+    float v = floorf(q / st);
+    v = fminf(fmaxf(v, -1.0e6f), 1.0e6f);  // NaN -> -1e6: outside every grid
+    return (int)v;
+}
+
+__device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.num_gt[b];
+    const float* recs = p.gt_rec + (long long)b * p.Lmax * GT_REC;
+    float* myrec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
+    __syncthreads();  // the scratch may still be in use by the previous item
+    if (tid < GT_REC) S.rec[tid] = myrec[tid];
+    if (tid < SEED_MAX) {
+        S.val[tid] = P24_NEG_INF;
+        S.anc[tid] = -1;
+    }
+    __syncthreads();
+    const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
+    const bool filter = !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && S.rec[GT_RGMAX] < 1.0e6f;
+    if (filter) {
+        // ---- the SEED_FAR farthest GTs (centre distance + their largest ray), this GT included: warp 0 ----------
+        if (warp == 0) {
+            float k0 = P24_NEG_INF, k1 = P24_NEG_INF, k2 = P24_NEG_INF;  // the lane's best keys
+            int h0 = -1, h1 = -1, h2 = -1;
+            for (int h = lane; h < n; h += 32) {
+                const float* r = recs + h * GT_REC;
+                const float dx = r[GT_CX] - gcx, dy = r[GT_CY] - gcy;
+                float key = sqrtf(fmaf(dx, dx, dy * dy)) + r[GT_RGMAX];
+                int hh = h;
+                if (!(key == key)) continue;
+                if (key > k0 || h0 < 0) { const float t = k0; k0 = key; key = t; const int u = h0; h0 = hh; hh = u; }
+                if (hh >= 0 && (key > k1 || h1 < 0)) { const float t = k1; k1 = key; key = t; const int u = h1; h1 = hh; hh = u; }
+                if (hh >= 0 && (key > k2 || h2 < 0)) { k2 = key; h2 = hh; }
+            }
+            int nf = 0;
+#pragma unroll 1
+            for (int r = 0; r < SEED_FAR; ++r) {
+                const KV best = warp_select<true>(KV{h0 >= 0 ? k0 : P24_NEG_INF, h0 >= 0 ? h0 : 0x7fffffff});
+                if (best.i == 0x7fffffff) break;
+                if (h0 == best.i) {  // pop
+                    k0 = k1; h0 = h1;
+                    k1 = k2; h1 = h2;
+                    h2 = -1;
+                }
+                if (lane == 0) S.far[r] = best.i;
+                ++nf;
+            }
+            if (lane == 0) S.nfar = nf;
+        }
+        __syncthreads();
+        const int nfar = S.nfar;
+        // ---- per far GT: its SEED_VERT vertices that look away from this GT the most: warps 0 .. nfar-1 ----------
+        if (warp < nfar) {
+            const float* r = recs + S.far[warp] * GT_REC;
+            float ux = r[GT_CX] - gcx, uy = r[GT_CY] - gcy;
+            if (!(fmaf(ux, ux, uy * uy) > 1e-12f)) {
+                ux = 1.0f;
+                uy = 0.0f;
+            }
+            float proj = P24_NEG_INF;
+            if (lane < P24_RAYS) {
+                proj = fmaf(r[GT_VX + lane] - r[GT_CX], ux, (r[GT_VY + lane] - r[GT_CY]) * uy);
+                if (!(proj == proj)) proj = -3.0e38f;
+            }
+#pragma unroll 1
+            for (int q = 0; q < SEED_VERT; ++q) {
+                const KV best = warp_select<true>(KV{proj, lane});
+                if (lane == 0) S.vsel[warp][q] = best.i < P24_RAYS ? best.i : 0;
+                if (lane == best.i) proj = P24_NEG_INF;
+            }
+        }
+        __syncthreads();
+        // ---- one seed point per thread: (far GT, level, point) -> grid cell -> certainly a candidate? -> value ----
+        const int per_h = p.nlev * SEED_PTS;
+        if (tid < nfar * per_h) {
+            const int f = tid / per_h, r0 = tid - f * per_h;
+            const int l = r0 / SEED_PTS, pt = r0 - l * SEED_PTS;
+            const float* h = recs + S.far[f] * GT_REC;
+            const Level lv = p.lev[l];
+            const float st = p.strides[lv.off];
+            const float hcx = h[GT_CX], hcy = h[GT_CY];
+            float qx, qy;
+            if (pt < 3) {
+                float ux = hcx - gcx, uy = hcy - gcy;
+                const float nn = fmaf(ux, ux, uy * uy);
+                if (nn > 1e-12f) {
+                    const float inv = rsqrtf(nn);
+                    ux *= inv;
+                    uy *= inv;
+                } else {
+                    ux = 1.0f;
+                    uy = 0.0f;
+                }
+                const float rho = pt == 0 ? 0.0f : (pt == 1 ? fmaxf(0.0f, sqrtf(h[GT_RIN2]) - 0.75f * st) : 2.0f * st);
+                qx = fmaf(ux, rho, hcx);
+                qy = fmaf(uy, rho, hcy);
+            } else {
+                const int k = S.vsel[f][pt - 3];
+                const float rr = h[GT_RG + k];
+                const float fct = fmaxf(0.0f, __fdividef(rr - st, fmaxf(rr, 1e-6f)));
+                qx = fmaf(h[GT_VX + k] - hcx, fct, hcx);
+                qy = fmaf(h[GT_VY + k] - hcy, fct, hcy);
+            }
+            const int ix = cell_index(qx, st), iy = cell_index(qy, st);
+            if (ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
+                const int a = lv.off + iy * lv.W + ix;
+                const float ast = p.strides[a];
+                const float xc = p24_anchor_centre(p.x_shifts[a], ast), yc = p24_anchor_centre(p.y_shifts[a], ast);
+                // the very tests of the anchor tiles: inscribed disc, centre window, polygon
+                const float dx = hcx - xc, dy = hcy - yc;
+                bool cand = fmaf(dx, dx, dy * dy) < h[GT_RIN2];
+                if (!cand) cand = p24_in_centre(hcx, hcy, xc, yc, ast);
+                if (!cand) cand = p24_in_polygon(h + GT_VX, h + GT_VY, xc, yc);
+                if (cand) {
+                    const float* row = p.outputs + (long long)b * p.img_stride + (long long)a * p.row_stride;
+                    // a certified LOWER bound of the pair value: when every ray is in the "apart" branch (the reference's
+                    // own fp32 comparison) the value has the closed form (1/48) sum_k (2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2),
+                    // evaluated in fast arithmetic to within 3e-6; other pairs are evaluated exactly
+                    const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
+                    float s = 0.0f;
+                    bool apart = true;
+#pragma unroll 4
+                    for (int k = 0; k < P24_RAYS; ++k) {
+                        const float rg = S.rec[GT_RG + k], rp = row[2 + k];
+                        apart = apart && (d >= rg + rp) && (rp >= 0.25f);
+                        const float t = (rg + rp) + d;
+                        s += 2.0f - __fdividef(4.0f * fmaf(rg, rg, rp * rp), t * t);
+                    }
+                    float v = apart ? s * (1.0f / 48.0f) - 1e-5f : pair_value_row(S.rec, row);
+                    if (!(v == v)) v = P24_NEG_INF;
+                    S.val[tid] = v;
+                    S.anc[tid] = a;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- the 10th largest value over the distinct seed anchors ---------------------------------------------
+        if (tid == 0) S.T = P24_NEG_INF;
+        bool mine = false;
+        float v = P24_NEG_INF;
+        if (tid < nfar * per_h) {
+            v = S.val[tid];
+            const int a = S.anc[tid];
+            mine = a >= 0 && v > P24_NEG_INF;
+            for (int j = 0; j < tid && mine; ++j) mine = S.anc[j] != a;  // the first copy of an anchor counts
+        }
+        __syncthreads();
+        if (tid < nfar * per_h && !mine) S.val[tid] = P24_NEG_INF;
+        __syncthreads();
+        if (mine) {
+            int rank = 0;
+            for (int j = 0; j < nfar * per_h; ++j) rank += kv_gt(S.val[j], j, v, tid) ? 1 : 0;
+            if (rank == P24_TOPK - 1) S.T = v;
+        }
+        __syncthreads();
+    } else {
+        if (tid == 0) S.T = P24_NEG_INF;
+        __syncthreads();
+    }
+    // ---- far2: pairs closer than D cannot reach T.  Bisection on H*(d) + 3e-5 < T (monotone in d): warp 0 -----------
+    if (warp == 0) {
+        const float T = S.T;
+        float far2 = 0.0f;  // 0: every pair is evaluated
+        if (T > P24_NEG_INF) {
+            const float rg = lane < P24_RAYS ? S.rec[GT_RG + lane] : 0.0f;
+            float lo = 0.0f, hi = 1.0e6f;
+            if (warp_bound_Hstar(rg, lo) + 3e-5f < T) {
+                if (warp_bound_Hstar(rg, hi) + 3e-5f < T) {
+                    lo = hi;  // (cannot happen: the seeds themselves obey the bound)
+                } else {
+#pragma unroll 1
+                    for (int it = 0; it < 32; ++it) {
+                        const float mid = 0.5f * (lo + hi);
+                        if (warp_bound_Hstar(rg, mid) + 3e-5f < T) lo = mid;
+                        else hi = mid;
+                    }
+                }
+                const float D = fmaxf(0.0f, lo * (1.0f - 1e-4f) - 0.02f);
+                far2 = D * D;
+            }
+            if (!(far2 == far2)) far2 = 0.0f;
+        }
+        if (lane == 0) {
+            myrec[GT_FAR2] = far2;
+            myrec[GT_T] = T;
+            __threadfence();
+            atomicAdd(&p.seed_done[b], 1);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// k_pass, anchor tiles: one item per 256-anchor tile
+// -------------------------------------------------------------------------------------------
+#define ITEM_CAP 1024
 #define ROW_CH 27  // channels 0..26 of a head row are read here: centre, 24 radii, objectness
+#define FIX_SCALE 68719476736.0     // 2^36: fixed-point unit of the loss accumulators (order-independent sums)
+#define FIX_SCALE_OBJ 4294967296.0  // 2^32 for the objectness sum over all anchors (range for B * A terms)
+
+__device__ __forceinline__ long long to_fix(double x) { return __double2ll_rn(x * FIX_SCALE); }
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -396,32 +553,51 @@ __device__ __forceinline__ void cp_async_wait_all() {
 struct AnchorShared {
     float row[P24_WARPS][ROW_CH][33];
     int cand[P24_THREADS];
-    int seedA[P24_SEEDS * 128];
-    double red[P24_WARPS];
-    float box[P24_WARPS][5];
-    int wcnt[P24_WARPS];
-    int nitems, n;
+    unsigned items[ITEM_CAP];
+    int nitems;
 };
 
-__device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, AnchorShared& S, int b, int tile, bool first) {
-    float* s_gt = reinterpret_cast<float*>(s_dyn4);  // [n * GT_REC_HEAD]: everything but the ray lengths
+// the tile's rows: each warp reads its 32 rows, 27 contiguous floats per row, straight into shared memory
+__device__ __forceinline__ void stage_rows(const Params& p, AnchorShared& S, int b, int tile) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* img = p.outputs + (long long)b * p.img_stride;
+    const int a0 = tile * P24_THREADS + warp * 32;
+    const int nrow = min(32, p.A - a0);
+    if (lane < ROW_CH) {
+        const float* src = img + (long long)a0 * p.row_stride + lane;
+        for (int r = 0; r < nrow; ++r) cp_async4(&S.row[warp][lane][r], src + (long long)r * p.row_stride);
+    }
+}
+
+// exact pair value of (GT record in shared memory, anchor `al` of the staged tile): one thread
+__device__ __noinline__ float pair_value_staged(const float* __restrict__ rec, const AnchorShared& S, int al) {
+    const int wr = al >> 5, lr = al & 31;
+    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], S.row[wr][0][lr], S.row[wr][1][lr]);
+    float s = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < P24_RAYS; ++k) s = s + p24_ray_loss(rec[GT_RG + k], S.row[wr][2 + k][lr], d);
+    return (s / 24.0f) / 2.0f;
+}
+
+// pair (GT g, staged anchor al) lies beyond far2: exact value, into the GT's top-10 list when it reaches T
+__device__ __forceinline__ void far_pair(const Params& p, const float* __restrict__ s_rec, const AnchorShared& S, int b,
+                                         int g, int al) {
+    const float* rec = s_rec + g * GT_REC;
+    float v = pair_value_staged(rec, S, al);
+    if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
+    if (v >= rec[GT_T]) {
+        const int slot = b * p.Lmax + g;
+        const int at = atomicAdd(&p.lcount[slot], 1);
+        if (at < P24_LISTCAP) p.list[(long long)slot * P24_LISTCAP + at] = v;
+    }
+}
+
+__device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, AnchorShared& S, int b, int tile, bool staged) {
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int a = tile * P24_THREADS + tid;
     const bool active = a < p.A;
-    // the work list lives in rows 5.. of S.row (free between the row reduction and the seed search)
-    unsigned* s_items = reinterpret_cast<unsigned*>(&S.row[0][5][0]);  // 726 floats per warp region; ITEM_CAP <= 726
-
-    // ---- the tile's rows: each warp reads its 32 rows, 27 contiguous floats per row (coalesced), straight into
-    // shared memory with cp.async; the GT records are computed while they are in flight -------------------------
-    const float* img = p.outputs + (long long)b * p.img_stride;
-    {
-        const int a0 = tile * P24_THREADS + warp * 32;
-        const int nrow = min(32, p.A - a0);
-        if (lane < ROW_CH) {
-            for (int r = 0; r < nrow; ++r) cp_async4(&S.row[warp][lane][r], img + (long long)(a0 + r) * p.row_stride + lane);
-        }
-    }
+    if (!staged) stage_rows(p, S, b, tile);
     float st = 1.f, xs = 0.f, ys = 0.f;
     if (active) {
         st = p.strides[a];
@@ -430,64 +606,67 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
     }
     if (tid == 0) S.nitems = 0;
     S.cand[tid] = 0;
-    TMARK(0, b * p.tiles + tile, 0);
-    if (first) pdl_wait();  // the records come from k_gt_prep
-    TMARK(0, b * p.tiles + tile, 1);
     const int n = p.num_gt[b];
+    // the records are complete once every seed item of the image has finished (the seed items are drawn from their own
+    // ticket counter before any tile: the CTAs that hold them are running, so this wait cannot deadlock)
+    if (tid == 0) {
+        while (ld_acquire(&p.seed_done[b]) < n) __nanosleep(64);
+    }
+    __syncthreads();
     {
         const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
-        for (int i = tid; i < n * (GT_REC_HEAD / 4); i += P24_THREADS) {
-            const int g = i / (GT_REC_HEAD / 4), q = i - g * (GT_REC_HEAD / 4);
-            s_dyn4[i] = gsrc[g * (GT_REC / 4) + q];
-        }
+        float4* dst = reinterpret_cast<float4*>(s_rec);
+        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) dst[i] = __ldcg(gsrc + i);
     }
     cp_async_wait_all();
     __syncthreads();
-    TMARK(0, b * p.tiles + tile, 2);
 
-    float pcx = 0.f, pcy = 0.f, rpmax = 0.f, rpmin = INFINITY, rpsum = 0.f, rp2sum = 0.f, obj = 0.f;
+    float pcx = 0.f, pcy = 0.f, rpmin = INFINITY, obj = 0.f;
     const float xc = p24_anchor_centre(xs, st);
     const float yc = p24_anchor_centre(ys, st);
     if (active) {
         pcx = S.row[warp][0][lane];
         pcy = S.row[warp][1][lane];
 #pragma unroll
-        for (int c = 2; c < 26; ++c) {
-            const float v = S.row[warp][c][lane];
-            rpmax = fmaxf(rpmax, v);
-            rpmin = fminf(rpmin, v);
-            rpsum += v;
-            rp2sum = fmaf(v, v, rp2sum);
-        }
+        for (int c = 2; c < 26; ++c) rpmin = fminf(rpmin, S.row[warp][c][lane]);
         obj = S.row[warp][26][lane];
     }
     double objpart = active ? (double)p24_bce_logits(obj, 0.0f) : 0.0;
-    __syncthreads();  // the radii rows of S.row are recycled as the work list from here on
 
-    // ---- one pass over the GTs: centre windows, the inscribed-disc accept, and a bit mask of the GTs whose reject
-    // radius the anchor is inside (the only ones that may need a polygon test) ------------------------------------
+    // ---- one pass over the GTs: centre windows, the inscribed-disc accept, a bit mask of the GTs whose reject radius
+    // the anchor is inside (the only ones that may need a polygon test) and a bit mask of the GTs whose far2 the
+    // PREDICTED centre is beyond (the only pairs whose value can reach the GT's top 10) -----------------------------
     bool cheap = false;
     const bool no_prune = (p.flags & P24_F_NO_PRUNE) != 0;
-    unsigned near[4] = {0u, 0u, 0u, 0u};  // GTs 0..127; beyond that every GT is tested in place (see below)
+    const bool no_filter = (p.flags & P24_F_NO_FILTER) != 0;
+    const bool tiny = !(rpmin >= 0.25f);  // a tiny (or NaN) predicted radius: outside the validated range of the bound
+    unsigned near[4] = {0u, 0u, 0u, 0u};  // GTs 0..127; beyond that every GT is handled in place (see below)
+    unsigned far[4] = {0u, 0u, 0u, 0u};
+    const float r25 = 2.5f * st + 1e-3f * st;  // conservative pre-filter radius of the window test
+    const float4* s_rec4 = reinterpret_cast<const float4*>(s_rec);
     {
-        const float r25 = 2.5f * st + 1e-3f * st;  // conservative pre-filter radius of the window test
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            unsigned m = 0u;
+            unsigned m = 0u, fm = 0u;
             const int ge = min(32, n - w * 32);
             for (int j = 0; j < ge; ++j) {
                 const int g = w * 32 + j;
-                const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
+                const float4 h = s_rec4[g * (GT_REC / 4)];
+                const float far2 = s_rec[g * GT_REC + GT_FAR2];
                 const float dx = h.x - xc, dy = h.y - yc;
                 const float d2 = fmaf(dx, dx, dy * dy);
                 cheap |= d2 < h.z;
                 m |= (d2 <= h.w ? 1u : 0u) << j;
                 if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
+                const float px = h.x - pcx, py = h.y - pcy;
+                fm |= (!(fmaf(px, px, py * py) < far2) ? 1u : 0u) << j;
             }
-            near[w] = no_prune ? (ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u)) : m;
+            const unsigned all = ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u);
+            near[w] = no_prune ? all : m;
+            far[w] = tiny ? all : fm;
         }
         for (int g = 128; g < n; ++g) {  // more than 128 GTs: windows and discs of the rest
-            const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
+            const float4 h = s_rec4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             cheap |= fmaf(dx, dx, dy * dy) < h.z;
             if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
@@ -506,19 +685,19 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
                 m &= m - 1;
                 const int slot = atomicAdd(&S.nitems, 1);
                 if (slot < ITEM_CAP) {
-                    s_items[slot] = (unsigned)tid | ((unsigned)g << 8);
+                    S.items[slot] = (unsigned)tid | ((unsigned)g << 8);
                 } else if (!mine) {
-                    const float* rec = s_gt + g * GT_REC_HEAD;
+                    const float* rec = s_rec + g * GT_REC;
                     mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
                                     : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
                 }
             }
         }
         for (int g = 128; g < n && !mine; ++g) {  // more than 128 GTs: test the rest in place
-            const float4 h = s_dyn4[g * (GT_REC_HEAD / 4)];
+            const float4 h = s_rec4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             if (no_prune || fmaf(dx, dx, dy * dy) <= h.w) {
-                const float* rec = s_gt + g * GT_REC_HEAD;
+                const float* rec = s_rec + g * GT_REC;
                 mine = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, xc, yc)
                                 : p24_in_polygon(rec + GT_VX, rec + GT_VY, xc, yc);
             }
@@ -526,623 +705,84 @@ __device__ __forceinline__ void anchor_part(const Params& p, float4* s_dyn4, Anc
     }
     if (mine) S.cand[tid] = 1;
     __syncthreads();
-    TMARK(0, b * p.tiles + tile, 3);
-    const int nitems = min(S.nitems, ITEM_CAP);
-    for (int i = tid; i < nitems; i += P24_THREADS) {
-        const unsigned it = s_items[i];
-        const int al = it & 0xFF;
-        if (((volatile int*)S.cand)[al]) continue;  // already a candidate through another GT
-        const int g = it >> 8;
-        const float* rec = s_gt + g * GT_REC_HEAD;
-        const int aa = tile * P24_THREADS + al;
-        const float st2 = p.strides[aa];
-        const float axc = p24_anchor_centre(p.x_shifts[aa], st2);
-        const float ayc = p24_anchor_centre(p.y_shifts[aa], st2);
-        const bool in = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, axc, ayc)
-                                 : p24_in_polygon(rec + GT_VX, rec + GT_VY, axc, ayc);
-        if (in) S.cand[al] = 1;
+    {
+        const int nitems = min(S.nitems, ITEM_CAP);
+        for (int i = tid; i < nitems; i += P24_THREADS) {
+            const unsigned it = S.items[i];
+            const int al = it & 0xFF;
+            if (((volatile int*)S.cand)[al]) continue;  // already a candidate through another GT
+            const int g = it >> 8;
+            const float* rec = s_rec + g * GT_REC;
+            const int aa = tile * P24_THREADS + al;
+            const float st2 = p.strides[aa];
+            const float axc = p24_anchor_centre(p.x_shifts[aa], st2);
+            const float ayc = p24_anchor_centre(p.y_shifts[aa], st2);
+            const bool in = no_prune ? p24_in_polygon_exact(rec + GT_VX, rec + GT_VY, axc, ayc)
+                                     : p24_in_polygon(rec + GT_VX, rec + GT_VY, axc, ayc);
+            if (in) S.cand[al] = 1;
+        }
     }
+    __syncthreads();
+    const bool cand = active && (n > 0) && (cheap || S.cand[tid]);
+    if (tid == 0) S.nitems = 0;
     __syncthreads();
 
-    TMARK(0, b * p.tiles + tile, 4);
-    // ---- compacted candidate list of the tile (deterministic order) + per-anchor scratch reset ----------
-    const bool cand = active && (n > 0) && (cheap || S.cand[tid]);
-    // ---- seeds of the top-10 search: lane g of every warp ranks the warp's candidates for GT g by the first-order
-    // proxy q = (mean rg^2 + mean rp^2) / (mean rg + mean rp + d)^2 of the pair value (value ~ 1 - q / 3 for far
-    // pairs; the smallest q are almost always the true top-10) and records the largest t = rpmax + d -----------
-    S.row[warp][2][lane] = rp2sum * (1.0f / 24.0f);
-    S.row[warp][3][lane] = rpsum * (1.0f / 24.0f);
-    S.row[warp][4][lane] = cand ? (rpmin < 0.25f ? INFINITY : rpmax) : -1.0f;
-    __syncthreads();
-    {
-        // bounding box of the warp's candidates (GT independent): k_match bounds t = rpmax + d with it
-        {
-            const float rz = cand ? (rpmin < 0.25f ? INFINITY : rpmax) : P24_NEG_INF;
-            const float bx0 = -warp_max(cand ? -pcx : P24_NEG_INF), bx1 = warp_max(cand ? pcx : P24_NEG_INF);
-            const float by0 = -warp_max(cand ? -pcy : P24_NEG_INF), by1 = warp_max(cand ? pcy : P24_NEG_INF);
-            const float rzm = warp_max(rz);
-            if (lane == 0) {
-                S.box[warp][0] = bx0;
-                S.box[warp][1] = bx1;
-                S.box[warp][2] = by0;
-                S.box[warp][3] = by1;
-                S.box[warp][4] = rzm;
+    // ---- the (GT, candidate) pairs beyond far2: exact values into the GTs' top-10 lists (again through a work list) ---
+    if (cand && !no_filter) {
+        for (int w = 0; w < 4; ++w) {
+            unsigned m = far[w];
+            while (m) {
+                const int g = w * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const int slot = atomicAdd(&S.nitems, 1);
+                if (slot < ITEM_CAP) S.items[slot] = (unsigned)tid | ((unsigned)g << 8);
+                else far_pair(p, s_rec, S, b, g, tid);
             }
         }
-        // warp w ranks a quarter of the tile's anchors, i = 8 j + ((w - j) & 7) for every 4th j: neighbouring anchors
-        // (nearly equal proxies) land in different warps, and a quarter sample is enough for seeds (any candidate
-        // is a valid seed; better ones only make the bracket tighter).  Per-warp results go to the free rows of S.row.
-        float* wres = &S.row[warp][5][0];  // [n][4]: q1, a1, q2, a2   (22 * 33 = 726 floats: n <= 181)
-        for (int g = lane; g < n; g += 32) {
-            const float* rec = s_gt + g * GT_REC_HEAD;
-            const float gcx = rec[GT_CX], gcy = rec[GT_CY], rgms = rec[GT_RGMS], rgmean = rec[GT_RGMEAN];
-            float q1 = P24_POS_INF, q2 = P24_POS_INF;
-            int a1 = -1, a2 = -1;
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const int j = 4 * jj + (warp & 3);
-                const int i = 8 * j + ((warp - j) & 7);
-                const int wj = i >> 5, lj = i & 31;
-                const float rz = S.row[wj][4][lj];
-                if (rz < 0.0f) continue;  // not a candidate
-                const float dx = gcx - S.row[wj][0][lj], dy = gcy - S.row[wj][1][lj];
-                const float d2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-12f);
-                const float d = d2 * rsqrtf(d2);
-                const float den = (rgmean + S.row[wj][3][lj]) + d;
-                const float q = __fdividef(rgms + S.row[wj][2][lj], den * den);
-                const int aj = tile * P24_THREADS + i;
-                if (q < q1) {
-                    q2 = q1;
-                    a2 = a1;
-                    q1 = q;
-                    a1 = aj;
-                } else if (q < q2) {
-                    q2 = q;
-                    a2 = aj;
-                }
-            }
-            if (g < 181) {
-                wres[g * 4 + 0] = q1;
-                wres[g * 4 + 1] = __int_as_float(a1);
-                wres[g * 4 + 2] = q2;
-                wres[g * 4 + 3] = __int_as_float(a2);
-            }
+        for (int g = 128; g < n; ++g) {  // more than 128 GTs: the rest in place
+            const float* rec = s_rec + g * GT_REC;
+            const float px = rec[GT_CX] - pcx, py = rec[GT_CY] - pcy;
+            if (tiny || !(fmaf(px, px, py * py) < rec[GT_FAR2])) far_pair(p, s_rec, S, b, g, tid);
         }
     }
+    // ---- per-anchor outputs, candidate bitmap and count, the all-anchor objectness term -------------------------
     const unsigned bal = __ballot_sync(0xffffffffu, cand);
-    if (lane == 0) S.wcnt[warp] = __popc(bal);
     objpart = warp_sum_d(objpart);
-    if (lane == 0) S.red[warp] = objpart;
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < P24_WARPS; ++w) {
-        const int c = S.wcnt[w];
-        base += (w < warp) ? c : 0;
-        total += c;
-    }
-    const long long blk = (long long)b * p.tiles + tile;
-    // the tile's two best seeds per GT (merge of the 8 warps), evaluated right away (8-lane groups): what
-    // k_match brackets the top-10 sum with.  128 GTs at a time.
-    for (int g0 = 0; g0 < n; g0 += 128) {
-        const int gn = min(128, n - g0);
-        if (tid < gn) {
-            const int g = g0 + tid;
-            float qb[P24_SEEDS];
-            int ab[P24_SEEDS];
-#pragma unroll
-            for (int u = 0; u < P24_SEEDS; ++u) {
-                qb[u] = P24_POS_INF;
-                ab[u] = -1;
-            }
-            if (g < 181) {
-#pragma unroll
-                for (int w = 0; w < P24_WARPS; ++w) {
-                    const float* e = &S.row[w][5][0] + g * 4;
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        float q = e[2 * u];
-                        int aq = __float_as_int(e[2 * u + 1]);
-#pragma unroll
-                        for (int r = 0; r < P24_SEEDS; ++r) {  // sorted insert
-                            if (q < qb[r]) {
-                                const float tq = qb[r];
-                                const int ta = ab[r];
-                                qb[r] = q;
-                                ab[r] = aq;
-                                q = tq;
-                                aq = ta;
-                            }
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < P24_SEEDS; ++u) S.seedA[P24_SEEDS * tid + u] = ab[u];
-        }
-        __syncthreads();
-        {
-            const unsigned gm = group_mask();
-            const int grp = tid >> 3, sub = tid & 7;
-            for (int t = grp; t < P24_SEEDS * gn; t += P24_THREADS / 8) {
-                const int sa = S.seedA[t];
-                const int g = g0 + t / P24_SEEDS;
-                float v = P24_NEG_INF;
-                if (sa >= 0)
-                    v = group_pair_value_lb(p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC, img + (long long)sa * p.row_stride, gm);
-                if (sub == 0)
-                    p.sval[((long long)b * p.Lmax + g) * P24_SEEDS * p.tiles + P24_SEEDS * tile + (t % P24_SEEDS)] = v;
-            }
-        }
-        __syncthreads();
-    }
-    if (tid == 32) {
-        float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY, rzm = -INFINITY;
-        for (int w = 0; w < P24_WARPS; ++w) {
-            bx0 = fminf(bx0, S.box[w][0]);
-            bx1 = fmaxf(bx1, S.box[w][1]);
-            by0 = fminf(by0, S.box[w][2]);
-            by1 = fmaxf(by1, S.box[w][3]);
-            rzm = fmaxf(rzm, S.box[w][4]);
-        }
-        float4* dst = reinterpret_cast<float4*>(p.tbox + blk * 8);
-        dst[0] = make_float4(bx0, bx1, by0, by1);
-        dst[1] = make_float4(rzm, 0.0f, 0.0f, 0.0f);
-    }
     if (lane == 0) {
-        // the warp's segment of the candidate list: box of its candidates' predicted centres, largest rpmax, extent
-        float4* dst = reinterpret_cast<float4*>(p.seg + (blk * P24_WARPS + warp) * 8);
-        dst[0] = make_float4(S.box[warp][0], S.box[warp][1], S.box[warp][2], S.box[warp][3]);
-        dst[1] = make_float4(S.box[warp][4], __int_as_float(S.wcnt[warp]), __int_as_float(base), __uint_as_float(bal));
-    }
-    if (cand) {
-        const int rank = base + __popc(bal & ((1u << lane) - 1u));
-        // a prediction with a tiny radius disables the bound filter for its pairs: rpmax = +inf
-        p.clist[blk * P24_THREADS + rank] = make_float4(pcx, pcy, rpmin < 0.25f ? INFINITY : rpmax, __int_as_float(a));
+        p.cbits[((long long)b * p.tiles + tile) * P24_WARPS + warp] = bal;
+        if (bal) atomicAdd(&p.ncand[b], __popc(bal));
+        if (p.sums28)
+            atomicAdd((unsigned long long*)&p.acc_fix[24], (unsigned long long)__double2ll_rn(objpart * FIX_SCALE_OBJ));
     }
     if (active) {
-        // every anchor starts as background; k_resolve_loss overwrites the claimed ones
+        // every anchor starts as background; k_tail overwrites the claimed ones
         const long long o = (long long)b * p.A + a;
-        p.claim_cnt[o] = 0;
         p.fg_mask[o] = 0;
         p.matched_gt[o] = -1;
         p.pred_iou[o] = 0.0f;
     }
-    if (tid == 0) {
-        p.ccount[blk] = total;
-        double t = 0.0;
-        for (int w = 0; w < P24_WARPS; ++w) t += S.red[w];
-        p.obj_part[blk] = t;
-    }
-    TMARK(0, b * p.tiles + tile, 5);
-}
-
-// -------------------------------------------------------------------------------------------
-// per-GT helpers of k_match
-// -------------------------------------------------------------------------------------------
-// GT g selects anchor a: count the claim; the first claimant also puts the anchor on the image's claimed list
-__device__ __forceinline__ void claim_anchor(const Params& p, int b, int a, int g) {
-    const long long o = (long long)b * p.A + a;
-    const int old = atomicAdd(&p.claim_cnt[o], 1);
-    p.claim_gt[o] = g;
-    if (old == 0) {
-        const int slot = atomicAdd(&p.nclaimed[b], 1);
-        if (slot < P24_TOPK * p.Lmax) p.claimed[(long long)b * P24_TOPK * p.Lmax + slot] = a;
-        else atomicOr(p.err_flag, 2);
-    }
-}
-
-#define HIT_CAP 2112
-#define MATCH_WCAP (25 * P24_MAX_LEVELS)  // at most 5 x 5 cells per level pass the window test
-#define MAX_TILES 1024  // candidate counts of an image kept in shared memory (A <= 262144)
-
-// Upper bound of the pair value as a function of t = rpmax + d: any ray has loss <= max(1, 2 - 4 rg^2 / (rg + rp + d)^2)
-// (nested rays: loss <= 1; partial and apart rays: loss <= 2 - uni/cs; DESIGN.md "top-10 bracket").
-// One thread evaluates it from the GT record in shared memory.
-__device__ __forceinline__ float bound_H_thread(const float* __restrict__ rec, float t) {
-    float s = 0.0f;
-#pragma unroll
-    for (int k = 0; k < P24_RAYS; ++k) {
-        const float rg = rec[GT_RG + k];
-        const float q = rg + t;
-        s += fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, q * q));
-    }
-    return s * (1.0f / 48.0f);
-}
-
-#define EXACT_CAP 2048   // candidates the exact path holds bounds for at a time
-#define EXACT_QCAP 512   // warp segments the exact path can keep (more -> brute force)
-struct MatchShared {
-    float rec[GT_REC];
-    int ccount[MAX_TILES];
-    int hit[HIT_CAP];       // brute force: exact values; bracket: staged tile boxes; exact path: anchors
-    float ev[1024];         // bracket: staged seed values; exact path: exact values of the survivors
-    float ub[EXACT_CAP];    // exact path: per-candidate bounds
-    float lb[EXACT_CAP];
-    int qseg[2 * EXACT_QCAP];  // exact path: kept segments (index, candidate ballot); later the survivors of the threshold
-    float qsu[EXACT_QCAP];     // their value bounds, counts, positions in decreasing order of the bound
-    int qcnt[EXACT_QCAP];
-    int qorder[EXACT_QCAP];
-    int hist[32];
-    float top[P24_TOPK];
-    KV kv[MATCH_WARPS];
-    float wmax[MATCH_WARPS];
-    int cnt, nhit, nev, k, slow, nvalid, overflow;
-    float T, L, tau, tmax, dmax;
-    int wanchor[MATCH_WCAP];   // the GT's valid (in window, in polygon) anchors and their costs
-    float wcost[MATCH_WCAP];
-    int wrank[MATCH_WCAP];     // how many valid pairs cost less
-};
-
-template <bool MAX>
-__device__ __forceinline__ KV match_block_select(KV x, KV* s_red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    x = warp_select<MAX>(x);
-    __syncthreads();
-    if (lane == 0) s_red[warp] = x;
-    __syncthreads();
-    KV y = s_red[lane < MATCH_WARPS ? lane : 0];
-    y = warp_select<MAX>(y);
-    return y;
-}
-
-// the `want` largest of vals[0..n) into S.top (descending) by one warp; destroys vals; returns the count
-__device__ int warp_select_top(float* vals, int n, int want, float* top) {
-    const int lane = threadIdx.x & 31;
-    int got = 0;
-    for (int r = 0; r < want; ++r) {
-        KV best = {P24_NEG_INF, 0x7fffffff};
-        for (int i = lane; i < n; i += 32) {
-            const float v = vals[i];
-            if (kv_gt(v, i, best.v, best.i)) {
-                best.v = v;
-                best.i = i;
-            }
-        }
-        best = warp_select<true>(best);
-        if (best.i == 0x7fffffff) break;
-        if (lane == 0) {
-            top[r] = best.v;
-            vals[best.i] = P24_NEG_INF;
-        }
-        __syncwarp();
-        ++got;
-    }
-    return got;
-}
-
-// Brute force (no usable threshold, P24_F_NO_FILTER, or list overflow): exact value of EVERY candidate, in chunks,
-// carrying the best kc forward.
-__device__ __noinline__ float topk_sum_bruteforce(const Params& p, MatchShared& S, int b, int kc) {
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const unsigned gm = group_mask();
-    const int grp = tid >> 3, sub = tid & 7;
-    const float* img = p.outputs + (long long)b * p.img_stride;
-    float* vals = reinterpret_cast<float*>(S.hit);  // HIT_CAP floats
-    int ncarry = 0;
-    const int tiles_per_chunk = (HIT_CAP - P24_TOPK) / P24_THREADS;
-    for (int t0 = 0; t0 < p.tiles; t0 += tiles_per_chunk) {
-        const int t1 = min(t0 + tiles_per_chunk, p.tiles);
-        __syncthreads();
-        if (tid < ncarry) vals[tid] = S.top[tid];
-        if (tid == 0) S.nhit = ncarry;
-        __syncthreads();
-        for (int tl = t0; tl < t1; ++tl) {
-            const long long blk = (long long)b * p.tiles + tl;
-            const int c = S.ccount[tl];
-            for (int i = grp; i < c; i += MATCH_GROUPS) {
-                const int a = __float_as_int(p.clist[blk * P24_THREADS + i].w);
-                const float v = group_pair_value(S.rec, img + (long long)a * p.row_stride, gm);
-                if (sub == 0) vals[atomicAdd(&S.nhit, 1)] = (v == v) ? v : P24_POS_INF;  // NaN sorts first (torch.topk)
-            }
-        }
-        __syncthreads();
-        if (warp == 0) warp_select_top(vals, S.nhit, kc, S.top);
-        __syncthreads();
-        ncarry = min(kc, S.nhit);
-    }
-    float ksum = 0.0f;
-    for (int i = 0; i < ncarry; ++i) ksum = ksum + (S.top[i] == P24_POS_INF ? NAN : S.top[i]);
-    return ksum;
-}
-
-// Upper bound of the pair value as a function of the centre distance d alone.  For an apart ray the loss is
-// 2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2 (and that expression bounds partial rays too, see bound_H_thread); over all
-// rp > 0 the fraction is smallest at rp* = rg^2 / (rg + d), where it equals rg^2 / ((rg + d)^2 + rg^2).  So every
-// ray has loss <= max(1, 2 - 4 rg^2 / ((rg + d)^2 + rg^2)) whatever the prediction: monotone in d, and tight for large
-// GTs, where bound_H_thread (which pays for the largest predicted radius of a whole tile) is loose.
-__device__ __forceinline__ float bound_Hstar_thread(const float* __restrict__ rec, float d) {
-    float s = 0.0f;
-#pragma unroll
-    for (int k = 0; k < P24_RAYS; ++k) {
-        const float rg = rec[GT_RG + k];
-        const float q = rg + d;
-        s += fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, fmaf(q, q, rg * rg)));
-    }
-    return s * (1.0f / 48.0f);
-}
-
-// Exact top-10 sum when the bracket is not conclusive (about 1 GT in 100; the large ones, whose values sit near 0.9
-// and whose sums sit near 9), in one pass over what can matter:
-//  1. every warp segment of the candidate lists (32 anchors: a short run of one grid row) whose value bound
-//     min(H(t), H*(d)) over its box reaches T (the 10th best seed value, a certified lower bound of the 10th largest
-//     value) is kept: the far corners of the image as seen from the GT;
-//  2. their candidates get per-candidate bounds (one thread each: ub = the apart formula, which bounds every ray;
-//     for a pair whose rays are all apart -- the reference's own fp32 comparison -- the value is ub to within 3e-6,
-//     so ub - 5e-5 is a certified lower bound);
-//  3. the 10th largest lower bound (two rounds of a 32-bin histogram) replaces T;
-//  4. the candidates whose ub still reaches it (a handful) are evaluated exactly (8-lane groups);
-//  5. the 10 largest exact values are summed in descending order (torch.topk order).
-// Returns NaN when the lists do not fit (the caller falls back to brute force).
-__device__ __noinline__ float topk_sum_exact(const Params& p, MatchShared& S, int b) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned gm = group_mask();
-    const int grp = tid >> 3, sub = tid & 7;
-    const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
-    const float* img = p.outputs + (long long)b * p.img_stride;
-    const float T0 = S.T;
-    if (tid == 0) {
-        S.nhit = 0;  // qualifying segments
-        S.cnt = 0;   // their candidates
-        S.nev = 0;
-        S.overflow = 0;
-    }
     __syncthreads();
     {
-        const float4* sg = reinterpret_cast<const float4*>(p.seg + (long long)b * p.tiles * P24_WARPS * 8);
-        const int nseg = p.tiles * P24_WARPS;
-        for (int si = tid; si < nseg; si += MATCH_THREADS) {
-            const float4 bx = sg[2 * si];
-            const float4 r1 = sg[2 * si + 1];
-            const int cnt = __float_as_int(r1.y);
-            if (cnt <= 0) continue;
-            const float fx = fmaxf(fabsf(gcx - bx.x), fabsf(gcx - bx.y));
-            const float fy = fmaxf(fabsf(gcy - bx.z), fabsf(gcy - bx.w));
-            const float dm = sqrtf(fmaf(fx, fx, fy * fy)) * 1.0001f + 0.01f;
-            const float u = fminf(bound_H_thread(S.rec, r1.x + dm), bound_Hstar_thread(S.rec, dm)) + 2e-5f;
-            if (u < T0 && r1.x < 60000.0f) continue;  // (NaN bounds and tiny predicted radii stay in)
-            const int q = atomicAdd(&S.nhit, 1);
-            const int pos = atomicAdd(&S.cnt, cnt);
-            if (q < EXACT_QCAP) {
-                S.qseg[2 * q] = si;
-                S.qseg[2 * q + 1] = __float_as_int(r1.w);  // which of the segment's 32 anchors are candidates
-                S.qsu[q] = (u == u && r1.x < 60000.0f) ? u : P24_POS_INF;
-                S.qcnt[q] = cnt;
-                S.qorder[q] = pos;  // the segment's first slot when everything fits (the usual case)
-            } else {
-                S.overflow = 1;
-            }
-        }
-    }
-    __syncthreads();
-    if (S.overflow) return NAN;
-    const int nq = S.nhit;
-    const bool all_fit = S.cnt <= EXACT_CAP;
-    __syncthreads();
-    if (all_fit) {
-        for (int q = tid; q < nq; q += MATCH_THREADS) {
-            S.qcnt[q] = S.qorder[q];
-            S.qorder[q] = q;
-        }
-        if (tid == 0) {
-            S.k = nq;
-            S.L = P24_NEG_INF;
-        }
-    }
-    // otherwise: the kept segments in decreasing order of their bound; the first ones that fit EXACT_CAP candidates are
-    // examined, and the best bound among the others (S.L) must end up below the refined threshold
-    for (int q = tid; q < nq && !all_fit; q += MATCH_THREADS) {
-        const float uq = S.qsu[q];
-        int rank = 0;
-        for (int j = 0; j < nq; ++j) rank += kv_gt(S.qsu[j], j, uq, q) ? 1 : 0;
-        S.qorder[rank] = q;
-    }
-    __syncthreads();
-    if (warp == 0 && !all_fit) {
-        int run = 0, ncut = nq;  // candidates so far; number of examined segments
-        for (int r0 = 0; r0 < nq && ncut == nq; r0 += 32) {
-            const int r = r0 + lane;
-            const int q = r < nq ? S.qorder[r] : 0;
-            const int c = r < nq ? S.qcnt[q] : 0;
-            int inc = c;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, off);
-                if (lane >= off) inc += t;
-            }
-            const bool fits = r < nq && run + inc <= EXACT_CAP;
-            if (fits) S.qcnt[q] = run + inc - c;  // from here on: the segment's first slot
-            const unsigned fm = __ballot_sync(0xffffffffu, fits);
-            const unsigned vm = __ballot_sync(0xffffffffu, r < nq);
-            const int nfit = __popc(fm);  // fits is a prefix of the valid lanes (counts are positive)
-            if (fm != vm) ncut = r0 + nfit;
-            const int last = __shfl_sync(0xffffffffu, inc, nfit > 0 ? nfit - 1 : 0);
-            if (nfit > 0) run += last;
-        }
-        if (lane == 0) {
-            S.k = ncut;
-            S.cnt = run;
-            S.L = ncut < nq ? S.qsu[S.qorder[ncut]] : P24_NEG_INF;
-        }
-    }
-    __syncthreads();
-#ifdef P24_TIMING
-    if (tid == 0) {
-        g_tstamp[1][b * 20 + (int)blockIdx.y][9] = S.nhit;
-        g_tstamp[1][b * 20 + (int)blockIdx.y][10] = S.cnt;
-        g_tstamp[1][b * 20 + (int)blockIdx.y][11] = S.k;
-    }
-    TMARK(1, b * 20 + (int)blockIdx.y, 16);
-#endif
-    const int n1 = S.cnt, ncut = S.k;
-    const float su_rest = S.L;
-    // the anchors of the examined segments (a segment is 32 consecutive anchors; its candidates are the set bits)
-    for (int r = warp; r < ncut; r += MATCH_WARPS) {
-        const int q = S.qorder[r];
-        const int si = S.qseg[2 * q], pos = S.qcnt[q];
-        const unsigned m = (unsigned)S.qseg[2 * q + 1];
-        if ((m >> lane) & 1u) S.hit[pos + __popc(m & ((1u << lane) - 1u))] = si * 32 + lane;
-    }
-    __syncthreads();
-    // per-candidate bounds, one candidate per thread and pass: all loads of a pass are independent
-    for (int i = tid; i < n1; i += MATCH_THREADS) {
-        const int a = S.hit[i];
-        const float* row = img + (long long)a * p.row_stride;
-        float rpv[P24_RAYS];
-#pragma unroll
-        for (int k = 0; k < P24_RAYS; ++k) rpv[k] = row[2 + k];  // one round trip for the whole row
-        const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
-        float u = 0.0f, rpmin = INFINITY;
-        bool apart = true;
-#pragma unroll
-        for (int k = 0; k < P24_RAYS; ++k) {
-            const float rg = S.rec[GT_RG + k], rp = rpv[k];
-            u += p24_ray_loss_ub(rg, rp, d);
-            apart = apart && (d >= rg + rp);
-            rpmin = fminf(rpmin, rp);
-        }
-        u = u * (1.0f / 48.0f) + 2e-5f;
-        const bool trust = rpmin >= 0.25f && u == u;  // tiny predicted radii / NaN: evaluated exactly, no bounds
-        S.ub[i] = trust ? u : P24_POS_INF;
-        S.lb[i] = (trust && apart) ? u - 5e-5f : P24_NEG_INF;
-    }
-    __syncthreads();
-    TMARK(1, b * 20 + (int)blockIdx.y, 17);
-    // the 10th largest lower bound to within (1 - T0) / 1024: two rounds of a 32-bin histogram, starting from [T0, 1]
-    float lo = T0, width = fmaxf(1.0f - T0, 1e-6f);
-#pragma unroll 1
-    for (int round = 0; round < 2; ++round) {
-        if (tid < 32) S.hist[tid] = 0;
-        __syncthreads();
-        const float scale = 32.0f / width;
-        for (int i = tid; i < n1; i += MATCH_THREADS) {
-            const float l = S.lb[i];
-            if (l >= lo) atomicAdd(&S.hist[min((int)((l - lo) * scale), 31)], 1);
-        }
-        __syncthreads();
-        // the highest bin whose count, together with the bins above it, reaches 10
-        int above = 0, bin = -1;
-        for (int j = 31; j >= 0; --j) {
-            above += S.hist[j];
-            if (above >= P24_TOPK) {
-                bin = j;
-                break;
-            }
-        }
-        __syncthreads();
-        if (bin < 0) break;  // fewer than 10 lower bounds reach lo: lo stays (it is certified by the seeds or the last round)
-        lo = lo + (float)bin * (width * (1.0f / 32.0f));
-        width = width * (1.0f / 32.0f);
-    }
-    const float tcur = fmaxf(T0, lo - 1e-6f);
-    if (!(su_rest < tcur)) return NAN;  // a segment that was not examined could still hold a top-10 value (rare)
-    for (int i = tid; i < n1; i += MATCH_THREADS)
-        if (!(S.ub[i] < tcur)) {
-            const int at = atomicAdd(&S.nev, 1);
-            if (at < 1024) S.qseg[at] = S.hit[i];  // (the segment list is no longer needed)
-            else S.overflow = 1;
-        }
-    __syncthreads();
-    TMARK(1, b * 20 + (int)blockIdx.y, 18);
-#ifdef P24_TIMING
-    if (tid == 0) g_tstamp[1][b * 20 + (int)blockIdx.y][7] = S.nev;
-#endif
-    if (S.overflow) return NAN;
-    const int nsurv = S.nev;
-    for (int i0 = 0; i0 < nsurv; i0 += MATCH_GROUPS) {
-        const int i = i0 + grp;
-        if (i >= nsurv) continue;
-        const float v = group_pair_value(S.rec, img + (long long)S.qseg[i] * p.row_stride, gm);
-        if (sub == 0) S.ev[i] = (v == v) ? v : P24_POS_INF;  // NaN sorts first (torch.topk)
-    }
-    __syncthreads();
-    TMARK(1, b * 20 + (int)blockIdx.y, 19);
-    if (nsurv < P24_TOPK) return NAN;
-    for (int i = tid; i < nsurv; i += MATCH_THREADS) {
-        const float vi = S.ev[i];
-        int rank = 0;
-        for (int j = 0; j < nsurv; ++j) rank += kv_gt(S.ev[j], j, vi, i) ? 1 : 0;
-        if (rank < P24_TOPK) S.top[rank] = vi;
-    }
-    __syncthreads();
-    float ksum = 0.0f;
-    for (int i = 0; i < P24_TOPK; ++i) ksum = ksum + (S.top[i] == P24_POS_INF ? NAN : S.top[i]);
-    return ksum;
-}
-
-// Spill path (rare: GT with fewer valid anchors than its dynamic k): take `need` more anchors with the
-// smallest PENALISED cost among the candidates that are not valid for this GT.  Ties -> lower anchor index.
-__device__ __noinline__ void spill_claims(const Params& p, MatchShared& S, int b, int g, int nwin, int need) {
-    float lv[P24_TOPK];
-    int li[P24_TOPK];
-#pragma unroll
-    for (int i = 0; i < P24_TOPK; ++i) {
-        lv[i] = P24_POS_INF;
-        li[i] = 0x7fffffff;
-    }
-    const int tid = threadIdx.x;
-    const float* img = p.outputs + (long long)b * p.img_stride;
-    const int c = gt_class(S.rec, p.nc);
-    for (int tl = 0; tl < p.tiles; ++tl) {
-        const long long blk = (long long)b * p.tiles + tl;
-        const int cc = S.ccount[tl];
-        for (int i = tid; i < cc; i += MATCH_THREADS) {
-            const int a = __float_as_int(p.clist[blk * P24_THREADS + i].w);
-            bool isvalid = false;
-            for (int j = 0; j < nwin; ++j) isvalid |= (S.wanchor[j] == a && S.wcost[j] != P24_POS_INF);
-            if (isvalid) continue;
-            const float* row = img + (long long)a * p.row_stride;
-            const float eo1 = 1.0f + expf(-row[26]);
-            const float neg = thread_cls_neg_sum(row + 27, p.nc, eo1);
-            const float v = pair_value_row(S.rec, row);
-            const float cost = p24_cost(cls_cost_from(neg, row[27 + c], 1.0f / eo1), v, false);
-            if (kv_lt(cost, a, lv[P24_TOPK - 1], li[P24_TOPK - 1])) {
-                float cv = cost;
-                int ci = a;
-#pragma unroll
-                for (int q = 0; q < P24_TOPK; ++q) {
-                    if (kv_lt(cv, ci, lv[q], li[q])) {
-                        const float tv = lv[q];
-                        const int ti = li[q];
-                        lv[q] = cv;
-                        li[q] = ci;
-                        cv = tv;
-                        ci = ti;
-                    }
-                }
-            }
-        }
-    }
-    for (int r = 0; r < need; ++r) {
-        const KV head = {lv[0], li[0]};
-        const KV win = match_block_select<false>(head, S.kv);
-        if (win.i == 0x7fffffff) break;  // fewer candidates than needed
-        if (li[0] == win.i && lv[0] == win.v) {
-            claim_anchor(p, b, win.i, g);
-#pragma unroll
-            for (int q = 0; q < P24_TOPK - 1; ++q) {
-                lv[q] = lv[q + 1];
-                li[q] = li[q + 1];
-            }
-            lv[P24_TOPK - 1] = P24_POS_INF;
-            li[P24_TOPK - 1] = 0x7fffffff;
+        const int nitems = min(S.nitems, ITEM_CAP);
+        for (int i = tid; i < nitems; i += P24_THREADS) {
+            const unsigned it = S.items[i];
+            far_pair(p, s_rec, S, b, (int)(it >> 8), (int)(it & 0xFF));
         }
     }
 }
 
 // -------------------------------------------------------------------------------------------
-// k_pass, centre-window CTAs: every (GT, centre-window anchor) pair as an independent 8-lane group task:
+// k_pass, centre-window items: every (GT, centre-window anchor) pair as an independent 8-lane group task:
 // polygon test (inscribed-disc accept, else the reference-order edge terms, 3 per lane), exact pair value and
 // SimOTA cost when inside.  The window of a GT is enumerated straight from the level grids (a 7 x 7 block of cells
 // per level around the centre holds every anchor that can pass the strict test of losses.py:523-542, which is then
-// applied in the reference's own arithmetic), so this part needs nothing from the anchor CTAs and runs beside them.
+// applied in the reference's own arithmetic), so this part needs nothing from the anchor tiles and runs beside them.
 // Costs land in the GT's window table by slot (level, row, column); the anchor of a slot and the slot of an anchor
-// are both computable, which is what k_match (selection) and k_resolve_loss (conflict argmin) rely on.
+// are both computable, which is what k_tail (selection and conflict argmin) relies on.
 // -------------------------------------------------------------------------------------------
 struct WindowShared {
     float rec[GT_REC];
     int list[P24_WSLOTS];  // slots of the level that pass the centre-window test
-    int org[2];
     int npair;
 };
 
@@ -1234,7 +874,21 @@ __device__ __forceinline__ void window_part(const Params& p, WindowShared& S, in
                 nsat = group_sum_i(nsat, gm);
                 neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(row + 27, p.nc, eo1, gm);
             } else {
-                neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+                // many classes: the log of a per-lane product, restarted before it can underflow
+                float prod = 1.0f, lsum = 0.0f;
+                int nsat = 0;
+                for (int j = sub; j < p.nc; j += 8) {
+                    p24_neg_factor(row[27 + j], eo1, prod, nsat);
+                    if (prod < 1e-20f) {
+                        lsum += logf(prod);
+                        prod = 1.0f;
+                    }
+                }
+                lsum += logf(prod);
+                lsum = group_sum(lsum, gm);
+                nsat = group_sum_i(nsat, gm);
+                neg = -lsum + 100.0f * (float)nsat;
+                if (!(neg == neg) || neg == P24_POS_INF) neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
             }
             float cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
             if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
@@ -1243,258 +897,76 @@ __device__ __forceinline__ void window_part(const Params& p, WindowShared& S, in
     }
 }
 
-// k_pass: persistent CTAs (one wave) drawing work items from a ticket counter: first the anchor tiles (the long items),
-// then the (GT, level) centre-window items.  Launched as a programmatic dependent of k_gt_prep: the first item's rows
-// are in flight before the CTA waits for the records.
+// k_pass: persistent CTAs (one wave: the grid never exceeds what the device holds at once) drawing work items from
+// ticket counters: first the seed items (their own counter), then the anchor tiles (the long items), then the
+// (GT, level) centre-window items.  Launched as a programmatic dependent of k_prep: the first tile's rows are in flight
+// before the CTA waits for the records.
 union PassShared {
     AnchorShared a;
     WindowShared w;
 };
 
 __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__ Params p) {
-    extern __shared__ float4 s_dyn4[];
+    extern __shared__ float4 s_dyn4[];   // [Lmax * GT_REC] floats: the image's records (anchor tiles); seed scratch
     __shared__ PassShared S;
-    __shared__ int s_item;
+    __shared__ int s_item, s_seed;
+    float* s_rec = reinterpret_cast<float*>(s_dyn4);
     const int n_anchor = p.B * p.tiles;
-    bool first = true;
-    int leff = 0;  // the batch's largest num_gt (known once k_gt_prep is complete)
-    for (;;) {
+    const int tid = threadIdx.x;
+    // the first tickets do not depend on k_prep
+    if (tid == 0) {
+        s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);
+        s_seed = (int)atomicAdd(&p.ticket[TK_SEED], 1u);
+    }
+    __syncthreads();
+    int item = s_item, seed = s_seed;
+    bool staged = false;
+    if (item < n_anchor) {
+        stage_rows(p, S.a, item / p.tiles, item % p.tiles);
+        staged = true;
+    }
+    pdl_wait();  // the records come from k_prep
+    const int leff = (int)__ldcg(&p.ticket[TK_LEFF]);  // the batch's largest num_gt
+    // ---- seed items: image fastest, so that the real GT rows (valid rows come first) are drawn first ---------------
+    {
+        SeedShared& SS = *reinterpret_cast<SeedShared*>(s_dyn4);
+        const int n_seed = p.B * leff;
+        while (seed < n_seed) {
+            __syncthreads();
+            if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_SEED], 1u);  // the next one, in flight meanwhile
+            const int g = seed / p.B, b = seed - g * p.B;
+            if (g < p.num_gt[b]) seed_part(p, SS, b, g);
+            __syncthreads();
+            seed = s_seed;
+        }
+    }
+    const int n_items = n_anchor + p.B * leff * p.nlev;
+    while (item < n_items) {
         __syncthreads();
-        if (threadIdx.x == 0) s_item = (int)atomicAdd(&p.ticket[1 + p.B], 1u);
-        __syncthreads();
-        const int item = s_item;
+        if (tid == 0) s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);  // the next one, in flight meanwhile
         if (item < n_anchor) {
             // image-major order keeps an image's tiles (and its records) together in time
-            anchor_part(p, s_dyn4, S.a, item / p.tiles, item % p.tiles, first);
-            first = false;
+            anchor_part(p, s_rec, S.a, item / p.tiles, item % p.tiles, staged);
+            staged = false;
         } else {
-            if (first) {
-                pdl_wait();
-                first = false;
-            }
-            if (leff == 0) leff = (int)__ldcg(&p.ticket[2 + p.B]);
             const int wi = item - n_anchor;
-            if (wi >= p.B * leff * p.nlev) break;
             const int l = wi % p.nlev, bg = wi / p.nlev;
             const int b = bg / leff, g = bg - b * leff;
-            if (g < p.num_gt[b]) {
-                TMARK(4, wi, 0);
-                window_part(p, S.w, b, g, l);
-                TMARK(4, wi, 1);
-            }
+            if (g < p.num_gt[b]) window_part(p, S.w, b, g, l);
         }
+        __syncthreads();
+        item = s_item;
     }
     pdl_trigger();
 }
 
-// dynamic k is known: record it and claim the k smallest costs among the GT's valid pairs (losses.py:460-464; the valid
-// pairs and their ranks -- ties -> lower anchor index -- were prepared while the bracket was being evaluated); spill into
-// the penalised regime when there are fewer valid pairs than k.
-__device__ __forceinline__ void claim_selected(const Params& p, MatchShared& S, int b, int g, int k) {
-    const int tid = threadIdx.x;
-    __syncthreads();
-    if (tid == 0) p.dyn_k[b * p.Lmax + g] = k;
-    const int nv = min(S.nvalid, MATCH_WCAP);
-    const int take = min(k, nv);
-    if (tid < nv && S.wrank[tid] < take) claim_anchor(p, b, S.wanchor[tid], g);
-    if (k > nv) spill_claims(p, S, b, g, nv, k - nv);
-}
+// -------------------------------------------------------------------------------------------
+// k_tail: one CTA per image
+// -------------------------------------------------------------------------------------------
+#define TAIL_THREADS 1024
+#define TAIL_WARPS (TAIL_THREADS / 32)
+#define MBOX_SLOT 64  // floats per (epoch half, rank) slot of a mailbox: 28 sums, flag at [32]
 
-// -------------------------------------------------------------------------------------------
-// k_match: per GT, dynamic k = clamp(int(sum of the 10 largest pair values over the candidates), 1) from the seed
-// values of the anchor pass (top-10 bracket; exact filtered / brute-force paths when it is not conclusive), then
-// the k smallest costs of its valid pairs -> claims (rank counting; spill into the penalised regime when the GT
-// has fewer valid anchors than k)
-// -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MATCH_THREADS, 3) k_match(const __grid_constant__ Params p) {
-    // images vary fastest over the grid: the low GT rows (the real ones: valid rows come first) are dispatched before
-    // the rows beyond num_gt, which leave at once
-    const int g = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-#define MCTA (b * 20 + g)
-    if (g < 20) TMARK(1, MCTA, 0);
-    pdl_trigger();  // k_resolve_loss may become resident
-    pdl_wait();
-    const int n = p.num_gt[b];
-    if (g >= n) {
-        if (tid == 0) p.dyn_k[b * p.Lmax + g] = 0;
-        return;
-    }
-    TMARK(1, MCTA, 1);
-    __shared__ MatchShared S;
-    const int wslot = b * p.Lmax + g;
-    if (tid < GT_REC) S.rec[tid] = p.gt_rec[(long long)wslot * GT_REC + tid];
-    int cnt = 0;
-    for (int tl = tid; tl < p.tiles; tl += MATCH_THREADS) {
-        const int c = p.ccount[(long long)b * p.tiles + tl];
-        S.ccount[tl] = c;
-        cnt += c;
-    }
-    // everything the bracket reads, staged by all threads in one round trip (S.hit / S.ev are free until a slow path)
-    float4* s_tb = reinterpret_cast<float4*>(S.hit);   // [2 * tiles] float4   (tiles <= 256 here, else read in place)
-    float* s_sv = S.ev;                                // [P24_SEEDS * tiles]
-    const bool staged = p.tiles <= 256;
-    if (staged) {
-        const float4* tbg = reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
-        for (int i = tid; i < 2 * p.tiles; i += MATCH_THREADS) s_tb[i] = tbg[i];
-        const float* svg = p.sval + (long long)wslot * (P24_SEEDS * p.tiles);
-        for (int i = tid; i < P24_SEEDS * p.tiles; i += MATCH_THREADS) s_sv[i] = svg[i];
-    }
-    // the GT's window table (costs of its valid pairs), requested in the same round trip: the selection is prepared by
-    // warps 1..7 while warp 0 evaluates the bracket
-    const float* tab = p.wtab + (long long)wslot * P24_WT_STRIDE;
-    const int nslot = P24_WSLOTS * p.nlev;  // <= 196 < MATCH_THREADS
-    float wc = P24_POS_INF, wox = 0.0f, woy = 0.0f;
-    if (tid < nslot) {
-        const int l = tid / P24_WSLOTS;
-        wc = tab[tid];
-        wox = tab[P24_WT_HDR + 2 * l];
-        woy = tab[P24_WT_HDR + 2 * l + 1];
-    }
-    if (tid == 0) {
-        S.cnt = 0;
-        S.nvalid = 0;
-    }
-    __syncthreads();
-    cnt = warp_sum_i(cnt);
-    if (lane == 0 && cnt) atomicAdd(&S.cnt, cnt);
-    if (wc < P24_POS_INF) {
-        const int l = tid / P24_WSLOTS, r = tid - l * P24_WSLOTS;
-        const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
-        const int ix = __float_as_int(wox) + sx, iy = __float_as_int(woy) + sy;
-        const int slot = atomicAdd(&S.nvalid, 1);
-        if (slot < MATCH_WCAP) {
-            S.wanchor[slot] = p.lev[l].off + iy * p.lev[l].W + ix;
-            S.wcost[slot] = wc;
-        } else {
-            atomicOr(p.err_flag, 1);
-        }
-    }
-    const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
-    __syncthreads();
-    TMARK(1, MCTA, 2);
-    const int ncand = S.cnt;
-    const int kc = min(P24_TOPK, ncand);  // losses.py:452
-
-    // ---- bracket the top-10 sum: L = sum of the 10 best seed values <= S <= 10 * H(t_max) = U (warp 0) ------------
-    if (warp == 0) {
-        // largest t = rpmax + d over the candidates, bounded per tile by its box
-        float tm = P24_NEG_INF, dm = P24_NEG_INF;  // ... and the largest centre distance d
-        const float4* tb = staged ? s_tb : reinterpret_cast<const float4*>(p.tbox + (long long)b * p.tiles * 8);
-        for (int i = lane; i < p.tiles; i += 32) {
-            const float4 bx = tb[2 * i];
-            const float rzm = tb[2 * i + 1].x;
-            if (rzm > P24_NEG_INF) {
-                const float fx = fmaxf(fabsf(gcx - bx.x), fabsf(gcx - bx.y));
-                const float fy = fmaxf(fabsf(gcy - bx.z), fabsf(gcy - bx.w));
-                const float dd = sqrtf(fmaf(fx, fx, fy * fy)) * 1.00001f;
-                tm = fmaxf(tm, rzm + dd);
-                dm = fmaxf(dm, dd);
-            }
-        }
-        tm = warp_max(tm);
-        dm = warp_max(dm);
-        // the 10 largest seed values, summed in descending order (like the reference sums torch.topk's output)
-        const int nseed = P24_SEEDS * p.tiles;
-        const float* sv = staged ? s_sv : p.sval + (long long)wslot * nseed;
-        float v0 = P24_NEG_INF, v1 = P24_NEG_INF, v2 = P24_NEG_INF, v3 = P24_NEG_INF;  // the lane's 4 best seeds
-        for (int i = lane; i < nseed; i += 32) {
-            float v = sv[i];
-            if (v > v0) { const float t0 = v0; v0 = v; v = t0; }
-            if (v > v1) { const float t1 = v1; v1 = v; v = t1; }
-            if (v > v2) { const float t2 = v2; v2 = v; v = t2; }
-            if (v > v3) v3 = v;
-        }
-        float T = P24_NEG_INF, L = 0.0f;
-        int got = 0;
-        if (kc == P24_TOPK) {
-#pragma unroll 1
-            for (int r = 0; r < P24_TOPK; ++r) {
-                const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-                const KV best = warp_select<true>(KV{m, lane});
-                if (!(best.v > P24_NEG_INF)) break;
-                if (lane == best.i) {  // remove one copy of the winner
-                    if (v0 == m) v0 = P24_NEG_INF;
-                    else if (v1 == m) v1 = P24_NEG_INF;
-                    else if (v2 == m) v2 = P24_NEG_INF;
-                    else v3 = P24_NEG_INF;
-                }
-                L = L + best.v;
-                T = best.v;
-                ++got;
-            }
-            if (got < P24_TOPK) T = P24_NEG_INF;
-        }
-        int slow = 1, k = 0;
-        const bool usable = T > P24_NEG_INF && !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && tm < 60000.0f;
-        if (usable) {
-            // two monotone bounds of any candidate's value: H(t_max) (bound_H_thread) and H*(d_max) (bound_Hstar_thread)
-            float term = 0.0f, term2 = 0.0f;
-            if (lane < P24_RAYS) {
-                const float rg = S.rec[GT_RG + lane];
-                const float q = rg + (tm * 1.0001f + 0.01f);
-                term = fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, q * q));
-                const float q2 = rg + (dm * 1.0001f + 0.01f);
-                term2 = fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, fmaf(q2, q2, rg * rg)));
-            }
-            const float U = 10.0f * (fminf(warp_sum(term), warp_sum(term2)) * (1.0f / 48.0f) + 2e-5f);
-            const float fl = floorf(L - 1e-4f), fu = floorf(U + 1e-4f);
-#ifdef P24_TIMING
-            if (lane == 0) {
-                g_tstamp[1][MCTA][12] = __float_as_uint(L);
-                g_tstamp[1][MCTA][13] = __float_as_uint(U);
-                g_tstamp[1][MCTA][14] = __float_as_uint(tm);
-                g_tstamp[1][MCTA][15] = __float_as_uint(S.rec[GT_RGMAX]);
-            }
-#endif
-            if (fl == fu && fl >= 1.0f) {
-                slow = 0;
-                k = (int)fl;
-            }
-        }
-        if (lane == 0) {
-            S.slow = slow ? (usable ? 1 : 2) : 0;  // 1: filtered exact path, 2: brute force
-            S.k = k;
-            S.T = T;
-            S.tmax = tm;
-        }
-    } else {
-        // ---- meanwhile: rank of every valid pair by (cost, anchor) -----------------------------------------------------
-        const int nv = min(S.nvalid, MATCH_WCAP);
-        for (int e = tid - 32; e < nv; e += MATCH_THREADS - 32) {
-            const float ci = S.wcost[e];
-            const int ai = S.wanchor[e];
-            int before = 0;
-            for (int j = 0; j < nv; ++j) before += kv_lt(S.wcost[j], S.wanchor[j], ci, ai) ? 1 : 0;
-            S.wrank[e] = before;
-        }
-    }
-    __syncthreads();
-    TMARK(1, MCTA, 4);
-#ifdef P24_TIMING
-    if (tid == 0) {
-        g_tstamp[1][MCTA][8] = S.slow;
-        g_tstamp[1][MCTA][9] = 0;
-    }
-#endif
-    int k;
-    if (S.slow) {
-        float ksum = NAN;
-        if (S.slow == 1) ksum = topk_sum_exact(p, S, b);
-        if (!(ksum == ksum)) ksum = topk_sum_bruteforce(p, S, b, kc);
-        k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
-        if (k < 1) k = 1;
-    } else {
-        k = S.k;
-    }
-    TMARK(1, MCTA, 5);
-    claim_selected(p, S, b, g, min(k, ncand));  // torch.topk would raise beyond the candidate count; clamp instead
-    TMARK(1, MCTA, 6);
-}
-
-// -------------------------------------------------------------------------------------------
-// k_resolve_loss
-// -------------------------------------------------------------------------------------------
 // normalisation + stateful re-weighting, losses.py:280-345; executed by one warp
 __device__ void finalize_warp(const float* sums28, float* state26, float* result54, float* weights_n27) {
     const int lane = threadIdx.x & 31;
@@ -1552,9 +1024,189 @@ __device__ __forceinline__ float warp_pair_value(const float* __restrict__ rec, 
     return (warp_sum(l) / 24.0f) / 2.0f;
 }
 
+struct TailShared {
+    long long acc[TAIL_WARPS][26];
+    KV kv[TAIL_WARPS];
+    float sums[28];
+    int nuniq, nbrute, nspill, last;
+    int lmax;
+};
+
+template <bool MAX>
+__device__ __forceinline__ KV tail_block_select(KV x, KV* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x = warp_select<MAX>(x);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = x;
+    __syncthreads();
+    KV y = s_red[lane];  // TAIL_WARPS == 32
+    y = warp_select<MAX>(y);
+    return y;
+}
+
+// sorted insert into a descending register list of P24_TOPK values
+__device__ __forceinline__ void top_insert_desc(float (&t)[P24_TOPK], float v) {
+#pragma unroll
+    for (int q = 0; q < P24_TOPK; ++q) {
+        if (v > t[q]) {
+            const float x = t[q];
+            t[q] = v;
+            v = x;
+        }
+    }
+}
+
+// Brute force (list overflow, P24_F_NO_FILTER, or fewer list entries than expected): the exact pair value of EVERY
+// candidate of the image (candidate bitmap), the kc largest summed in descending order.  Whole CTA.
+__device__ __noinline__ float topk_sum_bruteforce(const Params& p, TailShared& S, const float* __restrict__ rec, int b, int kc) {
+    const int tid = threadIdx.x;
+    const float* img = p.outputs + (long long)b * p.img_stride;
+    const unsigned* bits = p.cbits + (long long)b * p.tiles * P24_WARPS;
+    float t[P24_TOPK];
+#pragma unroll
+    for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;
+    for (int a = tid; a < p.A; a += TAIL_THREADS) {
+        if (!((bits[a >> 5] >> (a & 31)) & 1u)) continue;
+        float v = pair_value_row(rec, img + (long long)a * p.row_stride);
+        if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
+        top_insert_desc(t, v);
+    }
+    float ksum = 0.0f;
+    for (int r = 0; r < kc; ++r) {
+        const KV best = tail_block_select<true>(KV{t[0], t[0] > P24_NEG_INF ? tid : 0x7fffffff}, S.kv);
+        if (best.i == 0x7fffffff) break;
+        if (tid == best.i) {
+#pragma unroll
+            for (int q = 0; q < P24_TOPK - 1; ++q) t[q] = t[q + 1];
+            t[P24_TOPK - 1] = P24_NEG_INF;
+        }
+        ksum = ksum + (best.v == P24_POS_INF ? NAN : best.v);
+    }
+    return ksum;
+}
+
+// Spill path (rare: GT with fewer valid anchors than its dynamic k): `need` more anchors with the smallest PENALISED
+// cost among the candidates that are not valid for this GT (losses.py:460-464 on the penalised rows).  Ties -> lower
+// anchor index.  Whole CTA; the new claims go to claim[at..].
+__device__ __noinline__ void spill_claims(const Params& p, TailShared& S, const float* __restrict__ rec, int b, int g, int need,
+                                          int* claim, int at) {
+    float lv[P24_TOPK];
+    int li[P24_TOPK];
+#pragma unroll
+    for (int i = 0; i < P24_TOPK; ++i) {
+        lv[i] = P24_POS_INF;
+        li[i] = 0x7fffffff;
+    }
+    const int tid = threadIdx.x;
+    const float* img = p.outputs + (long long)b * p.img_stride;
+    const unsigned* bits = p.cbits + (long long)b * p.tiles * P24_WARPS;
+    const float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
+    const int c = gt_class(rec, p.nc);
+    for (int a = tid; a < p.A; a += TAIL_THREADS) {
+        if (!((bits[a >> 5] >> (a & 31)) & 1u)) continue;
+        // valid for this GT (in window and in polygon: a finite entry of the window table)?
+        int l = 0;
+#pragma unroll
+        for (int q = 1; q < P24_MAX_LEVELS; ++q) l += (q < p.nlev && a >= p.lev[q].off) ? 1 : 0;
+        const int r = a - p.lev[l].off;
+        const int iy = r / p.lev[l].W, ix = r - iy * p.lev[l].W;
+        const int sx = ix - __float_as_int(tab[P24_WT_HDR + 2 * l]), sy = iy - __float_as_int(tab[P24_WT_HDR + 2 * l + 1]);
+        if (sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE && tab[l * P24_WSLOTS + sy * P24_WSIDE + sx] < P24_POS_INF)
+            continue;
+        const float* row = img + (long long)a * p.row_stride;
+        const float eo1 = 1.0f + expf(-row[26]);
+        const float neg = thread_cls_neg_sum(row + 27, p.nc, eo1);
+        const float v = pair_value_row(rec, row);
+        const float cost = p24_cost(cls_cost_from(neg, row[27 + c], 1.0f / eo1), v, false);
+        if (kv_lt(cost, a, lv[P24_TOPK - 1], li[P24_TOPK - 1])) {
+            float cv = cost;
+            int ci = a;
+#pragma unroll
+            for (int q = 0; q < P24_TOPK; ++q) {
+                if (kv_lt(cv, ci, lv[q], li[q])) {
+                    const float tv = lv[q];
+                    const int ti = li[q];
+                    lv[q] = cv;
+                    li[q] = ci;
+                    cv = tv;
+                    ci = ti;
+                }
+            }
+        }
+    }
+    int got = 0;
+    for (int r = 0; r < need; ++r) {
+        const KV head = {lv[0], li[0]};
+        const KV win = tail_block_select<false>(head, S.kv);
+        if (win.i == 0x7fffffff) break;  // fewer candidates than needed
+        if (li[0] == win.i && lv[0] == win.v) {
+            claim[at + got] = win.i;
+#pragma unroll
+            for (int q = 0; q < P24_TOPK - 1; ++q) {
+                lv[q] = lv[q + 1];
+                li[q] = li[q + 1];
+            }
+            lv[P24_TOPK - 1] = P24_POS_INF;
+            li[P24_TOPK - 1] = 0x7fffffff;
+        }
+        ++got;
+    }
+}
+
+// The k smallest costs among the GT's valid pairs (window table) -> claim[g * 10 ..] (losses.py:460-464; ties -> lower
+// anchor index).  One warp.  Returns the number of valid pairs taken (< k: the GT must spill).
+#define WSL_PER_LANE ((P24_WT_HDR + 31) / 32)   // 7
+__device__ __forceinline__ int warp_select_claims(const Params& p, int b, int g, int k, int* claim) {
+    const int lane = threadIdx.x & 31;
+    const float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
+    const int nslot = P24_WSLOTS * p.nlev;
+    float wc[WSL_PER_LANE];
+    int wa[WSL_PER_LANE];
+    int nv = 0;
+#pragma unroll
+    for (int q = 0; q < WSL_PER_LANE; ++q) {
+        const int s = lane + 32 * q;
+        wc[q] = P24_POS_INF;
+        wa[q] = 0x7fffffff;
+        if (s < nslot) {
+            const float c = __ldcg(tab + s);
+            if (c < P24_POS_INF) {
+                const int l = s / P24_WSLOTS, r = s - l * P24_WSLOTS;
+                const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+                const int ix = __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l)) + sx;
+                const int iy = __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l + 1)) + sy;
+                wc[q] = c;
+                wa[q] = p.lev[l].off + iy * p.lev[l].W + ix;
+                ++nv;
+            }
+        }
+    }
+    nv = warp_sum_i(nv);
+    const int take = min(k, nv);
+#pragma unroll 1
+    for (int r = 0; r < take; ++r) {
+        KV best = {P24_POS_INF, 0x7fffffff};
+#pragma unroll
+        for (int q = 0; q < WSL_PER_LANE; ++q)
+            if (kv_lt(wc[q], wa[q], best.v, best.i)) {
+                best.v = wc[q];
+                best.i = wa[q];
+            }
+        const KV win = warp_select<false>(best);
+#pragma unroll
+        for (int q = 0; q < WSL_PER_LANE; ++q)
+            if (wa[q] == win.i) {  // an anchor appears once in a GT's table
+                wc[q] = P24_POS_INF;
+                wa[q] = 0x7fffffff;
+            }
+        if (lane == 0) claim[g * P24_TOPK + r] = win.i;
+    }
+    return take;
+}
+
 // Anchor claimed by several GTs none of which is valid for it (every claim came from a spill): argmin of the
 // PENALISED cost over all GTs (losses.py:471-476), first index on ties.  One warp, rare.
-__device__ __noinline__ int resolve_conflict(const Params& p, const float* recs, int n, const float* row, int a) {
+__device__ __noinline__ int resolve_conflict(const Params& p, const float* recs, int n, const float* row) {
     const float eo1 = 1.0f + expf(-row[26]);
     const float neg = warp_cls_neg_sum(row + 27, p.nc, eo1);
     const float obj_sig = 1.0f / eo1;
@@ -1569,7 +1221,6 @@ __device__ __noinline__ int resolve_conflict(const Params& p, const float* recs,
             best.i = g;
         }
     }
-    (void)a;
     return best.i != 0x7fffffff ? best.i : 0;
 }
 
@@ -1586,9 +1237,10 @@ __device__ __forceinline__ int valid_argmin(const Params& p, int b, int n, int a
     KV best = {P24_POS_INF, 0x7fffffff};
     for (int g = lane; g < n; g += 32) {
         const float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
-        const int sx = ix - __float_as_int(tab[P24_WT_HDR + 2 * l]), sy = iy - __float_as_int(tab[P24_WT_HDR + 2 * l + 1]);
+        const int sx = ix - __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l));
+        const int sy = iy - __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l + 1));
         if (sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE) {
-            const float c = tab[l * P24_WSLOTS + sy * P24_WSIDE + sx];
+            const float c = __ldcg(tab + l * P24_WSLOTS + sy * P24_WSIDE + sx);
             if (c < P24_POS_INF && kv_lt(c, g, best.v, best.i)) {
                 best.v = c;
                 best.i = g;
@@ -1599,171 +1251,274 @@ __device__ __forceinline__ int valid_argmin(const Params& p, int b, int n, int a
     return best.i != 0x7fffffff ? best.i : -1;
 }
 
-#define MBOX_SLOT 64  // floats per (epoch half, rank) slot of a mailbox: 28 sums, flag at [32]
-#define FIX_SCALE 68719476736.0  // 2^36: fixed-point unit of the loss accumulators (order-independent sums)
-#define RESOLVE_GRID_X 32
-
-__device__ __forceinline__ long long to_fix(double x) { return __double2ll_rn(x * FIX_SCALE); }
-
-__global__ void __launch_bounds__(P24_THREADS, 3) k_resolve_loss(const __grid_constant__ Params p) {
-    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 0);
-    pdl_trigger();  // the next step's k_gt_prep may become resident (it waits for this grid's completion)
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(const __grid_constant__ Params p) {
+    extern __shared__ float4 t_dyn4[];  // recs [Lmax * GT_REC] floats | claim [Lmax * 10] | uniq [Lmax * 10] | kreq, ntake [Lmax]
+    __shared__ TailShared S;
+    pdl_trigger();  // the next step's k_prep may become resident (it waits for this grid's completion)
     pdl_wait();
-    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 1);
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    float* s_rec = reinterpret_cast<float*>(t_dyn4);
+    int* claim = reinterpret_cast<int*>(s_rec + p.Lmax * GT_REC);
+    int* uniq = claim + p.Lmax * P24_TOPK;
+    int* kreq = uniq + p.Lmax * P24_TOPK;   // per GT: >= 0 clamped dynamic k a rare path must still honour, -1 none, -2 brute force
+    int* ntake = kreq + p.Lmax;             // per GT: valid pairs already claimed
     const int n = p.num_gt[b];
-    __shared__ long long s_acc[P24_WARPS][26];
-    __shared__ float s_sums[28];
-    __shared__ bool s_last;
-
+    const int ncand = p.ncand[b];
+    const int kc = min(P24_TOPK, ncand);  // losses.py:452
     const float* img = p.outputs + (long long)b * p.img_stride;
-    const float* recs = p.gt_rec + (long long)b * p.Lmax * GT_REC;
-    const int nclaim = min(p.nclaimed[b], P24_TOPK * p.Lmax);
-    if (blockIdx.x == 0 && tid == 0) p.num_fg[b] = nclaim;  // every claimed anchor ends up foreground (losses.py:479)
+    const bool no_filter = (p.flags & P24_F_NO_FILTER) != 0;
 
-    // ---- one warp per claimed anchor: conflict resolution, outputs, loss terms (lanes over rays / classes).
-    // Contributions are accumulated as 2^-36 fixed-point integers: the sums do not depend on the list order. ------
+    {
+        const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
+        for (int i = tid; i < n * (GT_REC / 4); i += TAIL_THREADS) t_dyn4[i] = __ldcg(gsrc + i);
+    }
+    for (int i = tid; i < n * P24_TOPK; i += TAIL_THREADS) claim[i] = -1;
+    if (tid == 0) {
+        S.nuniq = 0;
+        S.nbrute = 0;
+        S.nspill = 0;
+        S.lmax = 0;
+    }
+    __syncthreads();
+
+    // ---- phase 1, one warp per GT: dynamic k from the GT's list, then the k cheapest valid pairs -> claims --------
+    for (int g = warp; g < n; g += TAIL_WARPS) {
+        const int slot = b * p.Lmax + g;
+        const int lc = __ldcg(&p.lcount[slot]);
+        if (lane == 0) {
+            p.lcount[slot] = 0;  // ready for the next call
+            if (lc > S.lmax) atomicMax(&S.lmax, lc);
+        }
+        int k = -1;
+        if (!no_filter && lc <= P24_LISTCAP && lc >= kc) {
+            // the list holds every candidate value >= T and at least the 10 seeds: its kc largest are the image's
+            const float* lst = p.list + (long long)slot * P24_LISTCAP;
+            float t[P24_TOPK];
+#pragma unroll
+            for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;
+            for (int i = lane; i < lc; i += 32) top_insert_desc(t, __ldcg(lst + i));
+            float ksum = 0.0f;
+#pragma unroll 1
+            for (int r = 0; r < kc; ++r) {
+                const KV best = warp_select<true>(KV{t[0], t[0] > P24_NEG_INF ? lane : 0x7fffffff});
+                if (lane == best.i) {
+#pragma unroll
+                    for (int q = 0; q < P24_TOPK - 1; ++q) t[q] = t[q + 1];
+                    t[P24_TOPK - 1] = P24_NEG_INF;
+                }
+                ksum = ksum + (best.v == P24_POS_INF ? NAN : best.v);  // descending order, like torch.topk(...).sum()
+            }
+            k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
+            if (k < 1) k = 1;
+        }
+        if (k < 0) {
+            if (lane == 0) {
+                kreq[g] = -2;  // brute force
+                atomicAdd(&S.nbrute, 1);
+            }
+            continue;
+        }
+        const int kk = min(k, ncand);  // torch.topk would raise beyond the candidate count; clamp instead
+        const int take = warp_select_claims(p, b, g, kk, claim);
+        if (lane == 0) {
+            p.dyn_k[slot] = kk;
+            ntake[g] = take;
+            kreq[g] = take < kk ? kk : -1;
+            if (take < kk) atomicAdd(&S.nspill, 1);
+        }
+    }
+    for (int g = n + tid; g < p.Lmax; g += TAIL_THREADS) p.dyn_k[b * p.Lmax + g] = 0;
+    __syncthreads();
+    // ---- rare paths, whole CTA, one GT at a time ---------------------------------------------------------------------
+    if (S.nbrute > 0) {
+        for (int g = 0; g < n; ++g) {
+            if (kreq[g] != -2) continue;
+            const float ksum = topk_sum_bruteforce(p, S, s_rec + g * GT_REC, b, kc);
+            int k = (int)ksum;
+            if (k < 1) k = 1;
+            const int kk = min(k, ncand);
+            __syncthreads();
+            if (warp == 0) {
+                const int take = warp_select_claims(p, b, g, kk, claim);
+                if (lane == 0) {
+                    p.dyn_k[b * p.Lmax + g] = kk;
+                    ntake[g] = take;
+                    kreq[g] = take < kk ? kk : -1;
+                    if (take < kk) S.nspill += 1;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (S.nspill > 0) {
+        for (int g = 0; g < n; ++g) {
+            const int kk = kreq[g];
+            if (kk < 0) continue;
+            spill_claims(p, S, s_rec + g * GT_REC, b, g, kk - ntake[g], claim + g * P24_TOPK, ntake[g]);
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        if (S.nbrute) atomicAdd(&p.status[ST_BRUTE], S.nbrute);
+        if (S.nspill) atomicAdd(&p.status[ST_SPILL], S.nspill);
+        atomicMax(&p.status[ST_LISTMAX], S.lmax);
+        p.seed_done[b] = 0;  // ready for the next call
+        p.ncand[b] = 0;
+    }
+    // ---- phase 2: the distinct claimed anchors (first claim of every anchor) and whether several GTs claim them ------
+    const int nslots = n * P24_TOPK;
+    for (int t = tid; t < nslots; t += TAIL_THREADS) {
+        const int a = claim[t];
+        if (a < 0) continue;
+        bool first = true, multi = false;
+        for (int j = 0; j < nslots; ++j) {
+            if (j != t && claim[j] == a) {
+                multi = true;
+                if (j < t) first = false;
+            }
+        }
+        if (first) uniq[atomicAdd(&S.nuniq, 1)] = t | (multi ? 0x40000000 : 0);
+    }
+    __syncthreads();
+    const int nuniq = S.nuniq;
+    if (tid == 0) p.num_fg[b] = nuniq;  // every claimed anchor ends up foreground (losses.py:479)
+
+    // ---- phase 3, one warp per claimed anchor: conflict resolution, outputs, loss terms (lanes over rays / classes).
+    // Contributions are accumulated as fixed-point integers: the sums do not depend on the order. -----------------------
     long long acc = 0;  // lane k < 24: sum of loss24[:, k]; lane 24: -sum of obj logits at fg; lane 25: cls BCE
-    for (int e = blockIdx.x * P24_WARPS + warp; e < nclaim; e += gridDim.x * P24_WARPS) {
-        const int aa = p.claimed[(long long)b * P24_TOPK * p.Lmax + e];
-        const long long o = (long long)b * p.A + aa;
+    for (int e = warp; e < nuniq; e += TAIL_WARPS) {
+        const int u = uniq[e];
+        const int t = u & 0x3FFFFFFF;
+        const int aa = claim[t];
+        int g = t / P24_TOPK;
         const float* row = img + (long long)aa * p.row_stride;
-        const int cnt = p.claim_cnt[o];
-        int g = p.claim_gt[o];
-        if (cnt > 1) {
+        if (u & 0x40000000) {
             // claimed by several GTs: argmin of the cost over ALL GTs (losses.py:471-476).  Valid pairs always beat
             // penalised ones and their costs are in the GTs' window tables; without any valid pair (every claim came
             // from a spill) the penalised costs are evaluated here
             const int gv = valid_argmin(p, b, n, aa);
-            g = gv >= 0 ? gv : resolve_conflict(p, recs, n, row, aa);
+            g = gv >= 0 ? gv : resolve_conflict(p, s_rec, n, row);
         }
-        const float* rec = recs + g * GT_REC;
+        const float* rec = s_rec + g * GT_REC;
         float l;
         const float v = warp_pair_value(rec, row, l);  // pair value == pred_ious_this_matching (losses.py:491)
         if (lane == 0) {
+            const long long o = (long long)b * p.A + aa;
             p.fg_mask[o] = 1;
             p.matched_gt[o] = g;
             p.pred_iou[o] = v;
         }
         double contrib = (double)l;
+        long long fx = 0;
         if (p.sums28) {
             // sum_j BCEWithLogits(x_j, t_j), t = v at the GT class and 0 elsewhere (losses.py:246-248, 298-302):
-            // sum_j softplus(x_j) - x_c * v, the softplus sum in product form (one log per anchor)
+            // sum_j softplus(x_j) - x_c * v; the softplus sum as the log of a per-lane product (one log per lane;
+            // the product of a lane's factors is restarted before it can overflow)
             const int c = gt_class(rec, p.nc);
             float prod = 1.0f, big = 0.0f;
             for (int j = lane; j < p.nc; j += 32) {
                 const float x = row[27 + j];
-                if (x < 8.0f) prod *= 1.0f + __expf(x);
-                else big += x + log1pf(expf(-x));
+                if (x < 8.0f) {
+                    prod *= 1.0f + __expf(x);
+                    if (prod > 1.0e30f) {
+                        big += logf(prod);
+                        prod = 1.0f;
+                    }
+                } else {
+                    big += x + log1pf(expf(-x));
+                }
             }
-            prod = warp_prod(prod);
+            big += logf(prod);
             big = warp_sum(big);
-            if (lane == 24) contrib = -(double)row[26];
-            if (lane == 25) contrib = ((double)logf(prod) + (double)big) - (double)row[27 + c] * (double)v;
+            if (lane == 24) fx = __double2ll_rn(-(double)row[26] * FIX_SCALE_OBJ);
+            if (lane == 25) contrib = (double)big - (double)row[27 + c] * (double)v;
         }
-        if (lane < 26) acc += to_fix(contrib);
+        if (lane < 24 || lane == 25) fx = to_fix(contrib);
+        if (lane < 26) acc += fx;
     }
-    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 4);
-    if (lane < 26) s_acc[warp][lane] = acc;
+    if (lane < 26) S.acc[warp][lane] = acc;
     __syncthreads();
     if (tid < 26 && p.sums28) {
         long long t = 0;
 #pragma unroll
-        for (int w = 0; w < P24_WARPS; ++w) t += s_acc[w][tid];
-        if (t != 0) atomicAdd((unsigned long long*)&p.acc_fix[b * 28 + tid], (unsigned long long)t);
+        for (int w = 0; w < TAIL_WARPS; ++w) t += S.acc[w][tid];
+        if (t != 0) atomicAdd((unsigned long long*)&p.acc_fix[tid], (unsigned long long)t);
+    } else if (tid == 26 && p.sums28) {
+        atomicAdd((unsigned long long*)&p.acc_fix[26], (unsigned long long)nuniq);
+    } else if (tid == 27 && p.sums28) {
+        atomicAdd((unsigned long long*)&p.acc_fix[27], (unsigned long long)n);
     }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        // two-level completion count (image, then batch): few atomics per address
-        bool last = false;
-        const unsigned done = atomicAdd(&p.ticket[1 + b], 1u);
-        if (done == (unsigned)gridDim.x - 1u) {
-            p.ticket[1 + b] = 0u;  // ready for the next call
-            __threadfence();
-            const unsigned done2 = atomicAdd(&p.ticket[0], 1u);
-            last = (done2 == (unsigned)p.B - 1u);
-        }
-        s_last = last;
+        const unsigned done = atomicAdd(&p.ticket[TK_TAIL], 1u);
+        S.last = (done == (unsigned)p.B - 1u) ? 1 : 0;
     }
     __syncthreads();
-    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 5);
-    if (!s_last) return;
+    if (!S.last) return;
     __threadfence();
-    if (!p.sums28) {  // assignment only (get_assignments): nothing to reduce, but the tickets must be reset
-        if (tid == 0) {
-            p.ticket[0] = 0u;
-            p.ticket[1 + p.B] = 0u;
-            p.ticket[2 + p.B] = 0u;
-        }
-        return;
+    // ---- last CTA: the batch sums (integer adds: exact, order independent), then finalize or publish ----------------
+    if (tid < 28) {
+        const long long t = __ldcg(&p.acc_fix[tid]);
+        p.acc_fix[tid] = 0;  // ready for the next call
+        S.sums[tid] = tid < 26 ? (float)((double)t / (tid == 24 ? FIX_SCALE_OBJ : FIX_SCALE)) : (float)t;
     }
-    // ---- last CTA: batch sums (integer adds over the images: exact), the all-anchor objectness term in a fixed
-    // order, then the optional finalize ------------------------------------------------------------------------------
-    if (tid < 26) {
-        long long t = 0;
-        for (int i = 0; i < p.B; ++i) {
-            t += __ldcg(&p.acc_fix[i * 28 + tid]);
-            p.acc_fix[i * 28 + tid] = 0;  // ready for the next call
-        }
-        s_sums[tid] = (float)((double)t / FIX_SCALE);
-    } else if (tid == 26 || tid == 27) {
-        int t = 0;
-        const int32_t* src = (tid == 26) ? p.nclaimed : p.num_gt;
-        for (int i = 0; i < p.B; ++i) t += min(__ldcg(src + i), tid == 26 ? P24_TOPK * p.Lmax : 0x7fffffff);
-        s_sums[tid] = (float)t;
-    }
-    double objsum = 0.0;
-    if (warp == 1) {
-        const int nblk = p.B * p.tiles;
-        for (int i = lane; i < nblk; i += 32) objsum += __ldcg(p.obj_part + i);
-        objsum = warp_sum_d(objsum);
+    if (tid == 32) {
+        p.ticket[TK_ITEM] = 0u;  // ready for the next call
+        p.ticket[TK_LEFF] = 0u;
+        p.ticket[TK_TAIL] = 0u;
+        p.ticket[TK_SEED] = 0u;
     }
     __syncthreads();
-    if (tid == 32) s_sums[24] = (float)((double)s_sums[24] + objsum);
-    __syncthreads();
+    if (!p.sums28) return;
     if (p.nranks > 1) {
-        // ---- all-reduce of the 28 sums over peer memory: my sums into everybody's mailbox, a flag behind them, then the
-        // contributions of all ranks from my own mailbox, added in rank order (the same bits on every rank).  Two
-        // mailbox halves alternate with the epoch: a rank cannot run two epochs ahead of a peer, so a half is never
-        // overwritten before everybody has read it.
+        // ---- fused all-reduce, publish side: my 28 sums into everybody's mailbox (P2P stores over NVLink), a flag with the
+        // call's epoch behind them.  Two mailbox halves alternate with the epoch.  k_fin collects. ----------------------
         const unsigned ep = p.epoch;
         const int half = (int)(ep & 1u) * P24_MAX_RANKS;
-        for (int q = warp; q < p.nranks; q += P24_WARPS)
-            if (lane < 28) p.mbox[q][(half + p.rank) * MBOX_SLOT + lane] = s_sums[lane];
+        for (int q = warp; q < p.nranks; q += TAIL_WARPS)
+            if (lane < 28) p.mbox[q][(half + p.rank) * MBOX_SLOT + lane] = S.sums[lane];
         __threadfence_system();
         __syncthreads();
         if (tid < p.nranks) {
             __threadfence_system();
             *reinterpret_cast<volatile unsigned*>(p.mbox[tid] + (half + p.rank) * MBOX_SLOT + 32) = ep;
-            volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.mbox[p.rank] + (half + tid) * MBOX_SLOT + 32);
-            const long long t0 = clock64();
-            while (*f != ep) {
-                if (clock64() - t0 > 400000000LL) {  // ~0.2 s: a peer is gone; do not hang the GPU
-                    atomicOr(p.err_flag, 4);
-                    break;
-                }
-            }
-            __threadfence_system();
         }
-        __syncthreads();
-        if (tid < 28) {
-            float t = 0.0f;
-            for (int r = 0; r < p.nranks; ++r)
-                t += *reinterpret_cast<volatile float*>(p.mbox[p.rank] + (half + r) * MBOX_SLOT + tid);
-            s_sums[tid] = t;
-        }
-        __syncthreads();
+        return;
     }
-    if (tid < 28) p.sums28[tid] = s_sums[tid];
-    if (tid == 0) {
-        p.ticket[0] = 0u;  // ready for the next call
-        p.ticket[1 + p.B] = 0u;
-        p.ticket[2 + p.B] = 0u;
+    if (tid < 28) p.sums28[tid] = S.sums[tid];
+    if (p.state26 && warp == 0) finalize_warp(S.sums, p.state26, p.result54, p.weights27);
+}
+
+// k_fin (several GPUs): collect side of the fused all-reduce.  One warp: wait for the flag of every rank in my own
+// mailbox, add the contributions in rank order (the same bits on every rank), finalize.  It spins without a time-out,
+// like a NCCL kernel: a wrong loss is worse than a hang that the framework's watchdog reports.  The wait is measured
+// (status word) so that rank skew can be told from link latency.
+__global__ void __launch_bounds__(32) k_fin(const __grid_constant__ Params p) {
+    pdl_trigger();
+    pdl_wait();  // k_tail of this step is complete: my own contribution is in my mailbox
+    const int lane = threadIdx.x;
+    __shared__ float s_sums[28];
+    const unsigned ep = p.epoch;
+    const int half = (int)(ep & 1u) * P24_MAX_RANKS;
+    const long long t0 = clock64();
+    if (lane < p.nranks) {
+        volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.mbox[p.rank] + (half + lane) * MBOX_SLOT + 32);
+        while (*f != ep) __nanosleep(32);
+        __threadfence_system();
     }
-    if (p.state26 && warp == 0) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
-    TMARK(2, blockIdx.y * gridDim.x + blockIdx.x, 6);
+    __syncwarp();
+    if (lane == 0) p.status[ST_WAITCYC] = (int)min((long long)0x7fffffff, clock64() - t0);
+    if (lane < 28) {
+        float t = 0.0f;
+        for (int r = 0; r < p.nranks; ++r)
+            t += *reinterpret_cast<volatile float*>(p.mbox[p.rank] + (half + r) * MBOX_SLOT + lane);
+        s_sums[lane] = t;
+        p.sums28[lane] = t;
+    }
+    __syncwarp();
+    if (p.state26) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
 }
 
 __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__ state26, float* __restrict__ result54,
@@ -1771,10 +1526,13 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
     finalize_warp(sums28, state26, result54, weights_n27);
 }
 
-size_t anchor_pass_smem(int Lmax) { return (size_t)Lmax * GT_REC_HEAD * sizeof(float); }
-
-inline void prof_mark(int i, cudaStream_t st) { p24::prof_mark(i, st); }
-#define g_prof_on (p24::prof_on())
+size_t pass_smem(int Lmax) {
+    const size_t rec = (size_t)Lmax * GT_REC * sizeof(float);
+    return rec > sizeof(SeedShared) ? rec : sizeof(SeedShared);
+}
+size_t tail_smem(int Lmax) {
+    return (size_t)Lmax * GT_REC * sizeof(float) + (size_t)Lmax * (2 * P24_TOPK + 2) * sizeof(int);
+}
 
 template <typename K>
 cudaError_t launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Params& p) {
@@ -1806,6 +1564,15 @@ extern "C" int p24_workspace_init(void* workspace, size_t workspace_bytes, void*
     return (int)cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream);
 }
 
+extern "C" int p24_read_status(const void* workspace, int B, int A, int Lmax, int32_t* h_status8, void* stream) {
+    if (!workspace || !h_status8 || B <= 0 || A <= 0 || Lmax <= 0) return P24_E_BADARG;
+    const P24Workspace L = p24_layout(B, A, Lmax);
+    cudaError_t e = cudaMemcpyAsync(h_status8, (const char*)workspace + L.status, ST_WORDS * sizeof(int),
+                                    cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}
+
 extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A,
                                      int num_classes, const float* labels, int64_t lab_img_stride,
                                      int64_t lab_row_stride, int Lmax, const float* x_shifts, const float* y_shifts,
@@ -1824,8 +1591,8 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     const P24Workspace L = p24_layout(B, A, Lmax);
     if (workspace_bytes < L.total) return P24_E_WORKSPACE;
     if (((uintptr_t)workspace & 255) != 0) return P24_E_BADARG;
-    const size_t dyn = anchor_pass_smem(Lmax);
-    if (dyn > 160 * 1024 || p24_tiles(A) > MAX_TILES) return P24_E_UNSUPPORTED;
+    const size_t dyn_pass = pass_smem(Lmax), dyn_tail = tail_smem(Lmax);
+    if (dyn_pass > 160 * 1024 || dyn_tail > 200 * 1024 || p24_tiles(A) > 65535) return P24_E_UNSUPPORTED;
     char* ws = (char*)workspace;
     Params p;
     p.outputs = outputs; p.img_stride = img_stride; p.row_stride = row_stride;
@@ -1835,21 +1602,16 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.fg_mask = fg_mask; p.matched_gt = matched_gt; p.pred_iou = pred_iou;
     p.num_fg = num_fg; p.num_gt = num_gt; p.dyn_k = dyn_k; p.sums28 = sums28;
     p.state26 = state26; p.result54 = result54; p.weights27 = weights_n27;
-    p.gt_rec = (float*)(ws + L.gt_rec);
-    p.clist = (float4*)(ws + L.clist);
-    p.sval = (float*)(ws + L.sval);
-    p.wtab = (float*)(ws + L.wtab);
-    p.tbox = (float*)(ws + L.tbox);
-    p.seg = (float*)(ws + L.seg);
-    p.ccount = (int*)(ws + L.ccount);
-    p.claim_cnt = (int*)(ws + L.claim_cnt);
-    p.claim_gt = (int*)(ws + L.claim_gt);
-    p.obj_part = (double*)(ws + L.obj_part);
-    p.claimed = (int*)(ws + L.claimed);
-    p.nclaimed = (int*)(ws + L.nclaimed);
-    p.acc_fix = (long long*)(ws + L.acc_fix);
     p.ticket = (unsigned*)(ws + L.ticket);
-    p.err_flag = (int*)(ws + L.err_flag);
+    p.acc_fix = (long long*)(ws + L.acc_fix);
+    p.status = (int*)(ws + L.status);
+    p.seed_done = (int*)(ws + L.seed_done);
+    p.ncand = (int*)(ws + L.ncand);
+    p.lcount = (int*)(ws + L.lcount);
+    p.gt_rec = (float*)(ws + L.gt_rec);
+    p.wtab = (float*)(ws + L.wtab);
+    p.list = (float*)(ws + L.list);
+    p.cbits = (unsigned*)(ws + L.cbits);
     p.flags = flags;
     p.rank = 0; p.nranks = 1; p.epoch = 0;
     for (int r = 0; r < P24_MAX_RANKS; ++r) p.mbox[r] = nullptr;
@@ -1878,30 +1640,36 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
         if (next != A) return P24_E_BADARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-
-    if (p24::dev_once(1u << 0)) cudaFuncSetAttribute(k_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    const bool pdl = !(flags & P24_F_NO_PDL) && !g_prof_on;
+    if (p24::dev_once(1u << 0)) {  // per device: a process may drive several GPUs
+        cudaFuncSetAttribute(k_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }
+    const bool pdl = !(flags & P24_F_NO_PDL) && !p24::prof_on();
     cudaError_t e = cudaSuccess;
     const int n_sm = p24::dev_info().n_sm;
-    prof_mark(0, st);
-    e = launch(k_gt_prep, dim3(B), dim3(PREP_THREADS), 0, st, pdl, p);
+    p24::prof_mark(0, st);
+    e = launch(k_prep, dim3(B), dim3(PREP_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
+    p24::prof_mark(1, st);
     {
+        // one wave of persistent CTAs: the seed items are waited for inside the kernel, so every CTA must be resident
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass, P24_THREADS, dyn_pass);
+        if (e != cudaSuccess) return (int)e;
+        if (per_sm < 1) return P24_E_UNSUPPORTED;
         const long long items = (long long)B * p.tiles + (long long)B * Lmax * n_levels;
-        const long long cap = 4LL * n_sm;  // one wave of persistent CTAs (5 per SM at 48 registers measured slower)
-        e = launch(k_pass, dim3((unsigned)(items < cap ? items : cap)), dim3(P24_THREADS), dyn, st, pdl, p);
+        const long long cap = (long long)per_sm * n_sm;
+        e = launch(k_pass, dim3((unsigned)(items < cap ? items : cap)), dim3(P24_THREADS), dyn_pass, st, pdl, p);
         if (e != cudaSuccess) return (int)e;
     }
-    prof_mark(1, st);
-    e = launch(k_match, dim3(B, Lmax), dim3(MATCH_THREADS), 0, st, pdl, p);
+    p24::prof_mark(2, st);
+    e = launch(k_tail, dim3(B), dim3(TAIL_THREADS), dyn_tail, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
-    prof_mark(2, st);
-    {
-        const int gx = (P24_TOPK * Lmax + P24_WARPS - 1) / P24_WARPS;
-        e = launch(k_resolve_loss, dim3(gx < RESOLVE_GRID_X ? gx : RESOLVE_GRID_X, B), dim3(P24_THREADS), 0, st, pdl, p);
+    if (p.nranks > 1) {
+        e = launch(k_fin, dim3(1), dim3(32), 0, st, pdl, p);
         if (e != cudaSuccess) return (int)e;
     }
-    prof_mark(3, st);
+    p24::prof_mark(3, st);
     return (int)cudaGetLastError();
 }
 
@@ -1939,9 +1707,3 @@ extern "C" int p24_loss_finalize(const float* sums28, float* state26, float* res
     k_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(sums28, state26, result54, weights_n27);
     return (int)cudaGetLastError();
 }
-
-#ifdef P24_TIMING
-extern "C" int p24_debug_read_timers(unsigned long long* h_out) {
-    return (int)cudaMemcpyFromSymbol(h_out, g_tstamp, sizeof(unsigned long long) * 6 * 4096 * 20);
-}
-#endif

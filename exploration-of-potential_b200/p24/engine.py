@@ -15,7 +15,7 @@ import torch
 from . import lib as _lib
 
 F_NO_PRUNE = 1   # evaluate every polygon angle sum exactly (self-check of the geometric pruning)
-F_NO_FILTER = 2  # evaluate every pair value exactly (self-check of the top-10 bound filter)
+F_NO_FILTER = 2  # dynamic k from the exact value of every (GT, candidate) pair (self-check of the far-pair filter)
 F_ALL_ROWS = 4   # every label row is a GT (per-image API)
 F_NO_PDL = 8     # plain stream-ordered launches
 
@@ -79,7 +79,9 @@ class GridCache:
     def get(self, x_shifts, y_shifts, strides, device):
         if torch.is_tensor(x_shifts):
             x_shifts, y_shifts, strides = [x_shifts], [y_shifts], [strides]
-        key = tuple([(t.data_ptr(), t.numel(), t._version) for lst in (x_shifts, y_shifts, strides) for t in lst])
+        # shapes are part of the key: a grid re-created for another H x W with the same numel usually gets the same address
+        key = tuple([(t.data_ptr(), tuple(t.shape), t._version, str(t.device)) for lst in (x_shifts, y_shifts, strides)
+                     for t in lst])
         if key != self._key:
             cat = [torch.cat([t.reshape(1, -1) for t in lst], 1).reshape(-1).to(device=device, dtype=torch.float32)
                    .contiguous() for lst in (x_shifts, y_shifts, strides)]
@@ -175,6 +177,20 @@ class SimOTAEngine:
             with torch.cuda.device(dev):
                 code = lib.p24_simota_loss_batch(*args)
         _lib.check(code, "p24_simota_loss_batch")
+        return out
+
+    def read_status(self):
+        """Sticky status words of every workspace this engine has used (one small D2H copy + stream sync each):
+        list of (key, [err_bits, n_brute, n_spill, list_max, exchange_wait_cycles, 0, 0, 0])."""
+        lib = _lib.load()
+        out = []
+        for key, buf in self._bufs.items():
+            B, A, Lmax, dev = key
+            dev = torch.device(dev)
+            st = (C.c_int32 * 8)()
+            with torch.cuda.device(dev):
+                _lib.check(lib.p24_read_status(buf["ptr"], B, A, Lmax, st, _stream_ptr(dev)), "p24_read_status")
+            out.append((key, list(st)))
         return out
 
     def finalize(self, sums28: torch.Tensor, state26: torch.Tensor, result54: torch.Tensor | None = None,

@@ -12,7 +12,7 @@ import os
 from . import build as _build
 
 _LIB = None
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_f32p = C.c_void_p  # device pointers travel as integers
 c_ptr = C.c_void_p
@@ -51,6 +51,7 @@ _PROTOS = {
     "p24_postprocess": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int,
                                   c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "p24_read_status": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), c_ptr]),
     "p24_profile_enable": (C.c_int, [C.c_int]),
     "p24_profile_read": (C.c_int, [C.POINTER(C.c_float)]),
 }
@@ -71,9 +72,12 @@ def load(path: str | None = None):
             try:
                 if not _build.is_fresh():
                     _build.build()
-            except Exception:
+            except Exception as exc:
                 if not os.path.exists(path):
                     raise
+                import warnings
+                warnings.warn(f"p24: rebuilding libp24_b200.so failed ({exc}); loading the existing {path}, which does "
+                              "not match the current sources", RuntimeWarning)
     if not os.path.exists(path):
         raise P24Error(f"{path} not found: build it with `python -m p24.build` (no CPU fallback exists)")
     lib = C.CDLL(path)

@@ -201,19 +201,31 @@ class Loss_Function(nn.Module):
 
     # -- bookkeeping of the asynchronous path ---------------------------------------------------------------
     def wait_results(self):
-        """Order everything ``forward_async`` has enqueued before later work of the current stream."""
+        """Order everything ``forward_async`` has enqueued before later work of the current stream (the kernels of
+        this path all run on the caller's stream: nothing to do; kept as the one place that would change)."""
         return None
 
     def check_errors(self):
-        """Raise ``P24Error`` when a kernel reported an internal error (list overflow, peer time-out).  One host
-        read of a 4-byte flag: ``forward`` calls it with its own result read, ``forward_async`` does not."""
-        return None
+        """Raise ``P24Error`` when a kernel reported an internal error (sticky bits in the workspace: window-list
+        overflow, peer time-out).  Costs one small D2H copy and a stream synchronisation per workspace: ``forward``
+        does it together with its own result read, ``forward_async`` leaves it to the caller."""
+        for key, st in self._engine.read_status():
+            if st[0]:
+                raise _lib.P24Error(f"p24 kernels reported error bits {st[0]:#x} on workspace {key} "
+                                    "(1: window list overflow, 4: peer time-out in the fused all-reduce)")
 
     def exchange_wait_us(self):
-        return [0.0]
+        """[microseconds] the last fused all-reduce of this rank waited for its peers (0 on one GPU): rank skew shows
+        up here, link latency does not.  clock64 cycles at the nominal 1965 MHz."""
+        w = [st[4] for _, st in self._engine.read_status()]
+        return [max(w) / 1965.0 if w else 0.0]
 
     def path_stats(self):
-        return None
+        """Counts of the rare paths since the workspaces were created: GTs whose dynamic k needed the brute-force
+        evaluation, GTs that spilled into the penalised regime, the longest top-10 candidate list."""
+        st = [s for _, s in self._engine.read_status()]
+        return {"brute_force_gts": sum(s[1] for s in st), "spill_gts": sum(s[2] for s in st),
+                "list_max": max([s[3] for s in st] + [0]), "list_capacity": 2048}
 
     def forward(self, outputs_train, labels):
         outputs = outputs_train[3]
@@ -230,6 +242,7 @@ class Loss_Function(nn.Module):
             draw = [rows[:, 0], rows[:, 1], rows[:, 2:26]]
         draw += [r[28:52], r[52], r[53]]
         ratio = float(r[27].detach())  # one D2H read per step (the reference returns a Python float here)
+        self.check_errors()            # ... and the kernels' error bits with it (the reference raises on its failures)
         return (r[0], r[1:25], r[25], r[26], 0.0, ratio, draw)
 
     # -- per-image API (losses.py:359-442) -----------------------------------------------------------

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define P24_ABI_VERSION 3
+#define P24_ABI_VERSION 4
 #define P24_RAYS 24
 #define P24_TOPK 10        /* n_candidate_k cap, losses.py:452 */
 
@@ -37,7 +37,7 @@ extern "C" {
 
 #define P24_MAX_RANKS 16    /* GPUs of one box that can share the fused all-reduce */
 
-/* p24_assign_batch flags */
+/* p24_simota_loss_batch flags */
 #define P24_F_NO_PRUNE 1u      /* evaluate every polygon angle sum exactly (self-check of the pruning) */
 #define P24_F_NO_FILTER 2u     /* evaluate every pair value exactly (self-check of the top-k filter) */
 #define P24_F_NO_PDL 8u        /* plain stream-ordered launches instead of programmatic dependent launch */
@@ -170,12 +170,23 @@ int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_str
                     int32_t* cand_count, int32_t* det_count, float* det_rows, int32_t* keep_idx, float* rect_debug,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch records CUDA events around its three
- * kernels (k_pass, k_match, k_resolve_loss) on the launching stream and launches them in plain stream order;
- * p24_profile_read waits for the last call and returns the durations in milliseconds into h_ms6[0..2]
- * (h_ms6[3..5] = 0) of a HOST array.  Process-global. */
+/* Sticky status of a workspace, read back to the HOST (one small device-to-host copy + a synchronisation of `stream`):
+ *   h_status8[0]  error bits (P24_ERR_*); 0 = none.  The reference raises on its failures (losses.py:81-82); the Python
+ *                 host side raises P24Error when a bit is set
+ *   h_status8[1]  GTs whose dynamic k took the brute-force path (cumulative over the calls on this workspace)
+ *   h_status8[2]  GTs that spilled into the penalised regime (cumulative)
+ *   h_status8[3]  longest top-10 candidate list seen
+ *   h_status8[4]  clock cycles the last fused all-reduce waited for its peers (nranks > 1) */
+#define P24_ERR_WINDOW_OVERFLOW 1
+#define P24_ERR_PEER_TIMEOUT 4
+int p24_read_status(const void* workspace, int B, int A, int Lmax, int32_t* h_status8, void* stream);
+
+/* Profiling aid (bench.py): when enabled, p24_simota_loss_batch and p24_postprocess record CUDA events around their
+ * kernels on the launching stream and launch them in plain stream order; p24_profile_read waits for the last call and
+ * returns the durations in milliseconds into a HOST array: h_ms8[0..2] = k_prep, k_pass, k_tail (+ k_fin),
+ * h_ms8[4..5] = k_post_filter, k_post_nms; 0 for kernels that did not run since the last read.  Process-global. */
 int p24_profile_enable(int on);
-int p24_profile_read(float* h_ms6);
+int p24_profile_read(float* h_ms8);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_abi_version_error_strings_and_workspace_query():
     lib = p24_lib.load()
-    assert lib.p24_abi_version() == 3
+    assert lib.p24_abi_version() == p24_lib.ABI_VERSION == 4
     assert b"success" in lib.p24_error_string(0)
     assert b"workspace" in lib.p24_error_string(-2)
     n = lib.p24_workspace_bytes(20, 8400, 50)
