@@ -15,7 +15,7 @@
 #define P24_WT_HDR (P24_WSLOTS * P24_MAX_LEVELS)   // wtab row: [slot costs | ix0, iy0 per level (int bits)]
 #define P24_WT_STRIDE (P24_WT_HDR + 2 * P24_MAX_LEVELS + 4)   // 208 floats
 #define P24_WARPS (P24_THREADS / 32)
-#define P24_LISTCAP 2048   // pair values a GT's top-10 list can hold (more -> brute-force path of k_tail)
+#define P24_LISTCAP 1024   // entries a GT's top-10 list can hold (more -> brute-force path of k_tail)
 
 // ---- per-GT record (floats): k_prep writes it, the seed items of k_pass add [4] and [58] ----------------------
 // [0] cx  [1] cy  [2] rin2  [3] rrej2   (one 128-bit shared-memory load for the per-pair tests)
@@ -45,6 +45,8 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 #define ST_SPILL 2      // GTs that spilled into the penalised regime (cumulative)
 #define ST_LISTMAX 3    // longest top-10 list seen
 #define ST_WAITCYC 4    // clock cycles the last fused all-reduce waited for its peers
+#define ST_LISTSUM 5    // list entries seen (cumulative) ...
+#define ST_GTS 6        // ... over this many GTs
 #define ST_WORDS 8
 
 struct P24Workspace {
@@ -57,7 +59,12 @@ struct P24Workspace {
     size_t gt_rec;      // [B, Lmax, GT_REC] float
     size_t wtab;        // [B, Lmax, P24_WT_STRIDE] float  SimOTA cost of the GT's centre-window anchors by window slot
                         //                                  (+inf: not in the window / not in the polygon) + the window origins
-    size_t list;        // [B, Lmax, P24_LISTCAP] float    pair values >= T of the GT's far candidates (arrival order)
+    size_t rare;        // [B] int      GTs of the image that need a rare path of k_tail (zero between calls)
+    size_t list;        // [B, Lmax, P24_LISTCAP] float2   (value bound, anchor | all-apart flag) of the GT's far candidates whose bound
+                        //                                  reaches T (arrival order)
+    size_t claimg;      // [B, Lmax * 10] int   anchors claimed by the GTs (-1: unused slot)
+    size_t kreq;        // [B, Lmax] int
+    size_t ntake;       // [B, Lmax] int
     size_t cbits;       // [B, tiles * 8] unsigned         candidate bitmap (bit l of word w: anchor 32 w + l)
     size_t total;
 };
@@ -75,10 +82,14 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     w.status = off;     off = p24_align(off + ST_WORDS * sizeof(int));
     w.seed_done = off;  off = p24_align(off + (size_t)B * sizeof(int));
     w.ncand = off;      off = p24_align(off + (size_t)B * sizeof(int));
+    w.rare = off;       off = p24_align(off + (size_t)B * sizeof(int));
     w.lcount = off;     off = p24_align(off + BL * sizeof(int));
     w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
     w.wtab = off;       off = p24_align(off + BL * P24_WT_STRIDE * sizeof(float));
-    w.list = off;       off = p24_align(off + BL * P24_LISTCAP * sizeof(float));
+    w.list = off;       off = p24_align(off + BL * P24_LISTCAP * 2 * sizeof(float));
+    w.claimg = off;     off = p24_align(off + BL * P24_TOPK * sizeof(int));
+    w.kreq = off;       off = p24_align(off + BL * sizeof(int));
+    w.ntake = off;      off = p24_align(off + BL * sizeof(int));
     w.cbits = off;      off = p24_align(off + NB * P24_WARPS * sizeof(unsigned));
     w.total = off;
     return w;

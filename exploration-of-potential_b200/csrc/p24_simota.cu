@@ -68,8 +68,12 @@ struct Params {
     int* lcount;
     float* gt_rec;
     float* wtab;
-    float* list;
+    float2* list;
     unsigned* cbits;
+    int* claimg;
+    int* kreq;
+    int* ntake;
+    int* rare;
     unsigned flags;
     float* mbox[P24_MAX_RANKS];  // peer mailboxes of the fused all-reduce (nranks > 1)
     int rank, nranks;
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
     const int n = block_count_labels(p, lab, &s_n);
     if (tid == 0) {
         p.num_gt[b] = n;
+        p.num_fg[b] = 0;  // k_tail adds the foreground anchors of the image's cluster CTAs
         atomicMax(&p.ticket[TK_LEFF], (unsigned)n);  // the batch's largest num_gt: k_pass lays its items out for it
     }
     for (int g = warp; g < n; g += PREP_THREADS / 32)
@@ -326,17 +331,19 @@ __device__ __forceinline__ float warp_bound_Hstar(float rg_lane, float d) {
 // H*(d) < T: the anchor tiles evaluate only the (GT, candidate) pairs beyond it.
 // -------------------------------------------------------------------------------------------
 #define SEED_FAR 3
-#define SEED_VERT 6
-#define SEED_PTS (3 + SEED_VERT)
-#define SEED_MAX (SEED_FAR * P24_MAX_LEVELS * SEED_PTS)   // 108 <= P24_THREADS
+#define SEED_DISC 3                                    // points per (far GT, level): centre, far end of the inscribed disc, 2 strides out
+#define SEED_NV 24                                     // polygon vertices (of any GT of the image) farthest from this GT
+#define SEED_MAX (SEED_FAR * P24_MAX_LEVELS * SEED_DISC + SEED_NV * P24_MAX_LEVELS)   // 132 <= P24_THREADS
 
 struct SeedShared {
     float rec[GT_REC];
     int far[SEED_FAR];
-    int vsel[SEED_FAR][SEED_VERT];
+    int vsel[SEED_NV];        // (GT << 5) | vertex
+    float vkey[P24_THREADS];  // the threads' farthest vertices
+    int vidx[P24_THREADS];
     float val[SEED_MAX];
     int anc[SEED_MAX];
-    int nfar, nseed;
+    int nfar, nvert;
     float T;
 };
 
@@ -390,41 +397,51 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
             }
             if (lane == 0) S.nfar = nf;
         }
-        __syncthreads();
-        const int nfar = S.nfar;
-        // ---- per far GT: its SEED_VERT vertices that look away from this GT the most: warps 0 .. nfar-1 ----------
-        if (warp < nfar) {
-            const float* r = recs + S.far[warp] * GT_REC;
-            float ux = r[GT_CX] - gcx, uy = r[GT_CY] - gcy;
-            if (!(fmaf(ux, ux, uy * uy) > 1e-12f)) {
-                ux = 1.0f;
-                uy = 0.0f;
+        // ---- the SEED_NV polygon vertices of the image that are farthest from this GT's centre (every thread keeps the
+        // farthest of its share, then the block ranks the threads' picks) ----------------------------------------------
+        {
+            float best = P24_NEG_INF;
+            int bi = -1;
+            for (int i = tid; i < n * P24_RAYS; i += P24_THREADS) {
+                const int h = i / P24_RAYS, k = i - h * P24_RAYS;
+                const float* r = recs + h * GT_REC;
+                const float dx = r[GT_VX + k] - gcx, dy = r[GT_VY + k] - gcy;
+                const float d2 = fmaf(dx, dx, dy * dy);
+                if (d2 > best) {
+                    best = d2;
+                    bi = (h << 5) | k;
+                }
             }
-            float proj = P24_NEG_INF;
-            if (lane < P24_RAYS) {
-                proj = fmaf(r[GT_VX + lane] - r[GT_CX], ux, (r[GT_VY + lane] - r[GT_CY]) * uy);
-                if (!(proj == proj)) proj = -3.0e38f;
-            }
-#pragma unroll 1
-            for (int q = 0; q < SEED_VERT; ++q) {
-                const KV best = warp_select<true>(KV{proj, lane});
-                if (lane == 0) S.vsel[warp][q] = best.i < P24_RAYS ? best.i : 0;
-                if (lane == best.i) proj = P24_NEG_INF;
-            }
+            S.vkey[tid] = best;
+            S.vidx[tid] = bi;
         }
         __syncthreads();
-        // ---- one seed point per thread: (far GT, level, point) -> grid cell -> certainly a candidate? -> value ----
-        const int per_h = p.nlev * SEED_PTS;
-        if (tid < nfar * per_h) {
-            const int f = tid / per_h, r0 = tid - f * per_h;
-            const int l = r0 / SEED_PTS, pt = r0 - l * SEED_PTS;
-            const float* h = recs + S.far[f] * GT_REC;
-            const Level lv = p.lev[l];
-            const float st = p.strides[lv.off];
-            const float hcx = h[GT_CX], hcy = h[GT_CY];
-            float qx, qy;
-            if (pt < 3) {
-                float ux = hcx - gcx, uy = hcy - gcy;
+        {
+            const float mykey = S.vkey[tid];
+            const int myidx = S.vidx[tid];
+            if (myidx >= 0) {
+                int rank = 0;
+                for (int j = 0; j < P24_THREADS; ++j) rank += kv_gt(S.vkey[j], j, mykey, tid) ? 1 : 0;
+                if (rank < SEED_NV) S.vsel[rank] = myidx;
+            }
+            if (tid == 0) S.nvert = min(SEED_NV, min(n * P24_RAYS, P24_THREADS));
+        }
+        __syncthreads();
+        const int nfar = S.nfar, nvert = S.nvert;
+        // ---- one seed point per thread -> grid cell -> certainly a candidate? -> value ---------------------------
+        const int n_disc = nfar * p.nlev * SEED_DISC;
+        const int n_pts = n_disc + nvert * p.nlev;
+        if (tid < n_pts) {
+            int hsel, l;
+            float qx, qy, st;
+            if (tid < n_disc) {
+                const int f = tid / (p.nlev * SEED_DISC), r0 = tid - f * (p.nlev * SEED_DISC);
+                l = r0 / SEED_DISC;
+                const int pt = r0 - l * SEED_DISC;
+                hsel = S.far[f];
+                const float* h = recs + hsel * GT_REC;
+                st = p.strides[p.lev[l].off];
+                float ux = h[GT_CX] - gcx, uy = h[GT_CY] - gcy;
                 const float nn = fmaf(ux, ux, uy * uy);
                 if (nn > 1e-12f) {
                     const float inv = rsqrtf(nn);
@@ -435,15 +452,26 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
                     uy = 0.0f;
                 }
                 const float rho = pt == 0 ? 0.0f : (pt == 1 ? fmaxf(0.0f, sqrtf(h[GT_RIN2]) - 0.75f * st) : 2.0f * st);
-                qx = fmaf(ux, rho, hcx);
-                qy = fmaf(uy, rho, hcy);
+                qx = fmaf(ux, rho, h[GT_CX]);
+                qy = fmaf(uy, rho, h[GT_CY]);
             } else {
-                const int k = S.vsel[f][pt - 3];
+                const int r0 = tid - n_disc;
+                const int vi = r0 / p.nlev;
+                l = r0 - vi * p.nlev;
+                const int hv = S.vsel[vi];
+                hsel = hv >> 5;
+                const int k = hv & 31;
+                const float* h = recs + hsel * GT_REC;
+                st = p.strides[p.lev[l].off];
+                // one stride inside the vertex, on the ray from the GT's own centre
                 const float rr = h[GT_RG + k];
                 const float fct = fmaxf(0.0f, __fdividef(rr - st, fmaxf(rr, 1e-6f)));
-                qx = fmaf(h[GT_VX + k] - hcx, fct, hcx);
-                qy = fmaf(h[GT_VY + k] - hcy, fct, hcy);
+                qx = fmaf(h[GT_VX + k] - h[GT_CX], fct, h[GT_CX]);
+                qy = fmaf(h[GT_VY + k] - h[GT_CY], fct, h[GT_CY]);
             }
+            const float* h = recs + hsel * GT_REC;
+            const Level lv = p.lev[l];
+            const float hcx = h[GT_CX], hcy = h[GT_CY];
             const int ix = cell_index(qx, st), iy = cell_index(qy, st);
             if (ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
                 const int a = lv.off + iy * lv.W + ix;
@@ -460,16 +488,16 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
                     // own fp32 comparison) the value has the closed form (1/48) sum_k (2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2),
                     // evaluated in fast arithmetic to within 3e-6; other pairs are evaluated exactly
                     const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
-                    float s = 0.0f;
+                    float sm = 0.0f;
                     bool apart = true;
 #pragma unroll 4
                     for (int k = 0; k < P24_RAYS; ++k) {
                         const float rg = S.rec[GT_RG + k], rp = row[2 + k];
                         apart = apart && (d >= rg + rp) && (rp >= 0.25f);
                         const float t = (rg + rp) + d;
-                        s += 2.0f - __fdividef(4.0f * fmaf(rg, rg, rp * rp), t * t);
+                        sm += 2.0f - __fdividef(4.0f * fmaf(rg, rg, rp * rp), t * t);
                     }
-                    float v = apart ? s * (1.0f / 48.0f) - 1e-5f : pair_value_row(S.rec, row);
+                    float v = apart ? sm * (1.0f / 48.0f) - 1e-5f : pair_value_row(S.rec, row);
                     if (!(v == v)) v = P24_NEG_INF;
                     S.val[tid] = v;
                     S.anc[tid] = a;
@@ -481,18 +509,18 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
         if (tid == 0) S.T = P24_NEG_INF;
         bool mine = false;
         float v = P24_NEG_INF;
-        if (tid < nfar * per_h) {
+        if (tid < n_pts) {
             v = S.val[tid];
             const int a = S.anc[tid];
             mine = a >= 0 && v > P24_NEG_INF;
             for (int j = 0; j < tid && mine; ++j) mine = S.anc[j] != a;  // the first copy of an anchor counts
         }
         __syncthreads();
-        if (tid < nfar * per_h && !mine) S.val[tid] = P24_NEG_INF;
+        if (tid < n_pts && !mine) S.val[tid] = P24_NEG_INF;
         __syncthreads();
         if (mine) {
             int rank = 0;
-            for (int j = 0; j < nfar * per_h; ++j) rank += kv_gt(S.val[j], j, v, tid) ? 1 : 0;
+            for (int j = 0; j < n_pts; ++j) rank += kv_gt(S.val[j], j, v, tid) ? 1 : 0;
             if (rank == P24_TOPK - 1) S.T = v;
         }
         __syncthreads();
@@ -569,26 +597,34 @@ __device__ __forceinline__ void stage_rows(const Params& p, AnchorShared& S, int
     }
 }
 
-// exact pair value of (GT record in shared memory, anchor `al` of the staged tile): one thread
-__device__ __noinline__ float pair_value_staged(const float* __restrict__ rec, const AnchorShared& S, int al) {
+// Pair (GT g, staged anchor al) lies beyond far2.  A cheap upper bound of its value (the "apart" closed form bounds every
+// ray, p24_ray_loss_ub; for a pair whose rays are all apart -- the reference's own fp32 comparison -- it IS the value to
+// within 3e-6); when it reaches T the pair goes to the GT's list as (bound, anchor | all-apart flag): k_tail refines the
+// threshold with the certified lower bounds and evaluates the few pairs that remain exactly.
+__device__ __noinline__ void far_pair(const Params& p, const float* __restrict__ s_rec, const AnchorShared& S, int b, int tile,
+                                      int g, int al) {
+    const float* rec = s_rec + g * GT_REC;
     const int wr = al >> 5, lr = al & 31;
     const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], S.row[wr][0][lr], S.row[wr][1][lr]);
-    float s = 0.0f;
-#pragma unroll 1
-    for (int k = 0; k < P24_RAYS; ++k) s = s + p24_ray_loss(rec[GT_RG + k], S.row[wr][2 + k][lr], d);
-    return (s / 24.0f) / 2.0f;
-}
-
-// pair (GT g, staged anchor al) lies beyond far2: exact value, into the GT's top-10 list when it reaches T
-__device__ __forceinline__ void far_pair(const Params& p, const float* __restrict__ s_rec, const AnchorShared& S, int b,
-                                         int g, int al) {
-    const float* rec = s_rec + g * GT_REC;
-    float v = pair_value_staged(rec, S, al);
-    if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
-    if (v >= rec[GT_T]) {
+    float sm = 0.0f;
+    bool apart = true;
+#pragma unroll 4
+    for (int k = 0; k < P24_RAYS; ++k) {
+        const float rg = rec[GT_RG + k], rp = S.row[wr][2 + k][lr];
+        apart = apart && (d >= rg + rp);
+        sm += p24_ray_loss_ub(rg, rp, d);
+    }
+    float ub = sm * (1.0f / 48.0f) + 2e-5f;
+    if ((S.cand[al] & 2) || !(ub == ub)) {  // tiny predicted radius / NaN: no bound, evaluated exactly by k_tail
+        ub = P24_POS_INF;
+        apart = false;
+    }
+    if (ub >= rec[GT_T]) {
         const int slot = b * p.Lmax + g;
         const int at = atomicAdd(&p.lcount[slot], 1);
-        if (at < P24_LISTCAP) p.list[(long long)slot * P24_LISTCAP + at] = v;
+        if (at < P24_LISTCAP)
+            p.list[(long long)slot * P24_LISTCAP + at] =
+                make_float2(ub, __int_as_float((tile * P24_THREADS + al) | (apart ? (int)0x80000000 : 0)));
     }
 }
 
@@ -726,6 +762,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     const bool cand = active && (n > 0) && (cheap || S.cand[tid]);
     if (tid == 0) S.nitems = 0;
     __syncthreads();
+    S.cand[tid] = (cand ? 1 : 0) | (tiny ? 2 : 0);  // (read by far_pair, after the next barrier)
 
     // ---- the (GT, candidate) pairs beyond far2: exact values into the GTs' top-10 lists (again through a work list) ---
     if (cand && !no_filter) {
@@ -736,13 +773,13 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
                 m &= m - 1;
                 const int slot = atomicAdd(&S.nitems, 1);
                 if (slot < ITEM_CAP) S.items[slot] = (unsigned)tid | ((unsigned)g << 8);
-                else far_pair(p, s_rec, S, b, g, tid);
+                else far_pair(p, s_rec, S, b, tile, g, tid);
             }
         }
         for (int g = 128; g < n; ++g) {  // more than 128 GTs: the rest in place
             const float* rec = s_rec + g * GT_REC;
             const float px = rec[GT_CX] - pcx, py = rec[GT_CY] - pcy;
-            if (tiny || !(fmaf(px, px, py * py) < rec[GT_FAR2])) far_pair(p, s_rec, S, b, g, tid);
+            if (tiny || !(fmaf(px, px, py * py) < rec[GT_FAR2])) far_pair(p, s_rec, S, b, tile, g, tid);
         }
     }
     // ---- per-anchor outputs, candidate bitmap and count, the all-anchor objectness term -------------------------
@@ -766,7 +803,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
         const int nitems = min(S.nitems, ITEM_CAP);
         for (int i = tid; i < nitems; i += P24_THREADS) {
             const unsigned it = S.items[i];
-            far_pair(p, s_rec, S, b, (int)(it >> 8), (int)(it & 0xFF));
+            far_pair(p, s_rec, S, b, tile, (int)(it >> 8), (int)(it & 0xFF));
         }
     }
 }
@@ -961,11 +998,15 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
 }
 
 // -------------------------------------------------------------------------------------------
-// k_tail: one CTA per image
+// k_tail: one thread-block CLUSTER of TAIL_CL CTAs per image (the image's work spreads over TAIL_CL SMs; the phases are
+// separated by the hardware cluster barrier instead of kernel boundaries)
 // -------------------------------------------------------------------------------------------
-#define TAIL_THREADS 1024
+#define TAIL_CL 8
+#define TAIL_THREADS 256
 #define TAIL_WARPS (TAIL_THREADS / 32)
-#define MBOX_SLOT 64  // floats per (epoch half, rank) slot of a mailbox: 28 sums, flag at [32]
+#define TAIL_SURV 64   // survivors a GT warp evaluates per batch
+#define ROW_PAD 108    // floats per staged row (27 + nc <= ROW_PAD is required for staging; else rows are read in place)
+#define MBOX_SLOT 64   // floats per (epoch half, rank) slot of a mailbox: 28 sums, flag at [32]
 
 // normalisation + stateful re-weighting, losses.py:280-345; executed by one warp
 __device__ void finalize_warp(const float* sums28, float* state26, float* result54, float* weights_n27) {
@@ -1024,12 +1065,26 @@ __device__ __forceinline__ float warp_pair_value(const float* __restrict__ rec, 
     return (warp_sum(l) / 24.0f) / 2.0f;
 }
 
+// the same value by an 8-lane group (3 rays per lane, fixed reduction tree); every lane of the group returns it
+__device__ __forceinline__ float group_pair_value(const float* __restrict__ rec, const float* __restrict__ row, unsigned m) {
+    const int sub = threadIdx.x & 7;
+    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
+    float s = 0.0f;
+#pragma unroll 1
+    for (int q = 0; q < 3; ++q) {
+        const int k = sub * 3 + q;
+        s = s + ray_loss(rec[GT_RG + k], row[2 + k], d);
+    }
+    s = group_sum(s, m);
+    return (s / 24.0f) / 2.0f;
+}
+
 struct TailShared {
     long long acc[TAIL_WARPS][26];
     KV kv[TAIL_WARPS];
     float sums[28];
-    int nuniq, nbrute, nspill, last;
-    int lmax;
+    int surv[TAIL_WARPS][TAIL_SURV];
+    int nuniq, last;
 };
 
 template <bool MAX>
@@ -1039,7 +1094,7 @@ __device__ __forceinline__ KV tail_block_select(KV x, KV* s_red) {
     __syncthreads();
     if (lane == 0) s_red[warp] = x;
     __syncthreads();
-    KV y = s_red[lane];  // TAIL_WARPS == 32
+    KV y = s_red[lane < TAIL_WARPS ? lane : 0];
     y = warp_select<MAX>(y);
     return y;
 }
@@ -1056,6 +1111,19 @@ __device__ __forceinline__ void top_insert_desc(float (&t)[P24_TOPK], float v) {
     }
 }
 
+// the `want` (<= 10) largest values held in the lanes' descending lists, popped in descending order by the whole warp:
+// returns the r-th largest in every lane, one call per r
+__device__ __forceinline__ float warp_pop_max(float (&t)[P24_TOPK]) {
+    const int lane = threadIdx.x & 31;
+    const KV best = warp_select<true>(KV{t[0], t[0] > P24_NEG_INF ? lane : 0x7fffffff});
+    if (lane == best.i) {
+#pragma unroll
+        for (int q = 0; q < P24_TOPK - 1; ++q) t[q] = t[q + 1];
+        t[P24_TOPK - 1] = P24_NEG_INF;
+    }
+    return best.i == 0x7fffffff ? P24_NEG_INF : best.v;
+}
+
 // Brute force (list overflow, P24_F_NO_FILTER, or fewer list entries than expected): the exact pair value of EVERY
 // candidate of the image (candidate bitmap), the kc largest summed in descending order.  Whole CTA.
 __device__ __noinline__ float topk_sum_bruteforce(const Params& p, TailShared& S, const float* __restrict__ rec, int b, int kc) {
@@ -1066,7 +1134,7 @@ __device__ __noinline__ float topk_sum_bruteforce(const Params& p, TailShared& S
 #pragma unroll
     for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;
     for (int a = tid; a < p.A; a += TAIL_THREADS) {
-        if (!((bits[a >> 5] >> (a & 31)) & 1u)) continue;
+        if (!((__ldcg(bits + (a >> 5)) >> (a & 31)) & 1u)) continue;
         float v = pair_value_row(rec, img + (long long)a * p.row_stride);
         if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
         top_insert_desc(t, v);
@@ -1087,7 +1155,7 @@ __device__ __noinline__ float topk_sum_bruteforce(const Params& p, TailShared& S
 
 // Spill path (rare: GT with fewer valid anchors than its dynamic k): `need` more anchors with the smallest PENALISED
 // cost among the candidates that are not valid for this GT (losses.py:460-464 on the penalised rows).  Ties -> lower
-// anchor index.  Whole CTA; the new claims go to claim[at..].
+// anchor index.  Whole CTA; the new claims go to claim[at..] (global).
 __device__ __noinline__ void spill_claims(const Params& p, TailShared& S, const float* __restrict__ rec, int b, int g, int need,
                                           int* claim, int at) {
     float lv[P24_TOPK];
@@ -1103,15 +1171,17 @@ __device__ __noinline__ void spill_claims(const Params& p, TailShared& S, const 
     const float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
     const int c = gt_class(rec, p.nc);
     for (int a = tid; a < p.A; a += TAIL_THREADS) {
-        if (!((bits[a >> 5] >> (a & 31)) & 1u)) continue;
+        if (!((__ldcg(bits + (a >> 5)) >> (a & 31)) & 1u)) continue;
         // valid for this GT (in window and in polygon: a finite entry of the window table)?
         int l = 0;
 #pragma unroll
         for (int q = 1; q < P24_MAX_LEVELS; ++q) l += (q < p.nlev && a >= p.lev[q].off) ? 1 : 0;
         const int r = a - p.lev[l].off;
         const int iy = r / p.lev[l].W, ix = r - iy * p.lev[l].W;
-        const int sx = ix - __float_as_int(tab[P24_WT_HDR + 2 * l]), sy = iy - __float_as_int(tab[P24_WT_HDR + 2 * l + 1]);
-        if (sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE && tab[l * P24_WSLOTS + sy * P24_WSIDE + sx] < P24_POS_INF)
+        const int sx = ix - __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l));
+        const int sy = iy - __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l + 1));
+        if (sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE &&
+            __ldcg(tab + l * P24_WSLOTS + sy * P24_WSIDE + sx) < P24_POS_INF)
             continue;
         const float* row = img + (long long)a * p.row_stride;
         const float eo1 = 1.0f + expf(-row[26]);
@@ -1153,8 +1223,9 @@ __device__ __noinline__ void spill_claims(const Params& p, TailShared& S, const 
     }
 }
 
-// The k smallest costs among the GT's valid pairs (window table) -> claim[g * 10 ..] (losses.py:460-464; ties -> lower
-// anchor index).  One warp.  Returns the number of valid pairs taken (< k: the GT must spill).
+// The k smallest costs among the GT's valid pairs (window table) -> claim[0 .. 10) of the GT (global; unused slots -1)
+// (losses.py:460-464; ties -> lower anchor index).  One warp.  Returns the number of valid pairs taken (< k: the GT
+// must spill).
 #define WSL_PER_LANE ((P24_WT_HDR + 31) / 32)   // 7
 __device__ __forceinline__ int warp_select_claims(const Params& p, int b, int g, int k, int* claim) {
     const int lane = threadIdx.x & 31;
@@ -1163,43 +1234,50 @@ __device__ __forceinline__ int warp_select_claims(const Params& p, int b, int g,
     float wc[WSL_PER_LANE];
     int wa[WSL_PER_LANE];
     int nv = 0;
+    // (costs and origins requested together: one round trip)
+    const int org = lane < 2 * P24_MAX_LEVELS ? __float_as_int(__ldcg(tab + P24_WT_HDR + lane)) : 0;
 #pragma unroll
     for (int q = 0; q < WSL_PER_LANE; ++q) {
         const int s = lane + 32 * q;
-        wc[q] = P24_POS_INF;
+        wc[q] = s < nslot ? __ldcg(tab + s) : P24_POS_INF;
+    }
+#pragma unroll
+    for (int q = 0; q < WSL_PER_LANE; ++q) {
+        const int s = lane + 32 * q;
+        const int l = min(s / P24_WSLOTS, P24_MAX_LEVELS - 1), r = s - l * P24_WSLOTS;
+        const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+        const int ox = __shfl_sync(0xffffffffu, org, 2 * l), oy = __shfl_sync(0xffffffffu, org, 2 * l + 1);
         wa[q] = 0x7fffffff;
-        if (s < nslot) {
-            const float c = __ldcg(tab + s);
-            if (c < P24_POS_INF) {
-                const int l = s / P24_WSLOTS, r = s - l * P24_WSLOTS;
-                const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
-                const int ix = __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l)) + sx;
-                const int iy = __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l + 1)) + sy;
-                wc[q] = c;
-                wa[q] = p.lev[l].off + iy * p.lev[l].W + ix;
-                ++nv;
-            }
+        if (wc[q] < P24_POS_INF) {
+            wa[q] = p.lev[l].off + (oy + sy) * p.lev[l].W + (ox + sx);
+            ++nv;
+        } else {
+            wc[q] = P24_POS_INF;  // (NaN cannot occur: window_part stores finite costs or +inf)
         }
     }
     nv = warp_sum_i(nv);
     const int take = min(k, nv);
 #pragma unroll 1
-    for (int r = 0; r < take; ++r) {
-        KV best = {P24_POS_INF, 0x7fffffff};
+    for (int r = 0; r < P24_TOPK; ++r) {
+        int won = -1;
+        if (r < take) {
+            KV best = {P24_POS_INF, 0x7fffffff};
 #pragma unroll
-        for (int q = 0; q < WSL_PER_LANE; ++q)
-            if (kv_lt(wc[q], wa[q], best.v, best.i)) {
-                best.v = wc[q];
-                best.i = wa[q];
-            }
-        const KV win = warp_select<false>(best);
+            for (int q = 0; q < WSL_PER_LANE; ++q)
+                if (kv_lt(wc[q], wa[q], best.v, best.i)) {
+                    best.v = wc[q];
+                    best.i = wa[q];
+                }
+            const KV win = warp_select<false>(best);
 #pragma unroll
-        for (int q = 0; q < WSL_PER_LANE; ++q)
-            if (wa[q] == win.i) {  // an anchor appears once in a GT's table
-                wc[q] = P24_POS_INF;
-                wa[q] = 0x7fffffff;
-            }
-        if (lane == 0) claim[g * P24_TOPK + r] = win.i;
+            for (int q = 0; q < WSL_PER_LANE; ++q)
+                if (wa[q] == win.i) {  // an anchor appears once in a GT's table
+                    wc[q] = P24_POS_INF;
+                    wa[q] = 0x7fffffff;
+                }
+            won = win.i;
+        }
+        if (lane == 0) claim[r] = won;
     }
     return take;
 }
@@ -1224,151 +1302,199 @@ __device__ __noinline__ int resolve_conflict(const Params& p, const float* recs,
     return best.i != 0x7fffffff ? best.i : 0;
 }
 
-// Anchor claimed by several GTs: the GT with the smallest cost among those the anchor is valid for (in window and in
-// polygon), first index on ties; -1 when there is none.  One warp, lanes over the GTs: the anchor's slot in a GT's
-// window table follows from its grid cell and the table's origins.
-__device__ __forceinline__ int valid_argmin(const Params& p, int b, int n, int a) {
-    const int lane = threadIdx.x & 31;
-    int l = 0;
+// Dynamic k of one GT from its list (one warp): the list holds (upper bound, anchor | all-apart flag) of every candidate
+// pair whose bound reaches T.  (A) the 10th largest certified LOWER bound refines the threshold; (B) the entries whose
+// bound still reaches it are evaluated exactly (8-lane groups); the kc largest exact values are summed in descending
+// order (like torch.topk(...).sum()).
+__device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared& S, const float* __restrict__ rec, int b, int slot,
+                                                    int lc, int kc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float2* lst = p.list + (long long)slot * P24_LISTCAP;
+    const float* img = p.outputs + (long long)b * p.img_stride;
+    float t[P24_TOPK];
 #pragma unroll
-    for (int q = 1; q < P24_MAX_LEVELS; ++q) l += (q < p.nlev && a >= p.lev[q].off) ? 1 : 0;
-    const int r = a - p.lev[l].off;
-    const int iy = r / p.lev[l].W, ix = r - iy * p.lev[l].W;
-    KV best = {P24_POS_INF, 0x7fffffff};
-    for (int g = lane; g < n; g += 32) {
-        const float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
-        const int sx = ix - __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l));
-        const int sy = iy - __float_as_int(__ldcg(tab + P24_WT_HDR + 2 * l + 1));
-        if (sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE) {
-            const float c = __ldcg(tab + l * P24_WSLOTS + sy * P24_WSIDE + sx);
-            if (c < P24_POS_INF && kv_lt(c, g, best.v, best.i)) {
-                best.v = c;
-                best.i = g;
-            }
+    for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;
+    for (int i0 = 0; i0 < lc; i0 += 128) {  // four independent loads per lane in flight
+        float2 e[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u + lane;
+            e[u] = i < lc ? __ldcg(lst + i) : make_float2(P24_NEG_INF, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool apart = (__float_as_int(e[u].y) & 0x80000000) != 0;
+            // bound = value + 2e-5 (+- 3e-6) for an all-apart pair: bound - 7e-5 is a certified lower bound
+            if (apart) top_insert_desc(t, e[u].x - 7e-5f);
         }
     }
-    best = warp_select<false>(best);
-    return best.i != 0x7fffffff ? best.i : -1;
+    float tref = rec[GT_T];
+    {
+        float v10 = P24_NEG_INF;
+#pragma unroll 1
+        for (int r = 0; r < P24_TOPK; ++r) v10 = warp_pop_max(t);
+        tref = fmaxf(tref, v10);  // (v10 = -inf when fewer than 10 entries carry a lower bound)
+    }
+#pragma unroll
+    for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;  // from here on: exact values (group leaders)
+    const unsigned gm = group_mask();
+    const int grp = lane >> 3, sub = lane & 7;
+    int nbuf = 0;
+    for (int i0 = 0; i0 < lc || nbuf > 0; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false;
+        int anchor = 0;
+        if (i < lc) {
+            const float2 e = __ldcg(lst + i);
+            keep = !(e.x < tref);
+            anchor = __float_as_int(e.y) & 0x7fffffff;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) S.surv[warp][nbuf + __popc(bal & ((1u << lane) - 1u))] = anchor;
+        nbuf += __popc(bal);
+        __syncwarp();
+        if (nbuf > TAIL_SURV - 32 || i0 + 32 >= lc) {  // evaluate the batch
+            for (int j0 = 0; j0 < nbuf; j0 += 4) {
+                const int j = j0 + grp;
+                float v = P24_NEG_INF;
+                if (j < nbuf) {
+                    v = group_pair_value(rec, img + (long long)S.surv[warp][j] * p.row_stride, gm);
+                    if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
+                }
+                if (sub == 0 && j < nbuf) top_insert_desc(t, v);
+            }
+            nbuf = 0;
+            __syncwarp();
+        }
+    }
+    float ksum = 0.0f;
+#pragma unroll 1
+    for (int r = 0; r < kc; ++r) {
+        const float v = warp_pop_max(t);
+        ksum = ksum + (v == P24_POS_INF ? NAN : v);
+    }
+    return ksum;
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(const __grid_constant__ Params p) {
-    extern __shared__ float4 t_dyn4[];  // recs [Lmax * GT_REC] floats | claim [Lmax * 10] | uniq [Lmax * 10] | kreq, ntake [Lmax]
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ Params p) {
+    // recs [n * GT_REC] floats | org [n * 8] ints | claim [n * 10] ints | uniq [cap] ints | best [cap] u64 | rows [cap * ROW_PAD]
+    extern __shared__ float4 t_dyn4[];
     __shared__ TailShared S;
     pdl_trigger();  // the next step's k_prep may become resident (it waits for this grid's completion)
     pdl_wait();
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x / TAIL_CL, cr = blockIdx.x % TAIL_CL, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    float* s_rec = reinterpret_cast<float*>(t_dyn4);
-    int* claim = reinterpret_cast<int*>(s_rec + p.Lmax * GT_REC);
-    int* uniq = claim + p.Lmax * P24_TOPK;
-    int* kreq = uniq + p.Lmax * P24_TOPK;   // per GT: >= 0 clamped dynamic k a rare path must still honour, -1 none, -2 brute force
-    int* ntake = kreq + p.Lmax;             // per GT: valid pairs already claimed
     const int n = p.num_gt[b];
-    const int ncand = p.ncand[b];
+    const int ncand = __ldcg(&p.ncand[b]);
     const int kc = min(P24_TOPK, ncand);  // losses.py:452
+    const int cap = (p.Lmax * P24_TOPK + TAIL_CL - 1) / TAIL_CL;  // claim slots (hence distinct anchors) per CTA
+    float* s_rec = reinterpret_cast<float*>(t_dyn4);
+    int* org = reinterpret_cast<int*>(s_rec + p.Lmax * GT_REC);
+    int* claim = org + p.Lmax * 2 * P24_MAX_LEVELS;
+    int* uniq = claim + p.Lmax * P24_TOPK;
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(uniq + ((cap + 1) & ~1));
+    float* rows = reinterpret_cast<float*>(best + cap);
     const float* img = p.outputs + (long long)b * p.img_stride;
     const bool no_filter = (p.flags & P24_F_NO_FILTER) != 0;
+    int* claimg = p.claimg + (long long)b * p.Lmax * P24_TOPK;
+    int* kreq = p.kreq + b * p.Lmax;    // per GT: >= 0 clamped dynamic k a rare path must still honour, -1 none, -2 brute force
+    int* ntake = p.ntake + b * p.Lmax;  // per GT: valid pairs already claimed
 
     {
         const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
         for (int i = tid; i < n * (GT_REC / 4); i += TAIL_THREADS) t_dyn4[i] = __ldcg(gsrc + i);
+        for (int i = tid; i < n * 2 * P24_MAX_LEVELS; i += TAIL_THREADS) {
+            const int g = i / (2 * P24_MAX_LEVELS), q = i - g * (2 * P24_MAX_LEVELS);
+            org[i] = __float_as_int(__ldcg(p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE + P24_WT_HDR + q));
+        }
     }
-    for (int i = tid; i < n * P24_TOPK; i += TAIL_THREADS) claim[i] = -1;
-    if (tid == 0) {
-        S.nuniq = 0;
-        S.nbrute = 0;
-        S.nspill = 0;
-        S.lmax = 0;
-    }
+    if (tid == 0) S.nuniq = 0;
     __syncthreads();
 
-    // ---- phase 1, one warp per GT: dynamic k from the GT's list, then the k cheapest valid pairs -> claims --------
-    for (int g = warp; g < n; g += TAIL_WARPS) {
+    // ---- phase 1, one warp per GT (the image's GTs spread over the warps of the cluster): dynamic k from the GT's list,
+    // then the k cheapest valid pairs -> claims (global) ---------------------------------------------------------------
+    for (int g = cr * TAIL_WARPS + warp; g < n; g += TAIL_CL * TAIL_WARPS) {
         const int slot = b * p.Lmax + g;
         const int lc = __ldcg(&p.lcount[slot]);
         if (lane == 0) {
             p.lcount[slot] = 0;  // ready for the next call
-            if (lc > S.lmax) atomicMax(&S.lmax, lc);
+            atomicMax(&p.status[ST_LISTMAX], lc);
+            atomicAdd(&p.status[ST_LISTSUM], min(lc, 1 << 20));
+            atomicAdd(&p.status[ST_GTS], 1);
         }
-        int k = -1;
-        if (!no_filter && lc <= P24_LISTCAP && lc >= kc) {
-            // the list holds every candidate value >= T and at least the 10 seeds: its kc largest are the image's
-            const float* lst = p.list + (long long)slot * P24_LISTCAP;
-            float t[P24_TOPK];
-#pragma unroll
-            for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;
-            for (int i = lane; i < lc; i += 32) top_insert_desc(t, __ldcg(lst + i));
-            float ksum = 0.0f;
-#pragma unroll 1
-            for (int r = 0; r < kc; ++r) {
-                const KV best = warp_select<true>(KV{t[0], t[0] > P24_NEG_INF ? lane : 0x7fffffff});
-                if (lane == best.i) {
-#pragma unroll
-                    for (int q = 0; q < P24_TOPK - 1; ++q) t[q] = t[q + 1];
-                    t[P24_TOPK - 1] = P24_NEG_INF;
-                }
-                ksum = ksum + (best.v == P24_POS_INF ? NAN : best.v);  // descending order, like torch.topk(...).sum()
-            }
-            k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
-            if (k < 1) k = 1;
-        }
-        if (k < 0) {
+        int* cl = claimg + g * P24_TOPK;
+        if (no_filter || lc > P24_LISTCAP || lc < kc) {
             if (lane == 0) {
-                kreq[g] = -2;  // brute force
-                atomicAdd(&S.nbrute, 1);
+                kreq[g] = -2;  // brute force, by the cluster's first CTA
+                atomicAdd(&p.rare[b], 1);
             }
+            if (lane < P24_TOPK) cl[lane] = -1;
             continue;
         }
+        const float ksum = warp_topk_sum_list(p, S, s_rec + g * GT_REC, b, slot, lc, kc);
+        int k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
+        if (k < 1) k = 1;
         const int kk = min(k, ncand);  // torch.topk would raise beyond the candidate count; clamp instead
-        const int take = warp_select_claims(p, b, g, kk, claim);
+        const int take = warp_select_claims(p, b, g, kk, cl);
         if (lane == 0) {
             p.dyn_k[slot] = kk;
             ntake[g] = take;
             kreq[g] = take < kk ? kk : -1;
-            if (take < kk) atomicAdd(&S.nspill, 1);
+            if (take < kk) atomicAdd(&p.rare[b], 1);
         }
     }
-    for (int g = n + tid; g < p.Lmax; g += TAIL_THREADS) p.dyn_k[b * p.Lmax + g] = 0;
-    __syncthreads();
-    // ---- rare paths, whole CTA, one GT at a time ---------------------------------------------------------------------
-    if (S.nbrute > 0) {
-        for (int g = 0; g < n; ++g) {
-            if (kreq[g] != -2) continue;
-            const float ksum = topk_sum_bruteforce(p, S, s_rec + g * GT_REC, b, kc);
-            int k = (int)ksum;
-            if (k < 1) k = 1;
-            const int kk = min(k, ncand);
-            __syncthreads();
-            if (warp == 0) {
-                const int take = warp_select_claims(p, b, g, kk, claim);
-                if (lane == 0) {
-                    p.dyn_k[b * p.Lmax + g] = kk;
-                    ntake[g] = take;
-                    kreq[g] = take < kk ? kk : -1;
-                    if (take < kk) S.nspill += 1;
+    if (cr == 0)
+        for (int g = n + tid; g < p.Lmax; g += TAIL_THREADS) p.dyn_k[b * p.Lmax + g] = 0;
+    __threadfence();
+    cluster_sync_all();
+    // ---- rare paths, the cluster's first CTA, one GT at a time -----------------------------------------------------
+    if (__ldcg(&p.rare[b]) > 0) {  // (the same value in every CTA of the cluster: written before the barrier)
+        if (cr == 0) {
+            int nb = 0, ns = 0;
+            for (int g = 0; g < n; ++g) {
+                if (__ldcg(&kreq[g]) != -2) continue;
+                ++nb;
+                const float ksum = topk_sum_bruteforce(p, S, s_rec + g * GT_REC, b, kc);
+                int k = (int)ksum;
+                if (k < 1) k = 1;
+                const int kk = min(k, ncand);
+                __syncthreads();
+                if (warp == 0) {
+                    const int take = warp_select_claims(p, b, g, kk, claimg + g * P24_TOPK);
+                    if (lane == 0) {
+                        p.dyn_k[b * p.Lmax + g] = kk;
+                        ntake[g] = take;
+                        kreq[g] = take < kk ? kk : -1;
+                    }
                 }
+                __threadfence();
+                __syncthreads();
             }
-            __syncthreads();
+            for (int g = 0; g < n; ++g) {
+                const int kk = __ldcg(&kreq[g]);
+                if (kk < 0) continue;
+                ++ns;
+                spill_claims(p, S, s_rec + g * GT_REC, b, g, kk - __ldcg(&ntake[g]), claimg + g * P24_TOPK, __ldcg(&ntake[g]));
+                __syncthreads();
+            }
+            if (tid == 0) {
+                if (nb) atomicAdd(&p.status[ST_BRUTE], nb);
+                if (ns) atomicAdd(&p.status[ST_SPILL], ns);
+            }
+            __threadfence();
         }
+        cluster_sync_all();
     }
-    if (S.nspill > 0) {
-        for (int g = 0; g < n; ++g) {
-            const int kk = kreq[g];
-            if (kk < 0) continue;
-            spill_claims(p, S, s_rec + g * GT_REC, b, g, kk - ntake[g], claim + g * P24_TOPK, ntake[g]);
-            __syncthreads();
-        }
-    }
-    if (tid == 0) {
-        if (S.nbrute) atomicAdd(&p.status[ST_BRUTE], S.nbrute);
-        if (S.nspill) atomicAdd(&p.status[ST_SPILL], S.nspill);
-        atomicMax(&p.status[ST_LISTMAX], S.lmax);
-        p.seed_done[b] = 0;  // ready for the next call
-        p.ncand[b] = 0;
-    }
-    // ---- phase 2: the distinct claimed anchors (first claim of every anchor) and whether several GTs claim them ------
+    // ---- phase 2: every CTA looks at all claims of the image and owns a slice of the slots: the distinct claimed anchors
+    // (first claim of every anchor) of its slice and whether several GTs claim them -------------------------------------
     const int nslots = n * P24_TOPK;
-    for (int t = tid; t < nslots; t += TAIL_THREADS) {
+    for (int t = tid; t < nslots; t += TAIL_THREADS) claim[t] = __ldcg(claimg + t);
+    __syncthreads();
+    for (int t = cr * cap + tid; t < min(nslots, (cr + 1) * cap); t += TAIL_THREADS) {
         const int a = claim[t];
         if (a < 0) continue;
         bool first = true, multi = false;
@@ -1378,13 +1504,52 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(const __grid_constant_
                 if (j < t) first = false;
             }
         }
-        if (first) uniq[atomicAdd(&S.nuniq, 1)] = t | (multi ? 0x40000000 : 0);
+        if (first) {
+            const int e = atomicAdd(&S.nuniq, 1);
+            uniq[e] = t | (multi ? 0x40000000 : 0);
+            best[e] = ~0ull;
+        }
     }
     __syncthreads();
     const int nuniq = S.nuniq;
-    if (tid == 0) p.num_fg[b] = nuniq;  // every claimed anchor ends up foreground (losses.py:479)
+    if (tid == 0 && nuniq) atomicAdd(&p.num_fg[b], nuniq);  // every claimed anchor ends up foreground (losses.py:479)
 
-    // ---- phase 3, one warp per claimed anchor: conflict resolution, outputs, loss terms (lanes over rays / classes).
+    // ---- phase 3a: anchors claimed by several GTs: argmin of the cost over ALL GTs (losses.py:471-476).  Valid pairs
+    // always beat penalised ones and their costs are in the GTs' window tables: one thread per (anchor, GT), the anchor's
+    // slot in the GT's table follows from its grid cell and the table's origin; packed (cost, GT) minimum in shared memory.
+    // 3b (the same round trip): the rows of the CTA's anchors staged in shared memory, one warp per row ----------------
+    for (int q = tid; q < nuniq * n; q += TAIL_THREADS) {
+        const int e = q / n, g = q - e * n;
+        const int u = uniq[e];
+        if (!(u & 0x40000000)) continue;
+        const int a = claim[u & 0x3FFFFFFF];
+        int l = 0;
+#pragma unroll
+        for (int w = 1; w < P24_MAX_LEVELS; ++w) l += (w < p.nlev && a >= p.lev[w].off) ? 1 : 0;
+        const int r = a - p.lev[l].off;
+        const int iy = r / p.lev[l].W, ix = r - iy * p.lev[l].W;
+        const int sx = ix - org[g * 2 * P24_MAX_LEVELS + 2 * l], sy = iy - org[g * 2 * P24_MAX_LEVELS + 2 * l + 1];
+        if (sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE) {
+            const float c = __ldcg(p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE + l * P24_WSLOTS + sy * P24_WSIDE + sx);
+            if (c < P24_POS_INF) atomicMin(&best[e], ((unsigned long long)p24_ordered(c) << 32) | (unsigned)g);
+        }
+    }
+    const int C = 27 + p.nc;
+    const bool stage = C <= ROW_PAD;
+    if (stage) {
+        for (int e = warp; e < nuniq; e += TAIL_WARPS) {
+            const float* src = img + (long long)claim[uniq[e] & 0x3FFFFFFF] * p.row_stride;
+            float* dst = rows + e * ROW_PAD;
+#pragma unroll
+            for (int q = 0; q < (ROW_PAD + 31) / 32; ++q) {
+                const int c = lane + 32 * q;
+                if (c < C) dst[c] = src[c];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3c, one warp per claimed anchor: outputs and loss terms (lanes over rays / classes).
     // Contributions are accumulated as fixed-point integers: the sums do not depend on the order. -----------------------
     long long acc = 0;  // lane k < 24: sum of loss24[:, k]; lane 24: -sum of obj logits at fg; lane 25: cls BCE
     for (int e = warp; e < nuniq; e += TAIL_WARPS) {
@@ -1392,13 +1557,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(const __grid_constant_
         const int t = u & 0x3FFFFFFF;
         const int aa = claim[t];
         int g = t / P24_TOPK;
-        const float* row = img + (long long)aa * p.row_stride;
+        const float* row = stage ? rows + e * ROW_PAD : img + (long long)aa * p.row_stride;
         if (u & 0x40000000) {
-            // claimed by several GTs: argmin of the cost over ALL GTs (losses.py:471-476).  Valid pairs always beat
-            // penalised ones and their costs are in the GTs' window tables; without any valid pair (every claim came
-            // from a spill) the penalised costs are evaluated here
-            const int gv = valid_argmin(p, b, n, aa);
-            g = gv >= 0 ? gv : resolve_conflict(p, s_rec, n, row);
+            const unsigned long long bb = best[e];
+            // without any valid pair (every claim came from a spill) the penalised costs are evaluated here
+            g = bb != ~0ull ? (int)(bb & 0xFFFFFFFFull) : resolve_conflict(p, s_rec, n, row);
         }
         const float* rec = s_rec + g * GT_REC;
         float l;
@@ -1444,21 +1607,22 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(const __grid_constant_
 #pragma unroll
         for (int w = 0; w < TAIL_WARPS; ++w) t += S.acc[w][tid];
         if (t != 0) atomicAdd((unsigned long long*)&p.acc_fix[tid], (unsigned long long)t);
-    } else if (tid == 26 && p.sums28) {
+    } else if (tid == 26 && p.sums28 && nuniq) {
         atomicAdd((unsigned long long*)&p.acc_fix[26], (unsigned long long)nuniq);
-    } else if (tid == 27 && p.sums28) {
+    } else if (tid == 27 && p.sums28 && cr == 0) {
         atomicAdd((unsigned long long*)&p.acc_fix[27], (unsigned long long)n);
     }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
         const unsigned done = atomicAdd(&p.ticket[TK_TAIL], 1u);
-        S.last = (done == (unsigned)p.B - 1u) ? 1 : 0;
+        S.last = (done == (unsigned)(p.B * TAIL_CL) - 1u) ? 1 : 0;
     }
     __syncthreads();
     if (!S.last) return;
     __threadfence();
-    // ---- last CTA: the batch sums (integer adds: exact, order independent), then finalize or publish ----------------
+    // ---- last CTA of the grid: the batch sums (integer adds: exact, order independent), per-image counters reset, then
+    // finalize or publish ---------------------------------------------------------------------------------------------
     if (tid < 28) {
         const long long t = __ldcg(&p.acc_fix[tid]);
         p.acc_fix[tid] = 0;  // ready for the next call
@@ -1469,6 +1633,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(const __grid_constant_
         p.ticket[TK_LEFF] = 0u;
         p.ticket[TK_TAIL] = 0u;
         p.ticket[TK_SEED] = 0u;
+    }
+    for (int i = tid; i < p.B; i += TAIL_THREADS) {
+        p.seed_done[i] = 0;
+        p.ncand[i] = 0;
+        p.rare[i] = 0;
     }
     __syncthreads();
     if (!p.sums28) return;
@@ -1530,22 +1699,40 @@ size_t pass_smem(int Lmax) {
     const size_t rec = (size_t)Lmax * GT_REC * sizeof(float);
     return rec > sizeof(SeedShared) ? rec : sizeof(SeedShared);
 }
-size_t tail_smem(int Lmax) {
-    return (size_t)Lmax * GT_REC * sizeof(float) + (size_t)Lmax * (2 * P24_TOPK + 2) * sizeof(int);
+size_t tail_smem(int Lmax, int nc) {
+    const size_t cap = ((size_t)Lmax * P24_TOPK + TAIL_CL - 1) / TAIL_CL;
+    size_t b = (size_t)Lmax * GT_REC * sizeof(float);                 // recs
+    b += (size_t)Lmax * 2 * P24_MAX_LEVELS * sizeof(int);             // window origins
+    b += (size_t)Lmax * P24_TOPK * sizeof(int);                       // claims
+    b += ((cap + 1) & ~(size_t)1) * sizeof(int);                      // uniq
+    b += cap * sizeof(unsigned long long);                            // best
+    if (27 + nc <= ROW_PAD) b += cap * ROW_PAD * sizeof(float);       // staged rows
+    return b;
 }
 
 template <typename K>
-cudaError_t launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Params& p) {
+cudaError_t launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Params& p, int cluster = 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)cluster;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
@@ -1564,11 +1751,14 @@ extern "C" int p24_workspace_init(void* workspace, size_t workspace_bytes, void*
     return (int)cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int p24_read_status(const void* workspace, int B, int A, int Lmax, int32_t* h_status8, void* stream) {
+extern "C" int p24_read_status(void* workspace, int B, int A, int Lmax, int32_t* h_status8, void* stream) {
     if (!workspace || !h_status8 || B <= 0 || A <= 0 || Lmax <= 0) return P24_E_BADARG;
     const P24Workspace L = p24_layout(B, A, Lmax);
-    cudaError_t e = cudaMemcpyAsync(h_status8, (const char*)workspace + L.status, ST_WORDS * sizeof(int),
-                                    cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    char* st = (char*)workspace + L.status;
+    cudaError_t e = cudaMemcpyAsync(h_status8, st, ST_WORDS * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    // the counters restart with every read; the error bits (word 0) are sticky
+    e = cudaMemsetAsync(st + sizeof(int), 0, (ST_WORDS - 1) * sizeof(int), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaStreamSynchronize((cudaStream_t)stream);
 }
@@ -1591,7 +1781,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     const P24Workspace L = p24_layout(B, A, Lmax);
     if (workspace_bytes < L.total) return P24_E_WORKSPACE;
     if (((uintptr_t)workspace & 255) != 0) return P24_E_BADARG;
-    const size_t dyn_pass = pass_smem(Lmax), dyn_tail = tail_smem(Lmax);
+    const size_t dyn_pass = pass_smem(Lmax), dyn_tail = tail_smem(Lmax, num_classes);
     if (dyn_pass > 160 * 1024 || dyn_tail > 200 * 1024 || p24_tiles(A) > 65535) return P24_E_UNSUPPORTED;
     char* ws = (char*)workspace;
     Params p;
@@ -1610,8 +1800,12 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.lcount = (int*)(ws + L.lcount);
     p.gt_rec = (float*)(ws + L.gt_rec);
     p.wtab = (float*)(ws + L.wtab);
-    p.list = (float*)(ws + L.list);
+    p.list = (float2*)(ws + L.list);
     p.cbits = (unsigned*)(ws + L.cbits);
+    p.claimg = (int*)(ws + L.claimg);
+    p.kreq = (int*)(ws + L.kreq);
+    p.ntake = (int*)(ws + L.ntake);
+    p.rare = (int*)(ws + L.rare);
     p.flags = flags;
     p.rank = 0; p.nranks = 1; p.epoch = 0;
     for (int r = 0; r < P24_MAX_RANKS; ++r) p.mbox[r] = nullptr;
@@ -1663,7 +1857,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
         if (e != cudaSuccess) return (int)e;
     }
     p24::prof_mark(2, st);
-    e = launch(k_tail, dim3(B), dim3(TAIL_THREADS), dyn_tail, st, pdl, p);
+    e = launch(k_tail, dim3(B * TAIL_CL), dim3(TAIL_THREADS), dyn_tail, st, pdl, p, TAIL_CL);
     if (e != cudaSuccess) return (int)e;
     if (p.nranks > 1) {
         e = launch(k_fin, dim3(1), dim3(32), 0, st, pdl, p);

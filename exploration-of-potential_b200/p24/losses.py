@@ -221,11 +221,13 @@ class Loss_Function(nn.Module):
         return [max(w) / 1965.0 if w else 0.0]
 
     def path_stats(self):
-        """Counts of the rare paths since the workspaces were created: GTs whose dynamic k needed the brute-force
-        evaluation, GTs that spilled into the penalised regime, the longest top-10 candidate list."""
+        """Counts of the rare paths since the previous read: GTs whose dynamic k needed the brute-force evaluation, GTs
+        that spilled into the penalised regime, the longest and the mean top-10 candidate list."""
         st = [s for _, s in self._engine.read_status()]
-        return {"brute_force_gts": sum(s[1] for s in st), "spill_gts": sum(s[2] for s in st),
-                "list_max": max([s[3] for s in st] + [0]), "list_capacity": 2048}
+        gts = sum(s[6] for s in st)
+        return {"brute_force_gts": sum(s[1] for s in st), "spill_gts": sum(s[2] for s in st), "gts": gts,
+                "list_max": max([s[3] for s in st] + [0]), "list_mean": (sum(s[5] for s in st) / gts) if gts else 0.0,
+                "list_capacity": 1024}
 
     def forward(self, outputs_train, labels):
         outputs = outputs_train[3]

@@ -170,16 +170,18 @@ int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_str
                     int32_t* cand_count, int32_t* det_count, float* det_rows, int32_t* keep_idx, float* rect_debug,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* Sticky status of a workspace, read back to the HOST (one small device-to-host copy + a synchronisation of `stream`):
- *   h_status8[0]  error bits (P24_ERR_*); 0 = none.  The reference raises on its failures (losses.py:81-82); the Python
- *                 host side raises P24Error when a bit is set
- *   h_status8[1]  GTs whose dynamic k took the brute-force path (cumulative over the calls on this workspace)
- *   h_status8[2]  GTs that spilled into the penalised regime (cumulative)
+/* Status of a workspace, read back to the HOST (one small device-to-host copy + a synchronisation of `stream`):
+ *   h_status8[0]  error bits (P24_ERR_*), sticky; 0 = none.  The reference raises on its failures (losses.py:81-82); the
+ *                 Python host side raises P24Error when a bit is set
+ *   counters since the previous read (they restart with every read):
+ *   h_status8[1]  GTs whose dynamic k took the brute-force path
+ *   h_status8[2]  GTs that spilled into the penalised regime
  *   h_status8[3]  longest top-10 candidate list seen
- *   h_status8[4]  clock cycles the last fused all-reduce waited for its peers (nranks > 1) */
+ *   h_status8[4]  clock cycles the last fused all-reduce waited for its peers (nranks > 1)
+ *   h_status8[5]  list entries seen, over h_status8[6] GTs */
 #define P24_ERR_WINDOW_OVERFLOW 1
 #define P24_ERR_PEER_TIMEOUT 4
-int p24_read_status(const void* workspace, int B, int A, int Lmax, int32_t* h_status8, void* stream);
+int p24_read_status(void* workspace, int B, int A, int Lmax, int32_t* h_status8, void* stream);
 
 /* Profiling aid (bench.py): when enabled, p24_simota_loss_batch and p24_postprocess record CUDA events around their
  * kernels on the launching stream and launch them in plain stream order; p24_profile_read waits for the last call and
