@@ -83,6 +83,25 @@ struct Params {
     Level lev[P24_MAX_LEVELS];
 };
 
+// Debug-only phase timers (-DP24_TIMING): %globaltimer stamps at phase boundaries, read back with p24_debug_read_timers
+#ifdef P24_TIMING
+#define TM_ROWS 8192
+#define TM_SLOTS 16
+__device__ unsigned long long g_tstamp[3][TM_ROWS][TM_SLOTS];
+__device__ __forceinline__ void tmark(int kern, int row, int slot) {
+    if (row >= 0 && row < TM_ROWS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_tstamp[kern][row][slot] = t;
+    }
+}
+#define TMARK(kern, row, slot) do { if ((threadIdx.x & 31) == 0) tmark(kern, row, slot); } while (0)
+#define TMARK0(kern, row, slot) do { if (threadIdx.x == 0) tmark(kern, row, slot); } while (0)
+#else
+#define TMARK(kern, row, slot)
+#define TMARK0(kern, row, slot)
+#endif
+
 #define TK_ITEM 0   // ticket words
 #define TK_LEFF 1
 #define TK_TAIL 2
@@ -271,15 +290,7 @@ __device__ __forceinline__ int gt_class(const float* rec, int nc) {
     return min(max(c, 0), nc - 1);
 }
 
-// Sum over all classes of BCE(p_j, 0) (losses.py:406-416) in product form, by the 32 lanes of a warp
-__device__ __noinline__ float warp_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1) {
-    const int lane = threadIdx.x & 31;
-    const float obj_sig = 1.0f / eo1;
-    float s = 0.0f;
-    for (int j = lane; j < nc; j += 32) s += p24_bce_neg(p24_joint_prob(cls[j], obj_sig));
-    return warp_sum(s);
-}
-
+// Sum over all classes of BCE(p_j, 0) (losses.py:406-416)
 // ... by the 8 lanes of a group, term by term (fallback of the product form)
 __device__ __noinline__ float group_cls_neg_sum(const float* __restrict__ cls, int nc, float eo1, unsigned m) {
     const int sub = threadIdx.x & 7;
@@ -332,15 +343,14 @@ __device__ __forceinline__ float warp_bound_Hstar(float rg_lane, float d) {
 // -------------------------------------------------------------------------------------------
 #define SEED_FAR 3
 #define SEED_DISC 3                                    // points per (far GT, level): centre, far end of the inscribed disc, 2 strides out
-#define SEED_NV 24                                     // polygon vertices (of any GT of the image) farthest from this GT
+#define SEED_NV (3 * P24_WARPS)                        // polygon vertices (of any GT of the image) far from this GT: 3 per warp
 #define SEED_MAX (SEED_FAR * P24_MAX_LEVELS * SEED_DISC + SEED_NV * P24_MAX_LEVELS)   // 132 <= P24_THREADS
 
 struct SeedShared {
     float rec[GT_REC];
     int far[SEED_FAR];
     int vsel[SEED_NV];        // (GT << 5) | vertex
-    float vkey[P24_THREADS];  // the threads' farthest vertices
-    int vidx[P24_THREADS];
+    int hash[256];            // distinct seed anchors
     float val[SEED_MAX];
     int anc[SEED_MAX];
     int nfar, nvert;
@@ -412,19 +422,15 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
                     bi = (h << 5) | k;
                 }
             }
-            S.vkey[tid] = best;
-            S.vidx[tid] = bi;
-        }
-        __syncthreads();
-        {
-            const float mykey = S.vkey[tid];
-            const int myidx = S.vidx[tid];
-            if (myidx >= 0) {
-                int rank = 0;
-                for (int j = 0; j < P24_THREADS; ++j) rank += kv_gt(S.vkey[j], j, mykey, tid) ? 1 : 0;
-                if (rank < SEED_NV) S.vsel[rank] = myidx;
+            // the warp's three farthest picks (any subset of far vertices serves: better ones only tighten T)
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+                const KV w = warp_select<true>(KV{bi >= 0 ? best : P24_NEG_INF, bi >= 0 ? bi : 0x7fffffff});
+                if (lane == 0) S.vsel[warp * 3 + r] = w.i == 0x7fffffff ? -1 : w.i;
+                if (bi == w.i) bi = -1;
             }
-            if (tid == 0) S.nvert = min(SEED_NV, min(n * P24_RAYS, P24_THREADS));
+            S.hash[tid] = -1;
+            if (tid == 0) S.nvert = SEED_NV;
         }
         __syncthreads();
         const int nfar = S.nfar, nvert = S.nvert;
@@ -458,7 +464,7 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
                 const int r0 = tid - n_disc;
                 const int vi = r0 / p.nlev;
                 l = r0 - vi * p.nlev;
-                const int hv = S.vsel[vi];
+                const int hv = max(S.vsel[vi], 0);
                 hsel = hv >> 5;
                 const int k = hv & 31;
                 const float* h = recs + hsel * GT_REC;
@@ -473,7 +479,8 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
             const Level lv = p.lev[l];
             const float hcx = h[GT_CX], hcy = h[GT_CY];
             const int ix = cell_index(qx, st), iy = cell_index(qy, st);
-            if (ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
+            const bool pick_ok = tid < n_disc || S.vsel[(tid - n_disc) / p.nlev] >= 0;
+            if (pick_ok && ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
                 const int a = lv.off + iy * lv.W + ix;
                 const float ast = p.strides[a];
                 const float xc = p24_anchor_centre(p.x_shifts[a], ast), yc = p24_anchor_centre(p.y_shifts[a], ast);
@@ -505,21 +512,32 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
             }
         }
         __syncthreads();
-        // ---- the 10th largest value over the distinct seed anchors ---------------------------------------------
+        // ---- the 10th largest value over the distinct seed anchors (first arrival of an anchor in a small hash) -----
         if (tid == 0) S.T = P24_NEG_INF;
-        bool mine = false;
         float v = P24_NEG_INF;
         if (tid < n_pts) {
             v = S.val[tid];
             const int a = S.anc[tid];
-            mine = a >= 0 && v > P24_NEG_INF;
-            for (int j = 0; j < tid && mine; ++j) mine = S.anc[j] != a;  // the first copy of an anchor counts
+            if (a >= 0 && v > P24_NEG_INF) {
+                unsigned h = ((unsigned)a * 2654435761u) >> 24;
+                for (;;) {
+                    const int old = atomicCAS(&S.hash[h], -1, a);
+                    if (old == -1) break;   // mine
+                    if (old == a) {          // a copy of an anchor that is already in
+                        v = P24_NEG_INF;
+                        break;
+                    }
+                    h = (h + 1) & 255u;
+                }
+            } else {
+                v = P24_NEG_INF;
+            }
+            S.val[tid] = v;
         }
         __syncthreads();
-        if (tid < n_pts && !mine) S.val[tid] = P24_NEG_INF;
-        __syncthreads();
-        if (mine) {
+        if (v > P24_NEG_INF) {
             int rank = 0;
+#pragma unroll 4
             for (int j = 0; j < n_pts; ++j) rank += kv_gt(S.val[j], j, v, tid) ? 1 : 0;
             if (rank == P24_TOPK - 1) S.T = v;
         }
@@ -534,13 +552,13 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
         float far2 = 0.0f;  // 0: every pair is evaluated
         if (T > P24_NEG_INF) {
             const float rg = lane < P24_RAYS ? S.rec[GT_RG + lane] : 0.0f;
-            float lo = 0.0f, hi = 1.0e6f;
+            float lo = 0.0f, hi = 8192.0f;  // (pairs farther apart than hi are always evaluated)
             if (warp_bound_Hstar(rg, lo) + 3e-5f < T) {
                 if (warp_bound_Hstar(rg, hi) + 3e-5f < T) {
                     lo = hi;  // (cannot happen: the seeds themselves obey the bound)
                 } else {
 #pragma unroll 1
-                    for (int it = 0; it < 32; ++it) {
+                    for (int it = 0; it < 20; ++it) {
                         const float mid = 0.5f * (lo + hi);
                         if (warp_bound_Hstar(rg, mid) + 3e-5f < T) lo = mid;
                         else hi = mid;
@@ -645,10 +663,12 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     const int n = p.num_gt[b];
     // the records are complete once every seed item of the image has finished (the seed items are drawn from their own
     // ticket counter before any tile: the CTAs that hold them are running, so this wait cannot deadlock)
+    TMARK0(1, b * p.tiles + tile, 1);
     if (tid == 0) {
         while (ld_acquire(&p.seed_done[b]) < n) __nanosleep(64);
     }
     __syncthreads();
+    TMARK0(1, b * p.tiles + tile, 2);
     {
         const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
         float4* dst = reinterpret_cast<float4*>(s_rec);
@@ -656,6 +676,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     }
     cp_async_wait_all();
     __syncthreads();
+    TMARK0(1, b * p.tiles + tile, 3);
 
     float pcx = 0.f, pcy = 0.f, rpmin = INFINITY, obj = 0.f;
     const float xc = p24_anchor_centre(xs, st);
@@ -741,6 +762,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     }
     if (mine) S.cand[tid] = 1;
     __syncthreads();
+    TMARK0(1, b * p.tiles + tile, 4);
     {
         const int nitems = min(S.nitems, ITEM_CAP);
         for (int i = tid; i < nitems; i += P24_THREADS) {
@@ -759,6 +781,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
         }
     }
     __syncthreads();
+    TMARK0(1, b * p.tiles + tile, 5);
     const bool cand = active && (n > 0) && (cheap || S.cand[tid]);
     if (tid == 0) S.nitems = 0;
     __syncthreads();
@@ -799,6 +822,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
         p.pred_iou[o] = 0.0f;
     }
     __syncthreads();
+    TMARK0(1, b * p.tiles + tile, 6);
     {
         const int nitems = min(S.nitems, ITEM_CAP);
         for (int i = tid; i < nitems; i += P24_THREADS) {
@@ -963,6 +987,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
         staged = true;
     }
     pdl_wait();  // the records come from k_prep
+    TMARK0(1, 6000 + blockIdx.x, 0);
     const int leff = (int)__ldcg(&p.ticket[TK_LEFF]);  // the batch's largest num_gt
     // ---- seed items: image fastest, so that the real GT rows (valid rows come first) are drawn first ---------------
     {
@@ -972,7 +997,9 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
             __syncthreads();
             if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_SEED], 1u);  // the next one, in flight meanwhile
             const int g = seed / p.B, b = seed - g * p.B;
+            TMARK0(1, 4096 + seed, 0);
             if (g < p.num_gt[b]) seed_part(p, SS, b, g);
+            TMARK0(1, 4096 + seed, 1);
             __syncthreads();
             seed = s_seed;
         }
@@ -983,17 +1010,22 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
         if (tid == 0) s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);  // the next one, in flight meanwhile
         if (item < n_anchor) {
             // image-major order keeps an image's tiles (and its records) together in time
+            TMARK0(1, item, 0);
             anchor_part(p, s_rec, S.a, item / p.tiles, item % p.tiles, staged);
+            TMARK0(1, item, 7);
             staged = false;
         } else {
             const int wi = item - n_anchor;
             const int l = wi % p.nlev, bg = wi / p.nlev;
             const int b = bg / leff, g = bg - b * leff;
+            TMARK0(1, min(item, 4095), 0);
             if (g < p.num_gt[b]) window_part(p, S.w, b, g, l);
+            TMARK0(1, min(item, 4095), 7);
         }
         __syncthreads();
         item = s_item;
     }
+    TMARK0(1, 6000 + blockIdx.x, 1);
     pdl_trigger();
 }
 
@@ -1055,16 +1087,6 @@ __device__ void finalize_warp(const float* sums28, float* state26, float* result
     if (lane < 26) state26[lane] = loss;
 }
 
-// pair value by one warp (lanes over rays, fixed tree); every lane returns it, `l_out` is the lane's ray loss
-__device__ __forceinline__ float warp_pair_value(const float* __restrict__ rec, const float* __restrict__ row, float& l_out) {
-    const int lane = threadIdx.x & 31;
-    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
-    float l = 0.0f;
-    if (lane < P24_RAYS) l = ray_loss(rec[GT_RG + lane], row[2 + lane], d);
-    l_out = l;
-    return (warp_sum(l) / 24.0f) / 2.0f;
-}
-
 // the same value by an 8-lane group (3 rays per lane, fixed reduction tree); every lane of the group returns it
 __device__ __forceinline__ float group_pair_value(const float* __restrict__ rec, const float* __restrict__ row, unsigned m) {
     const int sub = threadIdx.x & 7;
@@ -1079,13 +1101,30 @@ __device__ __forceinline__ float group_pair_value(const float* __restrict__ rec,
     return (s / 24.0f) / 2.0f;
 }
 
+#define TAIL_WSEL 128  // entries of a GT's window table that can be valid (<= 25 per level)
 struct TailShared {
-    long long acc[TAIL_WARPS][26];
+    unsigned long long acc[26];   // fixed-point sums of the CTA (shared-memory atomics)
     KV kv[TAIL_WARPS];
     float sums[28];
-    int surv[TAIL_WARPS][TAIL_SURV];
+    int surv[TAIL_WARPS][TAIL_SURV];      // per GT warp: anchors of the list entries that survive the refined threshold
+    float sval[TAIL_WARPS][TAIL_SURV];    // ... and their exact pair values
+    float wc[TAIL_WARPS][TAIL_WSEL];      // per GT warp: the window-table entries that can be among the k cheapest
+    int wa[TAIL_WARPS][TAIL_WSEL];
     int nuniq, last;
 };
+
+// rank of the lane's value among the 32 lanes' values (0 = largest when MAX; ties -> lower lane first)
+template <bool MAX>
+__device__ __forceinline__ int lane_rank(float v) {
+    const int lane = threadIdx.x & 31;
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float o = __shfl_sync(0xffffffffu, v, j);
+        rank += (MAX ? kv_gt(o, j, v, lane) : kv_lt(o, j, v, lane)) ? 1 : 0;
+    }
+    return rank;
+}
 
 template <bool MAX>
 __device__ __forceinline__ KV tail_block_select(KV x, KV* s_red) {
@@ -1224,96 +1263,81 @@ __device__ __noinline__ void spill_claims(const Params& p, TailShared& S, const 
 }
 
 // The k smallest costs among the GT's valid pairs (window table) -> claim[0 .. 10) of the GT (global; unused slots -1)
-// (losses.py:460-464; ties -> lower anchor index).  One warp.  Returns the number of valid pairs taken (< k: the GT
-// must spill).
+// (losses.py:460-464; ties -> lower anchor index).  One warp: the 10th smallest of the lanes' minima bounds the k-th
+// smallest cost from above; the few entries up to it are ranked by counting.  Returns the number of valid pairs taken
+// (< k: the GT must spill).
 #define WSL_PER_LANE ((P24_WT_HDR + 31) / 32)   // 7
-__device__ __forceinline__ int warp_select_claims(const Params& p, int b, int g, int k, int* claim) {
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ int warp_select_claims(const Params& p, TailShared& S, int b, int g, int k, int* claim) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
     const int nslot = P24_WSLOTS * p.nlev;
     float wc[WSL_PER_LANE];
-    int wa[WSL_PER_LANE];
     int nv = 0;
     // (costs and origins requested together: one round trip)
     const int org = lane < 2 * P24_MAX_LEVELS ? __float_as_int(__ldcg(tab + P24_WT_HDR + lane)) : 0;
+    float lmin = P24_POS_INF;
 #pragma unroll
     for (int q = 0; q < WSL_PER_LANE; ++q) {
         const int s = lane + 32 * q;
-        wc[q] = s < nslot ? __ldcg(tab + s) : P24_POS_INF;
-    }
-#pragma unroll
-    for (int q = 0; q < WSL_PER_LANE; ++q) {
-        const int s = lane + 32 * q;
-        const int l = min(s / P24_WSLOTS, P24_MAX_LEVELS - 1), r = s - l * P24_WSLOTS;
-        const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
-        const int ox = __shfl_sync(0xffffffffu, org, 2 * l), oy = __shfl_sync(0xffffffffu, org, 2 * l + 1);
-        wa[q] = 0x7fffffff;
-        if (wc[q] < P24_POS_INF) {
-            wa[q] = p.lev[l].off + (oy + sy) * p.lev[l].W + (ox + sx);
-            ++nv;
-        } else {
-            wc[q] = P24_POS_INF;  // (NaN cannot occur: window_part stores finite costs or +inf)
-        }
+        float c = s < nslot ? __ldcg(tab + s) : P24_POS_INF;
+        if (!(c < P24_POS_INF)) c = P24_POS_INF;  // (NaN cannot occur: the table holds finite costs or +inf)
+        wc[q] = c;
+        nv += c < P24_POS_INF ? 1 : 0;
+        lmin = fminf(lmin, c);
     }
     nv = warp_sum_i(nv);
     const int take = min(k, nv);
-#pragma unroll 1
-    for (int r = 0; r < P24_TOPK; ++r) {
-        int won = -1;
-        if (r < take) {
-            KV best = {P24_POS_INF, 0x7fffffff};
+    // at least 10 entries (or all valid ones) are <= tau: the k <= 10 cheapest are among the entries <= tau
+    const int r0 = lane_rank<false>(lmin);
+    const unsigned pick = __ballot_sync(0xffffffffu, r0 == P24_TOPK - 1);
+    float tau = __shfl_sync(0xffffffffu, lmin, pick ? __ffs(pick) - 1 : 0);
+    if (!pick) tau = P24_POS_INF;
+    int ncomp = 0;
 #pragma unroll
-            for (int q = 0; q < WSL_PER_LANE; ++q)
-                if (kv_lt(wc[q], wa[q], best.v, best.i)) {
-                    best.v = wc[q];
-                    best.i = wa[q];
-                }
-            const KV win = warp_select<false>(best);
-#pragma unroll
-            for (int q = 0; q < WSL_PER_LANE; ++q)
-                if (wa[q] == win.i) {  // an anchor appears once in a GT's table
-                    wc[q] = P24_POS_INF;
-                    wa[q] = 0x7fffffff;
-                }
-            won = win.i;
+    for (int q = 0; q < WSL_PER_LANE; ++q) {
+        const int s = lane + 32 * q;
+        const bool in = wc[q] < P24_POS_INF && wc[q] <= tau;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int l = min(s / P24_WSLOTS, P24_MAX_LEVELS - 1), r = s - l * P24_WSLOTS;
+        const int ox = __shfl_sync(0xffffffffu, org, 2 * l), oy = __shfl_sync(0xffffffffu, org, 2 * l + 1);
+        if (in) {
+            const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+            const int at = ncomp + __popc(bal & ((1u << lane) - 1u));
+            if (at < TAIL_WSEL) {
+                S.wc[warp][at] = wc[q];
+                S.wa[warp][at] = p.lev[l].off + (oy + sy) * p.lev[l].W + (ox + sx);
+            }
         }
-        if (lane == 0) claim[r] = won;
+        ncomp += __popc(bal);
     }
+    ncomp = min(ncomp, TAIL_WSEL);
+    __syncwarp();
+    if (lane < P24_TOPK) claim[lane] = -1;
+    __syncwarp();
+    for (int e = lane; e < ncomp; e += 32) {
+        const float c = S.wc[warp][e];
+        const int a = S.wa[warp][e];
+        int rank = 0;
+        for (int j = 0; j < ncomp; ++j) rank += kv_lt(S.wc[warp][j], S.wa[warp][j], c, a) ? 1 : 0;
+        if (rank < take) claim[rank] = a;
+    }
+    __syncwarp();
     return take;
 }
 
-// Anchor claimed by several GTs none of which is valid for it (every claim came from a spill): argmin of the
-// PENALISED cost over all GTs (losses.py:471-476), first index on ties.  One warp, rare.
-__device__ __noinline__ int resolve_conflict(const Params& p, const float* recs, int n, const float* row) {
-    const float eo1 = 1.0f + expf(-row[26]);
-    const float neg = warp_cls_neg_sum(row + 27, p.nc, eo1);
-    const float obj_sig = 1.0f / eo1;
-    KV best = {P24_POS_INF, 0x7fffffff};
-    for (int g = 0; g < n; ++g) {
-        const float* rec = recs + g * GT_REC;
-        float l;
-        const float v = warp_pair_value(rec, row, l);
-        const float c = p24_cost(cls_cost_from(neg, row[27 + gt_class(rec, p.nc)], obj_sig), v, false);
-        if (kv_lt(c, g, best.v, best.i)) {
-            best.v = c;
-            best.i = g;
-        }
-    }
-    return best.i != 0x7fffffff ? best.i : 0;
-}
-
 // Dynamic k of one GT from its list (one warp): the list holds (upper bound, anchor | all-apart flag) of every candidate
-// pair whose bound reaches T.  (A) the 10th largest certified LOWER bound refines the threshold; (B) the entries whose
-// bound still reaches it are evaluated exactly (8-lane groups); the kc largest exact values are summed in descending
-// order (like torch.topk(...).sum()).
+// pair whose bound reaches T.  (A) a certified lower bound of the 10th largest value refines the threshold: the 10th
+// largest of the lanes' largest lower bounds (10 distinct entries reach it); (B) the entries whose bound still reaches it
+// are evaluated exactly (8-lane groups, rows requested up front); the kc largest exact values are summed in descending
+// order (like torch.topk(...).sum()).  Returns NaN-free sums only for clean inputs; `ok` = false: too many survivors
+// for the buffers (the caller takes the brute-force path).
 __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared& S, const float* __restrict__ rec, int b, int slot,
-                                                    int lc, int kc) {
+                                                    int lc, int kc, bool& ok) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float2* lst = p.list + (long long)slot * P24_LISTCAP;
     const float* img = p.outputs + (long long)b * p.img_stride;
-    float t[P24_TOPK];
-#pragma unroll
-    for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;
+    ok = true;
+    float lmax = P24_NEG_INF;
     for (int i0 = 0; i0 < lc; i0 += 128) {  // four independent loads per lane in flight
         float2 e[4];
 #pragma unroll
@@ -1325,22 +1349,20 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
         for (int u = 0; u < 4; ++u) {
             const bool apart = (__float_as_int(e[u].y) & 0x80000000) != 0;
             // bound = value + 2e-5 (+- 3e-6) for an all-apart pair: bound - 7e-5 is a certified lower bound
-            if (apart) top_insert_desc(t, e[u].x - 7e-5f);
+            if (apart) lmax = fmaxf(lmax, e[u].x - 7e-5f);
         }
     }
+    TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 2);
     float tref = rec[GT_T];
     {
-        float v10 = P24_NEG_INF;
-#pragma unroll 1
-        for (int r = 0; r < P24_TOPK; ++r) v10 = warp_pop_max(t);
-        tref = fmaxf(tref, v10);  // (v10 = -inf when fewer than 10 entries carry a lower bound)
+        const int r0 = lane_rank<true>(lmax);
+        const unsigned pick = __ballot_sync(0xffffffffu, r0 == P24_TOPK - 1);
+        const float v10 = __shfl_sync(0xffffffffu, lmax, pick ? __ffs(pick) - 1 : 0);
+        if (pick) tref = fmaxf(tref, v10);
     }
-#pragma unroll
-    for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;  // from here on: exact values (group leaders)
-    const unsigned gm = group_mask();
-    const int grp = lane >> 3, sub = lane & 7;
-    int nbuf = 0;
-    for (int i0 = 0; i0 < lc || nbuf > 0; i0 += 32) {
+    TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 3);
+    int nsurv = 0;
+    for (int i0 = 0; i0 < lc; i0 += 32) {
         const int i = i0 + lane;
         bool keep = false;
         int anchor = 0;
@@ -1350,29 +1372,78 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
             anchor = __float_as_int(e.y) & 0x7fffffff;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) S.surv[warp][nbuf + __popc(bal & ((1u << lane) - 1u))] = anchor;
-        nbuf += __popc(bal);
-        __syncwarp();
-        if (nbuf > TAIL_SURV - 32 || i0 + 32 >= lc) {  // evaluate the batch
-            for (int j0 = 0; j0 < nbuf; j0 += 4) {
-                const int j = j0 + grp;
-                float v = P24_NEG_INF;
-                if (j < nbuf) {
-                    v = group_pair_value(rec, img + (long long)S.surv[warp][j] * p.row_stride, gm);
-                    if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
-                }
-                if (sub == 0 && j < nbuf) top_insert_desc(t, v);
-            }
-            nbuf = 0;
-            __syncwarp();
+        const int at = nsurv + __popc(bal & ((1u << lane) - 1u));
+        if (keep && at < TAIL_SURV) S.surv[warp][at] = anchor;
+        nsurv += __popc(bal);
+    }
+    __syncwarp();
+#ifdef P24_TIMING
+    if (lane == 0) {
+        g_tstamp[2][1024 + b * 64 + (slot - b * p.Lmax)][8] = nsurv;
+        g_tstamp[2][1024 + b * 64 + (slot - b * p.Lmax)][9] = lc;
+    }
+#endif
+    if (nsurv > TAIL_SURV) {
+        ok = false;
+        return 0.0f;
+    }
+    // exact values, 16 survivors at a time: every 8-lane group requests the rows of its 4 pairs, then evaluates them
+    const unsigned gm = group_mask();
+    const int grp = lane >> 3, sub = lane & 7;
+    const float gcx = rec[GT_CX], gcy = rec[GT_CY];
+    for (int j0 = 0; j0 < nsurv; j0 += 16) {
+        float rp[4][3], pc[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 4 * u + grp;
+            const float* row = img + (long long)S.surv[warp][min(j, nsurv - 1)] * p.row_stride;
+            pc[u][0] = row[0];
+            pc[u][1] = row[1];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) rp[u][q] = row[2 + sub * 3 + q];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 4 * u + grp;
+            const float d = p24_centre_dist(gcx, gcy, pc[u][0], pc[u][1]);
+            float sm = 0.0f;
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) sm = sm + ray_loss(rec[GT_RG + sub * 3 + q], rp[u][q], d);
+            sm = group_sum(sm, gm);
+            float v = (sm / 24.0f) / 2.0f;
+            if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
+            if (sub == 0 && j < nsurv) S.sval[warp][j] = v;
         }
     }
+    __syncwarp();
+    TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 4);
+    // the kc largest by rank counting, then summed in descending order by one lane
+    float* top = reinterpret_cast<float*>(S.surv[warp]);  // (the anchors are no longer needed)
+    float mine[2];
+    int rk[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        mine[u] = j < nsurv ? S.sval[warp][j] : P24_NEG_INF;
+        rk[u] = 0;
+    }
+    for (int i = 0; i < nsurv; ++i) {
+        const float vi = S.sval[warp][i];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) rk[u] += kv_gt(vi, i, mine[u], lane + 32 * u) ? 1 : 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+        if (lane + 32 * u < nsurv && rk[u] < kc) top[rk[u]] = mine[u];
+    __syncwarp();
     float ksum = 0.0f;
-#pragma unroll 1
-    for (int r = 0; r < kc; ++r) {
-        const float v = warp_pop_max(t);
+    const int have = min(kc, nsurv);
+    for (int r = 0; r < have; ++r) {
+        const float v = top[r];
         ksum = ksum + (v == P24_POS_INF ? NAN : v);
     }
+    __syncwarp();
     return ksum;
 }
 
@@ -1413,13 +1484,18 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
         }
     }
     if (tid == 0) S.nuniq = 0;
+    if (tid < 26) S.acc[tid] = 0ull;
+    TMARK0(2, blockIdx.x, 0);
     __syncthreads();
+    TMARK0(2, blockIdx.x, 1);
 
     // ---- phase 1, one warp per GT (the image's GTs spread over the warps of the cluster): dynamic k from the GT's list,
     // then the k cheapest valid pairs -> claims (global) ---------------------------------------------------------------
-    for (int g = cr * TAIL_WARPS + warp; g < n; g += TAIL_CL * TAIL_WARPS) {
+    for (int g = warp * TAIL_CL + cr; g < n; g += TAIL_CL * TAIL_WARPS) {  // GT g -> CTA g % 8: spread over the cluster's SMs
         const int slot = b * p.Lmax + g;
+        TMARK(2, 1024 + b * 64 + g, 0);
         const int lc = __ldcg(&p.lcount[slot]);
+        TMARK(2, 1024 + b * 64 + g, 1);
         if (lane == 0) {
             p.lcount[slot] = 0;  // ready for the next call
             atomicMax(&p.status[ST_LISTMAX], lc);
@@ -1435,11 +1511,22 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
             if (lane < P24_TOPK) cl[lane] = -1;
             continue;
         }
-        const float ksum = warp_topk_sum_list(p, S, s_rec + g * GT_REC, b, slot, lc, kc);
+        bool ok;
+        const float ksum = warp_topk_sum_list(p, S, s_rec + g * GT_REC, b, slot, lc, kc, ok);
+        TMARK(2, 1024 + b * 64 + g, 5);
+        if (!ok) {
+            if (lane == 0) {
+                kreq[g] = -2;
+                atomicAdd(&p.rare[b], 1);
+            }
+            if (lane < P24_TOPK) cl[lane] = -1;
+            continue;
+        }
         int k = (int)ksum;  // dynamic k = clamp(int(sum of the top-kc values), min=1)   losses.py:454-456
         if (k < 1) k = 1;
         const int kk = min(k, ncand);  // torch.topk would raise beyond the candidate count; clamp instead
-        const int take = warp_select_claims(p, b, g, kk, cl);
+        const int take = warp_select_claims(p, S, b, g, kk, cl);
+        TMARK(2, 1024 + b * 64 + g, 6);
         if (lane == 0) {
             p.dyn_k[slot] = kk;
             ntake[g] = take;
@@ -1449,8 +1536,10 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
     }
     if (cr == 0)
         for (int g = n + tid; g < p.Lmax; g += TAIL_THREADS) p.dyn_k[b * p.Lmax + g] = 0;
+    TMARK0(2, blockIdx.x, 2);
     __threadfence();
     cluster_sync_all();
+    TMARK0(2, blockIdx.x, 3);
     // ---- rare paths, the cluster's first CTA, one GT at a time -----------------------------------------------------
     if (__ldcg(&p.rare[b]) > 0) {  // (the same value in every CTA of the cluster: written before the barrier)
         if (cr == 0) {
@@ -1464,7 +1553,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
                 const int kk = min(k, ncand);
                 __syncthreads();
                 if (warp == 0) {
-                    const int take = warp_select_claims(p, b, g, kk, claimg + g * P24_TOPK);
+                    const int take = warp_select_claims(p, S, b, g, kk, claimg + g * P24_TOPK);
                     if (lane == 0) {
                         p.dyn_k[b * p.Lmax + g] = kk;
                         ntake[g] = take;
@@ -1491,27 +1580,38 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
     }
     // ---- phase 2: every CTA looks at all claims of the image and owns a slice of the slots: the distinct claimed anchors
     // (first claim of every anchor) of its slice and whether several GTs claim them -------------------------------------
+    TMARK0(2, blockIdx.x, 4);
     const int nslots = n * P24_TOPK;
     for (int t = tid; t < nslots; t += TAIL_THREADS) claim[t] = __ldcg(claimg + t);
     __syncthreads();
-    for (int t = cr * cap + tid; t < min(nslots, (cr + 1) * cap); t += TAIL_THREADS) {
-        const int a = claim[t];
-        if (a < 0) continue;
-        bool first = true, multi = false;
-        for (int j = 0; j < nslots; ++j) {
-            if (j != t && claim[j] == a) {
-                multi = true;
-                if (j < t) first = false;
+    {
+        const unsigned gm = group_mask();
+        const int sub = tid & 7;
+        const int tend = min(nslots, (cr + 1) * cap);
+        for (int t0 = cr * cap; t0 < tend; t0 += TAIL_THREADS / 8) {
+            const int t = t0 + (tid >> 3);
+            const int a = t < tend ? claim[t] : -1;
+            int first = 1, multi = 0;
+            if (a >= 0) {
+                for (int j = sub; j < nslots; j += 8) {
+                    if (j != t && claim[j] == a) {
+                        multi = 1;
+                        if (j < t) first = 0;
+                    }
+                }
             }
-        }
-        if (first) {
-            const int e = atomicAdd(&S.nuniq, 1);
-            uniq[e] = t | (multi ? 0x40000000 : 0);
-            best[e] = ~0ull;
+            multi = group_sum_i(multi, gm);
+            first = group_sum_i(first, gm);
+            if (a >= 0 && first == 8 && sub == 0) {
+                const int e = atomicAdd(&S.nuniq, 1);
+                uniq[e] = t | (multi ? 0x40000000 : 0);
+                best[e] = ~0ull;
+            }
         }
     }
     __syncthreads();
     const int nuniq = S.nuniq;
+    TMARK0(2, blockIdx.x, 5);
     if (tid == 0 && nuniq) atomicAdd(&p.num_fg[b], nuniq);  // every claimed anchor ends up foreground (losses.py:479)
 
     // ---- phase 3a: anchors claimed by several GTs: argmin of the cost over ALL GTs (losses.py:471-476).  Valid pairs
@@ -1548,65 +1648,99 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
         }
     }
     __syncthreads();
+    TMARK0(2, blockIdx.x, 6);
 
-    // ---- phase 3c, one warp per claimed anchor: outputs and loss terms (lanes over rays / classes).
+    // ---- phase 3c, one 8-lane group per claimed anchor: outputs and loss terms (3 rays and every 8th class per lane).
     // Contributions are accumulated as fixed-point integers: the sums do not depend on the order. -----------------------
-    long long acc = 0;  // lane k < 24: sum of loss24[:, k]; lane 24: -sum of obj logits at fg; lane 25: cls BCE
-    for (int e = warp; e < nuniq; e += TAIL_WARPS) {
-        const int u = uniq[e];
-        const int t = u & 0x3FFFFFFF;
-        const int aa = claim[t];
-        int g = t / P24_TOPK;
-        const float* row = stage ? rows + e * ROW_PAD : img + (long long)aa * p.row_stride;
-        if (u & 0x40000000) {
-            const unsigned long long bb = best[e];
-            // without any valid pair (every claim came from a spill) the penalised costs are evaluated here
-            g = bb != ~0ull ? (int)(bb & 0xFFFFFFFFull) : resolve_conflict(p, s_rec, n, row);
-        }
-        const float* rec = s_rec + g * GT_REC;
-        float l;
-        const float v = warp_pair_value(rec, row, l);  // pair value == pred_ious_this_matching (losses.py:491)
-        if (lane == 0) {
-            const long long o = (long long)b * p.A + aa;
-            p.fg_mask[o] = 1;
-            p.matched_gt[o] = g;
-            p.pred_iou[o] = v;
-        }
-        double contrib = (double)l;
-        long long fx = 0;
-        if (p.sums28) {
-            // sum_j BCEWithLogits(x_j, t_j), t = v at the GT class and 0 elsewhere (losses.py:246-248, 298-302):
-            // sum_j softplus(x_j) - x_c * v; the softplus sum as the log of a per-lane product (one log per lane;
-            // the product of a lane's factors is restarted before it can overflow)
-            const int c = gt_class(rec, p.nc);
-            float prod = 1.0f, big = 0.0f;
-            for (int j = lane; j < p.nc; j += 32) {
-                const float x = row[27 + j];
-                if (x < 8.0f) {
-                    prod *= 1.0f + __expf(x);
-                    if (prod > 1.0e30f) {
-                        big += logf(prod);
-                        prod = 1.0f;
-                    }
+    {
+        const unsigned gm = group_mask();
+        const int sub = tid & 7;
+        long long acc_r[3] = {0, 0, 0};   // sum of loss24[:, 3 sub + q]
+        long long acc_o = 0, acc_c = 0;   // -sum of obj logits at fg; cls BCE (group leaders)
+        for (int e = tid >> 3; e < nuniq; e += TAIL_THREADS / 8) {
+            const int u = uniq[e];
+            const int t = u & 0x3FFFFFFF;
+            const int aa = claim[t];
+            int g = t / P24_TOPK;
+            const float* row = stage ? rows + e * ROW_PAD : img + (long long)aa * p.row_stride;
+            if (u & 0x40000000) {
+                const unsigned long long bb = best[e];
+                if (bb != ~0ull) {
+                    g = (int)(bb & 0xFFFFFFFFull);
                 } else {
-                    big += x + log1pf(expf(-x));
+                    // without any valid pair (every claim came from a spill) the penalised costs decide: argmin over all
+                    // GTs (losses.py:471-476), first index on ties.  Rare.
+                    const float eo1 = 1.0f + expf(-row[26]);
+                    const float neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
+                    KV bst = {P24_POS_INF, 0x7fffffff};
+                    for (int gg = 0; gg < n; ++gg) {
+                        const float* rc = s_rec + gg * GT_REC;
+                        const float vv = group_pair_value(rc, row, gm);
+                        const float c = p24_cost(cls_cost_from(neg, row[27 + gt_class(rc, p.nc)], 1.0f / eo1), vv, false);
+                        if (kv_lt(c, gg, bst.v, bst.i)) {
+                            bst.v = c;
+                            bst.i = gg;
+                        }
+                    }
+                    g = bst.i != 0x7fffffff ? bst.i : 0;
                 }
             }
-            big += logf(prod);
-            big = warp_sum(big);
-            if (lane == 24) fx = __double2ll_rn(-(double)row[26] * FIX_SCALE_OBJ);
-            if (lane == 25) contrib = (double)big - (double)row[27 + c] * (double)v;
-        }
-        if (lane < 24 || lane == 25) fx = to_fix(contrib);
-        if (lane < 26) acc += fx;
-    }
-    if (lane < 26) S.acc[warp][lane] = acc;
-    __syncthreads();
-    if (tid < 26 && p.sums28) {
-        long long t = 0;
+            const float* rec = s_rec + g * GT_REC;
+            const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], row[0], row[1]);
+            float l[3], sm = 0.0f;
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) {
+                l[q] = ray_loss(rec[GT_RG + sub * 3 + q], row[2 + sub * 3 + q], d);
+                sm = sm + l[q];
+            }
+            sm = group_sum(sm, gm);
+            const float v = (sm / 24.0f) / 2.0f;  // pair value == pred_ious_this_matching (losses.py:491)
+            if (sub == 0) {
+                const long long o = (long long)b * p.A + aa;
+                p.fg_mask[o] = 1;
+                p.matched_gt[o] = g;
+                p.pred_iou[o] = v;
+            }
 #pragma unroll
-        for (int w = 0; w < TAIL_WARPS; ++w) t += S.acc[w][tid];
-        if (t != 0) atomicAdd((unsigned long long*)&p.acc_fix[tid], (unsigned long long)t);
+            for (int q = 0; q < 3; ++q) acc_r[q] += to_fix((double)l[q]);
+            if (p.sums28) {
+                // sum_j BCEWithLogits(x_j, t_j), t = v at the GT class and 0 elsewhere (losses.py:246-248, 298-302):
+                // sum_j softplus(x_j) - x_c * v; the softplus sum as the log of a per-lane product (one log per lane;
+                // the product of a lane's factors is restarted before it can overflow)
+                const int c = gt_class(rec, p.nc);
+                float prod = 1.0f, big = 0.0f;
+                for (int j = sub; j < p.nc; j += 8) {
+                    const float x = row[27 + j];
+                    if (x < 8.0f) {
+                        prod *= 1.0f + __expf(x);
+                        if (prod > 1.0e30f) {
+                            big += logf(prod);
+                            prod = 1.0f;
+                        }
+                    } else {
+                        big += x + log1pf(expf(-x));
+                    }
+                }
+                big += logf(prod);
+                big = group_sum(big, gm);
+                if (sub == 0) {
+                    acc_o += __double2ll_rn(-(double)row[26] * FIX_SCALE_OBJ);
+                    acc_c += to_fix((double)big - (double)row[27 + c] * (double)v);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (acc_r[q] != 0) atomicAdd(&S.acc[sub * 3 + q], (unsigned long long)acc_r[q]);
+        if (acc_o != 0) atomicAdd(&S.acc[24], (unsigned long long)acc_o);
+        if (acc_c != 0) atomicAdd(&S.acc[25], (unsigned long long)acc_c);
+    }
+    TMARK0(2, blockIdx.x, 7);
+    __syncthreads();
+    TMARK0(2, blockIdx.x, 8);
+    if (tid < 26 && p.sums28) {
+        const unsigned long long t = S.acc[tid];
+        if (t != 0) atomicAdd((unsigned long long*)&p.acc_fix[tid], t);
     } else if (tid == 26 && p.sums28 && nuniq) {
         atomicAdd((unsigned long long*)&p.acc_fix[26], (unsigned long long)nuniq);
     } else if (tid == 27 && p.sums28 && cr == 0) {
@@ -1619,6 +1753,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
         S.last = (done == (unsigned)(p.B * TAIL_CL) - 1u) ? 1 : 0;
     }
     __syncthreads();
+    TMARK0(2, blockIdx.x, 9);
     if (!S.last) return;
     __threadfence();
     // ---- last CTA of the grid: the batch sums (integer adds: exact, order independent), per-image counters reset, then
@@ -1901,3 +2036,9 @@ extern "C" int p24_loss_finalize(const float* sums28, float* state26, float* res
     k_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(sums28, state26, result54, weights_n27);
     return (int)cudaGetLastError();
 }
+
+#ifdef P24_TIMING
+extern "C" int p24_debug_read_timers(unsigned long long* h_out) {
+    return (int)cudaMemcpyFromSymbol(h_out, g_tstamp, sizeof(unsigned long long) * 3 * TM_ROWS * TM_SLOTS);
+}
+#endif

@@ -15,12 +15,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.abspath(os.path.join(HERE, "..", "csrc"))
 INCLUDE = os.path.abspath(os.path.join(HERE, "..", "..", "include"))
 LIBDIR = os.path.join(HERE, "_lib")
-LIBNAME = "libp24_b200.so"
+LIBNAME = "libp24_b200_timing.so" if os.environ.get("P24_TIMING") else "libp24_b200.so"
 
 # -fmad=false: the SimOTA decisions are fp32 threshold tests evaluated in the reference's operation
 # order (one rounding per op, like eager PyTorch); bounds / backward code uses explicit fmaf.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
-              "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+              "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"] + \
+             (["-DP24_TIMING"] if os.environ.get("P24_TIMING") else [])  # debug build: phase timers (tests/tools/timeline.py)
 
 
 def _nvcc() -> str:
@@ -51,7 +52,7 @@ def lib_path() -> str:
 
 
 def is_fresh() -> bool:
-    stamp = os.path.join(LIBDIR, "build.stamp")
+    stamp = os.path.join(LIBDIR, LIBNAME + ".stamp")
     if not (os.path.exists(lib_path()) and os.path.exists(stamp)):
         return False
     with open(stamp) as fh:
@@ -80,7 +81,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 print(res.stdout + res.stderr)
             os.replace(tmp, lib_path())
-            with open(os.path.join(LIBDIR, "build.stamp"), "w") as fh:
+            with open(os.path.join(LIBDIR, LIBNAME + ".stamp"), "w") as fh:
                 fh.write(_fingerprint())
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)

@@ -1,71 +1,85 @@
-"""Debug tool (GPU box): per-kernel CTA start / end distribution of one step from the -DP24_TIMING build
-(nvcc ... -DP24_TIMING -o p24/_lib/libp24_timing.so).  Usage: timeline.py [flags] [B size G Lmax]"""
-import ctypes, os, sys
-import numpy as np
+"""Phase timeline of the training chain from the debug build (P24_TIMING=1 python tests/tools/timeline.py [workload]).
+%globaltimer stamps written by the kernels at phase boundaries; prints where the time of k_pass / k_tail goes."""
+import ctypes
+import os
+import sys
+
+os.environ["P24_TIMING"] = "1"
 ROOT = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
-sys.path.insert(0, os.path.join(ROOT, "exploration-of-potential_b200")); sys.path.insert(0, ROOT)
-import torch
-from p24 import lib as p24_lib
-from p24 import synth
-lib = p24_lib.load(os.path.join(ROOT, "exploration-of-potential_b200", "p24", "_lib", "libp24_timing.so"))
-p24_lib._LIB = lib
-from p24.losses import Loss_Function
-B, size, G, Lmax = 20, 640, 20, 50
-flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-if len(sys.argv) > 5:
-    B, size, G, Lmax = [int(x) for x in sys.argv[2:6]]
-dev = "cuda:0"
-SEED0 = int(os.environ.get("P24_SEED0", "1"))  # bench.py rank r uses 1 + 1000 r
-sets = [(synth.make_head_outputs(B, size, 80, seed=SEED0 + 100 * i).to(dev),
-         synth.make_labels(B, G, Lmax, size, 80, seed=SEED0 + 100 * i, kind="smooth").to(dev)) for i in range(5)]
-xs, ys, ss = synth.make_grids(size)
+sys.path.insert(0, os.path.join(ROOT, "exploration-of-potential_b200"))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from p24 import lib as p24_lib, synth  # noqa: E402
+from p24.losses import Loss_Function  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "train"
+wl = bench.TRAIN_WORKLOADS[name]
+B = wl["B"] or 20
+dev = torch.device("cuda:0")
+sets = []
+for i in range(3):
+    s = wl["seed"] + 100 * i
+    sets.append((synth.make_head_outputs(B, wl["size"], 80, seed=s).to(dev),
+                 synth.make_labels(B, wl["G"], wl["Lmax"], wl["size"], 80, seed=s, kind=wl["kind"]).to(dev)))
+xs, ys, ss = synth.make_grids(wl["size"])
 g = [[t.to(dev) for t in l] for l in (xs, ys, ss)]
 lf = Loss_Function(80)
-for i in range(10):
-    lf.forward_async((g[0], g[1], g[2], sets[i % 5][0], []), sets[i % 5][1], flags=flags)
+lf.reuse_buffers = True
+lib = p24_lib.load()
+for i in range(6):
+    lf.forward_async((g[0], g[1], g[2], sets[i % 3][0], []), sets[i % 3][1])
 torch.cuda.synchronize()
-buf = np.zeros((6, 4096, 20), dtype=np.uint64)
-lib.p24_debug_read_timers.argtypes = [ctypes.c_void_p]
-assert lib.p24_debug_read_timers(buf.ctypes.data) == 0
-t = buf.astype(np.int64)
-# (timer bank, name, slots in order)
-order = [(3, "k_gt_prep", ["start", "end"]),
-         (0, "k_pass/anchor", ["start", "wait", "recs+rows", "gt loop", "items", "end"]),
-         (4, "k_pass/window", ["start", "end"]),
-         (1, "k_match", ["start", "wait", "load", None, "bracket", "dyn_k", "select"]),
-         (2, "k_resolve_loss", ["start", "wait", None, None, "entries", "partials"])]
-base = None
-pct = lambda x: "min %7.1f p10 %7.1f p50 %7.1f p90 %7.1f max %7.1f" % tuple(np.percentile(x, [0, 10, 50, 90, 100]))
-for k, nm, slots in order:
-    tt = t[k]
-    last = max(i for i, s in enumerate(slots) if s)
-    ok = (tt[:, 0] > 0) & (tt[:, last] > 0)
-    if not ok.any():
-        print(nm, "no data"); continue
-    if base is None:
-        base = tt[ok, 0].min()
-    print(f"== {nm}: {int(ok.sum())} CTAs")
-    print(f"   start  {pct((tt[ok, 0] - base) / 1e3)}")
-    print(f"   end    {pct((tt[ok, last] - base) / 1e3)}")
-    prev = 0
-    for i in range(1, last + 1):
-        if not slots[i]:
-            continue
-        v = ok & (tt[:, i] > 0) & (tt[:, prev] > 0)
-        d = (tt[v, i] - tt[v, prev]) / 1e3
-        if d.size:
-            print(f"   {slots[i]:10s} mean {d.mean():7.2f}  {pct(d)}")
-        prev = i
-    if k == 1:
-        slow = tt[:, 8]
-        sl = ok & (slow != 0)
-        print("   slow-path CTAs:", int(sl.sum()), "kinds", slow[sl].tolist())
-        f32 = lambda x: np.array(x, dtype=np.uint64).astype(np.uint32).view(np.float32)
-        for ci in np.nonzero(sl)[0]:
-            print("      slow GT", int(ci), "L", f32(t[1, ci, 12]), "U", f32(t[1, ci, 13]), "tmax", f32(t[1, ci, 14]), "rgmax", f32(t[1, ci, 15]))
-        for ci in np.nonzero(sl)[0]:
-            r = t[1, ci]
-            print(f"      slow GT {int(ci)}: segments {r[9]} candidates {r[10]} examined segments {r[11]} survivors {r[7]} | seg scan {(r[16]-r[4])/1e3:.1f} bounds {(r[17]-r[16])/1e3:.1f} "
-                  f"threshold {(r[18]-r[17])/1e3:.1f} exact {(r[19]-r[18])/1e3:.1f} rest {(r[5]-r[19])/1e3:.1f} us")
-        wid = f32(t[1][ok][:, 13]) - f32(t[1][ok][:, 12])
-        print("   bracket width U-L quantiles (10/50/90/99 %):", np.percentile(wid, [10, 50, 90, 99]))
+ROWS, SLOTS = 8192, 16
+buf = np.zeros((3, ROWS, SLOTS), dtype=np.uint64)
+fn = lib.p24_debug_read_timers
+fn.restype = ctypes.c_int
+fn.argtypes = [ctypes.c_void_p]
+assert fn(buf.ctypes.data) == 0
+A = sum((wl["size"] // s) ** 2 for s in (8, 16, 32))
+tiles = (A + 255) // 256
+kp = buf[1].astype(np.float64)
+kt = buf[2].astype(np.float64)
+t0 = kp[6000:6000 + 1024, 0]
+t0 = t0[t0 > 0].min()
+
+
+def us(x):
+    return (x - t0) / 1e3
+
+
+def stat(label, d):
+    d = np.asarray(d) / 1e3
+    if d.size:
+        print(f"   {label:18s} mean {d.mean():7.2f}  p50 {np.median(d):7.2f}  max {d.max():7.2f}  (n={d.size})")
+
+
+print(f"== k_pass: CTAs past pdl_wait at 0 us; last CTA end {us(kp[6000:7024, 1].max()):.1f} us")
+sd = kp[4096:4096 + B * wl["G"]]
+ok = sd[:, 1] > 0
+print(f"   seed items: first start {us(sd[ok, 0].min()):.1f}  last end {us(sd[ok, 1].max()):.1f}")
+stat("seed item", sd[ok, 1] - sd[ok, 0])
+tl = kp[:min(B * tiles, 4095)]
+print(f"   tiles: first start {us(tl[:, 0].min()):.1f}  last end {us(tl[:, 7].max()):.1f}")
+for lab, a, b_ in [("pre", 0, 1), ("wait seeds", 1, 2), ("recs+rows", 2, 3), ("gt loop+lists", 3, 4), ("poly items", 4, 5),
+                   ("far list", 5, 6), ("far items+out", 6, 7), ("tile total", 0, 7)]:
+    stat(lab, tl[:, b_] - tl[:, a])
+if B * tiles < 4000:
+    wn = kp[B * tiles:min(4095, B * tiles + B * wl["G"] * 3)]
+    ok = (wn[:, 0] > 0) & (wn[:, 7] > 0)
+    print(f"   window items: first start {us(wn[ok, 0].min()):.1f}  last end {us(wn[ok, 7].max()):.1f}")
+    stat("window item", wn[ok, 7] - wn[ok, 0])
+c = kt[:B * 8]
+tt0 = c[:, 0].min()
+print(f"== k_tail: first CTA start {us(tt0):.1f} us, last end {us(c[:, 9].max()):.1f} us")
+for lab, a, b_ in [("stage recs", 0, 1), ("phase 1 (own GTs)", 1, 2), ("cluster barrier", 2, 3), ("rare", 3, 4), ("phase 2", 4, 5),
+                   ("phase 3a/b", 5, 6), ("phase 3c", 6, 7), ("reduce wait", 7, 8), ("atomics+ticket", 8, 9), ("CTA total", 0, 9)]:
+    stat(lab, c[:, b_] - c[:, a])
+gt = np.concatenate([kt[1024 + b * 64:1024 + b * 64 + wl["G"]] for b in range(B)]) if wl["G"] <= 64 else kt[1024:1024 + 64]
+for lab, a, b_ in [("lcount RT", 0, 1), ("list pass A", 1, 2), ("threshold", 2, 3), ("pass B + exact", 3, 4), ("sum", 4, 5),
+                   ("claims", 5, 6), ("GT total", 0, 6)]:
+    stat(lab, gt[:, b_] - gt[:, a])
+print(f"   survivors per GT mean {gt[:, 8].mean():.1f} max {gt[:, 8].max():.0f}; list length mean {gt[:, 9].mean():.1f} max {gt[:, 9].max():.0f}")
+print(f"   GT start offsets from kernel start: mean {((gt[:, 0] - tt0) / 1e3).mean():.2f} max {((gt[:, 0] - tt0) / 1e3).max():.2f}")
