@@ -15,7 +15,7 @@
 #define P24_WT_HDR (P24_WSLOTS * P24_MAX_LEVELS)   // wtab row: [slot costs | ix0, iy0 per level (int bits)]
 #define P24_WT_STRIDE (P24_WT_HDR + 2 * P24_MAX_LEVELS + 4)   // 208 floats
 #define P24_WARPS (P24_THREADS / 32)
-#define P24_LISTCAP 1024   // entries a GT's top-10 list can hold (more -> brute-force path of k_tail)
+#define P24_LISTCAP 2048   // entries a GT's top-10 list can hold (more -> brute-force path of k_tail)
 
 // ---- per-GT record (floats): k_prep writes it, the seed items of k_pass add [4] and [58] ----------------------
 // [0] cx  [1] cy  [2] rin2  [3] rrej2   (one 128-bit shared-memory load for the per-pair tests)

@@ -343,7 +343,8 @@ __device__ __forceinline__ float warp_bound_Hstar(float rg_lane, float d) {
 // -------------------------------------------------------------------------------------------
 #define SEED_FAR 3
 #define SEED_DISC 3                                    // points per (far GT, level): centre, far end of the inscribed disc, 2 strides out
-#define SEED_NV (3 * P24_WARPS)                        // polygon vertices (of any GT of the image) far from this GT: 3 per warp
+#define SEED_VPW 6
+#define SEED_NV (SEED_VPW * P24_WARPS)                 // polygon vertices (of any GT of the image) far from this GT: 6 per warp
 #define SEED_MAX (SEED_FAR * P24_MAX_LEVELS * SEED_DISC + SEED_NV * P24_MAX_LEVELS)   // 132 <= P24_THREADS
 
 struct SeedShared {
@@ -415,18 +416,18 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
             for (int i = tid; i < n * P24_RAYS; i += P24_THREADS) {
                 const int h = i / P24_RAYS, k = i - h * P24_RAYS;
                 const float* r = recs + h * GT_REC;
-                const float dx = r[GT_VX + k] - gcx, dy = r[GT_VY + k] - gcy;
+                const float dx = __ldcg(r + GT_VX + k) - gcx, dy = __ldcg(r + GT_VY + k) - gcy;
                 const float d2 = fmaf(dx, dx, dy * dy);
                 if (d2 > best) {
                     best = d2;
                     bi = (h << 5) | k;
                 }
             }
-            // the warp's three farthest picks (any subset of far vertices serves: better ones only tighten T)
+            // the warp's SEED_VPW farthest picks (any subset of far vertices serves: better ones only tighten T)
 #pragma unroll 1
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < SEED_VPW; ++r) {
                 const KV w = warp_select<true>(KV{bi >= 0 ? best : P24_NEG_INF, bi >= 0 ? bi : 0x7fffffff});
-                if (lane == 0) S.vsel[warp * 3 + r] = w.i == 0x7fffffff ? -1 : w.i;
+                if (lane == 0) S.vsel[warp * SEED_VPW + r] = w.i == 0x7fffffff ? -1 : w.i;
                 if (bi == w.i) bi = -1;
             }
             S.hash[tid] = -1;
@@ -494,12 +495,15 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
                     // a certified LOWER bound of the pair value: when every ray is in the "apart" branch (the reference's
                     // own fp32 comparison) the value has the closed form (1/48) sum_k (2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2),
                     // evaluated in fast arithmetic to within 3e-6; other pairs are evaluated exactly
+                    float rpv[P24_RAYS];
+#pragma unroll
+                    for (int k = 0; k < P24_RAYS; ++k) rpv[k] = row[2 + k];  // one round trip for the whole row
                     const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
                     float sm = 0.0f;
                     bool apart = true;
-#pragma unroll 4
+#pragma unroll
                     for (int k = 0; k < P24_RAYS; ++k) {
-                        const float rg = S.rec[GT_RG + k], rp = row[2 + k];
+                        const float rg = S.rec[GT_RG + k], rp = rpv[k];
                         apart = apart && (d >= rg + rp) && (rp >= 0.25f);
                         const float t = (rg + rp) + d;
                         sm += 2.0f - __fdividef(4.0f * fmaf(rg, rg, rp * rp), t * t);
@@ -546,27 +550,35 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
         if (tid == 0) S.T = P24_NEG_INF;
         __syncthreads();
     }
-    // ---- far2: pairs closer than D cannot reach T.  Bisection on H*(d) + 3e-5 < T (monotone in d): warp 0 -----------
+    // ---- far2: pairs closer than D cannot reach T.  H*(d) + 3e-5 < T is monotone in d: three rounds of a 32-way search by
+    // warp 0, every lane evaluating the bound at its own distance ------------------------------------------------------
     if (warp == 0) {
         const float T = S.T;
         float far2 = 0.0f;  // 0: every pair is evaluated
         if (T > P24_NEG_INF) {
-            const float rg = lane < P24_RAYS ? S.rec[GT_RG + lane] : 0.0f;
-            float lo = 0.0f, hi = 8192.0f;  // (pairs farther apart than hi are always evaluated)
-            if (warp_bound_Hstar(rg, lo) + 3e-5f < T) {
-                if (warp_bound_Hstar(rg, hi) + 3e-5f < T) {
-                    lo = hi;  // (cannot happen: the seeds themselves obey the bound)
-                } else {
+            float lo = 0.0f, step = 256.0f;  // pairs farther apart than 32 * 256 px are always evaluated
 #pragma unroll 1
-                    for (int it = 0; it < 20; ++it) {
-                        const float mid = 0.5f * (lo + hi);
-                        if (warp_bound_Hstar(rg, mid) + 3e-5f < T) lo = mid;
-                        else hi = mid;
-                    }
+            for (int round = 0; round < 3; ++round) {
+                const float dd = lo + step * (float)lane;
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < P24_RAYS; ++k) {
+                    const float rg = S.rec[GT_RG + k];
+                    const float q = rg + dd;
+                    sum += fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, fmaf(q, q, rg * rg)));
                 }
-                const float D = fmaxf(0.0f, lo * (1.0f - 1e-4f) - 0.02f);
-                far2 = D * D;
+                const bool below = sum * (1.0f / 48.0f) + 3e-5f < T;      // true for a prefix of the lanes (monotone)
+                const unsigned bal = __ballot_sync(0xffffffffu, below);
+                const int nb = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;  // length of the leading run of lanes
+                if (nb == 0) {
+                    step = 0.0f;  // even lo is not below: D = lo
+                    break;
+                }
+                lo = lo + step * (float)(nb - 1);
+                step = step * (1.0f / 32.0f);
             }
+            const float D = fmaxf(0.0f, lo * (1.0f - 1e-4f) - 0.02f);
+            far2 = D * D;
             if (!(far2 == far2)) far2 = 0.0f;
         }
         if (lane == 0) {
@@ -1362,19 +1374,21 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
     }
     TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 3);
     int nsurv = 0;
-    for (int i0 = 0; i0 < lc; i0 += 32) {
-        const int i = i0 + lane;
-        bool keep = false;
-        int anchor = 0;
-        if (i < lc) {
-            const float2 e = __ldcg(lst + i);
-            keep = !(e.x < tref);
-            anchor = __float_as_int(e.y) & 0x7fffffff;
+    for (int i0 = 0; i0 < lc; i0 += 256) {  // eight independent loads per lane in flight
+        float2 e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u + lane;
+            e[u] = i < lc ? __ldcg(lst + i) : make_float2(P24_NEG_INF, 0.0f);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        const int at = nsurv + __popc(bal & ((1u << lane) - 1u));
-        if (keep && at < TAIL_SURV) S.surv[warp][at] = anchor;
-        nsurv += __popc(bal);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool keep = !(e[u].x < tref);
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const int at = nsurv + __popc(bal & ((1u << lane) - 1u));
+            if (keep && at < TAIL_SURV) S.surv[warp][at] = __float_as_int(e[u].y) & 0x7fffffff;
+            nsurv += __popc(bal);
+        }
     }
     __syncwarp();
 #ifdef P24_TIMING
