@@ -47,6 +47,7 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 #define ST_WAITCYC 4    // clock cycles the last fused all-reduce waited for its peers
 #define ST_LISTSUM 5    // list entries seen (cumulative) ...
 #define ST_GTS 6        // ... over this many GTs
+#define ST_EXACT 7      // GTs whose dynamic k needed exact pair values (the bound bracket straddled an integer)
 #define ST_WORDS 8
 
 struct P24Workspace {

@@ -36,7 +36,8 @@
 namespace {
 
 struct Level {
-    int off, W, H, pad;  // anchors [off, off + W * H) form a W x H grid, row-major (yolo_head_24p.py:222-230)
+    int off, W, H;  // anchors [off, off + W * H) form a W x H grid, row-major (yolo_head_24p.py:222-230)
+    float st;       // the level's stride (expanded_strides of its anchors)
 };
 
 struct Params {
@@ -145,6 +146,19 @@ __device__ __forceinline__ int group_sum_i(int v, unsigned m) {
     v += __shfl_xor_sync(m, v, 2);
     v += __shfl_xor_sync(m, v, 4);
     return v;
+}
+
+// rank of the lane's value among the 32 lanes' values (0 = largest when MAX; ties -> lower lane first)
+template <bool MAX>
+__device__ __forceinline__ int lane_rank(float v) {
+    const int lane = threadIdx.x & 31;
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float o = __shfl_sync(0xffffffffu, v, j);
+        rank += (MAX ? kv_gt(o, j, v, lane) : kv_lt(o, j, v, lane)) ? 1 : 0;
+    }
+    return rank;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -354,7 +368,9 @@ struct SeedShared {
     int hash[256];            // distinct seed anchors
     float val[SEED_MAX];
     int anc[SEED_MAX];
-    int nfar, nvert;
+    float top[P24_WARPS * P24_TOPK];
+    float tmp[P24_WARPS * P24_TOPK];
+    int nvert, ntmp;
     float T;
 };
 
@@ -364,7 +380,7 @@ __device__ __forceinline__ int cell_index(float q, float st) {
     return (int)v;
 }
 
-__device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
+__device__ void seed_part(const Params& p, SeedShared& S, int b, int g, int dbg_row = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.num_gt[b];
     const float* recs = p.gt_rec + (long long)b * p.Lmax * GT_REC;
@@ -379,37 +395,25 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
     const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
     const bool filter = !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && S.rec[GT_RGMAX] < 1.0e6f;
     if (filter) {
-        // ---- the SEED_FAR farthest GTs (centre distance + their largest ray), this GT included: warp 0 ----------
+        // ---- the SEED_FAR farthest GTs (centre distance + their largest ray), this GT included: warp 0, every lane's best
+        // by rank among the lanes ------------------------------------------------------------------------------------------
         if (warp == 0) {
-            float k0 = P24_NEG_INF, k1 = P24_NEG_INF, k2 = P24_NEG_INF;  // the lane's best keys
-            int h0 = -1, h1 = -1, h2 = -1;
+            float key = P24_NEG_INF;
+            int hb = -1;
             for (int h = lane; h < n; h += 32) {
                 const float* r = recs + h * GT_REC;
-                const float dx = r[GT_CX] - gcx, dy = r[GT_CY] - gcy;
-                float key = sqrtf(fmaf(dx, dx, dy * dy)) + r[GT_RGMAX];
-                int hh = h;
-                if (!(key == key)) continue;
-                if (key > k0 || h0 < 0) { const float t = k0; k0 = key; key = t; const int u = h0; h0 = hh; hh = u; }
-                if (hh >= 0 && (key > k1 || h1 < 0)) { const float t = k1; k1 = key; key = t; const int u = h1; h1 = hh; hh = u; }
-                if (hh >= 0 && (key > k2 || h2 < 0)) { k2 = key; h2 = hh; }
-            }
-            int nf = 0;
-#pragma unroll 1
-            for (int r = 0; r < SEED_FAR; ++r) {
-                const KV best = warp_select<true>(KV{h0 >= 0 ? k0 : P24_NEG_INF, h0 >= 0 ? h0 : 0x7fffffff});
-                if (best.i == 0x7fffffff) break;
-                if (h0 == best.i) {  // pop
-                    k0 = k1; h0 = h1;
-                    k1 = k2; h1 = h2;
-                    h2 = -1;
+                const float dx = __ldcg(r + GT_CX) - gcx, dy = __ldcg(r + GT_CY) - gcy;
+                const float kk = sqrtf(fmaf(dx, dx, dy * dy)) + __ldcg(r + GT_RGMAX);
+                if (kk > key) {
+                    key = kk;
+                    hb = h;
                 }
-                if (lane == 0) S.far[r] = best.i;
-                ++nf;
             }
-            if (lane == 0) S.nfar = nf;
+            const int rk = lane_rank<true>(hb >= 0 ? key : P24_NEG_INF);
+            if (rk < SEED_FAR) S.far[rk] = hb;   // (-1: fewer GTs than SEED_FAR)
         }
-        // ---- the SEED_NV polygon vertices of the image that are farthest from this GT's centre (every thread keeps the
-        // farthest of its share, then the block ranks the threads' picks) ----------------------------------------------
+        // ---- polygon vertices of the image that are far from this GT's centre: every thread keeps the farthest of its
+        // share, every warp passes on its SEED_VPW farthest (any subset of far vertices serves: better ones only tighten T)
         {
             float best = P24_NEG_INF;
             int bi = -1;
@@ -423,18 +427,14 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
                     bi = (h << 5) | k;
                 }
             }
-            // the warp's SEED_VPW farthest picks (any subset of far vertices serves: better ones only tighten T)
-#pragma unroll 1
-            for (int r = 0; r < SEED_VPW; ++r) {
-                const KV w = warp_select<true>(KV{bi >= 0 ? best : P24_NEG_INF, bi >= 0 ? bi : 0x7fffffff});
-                if (lane == 0) S.vsel[warp * SEED_VPW + r] = w.i == 0x7fffffff ? -1 : w.i;
-                if (bi == w.i) bi = -1;
-            }
+            const int rk = lane_rank<true>(bi >= 0 ? best : P24_NEG_INF);
+            if (rk < SEED_VPW) S.vsel[warp * SEED_VPW + rk] = bi;
             S.hash[tid] = -1;
             if (tid == 0) S.nvert = SEED_NV;
         }
         __syncthreads();
-        const int nfar = S.nfar, nvert = S.nvert;
+        TMARK0(1, dbg_row, 2);
+        const int nfar = SEED_FAR, nvert = S.nvert;
         // ---- one seed point per thread -> grid cell -> certainly a candidate? -> value ---------------------------
         const int n_disc = nfar * p.nlev * SEED_DISC;
         const int n_pts = n_disc + nvert * p.nlev;
@@ -445,9 +445,9 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
                 const int f = tid / (p.nlev * SEED_DISC), r0 = tid - f * (p.nlev * SEED_DISC);
                 l = r0 / SEED_DISC;
                 const int pt = r0 - l * SEED_DISC;
-                hsel = S.far[f];
+                hsel = max(S.far[f], 0);
                 const float* h = recs + hsel * GT_REC;
-                st = p.strides[p.lev[l].off];
+                st = p.lev[l].st;
                 float ux = h[GT_CX] - gcx, uy = h[GT_CY] - gcy;
                 const float nn = fmaf(ux, ux, uy * uy);
                 if (nn > 1e-12f) {
@@ -469,7 +469,7 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
                 hsel = hv >> 5;
                 const int k = hv & 31;
                 const float* h = recs + hsel * GT_REC;
-                st = p.strides[p.lev[l].off];
+                st = p.lev[l].st;
                 // one stride inside the vertex, on the ray from the GT's own centre
                 const float rr = h[GT_RG + k];
                 const float fct = fmaxf(0.0f, __fdividef(rr - st, fmaxf(rr, 1e-6f)));
@@ -480,25 +480,28 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
             const Level lv = p.lev[l];
             const float hcx = h[GT_CX], hcy = h[GT_CY];
             const int ix = cell_index(qx, st), iy = cell_index(qy, st);
-            const bool pick_ok = tid < n_disc || S.vsel[(tid - n_disc) / p.nlev] >= 0;
+            const bool pick_ok = tid < n_disc ? S.far[tid / (p.nlev * SEED_DISC)] >= 0 : S.vsel[(tid - n_disc) / p.nlev] >= 0;
             if (pick_ok && ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
                 const int a = lv.off + iy * lv.W + ix;
-                const float ast = p.strides[a];
-                const float xc = p24_anchor_centre(p.x_shifts[a], ast), yc = p24_anchor_centre(p.y_shifts[a], ast);
+                // the anchor's row is requested right away: it is in flight while the candidate tests run
+                const float* row = p.outputs + (long long)b * p.img_stride + (long long)a * p.row_stride;
+                float rpv[P24_RAYS];
+#pragma unroll
+                for (int k = 0; k < P24_RAYS; ++k) rpv[k] = row[2 + k];
+                const float pcx = row[0], pcy = row[1];
+                // the grid is the head's (validated by the host side): x_shift = column, y_shift = row, one stride per level
+                const float xc = p24_anchor_centre((float)ix, st), yc = p24_anchor_centre((float)iy, st);
                 // the very tests of the anchor tiles: inscribed disc, centre window, polygon
                 const float dx = hcx - xc, dy = hcy - yc;
                 bool cand = fmaf(dx, dx, dy * dy) < h[GT_RIN2];
-                if (!cand) cand = p24_in_centre(hcx, hcy, xc, yc, ast);
+                if (!cand) cand = p24_in_centre(hcx, hcy, xc, yc, st);
                 if (!cand) cand = p24_in_polygon(h + GT_VX, h + GT_VY, xc, yc);
+                if (tid == n_pts - 1) TMARK(1, dbg_row, 3);
                 if (cand) {
-                    const float* row = p.outputs + (long long)b * p.img_stride + (long long)a * p.row_stride;
                     // a certified LOWER bound of the pair value: when every ray is in the "apart" branch (the reference's
                     // own fp32 comparison) the value has the closed form (1/48) sum_k (2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2),
-                    // evaluated in fast arithmetic to within 3e-6; other pairs are evaluated exactly
-                    float rpv[P24_RAYS];
-#pragma unroll
-                    for (int k = 0; k < P24_RAYS; ++k) rpv[k] = row[2 + k];  // one round trip for the whole row
-                    const float d = p24_centre_dist(gcx, gcy, row[0], row[1]);
+                    // evaluated in fast arithmetic to within 3e-6
+                    const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
                     float sm = 0.0f;
                     bool apart = true;
 #pragma unroll
@@ -508,7 +511,8 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
                         const float t = (rg + rp) + d;
                         sm += 2.0f - __fdividef(4.0f * fmaf(rg, rg, rp * rp), t * t);
                     }
-                    float v = apart ? sm * (1.0f / 48.0f) - 1e-5f : pair_value_row(S.rec, row);
+                    // (a seed with a ray that is not apart would need the exact evaluation: skipped, far seeds are apart)
+                    float v = apart ? sm * (1.0f / 48.0f) - 1e-5f : P24_NEG_INF;
                     if (!(v == v)) v = P24_NEG_INF;
                     S.val[tid] = v;
                     S.anc[tid] = a;
@@ -516,6 +520,9 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
             }
         }
         __syncthreads();
+        TMARK0(1, dbg_row, 4);
+        __syncthreads();
+        TMARK0(1, dbg_row, 5);
         // ---- the 10th largest value over the distinct seed anchors (first arrival of an anchor in a small hash) -----
         if (tid == 0) S.T = P24_NEG_INF;
         float v = P24_NEG_INF;
@@ -538,18 +545,47 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g) {
             }
             S.val[tid] = v;
         }
+        // every warp's 10 largest (rank among its lanes), then warp 0 picks the 10th largest of those
+        {
+            const int rk = lane_rank<true>(v);
+            if (rk < P24_TOPK) S.top[warp * P24_TOPK + rk] = v;
+            if (tid == 0) S.ntmp = 0;
+        }
         __syncthreads();
-        if (v > P24_NEG_INF) {
-            int rank = 0;
-#pragma unroll 4
-            for (int j = 0; j < n_pts; ++j) rank += kv_gt(S.val[j], j, v, tid) ? 1 : 0;
-            if (rank == P24_TOPK - 1) S.T = v;
+        if (warp == 0) {
+            // the 10th largest of the lanes' largest is a lower bound t0 of the 10th largest; the values >= t0 (a dozen) are
+            // ranked by counting
+            float e[3];
+            float lm = P24_NEG_INF;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int i = lane + 32 * u;
+                e[u] = i < P24_WARPS * P24_TOPK ? S.top[i] : P24_NEG_INF;
+                lm = fmaxf(lm, e[u]);
+            }
+            const int r0 = lane_rank<true>(lm);
+            const unsigned pick = __ballot_sync(0xffffffffu, r0 == P24_TOPK - 1);
+            const float t0 = __shfl_sync(0xffffffffu, lm, __ffs(pick) - 1);
+            if (t0 > P24_NEG_INF) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+                    if (e[u] >= t0) S.tmp[atomicAdd(&S.ntmp, 1)] = e[u];
+                __syncwarp();
+                const int m = S.ntmp;
+                for (int i = lane; i < m; i += 32) {
+                    const float vi = S.tmp[i];
+                    int rank = 0;
+                    for (int j = 0; j < m; ++j) rank += kv_gt(S.tmp[j], j, vi, i) ? 1 : 0;
+                    if (rank == P24_TOPK - 1) S.T = vi;
+                }
+            }
         }
         __syncthreads();
     } else {
         if (tid == 0) S.T = P24_NEG_INF;
         __syncthreads();
     }
+    TMARK0(1, dbg_row, 6);
     // ---- far2: pairs closer than D cannot reach T.  H*(d) + 3e-5 < T is monotone in d: three rounds of a 32-way search by
     // warp 0, every lane evaluating the bound at its own distance ------------------------------------------------------
     if (warp == 0) {
@@ -673,14 +709,8 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     if (tid == 0) S.nitems = 0;
     S.cand[tid] = 0;
     const int n = p.num_gt[b];
-    // the records are complete once every seed item of the image has finished (the seed items are drawn from their own
-    // ticket counter before any tile: the CTAs that hold them are running, so this wait cannot deadlock)
     TMARK0(1, b * p.tiles + tile, 1);
-    if (tid == 0) {
-        while (ld_acquire(&p.seed_done[b]) < n) __nanosleep(64);
-    }
     __syncthreads();
-    TMARK0(1, b * p.tiles + tile, 2);
     {
         const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
         float4* dst = reinterpret_cast<float4*>(s_rec);
@@ -702,37 +732,31 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     }
     double objpart = active ? (double)p24_bce_logits(obj, 0.0f) : 0.0;
 
-    // ---- one pass over the GTs: centre windows, the inscribed-disc accept, a bit mask of the GTs whose reject radius
-    // the anchor is inside (the only ones that may need a polygon test) and a bit mask of the GTs whose far2 the
-    // PREDICTED centre is beyond (the only pairs whose value can reach the GT's top 10) -----------------------------
+    // ---- one pass over the GTs: centre windows, the inscribed-disc accept and a bit mask of the GTs whose reject radius
+    // the anchor is inside (the only ones that may need a polygon test) ------------------------------------------------
     bool cheap = false;
     const bool no_prune = (p.flags & P24_F_NO_PRUNE) != 0;
     const bool no_filter = (p.flags & P24_F_NO_FILTER) != 0;
     const bool tiny = !(rpmin >= 0.25f);  // a tiny (or NaN) predicted radius: outside the validated range of the bound
     unsigned near[4] = {0u, 0u, 0u, 0u};  // GTs 0..127; beyond that every GT is handled in place (see below)
-    unsigned far[4] = {0u, 0u, 0u, 0u};
     const float r25 = 2.5f * st + 1e-3f * st;  // conservative pre-filter radius of the window test
     const float4* s_rec4 = reinterpret_cast<const float4*>(s_rec);
     {
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            unsigned m = 0u, fm = 0u;
+            unsigned m = 0u;
             const int ge = min(32, n - w * 32);
             for (int j = 0; j < ge; ++j) {
                 const int g = w * 32 + j;
                 const float4 h = s_rec4[g * (GT_REC / 4)];
-                const float far2 = s_rec[g * GT_REC + GT_FAR2];
                 const float dx = h.x - xc, dy = h.y - yc;
                 const float d2 = fmaf(dx, dx, dy * dy);
                 cheap |= d2 < h.z;
                 m |= (d2 <= h.w ? 1u : 0u) << j;
                 if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
-                const float px = h.x - pcx, py = h.y - pcy;
-                fm |= (!(fmaf(px, px, py * py) < far2) ? 1u : 0u) << j;
             }
             const unsigned all = ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u);
             near[w] = no_prune ? all : m;
-            far[w] = tiny ? all : fm;
         }
         for (int g = 128; g < n; ++g) {  // more than 128 GTs: windows and discs of the rest
             const float4 h = s_rec4[g * (GT_REC / 4)];
@@ -799,22 +823,33 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     __syncthreads();
     S.cand[tid] = (cand ? 1 : 0) | (tiny ? 2 : 0);  // (read by far_pair, after the next barrier)
 
-    // ---- the (GT, candidate) pairs beyond far2: exact values into the GTs' top-10 lists (again through a work list) ---
+    // ---- the (GT, candidate) pairs whose PREDICTED centre lies beyond the GT's far2 (the only pairs whose value can reach
+    // the GT's top 10): bounds into the GTs' lists, again through a work list.  far2 and T come from the image's seed
+    // items, which were drawn before any tile (the CTAs that hold them are running: this wait cannot deadlock) and have
+    // had the whole candidate phase to finish ---------------------------------------------------------------------------
+    TMARK0(1, b * p.tiles + tile, 2);
+    if (!no_filter) {
+        if (tid == 0) {
+            while (ld_acquire(&p.seed_done[b]) < n) __nanosleep(64);
+        }
+        __syncthreads();
+        TMARK0(1, b * p.tiles + tile, 8);
+        for (int g = tid; g < n; g += P24_THREADS) {
+            const float* r = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
+            s_rec[g * GT_REC + GT_FAR2] = __ldcg(r + GT_FAR2);
+            s_rec[g * GT_REC + GT_T] = __ldcg(r + GT_T);
+        }
+        __syncthreads();
+    }
     if (cand && !no_filter) {
-        for (int w = 0; w < 4; ++w) {
-            unsigned m = far[w];
-            while (m) {
-                const int g = w * 32 + __ffs(m) - 1;
-                m &= m - 1;
+        for (int g = 0; g < n; ++g) {
+            const float4 h = s_rec4[g * (GT_REC / 4)];
+            const float px = h.x - pcx, py = h.y - pcy;
+            if (tiny || !(fmaf(px, px, py * py) < s_rec[g * GT_REC + GT_FAR2])) {
                 const int slot = atomicAdd(&S.nitems, 1);
                 if (slot < ITEM_CAP) S.items[slot] = (unsigned)tid | ((unsigned)g << 8);
                 else far_pair(p, s_rec, S, b, tile, g, tid);
             }
-        }
-        for (int g = 128; g < n; ++g) {  // more than 128 GTs: the rest in place
-            const float* rec = s_rec + g * GT_REC;
-            const float px = rec[GT_CX] - pcx, py = rec[GT_CY] - pcy;
-            if (tiny || !(fmaf(px, px, py * py) < rec[GT_FAR2])) far_pair(p, s_rec, S, b, tile, g, tid);
         }
     }
     // ---- per-anchor outputs, candidate bitmap and count, the all-anchor objectness term -------------------------
@@ -1010,7 +1045,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
             if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_SEED], 1u);  // the next one, in flight meanwhile
             const int g = seed / p.B, b = seed - g * p.B;
             TMARK0(1, 4096 + seed, 0);
-            if (g < p.num_gt[b]) seed_part(p, SS, b, g);
+            if (g < p.num_gt[b]) seed_part(p, SS, b, g, 4096 + seed);
             TMARK0(1, 4096 + seed, 1);
             __syncthreads();
             seed = s_seed;
@@ -1119,24 +1154,12 @@ struct TailShared {
     KV kv[TAIL_WARPS];
     float sums[28];
     int surv[TAIL_WARPS][TAIL_SURV];      // per GT warp: anchors of the list entries that survive the refined threshold
-    float sval[TAIL_WARPS][TAIL_SURV];    // ... and their exact pair values
+    float sval[TAIL_WARPS][TAIL_SURV];    // ... their value bounds (upper; then the exact values)
+    float slb[TAIL_WARPS][TAIL_SURV];     // ... and lower bounds
     float wc[TAIL_WARPS][TAIL_WSEL];      // per GT warp: the window-table entries that can be among the k cheapest
     int wa[TAIL_WARPS][TAIL_WSEL];
     int nuniq, last;
 };
-
-// rank of the lane's value among the 32 lanes' values (0 = largest when MAX; ties -> lower lane first)
-template <bool MAX>
-__device__ __forceinline__ int lane_rank(float v) {
-    const int lane = threadIdx.x & 31;
-    int rank = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const float o = __shfl_sync(0xffffffffu, v, j);
-        rank += (MAX ? kv_gt(o, j, v, lane) : kv_lt(o, j, v, lane)) ? 1 : 0;
-    }
-    return rank;
-}
 
 template <bool MAX>
 __device__ __forceinline__ KV tail_block_select(KV x, KV* s_red) {
@@ -1386,7 +1409,12 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
             const bool keep = !(e[u].x < tref);
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             const int at = nsurv + __popc(bal & ((1u << lane) - 1u));
-            if (keep && at < TAIL_SURV) S.surv[warp][at] = __float_as_int(e[u].y) & 0x7fffffff;
+            if (keep && at < TAIL_SURV) {
+                const int bits = __float_as_int(e[u].y);
+                S.surv[warp][at] = bits & 0x7fffffff;
+                S.sval[warp][at] = e[u].x;
+                S.slb[warp][at] = (bits & 0x80000000) ? e[u].x - 7e-5f : 0.0f;  // (pair values are >= 0)
+            }
             nsurv += __popc(bal);
         }
     }
@@ -1397,10 +1425,46 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
         g_tstamp[2][1024 + b * 64 + (slot - b * p.Lmax)][9] = lc;
     }
 #endif
+    TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 10);
     if (nsurv > TAIL_SURV) {
         ok = false;
         return 0.0f;
     }
+    // ---- bracket: every survivor's value lies in [lower, upper]; the 10 largest lower bounds and the 10 largest upper
+    // bounds all belong to survivors, so  L = sum of the 10 largest lower bounds <= sum of the 10 largest values <= U.
+    // int(sum) is decided when floor(L) == floor(U): no exact evaluation (all-apart pairs: U - L = 7e-4) ---------------
+    if (kc == P24_TOPK && nsurv >= P24_TOPK) {
+        float ub[2], lb[2];
+        int ru[2] = {0, 0}, rl[2] = {0, 0};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = lane + 32 * u;
+            ub[u] = j < nsurv ? S.sval[warp][j] : P24_NEG_INF;
+            lb[u] = j < nsurv ? S.slb[warp][j] : P24_NEG_INF;
+        }
+        for (int i = 0; i < nsurv; ++i) {
+            const float ui = S.sval[warp][i], li = S.slb[warp][i];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                ru[u] += kv_gt(ui, i, ub[u], lane + 32 * u) ? 1 : 0;
+                rl[u] += kv_gt(li, i, lb[u], lane + 32 * u) ? 1 : 0;
+            }
+        }
+        float su = 0.0f, sl = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (lane + 32 * u < nsurv && ru[u] < P24_TOPK) su += ub[u];
+            if (lane + 32 * u < nsurv && rl[u] < P24_TOPK) sl += lb[u];
+        }
+        su = warp_sum(su);
+        sl = warp_sum(sl);
+        const float fl = floorf(sl - 1e-4f), fu = floorf(su + 1e-4f);
+        if (fl == fu && fl >= 1.0f) {
+            TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 4);
+            return fl + 0.5f;  // any value with the decided integer part
+        }
+    }
+    if (lane == 0) atomicAdd(&p.status[ST_EXACT], 1);
     // exact values, 16 survivors at a time: every 8-lane group requests the rows of its 4 pairs, then evaluates them
     const unsigned gm = group_mask();
     const int grp = lane >> 3, sub = lane & 7;
@@ -1422,11 +1486,12 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
             const float d = p24_centre_dist(gcx, gcy, pc[u][0], pc[u][1]);
             float sm = 0.0f;
 #pragma unroll 1
-            for (int q = 0; q < 3; ++q) sm = sm + ray_loss(rec[GT_RG + sub * 3 + q], rp[u][q], d);
+            for (int q = 0; q < 3; ++q) sm = sm + p24_ray_loss(rec[GT_RG + sub * 3 + q], rp[u][q], d);  // (inlined: no call on this latency chain)
             sm = group_sum(sm, gm);
             float v = (sm / 24.0f) / 2.0f;
             if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
             if (sub == 0 && j < nsurv) S.sval[warp][j] = v;
+            if (u == 0 && j0 == 0) TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 11);
         }
     }
     __syncwarp();
@@ -1704,7 +1769,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
             float l[3], sm = 0.0f;
 #pragma unroll 1
             for (int q = 0; q < 3; ++q) {
-                l[q] = ray_loss(rec[GT_RG + sub * 3 + q], row[2 + sub * 3 + q], d);
+                l[q] = p24_ray_loss(rec[GT_RG + sub * 3 + q], row[2 + sub * 3 + q], d);  // (inlined: no call on this latency chain)
                 sm = sm + l[q];
             }
             sm = group_sum(sm, gm);
@@ -1972,11 +2037,13 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
         // the levels must tile [0, A) in order: anchors [off, off + W * H) of level l form a W x H grid
         long long next = 0;
         for (int l = 0; l < P24_MAX_LEVELS; ++l) {
-            p.lev[l].off = 0; p.lev[l].W = 1; p.lev[l].H = 0; p.lev[l].pad = 0;
+            p.lev[l].off = 0; p.lev[l].W = 1; p.lev[l].H = 0; p.lev[l].st = 1.0f;
             if (l < n_levels) {
                 const int32_t* d = h_levels + 4 * l;
-                if (d[0] != next || d[1] <= 0 || d[2] <= 0) return P24_E_BADARG;
-                p.lev[l].off = d[0]; p.lev[l].W = d[1]; p.lev[l].H = d[2];
+                float stv;
+                memcpy(&stv, d + 3, sizeof(float));
+                if (d[0] != next || d[1] <= 0 || d[2] <= 0 || !(stv > 0.0f)) return P24_E_BADARG;
+                p.lev[l].off = d[0]; p.lev[l].W = d[1]; p.lev[l].H = d[2]; p.lev[l].st = stv;
                 next += (long long)d[1] * d[2];
             }
         }

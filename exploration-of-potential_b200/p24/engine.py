@@ -70,7 +70,11 @@ class GridCache:
             if not ok:
                 raise _lib.P24Error("x_shifts / y_shifts / expanded_strides do not form per-level row-major grids "
                                     "(yolo_head_24p.py:222-230): unsupported anchor layout")
-            levels.append((off, W, H, 0))
+            import struct
+            stride_bits = struct.unpack("<i", struct.pack("<f", float(st[off])))[0]
+            if not bool((st[off:end] == st[off]).all()):
+                raise _lib.P24Error("expanded_strides is not constant within a level")
+            levels.append((off, W, H, stride_bits))
         if len(levels) > 4:
             raise _lib.P24Error(f"{len(levels)} feature levels: at most 4 are supported")
         arr = (C.c_int32 * (4 * len(levels)))(*[v for lv in levels for v in lv])

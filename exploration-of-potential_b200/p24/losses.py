@@ -225,9 +225,10 @@ class Loss_Function(nn.Module):
         that spilled into the penalised regime, the longest and the mean top-10 candidate list."""
         st = [s for _, s in self._engine.read_status()]
         gts = sum(s[6] for s in st)
-        return {"brute_force_gts": sum(s[1] for s in st), "spill_gts": sum(s[2] for s in st), "gts": gts,
+        return {"brute_force_gts": sum(s[1] for s in st), "exact_gts": sum(s[7] for s in st),
+                "spill_gts": sum(s[2] for s in st), "gts": gts,
                 "list_max": max([s[3] for s in st] + [0]), "list_mean": (sum(s[5] for s in st) / gts) if gts else 0.0,
-                "list_capacity": 1024}
+                "list_capacity": 2048}
 
     def forward(self, outputs_train, labels):
         outputs = outputs_train[3]

@@ -59,7 +59,8 @@ int p24_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
  *   outputs  [B, A, 27+nc] decoded head output (strides img_stride / row_stride, channel stride 1)
  *   labels   [B, Lmax, 51]  (cls, cx, cy, 24 x (x, y)); valid rows first, zero padded
  *   x_shifts, y_shifts, strides: [A] (the head's 3-lists concatenated, losses.py:193-195)
- *   h_levels [n_levels][4] HOST int32 (anchor offset, grid width, grid height, 0): the level structure of the grid as
+ *   h_levels [n_levels][4] HOST int32 (anchor offset, grid width, grid height, the bits of the level's fp32 stride): the
+ *            level structure of the grid as
  *            the head builds it (yolo_head_24p.py:222-230): anchors [offset, offset + W*H) of a level are its W x H cells,
  *            row-major, x_shifts = column, y_shifts = row, one stride value.  The levels must tile [0, A) in order
  *            (n_levels <= 4).  The centre-window anchors of a GT are enumerated from it instead of being searched.
@@ -178,7 +179,8 @@ int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_str
  *   h_status8[2]  GTs that spilled into the penalised regime
  *   h_status8[3]  longest top-10 candidate list seen
  *   h_status8[4]  clock cycles the last fused all-reduce waited for its peers (nranks > 1)
- *   h_status8[5]  list entries seen, over h_status8[6] GTs */
+ *   h_status8[5]  list entries seen, over h_status8[6] GTs
+ *   h_status8[7]  GTs whose dynamic k needed exact pair values (the bracket of the bounds straddled an integer) */
 #define P24_ERR_WINDOW_OVERFLOW 1
 #define P24_ERR_PEER_TIMEOUT 4
 int p24_read_status(void* workspace, int B, int A, int Lmax, int32_t* h_status8, void* stream);

@@ -61,10 +61,13 @@ sd = kp[4096:4096 + B * wl["G"]]
 ok = sd[:, 1] > 0
 print(f"   seed items: first start {us(sd[ok, 0].min()):.1f}  last end {us(sd[ok, 1].max()):.1f}")
 stat("seed item", sd[ok, 1] - sd[ok, 0])
+for lab, a, b_ in [("seed: select", 0, 2), ("seed: cand tests", 2, 3), ("seed: rows+value", 3, 4), ("seed: barrier", 4, 5),
+                   ("seed: hash+rank", 5, 6), ("seed: far2", 6, 1)]:
+    stat(lab, sd[ok, b_] - sd[ok, a])
 tl = kp[:min(B * tiles, 4095)]
 print(f"   tiles: first start {us(tl[:, 0].min()):.1f}  last end {us(tl[:, 7].max()):.1f}")
-for lab, a, b_ in [("pre", 0, 1), ("wait seeds", 1, 2), ("recs+rows", 2, 3), ("gt loop+lists", 3, 4), ("poly items", 4, 5),
-                   ("far list", 5, 6), ("far items+out", 6, 7), ("tile total", 0, 7)]:
+for lab, a, b_ in [("pre", 0, 1), ("recs+rows", 1, 3), ("gt loop+lists", 3, 4), ("poly items", 4, 5), ("cand sync", 5, 2),
+                   ("wait seeds", 2, 8), ("far list", 8, 6), ("far items+out", 6, 7), ("tile total", 0, 7)]:
     stat(lab, tl[:, b_] - tl[:, a])
 if B * tiles < 4000:
     wn = kp[B * tiles:min(4095, B * tiles + B * wl["G"] * 3)]
@@ -78,7 +81,8 @@ for lab, a, b_ in [("stage recs", 0, 1), ("phase 1 (own GTs)", 1, 2), ("cluster 
                    ("phase 3a/b", 5, 6), ("phase 3c", 6, 7), ("reduce wait", 7, 8), ("atomics+ticket", 8, 9), ("CTA total", 0, 9)]:
     stat(lab, c[:, b_] - c[:, a])
 gt = np.concatenate([kt[1024 + b * 64:1024 + b * 64 + wl["G"]] for b in range(B)]) if wl["G"] <= 64 else kt[1024:1024 + 64]
-for lab, a, b_ in [("lcount RT", 0, 1), ("list pass A", 1, 2), ("threshold", 2, 3), ("pass B + exact", 3, 4), ("sum", 4, 5),
+for lab, a, b_ in [("lcount RT", 0, 1), ("list pass A", 1, 2), ("threshold", 2, 3), ("pass B + exact", 3, 4), ("  B: compaction", 3, 10),
+                   ("  B: rows + 1st eval", 10, 11), ("  B: rest", 11, 4), ("sum", 4, 5),
                    ("claims", 5, 6), ("GT total", 0, 6)]:
     stat(lab, gt[:, b_] - gt[:, a])
 print(f"   survivors per GT mean {gt[:, 8].mean():.1f} max {gt[:, 8].max():.0f}; list length mean {gt[:, 9].mean():.1f} max {gt[:, 9].max():.0f}")
