@@ -21,6 +21,7 @@
 // [0] cx  [1] cy  [2] rin2  [3] rrej2   (one 128-bit shared-memory load for the per-pair tests)
 // [4] far2  [5] class (as float)  [6] rgmax  [7] rgmin
 // [8..31] vertex x  [32..55] vertex y  [56] mean rg^2  [57] mean rg  [58] T  [59] pad  [60..83] ray length rg
+// [84..91] origin (column, row; int bits) of the GT's 7 x 7 centre-window block on every level
 #define GT_CX 0
 #define GT_CY 1
 #define GT_RIN2 2    // squared radius of a disc around (cx, cy) that lies inside the polygon (0: none)
@@ -35,7 +36,8 @@
 #define GT_RGMEAN 57  // mean of rg
 #define GT_T 58       // certified lower bound of the GT's 10th largest pair value over the candidates (-inf: none)
 #define GT_RG 60
-#define GT_REC 84
+#define GT_ORG 84
+#define GT_REC 92
 
 static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 

@@ -264,6 +264,13 @@ __device__ __forceinline__ void warp_gt_record(const float* __restrict__ row, fl
     }
 }
 
+// first cell of the 7-wide block that contains every cell centre within 2.5 strides of c (one cell of slack per side)
+__device__ __forceinline__ int window_origin(float c, float st) {
+    float v = floorf(c / st) - 3.0f;
+    v = fminf(fmaxf(v, -1.0e6f), 1.0e6f);  // NaN -> -1e6: an empty window
+    return (int)v;
+}
+
 #define PREP_THREADS 256
 __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ Params p) {
     // launched as a programmatic dependent of whatever precedes it in the stream (in back-to-back steps: the previous
@@ -279,8 +286,22 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
         p.num_fg[b] = 0;  // k_tail adds the foreground anchors of the image's cluster CTAs
         atomicMax(&p.ticket[TK_LEFF], (unsigned)n);  // the batch's largest num_gt: k_pass lays its items out for it
     }
-    for (int g = warp; g < n; g += PREP_THREADS / 32)
-        warp_gt_record(lab + (long long)g * p.lab_row_stride, p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC);
+    const int lane = tid & 31;
+    for (int g = warp; g < n; g += PREP_THREADS / 32) {
+        const float* row = lab + (long long)g * p.lab_row_stride;
+        float* rec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
+        warp_gt_record(row, rec);
+        // the GT's window cost table: origins of its 7 x 7 block of cells per level, every slot "not valid" until an
+        // anchor tile stores the pair's cost
+        float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
+        if (lane < 2 * P24_MAX_LEVELS) {
+            const int l = lane >> 1;
+            const float o = __int_as_float(l < p.nlev ? window_origin(row[1 + (lane & 1)], p.lev[l].st) : 0);
+            rec[GT_ORG + lane] = o;
+            tab[P24_WT_HDR + lane] = o;
+        }
+        for (int s = lane; s < P24_WT_HDR; s += 32) tab[s] = P24_POS_INF;
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -644,11 +665,13 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
+#define WIN_CAP 512
 struct AnchorShared {
     float row[P24_WARPS][ROW_CH][33];
     int cand[P24_THREADS];
     unsigned items[ITEM_CAP];
-    int nitems;
+    unsigned witems[WIN_CAP];   // (GT, anchor) pairs that pass the centre-window test
+    int nitems, nwin;
 };
 
 // the tile's rows: each warp reads its 32 rows, 27 contiguous floats per row, straight into shared memory
@@ -694,6 +717,90 @@ __device__ __noinline__ void far_pair(const Params& p, const float* __restrict__
     }
 }
 
+// One (GT g, anchor al of the staged tile) pair that passes the centre-window test of losses.py:523-542, by an 8-lane group:
+// polygon test (inscribed-disc accept, else the reference-order edge terms, 3 per lane), exact pair value and SimOTA cost
+// when inside -> the GT's window cost table, by slot (level, row, column) of its 7 x 7 block of cells.  The anchor of a
+// slot and the slot of an anchor are both computable, which is what k_tail (selection and conflict argmin) relies on.
+// Geometry and objectness come from the staged rows; the class logits are read from the head output.
+__device__ __forceinline__ void window_pair(const Params& p, const float* __restrict__ s_rec, const AnchorShared& S, int b,
+                                            int tile, int g, int al, unsigned gm) {
+    const int sub = threadIdx.x & 7;
+    const float* rec = s_rec + g * GT_REC;
+    const int wr = al >> 5, lr = al & 31;
+    const int aa = tile * P24_THREADS + al;
+    const float* cls = p.outputs + (long long)b * p.img_stride + (long long)aa * p.row_stride + 27;
+    const int c = gt_class(rec, p.nc);
+    float cl[10];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? cls[sub + 8 * q] : 0.0f;
+    const float clsc = cls[c];
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < P24_MAX_LEVELS; ++q) l += (q < p.nlev && aa >= p.lev[q].off) ? 1 : 0;
+    const int r = aa - p.lev[l].off;
+    const int iy = r / p.lev[l].W, ix = r - iy * p.lev[l].W;
+    const float st = p.lev[l].st;
+    // (the grid is the head's, validated by the host side: x_shift = column, y_shift = row, one stride per level)
+    const float xc = p24_anchor_centre((float)ix, st), yc = p24_anchor_centre((float)iy, st);
+    const float gcx = rec[GT_CX], gcy = rec[GT_CY];
+    bool inside = true;
+    {
+        // inside the inscribed disc the angle sum is >= 360 (see warp_gt_record): no edge terms needed
+        const float ddx = gcx - xc, ddy = gcy - yc;
+        if (!(fmaf(ddx, ddx, ddy * ddy) < rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
+            float ang = 0.0f;
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) {
+                const int k = sub * 3 + q;
+                const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
+                ang = ang + edge_angle(rec[GT_VX + k] - xc, rec[GT_VY + k] - yc, rec[GT_VX + k2] - xc, rec[GT_VY + k2] - yc);
+            }
+            ang = group_sum(ang, gm);
+            inside = ang >= 350.0f;  // losses.py:588
+        }
+    }
+    if (!inside) return;
+    const float d = p24_centre_dist(gcx, gcy, S.row[wr][0][lr], S.row[wr][1][lr]);
+    float sm = 0.0f;
+#pragma unroll 1
+    for (int q = 0; q < 3; ++q) sm = sm + ray_loss(rec[GT_RG + sub * 3 + q], S.row[wr][2 + sub * 3 + q][lr], d);
+    sm = group_sum(sm, gm);
+    const float v = (sm / 24.0f) / 2.0f;
+    const float eo1 = 1.0f + expf(-S.row[wr][26][lr]);
+    float neg;
+    if (p.nc <= 80) {
+        float prod = 1.0f;
+        int nsat = 0;
+#pragma unroll
+        for (int q = 0; q < 10; ++q)
+            if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
+        prod = group_prod(prod, gm);
+        nsat = group_sum_i(nsat, gm);
+        neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(cls, p.nc, eo1, gm);
+    } else {
+        // many classes: the log of a per-lane product, restarted before it can underflow
+        float prod = 1.0f, lsum = 0.0f;
+        int nsat = 0;
+        for (int j = sub; j < p.nc; j += 8) {
+            p24_neg_factor(cls[j], eo1, prod, nsat);
+            if (prod < 1e-20f) {
+                lsum += logf(prod);
+                prod = 1.0f;
+            }
+        }
+        lsum += logf(prod);
+        lsum = group_sum(lsum, gm);
+        nsat = group_sum_i(nsat, gm);
+        neg = -lsum + 100.0f * (float)nsat;
+        if (!(neg == neg) || neg == P24_POS_INF) neg = group_cls_neg_sum(cls, p.nc, eo1, gm);
+    }
+    float cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
+    if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
+    const int sx = ix - __float_as_int(rec[GT_ORG + 2 * l]), sy = iy - __float_as_int(rec[GT_ORG + 2 * l + 1]);
+    if (sub == 0 && sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE)
+        p.wtab[((long long)b * p.Lmax + g) * P24_WT_STRIDE + l * P24_WSLOTS + sy * P24_WSIDE + sx] = cost;
+}
+
 __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, AnchorShared& S, int b, int tile, bool staged) {
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -706,7 +813,10 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
         xs = p.x_shifts[a];
         ys = p.y_shifts[a];
     }
-    if (tid == 0) S.nitems = 0;
+    if (tid == 0) {
+        S.nitems = 0;
+        S.nwin = 0;
+    }
     S.cand[tid] = 0;
     const int n = p.num_gt[b];
     TMARK0(1, b * p.tiles + tile, 1);
@@ -753,7 +863,11 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
                 const float d2 = fmaf(dx, dx, dy * dy);
                 cheap |= d2 < h.z;
                 m |= (d2 <= h.w ? 1u : 0u) << j;
-                if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
+                if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st) && active) {
+                    cheap = true;
+                    const int slot = atomicAdd(&S.nwin, 1);
+                    if (slot < WIN_CAP) S.witems[slot] = (unsigned)tid | ((unsigned)g << 8);
+                }
             }
             const unsigned all = ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u);
             near[w] = no_prune ? all : m;
@@ -762,7 +876,11 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
             const float4 h = s_rec4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             cheap |= fmaf(dx, dx, dy * dy) < h.z;
-            if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
+            if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st) && active) {
+                cheap = true;
+                const int slot = atomicAdd(&S.nwin, 1);
+                if (slot < WIN_CAP) S.witems[slot] = (unsigned)tid | ((unsigned)g << 8);
+            }
         }
     }
     cheap = cheap && active;
@@ -799,6 +917,38 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     if (mine) S.cand[tid] = 1;
     __syncthreads();
     TMARK0(1, b * p.tiles + tile, 4);
+    // ---- the centre-window pairs of the tile: SimOTA costs into the GTs' window tables (8-lane groups) -------------
+    {
+        const unsigned gm = group_mask();
+        const int nwin = S.nwin;
+        if (nwin <= WIN_CAP) {
+            for (int wi = tid >> 3; wi < nwin; wi += P24_THREADS / 8) {
+                const unsigned it = S.witems[wi];
+                window_pair(p, s_rec, S, b, tile, (int)(it >> 8), (int)(it & 0xFF), gm);
+            }
+        } else {
+            // more pairs than the list holds (crowded coarse levels): every warp walks through the GTs again and hands the
+            // pairs of its own anchors to its four groups
+            const int grp = lane >> 3;
+            for (int g = 0; g < n; ++g) {
+                const float4 h = s_rec4[g * (GT_REC / 4)];
+                const bool hit = active && fmaxf(fabsf(h.x - xc), fabsf(h.y - yc)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st);
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    unsigned mm = m;
+                    int pick = -1;
+                    for (int q = 0; q <= grp && mm; ++q) {  // the grp-th set bit (if there is one)
+                        pick = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        if (q < grp) pick = -1;
+                    }
+                    if (pick >= 0) window_pair(p, s_rec, S, b, tile, g, warp * 32 + pick, gm);
+                    for (int q = 0; q < 4 && m; ++q) m &= m - 1;  // four pairs per round
+                }
+            }
+        }
+    }
+    TMARK0(1, b * p.tiles + tile, 9);
     {
         const int nitems = min(S.nitems, ITEM_CAP);
         for (int i = tid; i < nitems; i += P24_THREADS) {
@@ -879,144 +1029,13 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     }
 }
 
-// -------------------------------------------------------------------------------------------
-// k_pass, centre-window items: every (GT, centre-window anchor) pair as an independent 8-lane group task:
-// polygon test (inscribed-disc accept, else the reference-order edge terms, 3 per lane), exact pair value and
-// SimOTA cost when inside.  The window of a GT is enumerated straight from the level grids (a 7 x 7 block of cells
-// per level around the centre holds every anchor that can pass the strict test of losses.py:523-542, which is then
-// applied in the reference's own arithmetic), so this part needs nothing from the anchor tiles and runs beside them.
-// Costs land in the GT's window table by slot (level, row, column); the anchor of a slot and the slot of an anchor
-// are both computable, which is what k_tail (selection and conflict argmin) relies on.
-// -------------------------------------------------------------------------------------------
-struct WindowShared {
-    float rec[GT_REC];
-    int list[P24_WSLOTS];  // slots of the level that pass the centre-window test
-    int npair;
-};
-
-// first cell of the 7-wide block that contains every cell centre within 2.5 strides of c (one cell of slack per side)
-__device__ __forceinline__ int window_origin(float c, float st) {
-    float v = floorf(c / st) - 3.0f;
-    v = fminf(fmaxf(v, -1.0e6f), 1.0e6f);  // NaN -> -1e6: an empty window
-    return (int)v;
-}
-
-// one work item: the window of GT g of image b on level l
-__device__ __forceinline__ void window_part(const Params& p, WindowShared& S, int b, int g, int l) {
-    const int tid = threadIdx.x;
-    const unsigned gm = group_mask();
-    const int grp = tid >> 3, sub = tid & 7;
-    const float* img = p.outputs + (long long)b * p.img_stride;
-    const Level lv = p.lev[l];
-    if (tid < GT_REC) S.rec[tid] = p.gt_rec[((long long)b * p.Lmax + g) * GT_REC + tid];
-    if (tid == GT_REC) S.npair = 0;
-    __syncthreads();
-    const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
-    float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
-    const float lst = p.strides[lv.off];
-    const int ox = window_origin(gcx, lst), oy = window_origin(gcy, lst);
-    if (tid < 2) tab[P24_WT_HDR + 2 * l + tid] = __int_as_float(tid ? oy : ox);
-    if (tid < P24_WSLOTS) {
-        const int sy = tid / P24_WSIDE, sx = tid - sy * P24_WSIDE;
-        const int ix = ox + sx, iy = oy + sy;
-        bool in = false;
-        if (ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
-            const int a = lv.off + iy * lv.W + ix;
-            const float st = p.strides[a];
-            in = p24_in_centre(gcx, gcy, p24_anchor_centre(p.x_shifts[a], st), p24_anchor_centre(p.y_shifts[a], st), st);
-        }
-        tab[l * P24_WSLOTS + tid] = P24_POS_INF;
-        if (in) S.list[atomicAdd(&S.npair, 1)] = tid;
-    }
-    __syncthreads();
-    const int npair = S.npair;
-    const int c = gt_class(S.rec, p.nc);
-    for (int wi = grp; wi < npair; wi += P24_THREADS / 8) {
-        const int t = S.list[wi];
-        const int sy = t / P24_WSIDE, sx = t - sy * P24_WSIDE;
-        const int a = lv.off + (oy + sy) * lv.W + (ox + sx);
-        const float* row = img + (long long)a * p.row_stride;
-        const float st = p.strides[a];
-        const float xs = p.x_shifts[a], ys = p.y_shifts[a];
-        const float pcx = row[0], pcy = row[1], obj = row[26], clsc = row[27 + c];
-        float rp[3], cl[10];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) rp[q] = row[2 + sub * 3 + q];
-#pragma unroll
-        for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? row[27 + sub + 8 * q] : 0.0f;
-        const float xc = p24_anchor_centre(xs, st);
-        const float yc = p24_anchor_centre(ys, st);
-        bool inside = true;
-        {
-            // inside the inscribed disc the angle sum is >= 360 (see warp_gt_record): no edge terms needed
-            const float ddx = gcx - xc, ddy = gcy - yc;
-            if (!(fmaf(ddx, ddx, ddy * ddy) < S.rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
-                float ang = 0.0f;
-#pragma unroll 1
-                for (int q = 0; q < 3; ++q) {
-                    const int k = sub * 3 + q;
-                    const int k2 = (k == P24_RAYS - 1) ? 0 : k + 1;
-                    ang = ang + edge_angle(S.rec[GT_VX + k] - xc, S.rec[GT_VY + k] - yc, S.rec[GT_VX + k2] - xc,
-                                           S.rec[GT_VY + k2] - yc);
-                }
-                ang = group_sum(ang, gm);
-                inside = ang >= 350.0f;  // losses.py:588
-            }
-        }
-        if (inside) {
-            const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
-            float sm = 0.0f;
-#pragma unroll 1
-            for (int q = 0; q < 3; ++q) sm = sm + ray_loss(S.rec[GT_RG + sub * 3 + q], rp[q], d);
-            sm = group_sum(sm, gm);
-            const float v = (sm / 24.0f) / 2.0f;
-            const float eo1 = 1.0f + expf(-obj);
-            float neg;
-            if (p.nc <= 80) {
-                float prod = 1.0f;
-                int nsat = 0;
-#pragma unroll
-                for (int q = 0; q < 10; ++q)
-                    if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
-                prod = group_prod(prod, gm);
-                nsat = group_sum_i(nsat, gm);
-                neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(row + 27, p.nc, eo1, gm);
-            } else {
-                // many classes: the log of a per-lane product, restarted before it can underflow
-                float prod = 1.0f, lsum = 0.0f;
-                int nsat = 0;
-                for (int j = sub; j < p.nc; j += 8) {
-                    p24_neg_factor(row[27 + j], eo1, prod, nsat);
-                    if (prod < 1e-20f) {
-                        lsum += logf(prod);
-                        prod = 1.0f;
-                    }
-                }
-                lsum += logf(prod);
-                lsum = group_sum(lsum, gm);
-                nsat = group_sum_i(nsat, gm);
-                neg = -lsum + 100.0f * (float)nsat;
-                if (!(neg == neg) || neg == P24_POS_INF) neg = group_cls_neg_sum(row + 27, p.nc, eo1, gm);
-            }
-            float cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
-            if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
-            if (sub == 0) tab[l * P24_WSLOTS + t] = cost;
-        }
-    }
-}
-
 // k_pass: persistent CTAs (one wave: the grid never exceeds what the device holds at once) drawing work items from
 // ticket counters: first the seed items (their own counter), then the anchor tiles (the long items), then the
 // (GT, level) centre-window items.  Launched as a programmatic dependent of k_prep: the first tile's rows are in flight
 // before the CTA waits for the records.
-union PassShared {
-    AnchorShared a;
-    WindowShared w;
-};
-
 __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__ Params p) {
     extern __shared__ float4 s_dyn4[];   // [Lmax * GT_REC] floats: the image's records (anchor tiles); seed scratch
-    __shared__ PassShared S;
+    __shared__ AnchorShared S;
     __shared__ int s_item, s_seed;
     float* s_rec = reinterpret_cast<float*>(s_dyn4);
     const int n_anchor = p.B * p.tiles;
@@ -1030,7 +1049,7 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
     int item = s_item, seed = s_seed;
     bool staged = false;
     if (item < n_anchor) {
-        stage_rows(p, S.a, item / p.tiles, item % p.tiles);
+        stage_rows(p, S, item / p.tiles, item % p.tiles);
         staged = true;
     }
     pdl_wait();  // the records come from k_prep
@@ -1051,24 +1070,14 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
             seed = s_seed;
         }
     }
-    const int n_items = n_anchor + p.B * leff * p.nlev;
-    while (item < n_items) {
+    while (item < n_anchor) {
         __syncthreads();
         if (tid == 0) s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);  // the next one, in flight meanwhile
-        if (item < n_anchor) {
-            // image-major order keeps an image's tiles (and its records) together in time
-            TMARK0(1, item, 0);
-            anchor_part(p, s_rec, S.a, item / p.tiles, item % p.tiles, staged);
-            TMARK0(1, item, 7);
-            staged = false;
-        } else {
-            const int wi = item - n_anchor;
-            const int l = wi % p.nlev, bg = wi / p.nlev;
-            const int b = bg / leff, g = bg - b * leff;
-            TMARK0(1, min(item, 4095), 0);
-            if (g < p.num_gt[b]) window_part(p, S.w, b, g, l);
-            TMARK0(1, min(item, 4095), 7);
-        }
+        // image-major order keeps an image's tiles (and its records) together in time
+        TMARK0(1, item, 0);
+        anchor_part(p, s_rec, S, item / p.tiles, item % p.tiles, staged);
+        TMARK0(1, item, 7);
+        staged = false;
         __syncthreads();
         item = s_item;
     }
@@ -2067,7 +2076,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass, P24_THREADS, dyn_pass);
         if (e != cudaSuccess) return (int)e;
         if (per_sm < 1) return P24_E_UNSUPPORTED;
-        const long long items = (long long)B * p.tiles + (long long)B * Lmax * n_levels;
+        const long long items = (long long)B * p.tiles > (long long)B * Lmax ? (long long)B * p.tiles : (long long)B * Lmax;
         const long long cap = (long long)per_sm * n_sm;
         e = launch(k_pass, dim3((unsigned)(items < cap ? items : cap)), dim3(P24_THREADS), dyn_pass, st, pdl, p);
         if (e != cudaSuccess) return (int)e;
