@@ -53,7 +53,8 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 #define ST_WORDS 8
 
 struct P24Workspace {
-    size_t ticket;      // [4] unsigned: work-queue head of k_pass, largest num_gt, completion count of k_tail, seed-queue head
+    size_t ticket;      // [8] unsigned: tile-queue head of k_pass, largest num_gt, completion count of k_tail, seed-queue head,
+                        //               window-queue head, number of centre-window pairs of the batch
     size_t acc_fix;     // [28] int64   fixed-point loss sums of the batch (zero between calls)
     size_t status;      // [ST_WORDS] int
     size_t seed_done;   // [B] int      seed items of the image that are complete (zero between calls)
@@ -69,6 +70,7 @@ struct P24Workspace {
     size_t kreq;        // [B, Lmax] int
     size_t ntake;       // [B, Lmax] int
     size_t cbits;       // [B, tiles * 8] unsigned         candidate bitmap (bit l of word w: anchor 32 w + l)
+    size_t wlist;       // [B * Lmax * 100] int2           the batch's centre-window pairs (GT slot, anchor), written by k_prep
     size_t total;
 };
 
@@ -80,7 +82,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     const size_t BL = (size_t)B * (size_t)Lmax;
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
-    w.ticket = off;     off = p24_align(off + 4 * sizeof(unsigned));
+    w.ticket = off;     off = p24_align(off + 8 * sizeof(unsigned));
     w.acc_fix = off;    off = p24_align(off + 28 * sizeof(long long));
     w.status = off;     off = p24_align(off + ST_WORDS * sizeof(int));
     w.seed_done = off;  off = p24_align(off + (size_t)B * sizeof(int));
@@ -94,6 +96,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     w.kreq = off;       off = p24_align(off + BL * sizeof(int));
     w.ntake = off;      off = p24_align(off + BL * sizeof(int));
     w.cbits = off;      off = p24_align(off + NB * P24_WARPS * sizeof(unsigned));
+    w.wlist = off;      off = p24_align(off + BL * 25 * P24_MAX_LEVELS * 2 * sizeof(int));
     w.total = off;
     return w;
 }

@@ -71,6 +71,7 @@ struct Params {
     float* wtab;
     float2* list;
     unsigned* cbits;
+    int2* wlist;
     int* claimg;
     int* kreq;
     int* ntake;
@@ -107,6 +108,8 @@ __device__ __forceinline__ void tmark(int kern, int row, int slot) {
 #define TK_LEFF 1
 #define TK_TAIL 2
 #define TK_SEED 3
+#define TK_WIN 4    // window-chunk queue head
+#define TK_WTOT 5   // centre-window pairs of the batch (k_prep)
 
 __device__ __forceinline__ void pdl_wait() {
 #if __CUDA_ARCH__ >= 900
@@ -271,6 +274,28 @@ __device__ __forceinline__ int window_origin(float c, float st) {
     return (int)v;
 }
 
+// which of the lane's slots s = lane + 32 q of a GT's window table pass the strict centre-window test (losses.py:523-542,
+// in the reference's arithmetic); bit q of the result.  The anchor of a slot follows from the level grids.
+__device__ __forceinline__ unsigned window_slot_mask(const Params& p, float gcx, float gcy) {
+    const int lane = threadIdx.x & 31;
+    unsigned m = 0u;
+#pragma unroll
+    for (int q = 0; q < (P24_WT_HDR + 31) / 32; ++q) {
+        const int s = lane + 32 * q;
+        const int l = s / P24_WSLOTS, r = s - l * P24_WSLOTS;
+        if (l < p.nlev) {
+            const float st = p.lev[l].st;
+            const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+            const int ix = window_origin(gcx, st) + sx, iy = window_origin(gcy, st) + sy;
+            // (the grid is the head's, validated by the host side: x_shift = column, y_shift = row, one stride per level)
+            if (ix >= 0 && ix < p.lev[l].W && iy >= 0 && iy < p.lev[l].H &&
+                p24_in_centre(gcx, gcy, p24_anchor_centre((float)ix, st), p24_anchor_centre((float)iy, st), st))
+                m |= 1u << q;
+        }
+    }
+    return m;
+}
+
 #define PREP_THREADS 256
 __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ Params p) {
     // launched as a programmatic dependent of whatever precedes it in the stream (in back-to-back steps: the previous
@@ -287,12 +312,14 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
         atomicMax(&p.ticket[TK_LEFF], (unsigned)n);  // the batch's largest num_gt: k_pass lays its items out for it
     }
     const int lane = tid & 31;
+    extern __shared__ int s_wcnt[];  // [Lmax] centre-window pairs per GT, then their exclusive prefix
+    __shared__ int s_base;
     for (int g = warp; g < n; g += PREP_THREADS / 32) {
         const float* row = lab + (long long)g * p.lab_row_stride;
         float* rec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
         warp_gt_record(row, rec);
-        // the GT's window cost table: origins of its 7 x 7 block of cells per level, every slot "not valid" until an
-        // anchor tile stores the pair's cost
+        // the GT's window cost table: origins of its 7 x 7 block of cells per level, every slot "not valid" until the
+        // pair's cost is stored
         float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
         if (lane < 2 * P24_MAX_LEVELS) {
             const int l = lane >> 1;
@@ -301,6 +328,46 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
             tab[P24_WT_HDR + lane] = o;
         }
         for (int s = lane; s < P24_WT_HDR; s += 32) tab[s] = P24_POS_INF;
+        const int c = warp_sum_i(__popc(window_slot_mask(p, row[1], row[2])));
+        if (lane == 0) s_wcnt[g] = c;
+    }
+    __syncthreads();
+    // ---- the image's centre-window pairs (GT slot, anchor) appended to the batch's list: the window items of k_pass ----
+    if (warp == 0) {
+        int carry = 0;
+        for (int g0 = 0; g0 < n; g0 += 32) {
+            const int g = g0 + lane;
+            const int c = g < n ? s_wcnt[g] : 0;
+            int inc = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += t;
+            }
+            if (g < n) s_wcnt[g] = carry + inc - c;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) s_base = carry ? (int)atomicAdd(&p.ticket[TK_WTOT], (unsigned)carry) : 0;
+    }
+    __syncthreads();
+    for (int g = warp; g < n; g += PREP_THREADS / 32) {
+        const float* row = lab + (long long)g * p.lab_row_stride;
+        const float gcx = row[1], gcy = row[2];
+        const unsigned m = window_slot_mask(p, gcx, gcy);
+        int at = s_base + s_wcnt[g];
+#pragma unroll
+        for (int q = 0; q < (P24_WT_HDR + 31) / 32; ++q) {
+            const bool in = (m >> q) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const int s = lane + 32 * q;
+                const int l = s / P24_WSLOTS, r = s - l * P24_WSLOTS;
+                const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+                const int ix = window_origin(gcx, p.lev[l].st) + sx, iy = window_origin(gcy, p.lev[l].st) + sy;
+                p.wlist[at + __popc(bal & ((1u << lane) - 1u))] = make_int2(b * p.Lmax + g, p.lev[l].off + iy * p.lev[l].W + ix);
+            }
+            at += __popc(bal);
+        }
     }
 }
 
@@ -665,13 +732,11 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-#define WIN_CAP 512
 struct AnchorShared {
     float row[P24_WARPS][ROW_CH][33];
     int cand[P24_THREADS];
     unsigned items[ITEM_CAP];
-    unsigned witems[WIN_CAP];   // (GT, anchor) pairs that pass the centre-window test
-    int nitems, nwin;
+    int nitems;
 };
 
 // the tile's rows: each warp reads its 32 rows, 27 contiguous floats per row, straight into shared memory
@@ -717,23 +782,28 @@ __device__ __noinline__ void far_pair(const Params& p, const float* __restrict__
     }
 }
 
-// One (GT g, anchor al of the staged tile) pair that passes the centre-window test of losses.py:523-542, by an 8-lane group:
-// polygon test (inscribed-disc accept, else the reference-order edge terms, 3 per lane), exact pair value and SimOTA cost
-// when inside -> the GT's window cost table, by slot (level, row, column) of its 7 x 7 block of cells.  The anchor of a
-// slot and the slot of an anchor are both computable, which is what k_tail (selection and conflict argmin) relies on.
-// Geometry and objectness come from the staged rows; the class logits are read from the head output.
-__device__ __forceinline__ void window_pair(const Params& p, const float* __restrict__ s_rec, const AnchorShared& S, int b,
-                                            int tile, int g, int al, unsigned gm) {
+// One (GT, anchor) pair that passes the centre-window test of losses.py:523-542, by an 8-lane group: polygon test
+// (inscribed-disc accept, else the reference-order edge terms, 3 per lane), exact pair value and SimOTA cost when inside
+// -> the GT's window cost table, by slot (level, row, column) of its 7 x 7 block of cells.  The anchor of a slot and the
+// slot of an anchor are both computable, which is what k_tail (selection and conflict argmin) relies on.
+__device__ __forceinline__ void window_pair(const Params& p, int slot, int aa, unsigned gm) {
     const int sub = threadIdx.x & 7;
-    const float* rec = s_rec + g * GT_REC;
-    const int wr = al >> 5, lr = al & 31;
-    const int aa = tile * P24_THREADS + al;
-    const float* cls = p.outputs + (long long)b * p.img_stride + (long long)aa * p.row_stride + 27;
+    const int b = slot / p.Lmax;
+    const float* rec = p.gt_rec + (long long)slot * GT_REC;
+    const float* row = p.outputs + (long long)b * p.img_stride + (long long)aa * p.row_stride;
+    const float* cls = row + 27;
+    // everything the pair needs is requested up front
+    const float gcx = rec[GT_CX], gcy = rec[GT_CY], rin2 = rec[GT_RIN2];
     const int c = gt_class(rec, p.nc);
-    float cl[10];
+    float cl[10], rp[3], rg[3];
 #pragma unroll
     for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? cls[sub + 8 * q] : 0.0f;
-    const float clsc = cls[c];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        rp[q] = row[2 + sub * 3 + q];
+        rg[q] = rec[GT_RG + sub * 3 + q];
+    }
+    const float pcx = row[0], pcy = row[1], obj = row[26], clsc = cls[c];
     int l = 0;
 #pragma unroll
     for (int q = 1; q < P24_MAX_LEVELS; ++q) l += (q < p.nlev && aa >= p.lev[q].off) ? 1 : 0;
@@ -742,12 +812,11 @@ __device__ __forceinline__ void window_pair(const Params& p, const float* __rest
     const float st = p.lev[l].st;
     // (the grid is the head's, validated by the host side: x_shift = column, y_shift = row, one stride per level)
     const float xc = p24_anchor_centre((float)ix, st), yc = p24_anchor_centre((float)iy, st);
-    const float gcx = rec[GT_CX], gcy = rec[GT_CY];
     bool inside = true;
     {
         // inside the inscribed disc the angle sum is >= 360 (see warp_gt_record): no edge terms needed
         const float ddx = gcx - xc, ddy = gcy - yc;
-        if (!(fmaf(ddx, ddx, ddy * ddy) < rec[GT_RIN2]) || (p.flags & P24_F_NO_PRUNE)) {
+        if (!(fmaf(ddx, ddx, ddy * ddy) < rin2) || (p.flags & P24_F_NO_PRUNE)) {
             float ang = 0.0f;
 #pragma unroll 1
             for (int q = 0; q < 3; ++q) {
@@ -760,13 +829,13 @@ __device__ __forceinline__ void window_pair(const Params& p, const float* __rest
         }
     }
     if (!inside) return;
-    const float d = p24_centre_dist(gcx, gcy, S.row[wr][0][lr], S.row[wr][1][lr]);
+    const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
     float sm = 0.0f;
-#pragma unroll 1
-    for (int q = 0; q < 3; ++q) sm = sm + ray_loss(rec[GT_RG + sub * 3 + q], S.row[wr][2 + sub * 3 + q][lr], d);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) sm = sm + ray_loss(rg[q], rp[q], d);
     sm = group_sum(sm, gm);
     const float v = (sm / 24.0f) / 2.0f;
-    const float eo1 = 1.0f + expf(-S.row[wr][26][lr]);
+    const float eo1 = 1.0f + expf(-obj);
     float neg;
     if (p.nc <= 80) {
         float prod = 1.0f;
@@ -798,7 +867,7 @@ __device__ __forceinline__ void window_pair(const Params& p, const float* __rest
     if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
     const int sx = ix - __float_as_int(rec[GT_ORG + 2 * l]), sy = iy - __float_as_int(rec[GT_ORG + 2 * l + 1]);
     if (sub == 0 && sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE)
-        p.wtab[((long long)b * p.Lmax + g) * P24_WT_STRIDE + l * P24_WSLOTS + sy * P24_WSIDE + sx] = cost;
+        p.wtab[(long long)slot * P24_WT_STRIDE + l * P24_WSLOTS + sy * P24_WSIDE + sx] = cost;
 }
 
 __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, AnchorShared& S, int b, int tile, bool staged) {
@@ -813,10 +882,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
         xs = p.x_shifts[a];
         ys = p.y_shifts[a];
     }
-    if (tid == 0) {
-        S.nitems = 0;
-        S.nwin = 0;
-    }
+    if (tid == 0) S.nitems = 0;
     S.cand[tid] = 0;
     const int n = p.num_gt[b];
     TMARK0(1, b * p.tiles + tile, 1);
@@ -863,11 +929,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
                 const float d2 = fmaf(dx, dx, dy * dy);
                 cheap |= d2 < h.z;
                 m |= (d2 <= h.w ? 1u : 0u) << j;
-                if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st) && active) {
-                    cheap = true;
-                    const int slot = atomicAdd(&S.nwin, 1);
-                    if (slot < WIN_CAP) S.witems[slot] = (unsigned)tid | ((unsigned)g << 8);
-                }
+                if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
             }
             const unsigned all = ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u);
             near[w] = no_prune ? all : m;
@@ -876,11 +938,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
             const float4 h = s_rec4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             cheap |= fmaf(dx, dx, dy * dy) < h.z;
-            if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st) && active) {
-                cheap = true;
-                const int slot = atomicAdd(&S.nwin, 1);
-                if (slot < WIN_CAP) S.witems[slot] = (unsigned)tid | ((unsigned)g << 8);
-            }
+            if (fmaxf(fabsf(dx), fabsf(dy)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st)) cheap = true;
         }
     }
     cheap = cheap && active;
@@ -917,37 +975,6 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     if (mine) S.cand[tid] = 1;
     __syncthreads();
     TMARK0(1, b * p.tiles + tile, 4);
-    // ---- the centre-window pairs of the tile: SimOTA costs into the GTs' window tables (8-lane groups) -------------
-    {
-        const unsigned gm = group_mask();
-        const int nwin = S.nwin;
-        if (nwin <= WIN_CAP) {
-            for (int wi = tid >> 3; wi < nwin; wi += P24_THREADS / 8) {
-                const unsigned it = S.witems[wi];
-                window_pair(p, s_rec, S, b, tile, (int)(it >> 8), (int)(it & 0xFF), gm);
-            }
-        } else {
-            // more pairs than the list holds (crowded coarse levels): every warp walks through the GTs again and hands the
-            // pairs of its own anchors to its four groups
-            const int grp = lane >> 3;
-            for (int g = 0; g < n; ++g) {
-                const float4 h = s_rec4[g * (GT_REC / 4)];
-                const bool hit = active && fmaxf(fabsf(h.x - xc), fabsf(h.y - yc)) < r25 && p24_in_centre(h.x, h.y, xc, yc, st);
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    unsigned mm = m;
-                    int pick = -1;
-                    for (int q = 0; q <= grp && mm; ++q) {  // the grp-th set bit (if there is one)
-                        pick = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        if (q < grp) pick = -1;
-                    }
-                    if (pick >= 0) window_pair(p, s_rec, S, b, tile, g, warp * 32 + pick, gm);
-                    for (int q = 0; q < 4 && m; ++q) m &= m - 1;  // four pairs per round
-                }
-            }
-        }
-    }
     TMARK0(1, b * p.tiles + tile, 9);
     {
         const int nitems = min(S.nitems, ITEM_CAP);
@@ -1070,16 +1097,39 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
             seed = s_seed;
         }
     }
-    while (item < n_anchor) {
-        __syncthreads();
-        if (tid == 0) s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);  // the next one, in flight meanwhile
-        // image-major order keeps an image's tiles (and its records) together in time
-        TMARK0(1, item, 0);
-        anchor_part(p, s_rec, S, item / p.tiles, item % p.tiles, staged);
-        TMARK0(1, item, 7);
-        staged = false;
-        __syncthreads();
-        item = s_item;
+    // ---- anchor tiles and window chunks (32 centre-window pairs of the batch's list, one per 8-lane group), taken in
+    // turns from their own ticket counters: the issue-bound window work and the latency-bound tile work share every SM --
+    const int n_wchunk = ((int)__ldcg(&p.ticket[TK_WTOT]) + P24_THREADS / 8 - 1) / (P24_THREADS / 8);
+    int wchunk = n_wchunk;  // (the first window ticket is drawn after the first tile)
+    bool first_round = true;
+    while (item < n_anchor || wchunk < n_wchunk || first_round) {
+        if (item < n_anchor) {
+            __syncthreads();
+            if (tid == 0) s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);  // the next one, in flight meanwhile
+            // image-major order keeps an image's tiles (and its records) together in time
+            TMARK0(1, item, 0);
+            anchor_part(p, s_rec, S, item / p.tiles, item % p.tiles, staged);
+            TMARK0(1, item, 7);
+            staged = false;
+            __syncthreads();
+            item = s_item;
+        }
+        if (first_round || wchunk < n_wchunk) {
+            __syncthreads();
+            if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_WIN], 1u);
+            if (!first_round) {
+                const int e = wchunk * (P24_THREADS / 8) + (tid >> 3);
+                TMARK0(1, min(3000 + wchunk, 4095), 0);
+                if (e < (int)__ldcg(&p.ticket[TK_WTOT])) {
+                    const int2 pr = __ldcg(p.wlist + e);
+                    window_pair(p, pr.x, pr.y, group_mask());
+                }
+                TMARK0(1, min(3000 + wchunk, 4095), 7);
+            }
+            __syncthreads();
+            wchunk = s_seed;
+            first_round = false;
+        }
     }
     TMARK0(1, 6000 + blockIdx.x, 1);
     pdl_trigger();
@@ -1856,6 +1906,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
         p.ticket[TK_LEFF] = 0u;
         p.ticket[TK_TAIL] = 0u;
         p.ticket[TK_SEED] = 0u;
+        p.ticket[TK_WIN] = 0u;
+        p.ticket[TK_WTOT] = 0u;
     }
     for (int i = tid; i < p.B; i += TAIL_THREADS) {
         p.seed_done[i] = 0;
@@ -2025,6 +2077,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.wtab = (float*)(ws + L.wtab);
     p.list = (float2*)(ws + L.list);
     p.cbits = (unsigned*)(ws + L.cbits);
+    p.wlist = (int2*)(ws + L.wlist);
     p.claimg = (int*)(ws + L.claimg);
     p.kreq = (int*)(ws + L.kreq);
     p.ntake = (int*)(ws + L.ntake);
@@ -2067,7 +2120,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     cudaError_t e = cudaSuccess;
     const int n_sm = p24::dev_info().n_sm;
     p24::prof_mark(0, st);
-    e = launch(k_prep, dim3(B), dim3(PREP_THREADS), 0, st, pdl, p);
+    e = launch(k_prep, dim3(B), dim3(PREP_THREADS), (size_t)Lmax * sizeof(int), st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     p24::prof_mark(1, st);
     {

@@ -69,11 +69,11 @@ print(f"   tiles: first start {us(tl[:, 0].min()):.1f}  last end {us(tl[:, 7].ma
 for lab, a, b_ in [("pre", 0, 1), ("recs+rows", 1, 3), ("gt loop+lists", 3, 4), ("poly items", 4, 5), ("cand sync", 5, 2),
                    ("wait seeds", 2, 8), ("far list", 8, 6), ("far items+out", 6, 7), ("tile total", 0, 7)]:
     stat(lab, tl[:, b_] - tl[:, a])
-if B * tiles < 4000:
-    wn = kp[B * tiles:min(4095, B * tiles + B * wl["G"] * 3)]
-    ok = (wn[:, 0] > 0) & (wn[:, 7] > 0)
-    print(f"   window items: first start {us(wn[ok, 0].min()):.1f}  last end {us(wn[ok, 7].max()):.1f}")
-    stat("window item", wn[ok, 7] - wn[ok, 0])
+wn = kp[3000:4095]
+ok = (wn[:, 0] > 0) & (wn[:, 7] > 0)
+if ok.any():
+    print(f"   window chunks: first start {us(wn[ok, 0].min()):.1f}  last end {us(wn[ok, 7].max()):.1f}")
+    stat("window chunk", wn[ok, 7] - wn[ok, 0])
 c = kt[:B * 8]
 tt0 = c[:, 0].min()
 print(f"== k_tail: first CTA start {us(tt0):.1f} us, last end {us(c[:, 9].max()):.1f} us")
