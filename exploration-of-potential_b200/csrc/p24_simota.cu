@@ -297,67 +297,64 @@ __device__ __forceinline__ unsigned window_slot_mask(const Params& p, float gcx,
 }
 
 #define PREP_THREADS 256
+#define PREP_WARPS (PREP_THREADS / 32)
+// k_prep: grid (B, ceil(Lmax / 8)); CTA (b, y) counts the image's labels (cheap: the label block stays in L2) and prepares
+// the GTs y * 8 .. y * 8 + 7, one warp each: record, window table, centre-window pairs
 __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ Params p) {
     // launched as a programmatic dependent of whatever precedes it in the stream (in back-to-back steps: the previous
     // step's k_tail, which triggers at once): resident early, it starts the moment that work is complete
     pdl_wait();
     pdl_trigger();
-    __shared__ int s_n;
-    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+    __shared__ int s_n, s_base;
+    __shared__ int s_wcnt[PREP_WARPS];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* lab = p.labels + (long long)b * p.lab_img_stride;
     const int n = block_count_labels(p, lab, &s_n);
-    if (tid == 0) {
+    if (tid == 0 && blockIdx.y == 0) {
         p.num_gt[b] = n;
         p.num_fg[b] = 0;  // k_tail adds the foreground anchors of the image's cluster CTAs
         atomicMax(&p.ticket[TK_LEFF], (unsigned)n);  // the batch's largest num_gt: k_pass lays its items out for it
     }
-    const int lane = tid & 31;
-    extern __shared__ int s_wcnt[];  // [Lmax] centre-window pairs per GT, then their exclusive prefix
-    __shared__ int s_base;
-    for (int g = warp; g < n; g += PREP_THREADS / 32) {
-        const float* row = lab + (long long)g * p.lab_row_stride;
+    const int g = blockIdx.y * PREP_WARPS + warp;
+    const float* row = lab + (long long)g * p.lab_row_stride;
+    unsigned wmask = 0u;
+    float gcx = 0.0f, gcy = 0.0f;
+    if (g < n) {
         float* rec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
         warp_gt_record(row, rec);
+        gcx = row[1];
+        gcy = row[2];
         // the GT's window cost table: origins of its 7 x 7 block of cells per level, every slot "not valid" until the
         // pair's cost is stored
         float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
         if (lane < 2 * P24_MAX_LEVELS) {
             const int l = lane >> 1;
-            const float o = __int_as_float(l < p.nlev ? window_origin(row[1 + (lane & 1)], p.lev[l].st) : 0);
+            const float o = __int_as_float(l < p.nlev ? window_origin(lane & 1 ? gcy : gcx, p.lev[l].st) : 0);
             rec[GT_ORG + lane] = o;
             tab[P24_WT_HDR + lane] = o;
         }
         for (int s = lane; s < P24_WT_HDR; s += 32) tab[s] = P24_POS_INF;
-        const int c = warp_sum_i(__popc(window_slot_mask(p, row[1], row[2])));
-        if (lane == 0) s_wcnt[g] = c;
+        wmask = window_slot_mask(p, gcx, gcy);
     }
+    // ---- the CTA's centre-window pairs (GT slot, anchor) appended to the batch's list: the window items of k_pass ----
+    const int cnt = warp_sum_i(__popc(wmask));
+    if (lane == 0) s_wcnt[warp] = cnt;
     __syncthreads();
-    // ---- the image's centre-window pairs (GT slot, anchor) appended to the batch's list: the window items of k_pass ----
-    if (warp == 0) {
-        int carry = 0;
-        for (int g0 = 0; g0 < n; g0 += 32) {
-            const int g = g0 + lane;
-            const int c = g < n ? s_wcnt[g] : 0;
-            int inc = c;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, off);
-                if (lane >= off) inc += t;
-            }
-            if (g < n) s_wcnt[g] = carry + inc - c;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < PREP_WARPS; ++w) {
+            const int c = s_wcnt[w];
+            s_wcnt[w] = tot;
+            tot += c;
         }
-        if (lane == 0) s_base = carry ? (int)atomicAdd(&p.ticket[TK_WTOT], (unsigned)carry) : 0;
+        s_base = tot ? (int)atomicAdd(&p.ticket[TK_WTOT], (unsigned)tot) : 0;
     }
     __syncthreads();
-    for (int g = warp; g < n; g += PREP_THREADS / 32) {
-        const float* row = lab + (long long)g * p.lab_row_stride;
-        const float gcx = row[1], gcy = row[2];
-        const unsigned m = window_slot_mask(p, gcx, gcy);
-        int at = s_base + s_wcnt[g];
+    if (g < n) {
+        int at = s_base + s_wcnt[warp];
 #pragma unroll
         for (int q = 0; q < (P24_WT_HDR + 31) / 32; ++q) {
-            const bool in = (m >> q) & 1u;
+            const bool in = (wmask >> q) & 1u;
             const unsigned bal = __ballot_sync(0xffffffffu, in);
             if (in) {
                 const int s = lane + 32 * q;
@@ -445,7 +442,7 @@ __device__ __forceinline__ float warp_bound_Hstar(float rg_lane, float d) {
 // -------------------------------------------------------------------------------------------
 #define SEED_FAR 3
 #define SEED_DISC 3                                    // points per (far GT, level): centre, far end of the inscribed disc, 2 strides out
-#define SEED_VPW 6
+#define SEED_VPW 4
 #define SEED_NV (SEED_VPW * P24_WARPS)                 // polygon vertices (of any GT of the image) far from this GT: 6 per warp
 #define SEED_MAX (SEED_FAR * P24_MAX_LEVELS * SEED_DISC + SEED_NV * P24_MAX_LEVELS)   // 132 <= P24_THREADS
 
@@ -468,12 +465,17 @@ __device__ __forceinline__ int cell_index(float q, float st) {
     return (int)v;
 }
 
-__device__ void seed_part(const Params& p, SeedShared& S, int b, int g, int dbg_row = 0) {
+__device__ void seed_part(const Params& p, SeedShared& S, float* __restrict__ s_recs, int b, int g, int dbg_row = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.num_gt[b];
-    const float* recs = p.gt_rec + (long long)b * p.Lmax * GT_REC;
+    const float* recs = s_recs;  // the image's records, staged below (k_prep's part of them: far2 / T are not read here)
     float* myrec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
     __syncthreads();  // the scratch may still be in use by the previous item
+    {
+        const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
+        float4* dst = reinterpret_cast<float4*>(s_recs);
+        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) dst[i] = __ldcg(gsrc + i);
+    }
     if (tid < GT_REC) S.rec[tid] = myrec[tid];
     if (tid < SEED_MAX) {
         S.val[tid] = P24_NEG_INF;
@@ -490,8 +492,8 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g, int dbg_
             int hb = -1;
             for (int h = lane; h < n; h += 32) {
                 const float* r = recs + h * GT_REC;
-                const float dx = __ldcg(r + GT_CX) - gcx, dy = __ldcg(r + GT_CY) - gcy;
-                const float kk = sqrtf(fmaf(dx, dx, dy * dy)) + __ldcg(r + GT_RGMAX);
+                const float dx = r[GT_CX] - gcx, dy = r[GT_CY] - gcy;
+                const float kk = sqrtf(fmaf(dx, dx, dy * dy)) + r[GT_RGMAX];
                 if (kk > key) {
                     key = kk;
                     hb = h;
@@ -508,7 +510,7 @@ __device__ void seed_part(const Params& p, SeedShared& S, int b, int g, int dbg_
             for (int i = tid; i < n * P24_RAYS; i += P24_THREADS) {
                 const int h = i / P24_RAYS, k = i - h * P24_RAYS;
                 const float* r = recs + h * GT_REC;
-                const float dx = __ldcg(r + GT_VX + k) - gcx, dy = __ldcg(r + GT_VY + k) - gcy;
+                const float dx = r[GT_VX + k] - gcx, dy = r[GT_VY + k] - gcy;
                 const float d2 = fmaf(dx, dx, dy * dy);
                 if (d2 > best) {
                     best = d2;
@@ -1019,14 +1021,38 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
         __syncthreads();
     }
     if (cand && !no_filter) {
-        for (int g = 0; g < n; ++g) {
-            const float4 h = s_rec4[g * (GT_REC / 4)];
-            const float px = h.x - pcx, py = h.y - pcy;
-            if (tiny || !(fmaf(px, px, py * py) < s_rec[g * GT_REC + GT_FAR2])) {
-                const int slot = atomicAdd(&S.nitems, 1);
-                if (slot < ITEM_CAP) S.items[slot] = (unsigned)tid | ((unsigned)g << 8);
-                else far_pair(p, s_rec, S, b, tile, g, tid);
+        unsigned fm[4] = {0u, 0u, 0u, 0u};
+        int cnt = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int ge = min(32, n - w * 32);
+            unsigned m = 0u;
+            for (int j = 0; j < ge; ++j) {
+                const int g = w * 32 + j;
+                const float4 h = s_rec4[g * (GT_REC / 4)];
+                const float px = h.x - pcx, py = h.y - pcy;
+                m |= (!(fmaf(px, px, py * py) < s_rec[g * GT_REC + GT_FAR2]) ? 1u : 0u) << j;
             }
+            if (tiny) m = ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u);
+            fm[w] = m;
+            cnt += __popc(m);
+        }
+        int at = cnt ? atomicAdd(&S.nitems, cnt) : 0;  // one reservation for all of the anchor's pairs
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            unsigned m = fm[w];
+            while (m) {
+                const int g = w * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                if (at < ITEM_CAP) S.items[at] = (unsigned)tid | ((unsigned)g << 8);
+                else far_pair(p, s_rec, S, b, tile, g, tid);
+                ++at;
+            }
+        }
+        for (int g = 128; g < n; ++g) {  // more than 128 GTs: the rest in place
+            const float* rec = s_rec + g * GT_REC;
+            const float px = rec[GT_CX] - pcx, py = rec[GT_CY] - pcy;
+            if (tiny || !(fmaf(px, px, py * py) < rec[GT_FAR2])) far_pair(p, s_rec, S, b, tile, g, tid);
         }
     }
     // ---- per-anchor outputs, candidate bitmap and count, the all-anchor objectness term -------------------------
@@ -1061,7 +1087,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
 // (GT, level) centre-window items.  Launched as a programmatic dependent of k_prep: the first tile's rows are in flight
 // before the CTA waits for the records.
 __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__ Params p) {
-    extern __shared__ float4 s_dyn4[];   // [Lmax * GT_REC] floats: the image's records (anchor tiles); seed scratch
+    extern __shared__ float4 s_dyn4[];   // [Lmax * GT_REC] floats: the image's records | the scratch of the seed items
     __shared__ AnchorShared S;
     __shared__ int s_item, s_seed;
     float* s_rec = reinterpret_cast<float*>(s_dyn4);
@@ -1084,14 +1110,14 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
     const int leff = (int)__ldcg(&p.ticket[TK_LEFF]);  // the batch's largest num_gt
     // ---- seed items: image fastest, so that the real GT rows (valid rows come first) are drawn first ---------------
     {
-        SeedShared& SS = *reinterpret_cast<SeedShared*>(s_dyn4);
+        SeedShared& SS = *reinterpret_cast<SeedShared*>(s_rec + (size_t)p.Lmax * GT_REC);
         const int n_seed = p.B * leff;
         while (seed < n_seed) {
             __syncthreads();
             if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_SEED], 1u);  // the next one, in flight meanwhile
             const int g = seed / p.B, b = seed - g * p.B;
             TMARK0(1, 4096 + seed, 0);
-            if (g < p.num_gt[b]) seed_part(p, SS, b, g, 4096 + seed);
+            if (g < p.num_gt[b]) seed_part(p, SS, s_rec, b, g, 4096 + seed);
             TMARK0(1, 4096 + seed, 1);
             __syncthreads();
             seed = s_seed;
@@ -1432,19 +1458,27 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
     const float* img = p.outputs + (long long)b * p.img_stride;
     ok = true;
     float lmax = P24_NEG_INF;
-    for (int i0 = 0; i0 < lc; i0 += 128) {  // four independent loads per lane in flight
-        float2 e[4];
+    float2 e0[8];  // the first 256 entries stay in registers (most lists end there: one round trip for the whole list)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
+        const int i = 32 * u + lane;
+        e0[u] = i < lc ? __ldcg(lst + i) : make_float2(P24_NEG_INF, 0.0f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        // bound = value + 2e-5 (+- 3e-6) for an all-apart pair: bound - 7e-5 is a certified lower bound
+        if (__float_as_int(e0[u].y) & 0x80000000) lmax = fmaxf(lmax, e0[u].x - 7e-5f);
+    }
+    for (int i0 = 256; i0 < lc; i0 += 256) {  // eight independent loads per lane in flight
+        float2 e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
             const int i = i0 + 32 * u + lane;
             e[u] = i < lc ? __ldcg(lst + i) : make_float2(P24_NEG_INF, 0.0f);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const bool apart = (__float_as_int(e[u].y) & 0x80000000) != 0;
-            // bound = value + 2e-5 (+- 3e-6) for an all-apart pair: bound - 7e-5 is a certified lower bound
-            if (apart) lmax = fmaxf(lmax, e[u].x - 7e-5f);
-        }
+        for (int u = 0; u < 8; ++u)
+            if (__float_as_int(e[u].y) & 0x80000000) lmax = fmaxf(lmax, e[u].x - 7e-5f);
     }
     TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 2);
     float tref = rec[GT_T];
@@ -1456,12 +1490,12 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
     }
     TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 3);
     int nsurv = 0;
-    for (int i0 = 0; i0 < lc; i0 += 256) {  // eight independent loads per lane in flight
+    for (int i0 = 0; i0 < lc; i0 += 256) {
         float2 e[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + 32 * u + lane;
-            e[u] = i < lc ? __ldcg(lst + i) : make_float2(P24_NEG_INF, 0.0f);
+            e[u] = i0 == 0 ? e0[u] : (i < lc ? __ldcg(lst + i) : make_float2(P24_NEG_INF, 0.0f));
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -1970,10 +2004,7 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
     finalize_warp(sums28, state26, result54, weights_n27);
 }
 
-size_t pass_smem(int Lmax) {
-    const size_t rec = (size_t)Lmax * GT_REC * sizeof(float);
-    return rec > sizeof(SeedShared) ? rec : sizeof(SeedShared);
-}
+size_t pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float) + sizeof(SeedShared); }
 size_t tail_smem(int Lmax, int nc) {
     const size_t cap = ((size_t)Lmax * P24_TOPK + TAIL_CL - 1) / TAIL_CL;
     size_t b = (size_t)Lmax * GT_REC * sizeof(float);                 // recs
@@ -2120,7 +2151,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     cudaError_t e = cudaSuccess;
     const int n_sm = p24::dev_info().n_sm;
     p24::prof_mark(0, st);
-    e = launch(k_prep, dim3(B), dim3(PREP_THREADS), (size_t)Lmax * sizeof(int), st, pdl, p);
+    e = launch(k_prep, dim3(B, (Lmax + PREP_WARPS - 1) / PREP_WARPS), dim3(PREP_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
     p24::prof_mark(1, st);
     {
