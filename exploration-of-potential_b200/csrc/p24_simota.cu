@@ -440,23 +440,13 @@ __device__ __forceinline__ float warp_bound_Hstar(float rg_lane, float d) {
 // is a certified lower bound of the 10th largest pair value, and far2 = the squared centre distance below which
 // H*(d) < T: the anchor tiles evaluate only the (GT, candidate) pairs beyond it.
 // -------------------------------------------------------------------------------------------
-#define SEED_FAR 3
-#define SEED_DISC 3                                    // points per (far GT, level): centre, far end of the inscribed disc, 2 strides out
-#define SEED_VPW 4
-#define SEED_NV (SEED_VPW * P24_WARPS)                 // polygon vertices (of any GT of the image) far from this GT: 6 per warp
-#define SEED_MAX (SEED_FAR * P24_MAX_LEVELS * SEED_DISC + SEED_NV * P24_MAX_LEVELS)   // 132 <= P24_THREADS
+#define SEED_FAR 3      // farthest GTs whose centre-window / inscribed-disc anchors serve as seeds
+#define SEED_NV 16      // far polygon vertices (of any GT of the image), each on the two levels that suit this GT best
+#define SEED_GTS P24_WARPS   // GTs per seed item: one warp each, no block-wide step after the records are staged
 
 struct SeedShared {
-    float rec[GT_REC];
-    int far[SEED_FAR];
-    int vsel[SEED_NV];        // (GT << 5) | vertex
-    int hash[256];            // distinct seed anchors
-    float val[SEED_MAX];
-    int anc[SEED_MAX];
-    float top[P24_WARPS * P24_TOPK];
-    float tmp[P24_WARPS * P24_TOPK];
-    int nvert, ntmp;
-    float T;
+    int vsel[P24_WARPS][SEED_NV];   // (GT << 5) | vertex
+    int far[P24_WARPS][4];
 };
 
 __device__ __forceinline__ int cell_index(float q, float st) {
@@ -465,29 +455,63 @@ __device__ __forceinline__ int cell_index(float q, float st) {
     return (int)v;
 }
 
-__device__ void seed_part(const Params& p, SeedShared& S, float* __restrict__ s_recs, int b, int g, int dbg_row = 0) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = p.num_gt[b];
-    const float* recs = s_recs;  // the image's records, staged below (k_prep's part of them: far2 / T are not read here)
+// One seed point of GT `rec` by one lane: the grid cell of (qx, qy) on level l.  When the cell's anchor is certainly a
+// candidate (the very tests of the anchor tiles: inscribed disc / centre window / polygon of GT h) and every ray of the
+// pair is in the "apart" branch (the reference's own fp32 comparison), the pair value has the closed form
+// (1/48) sum_k (2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2), evaluated in fast arithmetic to within 3e-6: returns
+// (value - 1e-5, anchor), a certified LOWER bound of a candidate's pair value; (-inf, -1) otherwise.
+__device__ __forceinline__ KV seed_point(const Params& p, const float* __restrict__ rec, const float* __restrict__ h, int b, int l,
+                                         float qx, float qy, bool valid) {
+    KV out = {P24_NEG_INF, -1};
+    const Level lv = p.lev[l];
+    const float st = lv.st;
+    const int ix = cell_index(qx, st), iy = cell_index(qy, st);
+    if (!(valid && ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H)) return out;
+    const int a = lv.off + iy * lv.W + ix;
+    // the anchor's row is requested right away: it is in flight while the candidate tests run
+    const float* row = p.outputs + (long long)b * p.img_stride + (long long)a * p.row_stride;
+    float rpv[P24_RAYS];
+#pragma unroll
+    for (int k = 0; k < P24_RAYS; ++k) rpv[k] = row[2 + k];
+    const float pcx = row[0], pcy = row[1];
+    // (the grid is the head's, validated by the host side: x_shift = column, y_shift = row, one stride per level)
+    const float xc = p24_anchor_centre((float)ix, st), yc = p24_anchor_centre((float)iy, st);
+    const float hcx = h[GT_CX], hcy = h[GT_CY];
+    const float dx = hcx - xc, dy = hcy - yc;
+    bool cand = fmaf(dx, dx, dy * dy) < h[GT_RIN2];
+    if (!cand) cand = p24_in_centre(hcx, hcy, xc, yc, st);
+    if (!cand) cand = p24_in_polygon(h + GT_VX, h + GT_VY, xc, yc);
+    if (!cand) return out;
+    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], pcx, pcy);
+    float sm = 0.0f;
+    bool apart = true;
+#pragma unroll
+    for (int k = 0; k < P24_RAYS; ++k) {
+        const float rg = rec[GT_RG + k], rp = rpv[k];
+        apart = apart && (d >= rg + rp) && (rp >= 0.25f);
+        const float t = (rg + rp) + d;
+        sm += 2.0f - __fdividef(4.0f * fmaf(rg, rg, rp * rp), t * t);
+    }
+    // (a seed with a ray that is not apart would need the exact evaluation: skipped, far seeds are apart)
+    const float v = sm * (1.0f / 48.0f) - 1e-5f;
+    if (apart && v == v) {
+        out.v = v;
+        out.i = a;
+    }
+    return out;
+}
+
+// the seed work of one GT, by one warp.  recs: the image's records in shared memory.
+__device__ void seed_gt(const Params& p, SeedShared& S, const float* __restrict__ recs, int b, int g, int n) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* rec = recs + g * GT_REC;
     float* myrec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
-    __syncthreads();  // the scratch may still be in use by the previous item
-    {
-        const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
-        float4* dst = reinterpret_cast<float4*>(s_recs);
-        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) dst[i] = __ldcg(gsrc + i);
-    }
-    if (tid < GT_REC) S.rec[tid] = myrec[tid];
-    if (tid < SEED_MAX) {
-        S.val[tid] = P24_NEG_INF;
-        S.anc[tid] = -1;
-    }
-    __syncthreads();
-    const float gcx = S.rec[GT_CX], gcy = S.rec[GT_CY];
-    const bool filter = !(p.flags & P24_F_NO_FILTER) && S.rec[GT_RGMIN] >= 0.25f && S.rec[GT_RGMAX] < 1.0e6f;
+    const float gcx = rec[GT_CX], gcy = rec[GT_CY];
+    const bool filter = !(p.flags & P24_F_NO_FILTER) && rec[GT_RGMIN] >= 0.25f && rec[GT_RGMAX] < 1.0e6f;
+    float T = P24_NEG_INF;
     if (filter) {
-        // ---- the SEED_FAR farthest GTs (centre distance + their largest ray), this GT included: warp 0, every lane's best
-        // by rank among the lanes ------------------------------------------------------------------------------------------
-        if (warp == 0) {
+        // ---- the SEED_FAR farthest GTs (centre distance + their largest ray), this GT included ---------------------
+        {
             float key = P24_NEG_INF;
             int hb = -1;
             for (int h = lane; h < n; h += 32) {
@@ -500,14 +524,15 @@ __device__ void seed_part(const Params& p, SeedShared& S, float* __restrict__ s_
                 }
             }
             const int rk = lane_rank<true>(hb >= 0 ? key : P24_NEG_INF);
-            if (rk < SEED_FAR) S.far[rk] = hb;   // (-1: fewer GTs than SEED_FAR)
+            if (rk < SEED_FAR) S.far[warp][rk] = hb;   // (-1: fewer GTs than SEED_FAR)
         }
-        // ---- polygon vertices of the image that are far from this GT's centre: every thread keeps the farthest of its
-        // share, every warp passes on its SEED_VPW farthest (any subset of far vertices serves: better ones only tighten T)
+        // ---- the polygon vertices of the image that are far from this GT's centre: every lane keeps the farthest of its
+        // share, the SEED_NV farthest lanes pass theirs on (any subset of far vertices serves: better ones tighten T) ----
+        float dfar2 = 0.0f;
         {
             float best = P24_NEG_INF;
             int bi = -1;
-            for (int i = tid; i < n * P24_RAYS; i += P24_THREADS) {
+            for (int i = lane; i < n * P24_RAYS; i += 32) {
                 const int h = i / P24_RAYS, k = i - h * P24_RAYS;
                 const float* r = recs + h * GT_REC;
                 const float dx = r[GT_VX + k] - gcx, dy = r[GT_VY + k] - gcy;
@@ -518,202 +543,136 @@ __device__ void seed_part(const Params& p, SeedShared& S, float* __restrict__ s_
                 }
             }
             const int rk = lane_rank<true>(bi >= 0 ? best : P24_NEG_INF);
-            if (rk < SEED_VPW) S.vsel[warp * SEED_VPW + rk] = bi;
-            S.hash[tid] = -1;
-            if (tid == 0) S.nvert = SEED_NV;
+            if (rk < SEED_NV) S.vsel[warp][rk] = bi;
+            dfar2 = warp_max(best);
         }
-        __syncthreads();
-        TMARK0(1, dbg_row, 2);
-        const int nfar = SEED_FAR, nvert = S.nvert;
-        // ---- one seed point per thread -> grid cell -> certainly a candidate? -> value ---------------------------
-        const int n_disc = nfar * p.nlev * SEED_DISC;
-        const int n_pts = n_disc + nvert * p.nlev;
-        if (tid < n_pts) {
-            int hsel, l;
-            float qx, qy, st;
-            if (tid < n_disc) {
-                const int f = tid / (p.nlev * SEED_DISC), r0 = tid - f * (p.nlev * SEED_DISC);
-                l = r0 / SEED_DISC;
-                const int pt = r0 - l * SEED_DISC;
-                hsel = max(S.far[f], 0);
-                const float* h = recs + hsel * GT_REC;
-                st = p.lev[l].st;
-                float ux = h[GT_CX] - gcx, uy = h[GT_CY] - gcy;
-                const float nn = fmaf(ux, ux, uy * uy);
-                if (nn > 1e-12f) {
-                    const float inv = rsqrtf(nn);
-                    ux *= inv;
-                    uy *= inv;
-                } else {
-                    ux = 1.0f;
-                    uy = 0.0f;
-                }
-                const float rho = pt == 0 ? 0.0f : (pt == 1 ? fmaxf(0.0f, sqrtf(h[GT_RIN2]) - 0.75f * st) : 2.0f * st);
-                qx = fmaf(ux, rho, h[GT_CX]);
-                qy = fmaf(uy, rho, h[GT_CY]);
-            } else {
-                const int r0 = tid - n_disc;
-                const int vi = r0 / p.nlev;
-                l = r0 - vi * p.nlev;
-                const int hv = max(S.vsel[vi], 0);
-                hsel = hv >> 5;
-                const int k = hv & 31;
-                const float* h = recs + hsel * GT_REC;
-                st = p.lev[l].st;
-                // one stride inside the vertex, on the ray from the GT's own centre
-                const float rr = h[GT_RG + k];
-                const float fct = fmaxf(0.0f, __fdividef(rr - st, fmaxf(rr, 1e-6f)));
-                qx = fmaf(h[GT_VX + k] - h[GT_CX], fct, h[GT_CX]);
-                qy = fmaf(h[GT_VY + k] - h[GT_CY], fct, h[GT_CY]);
-            }
-            const float* h = recs + hsel * GT_REC;
-            const Level lv = p.lev[l];
-            const float hcx = h[GT_CX], hcy = h[GT_CY];
-            const int ix = cell_index(qx, st), iy = cell_index(qy, st);
-            const bool pick_ok = tid < n_disc ? S.far[tid / (p.nlev * SEED_DISC)] >= 0 : S.vsel[(tid - n_disc) / p.nlev] >= 0;
-            if (pick_ok && ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H) {
-                const int a = lv.off + iy * lv.W + ix;
-                // the anchor's row is requested right away: it is in flight while the candidate tests run
-                const float* row = p.outputs + (long long)b * p.img_stride + (long long)a * p.row_stride;
-                float rpv[P24_RAYS];
-#pragma unroll
-                for (int k = 0; k < P24_RAYS; ++k) rpv[k] = row[2 + k];
-                const float pcx = row[0], pcy = row[1];
-                // the grid is the head's (validated by the host side): x_shift = column, y_shift = row, one stride per level
-                const float xc = p24_anchor_centre((float)ix, st), yc = p24_anchor_centre((float)iy, st);
-                // the very tests of the anchor tiles: inscribed disc, centre window, polygon
-                const float dx = hcx - xc, dy = hcy - yc;
-                bool cand = fmaf(dx, dx, dy * dy) < h[GT_RIN2];
-                if (!cand) cand = p24_in_centre(hcx, hcy, xc, yc, st);
-                if (!cand) cand = p24_in_polygon(h + GT_VX, h + GT_VY, xc, yc);
-                if (tid == n_pts - 1) TMARK(1, dbg_row, 3);
-                if (cand) {
-                    // a certified LOWER bound of the pair value: when every ray is in the "apart" branch (the reference's
-                    // own fp32 comparison) the value has the closed form (1/48) sum_k (2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2),
-                    // evaluated in fast arithmetic to within 3e-6
-                    const float d = p24_centre_dist(gcx, gcy, pcx, pcy);
-                    float sm = 0.0f;
-                    bool apart = true;
-#pragma unroll
-                    for (int k = 0; k < P24_RAYS; ++k) {
-                        const float rg = S.rec[GT_RG + k], rp = rpv[k];
-                        apart = apart && (d >= rg + rp) && (rp >= 0.25f);
-                        const float t = (rg + rp) + d;
-                        sm += 2.0f - __fdividef(4.0f * fmaf(rg, rg, rp * rp), t * t);
-                    }
-                    // (a seed with a ray that is not apart would need the exact evaluation: skipped, far seeds are apart)
-                    float v = apart ? sm * (1.0f / 48.0f) - 1e-5f : P24_NEG_INF;
-                    if (!(v == v)) v = P24_NEG_INF;
-                    S.val[tid] = v;
-                    S.anc[tid] = a;
-                }
-            }
-        }
-        __syncthreads();
-        TMARK0(1, dbg_row, 4);
-        __syncthreads();
-        TMARK0(1, dbg_row, 5);
-        // ---- the 10th largest value over the distinct seed anchors (first arrival of an anchor in a small hash) -----
-        if (tid == 0) S.T = P24_NEG_INF;
-        float v = P24_NEG_INF;
-        if (tid < n_pts) {
-            v = S.val[tid];
-            const int a = S.anc[tid];
-            if (a >= 0 && v > P24_NEG_INF) {
-                unsigned h = ((unsigned)a * 2654435761u) >> 24;
-                for (;;) {
-                    const int old = atomicCAS(&S.hash[h], -1, a);
-                    if (old == -1) break;   // mine
-                    if (old == a) {          // a copy of an anchor that is already in
-                        v = P24_NEG_INF;
-                        break;
-                    }
-                    h = (h + 1) & 255u;
-                }
-            } else {
-                v = P24_NEG_INF;
-            }
-            S.val[tid] = v;
-        }
-        // every warp's 10 largest (rank among its lanes), then warp 0 picks the 10th largest of those
+        __syncwarp();
+        // the two levels whose typical predicted radius (about 1.1 strides) is closest to the radius that maximises the
+        // bound at the far distance, rp* = rg^2 / (rg + d)
+        int lvA = 0, lvB = 0;
         {
-            const int rk = lane_rank<true>(v);
-            if (rk < P24_TOPK) S.top[warp * P24_TOPK + rk] = v;
-            if (tid == 0) S.ntmp = 0;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // the 10th largest of the lanes' largest is a lower bound t0 of the 10th largest; the values >= t0 (a dozen) are
-            // ranked by counting
-            float e[3];
-            float lm = P24_NEG_INF;
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int i = lane + 32 * u;
-                e[u] = i < P24_WARPS * P24_TOPK ? S.top[i] : P24_NEG_INF;
-                lm = fmaxf(lm, e[u]);
-            }
-            const int r0 = lane_rank<true>(lm);
-            const unsigned pick = __ballot_sync(0xffffffffu, r0 == P24_TOPK - 1);
-            const float t0 = __shfl_sync(0xffffffffu, lm, __ffs(pick) - 1);
-            if (t0 > P24_NEG_INF) {
-#pragma unroll
-                for (int u = 0; u < 3; ++u)
-                    if (e[u] >= t0) S.tmp[atomicAdd(&S.ntmp, 1)] = e[u];
-                __syncwarp();
-                const int m = S.ntmp;
-                for (int i = lane; i < m; i += 32) {
-                    const float vi = S.tmp[i];
-                    int rank = 0;
-                    for (int j = 0; j < m; ++j) rank += kv_gt(S.tmp[j], j, vi, i) ? 1 : 0;
-                    if (rank == P24_TOPK - 1) S.T = vi;
+            const float rstar = __fdividef(rec[GT_RGMS], rec[GT_RGMEAN] + sqrtf(fmaxf(dfar2, 0.0f)) + 1e-6f);
+            float eA = P24_POS_INF, eB = P24_POS_INF;
+            for (int l = 0; l < p.nlev; ++l) {
+                const float e = fabsf(1.13f * p.lev[l].st - rstar);
+                if (e < eA) {
+                    eB = eA;
+                    lvB = lvA;
+                    eA = e;
+                    lvA = l;
+                } else if (e < eB) {
+                    eB = e;
+                    lvB = l;
                 }
             }
+            if (p.nlev < 2) lvB = lvA;
         }
-        __syncthreads();
-    } else {
-        if (tid == 0) S.T = P24_NEG_INF;
-        __syncthreads();
+        // ---- round 1: SEED_NV far vertices x two levels, one point per lane (one stride inside the vertex, on the ray from
+        // the vertex's own GT centre) ------------------------------------------------------------------------------------
+        KV s1, s2;
+        {
+            const int hv = S.vsel[warp][lane & (SEED_NV - 1)];
+            const int l = lane < SEED_NV ? lvA : lvB;
+            const float* h = recs + (max(hv, 0) >> 5) * GT_REC;
+            const int k = max(hv, 0) & 31;
+            const float st = p.lev[l].st;
+            const float rr = h[GT_RG + k];
+            const float fct = fmaxf(0.0f, __fdividef(rr - st, fmaxf(rr, 1e-6f)));
+            const float qx = fmaf(h[GT_VX + k] - h[GT_CX], fct, h[GT_CX]);
+            const float qy = fmaf(h[GT_VY + k] - h[GT_CY], fct, h[GT_CY]);
+            s1 = seed_point(p, rec, h, b, l, qx, qy, hv >= 0 && (lane < SEED_NV || lvB != lvA));
+        }
+        // ---- round 2: the SEED_FAR farthest GTs: centre, far end of the inscribed disc, 2 strides out, on every level ------
+        {
+            const int f = lane / 9, r0 = lane - f * 9;  // 3 GTs x 3 levels x 3 points = 27 lanes
+            const int l = r0 / 3, pt = r0 - l * 3;
+            const int hs = f < SEED_FAR ? S.far[warp][f] : -1;
+            const float* h = recs + max(hs, 0) * GT_REC;
+            const float st = p.lev[min(l, p.nlev - 1)].st;
+            float ux = h[GT_CX] - gcx, uy = h[GT_CY] - gcy;
+            const float nn = fmaf(ux, ux, uy * uy);
+            if (nn > 1e-12f) {
+                const float inv = rsqrtf(nn);
+                ux *= inv;
+                uy *= inv;
+            } else {
+                ux = 1.0f;
+                uy = 0.0f;
+            }
+            const float rho = pt == 0 ? 0.0f : (pt == 1 ? fmaxf(0.0f, sqrtf(h[GT_RIN2]) - 0.75f * st) : 2.0f * st);
+            s2 = seed_point(p, rec, h, b, min(l, p.nlev - 1), fmaf(ux, rho, h[GT_CX]), fmaf(uy, rho, h[GT_CY]),
+                            hs >= 0 && lane < 27 && l < p.nlev);
+        }
+        // ---- the 10th largest value over the distinct seed anchors (64 values, two per lane) --------------------------
+        {
+            // a copy of an anchor counts once: the earlier (round, lane) keeps it
+            bool d1 = false, d2 = false;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const int a1 = __shfl_sync(0xffffffffu, s1.i, j), a2 = __shfl_sync(0xffffffffu, s2.i, j);
+                d1 = d1 || (s1.i >= 0 && a1 == s1.i && j < lane);
+                d2 = d2 || (s2.i >= 0 && (a1 == s2.i || (a2 == s2.i && j < lane)));
+            }
+            const float v1 = d1 ? P24_NEG_INF : s1.v, v2 = d2 ? P24_NEG_INF : s2.v;
+            // rank of each of my two values among all 64 (ties: round 1 first, then the lower lane)
+            int r1 = 0, r2 = 0;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const float o1 = __shfl_sync(0xffffffffu, v1, j), o2 = __shfl_sync(0xffffffffu, v2, j);
+                r1 += (kv_gt(o1, j, v1, lane) ? 1 : 0) + (o2 > v1 ? 1 : 0);
+                r2 += (o1 >= v2 ? 1 : 0) + (kv_gt(o2, j, v2, lane) ? 1 : 0);
+            }
+            const float cand_T = (r1 == P24_TOPK - 1) ? v1 : ((r2 == P24_TOPK - 1) ? v2 : P24_NEG_INF);
+            T = warp_max(cand_T);
+        }
     }
-    TMARK0(1, dbg_row, 6);
-    // ---- far2: pairs closer than D cannot reach T.  H*(d) + 3e-5 < T is monotone in d: three rounds of a 32-way search by
-    // warp 0, every lane evaluating the bound at its own distance ------------------------------------------------------
-    if (warp == 0) {
-        const float T = S.T;
-        float far2 = 0.0f;  // 0: every pair is evaluated
-        if (T > P24_NEG_INF) {
-            float lo = 0.0f, step = 256.0f;  // pairs farther apart than 32 * 256 px are always evaluated
+    // ---- far2: pairs closer than D cannot reach T.  H*(d) + 3e-5 < T is monotone in d: three rounds of a 32-way search,
+    // every lane evaluating the bound at its own distance -----------------------------------------------------------------
+    float far2 = 0.0f;  // 0: every pair is evaluated
+    if (T > P24_NEG_INF) {
+        float lo = 0.0f, step = 256.0f;  // pairs farther apart than 32 * 256 px are always evaluated
 #pragma unroll 1
-            for (int round = 0; round < 3; ++round) {
-                const float dd = lo + step * (float)lane;
-                float sum = 0.0f;
+        for (int round = 0; round < 3; ++round) {
+            const float dd = lo + step * (float)lane;
+            float sum = 0.0f;
 #pragma unroll
-                for (int k = 0; k < P24_RAYS; ++k) {
-                    const float rg = S.rec[GT_RG + k];
-                    const float q = rg + dd;
-                    sum += fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, fmaf(q, q, rg * rg)));
-                }
-                const bool below = sum * (1.0f / 48.0f) + 3e-5f < T;      // true for a prefix of the lanes (monotone)
-                const unsigned bal = __ballot_sync(0xffffffffu, below);
-                const int nb = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;  // length of the leading run of lanes
-                if (nb == 0) {
-                    step = 0.0f;  // even lo is not below: D = lo
-                    break;
-                }
-                lo = lo + step * (float)(nb - 1);
-                step = step * (1.0f / 32.0f);
+            for (int k = 0; k < P24_RAYS; ++k) {
+                const float rg = rec[GT_RG + k];
+                const float q = rg + dd;
+                sum += fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, fmaf(q, q, rg * rg)));
             }
-            const float D = fmaxf(0.0f, lo * (1.0f - 1e-4f) - 0.02f);
-            far2 = D * D;
-            if (!(far2 == far2)) far2 = 0.0f;
+            const bool below = sum * (1.0f / 48.0f) + 3e-5f < T;      // true for a prefix of the lanes (monotone)
+            const unsigned bal = __ballot_sync(0xffffffffu, below);
+            const int nb = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;  // length of the leading run of lanes
+            if (nb == 0) break;  // even lo is not below: D = lo
+            lo = lo + step * (float)(nb - 1);
+            step = step * (1.0f / 32.0f);
         }
-        if (lane == 0) {
-            myrec[GT_FAR2] = far2;
-            myrec[GT_T] = T;
-            __threadfence();
-            atomicAdd(&p.seed_done[b], 1);
-        }
+        const float D = fmaxf(0.0f, lo * (1.0f - 1e-4f) - 0.02f);
+        far2 = D * D;
+        if (!(far2 == far2)) far2 = 0.0f;
     }
+    if (lane == 0) {
+        myrec[GT_FAR2] = far2;
+        myrec[GT_T] = T;
+        __threadfence();
+        atomicAdd(&p.seed_done[b], 1);
+    }
+}
+
+// one seed item: the GTs c * 8 .. c * 8 + 7 of image b, one warp each
+__device__ void seed_part(const Params& p, SeedShared& S, float* __restrict__ s_recs, int b, int c) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int n = p.num_gt[b];
+    __syncthreads();  // the scratch may still be in use by the previous item
+    {
+        const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
+        float4* dst = reinterpret_cast<float4*>(s_recs);
+        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) dst[i] = __ldcg(gsrc + i);
+    }
+    __syncthreads();
+    const int g = c * SEED_GTS + warp;
+    if (g < n) seed_gt(p, S, s_recs, b, g, n);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1108,16 +1067,18 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
     pdl_wait();  // the records come from k_prep
     TMARK0(1, 6000 + blockIdx.x, 0);
     const int leff = (int)__ldcg(&p.ticket[TK_LEFF]);  // the batch's largest num_gt
-    // ---- seed items: image fastest, so that the real GT rows (valid rows come first) are drawn first ---------------
+    // ---- seed items (8 GTs of one image, a warp each): image fastest, so that the real GT rows (valid rows come first)
+    // are drawn first ----------------------------------------------------------------------------------------------------
     {
         SeedShared& SS = *reinterpret_cast<SeedShared*>(s_rec + (size_t)p.Lmax * GT_REC);
-        const int n_seed = p.B * leff;
+        const int n_chunk = (leff + SEED_GTS - 1) / SEED_GTS;
+        const int n_seed = p.B * n_chunk;
         while (seed < n_seed) {
             __syncthreads();
             if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_SEED], 1u);  // the next one, in flight meanwhile
-            const int g = seed / p.B, b = seed - g * p.B;
+            const int c = seed / p.B, b = seed - c * p.B;
             TMARK0(1, 4096 + seed, 0);
-            if (g < p.num_gt[b]) seed_part(p, SS, s_rec, b, g, 4096 + seed);
+            if (c * SEED_GTS < p.num_gt[b]) seed_part(p, SS, s_rec, b, c);
             TMARK0(1, 4096 + seed, 1);
             __syncthreads();
             seed = s_seed;
