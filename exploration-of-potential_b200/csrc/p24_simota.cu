@@ -655,20 +655,24 @@ __device__ void seed_gt(const Params& p, SeedShared& S, const float* __restrict_
     if (lane == 0) {
         myrec[GT_FAR2] = far2;
         myrec[GT_T] = T;
-        __threadfence();
-        atomicAdd(&p.seed_done[b], 1);
     }
 }
 
-// one seed item: the GTs c * 8 .. c * 8 + 7 of image b, one warp each
-__device__ void seed_part(const Params& p, SeedShared& S, float* __restrict__ s_recs, int b, int c) {
-    const int tid = threadIdx.x, warp = tid >> 5;
+// k_seed: grid (ceil(Lmax / 8), B), the GTs c * 8 .. c * 8 + 7 of image b, one warp each.  It runs between k_prep and
+// k_pass, on an otherwise idle GPU: the seed work is a latency chain (a few scattered rows), which would crawl beside the
+// issue-bound tile work of k_pass.
+__global__ void __launch_bounds__(P24_THREADS) k_seed(const __grid_constant__ Params p) {
+    extern __shared__ float4 sd_dyn4[];  // [Lmax * GT_REC] floats: the image's records
+    __shared__ SeedShared S;
+    pdl_wait();     // the records come from k_prep
+    pdl_trigger();  // k_pass may become resident: it stages its first rows and waits for this grid
+    float* s_recs = reinterpret_cast<float*>(sd_dyn4);
+    const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
     const int n = p.num_gt[b];
-    __syncthreads();  // the scratch may still be in use by the previous item
+    if (c * SEED_GTS >= n) return;
     {
         const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
-        float4* dst = reinterpret_cast<float4*>(s_recs);
-        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) dst[i] = __ldcg(gsrc + i);
+        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) sd_dyn4[i] = __ldcg(gsrc + i);
     }
     __syncthreads();
     const int g = c * SEED_GTS + warp;
@@ -962,23 +966,9 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     S.cand[tid] = (cand ? 1 : 0) | (tiny ? 2 : 0);  // (read by far_pair, after the next barrier)
 
     // ---- the (GT, candidate) pairs whose PREDICTED centre lies beyond the GT's far2 (the only pairs whose value can reach
-    // the GT's top 10): bounds into the GTs' lists, again through a work list.  far2 and T come from the image's seed
-    // items, which were drawn before any tile (the CTAs that hold them are running: this wait cannot deadlock) and have
-    // had the whole candidate phase to finish ---------------------------------------------------------------------------
+    // the GT's top 10): bounds into the GTs' lists, again through a work list ------------------------------------------
     TMARK0(1, b * p.tiles + tile, 2);
-    if (!no_filter) {
-        if (tid == 0) {
-            while (ld_acquire(&p.seed_done[b]) < n) __nanosleep(64);
-        }
-        __syncthreads();
-        TMARK0(1, b * p.tiles + tile, 8);
-        for (int g = tid; g < n; g += P24_THREADS) {
-            const float* r = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
-            s_rec[g * GT_REC + GT_FAR2] = __ldcg(r + GT_FAR2);
-            s_rec[g * GT_REC + GT_T] = __ldcg(r + GT_T);
-        }
-        __syncthreads();
-    }
+    TMARK0(1, b * p.tiles + tile, 8);
     if (cand && !no_filter) {
         unsigned fm[4] = {0u, 0u, 0u, 0u};
         int cnt = 0;
@@ -1053,37 +1043,16 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
     const int n_anchor = p.B * p.tiles;
     const int tid = threadIdx.x;
     // the first tickets do not depend on k_prep
-    if (tid == 0) {
-        s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);
-        s_seed = (int)atomicAdd(&p.ticket[TK_SEED], 1u);
-    }
+    if (tid == 0) s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);
     __syncthreads();
-    int item = s_item, seed = s_seed;
+    int item = s_item;
     bool staged = false;
     if (item < n_anchor) {
         stage_rows(p, S, item / p.tiles, item % p.tiles);
         staged = true;
     }
-    pdl_wait();  // the records come from k_prep
+    pdl_wait();  // the records, thresholds and window pairs come from k_prep / k_seed
     TMARK0(1, 6000 + blockIdx.x, 0);
-    const int leff = (int)__ldcg(&p.ticket[TK_LEFF]);  // the batch's largest num_gt
-    // ---- seed items (8 GTs of one image, a warp each): image fastest, so that the real GT rows (valid rows come first)
-    // are drawn first ----------------------------------------------------------------------------------------------------
-    {
-        SeedShared& SS = *reinterpret_cast<SeedShared*>(s_rec + (size_t)p.Lmax * GT_REC);
-        const int n_chunk = (leff + SEED_GTS - 1) / SEED_GTS;
-        const int n_seed = p.B * n_chunk;
-        while (seed < n_seed) {
-            __syncthreads();
-            if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_SEED], 1u);  // the next one, in flight meanwhile
-            const int c = seed / p.B, b = seed - c * p.B;
-            TMARK0(1, 4096 + seed, 0);
-            if (c * SEED_GTS < p.num_gt[b]) seed_part(p, SS, s_rec, b, c);
-            TMARK0(1, 4096 + seed, 1);
-            __syncthreads();
-            seed = s_seed;
-        }
-    }
     // ---- anchor tiles and window chunks (32 centre-window pairs of the batch's list, one per 8-lane group), taken in
     // turns from their own ticket counters: the issue-bound window work and the latency-bound tile work share every SM --
     const int n_wchunk = ((int)__ldcg(&p.ticket[TK_WTOT]) + P24_THREADS / 8 - 1) / (P24_THREADS / 8);
@@ -1905,7 +1874,6 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
         p.ticket[TK_WTOT] = 0u;
     }
     for (int i = tid; i < p.B; i += TAIL_THREADS) {
-        p.seed_done[i] = 0;
         p.ncand[i] = 0;
         p.rare[i] = 0;
     }
@@ -1965,7 +1933,7 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
     finalize_warp(sums28, state26, result54, weights_n27);
 }
 
-size_t pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float) + sizeof(SeedShared); }
+size_t pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float); }
 size_t tail_smem(int Lmax, int nc) {
     const size_t cap = ((size_t)Lmax * P24_TOPK + TAIL_CL - 1) / TAIL_CL;
     size_t b = (size_t)Lmax * GT_REC * sizeof(float);                 // recs
@@ -2106,6 +2074,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     cudaStream_t st = (cudaStream_t)stream;
     if (p24::dev_once(1u << 0)) {  // per device: a process may drive several GPUs
         cudaFuncSetAttribute(k_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
     const bool pdl = !(flags & P24_F_NO_PDL) && !p24::prof_on();
@@ -2114,9 +2083,11 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p24::prof_mark(0, st);
     e = launch(k_prep, dim3(B, (Lmax + PREP_WARPS - 1) / PREP_WARPS), dim3(PREP_THREADS), 0, st, pdl, p);
     if (e != cudaSuccess) return (int)e;
+    e = launch(k_seed, dim3((Lmax + SEED_GTS - 1) / SEED_GTS, B), dim3(P24_THREADS), dyn_pass, st, pdl, p);
+    if (e != cudaSuccess) return (int)e;
     p24::prof_mark(1, st);
     {
-        // one wave of persistent CTAs: the seed items are waited for inside the kernel, so every CTA must be resident
+        // one wave of persistent CTAs drawing tiles and window chunks from ticket counters
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass, P24_THREADS, dyn_pass);
         if (e != cudaSuccess) return (int)e;

@@ -57,10 +57,6 @@ def stat(label, d):
 
 
 print(f"== k_pass: CTAs past pdl_wait at 0 us; last CTA end {us(kp[6000:7024, 1].max()):.1f} us")
-sd = kp[4096:4096 + B * ((wl["G"] + 7) // 8)]
-ok = sd[:, 1] > 0
-print(f"   seed items: first start {us(sd[ok, 0].min()):.1f}  last end {us(sd[ok, 1].max()):.1f}")
-stat("seed item", sd[ok, 1] - sd[ok, 0])
 tl = kp[:min(B * tiles, 4095)]
 print(f"   tiles: first start {us(tl[:, 0].min()):.1f}  last end {us(tl[:, 7].max()):.1f}")
 for lab, a, b_ in [("pre", 0, 1), ("recs+rows", 1, 3), ("gt loop+lists", 3, 4), ("poly items", 4, 5), ("cand sync", 5, 2),
