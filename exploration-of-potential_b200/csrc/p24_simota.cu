@@ -1053,38 +1053,37 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
     }
     pdl_wait();  // the records, thresholds and window pairs come from k_prep / k_seed
     TMARK0(1, 6000 + blockIdx.x, 0);
-    // ---- anchor tiles and window chunks (32 centre-window pairs of the batch's list, one per 8-lane group), taken in
-    // turns from their own ticket counters: the issue-bound window work and the latency-bound tile work share every SM --
-    const int n_wchunk = ((int)__ldcg(&p.ticket[TK_WTOT]) + P24_THREADS / 8 - 1) / (P24_THREADS / 8);
-    int wchunk = n_wchunk;  // (the first window ticket is drawn after the first tile)
-    bool first_round = true;
-    while (item < n_anchor || wchunk < n_wchunk || first_round) {
-        if (item < n_anchor) {
+    // ---- the anchor tiles first (the long items), image-major: an image's tiles (and its records) stay together in time --
+    while (item < n_anchor) {
+        __syncthreads();
+        if (tid == 0) s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);  // the next one, in flight meanwhile
+        TMARK0(1, item, 0);
+        anchor_part(p, s_rec, S, item / p.tiles, item % p.tiles, staged);
+        TMARK0(1, item, 7);
+        staged = false;
+        __syncthreads();
+        item = s_item;
+    }
+    // ---- then the window chunks: 32 centre-window pairs of the batch's list, one per 8-lane group -----------------------
+    {
+        const int wtot = (int)__ldcg(&p.ticket[TK_WTOT]);
+        const int n_wchunk = (wtot + P24_THREADS / 8 - 1) / (P24_THREADS / 8);
+        __syncthreads();
+        if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_WIN], 1u);
+        __syncthreads();
+        int wchunk = s_seed;
+        while (wchunk < n_wchunk) {
             __syncthreads();
-            if (tid == 0) s_item = (int)atomicAdd(&p.ticket[TK_ITEM], 1u);  // the next one, in flight meanwhile
-            // image-major order keeps an image's tiles (and its records) together in time
-            TMARK0(1, item, 0);
-            anchor_part(p, s_rec, S, item / p.tiles, item % p.tiles, staged);
-            TMARK0(1, item, 7);
-            staged = false;
-            __syncthreads();
-            item = s_item;
-        }
-        if (first_round || wchunk < n_wchunk) {
-            __syncthreads();
-            if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_WIN], 1u);
-            if (!first_round) {
-                const int e = wchunk * (P24_THREADS / 8) + (tid >> 3);
-                TMARK0(1, min(3000 + wchunk, 4095), 0);
-                if (e < (int)__ldcg(&p.ticket[TK_WTOT])) {
-                    const int2 pr = __ldcg(p.wlist + e);
-                    window_pair(p, pr.x, pr.y, group_mask());
-                }
-                TMARK0(1, min(3000 + wchunk, 4095), 7);
+            if (tid == 0) s_seed = (int)atomicAdd(&p.ticket[TK_WIN], 1u);  // the next one, in flight meanwhile
+            const int e = wchunk * (P24_THREADS / 8) + (tid >> 3);
+            TMARK0(1, min(3000 + wchunk, 4095), 0);
+            if (e < wtot) {
+                const int2 pr = __ldcg(p.wlist + e);
+                window_pair(p, pr.x, pr.y, group_mask());
             }
+            TMARK0(1, min(3000 + wchunk, 4095), 7);
             __syncthreads();
             wchunk = s_seed;
-            first_round = false;
         }
     }
     TMARK0(1, 6000 + blockIdx.x, 1);
@@ -1689,8 +1688,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
     {
         const unsigned gm = group_mask();
         const int sub = tid & 7;
-        const int tend = min(nslots, (cr + 1) * cap);
-        for (int t0 = cr * cap; t0 < tend; t0 += TAIL_THREADS / 8) {
+        const int per = (nslots + TAIL_CL - 1) / TAIL_CL;  // the image's claim slots spread evenly over the cluster (<= cap)
+        const int tend = min(nslots, (cr + 1) * per);
+        for (int t0 = cr * per; t0 < tend; t0 += TAIL_THREADS / 8) {
             const int t = t0 + (tid >> 3);
             const int a = t < tend ? claim[t] : -1;
             int first = 1, multi = 0;
