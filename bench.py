@@ -55,7 +55,7 @@ POST_SETTINGS = [
 ]
 METRIC = "24p loss+SimOTA images/s @640, 20 GT/img"
 L2_BYTES = 126 * 1024 * 1024
-TRAIN_STAGES = ["k_prep+k_seed", "k_pass", "k_tail"]      # p24_profile_read slots 0..2
+TRAIN_STAGES = ["k_prep", "k_pass", "k_tail"]      # p24_profile_read slots 0..2
 POST_STAGES = {4: "k_post_filter", 5: "k_post_nms"}  # slots 4, 5
 
 

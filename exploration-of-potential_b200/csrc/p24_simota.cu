@@ -296,78 +296,6 @@ __device__ __forceinline__ unsigned window_slot_mask(const Params& p, float gcx,
     return m;
 }
 
-#define PREP_THREADS 256
-#define PREP_WARPS (PREP_THREADS / 32)
-// k_prep: grid (B, ceil(Lmax / 8)); CTA (b, y) counts the image's labels (cheap: the label block stays in L2) and prepares
-// the GTs y * 8 .. y * 8 + 7, one warp each: record, window table, centre-window pairs
-__global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ Params p) {
-    // launched as a programmatic dependent of whatever precedes it in the stream (in back-to-back steps: the previous
-    // step's k_tail, which triggers at once): resident early, it starts the moment that work is complete
-    pdl_wait();
-    pdl_trigger();
-    __shared__ int s_n, s_base;
-    __shared__ int s_wcnt[PREP_WARPS];
-    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float* lab = p.labels + (long long)b * p.lab_img_stride;
-    const int n = block_count_labels(p, lab, &s_n);
-    if (tid == 0 && blockIdx.y == 0) {
-        p.num_gt[b] = n;
-        p.num_fg[b] = 0;  // k_tail adds the foreground anchors of the image's cluster CTAs
-        atomicMax(&p.ticket[TK_LEFF], (unsigned)n);  // the batch's largest num_gt: k_pass lays its items out for it
-    }
-    const int g = blockIdx.y * PREP_WARPS + warp;
-    const float* row = lab + (long long)g * p.lab_row_stride;
-    unsigned wmask = 0u;
-    float gcx = 0.0f, gcy = 0.0f;
-    if (g < n) {
-        float* rec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
-        warp_gt_record(row, rec);
-        gcx = row[1];
-        gcy = row[2];
-        // the GT's window cost table: origins of its 7 x 7 block of cells per level, every slot "not valid" until the
-        // pair's cost is stored
-        float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
-        if (lane < 2 * P24_MAX_LEVELS) {
-            const int l = lane >> 1;
-            const float o = __int_as_float(l < p.nlev ? window_origin(lane & 1 ? gcy : gcx, p.lev[l].st) : 0);
-            rec[GT_ORG + lane] = o;
-            tab[P24_WT_HDR + lane] = o;
-        }
-        for (int s = lane; s < P24_WT_HDR; s += 32) tab[s] = P24_POS_INF;
-        wmask = window_slot_mask(p, gcx, gcy);
-    }
-    // ---- the CTA's centre-window pairs (GT slot, anchor) appended to the batch's list: the window items of k_pass ----
-    const int cnt = warp_sum_i(__popc(wmask));
-    if (lane == 0) s_wcnt[warp] = cnt;
-    __syncthreads();
-    if (tid == 0) {
-        int tot = 0;
-        for (int w = 0; w < PREP_WARPS; ++w) {
-            const int c = s_wcnt[w];
-            s_wcnt[w] = tot;
-            tot += c;
-        }
-        s_base = tot ? (int)atomicAdd(&p.ticket[TK_WTOT], (unsigned)tot) : 0;
-    }
-    __syncthreads();
-    if (g < n) {
-        int at = s_base + s_wcnt[warp];
-#pragma unroll
-        for (int q = 0; q < (P24_WT_HDR + 31) / 32; ++q) {
-            const bool in = (wmask >> q) & 1u;
-            const unsigned bal = __ballot_sync(0xffffffffu, in);
-            if (in) {
-                const int s = lane + 32 * q;
-                const int l = s / P24_WSLOTS, r = s - l * P24_WSLOTS;
-                const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
-                const int ix = window_origin(gcx, p.lev[l].st) + sx, iy = window_origin(gcy, p.lev[l].st) + sy;
-                p.wlist[at + __popc(bal & ((1u << lane) - 1u))] = make_int2(b * p.Lmax + g, p.lev[l].off + iy * p.lev[l].W + ix);
-            }
-            at += __popc(bal);
-        }
-    }
-}
-
 // -------------------------------------------------------------------------------------------
 // shared device helpers
 // -------------------------------------------------------------------------------------------
@@ -441,13 +369,6 @@ __device__ __forceinline__ float warp_bound_Hstar(float rg_lane, float d) {
 // H*(d) < T: the anchor tiles evaluate only the (GT, candidate) pairs beyond it.
 // -------------------------------------------------------------------------------------------
 #define SEED_FAR 3      // farthest GTs whose centre-window / inscribed-disc anchors serve as seeds
-#define SEED_NV 16      // far polygon vertices (of any GT of the image), each on the two levels that suit this GT best
-#define SEED_GTS P24_WARPS   // GTs per seed item: one warp each, no block-wide step after the records are staged
-
-struct SeedShared {
-    int vsel[P24_WARPS][SEED_NV];   // (GT << 5) | vertex
-    int far[P24_WARPS][4];
-};
 
 __device__ __forceinline__ int cell_index(float q, float st) {
     float v = floorf(q / st);
@@ -501,35 +422,126 @@ __device__ __forceinline__ KV seed_point(const Params& p, const float* __restric
     return out;
 }
 
-// the seed work of one GT, by one warp.  recs: the image's records in shared memory.
-__device__ void seed_gt(const Params& p, SeedShared& S, const float* __restrict__ recs, int b, int g, int n) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* rec = recs + g * GT_REC;
-    float* myrec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
-    const float gcx = rec[GT_CX], gcy = rec[GT_CY];
-    const bool filter = !(p.flags & P24_F_NO_FILTER) && rec[GT_RGMIN] >= 0.25f && rec[GT_RGMAX] < 1.0e6f;
-    float T = P24_NEG_INF;
-    if (filter) {
-        // ---- the SEED_FAR farthest GTs (centre distance + their largest ray), this GT included ---------------------
-        {
-            float key = P24_NEG_INF;
-            int hb = -1;
-            for (int h = lane; h < n; h += 32) {
-                const float* r = recs + h * GT_REC;
-                const float dx = r[GT_CX] - gcx, dy = r[GT_CY] - gcy;
-                const float kk = sqrtf(fmaf(dx, dx, dy * dy)) + r[GT_RGMAX];
-                if (kk > key) {
-                    key = kk;
-                    hb = h;
-                }
-            }
-            const int rk = lane_rank<true>(hb >= 0 ? key : P24_NEG_INF);
-            if (rk < SEED_FAR) S.far[warp][rk] = hb;   // (-1: fewer GTs than SEED_FAR)
+// -------------------------------------------------------------------------------------------
+// k_prep: grid (ceil(Lmax / 2), B); CTA (c, b) prepares the GTs 2c and 2c + 1 of image b, four warps each.
+//   part 1 (warp 0 of the GT): nlabel is counted by every CTA (the label block stays in L2), the GT's record, its window
+//          table and its centre-window pairs (appended to the batch's list: the window chunks of k_pass);
+//   barrier over the image's CTAs (a counter of finished records; see p24_simota_loss_batch for the launch condition);
+//   part 2 (warps 0..2 of the GT): the seeds, 32 points per warp: warp 0 / warp 1 the polygon vertices of the image that
+//          are far from the GT (every lane the farthest of its share) on the two levels that suit the GT, warp 2 the
+//          centre-window / inscribed-disc anchors of the SEED_FAR farthest GTs.  The 10th largest of their certified
+//          values is T, and far2 follows from it.
+// mode 0: both parts; 1: part 1 only; 2: part 2 only (two launches, when the grid would not be resident at once).
+// -------------------------------------------------------------------------------------------
+#define PREP_THREADS 256
+#define PREP_GTS 2
+struct PrepShared {
+    int n, base;
+    int wcnt[PREP_GTS];
+    int far[PREP_GTS][4];
+    float tval[PREP_GTS][3][P24_TOPK];
+    int tanc[PREP_GTS][3][P24_TOPK];
+};
+
+__global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ Params p, int mode) {
+    extern __shared__ float4 pr_dyn4[];  // [Lmax * GT_REC] floats: the image's records (part 2)
+    __shared__ PrepShared S;
+    // launched as a programmatic dependent of whatever precedes it in the stream (in back-to-back steps: the previous
+    // step's k_tail, which triggers at once): resident early, it starts the moment that work is complete
+    pdl_wait();
+    pdl_trigger();
+    float* recs = reinterpret_cast<float*>(pr_dyn4);
+    const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gi = warp >> 2, role = warp & 3;
+    const int g = c * PREP_GTS + gi;
+    const float* lab = p.labels + (long long)b * p.lab_img_stride;
+    int n;
+    if (mode != 2) {
+        n = block_count_labels(p, lab, &S.n);
+        if (tid == 0 && c == 0) {
+            p.num_gt[b] = n;
+            p.num_fg[b] = 0;  // k_tail adds the foreground anchors of the image's cluster CTAs
+            atomicMax(&p.ticket[TK_LEFF], (unsigned)n);
         }
-        // ---- the polygon vertices of the image that are far from this GT's centre: every lane keeps the farthest of its
-        // share, the SEED_NV farthest lanes pass theirs on (any subset of far vertices serves: better ones tighten T) ----
-        float dfar2 = 0.0f;
-        {
+    } else {
+        n = p.num_gt[b];
+    }
+    if (c * PREP_GTS >= n) return;  // (the whole CTA)
+    const bool has = g < n;
+    if (mode != 2) {
+        // ---- part 1 ------------------------------------------------------------------------------------------------------
+        unsigned wmask = 0u;
+        float gcx = 0.0f, gcy = 0.0f;
+        if (has && role == 0) {
+            const float* row = lab + (long long)g * p.lab_row_stride;
+            float* rec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
+            warp_gt_record(row, rec);
+            gcx = row[1];
+            gcy = row[2];
+            // the GT's window cost table: origins of its 7 x 7 block of cells per level, every slot "not valid" until the
+            // pair's cost is stored
+            float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
+            if (lane < 2 * P24_MAX_LEVELS) {
+                const int l = lane >> 1;
+                const float o = __int_as_float(l < p.nlev ? window_origin(lane & 1 ? gcy : gcx, p.lev[l].st) : 0);
+                rec[GT_ORG + lane] = o;
+                tab[P24_WT_HDR + lane] = o;
+            }
+            for (int s = lane; s < P24_WT_HDR; s += 32) tab[s] = P24_POS_INF;
+            wmask = window_slot_mask(p, gcx, gcy);
+        }
+        const int cnt = warp_sum_i(__popc(wmask));
+        if (lane == 0 && role == 0) S.wcnt[gi] = has ? cnt : 0;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < PREP_GTS; ++w) {
+                const int cc = S.wcnt[w];
+                S.wcnt[w] = tot;
+                tot += cc;
+            }
+            S.base = tot ? (int)atomicAdd(&p.ticket[TK_WTOT], (unsigned)tot) : 0;
+        }
+        __syncthreads();
+        if (has && role == 0) {
+            int at = S.base + S.wcnt[gi];
+#pragma unroll
+            for (int q = 0; q < (P24_WT_HDR + 31) / 32; ++q) {
+                const bool in = (wmask >> q) & 1u;
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const int s = lane + 32 * q;
+                    const int l = s / P24_WSLOTS, r = s - l * P24_WSLOTS;
+                    const int sy = r / P24_WSIDE, sx = r - sy * P24_WSIDE;
+                    const int ix = window_origin(gcx, p.lev[l].st) + sx, iy = window_origin(gcy, p.lev[l].st) + sy;
+                    p.wlist[at + __popc(bal & ((1u << lane) - 1u))] = make_int2(b * p.Lmax + g, p.lev[l].off + iy * p.lev[l].W + ix);
+                }
+                at += __popc(bal);
+            }
+        }
+        if (mode == 1) return;
+        // ---- the image's records are complete when every CTA of the image has passed here --------------------------------
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(&p.seed_done[b], min(PREP_GTS, n - c * PREP_GTS));
+            while (ld_acquire(&p.seed_done[b]) < n) __nanosleep(32);
+        }
+        __syncthreads();
+    }
+    // ---- part 2 ----------------------------------------------------------------------------------------------------------
+    {
+        const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
+        for (int i = tid; i < n * (GT_REC / 4); i += PREP_THREADS) pr_dyn4[i] = __ldcg(gsrc + i);
+    }
+    __syncthreads();
+    const float* rec = recs + min(g, n - 1) * GT_REC;
+    const float gcx = rec[GT_CX], gcy = rec[GT_CY];
+    const bool filter = has && !(p.flags & P24_F_NO_FILTER) && rec[GT_RGMIN] >= 0.25f && rec[GT_RGMAX] < 1.0e6f;
+    if (filter && role < 3) {
+        KV sd = {P24_NEG_INF, -1};
+        if (role < 2) {
+            // the farthest polygon vertex of the lane's share of the image's vertices
             float best = P24_NEG_INF;
             int bi = -1;
             for (int i = lane; i < n * P24_RAYS; i += 32) {
@@ -542,53 +554,58 @@ __device__ void seed_gt(const Params& p, SeedShared& S, const float* __restrict_
                     bi = (h << 5) | k;
                 }
             }
-            const int rk = lane_rank<true>(bi >= 0 ? best : P24_NEG_INF);
-            if (rk < SEED_NV) S.vsel[warp][rk] = bi;
-            dfar2 = warp_max(best);
-        }
-        __syncwarp();
-        // the two levels whose typical predicted radius (about 1.1 strides) is closest to the radius that maximises the
-        // bound at the far distance, rp* = rg^2 / (rg + d)
-        int lvA = 0, lvB = 0;
-        {
-            const float rstar = __fdividef(rec[GT_RGMS], rec[GT_RGMEAN] + sqrtf(fmaxf(dfar2, 0.0f)) + 1e-6f);
-            float eA = P24_POS_INF, eB = P24_POS_INF;
-            for (int l = 0; l < p.nlev; ++l) {
-                const float e = fabsf(1.13f * p.lev[l].st - rstar);
-                if (e < eA) {
-                    eB = eA;
-                    lvB = lvA;
-                    eA = e;
-                    lvA = l;
-                } else if (e < eB) {
-                    eB = e;
-                    lvB = l;
+            const float dfar2 = warp_max(best);
+            // the two levels whose typical predicted radius (about 1.1 strides) is closest to the radius that maximises the
+            // bound at the far distance, rp* = rg^2 / (rg + d): warp 0 takes the best, warp 1 the second best
+            int lvA = 0, lvB = 0;
+            {
+                const float rstar = __fdividef(rec[GT_RGMS], rec[GT_RGMEAN] + sqrtf(fmaxf(dfar2, 0.0f)) + 1e-6f);
+                float eA = P24_POS_INF, eB = P24_POS_INF;
+                for (int l = 0; l < p.nlev; ++l) {
+                    const float e = fabsf(1.13f * p.lev[l].st - rstar);
+                    if (e < eA) {
+                        eB = eA;
+                        lvB = lvA;
+                        eA = e;
+                        lvA = l;
+                    } else if (e < eB) {
+                        eB = e;
+                        lvB = l;
+                    }
                 }
             }
-            if (p.nlev < 2) lvB = lvA;
-        }
-        // ---- round 1: SEED_NV far vertices x two levels, one point per lane (one stride inside the vertex, on the ray from
-        // the vertex's own GT centre) ------------------------------------------------------------------------------------
-        KV s1, s2;
-        {
-            const int hv = S.vsel[warp][lane & (SEED_NV - 1)];
-            const int l = lane < SEED_NV ? lvA : lvB;
-            const float* h = recs + (max(hv, 0) >> 5) * GT_REC;
-            const int k = max(hv, 0) & 31;
+            const int l = role == 0 ? lvA : lvB;
+            const float* h = recs + (max(bi, 0) >> 5) * GT_REC;
+            const int k = max(bi, 0) & 31;
             const float st = p.lev[l].st;
+            // one stride inside the vertex, on the ray from the vertex's own GT centre
             const float rr = h[GT_RG + k];
             const float fct = fmaxf(0.0f, __fdividef(rr - st, fmaxf(rr, 1e-6f)));
-            const float qx = fmaf(h[GT_VX + k] - h[GT_CX], fct, h[GT_CX]);
-            const float qy = fmaf(h[GT_VY + k] - h[GT_CY], fct, h[GT_CY]);
-            s1 = seed_point(p, rec, h, b, l, qx, qy, hv >= 0 && (lane < SEED_NV || lvB != lvA));
-        }
-        // ---- round 2: the SEED_FAR farthest GTs: centre, far end of the inscribed disc, 2 strides out, on every level ------
-        {
-            const int f = lane / 9, r0 = lane - f * 9;  // 3 GTs x 3 levels x 3 points = 27 lanes
+            sd = seed_point(p, rec, h, b, l, fmaf(h[GT_VX + k] - h[GT_CX], fct, h[GT_CX]),
+                            fmaf(h[GT_VY + k] - h[GT_CY], fct, h[GT_CY]), bi >= 0 && (role == 0 || p.nlev > 1));
+        } else {
+            // the SEED_FAR farthest GTs (centre distance + their largest ray), this GT included: centre, far end of the
+            // inscribed disc, 2 strides out, on every level (up to 3): 27 lanes
+            float key = P24_NEG_INF;
+            int hb = -1;
+            for (int h = lane; h < n; h += 32) {
+                const float* r = recs + h * GT_REC;
+                const float dx = r[GT_CX] - gcx, dy = r[GT_CY] - gcy;
+                const float kk = sqrtf(fmaf(dx, dx, dy * dy)) + r[GT_RGMAX];
+                if (kk > key) {
+                    key = kk;
+                    hb = h;
+                }
+            }
+            const int rk = lane_rank<true>(hb >= 0 ? key : P24_NEG_INF);
+            if (rk < SEED_FAR) S.far[gi][rk] = hb;   // (-1: fewer GTs than SEED_FAR)
+            __syncwarp();
+            const int f = lane / 9, r0 = lane - f * 9;
             const int l = r0 / 3, pt = r0 - l * 3;
-            const int hs = f < SEED_FAR ? S.far[warp][f] : -1;
+            const int hs = f < SEED_FAR ? S.far[gi][f] : -1;
             const float* h = recs + max(hs, 0) * GT_REC;
-            const float st = p.lev[min(l, p.nlev - 1)].st;
+            const int ll = min(l, p.nlev - 1);
+            const float st = p.lev[ll].st;
             float ux = h[GT_CX] - gcx, uy = h[GT_CY] - gcy;
             const float nn = fmaf(ux, ux, uy * uy);
             if (nn > 1e-12f) {
@@ -600,83 +617,73 @@ __device__ void seed_gt(const Params& p, SeedShared& S, const float* __restrict_
                 uy = 0.0f;
             }
             const float rho = pt == 0 ? 0.0f : (pt == 1 ? fmaxf(0.0f, sqrtf(h[GT_RIN2]) - 0.75f * st) : 2.0f * st);
-            s2 = seed_point(p, rec, h, b, min(l, p.nlev - 1), fmaf(ux, rho, h[GT_CX]), fmaf(uy, rho, h[GT_CY]),
-                            hs >= 0 && lane < 27 && l < p.nlev);
+            sd = seed_point(p, rec, h, b, ll, fmaf(ux, rho, h[GT_CX]), fmaf(uy, rho, h[GT_CY]), hs >= 0 && lane < 27 && l < p.nlev);
         }
-        // ---- the 10th largest value over the distinct seed anchors (64 values, two per lane) --------------------------
-        {
-            // a copy of an anchor counts once: the earlier (round, lane) keeps it
-            bool d1 = false, d2 = false;
+        // the warp's 10 largest values over distinct anchors (a copy of an anchor counts once: the lower lane keeps it)
+        bool dup = false;
 #pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
-                const int a1 = __shfl_sync(0xffffffffu, s1.i, j), a2 = __shfl_sync(0xffffffffu, s2.i, j);
-                d1 = d1 || (s1.i >= 0 && a1 == s1.i && j < lane);
-                d2 = d2 || (s2.i >= 0 && (a1 == s2.i || (a2 == s2.i && j < lane)));
-            }
-            const float v1 = d1 ? P24_NEG_INF : s1.v, v2 = d2 ? P24_NEG_INF : s2.v;
-            // rank of each of my two values among all 64 (ties: round 1 first, then the lower lane)
-            int r1 = 0, r2 = 0;
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
-                const float o1 = __shfl_sync(0xffffffffu, v1, j), o2 = __shfl_sync(0xffffffffu, v2, j);
-                r1 += (kv_gt(o1, j, v1, lane) ? 1 : 0) + (o2 > v1 ? 1 : 0);
-                r2 += (o1 >= v2 ? 1 : 0) + (kv_gt(o2, j, v2, lane) ? 1 : 0);
-            }
-            const float cand_T = (r1 == P24_TOPK - 1) ? v1 : ((r2 == P24_TOPK - 1) ? v2 : P24_NEG_INF);
-            T = warp_max(cand_T);
+        for (int j = 0; j < 32; ++j) {
+            const int aj = __shfl_sync(0xffffffffu, sd.i, j);
+            dup = dup || (sd.i >= 0 && aj == sd.i && j < lane);
         }
-    }
-    // ---- far2: pairs closer than D cannot reach T.  H*(d) + 3e-5 < T is monotone in d: three rounds of a 32-way search,
-    // every lane evaluating the bound at its own distance -----------------------------------------------------------------
-    float far2 = 0.0f;  // 0: every pair is evaluated
-    if (T > P24_NEG_INF) {
-        float lo = 0.0f, step = 256.0f;  // pairs farther apart than 32 * 256 px are always evaluated
-#pragma unroll 1
-        for (int round = 0; round < 3; ++round) {
-            const float dd = lo + step * (float)lane;
-            float sum = 0.0f;
-#pragma unroll
-            for (int k = 0; k < P24_RAYS; ++k) {
-                const float rg = rec[GT_RG + k];
-                const float q = rg + dd;
-                sum += fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, fmaf(q, q, rg * rg)));
-            }
-            const bool below = sum * (1.0f / 48.0f) + 3e-5f < T;      // true for a prefix of the lanes (monotone)
-            const unsigned bal = __ballot_sync(0xffffffffu, below);
-            const int nb = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;  // length of the leading run of lanes
-            if (nb == 0) break;  // even lo is not below: D = lo
-            lo = lo + step * (float)(nb - 1);
-            step = step * (1.0f / 32.0f);
+        const float v = dup ? P24_NEG_INF : sd.v;
+        const int rk = lane_rank<true>(v);
+        if (rk < P24_TOPK) {
+            S.tval[gi][role][rk] = v;
+            S.tanc[gi][role][rk] = v > P24_NEG_INF ? sd.i : -1;
         }
-        const float D = fmaxf(0.0f, lo * (1.0f - 1e-4f) - 0.02f);
-        far2 = D * D;
-        if (!(far2 == far2)) far2 = 0.0f;
-    }
-    if (lane == 0) {
-        myrec[GT_FAR2] = far2;
-        myrec[GT_T] = T;
-    }
-}
-
-// k_seed: grid (ceil(Lmax / 8), B), the GTs c * 8 .. c * 8 + 7 of image b, one warp each.  It runs between k_prep and
-// k_pass, on an otherwise idle GPU: the seed work is a latency chain (a few scattered rows), which would crawl beside the
-// issue-bound tile work of k_pass.
-__global__ void __launch_bounds__(P24_THREADS) k_seed(const __grid_constant__ Params p) {
-    extern __shared__ float4 sd_dyn4[];  // [Lmax * GT_REC] floats: the image's records
-    __shared__ SeedShared S;
-    pdl_wait();     // the records come from k_prep
-    pdl_trigger();  // k_pass may become resident: it stages its first rows and waits for this grid
-    float* s_recs = reinterpret_cast<float*>(sd_dyn4);
-    const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
-    const int n = p.num_gt[b];
-    if (c * SEED_GTS >= n) return;
-    {
-        const float4* gsrc = reinterpret_cast<const float4*>(p.gt_rec + (long long)b * p.Lmax * GT_REC);
-        for (int i = tid; i < n * (GT_REC / 4); i += P24_THREADS) sd_dyn4[i] = __ldcg(gsrc + i);
     }
     __syncthreads();
-    const int g = c * SEED_GTS + warp;
-    if (g < n) seed_gt(p, S, s_recs, b, g, n);
+    if (has && role == 0) {
+        float T = P24_NEG_INF;
+        if (filter) {
+            // the 10th largest of the three warps' best values over distinct anchors (30 values, one per lane)
+            const float* tv = &S.tval[gi][0][0];
+            const int* ta = &S.tanc[gi][0][0];
+            float v = lane < 3 * P24_TOPK ? tv[lane] : P24_NEG_INF;
+            const int a = lane < 3 * P24_TOPK ? ta[lane] : -1;
+            bool dup = false;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const int aj = __shfl_sync(0xffffffffu, a, j);
+                dup = dup || (a >= 0 && aj == a && j < lane);
+            }
+            if (dup || a < 0) v = P24_NEG_INF;
+            const int rk = lane_rank<true>(v);
+            T = warp_max(rk == P24_TOPK - 1 ? v : P24_NEG_INF);
+        }
+        // ---- far2: pairs closer than D cannot reach T.  H*(d) + 3e-5 < T is monotone in d: rounds of a 32-way search, every
+        // lane evaluating the bound at its own distance ----------------------------------------------------------------------
+        float far2 = 0.0f;  // 0: every pair is evaluated
+        if (T > P24_NEG_INF) {
+            float lo = 0.0f, step = 256.0f;  // pairs farther apart than 32 * 256 px are always evaluated
+#pragma unroll 1
+            for (int round = 0; round < 3; ++round) {
+                const float dd = lo + step * (float)lane;
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < P24_RAYS; ++k) {
+                    const float rg = rec[GT_RG + k];
+                    const float q = rg + dd;
+                    sum += fmaxf(1.0f, 2.0f - __fdividef(4.0f * rg * rg, fmaf(q, q, rg * rg)));
+                }
+                const bool below = sum * (1.0f / 48.0f) + 3e-5f < T;      // true for a prefix of the lanes (monotone)
+                const unsigned bal = __ballot_sync(0xffffffffu, below);
+                const int nb = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;  // length of the leading run of lanes
+                if (nb == 0) break;  // even lo is not below: D = lo
+                lo = lo + step * (float)(nb - 1);
+                step = step * (1.0f / 32.0f);
+            }
+            const float D = fmaxf(0.0f, lo * (1.0f - 1e-4f) - 0.02f);
+            far2 = D * D;
+            if (!(far2 == far2)) far2 = 0.0f;
+        }
+        if (lane == 0) {
+            float* myrec = p.gt_rec + ((long long)b * p.Lmax + g) * GT_REC;
+            myrec[GT_FAR2] = far2;
+            myrec[GT_T] = T;
+        }
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1874,6 +1881,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
         p.ticket[TK_WTOT] = 0u;
     }
     for (int i = tid; i < p.B; i += TAIL_THREADS) {
+        p.seed_done[i] = 0;
         p.ncand[i] = 0;
         p.rare[i] = 0;
     }
@@ -1969,6 +1977,21 @@ cudaError_t launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st
     cfg.attrs = attr;
     cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
+template <typename K>
+cudaError_t launch2(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Params& p, int arg) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, p, arg);
 }
 
 }  // namespace
@@ -2074,17 +2097,28 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     cudaStream_t st = (cudaStream_t)stream;
     if (p24::dev_once(1u << 0)) {  // per device: a process may drive several GPUs
         cudaFuncSetAttribute(k_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
     const bool pdl = !(flags & P24_F_NO_PDL) && !p24::prof_on();
     cudaError_t e = cudaSuccess;
     const int n_sm = p24::dev_info().n_sm;
     p24::prof_mark(0, st);
-    e = launch(k_prep, dim3(B, (Lmax + PREP_WARPS - 1) / PREP_WARPS), dim3(PREP_THREADS), 0, st, pdl, p);
-    if (e != cudaSuccess) return (int)e;
-    e = launch(k_seed, dim3((Lmax + SEED_GTS - 1) / SEED_GTS, B), dim3(P24_THREADS), dyn_pass, st, pdl, p);
-    if (e != cudaSuccess) return (int)e;
+    {
+        // k_prep waits inside for the records of all CTAs of an image: one launch when the whole grid is resident at once
+        // (always, at training batch sizes), else records and seeds in two launches
+        const dim3 pgrid((Lmax + PREP_GTS - 1) / PREP_GTS, B);
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prep, PREP_THREADS, dyn_pass);
+        if (e != cudaSuccess) return (int)e;
+        const bool fused = (long long)pgrid.x * pgrid.y <= (long long)per_sm * n_sm;
+        e = launch2(k_prep, pgrid, dim3(PREP_THREADS), dyn_pass, st, pdl, p, fused ? 0 : 1);
+        if (e != cudaSuccess) return (int)e;
+        if (!fused) {
+            e = launch2(k_prep, pgrid, dim3(PREP_THREADS), dyn_pass, st, pdl, p, 2);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
     p24::prof_mark(1, st);
     {
         // one wave of persistent CTAs drawing tiles and window chunks from ticket counters

@@ -47,5 +47,5 @@ for i in range(steps):
     for k in range(8):
         acc[k] += buf[k]
 lib.p24_profile_enable(0)
-print("kernel us:", {n: round(a / steps * 1e3, 1) for n, a in zip(["k_prep+k_seed", "k_pass", "k_tail"], acc)})
+print("kernel us:", {n: round(a / steps * 1e3, 1) for n, a in zip(["k_prep", "k_pass", "k_tail"], acc)})
 print("stats:", lf.path_stats())
