@@ -15,7 +15,7 @@
 #define P24_WT_HDR (P24_WSLOTS * P24_MAX_LEVELS)   // wtab row: [slot costs | ix0, iy0 per level (int bits)]
 #define P24_WT_STRIDE (P24_WT_HDR + 2 * P24_MAX_LEVELS + 4)   // 208 floats
 #define P24_WARPS (P24_THREADS / 32)
-#define P24_LISTCAP 2048   // entries a GT's top-10 list can hold (more -> brute-force path of k_tail)
+#define P24_LISTCAP 4096   // entries a GT's top-10 list can hold (more -> brute-force path of k_tail)
 
 // ---- per-GT record (floats): k_prep writes it, the seed items of k_pass add [4] and [58] ----------------------
 // [0] cx  [1] cy  [2] rin2  [3] rrej2   (one 128-bit shared-memory load for the per-pair tests)
@@ -70,6 +70,7 @@ struct P24Workspace {
     size_t kreq;        // [B, Lmax] int
     size_t ntake;       // [B, Lmax] int
     size_t cbits;       // [B, tiles * 8] unsigned         candidate bitmap (bit l of word w: anchor 32 w + l)
+    size_t brute;       // [B, 8, 10] float   per-CTA partial top-10 of the brute-force path of k_tail
     size_t wlist;       // [B * Lmax * 100] int2           the batch's centre-window pairs (GT slot, anchor), written by k_prep
     size_t total;
 };
@@ -96,6 +97,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     w.kreq = off;       off = p24_align(off + BL * sizeof(int));
     w.ntake = off;      off = p24_align(off + BL * sizeof(int));
     w.cbits = off;      off = p24_align(off + NB * P24_WARPS * sizeof(unsigned));
+    w.brute = off;      off = p24_align(off + (size_t)B * 8 * P24_TOPK * sizeof(float));
     w.wlist = off;      off = p24_align(off + BL * 25 * P24_MAX_LEVELS * 2 * sizeof(int));
     w.total = off;
     return w;

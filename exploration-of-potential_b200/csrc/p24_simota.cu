@@ -72,6 +72,7 @@ struct Params {
     float2* list;
     unsigned* cbits;
     int2* wlist;
+    float* brute;
     int* claimg;
     int* kreq;
     int* ntake;
@@ -452,6 +453,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
     pdl_trigger();
     float* recs = reinterpret_cast<float*>(pr_dyn4);
     const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    TMARK0(0, b * 64 + c, 0);
     const int gi = warp >> 2, role = warp & 3;
     const int g = c * PREP_GTS + gi;
     const float* lab = p.labels + (long long)b * p.lab_img_stride;
@@ -467,6 +469,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
         n = p.num_gt[b];
     }
     if (c * PREP_GTS >= n) return;  // (the whole CTA)
+    TMARK0(0, b * 64 + c, 1);
     const bool has = g < n;
     if (mode != 2) {
         // ---- part 1 ------------------------------------------------------------------------------------------------------
@@ -520,6 +523,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
             }
         }
         if (mode == 1) return;
+        TMARK0(0, b * 64 + c, 2);
         // ---- the image's records are complete when every CTA of the image has passed here --------------------------------
         __threadfence();
         __syncthreads();
@@ -528,6 +532,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
             while (ld_acquire(&p.seed_done[b]) < n) __nanosleep(32);
         }
         __syncthreads();
+        TMARK0(0, b * 64 + c, 3);
     }
     // ---- part 2 ----------------------------------------------------------------------------------------------------------
     {
@@ -535,6 +540,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
         for (int i = tid; i < n * (GT_REC / 4); i += PREP_THREADS) pr_dyn4[i] = __ldcg(gsrc + i);
     }
     __syncthreads();
+    TMARK0(0, b * 64 + c, 4);
     const float* rec = recs + min(g, n - 1) * GT_REC;
     const float gcx = rec[GT_CX], gcy = rec[GT_CY];
     const bool filter = has && !(p.flags & P24_F_NO_FILTER) && rec[GT_RGMIN] >= 0.25f && rec[GT_RGMAX] < 1.0e6f;
@@ -619,6 +625,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
             const float rho = pt == 0 ? 0.0f : (pt == 1 ? fmaxf(0.0f, sqrtf(h[GT_RIN2]) - 0.75f * st) : 2.0f * st);
             sd = seed_point(p, rec, h, b, ll, fmaf(ux, rho, h[GT_CX]), fmaf(uy, rho, h[GT_CY]), hs >= 0 && lane < 27 && l < p.nlev);
         }
+        if (warp == 0) TMARK(0, b * 64 + c, 5);
         // the warp's 10 largest values over distinct anchors (a copy of an anchor counts once: the lower lane keeps it)
         bool dup = false;
 #pragma unroll 8
@@ -634,6 +641,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
         }
     }
     __syncthreads();
+    TMARK0(0, b * 64 + c, 6);
     if (has && role == 0) {
         float T = P24_NEG_INF;
         if (filter) {
@@ -683,6 +691,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ P
             myrec[GT_FAR2] = far2;
             myrec[GT_T] = T;
         }
+        if (warp == 0) TMARK(0, b * 64 + c, 7);
     }
 }
 
@@ -1106,7 +1115,8 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
 #define TAIL_WARPS (TAIL_THREADS / 32)
 #define TAIL_SURV 64   // survivors a GT warp evaluates per batch
 #define ROW_PAD 108    // floats per staged row (27 + nc <= ROW_PAD is required for staging; else rows are read in place)
-#define MBOX_SLOT 64   // floats per (epoch half, rank) slot of a mailbox: 28 sums, flag at [32]
+#define MBOX_SLOT 64   // floats per (epoch, rank) slot of a mailbox: 28 sums, flag at [32]
+#define MBOX_EPOCHS 4  // slots alternate with the epoch: a rank runs at most one step ahead of its own collect kernel
 
 // normalisation + stateful re-weighting, losses.py:280-345; executed by one warp
 __device__ void finalize_warp(const float* sums28, float* state26, float* result54, float* weights_n27) {
@@ -1220,30 +1230,49 @@ __device__ __forceinline__ float warp_pop_max(float (&t)[P24_TOPK]) {
 }
 
 // Brute force (list overflow, P24_F_NO_FILTER, or fewer list entries than expected): the exact pair value of EVERY
-// candidate of the image (candidate bitmap), the kc largest summed in descending order.  Whole CTA.
-__device__ __noinline__ float topk_sum_bruteforce(const Params& p, TailShared& S, const float* __restrict__ rec, int b, int kc) {
+// candidate of the image (candidate bitmap).  Every CTA of the cluster scans its share of the anchors and leaves its
+// kc largest values (descending, -inf padded) in `out`; the first CTA merges them (brute_merge).  Whole CTA.
+__device__ __noinline__ void brute_partial(const Params& p, TailShared& S, const float* __restrict__ rec, int b, int kc, int cr,
+                                           float* __restrict__ out) {
     const int tid = threadIdx.x;
     const float* img = p.outputs + (long long)b * p.img_stride;
     const unsigned* bits = p.cbits + (long long)b * p.tiles * P24_WARPS;
+    const int per = (p.A + TAIL_CL - 1) / TAIL_CL;
     float t[P24_TOPK];
 #pragma unroll
     for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;
-    for (int a = tid; a < p.A; a += TAIL_THREADS) {
+    for (int a = cr * per + tid; a < min(p.A, (cr + 1) * per); a += TAIL_THREADS) {
         if (!((__ldcg(bits + (a >> 5)) >> (a & 31)) & 1u)) continue;
         float v = pair_value_row(rec, img + (long long)a * p.row_stride);
         if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
         top_insert_desc(t, v);
     }
+    for (int r = 0; r < P24_TOPK; ++r) {
+        KV best = {P24_NEG_INF, 0x7fffffff};
+        if (r < kc) {
+            best = tail_block_select<true>(KV{t[0], t[0] > P24_NEG_INF ? tid : 0x7fffffff}, S.kv);
+            if (tid == best.i) {
+#pragma unroll
+                for (int q = 0; q < P24_TOPK - 1; ++q) t[q] = t[q + 1];
+                t[P24_TOPK - 1] = P24_NEG_INF;
+            }
+        }
+        if (tid == 0) out[r] = best.i == 0x7fffffff ? P24_NEG_INF : best.v;
+    }
+}
+
+// the kc largest of the cluster's partial lists, summed in descending order; one warp
+__device__ __forceinline__ float brute_merge(const float* __restrict__ parts, int kc) {
+    const int lane = threadIdx.x & 31;
+    float t[P24_TOPK];
+#pragma unroll
+    for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;
+    for (int i = lane; i < TAIL_CL * P24_TOPK; i += 32) top_insert_desc(t, __ldcg(parts + i));
     float ksum = 0.0f;
     for (int r = 0; r < kc; ++r) {
-        const KV best = tail_block_select<true>(KV{t[0], t[0] > P24_NEG_INF ? tid : 0x7fffffff}, S.kv);
-        if (best.i == 0x7fffffff) break;
-        if (tid == best.i) {
-#pragma unroll
-            for (int q = 0; q < P24_TOPK - 1; ++q) t[q] = t[q + 1];
-            t[P24_TOPK - 1] = P24_NEG_INF;
-        }
-        ksum = ksum + (best.v == P24_POS_INF ? NAN : best.v);
+        const float v = warp_pop_max(t);
+        if (v == P24_NEG_INF) break;
+        ksum = ksum + (v == P24_POS_INF ? NAN : v);
     }
     return ksum;
 }
@@ -1650,27 +1679,30 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
     TMARK0(2, blockIdx.x, 3);
     // ---- rare paths, the cluster's first CTA, one GT at a time -----------------------------------------------------
     if (__ldcg(&p.rare[b]) > 0) {  // (the same value in every CTA of the cluster: written before the barrier)
-        if (cr == 0) {
-            int nb = 0, ns = 0;
-            for (int g = 0; g < n; ++g) {
-                if (__ldcg(&kreq[g]) != -2) continue;
-                ++nb;
-                const float ksum = topk_sum_bruteforce(p, S, s_rec + g * GT_REC, b, kc);
+        int nb = 0, ns = 0;
+        for (int g = 0; g < n; ++g) {
+            if (__ldcg(&kreq[g]) != -2) continue;  // (the same in every CTA)
+            ++nb;
+            // brute force over the candidate bitmap: every CTA its share of the anchors, the first CTA merges
+            brute_partial(p, S, s_rec + g * GT_REC, b, kc, cr, p.brute + ((long long)b * TAIL_CL + cr) * P24_TOPK);
+            __threadfence();
+            cluster_sync_all();
+            if (cr == 0 && warp == 0) {
+                const float ksum = brute_merge(p.brute + (long long)b * TAIL_CL * P24_TOPK, kc);
                 int k = (int)ksum;
                 if (k < 1) k = 1;
                 const int kk = min(k, ncand);
-                __syncthreads();
-                if (warp == 0) {
-                    const int take = warp_select_claims(p, S, b, g, kk, claimg + g * P24_TOPK);
-                    if (lane == 0) {
-                        p.dyn_k[b * p.Lmax + g] = kk;
-                        ntake[g] = take;
-                        kreq[g] = take < kk ? kk : -1;
-                    }
+                const int take = warp_select_claims(p, S, b, g, kk, claimg + g * P24_TOPK);
+                if (lane == 0) {
+                    p.dyn_k[b * p.Lmax + g] = kk;
+                    ntake[g] = take;
+                    kreq[g] = take < kk ? kk : -1;
                 }
-                __threadfence();
-                __syncthreads();
             }
+            __threadfence();
+            cluster_sync_all();
+        }
+        if (cr == 0) {
             for (int g = 0; g < n; ++g) {
                 const int kk = __ldcg(&kreq[g]);
                 if (kk < 0) continue;
@@ -1889,9 +1921,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
     if (!p.sums28) return;
     if (p.nranks > 1) {
         // ---- fused all-reduce, publish side: my 28 sums into everybody's mailbox (P2P stores over NVLink), a flag with the
-        // call's epoch behind them.  Two mailbox halves alternate with the epoch.  k_fin collects. ----------------------
+        // call's epoch behind them.  MBOX_EPOCHS slot sets alternate with the epoch.  k_fin (p24_comm_finish) collects. ----
         const unsigned ep = p.epoch;
-        const int half = (int)(ep & 1u) * P24_MAX_RANKS;
+        const int half = (int)(ep % MBOX_EPOCHS) * P24_MAX_RANKS;
         for (int q = warp; q < p.nranks; q += TAIL_WARPS)
             if (lane < 28) p.mbox[q][(half + p.rank) * MBOX_SLOT + lane] = S.sums[lane];
         __threadfence_system();
@@ -1906,29 +1938,38 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
     if (p.state26 && warp == 0) finalize_warp(S.sums, p.state26, p.result54, p.weights27);
 }
 
-// k_fin (several GPUs): collect side of the fused all-reduce.  One warp: wait for the flag of every rank in my own
-// mailbox, add the contributions in rank order (the same bits on every rank), finalize.  It spins without a time-out,
-// like a NCCL kernel: a wrong loss is worse than a hang that the framework's watchdog reports.  The wait is measured
-// (status word) so that rank skew can be told from link latency.
-__global__ void __launch_bounds__(32) k_fin(const __grid_constant__ Params p) {
-    pdl_trigger();
-    pdl_wait();  // k_tail of this step is complete: my own contribution is in my mailbox
+// k_fin (several GPUs): collect side of the fused all-reduce (p24_comm_finish).  One warp: wait for the flag of every rank
+// in my own mailbox, add the contributions in rank order (the same bits on every rank), finalize.  It spins without a
+// time-out, like a NCCL kernel: a wrong loss is worse than a hang that the framework's watchdog reports.  The wait is
+// measured (status word) so that rank skew can be told from link latency.  The host side launches it on a side stream,
+// behind an event of the chain: the next step's kernels do not depend on the global sums and run meanwhile.
+struct FinParams {
+    float* mbox;       // my own mailbox
+    int nranks;
+    unsigned epoch;
+    float* sums28;
+    float* state26;
+    float* result54;
+    float* weights27;
+    int* status;       // (may be NULL)
+};
+
+__global__ void __launch_bounds__(32) k_fin(const FinParams p) {
     const int lane = threadIdx.x;
     __shared__ float s_sums[28];
     const unsigned ep = p.epoch;
-    const int half = (int)(ep & 1u) * P24_MAX_RANKS;
+    const int half = (int)(ep % MBOX_EPOCHS) * P24_MAX_RANKS;
     const long long t0 = clock64();
     if (lane < p.nranks) {
-        volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.mbox[p.rank] + (half + lane) * MBOX_SLOT + 32);
+        volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.mbox + (half + lane) * MBOX_SLOT + 32);
         while (*f != ep) __nanosleep(32);
         __threadfence_system();
     }
     __syncwarp();
-    if (lane == 0) p.status[ST_WAITCYC] = (int)min((long long)0x7fffffff, clock64() - t0);
+    if (lane == 0 && p.status) p.status[ST_WAITCYC] = (int)min((long long)0x7fffffff, clock64() - t0);
     if (lane < 28) {
         float t = 0.0f;
-        for (int r = 0; r < p.nranks; ++r)
-            t += *reinterpret_cast<volatile float*>(p.mbox[p.rank] + (half + r) * MBOX_SLOT + lane);
+        for (int r = 0; r < p.nranks; ++r) t += *reinterpret_cast<volatile float*>(p.mbox + (half + r) * MBOX_SLOT + lane);
         s_sums[lane] = t;
         p.sums28[lane] = t;
     }
@@ -2061,6 +2102,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p.list = (float2*)(ws + L.list);
     p.cbits = (unsigned*)(ws + L.cbits);
     p.wlist = (int2*)(ws + L.wlist);
+    p.brute = (float*)(ws + L.brute);
     p.claimg = (int*)(ws + L.claimg);
     p.kreq = (int*)(ws + L.kreq);
     p.ntake = (int*)(ws + L.ntake);
@@ -2134,15 +2176,26 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     p24::prof_mark(2, st);
     e = launch(k_tail, dim3(B * TAIL_CL), dim3(TAIL_THREADS), dyn_tail, st, pdl, p, TAIL_CL);
     if (e != cudaSuccess) return (int)e;
-    if (p.nranks > 1) {
-        e = launch(k_fin, dim3(1), dim3(32), 0, st, pdl, p);
-        if (e != cudaSuccess) return (int)e;
-    }
     p24::prof_mark(3, st);
     return (int)cudaGetLastError();
 }
 
-extern "C" size_t p24_comm_mailbox_bytes(void) { return (size_t)2 * P24_MAX_RANKS * MBOX_SLOT * sizeof(float); }
+extern "C" size_t p24_comm_mailbox_bytes(void) { return (size_t)MBOX_EPOCHS * P24_MAX_RANKS * MBOX_SLOT * sizeof(float); }
+
+extern "C" int p24_comm_finish(void* d_own_mailbox, int nranks, uint32_t epoch, float* sums28, float* state26, float* result54,
+                               float* weights_n27, void* workspace, int B, int A, int Lmax, void* stream) {
+    if (!d_own_mailbox || !sums28 || nranks < 2 || nranks > P24_MAX_RANKS) return P24_E_BADARG;
+    if (state26 && (!result54 || !weights_n27)) return P24_E_BADARG;
+    FinParams f;
+    f.mbox = (float*)d_own_mailbox;
+    f.nranks = nranks;
+    f.epoch = epoch;
+    f.sums28 = sums28; f.state26 = state26; f.result54 = result54; f.weights27 = weights_n27;
+    f.status = nullptr;
+    if (workspace && B > 0 && A > 0 && Lmax > 0) f.status = (int*)((char*)workspace + p24_layout(B, A, Lmax).status);
+    k_fin<<<1, 32, 0, (cudaStream_t)stream>>>(f);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int p24_comm_alloc(void** d_mailbox) {
     if (!d_mailbox) return P24_E_BADARG;

@@ -5,9 +5,10 @@ at all.
 
 Two ways to do the all-reduce:
   * ``PeerComm`` (default on GPUs of one box): every rank owns a small mailbox in device memory that its peers map
-    through CUDA IPC; the last CTA of the kernel chain stores its sums into every peer's mailbox over NVLink / NVSwitch,
-    waits for the peers' flags and adds the contributions in rank order, then applies the normalisation itself: the
-    compute step and its collective are one kernel (no NCCL launch, no separate finalize kernel).
+    through CUDA IPC; the last CTA of the kernel chain stores its sums into every peer's mailbox over NVLink / NVSwitch
+    (the publish half is part of the compute kernel); a one-warp collect kernel on a side stream waits for the peers'
+    flags, adds the contributions in rank order and applies the normalisation, while the next step's chain already runs
+    (nothing in it depends on the global sums).  No NCCL launch.
   * NCCL ``all_reduce`` of the 28-float vector on the compute stream followed by ``p24_loss_finalize`` (fallback when
     the mailboxes cannot be mapped; gloo in the CPU tests).
 """
@@ -73,6 +74,13 @@ class PeerComm:
                 ptrs[r] = peer.value
         self.pointers = ptrs
         self._epoch = 0
+        # the collect half of the exchange (p24_comm_finish) runs on a side stream behind an event of the chain: the next
+        # step's kernels do not depend on the global sums.  A rank may run one step ahead of its own collect kernel, not
+        # more (four mailbox slot sets): step n + 1 waits for the finish of step n - 1.
+        self.side = torch.cuda.Stream()
+        self._chain_ev = [torch.cuda.Event() for _ in range(4)]
+        self._fin_ev = [torch.cuda.Event() for _ in range(4)]
+        self._pending = []   # epochs whose finish the compute stream has not been ordered behind yet
         dist.barrier(group=group)  # every mailbox is mapped everywhere before the first kernel writes to it
 
     def close(self):
@@ -87,8 +95,35 @@ class PeerComm:
         self._own = None
 
     def next_epoch(self) -> int:
+        """Called once per step, before the chain is enqueued: the new epoch; the compute stream is ordered behind the
+        collect kernel of the step before the previous one (flow control of the mailbox slots)."""
+        cur = torch.cuda.current_stream()
+        while len(self._pending) > 1:
+            cur.wait_event(self._fin_ev[self._pending.pop(0) % 4])
         self._epoch = (self._epoch + 1) & 0xFFFFFFFF or 1
         return self._epoch
+
+    def finish(self, sums28, state26, result54, weights27, ws_ptr, B, A, Lmax):
+        """Enqueue the collect kernel of the current epoch on the side stream, behind the chain just enqueued."""
+        from . import lib as _lib
+        e = self._epoch
+        cur = torch.cuda.current_stream()
+        self._chain_ev[e % 4].record(cur)
+        self.side.wait_event(self._chain_ev[e % 4])
+        code = self._lib.p24_comm_finish(self._own, self.nranks, e, sums28.data_ptr(),
+                                         state26.data_ptr() if state26 is not None else None,
+                                         result54.data_ptr() if result54 is not None else None,
+                                         weights27.data_ptr() if weights27 is not None else None,
+                                         ws_ptr, B, A, Lmax, self.side.cuda_stream)
+        _lib.check(code, "p24_comm_finish")
+        self._fin_ev[e % 4].record(self.side)
+        self._pending.append(e)
+
+    def wait(self):
+        """Order the current stream behind every collect kernel enqueued so far (results are then safe to read)."""
+        cur = torch.cuda.current_stream()
+        while self._pending:
+            cur.wait_event(self._fin_ev[self._pending.pop(0) % 4])
 
 
 def attach(loss_function, group=None, peer: bool = True):

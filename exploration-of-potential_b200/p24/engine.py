@@ -181,6 +181,10 @@ class SimOTAEngine:
             with torch.cuda.device(dev):
                 code = lib.p24_simota_loss_batch(*args)
         _lib.check(code, "p24_simota_loss_batch")
+        if comm is not None:
+            # the collect half of the fused all-reduce, on the comm's side stream (sums28 / the finalize buffers are valid
+            # once comm.wait() has ordered the consumer's stream behind it)
+            comm.finish(out.sums28, *(finalize if finalize is not None else (None, None, None)), ws_ptr, B, A, Lmax)
         return out
 
     def read_status(self):

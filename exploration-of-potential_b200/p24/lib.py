@@ -35,6 +35,8 @@ _PROTOS = {
     "p24_comm_export": (C.c_int, [c_ptr, C.c_char_p]),
     "p24_comm_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "p24_comm_close": (C.c_int, [c_ptr]),
+    "p24_comm_finish": (C.c_int, [c_ptr, C.c_int, C.c_uint32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
+                                  c_ptr]),
     "p24_workspace_init": (C.c_int, [c_ptr, C.c_size_t, c_ptr]),
     "p24_loss_finalize": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "p24_circle_inter_fwd": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int,

@@ -98,6 +98,7 @@ class _LossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, outputs, labels, owner, x_shifts, y_shifts, strides):
         result54, weights27, asg = owner.forward_async((x_shifts, y_shifts, strides, outputs.detach(), []), labels)
+        owner.wait_results()
         ctx.owner_nc = owner.num_classes
         ctx.asg = asg
         ctx.save_for_backward(outputs.detach(), labels, weights27)
@@ -201,9 +202,12 @@ class Loss_Function(nn.Module):
 
     # -- bookkeeping of the asynchronous path ---------------------------------------------------------------
     def wait_results(self):
-        """Order everything ``forward_async`` has enqueued before later work of the current stream (the kernels of
-        this path all run on the caller's stream: nothing to do; kept as the one place that would change)."""
-        return None
+        """Order the current stream behind everything ``forward_async`` has enqueued.  With the fused peer all-reduce
+        the normalisation runs on a side stream (``p24.dist.PeerComm``): result54 / weights27 / the state are valid for
+        the current stream only after this call (``forward`` makes it before it reads the result)."""
+        comm = getattr(self, "peer_comm", None)
+        if comm is not None:
+            comm.wait()
 
     def check_errors(self):
         """Raise ``P24Error`` when a kernel reported an internal error (sticky bits in the workspace: window-list
@@ -228,7 +232,7 @@ class Loss_Function(nn.Module):
         return {"brute_force_gts": sum(s[1] for s in st), "exact_gts": sum(s[7] for s in st),
                 "spill_gts": sum(s[2] for s in st), "gts": gts,
                 "list_max": max([s[3] for s in st] + [0]), "list_mean": (sum(s[5] for s in st) / gts) if gts else 0.0,
-                "list_capacity": 2048}
+                "list_capacity": 4096}
 
     def forward(self, outputs_train, labels):
         outputs = outputs_train[3]
@@ -237,6 +241,7 @@ class Loss_Function(nn.Module):
             asg = self.last_assignment
         else:
             r, _, asg = self.forward_async(outputs_train, labels)
+        self.wait_results()
         fg = asg.fg_mask.view(-1).bool()
         rows = outputs.reshape(-1, outputs.shape[-1])[fg]
         if rows.shape[0] == 0:  # losses.py:111-115

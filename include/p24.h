@@ -77,9 +77,9 @@ int p24_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
  *              sums[25]    = sum BCEWithLogits(cls[fg], onehot * pred_iou)   (losses.py:298)
  *              sums[26]    = sum_b num_fg, sums[27] = sum_b num_gt
  *              This 28-float vector is what is all-reduced across GPUs.
- *   state26 / result54 / weights_n27 (all three or none): when given, the last CTA also applies
- *              p24_loss_finalize (single-GPU case: one launch less); with several GPUs pass NULL, all-reduce
- *              sums28 and call p24_loss_finalize.
+ *   state26 / result54 / weights_n27 (all three or none): when given (single GPU), the last CTA also applies
+ *              p24_loss_finalize (one launch less); with several GPUs they are ignored here: p24_comm_finish (fused peer
+ *              exchange) or an all-reduce of sums28 followed by p24_loss_finalize apply them.
  * The workspace (p24_workspace_bytes, 256-byte aligned) must have been cleared once with p24_workspace_init;
  * a successful call leaves it ready for the next one.  One workspace serves one call at a time.
  */
@@ -100,16 +100,23 @@ int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_
  *   rank, nranks this process's rank and the number of ranks (<= P24_MAX_RANKS); nranks <= 1 or h_mailboxes == NULL:
  *                no exchange
  *   epoch        call counter, the same on every rank, starting at 1 and incremented by the caller for every call
- * and the last CTA of the chain stores its 28 sums into every peer's mailbox (P2P stores + a flag), waits for the
- * flags of all peers in its own mailbox, adds the contributions in rank order (bit-identical on all ranks) and goes on
- * to the normalisation / re-weighting: no NCCL launch, no separate finalize kernel.  sums28 then holds the global sums.
- * All ranks must make the same sequence of calls. */
+ * and the last CTA of the chain stores its 28 sums into every peer's mailbox (P2P stores + a flag with the epoch): the
+ * PUBLISH half of the exchange, fused into the compute kernel.  The COLLECT half is p24_comm_finish: one warp waits for the
+ * flags of all peers in the rank's own mailbox, adds the contributions in rank order (bit-identical on all ranks), writes
+ * sums28 and applies the normalisation / re-weighting (state26 / result54 / weights_n27 as in p24_loss_finalize): no NCCL
+ * launch.  Enqueue it behind the chain -- on a side stream with an event if the next step should not wait for the peers:
+ * nothing of the next step's chain depends on the global sums.  Four slot sets alternate with the epoch: a rank may run
+ * ONE step ahead of its own p24_comm_finish (make step n + 1 wait for the finish of step n - 1), not more.
+ * All ranks must make the same sequence of calls.  `workspace` (+ B, A, Lmax) is optional: the wait is recorded in its
+ * status word 4. */
 size_t p24_comm_mailbox_bytes(void);
 int p24_comm_alloc(void** d_mailbox);
 int p24_comm_free(void* d_mailbox);
 int p24_comm_export(void* d_mailbox, void* h_handle64);
 int p24_comm_import(const void* h_handle64, void** d_peer_mailbox);
 int p24_comm_close(void* d_peer_mailbox);
+int p24_comm_finish(void* d_own_mailbox, int nranks, uint32_t epoch, float* sums28, float* state26, float* result54,
+                    float* weights_n27, void* workspace, int B, int A, int Lmax, void* stream);
 
 /* Normalisation and stateful re-weighting (models/losses.py:280-345).
  * state[26] = last_iou_loss[24], last_obj_loss, last_cls_loss (initially 1.0), updated in place.

@@ -36,6 +36,29 @@ for step in range(6):  # several steps: the re-weighting state and the mailbox e
         if rank == 0:
             print(f"step {step} {name:5s} fused={lf.peer_comm is not None} loss {float(got[0]):.6f} full-batch {float(want[0]):.6f} rel {rel:.2e} "
                   f"same on all ranks {float(lo) == float(hi)} {'ok' if ok else 'FAIL'}")
+# back-to-back asynchronous steps: the collect kernels run on the side stream while the next chains are enqueued (the
+# mailbox slot sets and the one-step run-ahead limit are exercised); peer and NCCL must end in the same state
+a_peer, a_nccl = p24_dist.attach(Loss_Function(80), peer=True), p24_dist.attach(Loss_Function(80), peer=False)
+outs = [synth.make_head_outputs(B, size, 80, seed=70 + i).to(dev) for i in range(3)]
+labs = [synth.make_labels(B, 11, 50, size, 80, seed=70 + i, kind="smooth").to(dev) for i in range(3)]
+res = {}
+for name, lf in (("peer", a_peer), ("nccl", a_nccl)):
+    for step in range(9):
+        o_sh, l_sh = p24_dist.shard_batch(outs[step % 3], labs[step % 3], rank, world)
+        r, _, _ = lf.forward_async((g[0], g[1], g[2], o_sh, []), l_sh)
+    lf.wait_results()
+    torch.cuda.synchronize()
+    lf.check_errors()
+    res[name] = r.clone()
+rel = float(((res["peer"].double() - res["nccl"].double()).abs() / res["nccl"].double().abs().clamp_min(1e-9)).max())
+gat = [torch.zeros_like(res["peer"]) for _ in range(world)]
+dist.all_gather(gat, res["peer"])
+same = all(torch.equal(gat[0], x) for x in gat)
+ok = rel < 1e-5 and same
+fails += 0 if ok else 1
+if rank == 0:
+    print(f"async x9: peer vs nccl rel {rel:.2e}, peer result bit-identical on all ranks {same} {'ok' if ok else 'FAIL'}")
+a_peer.peer_comm and a_peer.peer_comm.close()
 t = torch.tensor([fails], device=dev)
 dist.all_reduce(t)
 if rank == 0:

@@ -56,6 +56,13 @@ def stat(label, d):
         print(f"   {label:18s} mean {d.mean():7.2f}  p50 {np.median(d):7.2f}  max {d.max():7.2f}  (n={d.size})")
 
 
+k0 = buf[0].astype(np.float64)
+rows0 = np.concatenate([k0[b * 64:b * 64 + (wl["G"] + 1) // 2] for b in range(B)])
+p0 = rows0[:, 0].min()
+print(f"== k_prep: first CTA start {us(p0):.1f} us, last end {us(rows0[:, 7].max()):.1f} us (k_pass past its pdl_wait at 0)")
+for lab, a, b_ in [("count labels", 0, 1), ("records+pairs", 1, 2), ("image barrier", 2, 3), ("stage records", 3, 4),
+                   ("seed points", 4, 5), ("dedupe+rank+sync", 5, 6), ("T + far2", 6, 7), ("CTA total", 0, 7)]:
+    stat(lab, rows0[:, b_] - rows0[:, a])
 print(f"== k_pass: CTAs past pdl_wait at 0 us; last CTA end {us(kp[6000:7024, 1].max()):.1f} us")
 tl = kp[:min(B * tiles, 4095)]
 print(f"   tiles: first start {us(tl[:, 0].min()):.1f}  last end {us(tl[:, 7].max()):.1f}")
