@@ -1454,29 +1454,82 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
         if (pick) tref = fmaxf(tref, v10);
     }
     TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 3);
-    int nsurv = 0;
-    for (int i0 = 0; i0 < lc; i0 += 256) {
-        float2 e[8];
+    // the entries whose bound reaches `thr`, compacted (anchor, upper bound, lower bound); returns their number (the buffers
+    // hold the first TAIL_SURV of them)
+    auto compact = [&](float thr) {
+        int ns = 0;
+        for (int i0 = 0; i0 < lc; i0 += 256) {
+            float2 e[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + 32 * u + lane;
-            e[u] = i0 == 0 ? e0[u] : (i < lc ? __ldcg(lst + i) : make_float2(P24_NEG_INF, 0.0f));
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const bool keep = !(e[u].x < tref);
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            const int at = nsurv + __popc(bal & ((1u << lane) - 1u));
-            if (keep && at < TAIL_SURV) {
-                const int bits = __float_as_int(e[u].y);
-                S.surv[warp][at] = bits & 0x7fffffff;
-                S.sval[warp][at] = e[u].x;
-                S.slb[warp][at] = (bits & 0x80000000) ? e[u].x - 7e-5f : 0.0f;  // (pair values are >= 0)
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 32 * u + lane;
+                e[u] = i0 == 0 ? e0[u] : (i < lc ? __ldcg(lst + i) : make_float2(P24_NEG_INF, 0.0f));
             }
-            nsurv += __popc(bal);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool keep = !(e[u].x < thr);
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                const int at = ns + __popc(bal & ((1u << lane) - 1u));
+                if (keep && at < TAIL_SURV) {
+                    const int bits = __float_as_int(e[u].y);
+                    S.surv[warp][at] = bits & 0x7fffffff;
+                    S.sval[warp][at] = e[u].x;
+                    S.slb[warp][at] = (bits & 0x80000000) ? e[u].x - 7e-5f : 0.0f;  // (pair values are >= 0)
+                }
+                ns += __popc(bal);
+            }
         }
+        __syncwarp();
+        return ns;
+    };
+    const unsigned gm = group_mask();
+    const int grp = lane >> 3, sub = lane & 7;
+    const float gcx = rec[GT_CX], gcy = rec[GT_CY];
+    // exact values of the first `cnt` buffered survivors into S.sval, 16 at a time: every 8-lane group requests the rows
+    // of its 4 pairs, then evaluates them
+    auto exact_eval = [&](int cnt) {
+        for (int j0 = 0; j0 < cnt; j0 += 16) {
+            float rp[4][3], pc[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 4 * u + grp;
+                const float* row = img + (long long)S.surv[warp][min(j, cnt - 1)] * p.row_stride;
+                pc[u][0] = row[0];
+                pc[u][1] = row[1];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) rp[u][q] = row[2 + sub * 3 + q];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 4 * u + grp;
+                const float d = p24_centre_dist(gcx, gcy, pc[u][0], pc[u][1]);
+                float sm = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) sm = sm + p24_ray_loss(rec[GT_RG + sub * 3 + q], rp[u][q], d);  // (inlined: no call on this latency chain)
+                sm = group_sum(sm, gm);
+                float v = (sm / 24.0f) / 2.0f;
+                if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
+                if (sub == 0 && j < cnt) S.sval[warp][j] = v;
+            }
+        }
+        __syncwarp();
+    };
+    int nsurv = compact(tref);
+    if (nsurv > TAIL_SURV) {
+        // more survivors than the buffers hold (a GT with many near-ties or few all-apart pairs): the exact values of the
+        // buffered ones give a certified threshold (their kc-th largest), then the list is compacted again
+        exact_eval(TAIL_SURV);
+        float t3 = P24_NEG_INF;
+        for (int j = lane; j < TAIL_SURV; j += 32) {
+            const float vj = S.sval[warp][j];
+            int rank = 0;
+            for (int i = 0; i < TAIL_SURV; ++i) rank += kv_gt(S.sval[warp][i], i, vj, j) ? 1 : 0;
+            if (rank == kc - 1 && vj < P24_POS_INF) t3 = vj;
+        }
+        t3 = warp_max(t3);
+        __syncwarp();
+        if (t3 > tref) nsurv = compact(t3);
     }
-    __syncwarp();
 #ifdef P24_TIMING
     if (lane == 0) {
         g_tstamp[2][1024 + b * 64 + (slot - b * p.Lmax)][8] = nsurv;
@@ -1523,36 +1576,7 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
         }
     }
     if (lane == 0) atomicAdd(&p.status[ST_EXACT], 1);
-    // exact values, 16 survivors at a time: every 8-lane group requests the rows of its 4 pairs, then evaluates them
-    const unsigned gm = group_mask();
-    const int grp = lane >> 3, sub = lane & 7;
-    const float gcx = rec[GT_CX], gcy = rec[GT_CY];
-    for (int j0 = 0; j0 < nsurv; j0 += 16) {
-        float rp[4][3], pc[4][2];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + 4 * u + grp;
-            const float* row = img + (long long)S.surv[warp][min(j, nsurv - 1)] * p.row_stride;
-            pc[u][0] = row[0];
-            pc[u][1] = row[1];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) rp[u][q] = row[2 + sub * 3 + q];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + 4 * u + grp;
-            const float d = p24_centre_dist(gcx, gcy, pc[u][0], pc[u][1]);
-            float sm = 0.0f;
-#pragma unroll 1
-            for (int q = 0; q < 3; ++q) sm = sm + p24_ray_loss(rec[GT_RG + sub * 3 + q], rp[u][q], d);  // (inlined: no call on this latency chain)
-            sm = group_sum(sm, gm);
-            float v = (sm / 24.0f) / 2.0f;
-            if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
-            if (sub == 0 && j < nsurv) S.sval[warp][j] = v;
-            if (u == 0 && j0 == 0) TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 11);
-        }
-    }
-    __syncwarp();
+    exact_eval(nsurv);
     TMARK(2, 1024 + b * 64 + (slot - b * p.Lmax), 4);
     // the kc largest by rank counting, then summed in descending order by one lane
     float* top = reinterpret_cast<float*>(S.surv[warp]);  // (the anchors are no longer needed)
