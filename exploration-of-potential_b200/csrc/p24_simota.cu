@@ -1116,7 +1116,9 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
 #define TAIL_SURV 64   // survivors a GT warp evaluates per batch
 #define ROW_PAD 108    // floats per staged row (27 + nc <= ROW_PAD is required for staging; else rows are read in place)
 #define MBOX_SLOT 64   // floats per (epoch, rank) slot of a mailbox: 28 sums, flag at [32]
-#define MBOX_EPOCHS 4  // slots alternate with the epoch: a rank runs at most one step ahead of its own collect kernel
+#define MBOX_EPOCHS 4  // slots alternate with the epoch: a rank runs at most two steps ahead of its own collect kernel
+#define MBOX_FLAGS (MBOX_EPOCHS * P24_MAX_RANKS * MBOX_SLOT)  // own flags behind the slots: [0] epoch published by k_tail,
+                                                              // [1] epoch finished by k_fin
 
 // normalisation + stateful re-weighting, losses.py:280-345; executed by one warp
 __device__ void finalize_warp(const float* sums28, float* state26, float* result54, float* weights_n27) {
@@ -1948,6 +1950,13 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
         // call's epoch behind them.  MBOX_EPOCHS slot sets alternate with the epoch.  k_fin (p24_comm_finish) collects. ----
         const unsigned ep = p.epoch;
         const int half = (int)(ep % MBOX_EPOCHS) * P24_MAX_RANKS;
+        // flow control of the slot sets: not before my own collect kernel of epoch ep - 2 has finished (then every peer has
+        // consumed epoch ep - 4, whose slots are overwritten here: see p24.h)
+        if (tid == 0) {
+            volatile unsigned* fin = reinterpret_cast<volatile unsigned*>(p.mbox[p.rank] + MBOX_FLAGS + 1);
+            while ((int)(ep - *fin) > 2) __nanosleep(64);
+        }
+        __syncthreads();
         for (int q = warp; q < p.nranks; q += TAIL_WARPS)
             if (lane < 28) p.mbox[q][(half + p.rank) * MBOX_SLOT + lane] = S.sums[lane];
         __threadfence_system();
@@ -1956,6 +1965,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
             __threadfence_system();
             *reinterpret_cast<volatile unsigned*>(p.mbox[tid] + (half + p.rank) * MBOX_SLOT + 32) = ep;
         }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile unsigned*>(p.mbox[p.rank] + MBOX_FLAGS) = ep;  // k_fin of this epoch may go
         return;
     }
     if (tid < 28) p.sums28[tid] = S.sums[tid];
@@ -1965,8 +1977,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
 // k_fin (several GPUs): collect side of the fused all-reduce (p24_comm_finish).  One warp: wait for the flag of every rank
 // in my own mailbox, add the contributions in rank order (the same bits on every rank), finalize.  It spins without a
 // time-out, like a NCCL kernel: a wrong loss is worse than a hang that the framework's watchdog reports.  The wait is
-// measured (status word) so that rank skew can be told from link latency.  The host side launches it on a side stream,
-// behind an event of the chain: the next step's kernels do not depend on the global sums and run meanwhile.
+// measured (status word) so that rank skew can be told from link latency.  The host side launches it on a side stream
+// with NO stream dependency on the chain (an event between two steps would break their programmatic overlap): it waits on
+// a flag that the chain's last CTA sets.  The next step's kernels do not depend on the global sums and run meanwhile.
 struct FinParams {
     float* mbox;       // my own mailbox
     int nranks;
@@ -1983,6 +1996,13 @@ __global__ void __launch_bounds__(32) k_fin(const FinParams p) {
     __shared__ float s_sums[28];
     const unsigned ep = p.epoch;
     const int half = (int)(ep % MBOX_EPOCHS) * P24_MAX_RANKS;
+    // launched on a side stream without any stream dependency on the chain: wait until this rank's k_tail has published
+    // the epoch (a one-warp kernel: it cannot keep the chain from running)
+    if (lane == 0) {
+        volatile unsigned* pub = reinterpret_cast<volatile unsigned*>(p.mbox + MBOX_FLAGS);
+        while (*pub != ep) __nanosleep(64);
+    }
+    __syncwarp();
     const long long t0 = clock64();
     if (lane < p.nranks) {
         volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.mbox + (half + lane) * MBOX_SLOT + 32);
@@ -1999,6 +2019,9 @@ __global__ void __launch_bounds__(32) k_fin(const FinParams p) {
     }
     __syncwarp();
     if (p.state26) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile unsigned*>(p.mbox + MBOX_FLAGS + 1) = ep;
 }
 
 __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__ state26, float* __restrict__ result54,
@@ -2204,7 +2227,7 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     return (int)cudaGetLastError();
 }
 
-extern "C" size_t p24_comm_mailbox_bytes(void) { return (size_t)MBOX_EPOCHS * P24_MAX_RANKS * MBOX_SLOT * sizeof(float); }
+extern "C" size_t p24_comm_mailbox_bytes(void) { return (size_t)(MBOX_FLAGS + 64) * sizeof(float); }
 
 extern "C" int p24_comm_finish(void* d_own_mailbox, int nranks, uint32_t epoch, float* sums28, float* state26, float* result54,
                                float* weights_n27, void* workspace, int B, int A, int Lmax, void* stream) {

@@ -74,13 +74,12 @@ class PeerComm:
                 ptrs[r] = peer.value
         self.pointers = ptrs
         self._epoch = 0
-        # the collect half of the exchange (p24_comm_finish) runs on a side stream behind an event of the chain: the next
-        # step's kernels do not depend on the global sums.  A rank may run one step ahead of its own collect kernel, not
-        # more (four mailbox slot sets): step n + 1 waits for the finish of step n - 1.
+        # the collect half of the exchange (p24_comm_finish) runs on a side stream with no stream dependency on the chain (it
+        # waits for a flag of the chain's last CTA): the next step's kernels do not depend on the global sums, and no event
+        # sits between two steps on the compute stream (that would break their programmatic overlap)
         self.side = torch.cuda.Stream()
-        self._chain_ev = [torch.cuda.Event() for _ in range(4)]
-        self._fin_ev = [torch.cuda.Event() for _ in range(4)]
-        self._pending = []   # epochs whose finish the compute stream has not been ordered behind yet
+        self._fin_ev = torch.cuda.Event()
+        self._dirty = False   # a collect kernel has been enqueued that the compute stream is not ordered behind yet
         dist.barrier(group=group)  # every mailbox is mapped everywhere before the first kernel writes to it
 
     def close(self):
@@ -95,35 +94,27 @@ class PeerComm:
         self._own = None
 
     def next_epoch(self) -> int:
-        """Called once per step, before the chain is enqueued: the new epoch; the compute stream is ordered behind the
-        collect kernel of the step before the previous one (flow control of the mailbox slots)."""
-        cur = torch.cuda.current_stream()
-        while len(self._pending) > 1:
-            cur.wait_event(self._fin_ev[self._pending.pop(0) % 4])
         self._epoch = (self._epoch + 1) & 0xFFFFFFFF or 1
         return self._epoch
 
     def finish(self, sums28, state26, result54, weights27, ws_ptr, B, A, Lmax):
-        """Enqueue the collect kernel of the current epoch on the side stream, behind the chain just enqueued."""
+        """Enqueue the collect kernel of the current epoch on the side stream (call it once per step, right after the
+        chain has been enqueued)."""
         from . import lib as _lib
-        e = self._epoch
-        cur = torch.cuda.current_stream()
-        self._chain_ev[e % 4].record(cur)
-        self.side.wait_event(self._chain_ev[e % 4])
-        code = self._lib.p24_comm_finish(self._own, self.nranks, e, sums28.data_ptr(),
+        code = self._lib.p24_comm_finish(self._own, self.nranks, self._epoch, sums28.data_ptr(),
                                          state26.data_ptr() if state26 is not None else None,
                                          result54.data_ptr() if result54 is not None else None,
                                          weights27.data_ptr() if weights27 is not None else None,
                                          ws_ptr, B, A, Lmax, self.side.cuda_stream)
         _lib.check(code, "p24_comm_finish")
-        self._fin_ev[e % 4].record(self.side)
-        self._pending.append(e)
+        self._dirty = True
 
     def wait(self):
         """Order the current stream behind every collect kernel enqueued so far (results are then safe to read)."""
-        cur = torch.cuda.current_stream()
-        while self._pending:
-            cur.wait_event(self._fin_ev[self._pending.pop(0) % 4])
+        if self._dirty:
+            self._fin_ev.record(self.side)
+            torch.cuda.current_stream().wait_event(self._fin_ev)
+            self._dirty = False
 
 
 def attach(loss_function, group=None, peer: bool = True):

@@ -104,9 +104,11 @@ int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_
  * PUBLISH half of the exchange, fused into the compute kernel.  The COLLECT half is p24_comm_finish: one warp waits for the
  * flags of all peers in the rank's own mailbox, adds the contributions in rank order (bit-identical on all ranks), writes
  * sums28 and applies the normalisation / re-weighting (state26 / result54 / weights_n27 as in p24_loss_finalize): no NCCL
- * launch.  Enqueue it behind the chain -- on a side stream with an event if the next step should not wait for the peers:
- * nothing of the next step's chain depends on the global sums.  Four slot sets alternate with the epoch: a rank may run
- * ONE step ahead of its own p24_comm_finish (make step n + 1 wait for the finish of step n - 1), not more.
+ * launch.  Enqueue it on ANY stream of the device after the call (it waits for the chain's publication through a flag
+ * in the mailbox, not through the stream): on a side stream the next step does not wait for the peers -- nothing of
+ * the next step's chain depends on the global sums.  Four slot sets alternate with the epoch; the chain itself holds
+ * back the publication of epoch e until this rank's p24_comm_finish of epoch e - 2 has completed, so the calls of
+ * p24_comm_finish must be enqueued in epoch order and none may be skipped.
  * All ranks must make the same sequence of calls.  `workspace` (+ B, A, Lmax) is optional: the wait is recorded in its
  * status word 4. */
 size_t p24_comm_mailbox_bytes(void);
