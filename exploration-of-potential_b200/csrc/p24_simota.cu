@@ -2000,7 +2000,7 @@ __global__ void __launch_bounds__(32) k_fin(const FinParams p) {
     // the epoch (a one-warp kernel: it cannot keep the chain from running)
     if (lane == 0) {
         volatile unsigned* pub = reinterpret_cast<volatile unsigned*>(p.mbox + MBOX_FLAGS);
-        while (*pub != ep) __nanosleep(64);
+        while ((int)(*pub - ep) < 0) __nanosleep(64);  // (the chain may already be epochs ahead)
     }
     __syncwarp();
     const long long t0 = clock64();
