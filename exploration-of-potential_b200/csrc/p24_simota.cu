@@ -1115,10 +1115,9 @@ __global__ void __launch_bounds__(P24_THREADS, 4) k_pass(const __grid_constant__
 #define TAIL_WARPS (TAIL_THREADS / 32)
 #define TAIL_SURV 64   // survivors a GT warp evaluates per batch
 #define ROW_PAD 108    // floats per staged row (27 + nc <= ROW_PAD is required for staging; else rows are read in place)
-#define MBOX_SLOT 64   // floats per (epoch, rank) slot of a mailbox: 28 sums, flag at [32]
+#define MBOX_SLOT 64   // floats per (epoch, rank) slot of a mailbox: 28 (value, epoch) words of 8 bytes
 #define MBOX_EPOCHS 4  // slots alternate with the epoch: a rank runs at most two steps ahead of its own collect kernel
-#define MBOX_FLAGS (MBOX_EPOCHS * P24_MAX_RANKS * MBOX_SLOT)  // own flags behind the slots: [0] epoch published by k_tail,
-                                                              // [1] epoch finished by k_fin
+#define MBOX_FLAGS (MBOX_EPOCHS * P24_MAX_RANKS * MBOX_SLOT)  // own flags behind the slots: [1] epoch finished by k_fin
 
 // normalisation + stateful re-weighting, losses.py:280-345; executed by one warp
 __device__ void finalize_warp(const float* sums28, float* state26, float* result54, float* weights_n27) {
@@ -1957,17 +1956,13 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
             while ((int)(ep - *fin) > 2) __nanosleep(64);
         }
         __syncthreads();
-        for (int q = warp; q < p.nranks; q += TAIL_WARPS)
-            if (lane < 28) p.mbox[q][(half + p.rank) * MBOX_SLOT + lane] = S.sums[lane];
-        __threadfence_system();
-        __syncthreads();
-        if (tid < p.nranks) {
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned*>(p.mbox[tid] + (half + p.rank) * MBOX_SLOT + 32) = ep;
+        // every sum travels as one 8-byte word (value, epoch): the word is written atomically, so the receiver needs no
+        // flag behind the data and this CTA no system-wide fence (the way NCCL's low-latency protocol moves small messages)
+        for (int q = tid; q < 28 * p.nranks; q += TAIL_THREADS) {
+            const int r = q / 28, i = q - r * 28;
+            const unsigned long long w = ((unsigned long long)ep << 32) | (unsigned long long)__float_as_uint(S.sums[i]);
+            *reinterpret_cast<volatile unsigned long long*>(p.mbox[r] + (half + p.rank) * MBOX_SLOT + 2 * i) = w;
         }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) *reinterpret_cast<volatile unsigned*>(p.mbox[p.rank] + MBOX_FLAGS) = ep;  // k_fin of this epoch may go
         return;
     }
     if (tid < 28) p.sums28[tid] = S.sums[tid];
@@ -1996,27 +1991,26 @@ __global__ void __launch_bounds__(32) k_fin(const FinParams p) {
     __shared__ float s_sums[28];
     const unsigned ep = p.epoch;
     const int half = (int)(ep % MBOX_EPOCHS) * P24_MAX_RANKS;
-    // launched on a side stream without any stream dependency on the chain: wait until this rank's k_tail has published
-    // the epoch (a one-warp kernel: it cannot keep the chain from running)
-    if (lane == 0) {
-        volatile unsigned* pub = reinterpret_cast<volatile unsigned*>(p.mbox + MBOX_FLAGS);
-        while ((int)(*pub - ep) < 0) __nanosleep(64);  // (the chain may already be epochs ahead)
-    }
-    __syncwarp();
+    // launched on a side stream without any stream dependency on the chain: every (value, epoch) word of every rank --
+    // this rank's own included -- is polled until it carries the epoch (a one-warp kernel: it cannot keep the chain from
+    // running); the values are added in rank order
     const long long t0 = clock64();
-    if (lane < p.nranks) {
-        volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.mbox + (half + lane) * MBOX_SLOT + 32);
-        while (*f != ep) __nanosleep(32);
-        __threadfence_system();
-    }
-    __syncwarp();
-    if (lane == 0 && p.status) p.status[ST_WAITCYC] = (int)min((long long)0x7fffffff, clock64() - t0);
+    float t = 0.0f;
     if (lane < 28) {
-        float t = 0.0f;
-        for (int r = 0; r < p.nranks; ++r) t += *reinterpret_cast<volatile float*>(p.mbox + (half + r) * MBOX_SLOT + lane);
+        for (int r = 0; r < p.nranks; ++r) {
+            volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(p.mbox + (half + r) * MBOX_SLOT + 2 * lane);
+            unsigned long long v = *w;
+            while ((unsigned)(v >> 32) != ep) {
+                __nanosleep(32);
+                v = *w;
+            }
+            t += __uint_as_float((unsigned)v);
+        }
         s_sums[lane] = t;
         p.sums28[lane] = t;
     }
+    __syncwarp();
+    if (lane == 0 && p.status) p.status[ST_WAITCYC] = (int)min((long long)0x7fffffff, clock64() - t0);
     __syncwarp();
     if (p.state26) finalize_warp(s_sums, p.state26, p.result54, p.weights27);
     __threadfence();
