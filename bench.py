@@ -317,7 +317,8 @@ def bench_train(ctx, name, steps, warmup, allreduce, want_e2e=True, want_cpu=Tru
     lf.wait_results()
     lib.p24_profile_enable(0)
     kern_ms = [a / ksteps for a in acc[:len(TRAIN_STAGES)]]
-    per_rank = gather_ranks(ctx, kern_ms + [ms_total / steps, t_host] + lf.exchange_wait_us())
+    status = lf.read_status()   # (one read: the counters restart with it)
+    per_rank = gather_ranks(ctx, kern_ms + [ms_total / steps, t_host, status["exchange_wait_us"]])
     top = max(range(len(TRAIN_STAGES)), key=lambda k: kern_ms[k])
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes_per_image(A, 107, Lmax) * B
@@ -333,7 +334,7 @@ def bench_train(ctx, name, steps, warmup, allreduce, want_e2e=True, want_cpu=Tru
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "kernel_ms": dict(zip(TRAIN_STAGES, kern_ms)),
                 "whole_step_frac": (alg / (ms_step * 1e-3) / 1e9) / peak}
-    stats = lf.path_stats()
+    stats = {k: v for k, v in status.items() if k != "exchange_wait_us"}
 
     # ---- e2e: public API, host (pinned) inputs, H2D + D2H inside the timed region ---------------------------------
     e2e = None

@@ -717,7 +717,8 @@ struct AnchorShared {
     float row[P24_WARPS][ROW_CH][33];
     int cand[P24_THREADS];
     unsigned items[ITEM_CAP];
-    int nitems;
+    float box[P24_WARPS][9];   // per warp: boxes of the anchor centres and of the predicted centres, largest stride
+    int nitems, nnear, nfarl;
 };
 
 // the tile's rows: each warp reads its 32 rows, 27 contiguous floats per row, straight into shared memory
@@ -888,13 +889,66 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
         obj = S.row[warp][26][lane];
     }
     double objpart = active ? (double)p24_bce_logits(obj, 0.0f) : 0.0;
-
-    // ---- one pass over the GTs: centre windows, the inscribed-disc accept and a bit mask of the GTs whose reject radius
-    // the anchor is inside (the only ones that may need a polygon test) ------------------------------------------------
-    bool cheap = false;
     const bool no_prune = (p.flags & P24_F_NO_PRUNE) != 0;
     const bool no_filter = (p.flags & P24_F_NO_FILTER) != 0;
     const bool tiny = !(rpmin >= 0.25f);  // a tiny (or NaN) predicted radius: outside the validated range of the bound
+
+    // ---- which GTs can matter for this tile at all?  The box of the tile's anchor centres against every GT's reject disc
+    // and centre window (-> s_near), the box of its predicted centres against every GT's far2 (-> s_farl): the per-anchor
+    // loops below only visit those ------------------------------------------------------------------------------------
+    int* s_near = reinterpret_cast<int*>(s_rec + (size_t)p.Lmax * GT_REC);
+    int* s_farl = s_near + p.Lmax;
+    {
+        const float big = 3.0e38f;
+        float ax0 = active ? xc : big, ax1 = active ? xc : -big, ay0 = active ? yc : big, ay1 = active ? yc : -big;
+        const bool pok = active && pcx == pcx && pcy == pcy;
+        float px0 = pok ? pcx : big, px1 = pok ? pcx : -big, py0 = pok ? pcy : big, py1 = pok ? pcy : -big;
+        float stm = active ? st : 0.0f;
+        ax0 = -warp_max(-ax0); ax1 = warp_max(ax1); ay0 = -warp_max(-ay0); ay1 = warp_max(ay1);
+        px0 = -warp_max(-px0); px1 = warp_max(px1); py0 = -warp_max(-py0); py1 = warp_max(py1);
+        stm = warp_max(stm);
+        const bool anynan = __any_sync(0xffffffffu, active && !pok);
+        if (lane == 0) {
+            S.box[warp][0] = ax0; S.box[warp][1] = ax1; S.box[warp][2] = ay0; S.box[warp][3] = ay1;
+            S.box[warp][4] = anynan ? -big : px0; S.box[warp][5] = anynan ? big : px1;
+            S.box[warp][6] = anynan ? -big : py0; S.box[warp][7] = anynan ? big : py1;
+            S.box[warp][8] = stm;
+        }
+        if (tid == 0) {
+            S.nnear = 0;
+            S.nfarl = 0;
+        }
+        __syncthreads();
+        ax0 = S.box[0][0]; ax1 = S.box[0][1]; ay0 = S.box[0][2]; ay1 = S.box[0][3];
+        px0 = S.box[0][4]; px1 = S.box[0][5]; py0 = S.box[0][6]; py1 = S.box[0][7];
+        stm = S.box[0][8];
+#pragma unroll
+        for (int w = 1; w < P24_WARPS; ++w) {
+            ax0 = fminf(ax0, S.box[w][0]); ax1 = fmaxf(ax1, S.box[w][1]); ay0 = fminf(ay0, S.box[w][2]); ay1 = fmaxf(ay1, S.box[w][3]);
+            px0 = fminf(px0, S.box[w][4]); px1 = fmaxf(px1, S.box[w][5]); py0 = fminf(py0, S.box[w][6]); py1 = fmaxf(py1, S.box[w][7]);
+            stm = fmaxf(stm, S.box[w][8]);
+        }
+        const float wr = 2.5f * stm * 1.001f + 1e-3f;  // (a little more than the window's half side)
+        for (int g = tid; g < n; g += P24_THREADS) {
+            const float* r = s_rec + g * GT_REC;
+            const float cx = r[GT_CX], cy = r[GT_CY];
+            // distance from the GT centre to the box of the anchor centres (0 inside), with a little slack
+            const float ddx = fmaxf(fmaxf(ax0 - cx, cx - ax1), 0.0f), ddy = fmaxf(fmaxf(ay0 - cy, cy - ay1), 0.0f);
+            const float dmin2 = fmaf(ddx, ddx, ddy * ddy) * 0.999f - 1e-3f;
+            const bool nearb = no_prune || !(dmin2 > r[GT_RREJ2]) || (ddx < wr && ddy < wr) || !(cx == cx) || !(cy == cy);
+            if (nearb) s_near[atomicAdd(&S.nnear, 1)] = g;
+            // largest distance from the GT centre to the box of the predicted centres
+            const float fx = fmaxf(fabsf(cx - px0), fabsf(cx - px1)), fy = fmaxf(fabsf(cy - py0), fabsf(cy - py1));
+            const float dmax2 = fmaf(fx, fx, fy * fy) * 1.001f + 1e-3f;
+            if (!(dmax2 < r[GT_FAR2])) s_farl[atomicAdd(&S.nfarl, 1)] = g;
+        }
+        __syncthreads();
+    }
+    const int nnear = S.nnear, nfarl = S.nfarl;
+
+    // ---- one pass over the GTs that can matter: centre windows, the inscribed-disc accept and a bit mask (by position in
+    // s_near) of the GTs whose reject radius the anchor is inside (the only ones that may need a polygon test) ----------
+    bool cheap = false;
     unsigned near[4] = {0u, 0u, 0u, 0u};  // GTs 0..127; beyond that every GT is handled in place (see below)
     const float r25 = 2.5f * st + 1e-3f * st;  // conservative pre-filter radius of the window test
     const float4* s_rec4 = reinterpret_cast<const float4*>(s_rec);
@@ -902,9 +956,9 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             unsigned m = 0u;
-            const int ge = min(32, n - w * 32);
+            const int ge = min(32, nnear - w * 32);
             for (int j = 0; j < ge; ++j) {
-                const int g = w * 32 + j;
+                const int g = s_near[w * 32 + j];
                 const float4 h = s_rec4[g * (GT_REC / 4)];
                 const float dx = h.x - xc, dy = h.y - yc;
                 const float d2 = fmaf(dx, dx, dy * dy);
@@ -915,7 +969,8 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
             const unsigned all = ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u);
             near[w] = no_prune ? all : m;
         }
-        for (int g = 128; g < n; ++g) {  // more than 128 GTs: windows and discs of the rest
+        for (int q = 128; q < nnear; ++q) {  // more than 128 GTs near the tile: windows and discs of the rest
+            const int g = s_near[q];
             const float4 h = s_rec4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             cheap |= fmaf(dx, dx, dy * dy) < h.z;
@@ -931,7 +986,7 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
         for (int w = 0; w < 4; ++w) {
             unsigned m = near[w];
             while (m) {
-                const int g = w * 32 + __ffs(m) - 1;
+                const int g = s_near[w * 32 + __ffs(m) - 1];
                 m &= m - 1;
                 const int slot = atomicAdd(&S.nitems, 1);
                 if (slot < ITEM_CAP) {
@@ -943,7 +998,8 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
                 }
             }
         }
-        for (int g = 128; g < n && !mine; ++g) {  // more than 128 GTs: test the rest in place
+        for (int q = 128; q < nnear && !mine; ++q) {  // more than 128 GTs near the tile: test the rest in place
+            const int g = s_near[q];
             const float4 h = s_rec4[g * (GT_REC / 4)];
             const float dx = h.x - xc, dy = h.y - yc;
             if (no_prune || fmaf(dx, dx, dy * dy) <= h.w) {
@@ -985,20 +1041,19 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     // the GT's top 10): bounds into the GTs' lists, again through a work list ------------------------------------------
     TMARK0(1, b * p.tiles + tile, 2);
     TMARK0(1, b * p.tiles + tile, 8);
-    if (cand && !no_filter) {
+    if (cand && !no_filter && !tiny) {
         unsigned fm[4] = {0u, 0u, 0u, 0u};
         int cnt = 0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            const int ge = min(32, n - w * 32);
+            const int ge = min(32, nfarl - w * 32);
             unsigned m = 0u;
             for (int j = 0; j < ge; ++j) {
-                const int g = w * 32 + j;
+                const int g = s_farl[w * 32 + j];
                 const float4 h = s_rec4[g * (GT_REC / 4)];
                 const float px = h.x - pcx, py = h.y - pcy;
                 m |= (!(fmaf(px, px, py * py) < s_rec[g * GT_REC + GT_FAR2]) ? 1u : 0u) << j;
             }
-            if (tiny) m = ge >= 32 ? 0xFFFFFFFFu : ((ge > 0 ? (1u << ge) : 1u) - 1u);
             fm[w] = m;
             cnt += __popc(m);
         }
@@ -1007,18 +1062,22 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
         for (int w = 0; w < 4; ++w) {
             unsigned m = fm[w];
             while (m) {
-                const int g = w * 32 + __ffs(m) - 1;
+                const int g = s_farl[w * 32 + __ffs(m) - 1];
                 m &= m - 1;
                 if (at < ITEM_CAP) S.items[at] = (unsigned)tid | ((unsigned)g << 8);
                 else far_pair(p, s_rec, S, b, tile, g, tid);
                 ++at;
             }
         }
-        for (int g = 128; g < n; ++g) {  // more than 128 GTs: the rest in place
+        for (int q = 128; q < nfarl; ++q) {  // more than 128 far GTs: the rest in place
+            const int g = s_farl[q];
             const float* rec = s_rec + g * GT_REC;
             const float px = rec[GT_CX] - pcx, py = rec[GT_CY] - pcy;
-            if (tiny || !(fmaf(px, px, py * py) < rec[GT_FAR2])) far_pair(p, s_rec, S, b, tile, g, tid);
+            if (!(fmaf(px, px, py * py) < rec[GT_FAR2])) far_pair(p, s_rec, S, b, tile, g, tid);
         }
+    } else if (cand && !no_filter) {
+        // a tiny (or NaN) predicted radius: every pair of the anchor goes to the lists without a bound
+        for (int g = 0; g < n; ++g) far_pair(p, s_rec, S, b, tile, g, tid);
     }
     // ---- per-anchor outputs, candidate bitmap and count, the all-anchor objectness term -------------------------
     const unsigned bal = __ballot_sync(0xffffffffu, cand);
@@ -2023,7 +2082,7 @@ __global__ void k_finalize(const float* __restrict__ sums28, float* __restrict__
     finalize_warp(sums28, state26, result54, weights_n27);
 }
 
-size_t pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float); }
+size_t pass_smem(int Lmax) { return (size_t)Lmax * GT_REC * sizeof(float) + (size_t)2 * Lmax * sizeof(int); }
 size_t tail_smem(int Lmax, int nc) {
     const size_t cap = ((size_t)Lmax * P24_TOPK + TAIL_CL - 1) / TAIL_CL;
     size_t b = (size_t)Lmax * GT_REC * sizeof(float);                 // recs

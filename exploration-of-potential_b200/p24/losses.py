@@ -218,21 +218,26 @@ class Loss_Function(nn.Module):
                 raise _lib.P24Error(f"p24 kernels reported error bits {st[0]:#x} on workspace {key} "
                                     "(1: window list overflow, 4: peer time-out in the fused all-reduce)")
 
-    def exchange_wait_us(self):
-        """[microseconds] the last fused all-reduce of this rank waited for its peers (0 on one GPU): rank skew shows
-        up here, link latency does not.  clock64 cycles at the nominal 1965 MHz."""
-        w = [st[4] for _, st in self._engine.read_status()]
-        return [max(w) / 1965.0 if w else 0.0]
-
-    def path_stats(self):
-        """Counts of the rare paths since the previous read: GTs whose dynamic k needed the brute-force evaluation, GTs
-        that spilled into the penalised regime, the longest and the mean top-10 candidate list."""
-        st = [s for _, s in self._engine.read_status()]
+    def read_status(self):
+        """One read of the kernels' status words (they restart with every read): the rare-path counters since the
+        previous read -- GTs whose dynamic k needed exact pair values / the brute-force evaluation, GTs that spilled into
+        the penalised regime, the longest and the mean top-10 candidate list -- and the microseconds the last fused
+        all-reduce of this rank waited for its peers (rank skew shows up there, link latency does not; clock64 cycles at
+        the nominal 1965 MHz).  Raises ``P24Error`` on error bits."""
+        st = self._engine.read_status()
+        for key, s in st:
+            if s[0]:
+                raise _lib.P24Error(f"p24 kernels reported error bits {s[0]:#x} on workspace {key} "
+                                    "(1: window list overflow, 4: peer time-out in the fused all-reduce)")
+        st = [s for _, s in st]
         gts = sum(s[6] for s in st)
         return {"brute_force_gts": sum(s[1] for s in st), "exact_gts": sum(s[7] for s in st),
                 "spill_gts": sum(s[2] for s in st), "gts": gts,
                 "list_max": max([s[3] for s in st] + [0]), "list_mean": (sum(s[5] for s in st) / gts) if gts else 0.0,
-                "list_capacity": 4096}
+                "list_capacity": 4096, "exchange_wait_us": max([s[4] for s in st] + [0]) / 1965.0}
+
+    def path_stats(self):
+        return self.read_status()
 
     def forward(self, outputs_train, labels):
         outputs = outputs_train[3]
