@@ -898,7 +898,18 @@ __device__ __forceinline__ void anchor_part(const Params& p, float* s_rec, Ancho
     // loops below only visit those ------------------------------------------------------------------------------------
     int* s_near = reinterpret_cast<int*>(s_rec + (size_t)p.Lmax * GT_REC);
     int* s_farl = s_near + p.Lmax;
-    {
+    if (n <= 32) {
+        // few GTs: the boxes would cost more than they save
+        if (tid < n) {
+            s_near[tid] = tid;
+            s_farl[tid] = tid;
+        }
+        if (tid == 0) {
+            S.nnear = n;
+            S.nfarl = n;
+        }
+        __syncthreads();
+    } else {
         const float big = 3.0e38f;
         float ax0 = active ? xc : big, ax1 = active ? xc : -big, ay0 = active ? yc : big, ay1 = active ? yc : -big;
         const bool pok = active && pcx == pcx && pcy == pcy;
