@@ -5,6 +5,8 @@
 //
 // The forward arithmetic follows the reference's operation order (compile with -fmad=false, see p24_math.cuh); the
 // backward kernels use fused multiply-adds freely (gradients are compared at 1e-5 relative).
+#include <string.h>
+
 #include "p24_common.cuh"
 
 namespace {
@@ -186,6 +188,87 @@ __global__ void k_loss_bwd(const float* __restrict__ outputs, long long img_stri
 }
 
 // -------------------------------------------------------------------------------------------
+// the same backward w.r.t. the head's RAW per-level conv outputs (the decode of yolo_head_24p.py:233-235 folded in:
+// d/d(raw centre) = stride * d/d(centre), d/d(raw radius) = radius * d/d(radius); obj / cls logits pass through).
+// One CTA per 256 consecutive anchors of one image: a thread per anchor writes the planar obj / cls / zero gradients
+// (coalesced across anchors), then the warps share the CTA's foreground anchors for the geometry part.
+// -------------------------------------------------------------------------------------------
+struct RawBwd {
+    const float* in[12];   // [reg | obj | cls][level]
+    long long in_bs[12];
+    float* out[12];        // dense [B, C, H, W] per tensor
+    int off[5], W[4];
+    float st[4];
+    int nlev;
+};
+
+__global__ void __launch_bounds__(256) k_loss_bwd_raw(RawBwd r, int B, int A, int nc, const float* __restrict__ labels,
+                                                      long long lab_img_stride, long long lab_row_stride,
+                                                      const uint8_t* __restrict__ fg_mask,
+                                                      const int32_t* __restrict__ matched_gt,
+                                                      const float* __restrict__ pred_iou, const float* __restrict__ wn27,
+                                                      const float* __restrict__ grad_scale) {
+    __shared__ int s_fg[256];
+    __shared__ int s_nfg;
+    __shared__ float s_q[8][26];
+    const int b = blockIdx.y, a = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_nfg = 0;
+    __syncthreads();
+    const float scale = (grad_scale ? grad_scale[0] : 1.0f) / wn27[26];
+    if (a < A) {
+        int l = 0;
+        for (int q = 1; q < r.nlev; ++q) l += a >= r.off[q] ? 1 : 0;
+        const int i = a - r.off[l];
+        const long long plane = (long long)(r.off[l + 1] - r.off[l]);
+        const bool fg = fg_mask[(long long)b * A + a] != 0;
+        const float xo = r.in[4 + l][b * r.in_bs[4 + l] + i];
+        r.out[4 + l][b * plane + i] = scale * wn27[24] * (p24_sigmoid(xo) - (fg ? 1.0f : 0.0f));
+        float* gc = r.out[8 + l] + (long long)b * nc * plane + i;
+        float* gr = r.out[l] + (long long)b * 26 * plane + i;
+        if (!fg) {
+            for (int j = 0; j < nc; ++j) gc[j * plane] = 0.0f;
+            for (int j = 0; j < 26; ++j) gr[j * plane] = 0.0f;
+        } else {
+            const int m = matched_gt[(long long)b * A + a];
+            int cls = (int)labels[b * lab_img_stride + m * lab_row_stride];
+            cls = min(max(cls, 0), nc - 1);
+            const float v = pred_iou[(long long)b * A + a];
+            const float* xc = r.in[8 + l] + b * r.in_bs[8 + l] + i;
+            for (int j = 0; j < nc; ++j) gc[j * plane] = scale * wn27[25] * (p24_sigmoid(xc[j * plane]) - (j == cls ? v : 0.0f));
+            s_fg[atomicAdd(&s_nfg, 1)] = a;
+        }
+    }
+    __syncthreads();
+    for (int f = warp; f < s_nfg; f += 8) {
+        const int aa = s_fg[f];
+        int l = 0;
+        for (int q = 1; q < r.nlev; ++q) l += aa >= r.off[q] ? 1 : 0;
+        const int i = aa - r.off[l];
+        const long long plane = (long long)(r.off[l + 1] - r.off[l]);
+        const float st = r.st[l];
+        float dec = 0.0f;
+        if (lane < 26) {
+            const float x = r.in[l][b * r.in_bs[l] + lane * plane + i];
+            if (lane >= 2) dec = expf(x) * st;
+            else dec = (x + (float)(lane == 0 ? i % r.W[l] : i / r.W[l])) * st;
+            s_q[warp][lane] = dec;
+        }
+        __syncwarp();
+        const int m = matched_gt[(long long)b * A + aa];
+        const float* lab = labels + b * lab_img_stride + m * lab_row_stride;
+        float gx, gy;
+        const float grp = pair_grad(lab + 1, s_q[warp], lane < P24_RAYS ? scale * wn27[lane] : 0.0f, lane, gx, gy);
+        float* gr = r.out[l] + (long long)b * 26 * plane + i;
+        if (lane < P24_RAYS) gr[(2 + lane) * plane] = grp * s_q[warp][2 + lane];
+        if (lane == 0) {
+            gr[0] = gx * st;
+            gr[plane] = gy * st;
+        }
+        __syncwarp();
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // dynamic_k_matching on materialised [G, P] matrices (losses.py:444-494)
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(P24_THREADS) k_dynk_select(const float* __restrict__ cost, const float* __restrict__ ious,
@@ -335,6 +418,40 @@ extern "C" int p24_loss_bwd(const float* outputs, int64_t img_stride, int64_t ro
                                                                           labels, lab_img_stride, lab_row_stride, fg_mask,
                                                                           matched_gt, pred_iou, weights_n27, grad_scale,
                                                                           grad_outputs);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int p24_loss_bwd_raw(const float* const* h_raw, const int64_t* h_raw_batch_stride, float* const* h_grad_raw,
+                                const int32_t* h_levels, int n_levels, int B, int A, int num_classes, const float* labels,
+                                int64_t lab_img_stride, int64_t lab_row_stride, const uint8_t* fg_mask,
+                                const int32_t* matched_gt, const float* pred_iou, const float* weights_n27,
+                                const float* grad_scale, void* stream) {
+    if (!h_raw || !h_raw_batch_stride || !h_grad_raw || !h_levels || !labels || !fg_mask || !matched_gt || !pred_iou ||
+        !weights_n27)
+        return P24_E_BADARG;
+    if (B <= 0 || A <= 0 || num_classes <= 0 || n_levels < 1 || n_levels > 4 || B > 65535) return P24_E_BADARG;
+    RawBwd r;
+    memset(&r, 0, sizeof(r));
+    r.nlev = n_levels;
+    int total = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        const int off = h_levels[4 * l], W = h_levels[4 * l + 1], H = h_levels[4 * l + 2];
+        if (off != total || W <= 0 || H <= 0) return P24_E_BADARG;
+        r.off[l] = off;
+        r.W[l] = W;
+        memcpy(&r.st[l], &h_levels[4 * l + 3], 4);
+        total += W * H;
+        for (int t = 0; t < 3; ++t) {
+            r.in[4 * t + l] = h_raw[t * n_levels + l];
+            r.in_bs[4 * t + l] = h_raw_batch_stride[t * n_levels + l];
+            r.out[4 * t + l] = h_grad_raw[t * n_levels + l];
+            if (!r.in[4 * t + l] || !r.out[4 * t + l]) return P24_E_BADARG;
+        }
+    }
+    if (total != A) return P24_E_BADARG;
+    r.off[n_levels] = A;
+    k_loss_bwd_raw<<<dim3((unsigned)((A + 255) / 256), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        r, B, A, num_classes, labels, lab_img_stride, lab_row_stride, fg_mask, matched_gt, pred_iou, weights_n27, grad_scale);
     return (int)cudaGetLastError();
 }
 

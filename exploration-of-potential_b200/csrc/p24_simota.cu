@@ -41,8 +41,10 @@ struct Level {
 };
 
 struct Params {
-    const float* outputs;
+    const float* outputs;            // decoded head output [B, A, 27 + nc] (rows), or NULL:
     long long img_stride, row_stride;
+    const float* raw[3][P24_MAX_LEVELS];   // raw conv outputs per level (reg [B,26,H,W], obj [B,1,H,W], cls [B,nc,H,W]) ...
+    long long raw_bs[3][P24_MAX_LEVELS];   // ... and their batch strides; decoded on load (yolo_head_24p.py:212-237)
     int B, A, nc;
     const float* labels;
     long long lab_img_stride, lab_row_stride;
@@ -343,6 +345,83 @@ __device__ __forceinline__ float cls_cost_from(float neg_sum, float cls_logit_c,
 }
 
 // -------------------------------------------------------------------------------------------
+// Access to one anchor's channels of the head output.  Two layouts:
+//   rows    the decoded buffer [B, A, 27 + nc] that YOLOXHead.forward(train=True) returns (yolo_head_24p.py:197);
+//   raw     the head's raw per-level conv outputs reg [B,26,H,W], obj [B,1,H,W], cls [B,nc,H,W] (yolo_head_24p.py:160-164),
+//           decoded on load exactly as get_output_and_grid does (yolo_head_24p.py:233-235): centre (v + grid) * stride,
+//           radii exp(v) * stride; the cat / view / permute / reshape copies of the reference never happen.
+// -------------------------------------------------------------------------------------------
+struct Src {
+    const float* reg;   // channel c of the anchor at reg[c * plane]
+    const float* obj;
+    const float* cls;   // class j at cls[j * plane]
+    long long plane;    // 1 (rows) or W * H of the level (raw)
+    float gx, gy, st;   // grid cell and stride (raw)
+    bool raw;
+};
+
+__device__ __forceinline__ Src src_of(const Params& p, int b, int a) {
+    Src s;
+    if (p.outputs) {
+        const float* row = p.outputs + (long long)b * p.img_stride + (long long)a * p.row_stride;
+        s.reg = row;
+        s.obj = row + 26;
+        s.cls = row + 27;
+        s.plane = 1;
+        s.gx = s.gy = 0.0f;
+        s.st = 1.0f;
+        s.raw = false;
+        return s;
+    }
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < P24_MAX_LEVELS; ++q) l += (q < p.nlev && a >= p.lev[q].off) ? 1 : 0;
+    const int r = a - p.lev[l].off;
+    const int iy = r / p.lev[l].W, ix = r - iy * p.lev[l].W;
+    s.plane = (long long)p.lev[l].W * p.lev[l].H;
+    s.reg = p.raw[0][l] + (long long)b * p.raw_bs[0][l] + r;
+    s.obj = p.raw[1][l] + (long long)b * p.raw_bs[1][l] + r;
+    s.cls = p.raw[2][l] + (long long)b * p.raw_bs[2][l] + r;
+    s.gx = (float)ix;
+    s.gy = (float)iy;
+    s.st = p.lev[l].st;
+    s.raw = true;
+    return s;
+}
+// decoded geometry channel c in [0, 26): centre x, centre y, 24 radii
+__device__ __forceinline__ float src_geo(const Src& s, int c) {
+    const float v = s.reg[(long long)c * s.plane];
+    if (!s.raw) return v;
+    if (c >= 2) return expf(v) * s.st;             // output[..., 2:26] = exp(output[..., 2:26]) * stride
+    return (v + (c == 0 ? s.gx : s.gy)) * s.st;    // output[..., :2] = (output[..., :2] + grid) * stride
+}
+__device__ __forceinline__ float src_obj(const Src& s) { return s.obj[0]; }
+__device__ __forceinline__ float src_cls(const Src& s, int j) { return s.cls[(long long)j * s.plane]; }
+
+// exact pair value of (GT record, anchor of the head output): utils/boxes.py:166-243, one thread
+__device__ __noinline__ float pair_value_src(const float* __restrict__ rec, const Src& s) {
+    const float d = p24_centre_dist(rec[GT_CX], rec[GT_CY], src_geo(s, 0), src_geo(s, 1));
+    float sm = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < P24_RAYS; ++k) sm = sm + ray_loss(rec[GT_RG + k], src_geo(s, 2 + k), d);
+    return (sm / 24.0f) / 2.0f;
+}
+// sum over all classes of BCE(p_j, 0) (losses.py:406-416), term by term, by a single thread / an 8-lane group (rare paths)
+__device__ __noinline__ float thread_cls_neg_sum_src(const Src& s, int nc, float eo1) {
+    const float obj_sig = 1.0f / eo1;
+    float t = 0.0f;
+    for (int j = 0; j < nc; ++j) t += p24_bce_neg(p24_joint_prob(src_cls(s, j), obj_sig));
+    return t;
+}
+__device__ __noinline__ float group_cls_neg_sum_src(const Src& s, int nc, float eo1, unsigned m) {
+    const int sub = threadIdx.x & 7;
+    const float obj_sig = 1.0f / eo1;
+    float t = 0.0f;
+    for (int j = sub; j < nc; j += 8) t += p24_bce_neg(p24_joint_prob(src_cls(s, j), obj_sig));
+    return group_sum(t, m);
+}
+
+// -------------------------------------------------------------------------------------------
 // Upper bound of the pair value as a function of the centre distance d alone.  Any ray has
 // loss <= max(1, 2 - 4 (rg^2 + rp^2) / (rg + rp + d)^2) (nested rays: loss <= 1; partial and apart rays:
 // loss <= 2 - uni/cs with the apart formula; tests/test_bounds_cpu.py).  Over all rp > 0 the fraction is smallest at
@@ -391,11 +470,11 @@ __device__ __forceinline__ KV seed_point(const Params& p, const float* __restric
     if (!(valid && ix >= 0 && ix < lv.W && iy >= 0 && iy < lv.H)) return out;
     const int a = lv.off + iy * lv.W + ix;
     // the anchor's row is requested right away: it is in flight while the candidate tests run
-    const float* row = p.outputs + (long long)b * p.img_stride + (long long)a * p.row_stride;
+    const Src src = src_of(p, b, a);
     float rpv[P24_RAYS];
 #pragma unroll
-    for (int k = 0; k < P24_RAYS; ++k) rpv[k] = row[2 + k];
-    const float pcx = row[0], pcy = row[1];
+    for (int k = 0; k < P24_RAYS; ++k) rpv[k] = src_geo(src, 2 + k);
+    const float pcx = src_geo(src, 0), pcy = src_geo(src, 1);
     // (the grid is the head's, validated by the host side: x_shift = column, y_shift = row, one stride per level)
     const float xc = p24_anchor_centre((float)ix, st), yc = p24_anchor_centre((float)iy, st);
     const float hcx = h[GT_CX], hcy = h[GT_CY];
@@ -721,15 +800,30 @@ struct AnchorShared {
     int nitems, nnear, nfarl;
 };
 
-// the tile's rows: each warp reads its 32 rows, 27 contiguous floats per row, straight into shared memory
+// the tile's rows into shared memory.  Row layout: each warp reads its 32 rows, 27 contiguous floats per row, with cp.async.
+// Raw layout: every lane reads the 27 channels of its own anchor -- 32 consecutive anchors of a level are 32 consecutive
+// floats of every channel plane: fully coalesced -- and decodes them on the way.
 __device__ __forceinline__ void stage_rows(const Params& p, AnchorShared& S, int b, int tile) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* img = p.outputs + (long long)b * p.img_stride;
     const int a0 = tile * P24_THREADS + warp * 32;
-    const int nrow = min(32, p.A - a0);
-    if (lane < ROW_CH) {
-        const float* src = img + (long long)a0 * p.row_stride + lane;
-        for (int r = 0; r < nrow; ++r) cp_async4(&S.row[warp][lane][r], src + (long long)r * p.row_stride);
+    if (p.outputs) {
+        const float* img = p.outputs + (long long)b * p.img_stride;
+        const int nrow = min(32, p.A - a0);
+        if (lane < ROW_CH) {
+            const float* src = img + (long long)a0 * p.row_stride + lane;
+            for (int r = 0; r < nrow; ++r) cp_async4(&S.row[warp][lane][r], src + (long long)r * p.row_stride);
+        }
+    } else if (a0 + lane < p.A) {
+        const Src s = src_of(p, b, a0 + lane);
+        float v[ROW_CH];
+#pragma unroll
+        for (int c = 0; c < 26; ++c) v[c] = s.reg[(long long)c * s.plane];   // all in flight together
+        v[26] = src_obj(s);
+        S.row[warp][0][lane] = (v[0] + s.gx) * s.st;
+        S.row[warp][1][lane] = (v[1] + s.gy) * s.st;
+#pragma unroll
+        for (int c = 2; c < 26; ++c) S.row[warp][c][lane] = expf(v[c]) * s.st;
+        S.row[warp][26][lane] = v[26];
     }
 }
 
@@ -772,20 +866,19 @@ __device__ __forceinline__ void window_pair(const Params& p, int slot, int aa, u
     const int sub = threadIdx.x & 7;
     const int b = slot / p.Lmax;
     const float* rec = p.gt_rec + (long long)slot * GT_REC;
-    const float* row = p.outputs + (long long)b * p.img_stride + (long long)aa * p.row_stride;
-    const float* cls = row + 27;
+    const Src src = src_of(p, b, aa);
     // everything the pair needs is requested up front
     const float gcx = rec[GT_CX], gcy = rec[GT_CY], rin2 = rec[GT_RIN2];
     const int c = gt_class(rec, p.nc);
     float cl[10], rp[3], rg[3];
 #pragma unroll
-    for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? cls[sub + 8 * q] : 0.0f;
+    for (int q = 0; q < 10; ++q) cl[q] = (sub + 8 * q < p.nc) ? src_cls(src, sub + 8 * q) : 0.0f;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-        rp[q] = row[2 + sub * 3 + q];
+        rp[q] = src_geo(src, 2 + sub * 3 + q);
         rg[q] = rec[GT_RG + sub * 3 + q];
     }
-    const float pcx = row[0], pcy = row[1], obj = row[26], clsc = cls[c];
+    const float pcx = src_geo(src, 0), pcy = src_geo(src, 1), obj = src_obj(src), clsc = src_cls(src, c);
     int l = 0;
 #pragma unroll
     for (int q = 1; q < P24_MAX_LEVELS; ++q) l += (q < p.nlev && aa >= p.lev[q].off) ? 1 : 0;
@@ -827,13 +920,13 @@ __device__ __forceinline__ void window_pair(const Params& p, int slot, int aa, u
             if (sub + 8 * q < p.nc) p24_neg_factor(cl[q], eo1, prod, nsat);
         prod = group_prod(prod, gm);
         nsat = group_sum_i(nsat, gm);
-        neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum(cls, p.nc, eo1, gm);
+        neg = (prod > 1e-30f) ? (-logf(prod) + 100.0f * (float)nsat) : group_cls_neg_sum_src(src, p.nc, eo1, gm);
     } else {
         // many classes: the log of a per-lane product, restarted before it can underflow
         float prod = 1.0f, lsum = 0.0f;
         int nsat = 0;
         for (int j = sub; j < p.nc; j += 8) {
-            p24_neg_factor(cls[j], eo1, prod, nsat);
+            p24_neg_factor(src_cls(src, j), eo1, prod, nsat);
             if (prod < 1e-20f) {
                 lsum += logf(prod);
                 prod = 1.0f;
@@ -843,7 +936,7 @@ __device__ __forceinline__ void window_pair(const Params& p, int slot, int aa, u
         lsum = group_sum(lsum, gm);
         nsat = group_sum_i(nsat, gm);
         neg = -lsum + 100.0f * (float)nsat;
-        if (!(neg == neg) || neg == P24_POS_INF) neg = group_cls_neg_sum(cls, p.nc, eo1, gm);
+        if (!(neg == neg) || neg == P24_POS_INF) neg = group_cls_neg_sum_src(src, p.nc, eo1, gm);
     }
     float cost = p24_cost(cls_cost_from(neg, clsc, 1.0f / eo1), v, true);
     if (!(cost < 3.0e38f)) cost = 3.0e38f;  // NaN / inf inputs: keep the pair selectable, last
@@ -1306,7 +1399,6 @@ __device__ __forceinline__ float warp_pop_max(float (&t)[P24_TOPK]) {
 __device__ __noinline__ void brute_partial(const Params& p, TailShared& S, const float* __restrict__ rec, int b, int kc, int cr,
                                            float* __restrict__ out) {
     const int tid = threadIdx.x;
-    const float* img = p.outputs + (long long)b * p.img_stride;
     const unsigned* bits = p.cbits + (long long)b * p.tiles * P24_WARPS;
     const int per = (p.A + TAIL_CL - 1) / TAIL_CL;
     float t[P24_TOPK];
@@ -1314,7 +1406,7 @@ __device__ __noinline__ void brute_partial(const Params& p, TailShared& S, const
     for (int q = 0; q < P24_TOPK; ++q) t[q] = P24_NEG_INF;
     for (int a = cr * per + tid; a < min(p.A, (cr + 1) * per); a += TAIL_THREADS) {
         if (!((__ldcg(bits + (a >> 5)) >> (a & 31)) & 1u)) continue;
-        float v = pair_value_row(rec, img + (long long)a * p.row_stride);
+        float v = pair_value_src(rec, src_of(p, b, a));
         if (!(v == v)) v = P24_POS_INF;  // NaN sorts first (torch.topk)
         top_insert_desc(t, v);
     }
@@ -1361,7 +1453,6 @@ __device__ __noinline__ void spill_claims(const Params& p, TailShared& S, const 
         li[i] = 0x7fffffff;
     }
     const int tid = threadIdx.x;
-    const float* img = p.outputs + (long long)b * p.img_stride;
     const unsigned* bits = p.cbits + (long long)b * p.tiles * P24_WARPS;
     const float* tab = p.wtab + ((long long)b * p.Lmax + g) * P24_WT_STRIDE;
     const int c = gt_class(rec, p.nc);
@@ -1378,11 +1469,11 @@ __device__ __noinline__ void spill_claims(const Params& p, TailShared& S, const 
         if (sx >= 0 && sx < P24_WSIDE && sy >= 0 && sy < P24_WSIDE &&
             __ldcg(tab + l * P24_WSLOTS + sy * P24_WSIDE + sx) < P24_POS_INF)
             continue;
-        const float* row = img + (long long)a * p.row_stride;
-        const float eo1 = 1.0f + expf(-row[26]);
-        const float neg = thread_cls_neg_sum(row + 27, p.nc, eo1);
-        const float v = pair_value_row(rec, row);
-        const float cost = p24_cost(cls_cost_from(neg, row[27 + c], 1.0f / eo1), v, false);
+        const Src src = src_of(p, b, a);
+        const float eo1 = 1.0f + expf(-src_obj(src));
+        const float neg = thread_cls_neg_sum_src(src, p.nc, eo1);
+        const float v = pair_value_src(rec, src);
+        const float cost = p24_cost(cls_cost_from(neg, src_cls(src, c), 1.0f / eo1), v, false);
         if (kv_lt(cost, a, lv[P24_TOPK - 1], li[P24_TOPK - 1])) {
             float cv = cost;
             int ci = a;
@@ -1491,7 +1582,6 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
                                                     int lc, int kc, bool& ok) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float2* lst = p.list + (long long)slot * P24_LISTCAP;
-    const float* img = p.outputs + (long long)b * p.img_stride;
     ok = true;
     float lmax = P24_NEG_INF;
     float2 e0[8];  // the first 256 entries stay in registers (most lists end there: one round trip for the whole list)
@@ -1564,11 +1654,11 @@ __device__ __forceinline__ float warp_topk_sum_list(const Params& p, TailShared&
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = j0 + 4 * u + grp;
-                const float* row = img + (long long)S.surv[warp][min(j, cnt - 1)] * p.row_stride;
-                pc[u][0] = row[0];
-                pc[u][1] = row[1];
+                const Src src = src_of(p, b, S.surv[warp][min(j, cnt - 1)]);
+                pc[u][0] = src_geo(src, 0);
+                pc[u][1] = src_geo(src, 1);
 #pragma unroll
-                for (int q = 0; q < 3; ++q) rp[u][q] = row[2 + sub * 3 + q];
+                for (int q = 0; q < 3; ++q) rp[u][q] = src_geo(src, 2 + sub * 3 + q);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -1701,7 +1791,6 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
     int* uniq = claim + p.Lmax * P24_TOPK;
     unsigned long long* best = reinterpret_cast<unsigned long long*>(uniq + ((cap + 1) & ~1));
     float* rows = reinterpret_cast<float*>(best + cap);
-    const float* img = p.outputs + (long long)b * p.img_stride;
     const bool no_filter = (p.flags & P24_F_NO_FILTER) != 0;
     int* claimg = p.claimg + (long long)b * p.Lmax * P24_TOPK;
     int* kreq = p.kreq + b * p.Lmax;    // per GT: >= 0 clamped dynamic k a rare path must still honour, -1 none, -2 brute force
@@ -1874,12 +1963,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
     const bool stage = C <= ROW_PAD;
     if (stage) {
         for (int e = warp; e < nuniq; e += TAIL_WARPS) {
-            const float* src = img + (long long)claim[uniq[e] & 0x3FFFFFFF] * p.row_stride;
+            const Src src = src_of(p, b, claim[uniq[e] & 0x3FFFFFFF]);
             float* dst = rows + e * ROW_PAD;
 #pragma unroll
             for (int q = 0; q < (ROW_PAD + 31) / 32; ++q) {
                 const int c = lane + 32 * q;
-                if (c < C) dst[c] = src[c];
+                if (c < C) dst[c] = c < 26 ? src_geo(src, c) : (c == 26 ? src_obj(src) : src_cls(src, c - 27));
             }
         }
     }
@@ -1898,7 +1987,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ P
             const int t = u & 0x3FFFFFFF;
             const int aa = claim[t];
             int g = t / P24_TOPK;
-            const float* row = stage ? rows + e * ROW_PAD : img + (long long)aa * p.row_stride;
+            const float* row = stage ? rows + e * ROW_PAD : p.outputs + (long long)b * p.img_stride + (long long)aa * p.row_stride;
             if (u & 0x40000000) {
                 const unsigned long long bb = best[e];
                 if (bb != ~0ull) {
@@ -2173,7 +2262,9 @@ extern "C" int p24_read_status(void* workspace, int B, int A, int Lmax, int32_t*
     return (int)cudaStreamSynchronize((cudaStream_t)stream);
 }
 
-extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A,
+namespace {
+int simota_impl(const float* outputs, int64_t img_stride, int64_t row_stride, const float* const* h_raw,
+                const int64_t* h_raw_bs, int B, int A,
                                      int num_classes, const float* labels, int64_t lab_img_stride,
                                      int64_t lab_row_stride, int Lmax, const float* x_shifts, const float* y_shifts,
                                      const float* strides, const int32_t* h_levels, int n_levels, uint8_t* fg_mask,
@@ -2181,9 +2272,10 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
                                      int32_t* dyn_k, float* sums28, float* state26, float* result54,
                                      float* weights_n27, void* workspace, size_t workspace_bytes, uint32_t flags,
                                      void* const* h_mailboxes, int rank, int nranks, uint32_t epoch, void* stream) {
-    if (!outputs || !labels || !x_shifts || !y_shifts || !strides || !fg_mask || !matched_gt || !pred_iou || !num_fg ||
+    if ((!outputs && !h_raw) || !labels || !x_shifts || !y_shifts || !strides || !fg_mask || !matched_gt || !pred_iou || !num_fg ||
         !num_gt || !dyn_k || !workspace || !h_levels)
         return P24_E_BADARG;
+    if (h_raw && (!h_raw_bs || 27 + num_classes > ROW_PAD)) return h_raw_bs ? P24_E_UNSUPPORTED : P24_E_BADARG;
     if (B <= 0 || A <= 0 || Lmax <= 0 || num_classes <= 0 || Lmax > 65535 || B > 65535) return P24_E_BADARG;
     if (state26 && (!sums28 || !result54 || !weights_n27)) return P24_E_BADARG;
     if (n_levels <= 0) return P24_E_BADARG;
@@ -2195,7 +2287,17 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     if (dyn_pass > 160 * 1024 || dyn_tail > 200 * 1024 || p24_tiles(A) > 65535) return P24_E_UNSUPPORTED;
     char* ws = (char*)workspace;
     Params p;
-    p.outputs = outputs; p.img_stride = img_stride; p.row_stride = row_stride;
+    p.outputs = h_raw ? nullptr : outputs; p.img_stride = img_stride; p.row_stride = row_stride;
+    for (int t = 0; t < 3; ++t)
+        for (int l = 0; l < P24_MAX_LEVELS; ++l) {
+            p.raw[t][l] = nullptr;
+            p.raw_bs[t][l] = 0;
+            if (h_raw && l < n_levels && n_levels <= P24_MAX_LEVELS) {
+                if (!h_raw[t * n_levels + l]) return P24_E_BADARG;
+                p.raw[t][l] = h_raw[t * n_levels + l];
+                p.raw_bs[t][l] = h_raw_bs[t * n_levels + l];
+            }
+        }
     p.B = B; p.A = A; p.nc = num_classes;
     p.labels = labels; p.lab_img_stride = lab_img_stride; p.lab_row_stride = lab_row_stride; p.Lmax = Lmax;
     p.x_shifts = x_shifts; p.y_shifts = y_shifts; p.strides = strides;
@@ -2289,6 +2391,37 @@ extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, i
     if (e != cudaSuccess) return (int)e;
     p24::prof_mark(3, st);
     return (int)cudaGetLastError();
+}
+}  // namespace
+
+extern "C" int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_stride, int B, int A,
+                                     int num_classes, const float* labels, int64_t lab_img_stride,
+                                     int64_t lab_row_stride, int Lmax, const float* x_shifts, const float* y_shifts,
+                                     const float* strides, const int32_t* h_levels, int n_levels, uint8_t* fg_mask,
+                                     int32_t* matched_gt, float* pred_iou, int32_t* num_fg, int32_t* num_gt,
+                                     int32_t* dyn_k, float* sums28, float* state26, float* result54,
+                                     float* weights_n27, void* workspace, size_t workspace_bytes, uint32_t flags,
+                                     void* const* h_mailboxes, int rank, int nranks, uint32_t epoch, void* stream) {
+    if (!outputs) return P24_E_BADARG;
+    return simota_impl(outputs, img_stride, row_stride, nullptr, nullptr, B, A, num_classes, labels, lab_img_stride,
+                       lab_row_stride, Lmax, x_shifts, y_shifts, strides, h_levels, n_levels, fg_mask, matched_gt, pred_iou,
+                       num_fg, num_gt, dyn_k, sums28, state26, result54, weights_n27, workspace, workspace_bytes, flags,
+                       h_mailboxes, rank, nranks, epoch, stream);
+}
+
+extern "C" int p24_simota_loss_batch_raw(const float* const* h_raw, const int64_t* h_raw_batch_stride, int B, int A,
+                                         int num_classes, const float* labels, int64_t lab_img_stride,
+                                         int64_t lab_row_stride, int Lmax, const float* x_shifts, const float* y_shifts,
+                                         const float* strides, const int32_t* h_levels, int n_levels, uint8_t* fg_mask,
+                                         int32_t* matched_gt, float* pred_iou, int32_t* num_fg, int32_t* num_gt,
+                                         int32_t* dyn_k, float* sums28, float* state26, float* result54,
+                                         float* weights_n27, void* workspace, size_t workspace_bytes, uint32_t flags,
+                                         void* const* h_mailboxes, int rank, int nranks, uint32_t epoch, void* stream) {
+    if (!h_raw || !h_raw_batch_stride) return P24_E_BADARG;
+    return simota_impl(nullptr, 0, 0, h_raw, h_raw_batch_stride, B, A, num_classes, labels, lab_img_stride, lab_row_stride,
+                       Lmax, x_shifts, y_shifts, strides, h_levels, n_levels, fg_mask, matched_gt, pred_iou, num_fg, num_gt,
+                       dyn_k, sums28, state26, result54, weights_n27, workspace, workspace_bytes, flags, h_mailboxes, rank,
+                       nranks, epoch, stream);
 }
 
 extern "C" size_t p24_comm_mailbox_bytes(void) { return (size_t)(MBOX_FLAGS + 64) * sizeof(float); }

@@ -20,6 +20,55 @@ F_ALL_ROWS = 4   # every label row is a GT (per-image API)
 F_NO_PDL = 8     # plain stream-ordered launches
 
 
+class RawLevels:
+    """The head's raw per-level conv outputs (``yolo_head_24p.py:160-164``), handed to the loss instead of the decoded
+    ``[B, A, 27 + nc]`` buffer: ``reg[k] [B, 26, H, W]``, ``obj[k] [B, 1, H, W]``, ``cls[k] [B, nc, H, W]`` for every
+    level k.  The kernels decode on load (``get_output_and_grid``, ``yolo_head_24p.py:233-235``); the cat / view /
+    permute / reshape copies of ``YOLOXHead.forward(train=True)`` never happen.  Channel slices of one concatenated
+    ``[B, 27 + nc, H, W]`` tensor are fine (only the H x W planes must be dense)."""
+
+    def __init__(self, reg, obj, cls):
+        self.reg, self.obj, self.cls = list(reg), list(obj), list(cls)
+        if not (len(self.reg) == len(self.obj) == len(self.cls)) or not self.reg:
+            raise IndexError("RawLevels needs reg / obj / cls tensors for the same levels")
+        for k, (r, o, c) in enumerate(zip(self.reg, self.obj, self.cls)):
+            if r.dim() != 4 or r.shape[1] != 26 or o.shape[1] != 1 or r.shape[2:] != o.shape[2:] or r.shape[2:] != c.shape[2:] \
+                    or not (r.shape[0] == o.shape[0] == c.shape[0]):
+                raise IndexError(f"level {k}: expected reg [B,26,H,W], obj [B,1,H,W], cls [B,nc,H,W]")
+
+    @property
+    def device(self):
+        return self.reg[0].device
+
+    @property
+    def batch(self):
+        return self.reg[0].shape[0]
+
+    @property
+    def num_classes(self):
+        return self.cls[0].shape[1]
+
+    @property
+    def num_anchors(self):
+        return sum(r.shape[2] * r.shape[3] for r in self.reg)
+
+    def requires_grad(self):
+        return any(t.requires_grad for lst in (self.reg, self.obj, self.cls) for t in lst)
+
+    def planes(self):
+        """(tensor list in ABI order, batch strides): every tensor with dense H x W planes and channel stride H * W."""
+        out, bs = [], []
+        for lst in (self.reg, self.obj, self.cls):
+            for t in lst:
+                _check_cuda_f32(t, "raw level tensor")
+                H, W = t.shape[2], t.shape[3]
+                if t.stride(3) != 1 or t.stride(2) != W or (t.shape[1] > 1 and t.stride(1) != H * W):
+                    t = t.contiguous()
+                out.append(t)
+                bs.append(t.stride(0))
+        return out, bs
+
+
 @dataclass
 class Assignment:
     """Device-resident result of one batch (no host sync has happened)."""
@@ -126,19 +175,26 @@ class SimOTAEngine:
         re-weighting into the last kernel.  ``comm`` (``p24.dist.PeerComm``): the 28 sums are all-reduced over peer
         memory inside the last kernel first (one process per GPU, images sharded by rank)."""
         lib = _lib.load()
-        _check_cuda_f32(outputs, "outputs")
+        raw = isinstance(outputs, RawLevels)
         _check_cuda_f32(labels, "labels")
-        if outputs.dim() != 3 or outputs.shape[2] != 27 + num_classes:
-            raise IndexError("outputs must be [B, A, 27 + num_classes]")
-        if labels.dim() != 3 or labels.shape[2] != 51 or labels.shape[0] != outputs.shape[0]:
+        if raw:
+            if outputs.num_classes != num_classes:
+                raise IndexError("raw cls tensors must have num_classes channels")
+            planes, plane_bs = outputs.planes()
+            B, A, dev = outputs.batch, outputs.num_anchors, outputs.device
+        else:
+            _check_cuda_f32(outputs, "outputs")
+            if outputs.dim() != 3 or outputs.shape[2] != 27 + num_classes:
+                raise IndexError("outputs must be [B, A, 27 + num_classes]")
+            if outputs.stride(2) != 1:
+                outputs = outputs.contiguous()
+            B, A, _ = outputs.shape
+            dev = outputs.device
+        if labels.dim() != 3 or labels.shape[2] != 51 or labels.shape[0] != B:
             raise IndexError("labels must be [B, Lmax, 51]")
-        if outputs.stride(2) != 1:
-            outputs = outputs.contiguous()
         if labels.stride(2) != 1:
             labels = labels.contiguous()
-        B, A, _ = outputs.shape
         Lmax = labels.shape[1]
-        dev = outputs.device
         gx, gy, gs, lv, nlev = self.grids.get(x_shifts, y_shifts, strides, dev)
         if gx.numel() != A:
             raise IndexError("grid length does not match the number of anchors")
@@ -159,12 +215,23 @@ class SimOTAEngine:
         if Lmax == 0:  # no label rows at all: everything is background
             out.fg_mask.zero_(); out.matched_gt.fill_(-1); out.pred_iou.zero_()
             out.num_fg.zero_(); out.num_gt.zero_(); out.dyn_k.zero_()
-            labels = outputs.new_zeros((B, 1, 51))
+            labels = labels.new_zeros((B, 1, 51))
             Lmax = 1
         buf = self._buffers(B, A, Lmax, dev)
         ws_ptr = buf["ptr"]
         fin = [t.data_ptr() for t in finalize] if finalize is not None else [None, None, None]
-        args = (outputs.data_ptr(), outputs.stride(0), outputs.stride(1), B, A, num_classes,
+        if raw:
+            if len(outputs.reg) != nlev:
+                raise IndexError("RawLevels and the grids describe different numbers of levels")
+            for k, r in enumerate(outputs.reg):
+                if (r.shape[3], r.shape[2]) != (lv[4 * k + 1], lv[4 * k + 2]):
+                    raise IndexError(f"level {k}: the raw tensors are {r.shape[2]}x{r.shape[3]}, the grid is not")
+            head = ((C.c_void_p * len(planes))(*[t.data_ptr() for t in planes]), (C.c_int64 * len(planes))(*plane_bs))
+            entry, what = lib.p24_simota_loss_batch_raw, "p24_simota_loss_batch_raw"
+        else:
+            head = (outputs.data_ptr(), outputs.stride(0), outputs.stride(1))
+            entry, what = lib.p24_simota_loss_batch, "p24_simota_loss_batch"
+        args = head + (B, A, num_classes,
                 labels.data_ptr(), labels.stride(0), labels.stride(1), Lmax,
                 gx.data_ptr(), gy.data_ptr(), gs.data_ptr(), lv, nlev,
                 out.fg_mask.data_ptr(), out.matched_gt.data_ptr(), out.pred_iou.data_ptr(),
@@ -176,11 +243,11 @@ class SimOTAEngine:
                 comm.nranks if comm is not None else 1, comm.next_epoch() if comm is not None else 0,
                 _stream_ptr(dev))
         if torch.cuda.current_device() == dev.index:
-            code = lib.p24_simota_loss_batch(*args)
+            code = entry(*args)
         else:  # the launches go to the tensors' device
             with torch.cuda.device(dev):
-                code = lib.p24_simota_loss_batch(*args)
-        _lib.check(code, "p24_simota_loss_batch")
+                code = entry(*args)
+        _lib.check(code, what)
         if comm is not None:
             # the collect half of the fused all-reduce, on the comm's side stream (sums28 / the finalize buffers are valid
             # once comm.wait() has ordered the consumer's stream behind it)

@@ -29,6 +29,14 @@ _PROTOS = {
                                         c_ptr, c_ptr, c_ptr,
                                         c_ptr, C.c_size_t, C.c_uint32,
                                         C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint32, c_ptr]),
+    "p24_simota_loss_batch_raw": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int,
+                                            c_ptr, C.c_int64, C.c_int64, C.c_int,
+                                            c_ptr, c_ptr, c_ptr,
+                                            C.POINTER(C.c_int32), C.c_int,
+                                            c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                            c_ptr, c_ptr, c_ptr,
+                                            c_ptr, C.c_size_t, C.c_uint32,
+                                            C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint32, c_ptr]),
     "p24_comm_mailbox_bytes": (C.c_size_t, []),
     "p24_comm_alloc": (C.c_int, [C.POINTER(C.c_void_p)]),
     "p24_comm_free": (C.c_int, [c_ptr]),
@@ -46,6 +54,9 @@ _PROTOS = {
     "p24_pair_iou": (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr]),
     "p24_loss_bwd": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "p24_loss_bwd_raw": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                   C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr,
+                                   c_ptr, c_ptr, c_ptr]),
     "p24_dynamic_k_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "p24_dynamic_k_matching": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                          c_ptr, C.c_size_t, c_ptr]),

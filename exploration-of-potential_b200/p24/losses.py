@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import lib as _lib
-from .engine import Assignment, SimOTAEngine, F_ALL_ROWS, _check_cuda_f32, _stream_ptr
+from .engine import Assignment, RawLevels, SimOTAEngine, F_ALL_ROWS, _check_cuda_f32, _stream_ptr
 
 
 def _rows(t: torch.Tensor, width: int, name: str) -> torch.Tensor:
@@ -123,6 +123,43 @@ class _LossFn(torch.autograd.Function):
         return gout, None, None, None, None, None
 
 
+class _RawLossFn(torch.autograd.Function):
+    """The same for the head's raw per-level conv outputs (``RawLevels``): backward = p24_loss_bwd_raw, one gradient
+    tensor per conv output (the chain rule through the decode of yolo_head_24p.py:233-235 is applied in the kernel)."""
+
+    @staticmethod
+    def forward(ctx, labels, owner, x_shifts, y_shifts, strides, nlev, *planes):
+        raw = RawLevels([t.detach() for t in planes[:nlev]], [t.detach() for t in planes[nlev:2 * nlev]],
+                        [t.detach() for t in planes[2 * nlev:]])
+        result54, weights27, asg = owner.forward_async((x_shifts, y_shifts, strides, raw, []), labels)
+        owner.wait_results()
+        ctx.owner, ctx.asg, ctx.raw, ctx.grid = owner, asg, raw, (x_shifts, y_shifts, strides)
+        ctx.save_for_backward(labels, weights27)
+        return result54
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        lib = _lib.load()
+        labels, w27 = ctx.saved_tensors
+        asg, raw = ctx.asg, ctx.raw
+        dev = raw.device
+        lab = labels if labels.stride(2) == 1 else labels.contiguous()
+        planes, bs = raw.planes()
+        grads = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in planes]
+        _, _, _, lv, nlev = ctx.owner._engine.grids.get(*ctx.grid, dev)
+        B, A = asg.fg_mask.shape
+        scale = g[0:1].contiguous().float()
+        n = len(planes)
+        with torch.cuda.device(dev):
+            _lib.check(lib.p24_loss_bwd_raw((C.c_void_p * n)(*[t.data_ptr() for t in planes]), (C.c_int64 * n)(*bs),
+                                            (C.c_void_p * n)(*[t.data_ptr() for t in grads]), lv, nlev, B, A,
+                                            ctx.owner.num_classes, lab.data_ptr(), lab.stride(0), lab.stride(1),
+                                            asg.fg_mask.data_ptr(), asg.matched_gt.data_ptr(), asg.pred_iou.data_ptr(),
+                                            w27.data_ptr(), scale.data_ptr(), _stream_ptr(dev)), "p24_loss_bwd_raw")
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
 class Loss_Function(nn.Module):
     def __init__(self, num_classes):
         super().__init__()
@@ -176,6 +213,8 @@ class Loss_Function(nn.Module):
         if self.use_l1:
             raise NotImplementedError("use_l1 is never enabled by the 24p scripts (losses.py:163)")
         x_shifts, y_shifts, expanded_strides, outputs = outputs_train[:4]
+        # (outputs: the decoded [B, A, 27 + nc] buffer of the reference's head, or p24.engine.RawLevels: the head's raw
+        # conv outputs, decoded inside the kernels)
         state = self._state(outputs.device)
         self._engine.reuse_buffers = self.reuse_buffers
         if self.process_group is None:
@@ -241,6 +280,8 @@ class Loss_Function(nn.Module):
 
     def forward(self, outputs_train, labels):
         outputs = outputs_train[3]
+        if isinstance(outputs, RawLevels):
+            return self._forward_raw(outputs_train, labels)
         if torch.is_grad_enabled() and outputs.requires_grad:
             r = _LossFn.apply(outputs, labels, self, outputs_train[0], outputs_train[1], outputs_train[2])
             asg = self.last_assignment
@@ -256,6 +297,48 @@ class Loss_Function(nn.Module):
         draw += [r[28:52], r[52], r[53]]
         ratio = float(r[27].detach())  # one D2H read per step (the reference returns a Python float here)
         self.check_errors()            # ... and the kernels' error bits with it (the reference raises on its failures)
+        return (r[0], r[1:25], r[25], r[26], 0.0, ratio, draw)
+
+    def _forward_raw(self, outputs_train, labels):
+        """``forward`` on the head's raw conv outputs (``p24.engine.RawLevels`` in place of the decoded buffer).  Same
+        7-tuple; the drawing entries (decoded centres / radii of the foreground anchors) are gathered from the raw planes.
+        Differentiable w.r.t. every conv output (``_RawLossFn``)."""
+        raw = outputs_train[3]
+        if torch.is_grad_enabled() and raw.requires_grad():
+            r = _RawLossFn.apply(labels, self, outputs_train[0], outputs_train[1], outputs_train[2], len(raw.reg),
+                                 *raw.reg, *raw.obj, *raw.cls)
+            asg = self.last_assignment
+        else:
+            r, _, asg = self.forward_async(outputs_train, labels)
+        self.wait_results()
+        fg = asg.fg_mask.view(-1).bool()
+        nfg = int(fg.sum())
+        if nfg == 0:  # losses.py:111-115
+            z = r.new_zeros(1, 24)
+            draw = [z, z.clone(), z.clone()]
+        else:
+            # decode the foreground anchors only (yolo_head_24p.py:233-235)
+            B, A = asg.fg_mask.shape
+            idx = fg.nonzero().flatten()
+            bi, ai = idx // A, idx % A
+            rows = []
+            off = 0
+            gx, gy, gs, _, _ = self._engine.grids.get(outputs_train[0], outputs_train[1], outputs_train[2], raw.device)
+            for reg in raw.reg:
+                n = reg.shape[2] * reg.shape[3]
+                m = (ai >= off) & (ai < off + n)
+                rows.append((m, reg.detach().flatten(2)[bi[m], :, ai[m] - off]))
+                off += n
+            dec = r.new_empty(nfg, 26)
+            for m, v in rows:
+                dec[m] = v
+            dec[:, 0] = (dec[:, 0] + gx[ai]) * gs[ai]
+            dec[:, 1] = (dec[:, 1] + gy[ai]) * gs[ai]
+            dec[:, 2:] = torch.exp(dec[:, 2:]) * gs[ai][:, None]
+            draw = [dec[:, 0], dec[:, 1], dec[:, 2:26]]
+        draw += [r[28:52], r[52], r[53]]
+        ratio = float(r[27].detach())
+        self.check_errors()
         return (r[0], r[1:25], r[25], r[26], 0.0, ratio, draw)
 
     # -- per-image API (losses.py:359-442) -----------------------------------------------------------

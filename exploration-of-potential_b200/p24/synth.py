@@ -69,6 +69,22 @@ def make_head_outputs(batch: int, img_size: int = 640, num_classes: int = 80, se
     return out.to(device)
 
 
+def make_raw_levels(batch: int, img_size: int = 640, num_classes: int = 80, seed: int = 0, device="cpu",
+                    strides: Sequence[int] = STRIDES, prior_logit: float = -4.6, raw_std: float = 0.5):
+    """Random-init-like RAW conv outputs of the head (yolo_head_24p.py:160-164), per level:
+    ``reg [B, 26, H, W]``, ``obj [B, 1, H, W]``, ``cls [B, nc, H, W]`` (same distributions as ``make_head_outputs``
+    before its decode).  Returns (reg list, obj list, cls list)."""
+    dev = torch.device(device)
+    gen_dev = dev if dev.type == "cuda" else torch.device("cpu")
+    g = torch.Generator(device=gen_dev).manual_seed(seed)
+    reg, obj, cls = [], [], []
+    for h, w in level_sizes(img_size, strides):
+        reg.append((torch.randn(batch, 26, h, w, generator=g, device=gen_dev) * raw_std).to(device))
+        obj.append((torch.randn(batch, 1, h, w, generator=g, device=gen_dev) * raw_std + prior_logit).to(device))
+        cls.append((torch.randn(batch, num_classes, h, w, generator=g, device=gen_dev) * raw_std + prior_logit).to(device))
+    return reg, obj, cls
+
+
 def make_labels(batch: int, num_gt, max_labels: int = 50, img_size: int = 640, num_classes: int = 80,
                 seed: int = 0, kind: str = "smooth", device="cpu", radius_range=(0.025, 0.2)) -> torch.Tensor:
     """``labels[B, Lmax, 51]``.  ``num_gt`` is an int or a per-image sequence.

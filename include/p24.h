@@ -93,6 +93,25 @@ int p24_simota_loss_batch(const float* outputs, int64_t img_stride, int64_t row_
                           void* workspace, size_t workspace_bytes, uint32_t flags,
                           void* const* h_mailboxes, int rank, int nranks, uint32_t epoch, void* stream);
 
+/* The same path on the head's RAW conv outputs (head decode fused into the kernels).  Replaces
+ * YOLOXHead.get_output_and_grid + the cat / view / permute / reshape copies of YOLOXHead.forward(train=True)
+ * (models/yolo_head_24p.py:167-197, 212-237): the kernels read the per-level NCHW tensors
+ *   reg [B, 26, H, W]   obj [B, 1, H, W]   cls [B, nc, H, W]      (yolo_head_24p.py:160-164; H x W planes dense)
+ * and decode on load -- centre (v + grid) * stride, radii exp(v) * stride (yolo_head_24p.py:233-235) -- so the decoded
+ * [B, A, 27 + nc] buffer is never written.
+ *   h_raw               HOST array of 3 * n_levels device pointers: reg of level 0 .. n_levels-1, then obj, then cls
+ *   h_raw_batch_stride  HOST array of 3 * n_levels batch strides (elements); channel stride = H * W
+ * Grids, labels, outputs and everything else as in p24_simota_loss_batch; 27 + nc <= 108. */
+int p24_simota_loss_batch_raw(const float* const* h_raw, const int64_t* h_raw_batch_stride, int B, int A, int num_classes,
+                              const float* labels, int64_t lab_img_stride, int64_t lab_row_stride, int Lmax,
+                              const float* x_shifts, const float* y_shifts, const float* strides,
+                              const int32_t* h_levels, int n_levels,
+                              uint8_t* fg_mask, int32_t* matched_gt, float* pred_iou,
+                              int32_t* num_fg, int32_t* num_gt, int32_t* dyn_k, float* sums28,
+                              float* state26, float* result54, float* weights_n27,
+                              void* workspace, size_t workspace_bytes, uint32_t flags,
+                              void* const* h_mailboxes, int rank, int nranks, uint32_t epoch, void* stream);
+
 /* Fused all-reduce of the 28 loss sums over NVLink / NVSwitch peer memory (the one collective of the path).
  * Every rank (one process per GPU) owns a small mailbox allocated with p24_comm_alloc and maps its peers' mailboxes
  * through CUDA IPC (p24_comm_export on the owner, p24_comm_import on the peers).  p24_simota_loss_batch then takes
@@ -154,6 +173,16 @@ int p24_loss_bwd(const float* outputs, int64_t img_stride, int64_t row_stride, i
                  const float* labels, int64_t lab_img_stride, int64_t lab_row_stride,
                  const uint8_t* fg_mask, const int32_t* matched_gt, const float* pred_iou,
                  const float* weights_n27, const float* grad_scale, float* grad_outputs, void* stream);
+
+/* The same backward w.r.t. the head's RAW per-level conv outputs (p24_simota_loss_batch_raw; the decode of
+ * models/yolo_head_24p.py:233-235 folded in).  h_raw / h_raw_batch_stride as for p24_simota_loss_batch_raw;
+ * h_grad_raw: HOST array of 3 * n_levels DEVICE pointers in the same order, each a dense [B, C, H, W] tensor
+ * (C = 26 / 1 / nc), fully overwritten; h_levels: HOST (anchor offset, W, H, stride bits) per level. */
+int p24_loss_bwd_raw(const float* const* h_raw, const int64_t* h_raw_batch_stride, float* const* h_grad_raw,
+                     const int32_t* h_levels, int n_levels, int B, int A, int num_classes,
+                     const float* labels, int64_t lab_img_stride, int64_t lab_row_stride,
+                     const uint8_t* fg_mask, const int32_t* matched_gt, const float* pred_iou,
+                     const float* weights_n27, const float* grad_scale, void* stream);
 
 /* Loss_Function.dynamic_k_matching (models/losses.py:444-494) on a materialised cost matrix.
  * cost, ious: dense [G, P];  fg_in [P] uint8, matched [P] int32 (-1 when not fg), matched_iou [P] fp32,

@@ -84,3 +84,16 @@ def test_postprocess_matches_reference_fixture():
                 assert np.array_equal(r.numpy(), want)
         si += 1
     assert si == 4
+
+
+def test_head_decode_matches_reference_fixture():
+    """Head decode restatement (yolo_head_24p.py:212-256) against the reference-made fixture: raw conv outputs are
+    re-drawn from the seed; exp() may differ in the last bit between hosts."""
+    g = _load("head_s64.npz")
+    reg, obj, cls = synth.make_raw_levels(int(g["batch"]), int(g["img_size"]), 80, seed=int(g["seed"]))
+    xs, ys, ss, train = orc.head_decode_train(reg, obj, cls, list(synth.STRIDES))
+    np.testing.assert_allclose(train.numpy(), g["train"], rtol=RTOL, atol=0)
+    assert np.array_equal(train[:, :, 26:].numpy(), g["train"][:, :, 26:])   # logits pass through untouched
+    mx, my, ms = synth.make_grids(int(g["img_size"]))
+    assert all(torch.equal(a, b) for a, b in zip(xs + ys + ss, mx + my + ms))
+    np.testing.assert_allclose(orc.head_decode_infer(reg, obj, cls, list(synth.STRIDES)).numpy(), g["infer"], rtol=RTOL, atol=0)

@@ -50,3 +50,29 @@ def test_postprocess_bit_equal():
             r = ref_utils.postprocess(p[i:i + 1].clone(), 80, c, n, ag)[0]
             o = orc.postprocess(p[i:i + 1].clone(), 80, c, n, ag)[0]
             assert (r is None) == (o is None) and (r is None or torch.equal(r, o))
+
+
+def test_head_decode_bit_equal():
+    """The head-decode restatement (train and inference) against the reference's own methods
+    (yolo_head_24p.py:212-256), called unbound on a stand-in for the module state they read."""
+    import types
+    ref_models, _ = load_reference()
+    head = ref_models.YOLOXHead
+    reg, obj, cls = synth.make_raw_levels(2, 160, 80, seed=21)
+    strides = [8, 16, 32]
+    me = types.SimpleNamespace(grids=[torch.zeros(1)] * 3, num_classes=80, n_anchors=1)
+    outs, xs, ys = [], [], []
+    for k in range(3):
+        o, grid = head.get_output_and_grid(me, torch.cat([reg[k], obj[k], cls[k]], 1), k, strides[k], "torch.FloatTensor")
+        outs.append(o), xs.append(grid[:, :, 0]), ys.append(grid[:, :, 1])
+    want = torch.cat(outs, 1)
+    gx, gy, gs, got = orc.head_decode_train(reg, obj, cls, strides)
+    assert torch.equal(got, want)
+    assert all(torch.equal(a, b) for a, b in zip(gx, xs)) and all(torch.equal(a, b) for a, b in zip(gy, ys))
+    assert all(float(s[0, 0]) == st and s.shape[1] == x.shape[1] for s, st, x in zip(gs, strides, xs))
+    # inference: cat(sigmoid) -> flatten/cat/permute -> decode_outputs
+    flat = [torch.cat([reg[k], obj[k].sigmoid(), cls[k].sigmoid()], 1) for k in range(3)]
+    me.hw, me.strides = [x.shape[-2:] for x in flat], strides
+    pred = torch.cat([x.flatten(start_dim=2) for x in flat], dim=2).permute(0, 2, 1)
+    want = head.decode_outputs(me, pred, dtype="torch.FloatTensor")
+    assert torch.equal(orc.head_decode_infer(reg, obj, cls, strides), want)

@@ -154,7 +154,32 @@ def post_case(ref_utils, name, img_size, B, seed, settings):
     np.savez_compressed(os.path.join(GOLD, f"post_{name}.npz"), **rec)
 
 
+def head_case(ref_models, name, img_size, B, seed):
+    """Head decode (yolo_head_24p.py:212-256): raw per-level conv outputs -> the reference's decoded training buffer and
+    inference prediction, by the reference's own methods called on a stand-in for the module state they read."""
+    import types
+    head = ref_models.YOLOXHead
+    reg, obj, cls = synth.make_raw_levels(B, img_size, NC, seed=seed)
+    strides = list(synth.STRIDES)
+    me = types.SimpleNamespace(grids=[torch.zeros(1)] * len(strides), num_classes=NC, n_anchors=1)
+    outs = [head.get_output_and_grid(me, torch.cat([reg[k], obj[k], cls[k]], 1), k, strides[k], "torch.FloatTensor")[0]
+            for k in range(len(strides))]
+    train = torch.cat(outs, 1)
+    flat = [torch.cat([reg[k], obj[k].sigmoid(), cls[k].sigmoid()], 1) for k in range(len(strides))]
+    me.hw, me.strides = [x.shape[-2:] for x in flat], strides
+    infer = head.decode_outputs(me, torch.cat([x.flatten(start_dim=2) for x in flat], dim=2).permute(0, 2, 1),
+                                dtype="torch.FloatTensor")
+    assert torch.equal(orc.head_decode_train(reg, obj, cls, strides)[3], train)
+    assert torch.equal(orc.head_decode_infer(reg, obj, cls, strides), infer)
+    np.savez_compressed(os.path.join(GOLD, f"head_{name}.npz"), img_size=np.int64(img_size), batch=np.int64(B),
+                        seed=np.int64(seed), train=train.numpy(), infer=infer.numpy())
+    print(f"head_{name}: train {tuple(train.shape)} infer {tuple(infer.shape)}")
+
+
 def main():
+    if sys.argv[1:] == ["head"]:   # only the head-decode fixture (the others stay byte-identical)
+        head_case(load_reference()[0], "s64", 64, 2, 21)
+        return
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
     ref_models, ref_utils = load_reference()
@@ -170,6 +195,7 @@ def main():
             raise SystemExit(f"no certified seed for {name}")
     post_case(ref_utils, "s256", 256, 2, 3,
               [(0.25, 0.45, False), (0.01, 0.65, False), (0.01, 0.3, True), (0.99, 0.45, False)])
+    head_case(ref_models, "s64", 64, 2, 21)
 
 
 if __name__ == "__main__":

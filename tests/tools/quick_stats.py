@@ -1,5 +1,6 @@
 """Quick look at one workload on the GPU: per-kernel CUDA-event times, rare-path counters, step time.
-Usage: python tests/tools/quick_stats.py [train|train_spiky|crowded|hires] [steps]"""
+Usage: python tests/tools/quick_stats.py [train|train_spiky|crowded|hires] [steps] [raw]
+(raw: feed the head's raw per-level conv outputs, p24.engine.RawLevels, instead of the decoded buffer)"""
 import ctypes
 import os
 import sys
@@ -11,6 +12,7 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 from p24 import lib as p24_lib, synth  # noqa: E402
+from p24.engine import RawLevels  # noqa: E402
 from p24.losses import Loss_Function  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "train"
@@ -18,10 +20,16 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 wl = bench.TRAIN_WORKLOADS[name]
 B = wl["B"] or 20
 dev = torch.device("cuda:0")
+RAW = len(sys.argv) > 3 and sys.argv[3] == "raw"
 sets = []
 for i in range(5 if wl["size"] == 640 else 2):
     s = wl["seed"] + 100 * i
-    sets.append((synth.make_head_outputs(B, wl["size"], 80, seed=s).to(dev),
+    if RAW:
+        r, o, c = synth.make_raw_levels(B, wl["size"], 80, seed=s)
+        head = RawLevels([t.to(dev) for t in r], [t.to(dev) for t in o], [t.to(dev) for t in c])
+    else:
+        head = synth.make_head_outputs(B, wl["size"], 80, seed=s).to(dev)
+    sets.append((head,
                  synth.make_labels(B, wl["G"], wl["Lmax"], wl["size"], 80, seed=s, kind=wl["kind"]).to(dev)))
 xs, ys, ss = synth.make_grids(wl["size"])
 g = [[t.to(dev) for t in l] for l in (xs, ys, ss)]
