@@ -379,6 +379,55 @@ def bench_train(ctx, name, steps, warmup, allreduce, want_e2e=True, want_cpu=Tru
             "slow_path": stats, "loss_check": loss_check, "allreduce_check": check}
 
 
+def bench_head_fusion(ctx, steps, warmup):
+    """the loss on the head's RAW per-level conv outputs (decode fused into the kernels) against the
+    reference's way (torch cat / permute / decode passes, then the loss on the decoded buffer).  configs[1] shapes."""
+    from p24 import head as p24_head
+    from p24 import synth
+    wl = TRAIN_WORKLOADS["train"]
+    B, size, G, Lmax = wl["B"], wl["size"], wl["G"], wl["Lmax"]
+    A = sum((size // s) ** 2 for s in (8, 16, 32))
+    n_sets = max(2, -(-int(2.2 * L2_BYTES) // (B * A * 107 * 4)))
+    raws, labs = [], []
+    for i in range(n_sets):
+        r, o, c = synth.make_raw_levels(B, size, 80, seed=wl["seed"] + 100 * i, device=ctx.dev)
+        raws.append((r, o, c))
+        labs.append(synth.make_labels(B, G, Lmax, size, 80, seed=wl["seed"] + 100 * i, kind=wl["kind"]).to(ctx.dev))
+    out = {}
+    for mode in ("fused", "unfused"):
+        lf = new_loss_function(ctx, "peer")
+
+        def step(i):
+            r, o, c = raws[i % n_sets]
+            tup = p24_head.train_outputs(r, o, c, synth.STRIDES, fused=(mode == "fused"))
+            return lf.forward_async(tup, labs[i % n_sets])
+
+        for i in range(warmup + 5):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            res = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        lf.check_errors()
+        ms = e0.elapsed_time(e1) / steps
+        out[mode] = {"ms_per_step": ms, "value": B / (ms * 1e-3), "loss_check": float(res[0][0])}
+    alg = algorithmic_bytes_per_image(A, 107, Lmax) * B
+    peak, _ = measured_peak()
+    return {"metric": "train_step_images_per_sec_from_raw_head_outputs", "unit": "images/s",
+            "config": {"workload": f"configs[1] shapes, inputs = raw per-level conv outputs reg/obj/cls [B, C, H, W] "
+                                   f"(batch {B}, {A} anchors, {G} GT/img)",
+                       "l2": f"inputs rotate over {n_sets} distinct batches"},
+            "value": out["fused"]["value"], "ms_per_step": out["fused"]["ms_per_step"],
+            "unfused_torch_decode_then_loss": out["unfused"],
+            "speedup_vs_unfused": out["unfused"]["ms_per_step"] / out["fused"]["ms_per_step"],
+            "loss_check_equal": out["fused"]["loss_check"] == out["unfused"]["loss_check"],
+            "whole_step_frac_of_hbm_peak": (alg / (out["fused"]["ms_per_step"] * 1e-3) / 1e9) / peak,
+            "algorithmic_bytes_per_step": alg}
+
+
 def allreduce_check(ctx, dset, grids):
     """N > 1: the fused peer-memory exchange against NCCL + finalize on the same shard (first batch): the loss must be
     bit-identical on all ranks in both modes, and the two modes must agree to fp32 rounding of the 28-float sums."""
@@ -509,7 +558,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--only", default=None, help="comma list of blocks to run beside nothing else: "
-                    "train,train_spiky,crowded,hires,postprocess (default: headline + all extras)")
+                    "train,train_spiky,crowded,hires,train_raw,postprocess (default: headline + all extras)")
     ap.add_argument("--workload", default=None, help="(compat) same as --only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -539,7 +588,7 @@ def main():
     ctx.lfs = []
     only = args.only or args.workload
     blocks = only.split(",") if only else (["train"] if args.no_extras else
-                                           ["train", "train_spiky", "crowded", "hires", "postprocess"])
+                                           ["train", "train_spiky", "crowded", "hires", "train_raw", "postprocess"])
     want_cpu, want_e2e = not args.no_cpu_baseline, not args.no_e2e
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("P24_NO_CLOCK_SAMPLER"):
@@ -555,6 +604,9 @@ def main():
                                          e2e_steps=None if bname != "hires" else 3)
             if head:
                 clocks = sampler.stop() if rank == 0 else None
+        elif bname == "train_raw":
+            if world == 1:   # (a single-GPU comparison: the sharded path is the same chain)
+                results["train_raw"] = bench_head_fusion(ctx, max(5, args.steps // 2), args.warmup)
         elif bname == "postprocess":
             k = max(5, args.steps // 2)
             results["postprocess"] = {lab: bench_post(ctx, lab, c, n, a, k, args.warmup, want_e2e, want_cpu)

@@ -26,6 +26,7 @@
 #define GT_CY 1
 #define GT_RIN2 2    // squared radius of a disc around (cx, cy) that lies inside the polygon (0: none)
 #define GT_RREJ2 3   // squared radius beyond which the angle sum is provably < 349 degrees
+#define P24_FQ_PER_GT 256
 #define GT_FAR2 4    // squared centre distance below which no prediction's pair value can reach T (0: none)
 #define GT_CLS 5
 #define GT_RGMAX 6
@@ -53,8 +54,8 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 #define ST_WORDS 8
 
 struct P24Workspace {
-    size_t ticket;      // [8] unsigned: tile-queue head of k_pass, largest num_gt, completion count of k_tail, seed-queue head,
-                        //               window-queue head, number of centre-window pairs of the batch
+    size_t ticket;      // [8] unsigned: tile-queue head of k_pass, largest num_gt, completion count of k_tail, far-queue entries,
+                        //               window-queue head, number of centre-window pairs of the batch, far-queue head, tiles done
     size_t acc_fix;     // [28] int64   fixed-point loss sums of the batch (zero between calls)
     size_t status;      // [ST_WORDS] int
     size_t seed_done;   // [B] int      seed items of the image that are complete (zero between calls)
@@ -72,6 +73,8 @@ struct P24Workspace {
     size_t cbits;       // [B, tiles * 8] unsigned         candidate bitmap (bit l of word w: anchor 32 w + l)
     size_t brute;       // [B, 8, 10] float   per-CTA partial top-10 of the brute-force path of k_tail
     size_t wlist;       // [B * Lmax * 100] int2           the batch's centre-window pairs (GT slot, anchor), written by k_prep
+    size_t fq;          // [B * Lmax * P24_FQ_PER_GT] int2   the batch's far queue (GT slot, anchor): far pairs that did not fit a
+                        //                                    tile's own work list (k_pass)
     size_t total;
 };
 
@@ -99,6 +102,7 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     w.cbits = off;      off = p24_align(off + NB * P24_WARPS * sizeof(unsigned));
     w.brute = off;      off = p24_align(off + (size_t)B * 8 * P24_TOPK * sizeof(float));
     w.wlist = off;      off = p24_align(off + BL * 25 * P24_MAX_LEVELS * 2 * sizeof(int));
+    w.fq = off;         off = p24_align(off + BL * P24_FQ_PER_GT * 2 * sizeof(int));
     w.total = off;
     return w;
 }

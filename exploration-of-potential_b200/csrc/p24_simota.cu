@@ -74,6 +74,8 @@ struct Params {
     float2* list;
     unsigned* cbits;
     int2* wlist;
+    int2* fq;      // the batch's far queue (GT slot, anchor): overflow of the tiles' own far-pair lists
+    int fq_cap;
     float* brute;
     int* claimg;
     int* kreq;
@@ -110,9 +112,11 @@ __device__ __forceinline__ void tmark(int kern, int row, int slot) {
 #define TK_ITEM 0   // ticket words
 #define TK_LEFF 1
 #define TK_TAIL 2
-#define TK_SEED 3
+#define TK_FQ 3     // far queue: entries reserved
 #define TK_WIN 4    // window-chunk queue head
 #define TK_WTOT 5   // centre-window pairs of the batch (k_prep)
+#define TK_FQH 6    // far queue: chunk head
+#define TK_TDONE 7  // anchor tiles complete
 
 #define P24_HEAD_RAW 0
 namespace rows {
@@ -313,6 +317,8 @@ int simota_impl(const float* outputs, int64_t img_stride, int64_t row_stride, co
     p.list = (float2*)(ws + L.list);
     p.cbits = (unsigned*)(ws + L.cbits);
     p.wlist = (int2*)(ws + L.wlist);
+    p.fq = (int2*)(ws + L.fq);
+    p.fq_cap = (int)((size_t)B * Lmax * P24_FQ_PER_GT);
     p.brute = (float*)(ws + L.brute);
     p.claimg = (int*)(ws + L.claimg);
     p.kreq = (int*)(ws + L.kreq);

@@ -66,6 +66,18 @@ for lab, a, b_ in [("count labels", 0, 1), ("records+pairs", 1, 2), ("image barr
 print(f"== k_pass: CTAs past pdl_wait at 0 us; last CTA end {us(kp[6000:7024, 1].max()):.1f} us")
 tl = kp[:min(B * tiles, 4095)]
 print(f"   tiles: first start {us(tl[:, 0].min()):.1f}  last end {us(tl[:, 7].max()):.1f}")
+if tl.shape[0] == B * tiles:
+    per = (tl[:, 7] - tl[:, 0]).reshape(B, tiles) / 1e3
+    st_ = ((tl[:, 0]).reshape(B, tiles) - t0) / 1e3
+    print("   tile total by tile-in-image (mean us):", " ".join(f"{v:.0f}" for v in per.mean(0)))
+    print("   tile start by tile-in-image (mean us):", " ".join(f"{v:.0f}" for v in st_.mean(0)))
+    late = np.argsort(-(tl[:, 7]))[:8]
+    print("   last tiles to end (image, tile, start, end):", [(int(k // tiles), int(k % tiles), round(us(tl[k, 0]), 1), round(us(tl[k, 7]), 1)) for k in late])
+fq = kp[4096:6000]
+fq = fq[fq[:, 0] > 0]
+if fq.shape[0]:
+    print(f"   far-queue chunks: n={fq.shape[0]} first start {us(fq[:, 0].min()):.1f} last end {us(fq[:, 7].max()):.1f}")
+    stat("far chunk", fq[:, 7] - fq[:, 0])
 for lab, a, b_ in [("pre", 0, 1), ("recs+rows", 1, 3), ("gt loop+lists", 3, 4), ("poly items", 4, 5), ("cand sync", 5, 2),
                    ("wait seeds", 2, 8), ("far list", 8, 6), ("far items+out", 6, 7), ("tile total", 0, 7)]:
     stat(lab, tl[:, b_] - tl[:, a])
