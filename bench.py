@@ -595,7 +595,12 @@ def main():
         sampler.start()
     results = {}
     head_name = blocks[0] if blocks[0] in TRAIN_WORKLOADS else None
-    for bname in blocks:
+    clocks = None
+    for bi, bname in enumerate(blocks):
+        if bi == 1 and head_name is None:
+            # (no training block first: the clocks were sampled under the first block; nvidia-smi polling stops here, it
+            # can stall launches for milliseconds and the remaining blocks are short)
+            clocks = sampler.stop() if rank == 0 else None
         if bname in TRAIN_WORKLOADS:
             head = bname == head_name
             k = args.steps if head else max(5, args.steps // (4 if bname == "hires" else 2))
@@ -613,7 +618,7 @@ def main():
                                       for lab, c, n, a in POST_SETTINGS}
         else:
             raise SystemExit(f"unknown block {bname}")
-    if head_name is None:
+    if head_name is None and clocks is None:
         clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         if head_name is not None:

@@ -20,6 +20,8 @@
 // torchvision's expression  inter / (area_a + area_b - inter) > thr  in fp32 without FMA contraction (this file is
 // compiled with -fmad=false), the sort is stable, and batched NMS adds  class * (max_coordinate + 1)  to the boxes in
 // fp32 exactly like _batched_nms_coordinate_trick.
+#include <stdio.h>
+
 #include "p24_common.cuh"
 #include "p24_host.h"
 
@@ -251,6 +253,14 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     __shared__ int s_nkept;
     __shared__ float s_red[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef P24_TIMING
+    unsigned long long tm[8];
+    int path = 0, dbg_ng = 0, dbg_maxm = 0;
+#define PT(k) do { __syncthreads(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm[k])); } while (0)
+#else
+#define PT(k)
+#endif
+    PT(0);
 
     // ---- number of candidates, prefix of the tile counts ----------------------------------------------------------
     if (tid == 0) {
@@ -293,7 +303,9 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     __syncthreads();
     cmax = s_red[0];
     for (int w = 1; w < NMS_THREADS / 32; ++w) cmax = fmaxf(cmax, s_red[w]);
+    PT(1);
     bitonic_sort(keys, npad);
+    PT(2);
 
     // ---- sorted rectangles (+ class offset for batched NMS: boxes + idxs * (max_coordinate + 1)) --------------------
     float4* srect = p.s_rect + (long long)b * p.A;
@@ -368,7 +380,275 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
         cellw = fmaxf(fmaxf(wmx, span * (1.0f / (float)NCELL_MAX)) * 1.0001f, 1e-6f);
         ncell = min(NCELL_MAX, (int)(span / cellw) + 1);
     }
-    if (ncell >= 16 && p.nms_thre >= 0.0f) {
+    // (G) batched NMS with a non-negative threshold: boxes of different classes are disjoint after the class offsets (IoU 0),
+    //     so the recursion splits into independent GROUPS of classes.  A group is a maximal run of classes whose offset
+    //     x ranges [min x0, max x1] overlap (conservative: a class whose boxes reach below x = -1 may touch the class
+    //     before it, torchvision lets such boxes interact); almost always one class each.  One warp per group: its boxes
+    //     in sorted order, eight per lane in registers, the classic serial sweep "kept box i suppresses the later boxes it
+    //     overlaps" with the box broadcast by shuffles.
+    PT(3);
+    bool done = false;
+    if (!p.class_agnostic && allfinite && p.nc <= NCELL_MAX / 2 && p.nms_thre >= 0.0f) {
+        __shared__ short s_gid[NCELL_MAX / 2];
+        __shared__ int s_reach[NCELL_MAX / 2];
+        __shared__ unsigned s_pm[2][NCELL_MAX / 2];
+        __shared__ int s_ng, s_maxm;
+        int* gcnt = s_cellstart;                                   // per group: count, then start (prefix)
+        unsigned* hix = reinterpret_cast<unsigned*>(s_cellfill);   // per class: ordered max x1 | ordered max y1 (offset coordinates)
+        unsigned* hiy = hix + NCELL_MAX / 2;
+        int* grp = p.s_cell + (long long)b * p.A;                  // class, then group, of every sorted box
+        int* order = p.s_order + (long long)b * p.A;
+        const int nc = p.nc;
+        for (int c = tid; c < nc; c += NMS_THREADS) {
+            hix[c] = 0u;
+            hiy[c] = 0u;
+            s_reach[c] = c;
+        }
+        for (int c = tid; c <= nc; c += NMS_THREADS) gcnt[c] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const int c = min(max(p.c_cls[slot0 + (long long)(keys[i] & 0x3FFFFFFFull)], 0), nc - 1);
+            const float4 r = srect[i];
+            atomicMax(&hix[c], p24_ordered(r.z));
+            atomicMax(&hiy[c], p24_ordered(r.w));
+            grp[i] = c;
+        }
+        __syncthreads();
+        if (warp < 2) {  // prefix maxima over the classes before c (warp 0: x, warp 1: y)
+            const unsigned* src = warp == 0 ? hix : hiy;
+            unsigned carry = 0u;
+            for (int c0 = 0; c0 < nc; c0 += 32) {
+                const int c = c0 + lane;
+                unsigned v = c < nc ? src[c] : 0u;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, v, off);
+                    if (lane >= off) v = max(v, t);
+                }
+                const unsigned incl = max(v, carry);
+                unsigned excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = carry;
+                if (c < nc) s_pm[warp][c] = excl;
+                carry = __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        __syncthreads();
+        // a box whose upper-left corner lies below the lower-right extent of an earlier class (in x AND in y) may overlap
+        // boxes of that class (rare: boxes sticking out of the image corner).  Those few boxes are tested against every box
+        // of the earlier classes: only a pair that really exceeds the threshold ties the two classes together.
+        __shared__ int s_flag[64];
+        __shared__ int s_nflag;
+        if (tid == 0) s_nflag = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const int c = grp[i];
+            const float4 r = srect[i];
+            const unsigned ox = p24_ordered(r.x), oy = p24_ordered(r.y);
+            if (ox < s_pm[0][c] && oy < s_pm[1][c]) {
+                const int at = atomicAdd(&s_nflag, 1);
+                if (at < 64) {
+                    s_flag[at] = i;
+                } else {  // (too many to test one by one: tie the class to the earliest class it reaches into)
+                    for (int c2 = 0; c2 < c; ++c2)
+                        if (hix[c2] > ox && hiy[c2] > oy) {
+                            atomicMin(&s_reach[c], c2);
+                            break;
+                        }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const int nflag = min(s_nflag, 64);
+            for (int f = 0; f < nflag; ++f) {
+                const int fi = s_flag[f];
+                const int cf = grp[fi];
+                const float4 bf = srect[fi];
+                for (int i = tid; i < n; i += NMS_THREADS) {
+                    const int c = grp[i];
+                    if (c < cf && iou_over(srect[i], bf, p.nms_thre)) atomicMin(&s_reach[cf], c);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int sm = nc;
+            for (int c = nc - 1; c >= 0; --c) {  // a group starts at c iff no class >= c reaches below c
+                sm = min(sm, (int)s_reach[c]);
+                s_gid[c] = (short)(sm >= c ? 1 : 0);
+            }
+            int g = -1;
+            for (int c = 0; c < nc; ++c) {
+                g += s_gid[c];
+                s_gid[c] = (short)g;
+            }
+            s_ng = g + 1;
+        }
+        __syncthreads();
+        const int ng = s_ng;
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const int g = s_gid[grp[i]];
+            grp[i] = g;
+            atomicAdd(&gcnt[g], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0, mx = 0;
+            for (int g = 0; g < ng; ++g) {
+                const int c = gcnt[g];
+                mx = max(mx, c);
+                gcnt[g] = acc;
+                acc += c;
+            }
+            gcnt[ng] = acc;
+            s_maxm = mx;
+        }
+        __syncthreads();
+        PT(4);
+#ifdef P24_TIMING
+        dbg_ng = s_ng;
+        dbg_maxm = s_maxm;
+#endif
+        // largest group that the group sweep handles: beyond it the serial part of a single warp would dominate
+        if (s_maxm <= 4096) {
+            done = true;
+            const float thr = p.nms_thre;
+            // ---- every group's boxes in sorted order: a stable counting sort of the sorted ranks by group.  Warp w owns
+            // the ranks [w * per, (w + 1) * per): counts per (warp, group), prefix over the warps, placement.
+            unsigned short (*s_hist)[128] = reinterpret_cast<unsigned short (*)[128]>(&s_pm[0][0]);  // (s_pm is dead by now)
+            static_assert(sizeof(s_pm) >= (NMS_THREADS / 32) * 128 * sizeof(unsigned short), "s_hist does not fit s_pm");
+            const bool counting = ng <= 128 && n <= 65535;
+            if (counting) {
+                const int per = (((n + NMS_THREADS / 32 - 1) / (NMS_THREADS / 32)) + 31) & ~31;
+                const int r0 = warp * per, r1 = min(n, r0 + per);
+                for (int g = lane; g < ng; g += 32) s_hist[warp][g] = 0;
+                __syncwarp();
+                for (int i0 = r0; i0 < r1; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int g = i < r1 ? grp[i] : -1;
+                    const unsigned same = __match_any_sync(0xffffffffu, g);
+                    if (g >= 0 && lane == __ffs(same) - 1) s_hist[warp][g] += __popc(same);
+                    __syncwarp();
+                }
+                __syncthreads();
+                for (int g = tid; g < ng; g += NMS_THREADS) {  // counts -> start of the warp's run inside the group
+                    int acc = 0;  // (relative to the group's start: fits 16 bits)
+                    for (int w = 0; w < NMS_THREADS / 32; ++w) {
+                        const int c = s_hist[w][g];
+                        s_hist[w][g] = (unsigned short)acc;
+                        acc += c;
+                    }
+                }
+                __syncthreads();
+                for (int i0 = r0; i0 < r1; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int g = i < r1 ? grp[i] : -1;
+                    const unsigned same = __match_any_sync(0xffffffffu, g);
+                    if (g >= 0) order[gcnt[g] + s_hist[warp][g] + __popc(same & ((1u << lane) - 1u))] = i;
+                    __syncwarp();
+                    if (g >= 0 && lane == __ffs(same) - 1) s_hist[warp][g] += __popc(same);
+                    __syncwarp();
+                }
+                __syncthreads();
+            }
+            // the warps draw the groups from a counter, the largest first (a group's sweep is serial and grows with the
+            // square of its size: the big ones must not come last)
+            __shared__ int s_next;
+            __syncthreads();
+            if (ng <= NCELL_MAX / 2) {
+                for (int g = tid; g < ng; g += NMS_THREADS) {
+                    const int mg = gcnt[g + 1] - gcnt[g];
+                    int rank = 0;
+                    for (int g2 = 0; g2 < ng; ++g2) {
+                        const int m2 = gcnt[g2 + 1] - gcnt[g2];
+                        rank += (m2 > mg || (m2 == mg && g2 < g)) ? 1 : 0;
+                    }
+                    s_reach[rank] = g;
+                }
+            }
+            if (tid == 0) s_next = 0;
+            __syncthreads();
+            for (;;) {
+                int gi = 0;
+                if (lane == 0) gi = atomicAdd(&s_next, 1);
+                gi = __shfl_sync(0xffffffffu, gi, 0);
+                if (gi >= ng) break;
+                const int g = s_reach[gi];
+                const int g0 = gcnt[g], m = gcnt[g + 1] - g0;
+                if (m == 0) continue;
+                if (!counting) {  // (many groups: one scan of the ranks per group)
+                    int pos = g0;
+                    for (int i0 = 0; i0 < n && pos < g0 + m; i0 += 32) {
+                        const int i = i0 + lane;
+                        const bool mine = i < n && grp[i] == g;
+                        const unsigned bal = __ballot_sync(0xffffffffu, mine);
+                        if (mine) order[pos + __popc(bal & ((1u << lane) - 1u))] = i;
+                        pos += __popc(bal);
+                    }
+                    __syncwarp();
+                }
+                // blocks of 256 boxes, eight per lane in registers: first the kept boxes of the earlier blocks sweep the
+                // block, then the serial sweep inside it
+                for (int blk = 0; blk < m; blk += 256) {
+                    const int mb = min(256, m - blk);
+                    float4 rc[8];
+                    int idx[8];
+                    unsigned dead = 0u;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int j = t * 32 + lane;
+                        idx[t] = j < mb ? order[g0 + blk + j] : -1;
+                        rc[t] = j < mb ? srect[idx[t]] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    for (int i = 0; i < blk; ++i) {
+                        const int ii = order[g0 + i];
+                        if ((((volatile unsigned long long*)keys)[ii] >> 31) & 1ull) continue;
+                        const float4 bi = srect[ii];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            if (t * 32 < mb && idx[t] >= 0 && !((dead >> t) & 1u)) {
+                                const float4 bj = rc[t];
+                                const bool disjoint = bj.x >= bi.z || bi.x >= bj.z || bj.y >= bi.w || bi.y >= bj.w;
+                                if (!disjoint && iou_over(bi, bj, thr)) dead |= 1u << t;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; ++s8) {
+                        if (s8 * 32 < mb) {
+                            const int lim = min(32, mb - s8 * 32);
+                            for (int l = 0; l < lim; ++l) {
+                                if (__shfl_sync(0xffffffffu, (dead >> s8) & 1u, l)) continue;  // suppressed by a kept box
+                                float4 bi;
+                                bi.x = __shfl_sync(0xffffffffu, rc[s8].x, l);
+                                bi.y = __shfl_sync(0xffffffffu, rc[s8].y, l);
+                                bi.z = __shfl_sync(0xffffffffu, rc[s8].z, l);
+                                bi.w = __shfl_sync(0xffffffffu, rc[s8].w, l);
+                                const int i = s8 * 32 + l;
+#pragma unroll
+                                for (int t = s8; t < 8; ++t) {
+                                    const int j = t * 32 + lane;
+                                    if (t * 32 < mb && j > i && j < mb && !((dead >> t) & 1u)) {
+                                        const float4 bj = rc[t];
+                                        const bool disjoint = bj.x >= bi.z || bi.x >= bj.z || bj.y >= bi.w || bi.y >= bj.w;  // IoU = 0
+                                        if (!disjoint && iou_over(bi, bj, thr)) dead |= 1u << t;
+                                    }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (idx[t] >= 0 && ((dead >> t) & 1u)) keys[idx[t]] |= (1ull << 31);
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (done) {
+        // (decided above)
+    } else if (ncell >= 16 && p.nms_thre >= 0.0f) {
         // ---- (I) ----
         int* order = p.s_order + (long long)b * p.A;
         int* cellof = p.s_cell + (long long)b * p.A;
@@ -521,11 +801,16 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     }
     __syncthreads();
 
+    PT(5);
+#ifdef P24_TIMING
+    path = done ? 1 : 2;
+#endif
     // ---- output rows of the survivors in sorted order ------------------------------------------------------------
     // ordered compaction over i = 0..n-1
     __shared__ int s_base;
     if (tid == 0) s_base = 0;
     __syncthreads();
+    int* klist = p.s_order + (long long)b * p.A;  // sorted rank of the k-th kept box (the group lists are no longer needed)
     for (int i0 = 0; i0 < n; i0 += NMS_THREADS) {
         const int i = i0 + tid;
         const bool keep = i < n && !((keys[i] >> 31) & 1ull);
@@ -536,22 +821,52 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
         for (int w = 0; w < warp; ++w) before += __float_as_int(s_red[w]);
         int tot = 0;
         for (int w = 0; w < NMS_THREADS / 32; ++w) tot += __float_as_int(s_red[w]);
-        if (keep) {
-            const int k = before + __popc(bal & ((1u << lane) - 1u));
-            const long long o = slot0 + (long long)(keys[i] & 0x3FFFFFFFull);
-            const int a = p.c_anchor[o];
-            const float* row = p.pred + (long long)b * p.img_stride + (long long)a * p.row_stride;
-            float* dst = p.det_rows + ((long long)b * p.A + k) * 29;
-            for (int c = 0; c < 27; ++c) dst[c] = row[c];
-            dst[27] = p.c_conf[o];
-            dst[28] = (float)p.c_cls[o];
-            p.keep_idx[(long long)b * p.A + k] = a;
-        }
+        if (keep) klist[before + __popc(bal & ((1u << lane) - 1u))] = i;
         __syncthreads();
         if (tid == 0) s_base += tot;
         __syncthreads();
     }
+    // rows: one warp per kept box, the 27 leading floats of its prediction row in one coalesced read
+    const int nkept = s_base;
+    for (int k0 = warp * 32; k0 < nkept; k0 += NMS_THREADS) {
+        // the lanes fetch what 32 rows need (rank -> slot -> anchor, confidence, class), then the warp copies the rows,
+        // four in flight
+        const int kk = k0 + lane;
+        int a = 0;
+        float conf = 0.0f, clsf = 0.0f;
+        if (kk < nkept) {
+            const int i = klist[kk];
+            const long long o = slot0 + (long long)(keys[i] & 0x3FFFFFFFull);
+            a = p.c_anchor[o];
+            conf = p.c_conf[o];
+            clsf = (float)p.c_cls[o];
+            p.keep_idx[(long long)b * p.A + kk] = a;
+        }
+        const int cnt = min(32, nkept - k0);
+        for (int r0 = 0; r0 < cnt; r0 += 4) {
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = min(r0 + q, cnt - 1);
+                const int ar = __shfl_sync(0xffffffffu, a, r);
+                const float cr = __shfl_sync(0xffffffffu, conf, r), lr = __shfl_sync(0xffffffffu, clsf, r);
+                const float* row = p.pred + (long long)b * p.img_stride + (long long)ar * p.row_stride;
+                v[q] = lane < 27 ? row[lane] : (lane == 27 ? cr : lr);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (r0 + q < cnt && lane < 29) p.det_rows[((long long)b * p.A + k0 + r0 + q) * 29 + lane] = v[q];
+        }
+    }
     if (tid == 0) p.det_count[b] = s_base;
+#ifdef P24_TIMING
+    PT(6);
+    if (tid == 0 && (b == 0 || b == 7))
+        printf("ng=%d maxm=%d "
+               "nms b=%d n=%d path=%d keys %.1f sort %.1f rects %.1f groups %.1f nms %.1f out %.1f us\n", dbg_ng, dbg_maxm, b, n, path,
+               (tm[1] - tm[0]) * 1e-3, (tm[2] - tm[1]) * 1e-3, (tm[3] - tm[2]) * 1e-3, (tm[4] - tm[3]) * 1e-3,
+               (tm[5] - tm[4]) * 1e-3, (tm[6] - tm[5]) * 1e-3);
+#endif
 }
 
 }  // namespace

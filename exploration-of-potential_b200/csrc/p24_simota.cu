@@ -155,6 +155,19 @@ __global__ void __launch_bounds__(32) k_fin(const FinParams p) {
     // launched on a side stream without any stream dependency on the chain: every (value, epoch) word of every rank --
     // this rank's own included -- is polled until it carries the epoch (a one-warp kernel: it cannot keep the chain from
     // running); the values are added in rank order
+    // (the wait that is reported runs from the FIRST contribution of any rank to the last one: the skew between the ranks
+    // plus the link latency, not the time this early-launched kernel spent waiting for its own chain)
+    if (lane == 0) {
+        bool any = false;
+        while (!any) {
+            for (int r = 0; r < p.nranks && !any; ++r) {
+                volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(p.mbox + (half + r) * MBOX_SLOT);
+                any = (unsigned)(*w >> 32) == ep;
+            }
+            if (!any) __nanosleep(32);
+        }
+    }
+    __syncwarp();
     const long long t0 = clock64();
     float t = 0.0f;
     if (lane < 28) {

@@ -260,9 +260,9 @@ class Loss_Function(nn.Module):
     def read_status(self):
         """One read of the kernels' status words (they restart with every read): the rare-path counters since the
         previous read -- GTs whose dynamic k needed exact pair values / the brute-force evaluation, GTs that spilled into
-        the penalised regime, the longest and the mean top-10 candidate list -- and the microseconds the last fused
-        all-reduce of this rank waited for its peers (rank skew shows up there, link latency does not; clock64 cycles at
-        the nominal 1965 MHz).  Raises ``P24Error`` on error bits."""
+        the penalised regime, the longest and the mean top-10 candidate list -- and the microseconds between the
+        first and the last rank's contribution to the last fused all-reduce arriving at this rank (rank skew plus link
+        latency; clock64 cycles at the nominal 1965 MHz).  Raises ``P24Error`` on error bits."""
         st = self._engine.read_status()
         for key, s in st:
             if s[0]:

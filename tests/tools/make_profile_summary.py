@@ -22,7 +22,7 @@ if os.path.exists(lp):
     #          Section Name, Metric Name, Metric Unit, Metric Value
     per = collections.OrderedDict()
     for r in rows:
-        name = r[4].split("(")[0].replace("<unnamed>::", "")
+        name = r[4].split("(")[0].replace("<unnamed>::", "").replace("rows::", "").replace("rawlv::", "raw_")
         unit, val = r[-2], float(r[-1].replace(",", ""))
         us = val / 1e3 if unit in ("nsecond", "ns") else val
         per.setdefault(name, []).append(us)
@@ -55,7 +55,7 @@ if os.path.exists(rp):
                  f"batch 20 @640x640, 20 GT/img)\n")
     lines.append("| kernel | " + " | ".join(w[1] for w in want) + " |\n|" + "---|" * (len(want) + 1))
     for r in rows[2:]:
-        name = r[idx["Kernel Name"]].split("(")[0].replace("<unnamed>::", "")
+        name = r[idx["Kernel Name"]].split("(")[0].replace("<unnamed>::", "").replace("rows::", "").replace("rawlv::", "raw_")
         cells = []
         for key, _ in want:
             v = r[idx[key]] if key in idx else ""
