@@ -269,6 +269,47 @@ __global__ void __launch_bounds__(256) k_loss_bwd_raw(RawBwd r, int B, int A, in
 }
 
 // -------------------------------------------------------------------------------------------
+// label packing of the dataset's TrainTransform (datasets/data_augment.py:131-174) for a whole batch: ragged normalised
+// targets [cls, cx, cy, 24 x (x, y)] in float64 (np.loadtxt) -> labels[B, max_labels, 51] fp32 in pixels of the padded
+// input.  The reference computes in float64 (x * width_o, y * height_o, then * r_o) and casts once at the end: so does
+// this kernel, with r_o = min(in_h / h_o, in_w / w_o) in float64 like preproc (data_augment.py:104).  One thread per
+// output element; rows beyond the image's targets (and beyond max_labels) are zero.  nlabel = the count of
+// losses.py:190 ((labels.sum(dim=2) > 0).sum) of the packed rows.
+// -------------------------------------------------------------------------------------------
+__global__ void k_pack_labels(const double* __restrict__ targets, const int32_t* __restrict__ offsets,
+                              const int32_t* __restrict__ shapes, int in_h, int in_w, int B, int max_labels,
+                              float* __restrict__ labels, int32_t* __restrict__ nlabel) {
+    const int b = blockIdx.y;
+    const int n = min(offsets[b + 1] - offsets[b], max_labels);
+    const double h_o = (double)shapes[2 * b], w_o = (double)shapes[2 * b + 1];
+    const double r_o = fmin((double)in_h / h_o, (double)in_w / w_o);
+    float* out = labels + (long long)b * max_labels * 51;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < max_labels * 51; e += gridDim.x * blockDim.x) {
+        const int row = e / 51, c = e - row * 51;
+        float v = 0.0f;
+        if (row < n) {
+            const double t = targets[((long long)offsets[b] + row) * 51 + c];
+            if (c == 0) v = (float)t;
+            else v = (float)((t * (((c - 1) & 1) ? h_o : w_o)) * r_o);  // boxes[:, 0::2] *= width, [:, 1::2] *= height, then *= r
+        }
+        out[e] = v;
+    }
+    if (nlabel && blockIdx.x == 0 && threadIdx.x < 32) {
+        int cnt = 0;
+        for (int row = threadIdx.x; row < n; row += 32) {
+            float sm = 0.0f;  // torch sums the 51 floats of a row in fp32; only the sign matters here
+            for (int c = 0; c < 51; ++c) {
+                const double t = targets[((long long)offsets[b] + row) * 51 + c];
+                sm += c == 0 ? (float)t : (float)((t * (((c - 1) & 1) ? h_o : w_o)) * r_o);
+            }
+            cnt += sm > 0.0f ? 1 : 0;
+        }
+        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (threadIdx.x == 0) nlabel[b] = cnt;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // dynamic_k_matching on materialised [G, P] matrices (losses.py:444-494)
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(P24_THREADS) k_dynk_select(const float* __restrict__ cost, const float* __restrict__ ious,
@@ -452,6 +493,17 @@ extern "C" int p24_loss_bwd_raw(const float* const* h_raw, const int64_t* h_raw_
     r.off[n_levels] = A;
     k_loss_bwd_raw<<<dim3((unsigned)((A + 255) / 256), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
         r, B, A, num_classes, labels, lab_img_stride, lab_row_stride, fg_mask, matched_gt, pred_iou, weights_n27, grad_scale);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int p24_pack_labels(const double* targets, const int32_t* offsets, const int32_t* shapes_hw, int in_h, int in_w,
+                               int B, int max_labels, float* labels, int32_t* nlabel, void* stream) {
+    if (!offsets || !shapes_hw || !labels || B <= 0 || max_labels <= 0 || in_h <= 0 || in_w <= 0 || B > 65535)
+        return P24_E_BADARG;
+    // (targets may be NULL when no image of the batch has a target: every offset is 0)
+    const int per = max_labels * 51;
+    k_pack_labels<<<dim3((unsigned)((per + 255) / 256), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        targets, offsets, shapes_hw, in_h, in_w, B, max_labels, labels, nlabel);
     return (int)cudaGetLastError();
 }
 

@@ -229,15 +229,13 @@ __device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float t
 __device__ void bitonic_sort(unsigned long long* keys, int npad) {
     for (int k = 2; k <= npad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long x = keys[i], y = keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) {
-                        keys[i] = y;
-                        keys[ixj] = x;
-                    }
+            for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {  // one compare-exchange per thread and round
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
+                const unsigned long long x = keys[i], y = keys[ixj];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) {
+                    keys[i] = y;
+                    keys[ixj] = x;
                 }
             }
             __syncthreads();

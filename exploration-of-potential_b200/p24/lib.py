@@ -57,6 +57,7 @@ _PROTOS = {
     "p24_loss_bwd_raw": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
                                    C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr,
                                    c_ptr, c_ptr, c_ptr]),
+    "p24_pack_labels": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
     "p24_dynamic_k_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "p24_dynamic_k_matching": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                          c_ptr, C.c_size_t, c_ptr]),

@@ -184,6 +184,20 @@ int p24_loss_bwd_raw(const float* const* h_raw, const int64_t* h_raw_batch_strid
                      const uint8_t* fg_mask, const int32_t* matched_gt, const float* pred_iou,
                      const float* weights_n27, const float* grad_scale, void* stream);
 
+/* Label packing of the dataset transform for a whole batch (TrainTransform.__call__, datasets/data_augment.py:131-174;
+ * the wire format COCO24PDataset.__getitem__ hands to the loss, datasets/coco24p.py:107-131).
+ *   targets    DEVICE float64 [sum_b n_b, 51]: the images' label-file rows [cls, cx, cy, 24 x (x, y)], normalised to
+ *              [0, 1] (np.loadtxt), image after image (may be NULL when the batch has no target at all)
+ *   offsets    DEVICE int32 [B + 1]: first row of image b (offsets[B] = total)
+ *   shapes_hw  DEVICE int32 [B, 2]: (height, width) of the RESIZED, unpadded image the transform receives
+ *   in_h, in_w the padded network input (input_dim)
+ *   labels     DEVICE fp32 [B, max_labels, 51], fully overwritten: pixel coordinates x * width * r, y * height * r with
+ *              r = min(in_h / height, in_w / width), computed in float64 and cast once like the reference; rows past
+ *              the image's targets are zero, targets past max_labels are dropped
+ *   nlabel     DEVICE int32 [B] or NULL: rows with a positive sum (models/losses.py:190) */
+int p24_pack_labels(const double* targets, const int32_t* offsets, const int32_t* shapes_hw, int in_h, int in_w,
+                    int B, int max_labels, float* labels, int32_t* nlabel, void* stream);
+
 /* Loss_Function.dynamic_k_matching (models/losses.py:444-494) on a materialised cost matrix.
  * cost, ious: dense [G, P];  fg_in [P] uint8, matched [P] int32 (-1 when not fg), matched_iou [P] fp32,
  * dyn_k [G] int32, num_fg [1] int32.  torch.topk leaves tie order unspecified; ties go to the lower index here. */

@@ -97,3 +97,14 @@ def test_head_decode_matches_reference_fixture():
     mx, my, ms = synth.make_grids(int(g["img_size"]))
     assert all(torch.equal(a, b) for a, b in zip(xs + ys + ss, mx + my + ms))
     np.testing.assert_allclose(orc.head_decode_infer(reg, obj, cls, list(synth.STRIDES)).numpy(), g["infer"], rtol=RTOL, atol=0)
+
+
+def test_label_packing_matches_reference_fixture():
+    """oracle.pack_labels against the reference-made fixture (TrainTransform, datasets/data_augment.py:131-174):
+    float64 arithmetic cast once to fp32 -> bit-exact on every host."""
+    g = _load("pack_labels.npz")
+    off = 0
+    for i, (n, hw) in enumerate(zip(g["counts"].tolist(), g["shapes"].tolist())):
+        t = g["targets"][off:off + n] if n else np.zeros((1, 0))
+        off += n
+        assert np.array_equal(orc.pack_labels(t, tuple(hw), (640, 640), 50), g[f"labels{i}"])

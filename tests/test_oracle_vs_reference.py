@@ -76,3 +76,30 @@ def test_head_decode_bit_equal():
     pred = torch.cat([x.flatten(start_dim=2) for x in flat], dim=2).permute(0, 2, 1)
     want = head.decode_outputs(me, pred, dtype="torch.FloatTensor")
     assert torch.equal(orc.head_decode_infer(reg, obj, cls, strides), want)
+
+
+def _ref_train_transform():
+    """The reference's datasets/data_augment.py imported as a stand-alone file (the package __init__ needs pycocotools)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_data_augment", "/root/reference/yolox_24p/datasets/data_augment.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.TrainTransform
+
+
+def test_label_packing_bit_equal():
+    """oracle.pack_labels against TrainTransform.__call__ of the reference (datasets/data_augment.py:131-174): ragged
+    counts, more targets than max_labels, an empty label file, non-square images."""
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")  # the reference resizes the image in the same call
+    TT = _ref_train_transform()
+    rng = np.random.default_rng(5)
+    for n, (h, w), max_labels in [(7, (480, 640), 50), (60, (640, 427), 50), (1, (333, 500), 10), (0, (640, 640), 50)]:
+        img = np.zeros((h, w, 3), dtype=np.uint8)
+        if n:
+            t = np.concatenate([rng.integers(0, 80, (n, 1)).astype(np.float64), rng.random((n, 50))], 1)
+        else:
+            t = np.zeros((0,))[np.newaxis, :]   # what pull_item yields for an empty label file (coco24p.py:84-85)
+        _, want = TT(max_labels=max_labels)(img, t.copy(), [640, 640])
+        got = orc.pack_labels(t, (h, w), (640, 640), max_labels)
+        assert want.dtype == got.dtype and np.array_equal(want, got)

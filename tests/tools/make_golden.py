@@ -176,7 +176,31 @@ def head_case(ref_models, name, img_size, B, seed):
     print(f"head_{name}: train {tuple(train.shape)} infer {tuple(infer.shape)}")
 
 
+def pack_case():
+    """Label packing (datasets/data_augment.py:131-174): the reference's TrainTransform on seeded ragged targets."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_data_augment", "/root/reference/yolox_24p/datasets/data_augment.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(11)
+    cases = [(7, (480, 640)), (60, (640, 427)), (1, (333, 500)), (0, (640, 640)), (50, (640, 640))]
+    rec = {"counts": np.array([c[0] for c in cases]), "shapes": np.array([c[1] for c in cases])}
+    flat = []
+    for i, (n, (h, w)) in enumerate(cases):
+        t = np.concatenate([rng.integers(0, 80, (n, 1)).astype(np.float64), rng.random((n, 50))], 1) if n else np.zeros((1, 0))
+        _, want = mod.TrainTransform(max_labels=50)(np.zeros((h, w, 3), dtype=np.uint8), t.copy(), [640, 640])
+        assert np.array_equal(orc.pack_labels(t, (h, w), (640, 640), 50), want)
+        rec[f"labels{i}"] = want
+        flat.append(t if n else np.zeros((0, 51)))
+    rec["targets"] = np.concatenate(flat, 0)
+    np.savez_compressed(os.path.join(GOLD, "pack_labels.npz"), **rec)
+    print("pack_labels:", rec["counts"].tolist())
+
+
 def main():
+    if sys.argv[1:] == ["pack"]:
+        pack_case()
+        return
     if sys.argv[1:] == ["head"]:   # only the head-decode fixture (the others stay byte-identical)
         head_case(load_reference()[0], "s64", 64, 2, 21)
         return
@@ -196,6 +220,7 @@ def main():
     post_case(ref_utils, "s256", 256, 2, 3,
               [(0.25, 0.45, False), (0.01, 0.65, False), (0.01, 0.3, True), (0.99, 0.45, False)])
     head_case(ref_models, "s64", 64, 2, 21)
+    pack_case()
 
 
 if __name__ == "__main__":
