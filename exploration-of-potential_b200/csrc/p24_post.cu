@@ -21,6 +21,7 @@
 // compiled with -fmad=false), the sort is stable, and batched NMS adds  class * (max_coordinate + 1)  to the boxes in
 // fp32 exactly like _batched_nms_coordinate_trick.
 #include <stdio.h>
+#include <string.h>
 
 #include "p24_common.cuh"
 #include "p24_host.h"
@@ -59,7 +60,26 @@ struct PostParams {
     float4* c_srect; // [B, A]   the sorted rectangles again, in cell order (coalesced reads of a cell)
     int tiles;
     int npad_global;
+    // raw head outputs (pred == NULL): per level reg [B,26,H,W], obj [B,1,H,W], cls [B,nc,H,W] before the sigmoid / decode of
+    // YOLOXHead.forward(train=False) + decode_outputs (models/yolo_head_24p.py:191, 201-211, 239-256)
+    const float* raw[3][4];
+    long long raw_bs[3][4];
+    int nlev;
+    int lev_off[5], lev_w[4];
+    float lev_st[4];
 };
+
+// the decoded prediction value of channel c in [0, 27) of anchor a, from the raw planes
+__device__ __forceinline__ float raw_pred(const PostParams& p, int b, int a, int c) {
+    int l = 0;
+    for (int q = 1; q < p.nlev; ++q) l += a >= p.lev_off[q] ? 1 : 0;
+    const int i = a - p.lev_off[l];
+    const long long plane = p.lev_off[l + 1] - p.lev_off[l];
+    if (c == 26) return p24_sigmoid(p.raw[1][l][b * p.raw_bs[1][l] + i]);
+    const float v = p.raw[0][l][b * p.raw_bs[0][l] + c * plane + i];
+    if (c >= 2) return expf(v) * p.lev_st[l];                                     // outputs[..., 2:26] = exp(.) * strides
+    return (v + (float)(c == 0 ? i % p.lev_w[l] : i / p.lev_w[l])) * p.lev_st[l];  // outputs[..., :2] = (. + grids) * strides
+}
 
 struct PostWorkspace {
     size_t tcount, c_score, c_conf, c_anchor, c_cls, c_rect, s_rect, g_keys, s_order, s_cell, c_srect, total;
@@ -189,6 +209,96 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_filter(PostParams p) {
         }
     }
     // ---- ordered compaction of the tile's candidates -----------------------------------------------------------
+    const unsigned bal = __ballot_sync(0xffffffffu, cand);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < POST_WARPS; ++w) {
+        const int c = s_wcnt[w];
+        base += (w < warp) ? c : 0;
+        total += c;
+    }
+    const long long blk = (long long)b * p.tiles + tile;
+    if (cand) {
+        const long long o = blk * POST_THREADS + base + __popc(bal & ((1u << lane) - 1u));
+        p.c_score[o] = score;
+        p.c_conf[o] = conf;
+        p.c_anchor[o] = a;
+        p.c_cls[o] = cls;
+        p.c_rect[o] = rect;
+    }
+    if (tid == 0) p.tcount[blk] = total;
+}
+
+// -------------------------------------------------------------------------------------------
+// k_post_filter_raw: the same pass on the head's RAW conv outputs.  One thread per anchor: 32 consecutive anchors of a
+// level are 32 consecutive floats of every channel plane, so the planar loads are coalesced.  obj / cls sigmoids and the
+// centre / radius decode happen on load, bit for bit like torch (1 / (1 + exp(-x)), (v + grid) * stride, exp(v) * stride).
+// class_conf = max_j sigmoid(cls_j), first maximum on ties: the sigmoid is only evaluated for a class whose LOGIT comes
+// within a margin of the running best (a smaller logit cannot have a larger sigmoid; equal sigmoids of different logits
+// -- the flat ends -- keep the first index because the comparison itself is made on the sigmoids).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(POST_THREADS) k_post_filter_raw(PostParams p) {
+    __shared__ int s_wcnt[POST_WARPS];
+    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int a = tile * POST_THREADS + tid;
+    const bool active = a < p.A;
+    bool cand = false;
+    float score = 0.f, conf = 0.f;
+    int cls = 0;
+    float4 rect = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        int l = 0;
+        for (int q = 1; q < p.nlev; ++q) l += a >= p.lev_off[q] ? 1 : 0;
+        const int i = a - p.lev_off[l];
+        const long long plane = p.lev_off[l + 1] - p.lev_off[l];
+        const float* pc = p.raw[2][l] + b * p.raw_bs[2][l] + i;
+        const float obj = p24_sigmoid(p.raw[1][l][b * p.raw_bs[1][l] + i]);
+        float xbest = pc[0];
+        conf = p24_sigmoid(xbest);
+        for (int j0 = 1; j0 < p.nc; j0 += 8) {
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = (j0 + q < p.nc) ? pc[(long long)(j0 + q) * plane] : -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (j0 + q >= p.nc) break;
+                const float xv = x[q];
+                if (!(xv < xbest - (1e-4f * fabsf(xbest) + 1e-6f))) {  // (also taken for NaN)
+                    const float v = p24_sigmoid(xv);
+                    if (v > conf || (v != v && conf == conf)) {  // torch.max: first maximum on ties, NaN wins
+                        conf = v;
+                        cls = j0 + q;
+                        xbest = xv;
+                    }
+                }
+            }
+        }
+        score = obj * conf;              // boxes.py:55, 78
+        cand = score >= p.conf_thre;
+        if (cand) {
+            const float* pr = p.raw[0][l] + b * p.raw_bs[0][l] + i;
+            const float st = p.lev_st[l];
+            float v[26];
+#pragma unroll
+            for (int c = 0; c < 26; ++c) v[c] = pr[(long long)c * plane];
+            const float cx = (v[0] + (float)(i % p.lev_w[l])) * st, cy = (v[1] + (float)(i / p.lev_w[l])) * st;
+            float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < P24_RAYS; ++k) {
+                const float r = expf(v[2 + k]) * st;
+                const float px = (r * p.coef_x[k]) + cx;  // boxes.py:67-68 (sic: theta * cos theta)
+                const float py = (r * p.coef_y[k]) + cy;
+                x0 = fminf(x0, px);
+                x1 = fmaxf(x1, px);
+                y0 = fminf(y0, py);
+                y1 = fmaxf(y1, py);
+            }
+            rect = make_float4(x0, y0, x1, y1);
+        }
+    }
     const unsigned bal = __ballot_sync(0xffffffffu, cand);
     if (lane == 0) s_wcnt[warp] = __popc(bal);
     __syncthreads();
@@ -848,8 +958,12 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
                 const int r = min(r0 + q, cnt - 1);
                 const int ar = __shfl_sync(0xffffffffu, a, r);
                 const float cr = __shfl_sync(0xffffffffu, conf, r), lr = __shfl_sync(0xffffffffu, clsf, r);
-                const float* row = p.pred + (long long)b * p.img_stride + (long long)ar * p.row_stride;
-                v[q] = lane < 27 ? row[lane] : (lane == 27 ? cr : lr);
+                if (p.pred) {
+                    const float* row = p.pred + (long long)b * p.img_stride + (long long)ar * p.row_stride;
+                    v[q] = lane < 27 ? row[lane] : (lane == 27 ? cr : lr);
+                } else {
+                    v[q] = lane < 27 ? raw_pred(p, b, ar, lane) : (lane == 27 ? cr : lr);
+                }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -874,12 +988,14 @@ extern "C" size_t p24_postprocess_workspace_bytes(int B, int A) {
     return post_layout(B, A).total;
 }
 
-extern "C" int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_stride, int B, int A,
-                               int num_classes, const float* h_coef_x, const float* h_coef_y, float conf_thre,
-                               float nms_thre, int class_agnostic, int32_t* cand_count, int32_t* det_count,
-                               float* det_rows, int32_t* keep_idx, float* rect_debug, void* workspace,
-                               size_t workspace_bytes, void* stream) {
-    if (!prediction || !h_coef_x || !h_coef_y || !cand_count || !det_count || !det_rows || !keep_idx || !workspace)
+namespace {
+int post_impl(const float* prediction, int64_t img_stride, int64_t row_stride, const float* const* h_raw,
+              const int64_t* h_raw_bs, const int32_t* h_levels, int n_levels, int B, int A,
+              int num_classes, const float* h_coef_x, const float* h_coef_y, float conf_thre,
+              float nms_thre, int class_agnostic, int32_t* cand_count, int32_t* det_count,
+              float* det_rows, int32_t* keep_idx, float* rect_debug, void* workspace,
+              size_t workspace_bytes, void* stream) {
+    if ((!prediction && !h_raw) || !h_coef_x || !h_coef_y || !cand_count || !det_count || !det_rows || !keep_idx || !workspace)
         return P24_E_BADARG;
     if (B <= 0 || A <= 0 || num_classes <= 0) return P24_E_BADARG;
     if (((uintptr_t)workspace & 255) != 0) return P24_E_BADARG;
@@ -889,9 +1005,30 @@ extern "C" int p24_postprocess(const float* prediction, int64_t img_stride, int6
     if (tiles > 1024) return P24_E_UNSUPPORTED;
     const int C = 27 + num_classes;
     const size_t smem_filter = (size_t)POST_WARPS * 32 * C * sizeof(float);
-    if (smem_filter > 200 * 1024) return P24_E_UNSUPPORTED;
+    if (prediction && smem_filter > 200 * 1024) return P24_E_UNSUPPORTED;
     char* ws = (char*)workspace;
     PostParams p;
+    memset(&p, 0, sizeof(p));
+    if (!prediction) {
+        if (!h_raw_bs || !h_levels || n_levels < 1 || n_levels > 4) return P24_E_BADARG;
+        int total = 0;
+        p.nlev = n_levels;
+        for (int l = 0; l < n_levels; ++l) {
+            const int off = h_levels[4 * l], W = h_levels[4 * l + 1], H = h_levels[4 * l + 2];
+            if (off != total || W <= 0 || H <= 0) return P24_E_BADARG;
+            p.lev_off[l] = off;
+            p.lev_w[l] = W;
+            memcpy(&p.lev_st[l], &h_levels[4 * l + 3], sizeof(float));
+            total += W * H;
+            for (int t = 0; t < 3; ++t) {
+                p.raw[t][l] = h_raw[t * n_levels + l];
+                p.raw_bs[t][l] = h_raw_bs[t * n_levels + l];
+                if (!p.raw[t][l]) return P24_E_BADARG;
+            }
+        }
+        if (total != A) return P24_E_BADARG;
+        p.lev_off[n_levels] = A;
+    }
     p.pred = prediction; p.img_stride = img_stride; p.row_stride = row_stride;
     p.B = B; p.A = A; p.nc = num_classes; p.C = C;
     for (int k = 0; k < P24_RAYS; ++k) {
@@ -922,9 +1059,33 @@ extern "C" int p24_postprocess(const float* prediction, int64_t img_stride, int6
         cudaFuncSetAttribute(k_post_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_MAX * 8);
     }
     p24::prof_mark(4, st);
-    k_post_filter<<<dim3(tiles, B), POST_THREADS, smem_filter, st>>>(p);
+    if (prediction) k_post_filter<<<dim3(tiles, B), POST_THREADS, smem_filter, st>>>(p);
+    else k_post_filter_raw<<<dim3(tiles, B), POST_THREADS, 0, st>>>(p);
     p24::prof_mark(5, st);
     k_post_nms<<<B, NMS_THREADS, smem_nms, st>>>(p);
     p24::prof_mark(6, st);
     return (int)cudaGetLastError();
+}
+}  // namespace
+
+extern "C" int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_stride, int B, int A,
+                               int num_classes, const float* h_coef_x, const float* h_coef_y, float conf_thre,
+                               float nms_thre, int class_agnostic, int32_t* cand_count, int32_t* det_count,
+                               float* det_rows, int32_t* keep_idx, float* rect_debug, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!prediction) return P24_E_BADARG;
+    return post_impl(prediction, img_stride, row_stride, nullptr, nullptr, nullptr, 0, B, A, num_classes, h_coef_x, h_coef_y,
+                     conf_thre, nms_thre, class_agnostic, cand_count, det_count, det_rows, keep_idx, rect_debug, workspace,
+                     workspace_bytes, stream);
+}
+
+extern "C" int p24_postprocess_raw(const float* const* h_raw, const int64_t* h_raw_batch_stride, const int32_t* h_levels,
+                                   int n_levels, int B, int A, int num_classes, const float* h_coef_x, const float* h_coef_y,
+                                   float conf_thre, float nms_thre, int class_agnostic, int32_t* cand_count,
+                                   int32_t* det_count, float* det_rows, int32_t* keep_idx, float* rect_debug, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    if (!h_raw) return P24_E_BADARG;
+    return post_impl(nullptr, 0, 0, h_raw, h_raw_batch_stride, h_levels, n_levels, B, A, num_classes, h_coef_x, h_coef_y,
+                     conf_thre, nms_thre, class_agnostic, cand_count, det_count, det_rows, keep_idx, rect_debug, workspace,
+                     workspace_bytes, stream);
 }

@@ -49,13 +49,23 @@ def postprocess_raw(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, class
     rects[B, A, 4] | None).  No host synchronisation.  ``coef``: (coef_x[24], coef_y[24]) host fp32 tensors overriding the
     coefficients evaluated on the prediction's device (tests against CPU-made fixtures pass the CPU ones)."""
     lib = _lib.load()
-    _check_cuda_f32(prediction, "prediction")
-    if prediction.dim() != 3 or prediction.shape[2] != 27 + num_classes:
-        raise IndexError("prediction must be [B, A, 27 + num_classes]")
-    if prediction.stride(2) != 1:
-        prediction = prediction.contiguous()
-    B, A, _ = prediction.shape
-    dev = prediction.device
+    from .engine import RawLevels
+    raw = isinstance(prediction, RawLevels)
+    if raw:
+        # the head's raw conv outputs (p24.head.infer_outputs): sigmoid + decode happen inside the filter pass
+        if prediction.num_classes != num_classes:
+            raise IndexError("raw cls tensors must have num_classes channels")
+        planes, plane_bs = prediction.planes()
+        lv, nlev = prediction.level_table()
+        B, A, dev = prediction.batch, prediction.num_anchors, prediction.device
+    else:
+        _check_cuda_f32(prediction, "prediction")
+        if prediction.dim() != 3 or prediction.shape[2] != 27 + num_classes:
+            raise IndexError("prediction must be [B, A, 27 + num_classes]")
+        if prediction.stride(2) != 1:
+            prediction = prediction.contiguous()
+        B, A, _ = prediction.shape
+        dev = prediction.device
     cand = torch.empty(B, dtype=torch.int32, device=dev)
     cnt = torch.empty(B, dtype=torch.int32, device=dev)
     rows = torch.empty((B, A, 29), dtype=torch.float32, device=dev)
@@ -67,13 +77,17 @@ def postprocess_raw(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, class
     cxp = cx.numpy().ctypes.data_as(C.POINTER(C.c_float))
     cyp = cy.numpy().ctypes.data_as(C.POINTER(C.c_float))
     # the reference compares fp32 tensors with Python floats: the scalars are rounded to fp32 (boxes.py:55)
+    tail = (B, A, num_classes, cxp, cyp, float(np.float32(conf_thre)), float(np.float32(nms_thre)),
+            1 if class_agnostic else 0, cand.data_ptr(), cnt.data_ptr(), rows.data_ptr(),
+            keep.data_ptr(), rects.data_ptr() if rects is not None else None, ws_ptr, nbytes, _stream_ptr(dev))
     with torch.cuda.device(dev):
-        code = lib.p24_postprocess(prediction.data_ptr(), prediction.stride(0), prediction.stride(1), B, A, num_classes,
-                                   cxp, cyp, float(np.float32(conf_thre)), float(np.float32(nms_thre)),
-                                   1 if class_agnostic else 0, cand.data_ptr(), cnt.data_ptr(), rows.data_ptr(),
-                                   keep.data_ptr(), rects.data_ptr() if rects is not None else None,
-                                   ws_ptr, nbytes, _stream_ptr(dev))
-    _lib.check(code, "p24_postprocess")
+        if raw:
+            n = len(planes)
+            code = lib.p24_postprocess_raw((C.c_void_p * n)(*[t.data_ptr() for t in planes]), (C.c_int64 * n)(*plane_bs),
+                                           lv, nlev, *tail)
+        else:
+            code = lib.p24_postprocess(prediction.data_ptr(), prediction.stride(0), prediction.stride(1), *tail)
+    _lib.check(code, "p24_postprocess_raw" if raw else "p24_postprocess")
     return cand, cnt, rows, keep, rects
 
 
@@ -81,10 +95,12 @@ def postprocess(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, class_agn
     """``utils.boxes.postprocess``: list of B entries, ``Tensor[n_i, 29]`` (rows ``[cx, cy, r0..r23, obj, class_conf,
     class_pred]`` in NMS order) or ``None``.  For B >= 2 the reference itself raises (boxes.py:64-65); this returns
     the per-image result for each image."""
-    if prediction.shape[0] == 0:
-        return []
-    if prediction.shape[1] == 0:
-        return [None for _ in range(len(prediction))]
+    from .engine import RawLevels
+    if not isinstance(prediction, RawLevels):
+        if prediction.shape[0] == 0:
+            return []
+        if prediction.shape[1] == 0:
+            return [None for _ in range(len(prediction))]
     _, cnt, rows, _, _ = postprocess_raw(prediction, num_classes, conf_thre, nms_thre, class_agnostic)
     counts = cnt.tolist()  # the one host read (the reference returns a Python list)
     return [rows[i, :n].clone() if n else None for i, n in enumerate(counts)]

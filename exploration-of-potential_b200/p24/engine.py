@@ -27,8 +27,10 @@ class RawLevels:
     permute / reshape copies of ``YOLOXHead.forward(train=True)`` never happen.  Channel slices of one concatenated
     ``[B, 27 + nc, H, W]`` tensor are fine (only the H x W planes must be dense)."""
 
-    def __init__(self, reg, obj, cls):
+    def __init__(self, reg, obj, cls, strides=None):
         self.reg, self.obj, self.cls = list(reg), list(obj), list(cls)
+        # (the loss takes the strides from the grid lists of the 5-tuple; the postprocess needs them here)
+        self.strides = None if strides is None else [float(s) for s in strides]
         if not (len(self.reg) == len(self.obj) == len(self.cls)) or not self.reg:
             raise IndexError("RawLevels needs reg / obj / cls tensors for the same levels")
         for k, (r, o, c) in enumerate(zip(self.reg, self.obj, self.cls)):
@@ -54,6 +56,18 @@ class RawLevels:
 
     def requires_grad(self):
         return any(t.requires_grad for lst in (self.reg, self.obj, self.cls) for t in lst)
+
+    def level_table(self):
+        """HOST (anchor offset, W, H, stride bits) per level, as the C ABI takes it."""
+        import struct
+        if self.strides is None or len(self.strides) != len(self.reg):
+            raise IndexError("RawLevels needs one stride per level here")
+        lv, off = [], 0
+        for r, s in zip(self.reg, self.strides):
+            H, W = r.shape[2], r.shape[3]
+            lv += [off, W, H, struct.unpack("<i", struct.pack("<f", s))[0]]
+            off += H * W
+        return (C.c_int32 * len(lv))(*lv), len(self.reg)
 
     def planes(self):
         """(tensor list in ABI order, batch strides): every tensor with dense H x W planes and channel stride H * W."""

@@ -56,3 +56,22 @@ def train_outputs(reg: Sequence[torch.Tensor], obj: Sequence[torch.Tensor], cls:
         out[..., 2:26] = torch.exp(out[..., 2:26]) * s                         # :235
         outs.append(out)
     return xs, ys, ss, torch.cat(outs, 1), []
+
+
+def infer_outputs(reg: Sequence[torch.Tensor], obj: Sequence[torch.Tensor], cls: Sequence[torch.Tensor],
+                  strides: Sequence[float] = (8, 16, 32), fused: bool = True):
+    """The tail of ``YOLOXHead.forward(train=False)`` (``yolo_head_24p.py:191, 201-211``) + ``decode_outputs``
+    (``:239-256``).  ``fused=True``: the raw conv outputs wrapped for ``p24.boxes.postprocess`` (sigmoid and decode happen
+    inside its filter pass, the decoded ``[B, A, 27 + nc]`` prediction is never written); ``fused=False``: the reference's
+    torch ops, returning that prediction."""
+    if fused:
+        return RawLevels(reg, obj, cls, strides=strides)
+    outs = [torch.cat([r, o.sigmoid(), c.sigmoid()], 1) for r, o, c in zip(reg, obj, cls)]
+    shapes = [tuple(x.shape[-2:]) for x in outs]
+    outputs = torch.cat([x.flatten(start_dim=2) for x in outs], dim=2).permute(0, 2, 1)
+    xs, ys, ss = level_grids(shapes, strides, outputs.device)
+    grids = torch.stack((torch.cat(xs, 1), torch.cat(ys, 1)), 2)
+    st = torch.cat(ss, 1).unsqueeze(-1)
+    outputs[..., :2] = (outputs[..., :2] + grids) * st
+    outputs[..., 2:26] = torch.exp(outputs[..., 2:26]) * st
+    return outputs

@@ -65,6 +65,10 @@ _PROTOS = {
     "p24_postprocess": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int,
                                   c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "p24_postprocess_raw": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int,
+                                      C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int,
+                                      c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "p24_read_status": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), c_ptr]),
     "p24_profile_enable": (C.c_int, [C.c_int]),
     "p24_profile_read": (C.c_int, [C.POINTER(C.c_float)]),

@@ -223,6 +223,17 @@ int p24_postprocess(const float* prediction, int64_t img_stride, int64_t row_str
                     int32_t* cand_count, int32_t* det_count, float* det_rows, int32_t* keep_idx, float* rect_debug,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same on the head's RAW per-level conv outputs (YOLOXHead.forward(train=False) after the prediction convs:
+ * sigmoid on obj / cls, flatten + cat + permute, decode_outputs, models/yolo_head_24p.py:191, 201-211, 239-256 -- folded
+ * into the filter pass; the decoded [B, A, 27+nc] prediction is never written).  h_raw / h_raw_batch_stride / h_levels as
+ * for p24_simota_loss_batch_raw (reg [B,26,H,W], obj [B,1,H,W], cls [B,nc,H,W] logits per level).  det_rows carry the
+ * decoded [cx, cy, r0..r23, sigmoid(obj)] like the reference's rows. */
+int p24_postprocess_raw(const float* const* h_raw, const int64_t* h_raw_batch_stride, const int32_t* h_levels,
+                        int n_levels, int B, int A, int num_classes, const float* h_coef_x, const float* h_coef_y,
+                        float conf_thre, float nms_thre, int class_agnostic, int32_t* cand_count,
+                        int32_t* det_count, float* det_rows, int32_t* keep_idx, float* rect_debug, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* Status of a workspace, read back to the HOST (one small device-to-host copy + a synchronisation of `stream`):
  *   h_status8[0]  error bits (P24_ERR_*), sticky; 0 = none.  The reference raises on its failures (losses.py:81-82); the
  *                 Python host side raises P24Error when a bit is set

@@ -132,3 +132,28 @@ def test_raw_levels_backward_matches_autograd_through_torch_decode():
         scale = float(oracle.grad.abs().max()) + 1e-12
         torch.testing.assert_close(mine.grad, viarows.grad, rtol=1e-5, atol=scale * 1e-6)
         torch.testing.assert_close(mine.grad, oracle.grad, rtol=1e-4, atol=scale * 2e-6)
+
+
+@pytest.mark.parametrize("conf,nms,agnostic", [(0.25, 0.45, False), (0.01, 0.3, True), (0.01, 0.65, False)])
+def test_raw_levels_postprocess_vs_oracle_decode(conf, nms, agnostic):
+    """Inference side of the fusion: postprocess on the raw conv outputs (sigmoid + decode inside the filter pass)
+    against (1) this library's postprocess on the oracle-decoded prediction (yolo_head_24p.py:191, 201-211, 239-256) and
+    (2) the oracle postprocess of that prediction: rows, order and counts bit for bit."""
+    from p24 import boxes as p24_boxes
+    from p24 import head as p24_head
+    reg, obj, cls = _levels(4, 320, 80, 33)
+    for t in obj + cls:  # raise the scores into the interesting range (the synthetic logits sit at the prior)
+        t += 4.5
+    pred = orc.head_decode_infer(reg, obj, cls, list(synth.STRIDES))
+    fused = p24_boxes.postprocess(p24_head.infer_outputs(reg, obj, cls, synth.STRIDES), 80, conf, nms, agnostic)
+    plain = p24_boxes.postprocess(pred, 80, conf, nms, agnostic)
+    assert torch.equal(p24_head.infer_outputs(reg, obj, cls, synth.STRIDES, fused=False), pred)
+    nonempty = 0
+    for i in range(4):
+        want = orc.postprocess_image(pred[i], 80, conf, nms, agnostic)
+        for got in (fused[i], plain[i]):
+            assert (got is None) == (want is None or want.shape[0] == 0)
+            if got is not None:
+                assert torch.equal(got, want), f"image {i}"
+                nonempty += 1
+    assert nonempty > 0
