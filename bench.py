@@ -428,6 +428,64 @@ def bench_head_fusion(ctx, steps, warmup):
             "algorithmic_bytes_per_step": alg}
 
 
+def bench_post_fusion(ctx, steps, warmup):
+    """SURVEY.md 8f row 2, inference side: postprocess on the head's RAW conv outputs (sigmoid + decode inside the
+    filter pass) against the reference's way (torch sigmoid / cat / permute / decode passes, then the postprocess on the
+    decoded prediction).  configs[3] shapes (batch 64 at 640x640), conf 0.25 / nms 0.45 batched."""
+    from p24 import boxes as p24_boxes
+    from p24 import head as p24_head
+    from p24 import synth
+    B, size = 64, 640
+    A = sum((size // s) ** 2 for s in (8, 16, 32))
+    raws = []
+    for i in range(2):  # 2 x 230 MB > 126 MiB L2
+        r, o, c = synth.make_raw_levels(B, size, 80, seed=3 + 100 * i, device=ctx.dev)
+        for t in o + c:
+            t += 3.6   # (scores reach the 0.25 threshold for a few hundred anchors per image)
+        raws.append((r, o, c))
+    out = {}
+    for mode in ("fused", "unfused"):
+        def step(i):
+            r, o, c = raws[i % 2]
+            return p24_boxes.postprocess_raw(p24_head.infer_outputs(r, o, c, synth.STRIDES, fused=(mode == "fused")),
+                                             80, 0.25, 0.45, False)
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            res = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[mode] = {"ms_per_step": ms, "value": B / (ms * 1e-3), "kept_check": int(res[1].sum())}
+        if mode == "fused":
+            from p24 import lib as p24_lib
+            ctx.lib.p24_profile_enable(1)
+            buf = (ctypes.c_float * 8)()
+            acc = {k: 0.0 for k in POST_STAGES}
+            for i in range(5):
+                step(i)
+                p24_lib.check(ctx.lib.p24_profile_read(buf), "p24_profile_read")
+                for k in POST_STAGES:
+                    acc[k] += buf[k]
+            ctx.lib.p24_profile_enable(0)
+            out[mode]["kernel_ms"] = {POST_STAGES[k].replace("filter", "filter_raw"): v / 5 for k, v in acc.items()}
+    alg = A * 107 * 4 * B
+    peak, _ = measured_peak()
+    return {"metric": "postprocess_images_per_sec_from_raw_head_outputs", "unit": "images/s",
+            "config": {"workload": f"configs[3] shapes, inputs = raw per-level conv outputs (batch {B}, {A} anchors), "
+                                   "conf 0.25 / nms 0.45 batched", "l2": "inputs rotate over 2 distinct batches (460 MB)"},
+            "value": out["fused"]["value"], "ms_per_step": out["fused"]["ms_per_step"],
+            "kernel_ms": out["fused"]["kernel_ms"],
+            "unfused_torch_decode_then_postprocess": out["unfused"],
+            "speedup_vs_unfused": out["unfused"]["ms_per_step"] / out["fused"]["ms_per_step"],
+            "kept_equal": out["fused"]["kept_check"] == out["unfused"]["kept_check"],
+            "whole_step_frac_of_hbm_peak": (alg / (out["fused"]["ms_per_step"] * 1e-3) / 1e9) / peak,
+            "algorithmic_bytes_per_step": alg}
+
+
 def allreduce_check(ctx, dset, grids):
     """N > 1: the fused peer-memory exchange against NCCL + finalize on the same shard (first batch): the loss must be
     bit-identical on all ranks in both modes, and the two modes must agree to fp32 rounding of the 28-float sums."""
@@ -558,7 +616,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--only", default=None, help="comma list of blocks to run beside nothing else: "
-                    "train,train_spiky,crowded,hires,train_raw,postprocess (default: headline + all extras)")
+                    "train,train_spiky,crowded,hires,train_raw,postprocess,post_raw (default: headline + all extras)")
     ap.add_argument("--workload", default=None, help="(compat) same as --only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -588,7 +646,7 @@ def main():
     ctx.lfs = []
     only = args.only or args.workload
     blocks = only.split(",") if only else (["train"] if args.no_extras else
-                                           ["train", "train_spiky", "crowded", "hires", "train_raw", "postprocess"])
+                                           ["train", "train_spiky", "crowded", "hires", "train_raw", "postprocess", "post_raw"])
     want_cpu, want_e2e = not args.no_cpu_baseline, not args.no_e2e
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("P24_NO_CLOCK_SAMPLER"):
@@ -612,6 +670,9 @@ def main():
         elif bname == "train_raw":
             if world == 1:   # (a single-GPU comparison: the sharded path is the same chain)
                 results["train_raw"] = bench_head_fusion(ctx, max(5, args.steps // 2), args.warmup)
+        elif bname == "post_raw":
+            if world == 1:
+                results["post_raw"] = bench_post_fusion(ctx, max(5, args.steps // 2), args.warmup)
         elif bname == "postprocess":
             k = max(5, args.steps // 2)
             results["postprocess"] = {lab: bench_post(ctx, lab, c, n, a, k, args.warmup, want_e2e, want_cpu)

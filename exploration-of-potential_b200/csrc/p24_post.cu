@@ -258,12 +258,12 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_filter_raw(PostParams p) 
         const float obj = p24_sigmoid(p.raw[1][l][b * p.raw_bs[1][l] + i]);
         float xbest = pc[0];
         conf = p24_sigmoid(xbest);
-        for (int j0 = 1; j0 < p.nc; j0 += 8) {
-            float x[8];
+        for (int j0 = 1; j0 < p.nc; j0 += 16) {
+            float x[16];  // sixteen planes in flight per thread (the prediction is read once: streaming loads)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) x[q] = (j0 + q < p.nc) ? pc[(long long)(j0 + q) * plane] : -INFINITY;
+            for (int q = 0; q < 16; ++q) x[q] = (j0 + q < p.nc) ? __ldcs(pc + (long long)(j0 + q) * plane) : -INFINITY;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 16; ++q) {
                 if (j0 + q >= p.nc) break;
                 const float xv = x[q];
                 if (!(xv < xbest - (1e-4f * fabsf(xbest) + 1e-6f))) {  // (also taken for NaN)
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_filter_raw(PostParams p) 
             const float st = p.lev_st[l];
             float v[26];
 #pragma unroll
-            for (int c = 0; c < 26; ++c) v[c] = pr[(long long)c * plane];
+            for (int c = 0; c < 26; ++c) v[c] = __ldcs(pr + (long long)c * plane);
             const float cx = (v[0] + (float)(i % p.lev_w[l])) * st, cy = (v[1] + (float)(i / p.lev_w[l])) * st;
             float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
 #pragma unroll
