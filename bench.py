@@ -255,10 +255,15 @@ def bench_train(ctx, name, steps, warmup, allreduce, want_e2e=True, want_cpu=Tru
     dsets = [(o.to(ctx.dev), l.to(ctx.dev)) for o, l in sets]
     gx, gy, gs = [t.to(ctx.dev) for t in xs], [t.to(ctx.dev) for t in ys], [t.to(ctx.dev) for t in ss]
     lf = new_loss_function(ctx, allreduce)
+    # the batches are resident in HBM before the first step is enqueued: the steps may be pipelined (the preparation
+    # kernel of a step beside the last kernel of the step before it, Loss_Function.pipelined / P24_F_EARLY_PREP).  The e2e
+    # leg below copies its inputs inside the loop and does not set it.
+    lf.pipelined = not os.environ.get("P24_NO_PIPELINE")
     fused = getattr(lf, "peer_comm", None) is not None
     config = {"workload": f"{wl['cfg']}: batch {B}/GPU at {size}x{size} ({A} anchors), {G} GT/img, 80 classes",
               "per_gpu_batch": B, "global_batch": B * ctx.world, "anchors": A, "gt_per_image": G,
               "label_kind": wl["kind"],
+              "pipelined": bool(lf.pipelined),
               "l2": f"inputs rotate over {n_sets} distinct batches ({n_sets * B * img_bytes / 2**20:.0f} MiB > 126 MiB L2)",
               "sharding": "single GPU" if ctx.world == 1 else
               (f"images sharded over {ctx.world} GPU(s); 28-float all-reduce per step: " +

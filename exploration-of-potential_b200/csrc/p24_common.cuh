@@ -54,11 +54,13 @@ static inline size_t p24_align(size_t x) { return (x + 255) & ~(size_t)255; }
 #define ST_WORDS 8
 
 struct P24Workspace {
-    size_t ticket;      // [8] unsigned: tile-queue head of k_pass, largest num_gt, completion count of k_tail, far-queue entries,
+    size_t ticket;      // [16] unsigned: tile-queue head of k_pass, largest num_gt, completion count of k_tail, far-queue entries,
                         //               window-queue head, number of centre-window pairs of the batch, far-queue head, tiles done
     size_t acc_fix;     // [28] int64   fixed-point loss sums of the batch (zero between calls)
     size_t status;      // [ST_WORDS] int
-    size_t seed_done;   // [B] int      seed items of the image that are complete (zero between calls)
+    // (what k_prep writes exists twice, by step parity: it runs beside the previous step's k_tail)
+    size_t seed_done;   // [2][B] int   seed items of the image that are complete (zero between calls)
+    size_t ngt;         // [2][B] int   num_gt of the image
     size_t ncand;       // [B] int      candidate anchors of the image (zero between calls)
     size_t lcount;      // [B, Lmax] int   entries in the GT's top-10 list (zero between calls)
     size_t gt_rec;      // [B, Lmax, GT_REC] float
@@ -86,22 +88,23 @@ static inline P24Workspace p24_layout(int B, int A, int Lmax) {
     const size_t BL = (size_t)B * (size_t)Lmax;
     const size_t NB = (size_t)B * (size_t)p24_tiles(A);
     // the counters that must be zero between calls come first (p24_workspace_init clears everything)
-    w.ticket = off;     off = p24_align(off + 8 * sizeof(unsigned));
+    w.ticket = off;     off = p24_align(off + 16 * sizeof(unsigned));
     w.acc_fix = off;    off = p24_align(off + 28 * sizeof(long long));
     w.status = off;     off = p24_align(off + ST_WORDS * sizeof(int));
-    w.seed_done = off;  off = p24_align(off + (size_t)B * sizeof(int));
+    w.seed_done = off;  off = p24_align(off + 2 * (size_t)B * sizeof(int));
+    w.ngt = off;        off = p24_align(off + 2 * (size_t)B * sizeof(int));
     w.ncand = off;      off = p24_align(off + (size_t)B * sizeof(int));
     w.rare = off;       off = p24_align(off + (size_t)B * sizeof(int));
     w.lcount = off;     off = p24_align(off + BL * sizeof(int));
-    w.gt_rec = off;     off = p24_align(off + BL * GT_REC * sizeof(float));
-    w.wtab = off;       off = p24_align(off + BL * P24_WT_STRIDE * sizeof(float));
+    w.gt_rec = off;     off = p24_align(off + 2 * BL * GT_REC * sizeof(float));
+    w.wtab = off;       off = p24_align(off + 2 * BL * P24_WT_STRIDE * sizeof(float));
     w.list = off;       off = p24_align(off + BL * P24_LISTCAP * 2 * sizeof(float));
     w.claimg = off;     off = p24_align(off + BL * P24_TOPK * sizeof(int));
     w.kreq = off;       off = p24_align(off + BL * sizeof(int));
     w.ntake = off;      off = p24_align(off + BL * sizeof(int));
     w.cbits = off;      off = p24_align(off + NB * P24_WARPS * sizeof(unsigned));
     w.brute = off;      off = p24_align(off + (size_t)B * 8 * P24_TOPK * sizeof(float));
-    w.wlist = off;      off = p24_align(off + BL * 25 * P24_MAX_LEVELS * 2 * sizeof(int));
+    w.wlist = off;      off = p24_align(off + 2 * BL * 25 * P24_MAX_LEVELS * 2 * sizeof(int));
     w.fq = off;         off = p24_align(off + BL * P24_FQ_PER_GT * 2 * sizeof(int));
     w.total = off;
     return w;

@@ -33,6 +33,9 @@
 #include "p24_host.h"
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 namespace {
 
 struct Level {
@@ -74,6 +77,10 @@ struct Params {
     float2* list;
     unsigned* cbits;
     int2* wlist;
+    int* ngt;      // num_gt per image (workspace copy of this step's parity)
+    int tk_wtot;   // ticket word of this step's centre-window pair count
+    int tk_item;   // ticket word of this step's tile queue
+    int early;     // k_prep works before it waits for the previous grid
     int2* fq;      // the batch's far queue (GT slot, anchor): overflow of the tiles' own far-pair lists
     int fq_cap;
     float* brute;
@@ -110,7 +117,8 @@ __device__ __forceinline__ void tmark(int kern, int row, int slot) {
 #endif
 
 #define TK_ITEM 0   // ticket words
-#define TK_LEFF 1
+#define TK_WTOT1 8  // (second parity of TK_WTOT)
+#define TK_ITEM1 9  // (second parity of TK_ITEM)
 #define TK_TAIL 2
 #define TK_FQ 3     // far queue: entries reserved
 #define TK_WIN 4    // window-chunk queue head
@@ -278,6 +286,14 @@ extern "C" int p24_read_status(void* workspace, int B, int A, int Lmax, int32_t*
 }
 
 namespace {
+// calls made on a workspace so far (host side; the kernels double-buffer by its parity)
+unsigned step_parity(const void* workspace) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, unsigned> count;
+    std::lock_guard<std::mutex> lock(mu);
+    return count[workspace]++;
+}
+
 int simota_impl(const float* outputs, int64_t img_stride, int64_t row_stride, const float* const* h_raw,
                 const int64_t* h_raw_bs, int B, int A,
                                      int num_classes, const float* labels, int64_t lab_img_stride,
@@ -322,14 +338,21 @@ int simota_impl(const float* outputs, int64_t img_stride, int64_t row_stride, co
     p.ticket = (unsigned*)(ws + L.ticket);
     p.acc_fix = (long long*)(ws + L.acc_fix);
     p.status = (int*)(ws + L.status);
-    p.seed_done = (int*)(ws + L.seed_done);
+    // what k_prep writes exists twice: consecutive calls on a workspace alternate (the count is kept per workspace)
+    const size_t BLs = (size_t)B * Lmax;
+    const int par = (int)(step_parity(workspace) & 1u);
+    p.seed_done = (int*)(ws + L.seed_done) + (size_t)par * B;
+    p.ngt = (int*)(ws + L.ngt) + (size_t)par * B;
     p.ncand = (int*)(ws + L.ncand);
     p.lcount = (int*)(ws + L.lcount);
-    p.gt_rec = (float*)(ws + L.gt_rec);
-    p.wtab = (float*)(ws + L.wtab);
+    p.gt_rec = (float*)(ws + L.gt_rec) + (size_t)par * BLs * GT_REC;
+    p.wtab = (float*)(ws + L.wtab) + (size_t)par * BLs * P24_WT_STRIDE;
     p.list = (float2*)(ws + L.list);
     p.cbits = (unsigned*)(ws + L.cbits);
-    p.wlist = (int2*)(ws + L.wlist);
+    p.wlist = (int2*)(ws + L.wlist) + (size_t)par * BLs * 25 * P24_MAX_LEVELS;
+    p.tk_wtot = par ? TK_WTOT1 : TK_WTOT;
+    p.tk_item = par ? TK_ITEM1 : TK_ITEM;
+    p.early = 0;
     p.fq = (int2*)(ws + L.fq);
     p.fq_cap = (int)((size_t)B * Lmax * P24_FQ_PER_GT);
     p.brute = (float*)(ws + L.brute);
@@ -389,6 +412,11 @@ int simota_impl(const float* outputs, int64_t img_stride, int64_t row_stride, co
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prep, PREP_THREADS, dyn_pass);
         if (e != cudaSuccess) return (int)e;
         const bool fused = (long long)pgrid.x * pgrid.y <= (long long)per_sm * n_sm;
+        // early mode (opt-in, P24_F_EARLY_PREP): k_prep works beside the previous step's k_tail.  Not while the stream is
+        // being captured (a replayed graph repeats one parity) and not in the two-launch fallback.
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusActive;
+        p.early = (fused && pdl && cap == cudaStreamCaptureStatusNone && (flags & P24_F_EARLY_PREP)) ? 1 : 0;
         e = launch2(k_prep, pgrid, dim3(PREP_THREADS), dyn_pass, st, pdl, p, fused ? 0 : 1);
         if (e != cudaSuccess) return (int)e;
         if (!fused) {

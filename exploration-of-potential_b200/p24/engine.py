@@ -18,6 +18,7 @@ F_NO_PRUNE = 1   # evaluate every polygon angle sum exactly (self-check of the g
 F_NO_FILTER = 2  # dynamic k from the exact value of every (GT, candidate) pair (self-check of the far-pair filter)
 F_ALL_ROWS = 4   # every label row is a GT (per-image API)
 F_NO_PDL = 8     # plain stream-ordered launches
+F_EARLY_PREP = 16  # back-to-back steps on resident inputs: k_prep runs beside the previous step's last kernel
 
 
 class RawLevels:

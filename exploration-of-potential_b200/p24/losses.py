@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import lib as _lib
-from .engine import Assignment, RawLevels, SimOTAEngine, F_ALL_ROWS, _check_cuda_f32, _stream_ptr
+from .engine import Assignment, RawLevels, SimOTAEngine, F_ALL_ROWS, F_EARLY_PREP, _check_cuda_f32, _stream_ptr
 
 
 def _rows(t: torch.Tensor, width: int, name: str) -> torch.Tensor:
@@ -182,6 +182,11 @@ class Loss_Function(nn.Module):
         # forward (less host work per step); the default hands out fresh tensors like the reference does
         self.reuse_buffers = False
         self._res_cache = {}
+        # pipelined = True: the caller guarantees that the inputs of every forward were complete before the previous
+        # forward was enqueued (loss steps back to back on resident batches): the preparation kernel of a step then runs
+        # beside the last kernel of the step before it (P24_F_EARLY_PREP).  Off by default: a head that writes `outputs`
+        # right before the call is the normal case.
+        self.pipelined = False
 
     def _result_buffers(self, device):
         if self.reuse_buffers:
@@ -217,6 +222,8 @@ class Loss_Function(nn.Module):
         # conv outputs, decoded inside the kernels)
         state = self._state(outputs.device)
         self._engine.reuse_buffers = self.reuse_buffers
+        if self.pipelined:
+            flags |= F_EARLY_PREP
         if self.process_group is None:
             # single GPU: the last CTA of the chain applies the normalisation and re-weighting itself
             result54, weights27 = self._result_buffers(outputs.device)

@@ -42,6 +42,10 @@ extern "C" {
 #define P24_F_NO_FILTER 2u     /* evaluate every pair value exactly (self-check of the top-k filter) */
 #define P24_F_NO_PDL 8u        /* plain stream-ordered launches instead of programmatic dependent launch */
 #define P24_F_ALL_ROWS 4u      /* every label row is a GT (per-image API: the caller passes num_gt rows) */
+#define P24_F_EARLY_PREP 16u   /* the caller guarantees that `labels` and the head output of THIS call were complete before
+                                  the previous call on this workspace and stream was enqueued (back-to-back loss steps on
+                                  resident inputs): k_prep then prepares the step beside the previous step's last kernel and
+                                  waits for it only before it exits.  Without the flag k_prep waits first (always safe). */
 
 int p24_abi_version(void);
 const char* p24_error_string(int code);

@@ -96,3 +96,32 @@ def test_class_bce_sum_does_not_overflow(nc, shift):
     _assert_assignment_equal(asg, o.trace)
     np.testing.assert_allclose(float(res[26]), float(r[3]), rtol=RTOL)
     np.testing.assert_allclose(float(res[0]), float(r[0]), rtol=RTOL)
+
+
+def test_pipelined_steps_give_the_bits_of_plain_steps():
+    """Loss_Function.pipelined (P24_F_EARLY_PREP): the preparation kernel of a step runs beside the last kernel of the
+    step before it, on double-buffered workspace halves.  Eight back-to-back steps over three resident batches (different
+    GT counts, one image without GTs) must reproduce the plain sequence bit for bit, including the stateful re-weighting."""
+    gx, gy, gs = _grids(640)
+    sets = []
+    for i, counts in enumerate([[20] * 6, [3, 0, 50, 7, 1, 12], [33] * 6]):
+        sets.append((synth.make_head_outputs(6, 640, 80, seed=70 + i).to(DEV),
+                     synth.make_labels(6, counts, 50, 640, 80, seed=70 + i, kind="spiky" if i == 1 else "smooth").to(DEV)))
+    plain, piped = Loss_Function(80), Loss_Function(80)
+    piped.pipelined = True
+    want = []
+    for s in range(8):
+        o, l = sets[s % 3]
+        r, _, a = plain.forward_async((gx, gy, gs, o, []), l)
+        want.append((r.clone(), a.fg_mask.clone(), a.matched_gt.clone(), a.dyn_k.clone(), a.num_gt.clone(), a.num_fg.clone()))
+    torch.cuda.synchronize()
+    got = []
+    for s in range(8):   # enqueued back to back, no synchronisation in between
+        o, l = sets[s % 3]
+        r, _, a = piped.forward_async((gx, gy, gs, o, []), l)
+        got.append((r, a.fg_mask, a.matched_gt, a.dyn_k, a.num_gt, a.num_fg))
+    torch.cuda.synchronize()
+    for s in range(8):
+        for x, y in zip(want[s], got[s]):
+            assert torch.equal(x, y), s
+    piped.check_errors()

@@ -39,6 +39,7 @@ for step in range(6):  # several steps: the re-weighting state and the mailbox e
 # back-to-back asynchronous steps: the collect kernels run on the side stream while the next chains are enqueued (the
 # mailbox slot sets and the one-step run-ahead limit are exercised); peer and NCCL must end in the same state
 a_peer, a_nccl = p24_dist.attach(Loss_Function(80), peer=True), p24_dist.attach(Loss_Function(80), peer=False)
+a_peer.pipelined = True   # (the shards are resident before the first step: the steps of the fused path are pipelined)
 outs = [synth.make_head_outputs(B, size, 80, seed=70 + i).to(dev) for i in range(3)]
 labs = [synth.make_labels(B, 11, 50, size, 80, seed=70 + i, kind="smooth").to(dev) for i in range(3)]
 res = {}

@@ -35,6 +35,7 @@ xs, ys, ss = synth.make_grids(wl["size"])
 g = [[t.to(dev) for t in l] for l in (xs, ys, ss)]
 lf = Loss_Function(80)
 lf.reuse_buffers = True
+lf.pipelined = bool(int(os.environ.get("P24_PIPELINED", "1")))
 lib = p24_lib.load()
 for i in range(10):
     lf.forward_async((g[0], g[1], g[2], sets[i % len(sets)][0], []), sets[i % len(sets)][1])

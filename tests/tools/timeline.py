@@ -28,6 +28,7 @@ xs, ys, ss = synth.make_grids(wl["size"])
 g = [[t.to(dev) for t in l] for l in (xs, ys, ss)]
 lf = Loss_Function(80)
 lf.reuse_buffers = True
+lf.pipelined = bool(int(os.environ.get("P24_PIPELINED", "1")))
 lib = p24_lib.load()
 for i in range(6):
     lf.forward_async((g[0], g[1], g[2], sets[i % 3][0], []), sets[i % 3][1])
@@ -60,6 +61,9 @@ k0 = buf[0].astype(np.float64)
 rows0 = np.concatenate([k0[b * 64:b * 64 + (wl["G"] + 1) // 2] for b in range(B)])
 p0 = rows0[:, 0].min()
 print(f"== k_prep: first CTA start {us(p0):.1f} us, last end {us(rows0[:, 7].max()):.1f} us (k_pass past its pdl_wait at 0)")
+_st, _en = np.sort(us(rows0[:, 0])), np.sort(us(rows0[:, 7]))
+print("   CTA work start percentiles (0/25/50/75/100):", " ".join(f"{np.percentile(_st, q):.1f}" for q in (0, 25, 50, 75, 100)))
+print("   CTA work end   percentiles (0/25/50/75/100):", " ".join(f"{np.percentile(_en, q):.1f}" for q in (0, 25, 50, 75, 100)))
 for lab, a, b_ in [("count labels", 0, 1), ("records+pairs", 1, 2), ("image barrier", 2, 3), ("stage records", 3, 4),
                    ("seed points", 4, 5), ("dedupe+rank+sync", 5, 6), ("T + far2", 6, 7), ("CTA total", 0, 7)]:
     stat(lab, rows0[:, b_] - rows0[:, a])
