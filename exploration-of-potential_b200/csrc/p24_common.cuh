@@ -187,6 +187,10 @@ __device__ __forceinline__ unsigned p24_ordered(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+__device__ __forceinline__ float p24_unordered(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
 #define P24_NEG_INF (-INFINITY)
 #define P24_POS_INF (INFINITY)
 #endif  // __CUDACC__

@@ -33,6 +33,9 @@ namespace {
 #define NMS_THREADS 1024
 #define SORT_SMEM_MAX 16384  // candidates of one image sorted in shared memory (128 KB of keys)
 #define NCELL_MAX 2048
+#define SPLIT_GROUPS 128               // most groups of an image that the split sweep handles (one warp per group)
+#define META_WORDS (SPLIT_GROUPS + 4)
+#define OUT_SPLIT 4                    // CTAs per image of k_post_out
 
 struct PostParams {
     const float* pred;
@@ -54,7 +57,9 @@ struct PostParams {
     int* c_cls;      // [B, tiles*256]
     float4* c_rect;  // [B, tiles*256]
     float4* s_rect;  // [B, A]   sorted (and class-shifted) rectangles
-    unsigned long long* g_keys;  // [B, npad]  global sort scratch (only when an image has > SORT_SMEM_MAX candidates)
+    unsigned long long* g_keys;  // [B, npad]  the sorted keys (slot, kept / suppressed bits): sort scratch when an image has more than
+                                 //            SORT_SMEM_MAX candidates, and what k_post_nms hands to k_post_sweep / k_post_out
+    int* g_meta;     // [B, META_WORDS]  k_post_nms -> k_post_sweep: [0] sweeps pending, [1] groups, [2 ..] group starts
     int* s_order;    // [B, A]   sorted boxes grouped by x cell
     int* s_cell;     // [B, A]   x cell of every sorted box
     float4* c_srect; // [B, A]   the sorted rectangles again, in cell order (coalesced reads of a cell)
@@ -82,7 +87,7 @@ __device__ __forceinline__ float raw_pred(const PostParams& p, int b, int a, int
 }
 
 struct PostWorkspace {
-    size_t tcount, c_score, c_conf, c_anchor, c_cls, c_rect, s_rect, g_keys, s_order, s_cell, c_srect, total;
+    size_t tcount, c_score, c_conf, c_anchor, c_cls, c_rect, s_rect, g_keys, g_meta, s_order, s_cell, c_srect, total;
 };
 
 inline int next_pow2(int x) {
@@ -103,7 +108,8 @@ inline PostWorkspace post_layout(int B, int A) {
     w.c_cls = off;    off = p24_align(off + slots * sizeof(int));
     w.c_rect = off;   off = p24_align(off + slots * sizeof(float4));
     w.s_rect = off;   off = p24_align(off + (size_t)B * A * sizeof(float4));
-    w.g_keys = off;   off = p24_align(off + (A > SORT_SMEM_MAX ? (size_t)B * next_pow2(A) * sizeof(unsigned long long) : 0));
+    w.g_keys = off;   off = p24_align(off + (size_t)B * next_pow2(A) * sizeof(unsigned long long));
+    w.g_meta = off;   off = p24_align(off + (size_t)B * META_WORDS * sizeof(int));
     w.s_order = off;  off = p24_align(off + (size_t)B * A * sizeof(int));
     w.s_cell = off;   off = p24_align(off + (size_t)B * A * sizeof(int));
     w.c_srect = off;  off = p24_align(off + (size_t)B * A * sizeof(float4));
@@ -353,6 +359,68 @@ __device__ void bitonic_sort(unsigned long long* keys, int npad) {
     }
 }
 
+// One group of batched NMS, by one warp: the group's boxes in sorted order (their sorted ranks in order[g0 .. g0 + m)), the
+// classic serial sweep "a kept box suppresses the later boxes it overlaps".  Suppressed boxes get bit 31 of their key.
+__device__ __forceinline__ void sweep_group(unsigned long long* keys, const float4* __restrict__ srect,
+                                            const int* __restrict__ order, int g0, int m, float thr) {
+    const int lane = threadIdx.x & 31;
+                    // blocks of 256 boxes, eight per lane in registers: first the kept boxes of the earlier blocks sweep the
+                    // block, then the serial sweep inside it
+                    for (int blk = 0; blk < m; blk += 256) {
+                        const int mb = min(256, m - blk);
+                        float4 rc[8];
+                        int idx[8];
+                        unsigned dead = 0u;
+    #pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const int j = t * 32 + lane;
+                            idx[t] = j < mb ? order[g0 + blk + j] : -1;
+                            rc[t] = j < mb ? srect[idx[t]] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        for (int i = 0; i < blk; ++i) {
+                            const int ii = order[g0 + i];
+                            if ((((volatile unsigned long long*)keys)[ii] >> 31) & 1ull) continue;
+                            const float4 bi = srect[ii];
+    #pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                if (t * 32 < mb && idx[t] >= 0 && !((dead >> t) & 1u)) {
+                                    const float4 bj = rc[t];
+                                    const bool disjoint = bj.x >= bi.z || bi.x >= bj.z || bj.y >= bi.w || bi.y >= bj.w;
+                                    if (!disjoint && iou_over(bi, bj, thr)) dead |= 1u << t;
+                                }
+                            }
+                        }
+    #pragma unroll
+                        for (int s8 = 0; s8 < 8; ++s8) {
+                            if (s8 * 32 < mb) {
+                                const int lim = min(32, mb - s8 * 32);
+                                for (int l = 0; l < lim; ++l) {
+                                    if (__shfl_sync(0xffffffffu, (dead >> s8) & 1u, l)) continue;  // suppressed by a kept box
+                                    float4 bi;
+                                    bi.x = __shfl_sync(0xffffffffu, rc[s8].x, l);
+                                    bi.y = __shfl_sync(0xffffffffu, rc[s8].y, l);
+                                    bi.z = __shfl_sync(0xffffffffu, rc[s8].z, l);
+                                    bi.w = __shfl_sync(0xffffffffu, rc[s8].w, l);
+                                    const int i = s8 * 32 + l;
+    #pragma unroll
+                                    for (int t = s8; t < 8; ++t) {
+                                        const int j = t * 32 + lane;
+                                        if (t * 32 < mb && j > i && j < mb && !((dead >> t) & 1u)) {
+                                            const float4 bj = rc[t];
+                                            const bool disjoint = bj.x >= bi.z || bi.x >= bj.z || bj.y >= bi.w || bi.y >= bj.w;  // IoU = 0
+                                            if (!disjoint && iou_over(bi, bj, thr)) dead |= 1u << t;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+    #pragma unroll
+                        for (int t = 0; t < 8; ++t)
+                            if (idx[t] >= 0 && ((dead >> t) & 1u)) keys[idx[t]] |= (1ull << 31);
+                        __syncwarp();
+                    }
+}
+
 __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     extern __shared__ __align__(16) unsigned long long s_keys[];  // [npad] when the image fits, else unused
     __shared__ int s_prefix[1025];                               // candidates before tile t (tiles <= 1024)
@@ -371,13 +439,21 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     PT(0);
 
     // ---- number of candidates, prefix of the tile counts ----------------------------------------------------------
-    if (tid == 0) {
-        int acc = 0;
-        for (int t = 0; t < p.tiles; ++t) {
-            s_prefix[t] = acc;
-            acc += p.tcount[(long long)b * p.tiles + t];
+    if (warp == 0) {  // exclusive scan of the tile counts (tiles <= 1024)
+        int carry = 0;
+        for (int t0 = 0; t0 < p.tiles; t0 += 32) {
+            const int t = t0 + lane;
+            const int c = t < p.tiles ? p.tcount[(long long)b * p.tiles + t] : 0;
+            int v = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, off);
+                if (lane >= off) v += u;
+            }
+            if (t < p.tiles) s_prefix[t] = carry + v - c;
+            carry += __shfl_sync(0xffffffffu, v, 31);
         }
-        s_prefix[p.tiles] = acc;
+        if (lane == 0) s_prefix[p.tiles] = carry;
     }
     __syncthreads();
     const int n = s_prefix[p.tiles];
@@ -495,7 +571,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     //     in sorted order, eight per lane in registers, the classic serial sweep "kept box i suppresses the later boxes it
     //     overlaps" with the box broadcast by shuffles.
     PT(3);
-    bool done = false;
+    bool done = false, handed = false;
     if (!p.class_agnostic && allfinite && p.nc <= NCELL_MAX / 2 && p.nms_thre >= 0.0f) {
         __shared__ short s_gid[NCELL_MAX / 2];
         __shared__ int s_reach[NCELL_MAX / 2];
@@ -567,14 +643,56 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
         }
         __syncthreads();
         {
+            // A partner of a flagged box f overlaps it: its right / lower edge lies beyond f's left / upper edge, which lies at
+            // most R = max_f (extent of the earlier classes - f's edge) below that extent: partners are the few boxes whose
+            // lower-right corner comes within (Rx, Ry) of their own class's extent.  Flagged x partners, pair by pair.
+            __shared__ int s_part[256];
+            __shared__ int s_npart;
+            __shared__ float s_R[2];
             const int nflag = min(s_nflag, 64);
-            for (int f = 0; f < nflag; ++f) {
-                const int fi = s_flag[f];
-                const int cf = grp[fi];
-                const float4 bf = srect[fi];
+            if (tid == 0) {
+                float rx = 0.0f, ry = 0.0f;
+                for (int f = 0; f < nflag; ++f) {
+                    const int fi = s_flag[f];
+                    const float4 bf = srect[fi];
+                    rx = fmaxf(rx, p24_unordered(s_pm[0][grp[fi]]) - bf.x);
+                    ry = fmaxf(ry, p24_unordered(s_pm[1][grp[fi]]) - bf.y);
+                }
+                s_R[0] = rx * 1.001f + 0.05f;  // (slack: the offset coordinates are ~1e5 with an ulp of ~0.01)
+                s_R[1] = ry * 1.001f + 0.05f;
+                s_npart = 0;
+            }
+            __syncthreads();
+            if (nflag > 0) {
+                const float rx = s_R[0], ry = s_R[1];
                 for (int i = tid; i < n; i += NMS_THREADS) {
                     const int c = grp[i];
-                    if (c < cf && iou_over(srect[i], bf, p.nms_thre)) atomicMin(&s_reach[cf], c);
+                    const float4 r = srect[i];
+                    if (r.z > p24_unordered(hix[c]) - rx && r.w > p24_unordered(hiy[c]) - ry) {
+                        const int at = atomicAdd(&s_npart, 1);
+                        if (at < 256) s_part[at] = i;
+                    }
+                }
+            }
+            __syncthreads();
+            const int npart = s_npart;
+            if (npart <= 256) {
+                for (int q = tid; q < nflag * npart; q += NMS_THREADS) {
+                    const int fi = s_flag[q / npart], i = s_part[q % npart];
+                    const int cf = grp[fi], c = grp[i];
+                    if (c < cf && iou_over(srect[i], srect[fi], p.nms_thre)) atomicMin(&s_reach[cf], c);
+                }
+            } else {  // (many corner boxes: every flagged box against every box)
+                for (int f = 0; f < nflag; ++f) {
+                    const int fi = s_flag[f];
+                    const int cf = grp[fi];
+                    const float4 bf = srect[fi];
+                    for (int i = tid; i < n; i += NMS_THREADS) {
+                        const int c = grp[i];
+                        if (c >= cf) continue;
+                        const float4 r = srect[i];
+                        if (r.z > bf.x && r.w > bf.y && iou_over(r, bf, p.nms_thre)) atomicMin(&s_reach[cf], c);  // (else disjoint)
+                    }
                 }
             }
         }
@@ -659,8 +777,18 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
                 }
                 __syncthreads();
             }
-            // the warps draw the groups from a counter, the largest first (a group's sweep is serial and grows with the
-            // square of its size: the big ones must not come last)
+            if (counting) {
+                // ---- the sweeps run as a grid of their own over all SMs (k_post_sweep, one warp per group) ----------------
+                int* meta = p.g_meta + (long long)b * META_WORDS;
+                for (int g = tid; g <= ng; g += NMS_THREADS) meta[2 + g] = gcnt[g];
+                if (tid == 0) {
+                    meta[0] = 1;
+                    meta[1] = ng;
+                }
+                handed = true;
+            }
+            // (no lists: too many groups) the warps draw the groups from a counter, the largest first (a group's sweep is
+            // serial and grows with the square of its size: the big ones must not come last)
             __shared__ int s_next;
             __syncthreads();
             if (ng <= NCELL_MAX / 2) {
@@ -674,7 +802,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
                     s_reach[rank] = g;
                 }
             }
-            if (tid == 0) s_next = 0;
+            if (tid == 0) s_next = handed ? ng : 0;
             __syncthreads();
             for (;;) {
                 int gi = 0;
@@ -695,61 +823,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
                     }
                     __syncwarp();
                 }
-                // blocks of 256 boxes, eight per lane in registers: first the kept boxes of the earlier blocks sweep the
-                // block, then the serial sweep inside it
-                for (int blk = 0; blk < m; blk += 256) {
-                    const int mb = min(256, m - blk);
-                    float4 rc[8];
-                    int idx[8];
-                    unsigned dead = 0u;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const int j = t * 32 + lane;
-                        idx[t] = j < mb ? order[g0 + blk + j] : -1;
-                        rc[t] = j < mb ? srect[idx[t]] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    for (int i = 0; i < blk; ++i) {
-                        const int ii = order[g0 + i];
-                        if ((((volatile unsigned long long*)keys)[ii] >> 31) & 1ull) continue;
-                        const float4 bi = srect[ii];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            if (t * 32 < mb && idx[t] >= 0 && !((dead >> t) & 1u)) {
-                                const float4 bj = rc[t];
-                                const bool disjoint = bj.x >= bi.z || bi.x >= bj.z || bj.y >= bi.w || bi.y >= bj.w;
-                                if (!disjoint && iou_over(bi, bj, thr)) dead |= 1u << t;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int s8 = 0; s8 < 8; ++s8) {
-                        if (s8 * 32 < mb) {
-                            const int lim = min(32, mb - s8 * 32);
-                            for (int l = 0; l < lim; ++l) {
-                                if (__shfl_sync(0xffffffffu, (dead >> s8) & 1u, l)) continue;  // suppressed by a kept box
-                                float4 bi;
-                                bi.x = __shfl_sync(0xffffffffu, rc[s8].x, l);
-                                bi.y = __shfl_sync(0xffffffffu, rc[s8].y, l);
-                                bi.z = __shfl_sync(0xffffffffu, rc[s8].z, l);
-                                bi.w = __shfl_sync(0xffffffffu, rc[s8].w, l);
-                                const int i = s8 * 32 + l;
-#pragma unroll
-                                for (int t = s8; t < 8; ++t) {
-                                    const int j = t * 32 + lane;
-                                    if (t * 32 < mb && j > i && j < mb && !((dead >> t) & 1u)) {
-                                        const float4 bj = rc[t];
-                                        const bool disjoint = bj.x >= bi.z || bi.x >= bj.z || bj.y >= bi.w || bi.y >= bj.w;  // IoU = 0
-                                        if (!disjoint && iou_over(bi, bj, thr)) dead |= 1u << t;
-                                    }
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < 8; ++t)
-                        if (idx[t] >= 0 && ((dead >> t) & 1u)) keys[idx[t]] |= (1ull << 31);
-                    __syncwarp();
-                }
+                sweep_group(keys, srect, order, g0, m, thr);
             }
         }
         __syncthreads();
@@ -913,15 +987,63 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
 #ifdef P24_TIMING
     path = done ? 1 : 2;
 #endif
+    // ---- hand over: the keys (slot + kept / suppressed bits) in global memory, the sweeps pending or not -----------------
+    if (!handed && tid == 0) p.g_meta[(long long)b * META_WORDS] = 0;
+    if (in_smem) {
+        unsigned long long* gk = p.g_keys + (long long)b * p.npad_global;
+        for (int i = tid; i < n; i += NMS_THREADS) gk[i] = keys[i];
+    }
+#ifdef P24_TIMING
+    PT(6);
+    if (tid == 0 && (b == 0 || b == 7))
+        printf("ng=%d maxm=%d nms b=%d n=%d path=%d handed=%d keys %.1f sort %.1f rects %.1f groups %.1f nms+lists %.1f store %.1f us\n",
+               dbg_ng, dbg_maxm, b, n, path, (int)handed, (tm[1] - tm[0]) * 1e-3, (tm[2] - tm[1]) * 1e-3, (tm[3] - tm[2]) * 1e-3,
+               (tm[4] - tm[3]) * 1e-3, (tm[5] - tm[4]) * 1e-3, (tm[6] - tm[5]) * 1e-3);
+#endif
+}
+
+// k_post_sweep: the group sweeps of batched NMS as a grid over all SMs: one warp per group (ceil(groups / 8) x B CTAs)
+__global__ void __launch_bounds__(256) k_post_sweep(PostParams p) {
+    const int b = blockIdx.y, warp = threadIdx.x >> 5;
+    const int* meta = p.g_meta + (long long)b * META_WORDS;
+    if (p.cand_count[b] == 0 || meta[0] != 1) return;
+    const int g = blockIdx.x * 8 + warp;
+    if (g >= meta[1]) return;
+    const int g0 = meta[2 + g], m = meta[3 + g] - g0;
+    if (m <= 0) return;
+    sweep_group(p.g_keys + (long long)b * p.npad_global, p.s_rect + (long long)b * p.A, p.s_order + (long long)b * p.A, g0, m,
+                p.nms_thre);
+}
+
+// k_post_out: OUT_SPLIT CTAs per image: the kept boxes of a quarter of the sorted ranks -> output rows in sorted order
+__global__ void __launch_bounds__(NMS_THREADS) k_post_out(PostParams p) {
+    __shared__ float s_red[32];
+    __shared__ int s_cnt[32];
+    const int b = blockIdx.y, q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.cand_count[b];
+    const unsigned long long* keys = p.g_keys + (long long)b * p.npad_global;
+    const long long slot0 = (long long)b * p.tiles * POST_THREADS;
+    const int chunk = (((n + OUT_SPLIT - 1) / OUT_SPLIT) + NMS_THREADS - 1) / NMS_THREADS * NMS_THREADS;
+    const int r0 = min(n, q * chunk), r1 = min(n, r0 + chunk);
+    // kept boxes before my range
+    int before0 = 0;
+    for (int i = tid; i < r0; i += NMS_THREADS) before0 += ((keys[i] >> 31) & 1ull) ? 0 : 1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) before0 += __shfl_xor_sync(0xffffffffu, before0, off);
+    if (lane == 0) s_cnt[warp] = before0;
+    __syncthreads();
+    before0 = 0;
+    for (int w = 0; w < NMS_THREADS / 32; ++w) before0 += s_cnt[w];
+    __syncthreads();
     // ---- output rows of the survivors in sorted order ------------------------------------------------------------
     // ordered compaction over i = 0..n-1
     __shared__ int s_base;
-    if (tid == 0) s_base = 0;
+    if (tid == 0) s_base = before0;
     __syncthreads();
     int* klist = p.s_order + (long long)b * p.A;  // sorted rank of the k-th kept box (the group lists are no longer needed)
-    for (int i0 = 0; i0 < n; i0 += NMS_THREADS) {
+    for (int i0 = r0; i0 < r1; i0 += NMS_THREADS) {
         const int i = i0 + tid;
-        const bool keep = i < n && !((keys[i] >> 31) & 1ull);
+        const bool keep = i < r1 && !((keys[i] >> 31) & 1ull);
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_red[warp] = __int_as_float(__popc(bal));
         __syncthreads();
@@ -936,7 +1058,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
     }
     // rows: one warp per kept box, the 27 leading floats of its prediction row in one coalesced read
     const int nkept = s_base;
-    for (int k0 = warp * 32; k0 < nkept; k0 += NMS_THREADS) {
+    for (int k0 = before0 + warp * 32; k0 < nkept; k0 += NMS_THREADS) {
         // the lanes fetch what 32 rows need (rank -> slot -> anchor, confidence, class), then the warp copies the rows,
         // four in flight
         const int kk = k0 + lane;
@@ -970,15 +1092,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
                 if (r0 + q < cnt && lane < 29) p.det_rows[((long long)b * p.A + k0 + r0 + q) * 29 + lane] = v[q];
         }
     }
-    if (tid == 0) p.det_count[b] = s_base;
-#ifdef P24_TIMING
-    PT(6);
-    if (tid == 0 && (b == 0 || b == 7))
-        printf("ng=%d maxm=%d "
-               "nms b=%d n=%d path=%d keys %.1f sort %.1f rects %.1f groups %.1f nms %.1f out %.1f us\n", dbg_ng, dbg_maxm, b, n, path,
-               (tm[1] - tm[0]) * 1e-3, (tm[2] - tm[1]) * 1e-3, (tm[3] - tm[2]) * 1e-3, (tm[4] - tm[3]) * 1e-3,
-               (tm[5] - tm[4]) * 1e-3, (tm[6] - tm[5]) * 1e-3);
-#endif
+    if (tid == 0 && q == OUT_SPLIT - 1) p.det_count[b] = s_base;
 }
 
 }  // namespace
@@ -1046,6 +1160,7 @@ int post_impl(const float* prediction, int64_t img_stride, int64_t row_stride, c
     p.c_rect = (float4*)(ws + L.c_rect);
     p.s_rect = (float4*)(ws + L.s_rect);
     p.g_keys = (unsigned long long*)(ws + L.g_keys);
+    p.g_meta = (int*)(ws + L.g_meta);
     p.s_order = (int*)(ws + L.s_order);
     p.s_cell = (int*)(ws + L.s_cell);
     p.c_srect = (float4*)(ws + L.c_srect);
@@ -1062,7 +1177,12 @@ int post_impl(const float* prediction, int64_t img_stride, int64_t row_stride, c
     if (prediction) k_post_filter<<<dim3(tiles, B), POST_THREADS, smem_filter, st>>>(p);
     else k_post_filter_raw<<<dim3(tiles, B), POST_THREADS, 0, st>>>(p);
     p24::prof_mark(5, st);
-    k_post_nms<<<B, NMS_THREADS, smem_nms, st>>>(p);
+    k_post_nms<<<B, NMS_THREADS, smem_nms, st>>>(p);  // sort, groups, lists (+ the NMS itself on the other paths)
+    {
+        const int gmax = num_classes < SPLIT_GROUPS ? num_classes : SPLIT_GROUPS;
+        if (!class_agnostic) k_post_sweep<<<dim3((gmax + 7) / 8, B), 256, 0, st>>>(p);
+        k_post_out<<<dim3(OUT_SPLIT, B), NMS_THREADS, 0, st>>>(p);
+    }
     p24::prof_mark(6, st);
     return (int)cudaGetLastError();
 }
