@@ -401,6 +401,9 @@ def bench_head_fusion(ctx, steps, warmup):
     out = {}
     for mode in ("fused", "unfused"):
         lf = new_loss_function(ctx, "peer")
+        # (fused: the raw batches are resident, the steps may be pipelined like the headline loop; unfused: torch kernels
+        # write the decoded buffer between the steps, so they may not)
+        lf.pipelined = mode == "fused" and not os.environ.get("P24_NO_PIPELINE")
 
         def step(i):
             r, o, c = raws[i % n_sets]
