@@ -6,26 +6,33 @@
 //   Loss_Function.dynamic_k_matching                                 models/losses.py:444-494
 //   the loss sums and re-weighting of Loss_Function.forward          models/losses.py:246-345
 //
-// Kernel chain (caller's stream, no host synchronisation, programmatic dependent launch between the stages):
-//   k_prep   one CTA per image: nlabel (losses.py:190) and the per-GT records (ray lengths, inscribed / reject radii)
+// Kernel chain (caller's stream, no host synchronisation, programmatic dependent launch between the stages; the device
+// code is p24_simota_kernels.inc, compiled twice: decoded rows / raw per-level head planes):
+//   k_prep   two GTs per CTA: nlabel (losses.py:190), the per-GT records (ray lengths, inscribed / reject radii), the
+//            GT's centre-window pairs (appended to the batch's list), a per-image barrier, then the seeds: a handful of
+//            anchors that are certainly candidates (polygon tips, centre windows and inscribed discs of the farthest
+//            other GTs) are evaluated; the 10th best value T is a certified lower bound of the GT's 10th largest pair
+//            value, and far2 the squared centre distance below which no prediction whatsoever can reach T (the bound H*
+//            depends on the GT and the distance only).  What it writes is double-buffered by step parity: with
+//            P24_F_EARLY_PREP it works beside the previous step's k_tail.
 //   k_pass   persistent CTAs drawing work items from ticket counters:
-//            - seed items, one per GT: a handful of anchors that are certainly candidates (centre windows, inscribed
-//              discs and polygon tips of the farthest other GTs) are evaluated; the 10th best value T is a certified
-//              lower bound of the GT's 10th largest pair value, and far2 the squared centre distance below which no
-//              prediction whatsoever can reach T (the bound H* depends on the GT and the distance only);
 //            - anchor tiles (256 anchors): THE pass over the head output (cp.async reads of the 27 geometry channels
-//              of every row).  Candidate mask (polygon test OR centre window) with geometric pruning and an atan2-free
-//              angle test; for the few (GT, candidate) pairs beyond far2 the exact pair value, appended to the GT's
-//              top-10 list when it reaches T; sum BCEWithLogits(obj, 0); outputs initialised to background;
-//            - centre-window items, one per (GT, level): polygon test, exact pair value and SimOTA cost of the <= 25
-//              anchors that can pass the centre-window test -> the GT's window cost table
-//   k_tail   one CTA per image: dynamic k = clamp(int(sum of the 10 largest list values), 1) per GT (exact: the list
-//            holds every candidate value >= T), the k smallest costs of the window table -> claims in shared memory,
-//            conflict resolution (argmin over all GTs), fg_mask / matched_gt / pred_iou, the loss terms of the
-//            foreground anchors; the last CTA reduces the batch sums and applies the normalisation and the stateful
-//            re-weighting (losses.py:280-345), or hands the sums to the fused peer all-reduce (k_fin)
-//   k_fin    (several GPUs) one warp: waits for the peers' sums in the mailbox, adds them in rank order, finalizes.
-//            It overlaps the next step's k_prep / k_pass, which do not depend on the global sums.
+//              of every row, or coalesced planar loads + decode).  Candidate mask (polygon test OR centre window) with
+//              geometric pruning and an atan2-free angle test; for the few (GT, candidate) pairs beyond far2 a cheap
+//              closed-form upper bound of the pair value, appended to the GT's top-10 list when it reaches T (overflow
+//              of a tile's own work list goes to a batch-wide far queue); sum BCEWithLogits(obj, 0); outputs
+//              initialised to background;
+//            - window chunks (32 centre-window pairs): polygon test, exact pair value and SimOTA cost -> the GT's
+//              window cost table;
+//            - far-queue chunks (256 queued pairs), once every tile is done
+//   k_tail   a cluster of 8 CTAs per image: dynamic k = clamp(int(sum of the 10 largest pair values), 1) per GT from
+//            the bracket of the list's bounds (exact evaluation of the survivors only when the floors differ), the k
+//            smallest costs of the window table -> claims, conflict resolution (argmin over all GTs), fg_mask /
+//            matched_gt / pred_iou, the loss terms of the foreground anchors; the batch's last CTA reduces the sums and
+//            applies the normalisation and the stateful re-weighting (losses.py:280-345), or publishes the sums to the
+//            peers' mailboxes (several GPUs)
+//   k_fin    (several GPUs) one warp on a side stream: waits for all ranks' sums in its mailbox, adds them in rank
+//            order, finalizes.  It overlaps the next step's k_prep / k_pass, which do not depend on the global sums.
 //
 // Compile with -fmad=false: the discrete decisions hang on fp32 thresholds evaluated in the
 // reference's operation order; bounds and fast paths use explicit fmaf.
