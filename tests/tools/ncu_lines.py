@@ -1,5 +1,5 @@
 """Join an ncu SASS source page with nvdisasm line info -> per-source-line instruction / stall-sample shares.
-Usage: python tests/tools/ncu_lines.py <report.ncu-rep> <kernel-regex> [top_n]   (run in the build container)"""
+Usage: python tests/tools/ncu_lines.py <report.ncu-rep> <kernel-regex> [top_n] [mangled-name substring]   (build container)"""
 import csv
 import io
 import os
@@ -41,6 +41,7 @@ def disasm_lines(kernel):
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    dis = sys.argv[4] if len(sys.argv) > 4 else kernel   # substring of the MANGLED name (rows6k_pass / rawlv6k_pass)
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kernel}"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
@@ -55,7 +56,7 @@ def main():
             inst.append((int(r[ci]), int(r[cs]), r[1]))
         except ValueError:
             break
-    lines = disasm_lines(kernel)
+    lines = disasm_lines(dis)
     print(f"ncu instructions: {len(inst)}  nvdisasm instructions: {len(lines)}")
     n = min(len(inst), len(lines))
     agg = {}
