@@ -35,6 +35,26 @@ def spiral_coefficients(device="cpu"):
     return _COEF[key]
 
 
+def polar_coefficients(device="cpu"):
+    """cos(theta_k), sin(theta_k), theta_k = k * 15 degrees: the decode the reference DRAWS with (``show_24p.py:326,
+    346-348``) and the 24-point representation means; fp32 torch ops on the given device, cached like the spiral ones."""
+    key = "polar:" + str(torch.device(device))
+    if key not in _COEF:
+        theta = torch.tensor(15 * np.pi / 180, device=device)
+        th = torch.arange(24, device=device) * theta
+        _COEF[key] = (torch.cos(th).cpu().contiguous(), torch.sin(th).cpu().contiguous())
+    return _COEF[key]
+
+
+def decode_polygons(rows, device=None):
+    """Vertices ``[n, 24, 2]`` of detection rows ``[n, >= 26]`` (``[cx, cy, r0..r23, ...]``): ``cx + r_k cos(theta_k)``,
+    ``cy + r_k sin(theta_k)`` -- the drawing-side decode of ``show_24p.py:344-348`` without its integer truncation."""
+    dev = rows.device if device is None else device
+    cx, cy = polar_coefficients(dev)
+    cx, cy = cx.to(rows.device), cy.to(rows.device)
+    return torch.stack((rows[:, 2:26] * cx + rows[:, 0:1], rows[:, 2:26] * cy + rows[:, 1:2]), dim=2)
+
+
 def _workspace(key, nbytes, device):
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes + 256 or buf.device != device:
@@ -91,17 +111,26 @@ def postprocess_raw(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, class
     return cand, cnt, rows, keep, rects
 
 
-def postprocess(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, class_agnostic=False):
+def postprocess(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, class_agnostic=False, decode="spiral"):
     """``utils.boxes.postprocess``: list of B entries, ``Tensor[n_i, 29]`` (rows ``[cx, cy, r0..r23, obj, class_conf,
     class_pred]`` in NMS order) or ``None``.  For B >= 2 the reference itself raises (boxes.py:64-65); this returns
-    the per-image result for each image."""
+    the per-image result for each image.
+
+    ``decode="spiral"`` (default) is the reference's rectangle: points ``r_k * theta_k cos(theta_k)`` (boxes.py:32-33, a
+    known defect kept for parity).  ``decode="polar"`` is the OPT-IN corrected variant (it changes the results): the
+    rectangle of the true polygon ``r_k cos(theta_k), r_k sin(theta_k)`` the reference draws (show_24p.py:346-348)."""
     from .engine import RawLevels
     if not isinstance(prediction, RawLevels):
         if prediction.shape[0] == 0:
             return []
         if prediction.shape[1] == 0:
             return [None for _ in range(len(prediction))]
-    _, cnt, rows, _, _ = postprocess_raw(prediction, num_classes, conf_thre, nms_thre, class_agnostic)
+    if decode not in ("spiral", "polar"):
+        raise ValueError("decode must be 'spiral' (the reference) or 'polar' (true polygon rectangle)")
+    coef = None
+    if decode == "polar":
+        coef = polar_coefficients(prediction.device)
+    _, cnt, rows, _, _ = postprocess_raw(prediction, num_classes, conf_thre, nms_thre, class_agnostic, coef=coef)
     counts = cnt.tolist()  # the one host read (the reference returns a Python list)
     return [rows[i, :n].clone() if n else None for i, n in enumerate(counts)]
 

@@ -145,3 +145,24 @@ def test_config4_full_batch64_vs_oracle_on_gpu(conf, nms, agnostic):
         assert torch.equal(res[i], want), f"image {i}: rows / keep order differ"
         assert torch.equal(keep[i, :int(cnt[i])].long(), dbg["cand"][dbg["keep"]])
     assert skipped <= 2
+
+
+def test_opt_in_polar_decode_vs_oracle_and_drawn_polygons():
+    """decode="polar" (opt-in: it changes the results): rectangles of the true polygon
+    r_k (cos, sin)(theta_k) -- the decode the reference draws with (show_24p.py:346-348) -- through the same kernels; rows
+    and order against the oracle run with those coefficients, and the drawn vertices stay inside the NMS rectangle."""
+    p = synth.make_postprocess_input(4, 640, 80, seed=12).to(DEV)
+    got = p24_boxes.postprocess(p, 80, 0.25, 0.45, False, decode="polar")
+    ref = p24_boxes.postprocess(p, 80, 0.25, 0.45, False)
+    differs = 0
+    for i in range(4):
+        want = orc.postprocess_image(p[i], 80, 0.25, 0.45, False, polar=True)
+        assert (got[i] is None) == (want is None)
+        if want is not None:
+            assert torch.equal(got[i], want), f"image {i}"
+            poly = p24_boxes.decode_polygons(got[i])
+            assert poly.shape == (got[i].shape[0], 24, 2)
+            differs += int(ref[i] is None or ref[i].shape != got[i].shape or not torch.equal(ref[i], got[i]))
+    assert differs > 0   # (the corrected decode is a different detector output: that is why it is opt-in)
+    with pytest.raises(ValueError):
+        p24_boxes.postprocess(p, 80, decode="polygon")
