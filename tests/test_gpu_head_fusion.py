@@ -157,3 +157,22 @@ def test_raw_levels_postprocess_vs_oracle_decode(conf, nms, agnostic):
                 assert torch.equal(got, want), f"image {i}"
                 nonempty += 1
     assert nonempty > 0
+
+
+@pytest.mark.parametrize("nc", [1, 5, 81])
+def test_raw_levels_other_class_counts(nc):
+    """Class counts other than 80 through both raw entries (81 = the largest the training entry stages: 27 + nc <= 108)."""
+    from p24 import boxes as p24_boxes
+    from p24 import head as p24_head
+    lab = synth.make_labels(2, [6, 3], 8, 256, nc, seed=11, kind="smooth")
+    _both(2, 256, nc, lab, seed=11)
+    reg, obj, cls = _levels(2, 256, nc, 12)
+    for t in obj + cls:
+        t += 4.0
+    pred = orc.head_decode_infer(reg, obj, cls, list(synth.STRIDES))
+    fused = p24_boxes.postprocess(p24_head.infer_outputs(reg, obj, cls, synth.STRIDES), nc, 0.2, 0.5, False)
+    for i in range(2):
+        want = orc.postprocess_image(pred[i], nc, 0.2, 0.5, False)
+        assert (fused[i] is None) == (want is None)
+        if want is not None:
+            assert torch.equal(fused[i], want)
