@@ -7,9 +7,12 @@ A step = one pass of the hot path (fused SimOTA assignment + loss sums + re-weig
 ``Loss_Function.forward``) over one batch of synthetic head outputs.  Headline workload = BASELINE.json configs[1]:
 batch 20 per GPU at 640x640 (8400 anchors), 20 GT/img, 80 classes, smooth labels.
 
-  value         images/s, inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks
+  value         images/s, inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks; the steps are
+                pipelined (``Loss_Function.pipelined``: legal because the batches are resident before the loop starts;
+                ``config.pipelined``, P24_NO_PIPELINE=1 switches it off)
   e2e           the same metric through the public ``Loss_Function.forward`` with HOST (pinned) inputs:
-                H2D of the head output + labels and the D2H read of the loss inside the timed region
+                H2D of the head output + labels (prefetched on a copy stream while the previous step computes) and the
+                D2H read of the loss inside the timed region
   roofline      the dominant kernel's algorithmic bytes / its live CUDA-event duration vs MEASURED_PEAKS.json
   cpu_baseline  the reference's own CPU code (oracle/_ref, kind "reference"; else the oracle port) on a bounded sample
 
@@ -19,6 +22,8 @@ line, each with its own value / roofline / e2e / cpu_baseline:
   "crowded"      configs[2]: batch 20, 100 GT/img
   "hires"        configs[4]: 1280x1280 (33600 anchors), GLOBAL batch 160 sharded over the GPUs (strong scaling)
   "postprocess"  configs[3]: batch 64 per GPU through utils.boxes.postprocess at the three settings of SURVEY.md 8(d)
+  "train_raw"    configs[1] fed with the head's RAW conv outputs (decode fused into the kernels) vs torch decode + loss
+  "post_raw"     configs[3] fed with the head's RAW conv outputs (sigmoid + decode fused) vs torch decode + postprocess
 
 Multi-GPU (torchrun, one rank per GPU): images shard by rank (weak scaling, 20 images per GPU for the headline); the
 only exchange is the SUM all-reduce of the 28 loss sums, fused into the kernel chain over NVLink peer memory (NCCL +

@@ -271,7 +271,8 @@ class SimOTAEngine:
 
     def read_status(self):
         """Sticky status words of every workspace this engine has used (one small D2H copy + stream sync each):
-        list of (key, [err_bits, n_brute, n_spill, list_max, exchange_wait_cycles, 0, 0, 0])."""
+        list of (key, [err_bits, n_brute, n_spill, list_max, exchange_wait_cycles, list_sum, gts, n_exact]); the
+        counters restart with every read, the error bits are sticky."""
         lib = _lib.load()
         out = []
         for key, buf in self._bufs.items():
