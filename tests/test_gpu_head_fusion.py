@@ -176,3 +176,21 @@ def test_raw_levels_other_class_counts(nc):
         assert (fused[i] is None) == (want is None)
         if want is not None:
             assert torch.equal(fused[i], want)
+
+
+def test_raw_levels_postprocess_odd_level_sizes():
+    """96 x 96 input: level sizes 144 / 36 / 9 (odd, not a multiple of the warp or of 4): tiles straddle two levels and
+    the last tile is partial; same result as the decoded path."""
+    from p24 import boxes as p24_boxes
+    from p24 import head as p24_head
+    reg, obj, cls = _levels(3, 96, 80, 44)
+    for t in obj + cls:
+        t += 4.5
+    pred = orc.head_decode_infer(reg, obj, cls, list(synth.STRIDES))
+    for conf, nms, ag in [(0.25, 0.45, False), (0.01, 0.65, False)]:
+        fused = p24_boxes.postprocess(p24_head.infer_outputs(reg, obj, cls, synth.STRIDES), 80, conf, nms, ag)
+        for i in range(3):
+            want = orc.postprocess_image(pred[i], 80, conf, nms, ag)
+            assert (fused[i] is None) == (want is None)
+            if want is not None:
+                assert torch.equal(fused[i], want)
