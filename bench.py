@@ -310,6 +310,24 @@ def bench_train(ctx, name, steps, warmup, allreduce, want_e2e=True, want_cpu=Tru
     value = B * ctx.world / (ms_step * 1e-3)
     lf.check_errors()
     loss_check = float(res[0][0])
+    # the same loop without the pipelining promise (what a training loop sees when the head writes `outputs` right before
+    # the loss): reported beside the headline, never as the headline
+    plain = None
+    if lf.pipelined:
+        lf.pipelined = False
+        for i in range(3):
+            step(i)
+        barrier(ctx)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(steps):
+            step(i)
+        lf.wait_results()
+        p1.record()
+        barrier(ctx)
+        ms_plain = max_over_ranks(ctx, p0.elapsed_time(p1)) / steps
+        plain = {"ms_per_step": ms_plain, "value": B * ctx.world / (ms_plain * 1e-3)}
+        lf.pipelined = True
 
     # ---- per-kernel durations (second pass over the same steps, CUDA events recorded inside the C call on the
     # launching stream, plain stream order) -> roofline of the dominant kernel -------------------------------------
@@ -400,7 +418,7 @@ def bench_train(ctx, name, steps, warmup, allreduce, want_e2e=True, want_cpu=Tru
             "host_enqueue_ms_per_step": round(t_host, 4),
             "per_rank_ms": {"columns": TRAIN_STAGES + ["step", "host_enqueue", "exchange_wait_us"],
                             "rows": [[round(v, 4) for v in r] for r in per_rank]},
-            "slow_path": stats, "loss_check": loss_check, "allreduce_check": check}
+            "slow_path": stats, "loss_check": loss_check, "allreduce_check": check, "unpipelined": plain}
 
 
 def bench_head_fusion(ctx, steps, warmup):
@@ -717,7 +735,7 @@ def main():
                     "config": h["config"], "clocks": clocks, "e2e": h["e2e"], "gpu_launches": h["gpu_launches"],
                     "roofline": h["roofline"], "cpu_baseline": h["cpu_baseline"],
                     "host_enqueue_ms_per_step": h["host_enqueue_ms_per_step"], "per_rank_ms": h["per_rank_ms"],
-                    "slow_path": h["slow_path"], "loss_check": h["loss_check"],
+                    "slow_path": h["slow_path"], "loss_check": h["loss_check"], "unpipelined": h["unpipelined"],
                     "allreduce_check": h["allreduce_check"]}
         else:
             line = {"metric": METRIC, "n_gpus": world, "warmup": args.warmup, "clocks": clocks}

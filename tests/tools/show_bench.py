@@ -14,6 +14,7 @@ if "value" in d:
     print("  clocks:", d.get("clocks"), " launches:", d.get("gpu_launches"), " host_enqueue_ms:", d.get("host_enqueue_ms_per_step"))
     print("  slow_path:", d.get("slow_path"), " allreduce_check:", d.get("allreduce_check"))
     print("  per_rank_ms:", d.get("per_rank_ms"))
+    print("  unpipelined:", d.get("unpipelined"))
 for k in ("train_spiky", "crowded", "hires"):
     if k in d:
         v = d[k]
