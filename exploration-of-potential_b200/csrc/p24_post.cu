@@ -948,11 +948,15 @@ __global__ void __launch_bounds__(NMS_THREADS) k_post_nms(PostParams p) {
             const int cn = s_cn;
             const int cend = s_last;  // everything before cend is decided after this round
             if (cn == 0) break;
-            if (tid < 64) s_mask[tid] = 0ull;
-            __syncthreads();
-            for (int q = tid; q < cn * cn; q += NMS_THREADS) {
-                const int i = q / cn, j = q - i * cn;
-                if (j > i && iou_over(srect[s_idx[i]], srect[s_idx[j]], p.nms_thre)) atomicOr(&s_mask[i], 1ull << j);
+            // row i of the 64 x 64 overlap matrix by one warp: two ballots, no atomics (64-bit shared-memory atomics are
+            // compare-and-swap loops)
+            for (int i = warp; i < cn; i += NMS_THREADS / 32) {
+                const float4 bi = srect[s_idx[i]];
+                const int j0 = lane, j1 = lane + 32;
+                const bool t0 = j0 > i && j0 < cn && iou_over(bi, srect[s_idx[j0]], p.nms_thre);
+                const bool t1 = j1 > i && j1 < cn && iou_over(bi, srect[s_idx[j1]], p.nms_thre);
+                const unsigned lo = __ballot_sync(0xffffffffu, t0), hi = __ballot_sync(0xffffffffu, t1);
+                if (lane == 0) s_mask[i] = (unsigned long long)lo | ((unsigned long long)hi << 32);
             }
             __syncthreads();
             if (tid == 0) {
