@@ -103,3 +103,41 @@ def test_label_packing_bit_equal():
         _, want = TT(max_labels=max_labels)(img, t.copy(), [640, 640])
         got = orc.pack_labels(t, (h, w), (640, 640), max_labels)
         assert want.dtype == got.dtype and np.array_equal(want, got)
+
+
+def test_staged_reference_tree_is_the_unmodified_reference(tmp_path, monkeypatch):
+    """oracle/make_ref.py (the recipe behind bench.py's `kind: "reference"` CPU arm): the staged files are byte-identical
+    to the reference's, the manifest says so, and the tree loaded through oracle/ref_runtime.py gives the oracle's bits."""
+    import hashlib
+    import json
+    import os
+    import subprocess
+    import sys
+    from oracle import make_ref
+    monkeypatch.setattr(make_ref, "DEST", str(tmp_path / "yolox_24p"))
+    assert make_ref.make("/root/reference")
+    man = json.load(open(tmp_path / "yolox_24p" / "MANIFEST.json"))
+    for f in make_ref.FILES:
+        a = open(tmp_path / "yolox_24p" / f, "rb").read()
+        b = open(os.path.join("/root/reference/yolox_24p", f), "rb").read()
+        assert a == b and hashlib.sha256(a).hexdigest() == man["sha256"][f]
+    # load it in a fresh interpreter (this one already holds the reference's top-level `models` / `utils` modules)
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'exploration-of-potential_b200')!r})\n"
+        "from oracle import ref_runtime, p24_oracle as orc\n"
+        "from p24 import synth\n"
+        f"models, utils = ref_runtime.load({str(tmp_path / 'yolox_24p')!r})\n"
+        "out = synth.make_head_outputs(1, 160, 80, seed=2); lab = synth.make_labels(1, [4], 6, 160, 80, seed=2, kind='smooth')\n"
+        "xs, ys, ss = synth.make_grids(160)\n"
+        "with ref_runtime.cuda0_shim(torch.device('cpu')):\n"
+        "    r = models.Loss_Function(80).forward((xs, ys, ss, out.clone(), []), lab)\n"
+        "o = orc.LossOracle(80).forward((xs, ys, ss, out.clone(), []), lab)\n"
+        "assert all(torch.equal(r[i], o[i]) for i in range(4))\n"
+        "p = synth.make_postprocess_input(1, 160, 80, seed=4)\n"
+        "a, b = utils.postprocess(p.clone(), 80, 0.01, 0.5, False)[0], orc.postprocess(p.clone(), 80, 0.01, 0.5, False)[0]\n"
+        "assert (a is None) == (b is None) and (a is None or torch.equal(a, b))\n"
+        "print('STAGED_OK')\n")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "STAGED_OK" in res.stdout, res.stderr[-2000:]
