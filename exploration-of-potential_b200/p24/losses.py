@@ -262,7 +262,7 @@ class Loss_Function(nn.Module):
         for key, st in self._engine.read_status():
             if st[0]:
                 raise _lib.P24Error(f"p24 kernels reported error bits {st[0]:#x} on workspace {key} "
-                                    "(1: window list overflow, 4: peer time-out in the fused all-reduce)")
+                                    "(P24_ERR_* of include/p24.h: 1 window list overflow, 4 peer time-out)")
 
     def read_status(self):
         """One read of the kernels' status words (they restart with every read): the rare-path counters since the
@@ -274,7 +274,7 @@ class Loss_Function(nn.Module):
         for key, s in st:
             if s[0]:
                 raise _lib.P24Error(f"p24 kernels reported error bits {s[0]:#x} on workspace {key} "
-                                    "(1: window list overflow, 4: peer time-out in the fused all-reduce)")
+                                    "(P24_ERR_* of include/p24.h: 1 window list overflow, 4 peer time-out)")
         st = [s for _, s in st]
         gts = sum(s[6] for s in st)
         return {"brute_force_gts": sum(s[1] for s in st), "exact_gts": sum(s[7] for s in st),

@@ -240,12 +240,15 @@ int p24_postprocess_raw(const float* const* h_raw, const int64_t* h_raw_batch_st
 
 /* Status of a workspace, read back to the HOST (one small device-to-host copy + a synchronisation of `stream`):
  *   h_status8[0]  error bits (P24_ERR_*), sticky; 0 = none.  The reference raises on its failures (losses.py:81-82); the
- *                 Python host side raises P24Error when a bit is set
+ *                 Python host side raises P24Error when a bit is set.  (Channel and bit values are part of the ABI; the
+ *                 kernels of this version have no failure left to report: the window-pair list is sized for the worst case
+ *                 and the collect kernel of the fused all-reduce waits without a time-out.)
  *   counters since the previous read (they restart with every read):
  *   h_status8[1]  GTs whose dynamic k took the brute-force path
  *   h_status8[2]  GTs that spilled into the penalised regime
  *   h_status8[3]  longest top-10 candidate list seen
- *   h_status8[4]  clock cycles the last fused all-reduce waited for its peers (nranks > 1)
+ *   h_status8[4]  clock cycles between the first and the last rank's contribution to the last fused all-reduce
+ *                 arriving at this rank (nranks > 1)
  *   h_status8[5]  list entries seen, over h_status8[6] GTs
  *   h_status8[7]  GTs whose dynamic k needed exact pair values (the bracket of the bounds straddled an integer) */
 #define P24_ERR_WINDOW_OVERFLOW 1
